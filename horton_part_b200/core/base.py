@@ -1,0 +1,274 @@
+"""``Part`` / ``WPart``: the class API the accelerated hot path sits behind.
+
+Same constructor arguments, properties, cache keys and ``@just_once`` semantics as the reference
+(/root/reference/src/horton_part/core/base.py:35-411 ``Part``, :413-683 ``WPart``), but the
+per-point work is done by CUDA kernels on a device-resident :class:`GridSlab`; NumPy arrays in the
+cache are downloads of device results.  Additional keyword arguments of this implementation:
+
+    device     torch device / index of the B200 to use (default: current CUDA device)
+    comm       a ``torch.distributed`` process group: the grid is sharded by atom blocks over its
+               ranks and per-iteration results are exchanged with NCCL
+"""
+
+from __future__ import annotations
+
+import logging
+
+import numpy as np
+
+from ..utils import DENSITY_CUTOFF, NEGATIVE_CUTOFF, POPULATION_CUTOFF, typecheck_geo
+from .cache import Cache, JustOnceClass, just_once
+from .logging import deflist, setup_logger
+
+__all__ = ["Part", "WPart", "get_ncart_cumul", "get_npure_cumul"]
+
+
+def get_ncart_cumul(lmax):
+    """Number of Cartesian monomials x^i y^j z^k with i+j+k <= lmax."""
+    return ((lmax + 1) * (lmax + 2) * (lmax + 3)) // 6
+
+
+def get_npure_cumul(lmax):
+    """Number of real solid harmonics with l <= lmax."""
+    return (lmax + 1) ** 2
+
+
+class Part(JustOnceClass):
+    name = None
+
+    def __init__(self, coordinates, numbers, pseudo_numbers, grid, moldens, spindens, local, lmax,
+                 logger, *args, **kwargs):  # fmt: skip
+        super().__init__()
+        natom, coordinates, numbers, pseudo_numbers = typecheck_geo(coordinates, numbers, pseudo_numbers)
+        self._natom = natom
+        self._coordinates = coordinates
+        self._numbers = numbers
+        self._pseudo_numbers = pseudo_numbers
+        self._grid = grid
+        self._moldens = moldens
+        self._spindens = spindens
+        self._local = local
+        self._lmax = lmax
+        self._cache = Cache()
+        self.logger = logger
+        if local:
+            self._init_subgrids()
+        self._init_log_base()
+        self._init_log_scheme()
+
+    # -- mapping-style access to results ---------------------------------------------------------
+    def __getitem__(self, key):
+        return self.cache.load(key)
+
+    def variables_stored_in_cache(self):
+        return list(self.cache.iterkeys())
+
+    natom = property(lambda self: self._natom)
+    coordinates = property(lambda self: self._coordinates)
+    numbers = property(lambda self: self._numbers)
+    pseudo_numbers = property(lambda self: self._pseudo_numbers)
+    local = property(lambda self: self._local)
+    lmax = property(lambda self: self._lmax)
+    cache = property(lambda self: self._cache)
+
+    @property
+    def nelec(self):
+        return self.grid.integrate(self._moldens)
+
+    @property
+    def grid(self):
+        return self.get_grid()
+
+    def __clear__(self):
+        self.clear()
+
+    def clear(self):
+        JustOnceClass.clear(self)
+        self.cache.clear()
+
+    def get_grid(self, index=None):
+        if index is None or not self.local:
+            return self._grid
+        return self._subgrids[index]
+
+    def _on_atom(self, index, data, output):
+        result = data if (index is None or not self.local) else self.to_atomic_grid(index, data)
+        if output is not None:
+            output[:] = result
+        return result
+
+    def get_moldens(self, index=None, output=None):
+        return self._on_atom(index, self._moldens, output)
+
+    def get_spindens(self, index=None, output=None):
+        return self._on_atom(index, self._spindens, output)
+
+    def _init_subgrids(self):
+        raise NotImplementedError
+
+    def _init_log_base(self):
+        raise NotImplementedError
+
+    def _init_log_scheme(self):
+        raise NotImplementedError
+
+    def to_atomic_grid(self, index, data):
+        raise NotImplementedError
+
+    def get_wcor(self, index):
+        return 1.0
+
+    def compute_pseudo_population(self, index):
+        grid = self.get_grid(index)
+        return grid.integrate(self.cache.load(f"at_weights_{index}"), self.get_moldens(index))
+
+    @just_once
+    def do_partitioning(self):
+        self.update_at_weights()
+
+    do_partitioning.names = []
+
+    def update_at_weights(self, *args, **kwargs):
+        raise NotImplementedError
+
+    def _owner_weights(self, index):
+        w = self.cache.load(f"at_weights_{index}")
+        if w.shape == self._grid.weights.shape:
+            w = self.to_atomic_grid(index, w)
+        return w
+
+    @just_once
+    def do_populations(self):
+        populations, new = self.cache.load("populations", alloc=self.natom, tags="o")
+        if new:
+            self.do_partitioning()
+            pseudo_populations = self.cache.load("pseudo_populations", alloc=self.natom, tags="o")[0]
+            self.logger.info("Computing atomic populations.")
+            pseudo_populations[:] = self._atom_integrals(self._moldens)
+            populations[:] = pseudo_populations
+            populations += self.numbers - self.pseudo_numbers
+
+    @just_once
+    def do_charges(self):
+        charges, new = self._cache.load("charges", alloc=self.natom, tags="o")
+        if new:
+            self.do_populations()
+            populations = self._cache.load("populations")
+            self.logger.info("Computing atomic charges.")
+            charges[:] = self.numbers - populations
+
+    @just_once
+    def do_spin_charges(self):
+        if self._spindens is not None:
+            spin_charges, new = self._cache.load("spin_charges", alloc=self.natom, tags="o")
+            self.do_partitioning()
+            self.logger.info("Computing atomic spin charges.")
+            spin_charges[:] = self._atom_integrals(self._spindens)
+
+    def _atom_integrals(self, density):
+        """int w_a * density over each atom's own grid (core/base.py:287-298, 320-326)."""
+        raise NotImplementedError
+
+    def do_all(self):
+        for attr_name in dir(self):
+            attr = getattr(self, attr_name)
+            if callable(attr) and attr_name.startswith("do_") and attr_name != "do_all":
+                attr()
+        return list(self.cache.iterkeys(tags="o"))
+
+
+class WPart(Part):
+    """Base class of the weight-function partitioning schemes."""
+
+    def __init__(self, coordinates, numbers, pseudo_numbers, grid, moldens, spindens=None, lmax=3,
+                 logger=None, grid_type=1, density_cutoff=DENSITY_CUTOFF,
+                 negative_cutoff=NEGATIVE_CUTOFF, population_cutoff=POPULATION_CUTOFF,
+                 device=None, comm=None, **kwargs):  # fmt: skip
+        self._grid_type = grid_type
+        self._on_molgrid = None
+        self._only_use_molgrid = None
+        self.setup_grids()
+        local = not self._only_use_molgrid
+        if local and grid.atgrids is None:
+            raise ValueError(
+                "Atomic grids are discarded from molecular grid object, "
+                "but are needed for local integrations."
+            )
+        if logger is None:
+            logger = logging.getLogger(self.__class__.__name__)
+            setup_logger(logger)
+        self._device = device
+        self._comm = comm
+        self._slab = None
+        self._density_cutoff = density_cutoff
+        self._population_cutoff = population_cutoff
+        self._negative_cutoff = negative_cutoff
+        super().__init__(coordinates, numbers, pseudo_numbers, grid, moldens, spindens, local, lmax, logger)
+        self.history_propars = []
+        self.history_charges = []
+        self.history_entropies = []
+        self.history_changes = []
+        self.history_time_update_at_weights = []
+        self.history_time_update_propars = []
+        self._radial_distances = []
+
+    def setup_grids(self):
+        """grid_type 1: atomic grids + molecular grid (weights only); 2: molecular grid for
+        everything, atomic grids for constraints; 3: molecular grid only."""
+        assert self.grid_type in [1, 2, 3]
+        self._on_molgrid = self.grid_type in (2, 3)
+        self._only_use_molgrid = self.grid_type == 3
+
+    grid_type = property(lambda self: self._grid_type)
+    only_use_molgrid = property(lambda self: self._only_use_molgrid)
+    on_molgrid = property(lambda self: self._on_molgrid)
+    density_cutoff = property(lambda self: self._density_cutoff)
+    population_cutoff = property(lambda self: self._population_cutoff)
+    negative_cutoff = property(lambda self: self._negative_cutoff)
+
+    @property
+    def radial_distances(self):
+        """|r_p - R_a| for every atom on every grid point (host NumPy, built on first access).
+
+        The kernels never use this table (distances are recomputed in registers); it exists for
+        user code that reads the reference's property (core/base.py:545-564)."""
+        self.calc_radial_distances()
+        return self._radial_distances
+
+    @just_once
+    def calc_radial_distances(self):
+        for iatom in range(self.natom):
+            self._radial_distances.append(np.linalg.norm(self.grid.points - self.coordinates[iatom], axis=1))
+
+    def _init_log_base(self):
+        self.logger.info("Performing a density-based AIM analysis with a wavefunction as input.")
+        deflist(
+            self.logger,
+            [("Molecular grid", self._grid.__class__.__name__), ("Using local grids", self._local)],
+        )
+
+    def _init_subgrids(self):
+        self._subgrids = self._grid.atgrids
+
+    def to_atomic_grid(self, index, data):
+        if index is None or not self.local:
+            return data
+        begin, end = self.grid.indices[index], self.grid.indices[index + 1]
+        return data[begin:end]
+
+    # -- device plumbing -----------------------------------------------------------------------
+    @property
+    def slab(self):
+        """Device-resident grid slab of this rank (uploaded on first use)."""
+        if self._slab is None:
+            from .device import GridSlab, Shard
+
+            shard = None
+            if self._comm is not None:
+                import torch.distributed as dist
+
+                shard = Shard(self.natom, self._grid.indices, dist.get_rank(self._comm),
+                              dist.get_world_size(self._comm))  # fmt: skip
+            self._slab = GridSlab(self._grid, self._moldens, self.coordinates, self._device, shard,
+                                  need_atgrids=self.local)  # fmt: skip
+        return self._slab

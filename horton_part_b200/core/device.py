@@ -1,0 +1,214 @@
+"""Device-resident data of one partitioning job: the grid slab owned by this rank, the pro-atom
+shell table, and thin wrappers that launch the C-ABI kernels on torch-owned buffers.
+
+PyTorch is plumbing here: it allocates FP64 device buffers, provides the CUDA stream and (for
+multi-GPU runs) ``torch.distributed``; every arithmetic pass over grid points is a kernel from
+``libhp_b200.so``.  There is no CPU path: constructing a slab without CUDA raises.
+
+Layout in HBM (per rank, ``n`` = local grid points, all FP64 unless noted):
+    px, py, pz      n each     point coordinates, structure-of-arrays (coalesced 8-byte loads)
+    molw            n          molecular quadrature weights (atomic weight x Becke weight)
+    atw             n          the owner atom's un-Becke'd atomic-grid weights (grid_type=1 only)
+    rho             n          molecular density
+    promol, at_w    n each     outputs of the fused pass (promolecule, owner weight)
+    shell tables    ~KBs       atoms' coordinates, (A, alpha, n) per shell, radial grids
+Config 5 (2,000 atoms, 58.2 M points): 8 x 8 B x 58.2 M = 3.7 GB on one GPU, 0.47 GB per GPU on 8.
+"""
+
+from __future__ import annotations
+
+import numpy as np
+
+from .. import _lib
+
+__all__ = ["Shard", "GridSlab", "ShellTable", "require_cuda", "to_device", "stream_ptr"]
+
+
+def require_cuda(device=None):
+    import torch
+
+    if not torch.cuda.is_available():
+        raise RuntimeError(
+            "horton_part_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback"
+        )
+    _lib.lib()  # fail loudly if the extension is not built
+    if device is None:
+        device = torch.device("cuda", torch.cuda.current_device())
+    return torch.device(device)
+
+
+def to_device(array, device, dtype=None):
+    import torch
+
+    a = np.ascontiguousarray(array, dtype=dtype)
+    return torch.from_numpy(a).to(device)
+
+
+def stream_ptr(device):
+    import torch
+
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+class Shard:
+    """Contiguous range of atom blocks [atom_lo, atom_hi) owned by one rank.
+
+    The molecular grid is the concatenation of per-atom grids, so whole atom blocks are assigned to
+    ranks, balanced by point count (dense mode: work per point is identical).  SURVEY.md 8(e).
+    """
+
+    def __init__(self, natom, atom_point_offsets, rank=0, world=1):
+        self.rank, self.world, self.natom = rank, world, natom
+        off = np.asarray(atom_point_offsets, dtype=np.int64)
+        total = int(off[-1])
+        # boundary b_k = first atom whose start offset >= k/world of the points
+        targets = (np.arange(1, world) * total) / world
+        cuts = np.searchsorted(off[:-1], targets, side="left") if world > 1 else np.array([], int)
+        bounds = np.concatenate([[0], cuts, [natom]]).astype(np.int64)
+        bounds = np.maximum.accumulate(bounds)
+        self.bounds = bounds
+        self.atom_lo, self.atom_hi = int(bounds[rank]), int(bounds[rank + 1])
+        self.point_lo, self.point_hi = int(off[self.atom_lo]), int(off[self.atom_hi])
+        self.counts = np.diff(bounds)  # atoms per rank
+
+    @property
+    def nlocal(self):
+        return self.atom_hi - self.atom_lo
+
+
+class GridSlab:
+    """This rank's slice of the molecular grid on the device, plus its shell / radial bookkeeping."""
+
+    def __init__(self, grid, moldens, coordinates, device=None, shard=None, need_atgrids=True,
+                 keep_aos=False):  # fmt: skip
+        import torch
+
+        self.device = require_cuda(device)
+        dev = self.device
+        self.natom = len(coordinates)
+        self.atom_point_offsets_host = np.ascontiguousarray(grid.indices, dtype=np.int64)
+        self.npts_global = int(self.atom_point_offsets_host[-1])
+        self.shard = shard or Shard(self.natom, self.atom_point_offsets_host)
+        lo, hi = self.shard.point_lo, self.shard.point_hi
+        self.point_base = lo
+        self.npts = hi - lo
+
+        pts = np.asarray(grid.points)
+        if pts.shape != (self.npts_global, 3):
+            raise ValueError("grid.points must have shape (Npts, 3)")
+        self.bytes_h2d = 0
+
+        def up(a, dtype=np.float64):
+            t = to_device(a, dev, dtype)
+            self.bytes_h2d += t.numel() * t.element_size()
+            return t
+
+        aos = up(pts[lo:hi])
+        self.px = torch.empty(self.npts, dtype=torch.float64, device=dev)
+        self.py = torch.empty_like(self.px)
+        self.pz = torch.empty_like(self.px)
+        _lib.call("hp_split_points", aos, self.npts, self.px, self.py, self.pz, stream_ptr(dev))
+        self.points_aos = aos if keep_aos else None
+        self.molw = up(np.asarray(grid.weights)[lo:hi])
+        self.rho = up(np.asarray(moldens)[lo:hi])
+        self.atom_xyz = up(coordinates)
+        self.atom_point_offsets = up(self.atom_point_offsets_host, np.int64)
+
+        self.atw = None
+        if need_atgrids:
+            atgrids = grid.atgrids
+            if atgrids is None:
+                raise ValueError(
+                    "Atomic grids are discarded from molecular grid object, "
+                    "but are needed for local integrations."
+                )
+            a_lo, a_hi = self.shard.atom_lo, self.shard.atom_hi
+            whole = getattr(grid, "atweights", None)
+            if whole is not None and len(whole) == self.npts_global:
+                atw = np.asarray(whole)[lo:hi]
+            else:
+                atw = np.concatenate([atgrids[a].weights for a in range(a_lo, a_hi)]) if a_hi > a_lo else np.zeros(0)
+            self.atw = up(atw)
+            shell_off, rad_off = [0], [0]
+            rad_r, rad_w, rad_w4, rad_r2w = [], [], [], []
+            for a in range(a_lo, a_hi):
+                g = atgrids[a]
+                r, w = np.asarray(g.rgrid.points, float), np.asarray(g.rgrid.weights, float)
+                idx = np.asarray(g.indices, dtype=np.int64)
+                base = self.atom_point_offsets_host[a] - lo
+                shell_off.extend((base + idx[1:]).tolist())
+                rad_off.append(rad_off[-1] + len(r))
+                rad_r.append(r)
+                rad_w.append(w)
+                rad_w4.append(4 * np.pi * r**2 * w)  # mbis.py:182, gisa.py:298
+                rad_r2w.append(r**2 * w)  # qc-grid integrate_angular_coordinates
+            cat = lambda xs: np.concatenate(xs) if xs else np.zeros(0)  # noqa: E731
+            self.rad_offsets_host = np.asarray(rad_off, dtype=np.int32)
+            self.rad_r_host, self.rad_w_host, self.rad_w4_host = cat(rad_r), cat(rad_w), cat(rad_w4)
+            self.nshell = len(shell_off) - 1
+            self.shell_point_offsets = up(np.asarray(shell_off, dtype=np.int64), np.int64)
+            self.rad_offsets = up(self.rad_offsets_host, np.int32)
+            self.rad_r = up(self.rad_r_host)
+            self.rad_w4 = up(self.rad_w4_host)
+            self.rad_r2w = up(cat(rad_r2w))
+            if self.nshell and int(np.max(np.diff(self.rad_offsets_host))) > 4096:
+                raise ValueError("radial grids with more than 4096 points are not supported")
+            self.sph_avg = torch.zeros(self.nshell, dtype=torch.float64, device=dev)
+
+        self.promol = torch.empty(self.npts, dtype=torch.float64, device=dev)
+        self.at_w = torch.empty(self.npts, dtype=torch.float64, device=dev)
+        self.npartial = int(_lib.call("hp_num_partials"))
+        self.entropy_partials = torch.zeros(self.npartial, dtype=torch.float64, device=dev)
+
+    # ------------------------------------------------------------------------------------------
+    def shell_project(self):
+        """Spherical averages of at_w*rho over this rank's atoms' radial shells -> self.sph_avg."""
+        _lib.call("hp_shell_project", self.nshell, self.shell_point_offsets, self.at_w, self.rho,
+                  self.atw, self.rad_r, self.rad_r2w, self.sph_avg, stream_ptr(self.device))  # fmt: skip
+        return self.sph_avg
+
+
+class ShellTable:
+    """(A, alpha, n) per shell for ALL atoms (replicated on every rank) and the atom tiling the
+    promolecule kernel streams through shared memory."""
+
+    def __init__(self, slab: GridSlab, functor: int, shells_per_atom):
+        import torch
+
+        self.slab, self.functor = slab, int(functor)
+        dev = slab.device
+        counts = np.asarray(shells_per_atom, dtype=np.int64)
+        if len(counts) != slab.natom:
+            raise ValueError("need one shell count per atom")
+        self.offsets_host = np.concatenate([[0], np.cumsum(counts)]).astype(np.int32)
+        self.nshell = int(self.offsets_host[-1])
+        max_atoms = np.zeros(1, np.int32)
+        max_shells = np.zeros(1, np.int32)
+        _lib.call("hp_tile_limits", max_atoms, max_shells)
+        if counts.max(initial=0) > int(max_shells[0]):
+            raise ValueError("an atom has more shells than one shared-memory tile can hold")
+        tiles, a = [0], 0
+        while a < slab.natom:
+            b, nsh = a, 0
+            while b < slab.natom and b - a < int(max_atoms[0]) and nsh + counts[b] <= int(max_shells[0]):
+                nsh += counts[b]
+                b += 1
+            tiles.append(b)
+            a = b
+        self.ntile = len(tiles) - 1
+        self.tiles = to_device(np.asarray(tiles, dtype=np.int32), dev)
+        self.offsets = to_device(self.offsets_host, dev)
+        self.A = torch.zeros(max(self.nshell, 1), dtype=torch.float64, device=dev)
+        self.alpha = torch.zeros_like(self.A)
+        self.order = torch.ones_like(self.A) if functor == 3 else None
+
+    def promol_weights(self, density_cutoff, want_promol=True, want_weights=True, want_entropy=True):
+        """Launch the fused promolecule / owner-weight / entropy pass over the local slab."""
+        s = self.slab
+        _lib.call(
+            "hp_promol_weights", self.functor, s.npts, s.px, s.py, s.pz, s.point_base, s.natom,
+            s.atom_xyz, s.atom_point_offsets, self.offsets, self.A, self.alpha, self.order,
+            self.ntile, self.tiles, s.rho, s.molw, float(density_cutoff),
+            s.promol if want_promol else None, s.at_w if want_weights else None,
+            s.entropy_partials if want_entropy else None, stream_ptr(s.device),
+        )  # fmt: skip

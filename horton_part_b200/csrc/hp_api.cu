@@ -1,0 +1,97 @@
+// Library plumbing: error strings, device properties, and the FP64 throughput probe.
+#include "hp_common.cuh"
+
+namespace hp {
+
+static thread_local char g_error[512] = "";
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_error, sizeof(g_error), fmt, ap);
+    va_end(ap);
+}
+
+int check_cuda(cudaError_t err, const char* what) {
+    if (err == cudaSuccess) return HP_OK;
+    set_error("%s: CUDA error %d (%s)", what, int(err), cudaGetErrorString(err));
+    return HP_ERR_CUDA;
+}
+
+int sm_count() {
+    static thread_local int cached_dev = -1, cached = 0;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+    if (dev != cached_dev) {
+        int n = 0;
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
+            n = 148;
+        cached = n;
+        cached_dev = dev;
+    }
+    return cached;
+}
+
+// 8 independent DFMA chains per thread, fully unrolled inner body: measures the FP64 FMA issue rate.
+__global__ void __launch_bounds__(256) dfma_probe_kernel(int iters, double* sink) {
+    double a0 = threadIdx.x * 1e-9, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3;
+    double a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+    const double m = 0.999999999, c = 1e-12;
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int u = 0; u < 16; ++u) {
+            a0 = fma(a0, m, c); a1 = fma(a1, m, c); a2 = fma(a2, m, c); a3 = fma(a3, m, c);
+            a4 = fma(a4, m, c); a5 = fma(a5, m, c); a6 = fma(a6, m, c); a7 = fma(a7, m, c);
+        }
+    }
+    const double s = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
+    if (s == 123.456) sink[0] = s;  // never true; keeps the chains alive
+}
+
+}  // namespace hp
+
+using namespace hp;
+
+extern "C" const char* hp_last_error(void) { return g_error; }
+
+extern "C" int hp_abi_version(void) { return 1; }
+
+extern "C" int hp_device_props(int32_t* out_host) {
+    HP_REQUIRE(out_host, "null output");
+    int dev = 0;
+    int rc = check_cuda(cudaGetDevice(&dev), "cudaGetDevice");
+    if (rc) return rc;
+    int sm = 0, major = 0, minor = 0;
+    rc = check_cuda(cudaDeviceGetAttribute(&sm, cudaDevAttrMultiProcessorCount, dev), "attr sm");
+    if (rc) return rc;
+    cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
+    cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, dev);
+    out_host[0] = sm;
+    out_host[1] = major;
+    out_host[2] = minor;
+    return HP_OK;
+}
+
+extern "C" int hp_dfma_probe(int32_t iters, double* sink, float* ms_host, double* flops_host,
+                             void* stream) {
+    HP_REQUIRE(iters > 0 && sink && ms_host && flops_host, "bad arguments");
+    cudaStream_t st = as_stream(stream);
+    const int blocks = sm_count() * 8;
+    cudaEvent_t e0, e1;
+    int rc = check_cuda(cudaEventCreate(&e0), "event");
+    if (rc) return rc;
+    rc = check_cuda(cudaEventCreate(&e1), "event");
+    if (rc) return rc;
+    dfma_probe_kernel<<<blocks, 256, 0, st>>>(iters / 8 + 1, sink);  // warm-up
+    cudaEventRecord(e0, st);
+    dfma_probe_kernel<<<blocks, 256, 0, st>>>(iters, sink);
+    cudaEventRecord(e1, st);
+    rc = check_cuda(cudaEventSynchronize(e1), "dfma_probe_kernel");
+    if (rc == HP_OK) {
+        cudaEventElapsedTime(ms_host, e0, e1);
+        *flops_host = 2.0 * 8.0 * 16.0 * double(iters) * 256.0 * double(blocks);
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    return rc;
+}

@@ -1,0 +1,343 @@
+// Per-atom projection and radial pro-atom solves (rows a8, a9, a10 of SURVEY.md section 8a).
+#include "hp_common.cuh"
+
+namespace hp {
+
+// ---------------------------------------------------------------------------------------------
+// Shell tables
+// ---------------------------------------------------------------------------------------------
+__global__ void table_mbis_kernel(int nshell, const double* __restrict__ propars,
+                                  double* __restrict__ A, double* __restrict__ alpha) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= nshell) return;
+    const double N = propars[2 * k], S = propars[2 * k + 1];
+    // mbis.py:286  N * S**3 * exp(-S r) / (8 pi): everything but the exponential
+    A[k] = N * (S * S * S) / kEightPi;
+    alpha[k] = S;
+}
+
+__global__ void table_scaled_kernel(int nshell, const double* __restrict__ c,
+                                    const double* __restrict__ norms, double* __restrict__ A) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < nshell) A[k] = c[k] * norms[k];
+}
+
+__global__ void table_nlis_kernel(int nshell, const double* __restrict__ propars,
+                                  const double* __restrict__ inv_gamma, double* __restrict__ A,
+                                  double* __restrict__ alpha, double* __restrict__ order) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= nshell) return;
+    const double N = propars[3 * k], S = propars[3 * k + 1], n = propars[3 * k + 2];
+    // nlis.py:325  N * n * S**(3/n) * exp(-S r**n) / (4 pi Gamma(3/n))
+    A[k] = N * n * pow(S, 3.0 / n) * inv_gamma[k] / kFourPi;
+    alpha[k] = S;
+    order[k] = n;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Spherical average: one warp per radial shell
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+shell_project_kernel(int nshell, const int64_t* __restrict__ shell_off, const double* __restrict__ w,
+                     const double* __restrict__ rho, const double* __restrict__ atw,
+                     const double* __restrict__ shell_r, const double* __restrict__ r2w,
+                     double* __restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int nwarp = (gridDim.x * blockDim.x) >> 5;
+    for (int s = warp; s < nshell; s += nwarp) {
+        const int64_t lo = shell_off[s], hi = shell_off[s + 1];
+        double acc = 0.0;
+        for (int64_t p = lo + lane; p < hi; p += 32) acc += (w[p] * rho[p]) * atw[p];
+        acc = warp_allsum(acc);
+        if (lane == 0) {
+            // qc-grid integrate_angular_coordinates + spherical_average: divide the radial factor
+            // r^2 w_rad out again, zero at the nucleus, then 1/(4 pi)
+            double v = acc / r2w[s];
+            if (fabs(shell_r[s]) < 1e-8) v = 0.0;
+            out[s] = v / kFourPi;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// MBIS radial fixed point, one warp per atom
+// ---------------------------------------------------------------------------------------------
+constexpr int kMaxMbisShells = 7;  // periodic table: get_nshell <= 7 (mbis.py:36-46)
+
+__global__ void __launch_bounds__(32)
+mbis_radial_kernel(int natom, int atom_base, const int* __restrict__ rad_off, const double* __restrict__ rad_r,
+                   const double* __restrict__ rad_w4, const double* __restrict__ sph,
+                   const int* __restrict__ par_off, double* __restrict__ propars,
+                   const double* __restrict__ pseudo, double threshold, double density_cutoff,
+                   int max_inner, double* __restrict__ charges, double* __restrict__ msd,
+                   int* __restrict__ niter_out, uint32_t* __restrict__ flags_out) {
+    extern __shared__ double smem[];  // [oldpro | pro] each nrad_max
+    if (int(blockIdx.x) >= natom) return;
+    const int a = atom_base + blockIdx.x;  // global atom index; radial data are rank-local
+    const int lane = threadIdx.x;
+    const int r0 = rad_off[blockIdx.x], nrad = rad_off[blockIdx.x + 1] - r0;
+    const int p0 = par_off[a], K = (par_off[a + 1] - p0) / 2;
+    const double* r = rad_r + r0;
+    const double* w = rad_w4 + r0;
+    const double* rho = sph + r0;
+    double* oldpro = smem;
+
+    double N[kMaxMbisShells], S[kMaxMbisShells], N0[kMaxMbisShells], S0[kMaxMbisShells];
+#pragma unroll
+    for (int k = 0; k < kMaxMbisShells; ++k) {
+        N[k] = S[k] = 0.0;
+        if (k < K) {
+            N[k] = propars[p0 + 2 * k];
+            S[k] = propars[p0 + 2 * k + 1];
+        }
+        N0[k] = N[k];
+        S0[k] = S[k];
+    }
+
+    // pop = sum weights * rho  (mbis.py:122); also the pseudo-population of mbis.py:201
+    double pop = 0.0;
+    for (int i = lane; i < nrad; i += 32) pop += w[i] * rho[i];
+    pop = warp_allsum(pop);
+
+    uint32_t flags = HP_SOLVE_NOT_CONVERGED;
+    int it = 0;
+    for (; it < max_inner; ++it) {
+        double m0[kMaxMbisShells], m1[kMaxMbisShells];
+#pragma unroll
+        for (int k = 0; k < kMaxMbisShells; ++k) m0[k] = m1[k] = 0.0;
+        double chg = 0.0;
+        for (int i = lane; i < nrad; i += 32) {
+            const double ri = r[i];
+            double term[kMaxMbisShells];
+            double pro = 0.0;
+#pragma unroll
+            for (int k = 0; k < kMaxMbisShells; ++k) {
+                term[k] = 0.0;
+                if (k < K) {
+                    // mbis.py:128
+                    term[k] = N[k] * (S[k] * S[k] * S[k]) * exp(-S[k] * ri) / kEightPi;
+                    pro += term[k];
+                }
+            }
+            const double rh = rho[i];
+            const bool sick = (rh < density_cutoff) || (pro < density_cutoff);
+            const double ratio = sick ? 0.0 : rh / pro;
+#pragma unroll
+            for (int k = 0; k < kMaxMbisShells; ++k) {
+                if (k < K) {
+                    const double tr = term[k] * ratio;
+                    m0[k] += w[i] * tr;          // mbis.py:143
+                    m1[k] += w[i] * tr * ri;     // mbis.py:144
+                }
+            }
+            if (it > 0) {
+                const double e = oldpro[i] - pro;
+                chg += w[i] * e * e;             // mbis.py:151-152
+            }
+            oldpro[i] = pro;
+        }
+#pragma unroll
+        for (int k = 0; k < kMaxMbisShells; ++k) {
+            if (k < K) {
+                const double a0 = warp_allsum(m0[k]);
+                const double a1 = warp_allsum(m1[k]);
+                N[k] = a0;                       // mbis.py:145
+                S[k] = 3.0 * a0 / a1;            // mbis.py:146
+            }
+        }
+        const double change = (it == 0) ? 1e100 : sqrt(warp_allsum(chg));
+        if (change < threshold) {
+            flags &= ~HP_SOLVE_NOT_CONVERGED;
+            ++it;
+            break;
+        }
+    }
+
+    double nsum = 0.0;
+    bool finite = true;
+#pragma unroll
+    for (int k = 0; k < kMaxMbisShells; ++k) {
+        if (k < K) {
+            nsum += N[k];
+            finite = finite && isfinite(N[k]) && isfinite(S[k]);
+        }
+    }
+    // mbis.py:157 np.isclose(pop, sum N, atol=1e-4) -> |a-b| <= atol + rtol*|b|, rtol = 1e-5
+    if (!(fabs(pop - nsum) <= 1e-4 + 1e-5 * fabs(nsum))) flags |= HP_SOLVE_POP_MISMATCH;
+    if (!finite) flags |= HP_SOLVE_NONFINITE;
+
+    // this atom's contribution to compute_change (core/iterstock.py:36-44, mbis.py:256-260)
+    double dev = 0.0;
+    for (int i = lane; i < nrad; i += 32) {
+        const double ri = r[i];
+        double ynew = 0.0, yold = 0.0;
+#pragma unroll
+        for (int k = 0; k < kMaxMbisShells; ++k) {
+            if (k < K) {
+                ynew += N[k] * (S[k] * S[k] * S[k]) * exp(-S[k] * ri) / kEightPi;
+                yold += N0[k] * (S0[k] * S0[k] * S0[k]) * exp(-S0[k] * ri) / kEightPi;
+            }
+        }
+        const double d = ynew - yold;
+        dev += w[i] * d * d;
+    }
+    dev = warp_allsum(dev);
+
+    if (lane == 0) {
+#pragma unroll
+        for (int k = 0; k < kMaxMbisShells; ++k) {
+            if (k < K) {
+                propars[p0 + 2 * k] = N[k];
+                propars[p0 + 2 * k + 1] = S[k];
+            }
+        }
+        charges[a] = pseudo[a] - pop;  // mbis.py:203
+        msd[a] = dev;
+        niter_out[a] = it;
+        flags_out[a] = flags;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// End-of-iteration scalars in a fixed summation order
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+finish_iteration_kernel(int npartial, const double* __restrict__ partials, int natom,
+                        const double* __restrict__ msd, double* __restrict__ out2) {
+    __shared__ double red[32];
+    double e = 0.0;
+    if (partials)
+        for (int i = threadIdx.x; i < npartial; i += blockDim.x) e += partials[i];
+    e = block_sum(e, red);
+    double m = 0.0;
+    for (int i = threadIdx.x; i < natom; i += blockDim.x) m += msd[i];
+    m = block_sum(m, red);
+    if (threadIdx.x == 0) {
+        out2[0] = sqrt(m);  // core/iterstock.py:45
+        out2[1] = e;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+sum_partials_kernel(int n, const double* __restrict__ partials, double* __restrict__ out) {
+    __shared__ double red[32];
+    double e = 0.0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) e += partials[i];
+    e = block_sum(e, red);
+    if (threadIdx.x == 0) out[0] = e;
+}
+
+// out[s] = sum_{p in segment s} w[p] * f[p] * (g ? g[p] : 1): one block per segment, fixed order
+__global__ void __launch_bounds__(256)
+segment_integrate_kernel(int nseg, const int64_t* __restrict__ seg_off, const double* __restrict__ w,
+                         const double* __restrict__ f, const double* __restrict__ g,
+                         double* __restrict__ out) {
+    __shared__ double red[32];
+    for (int s = blockIdx.x; s < nseg; s += gridDim.x) {
+        const int64_t lo = seg_off[s], hi = seg_off[s + 1];
+        double acc = 0.0;
+        for (int64_t p = lo + threadIdx.x; p < hi; p += blockDim.x)
+            acc += g ? (w[p] * f[p]) * g[p] : w[p] * f[p];
+        acc = block_sum(acc, red);
+        if (threadIdx.x == 0) out[s] = acc;
+    }
+}
+
+}  // namespace hp
+
+using namespace hp;
+
+extern "C" int hp_sum_partials(int32_t n, const double* partials, double* out1, void* stream) {
+    HP_REQUIRE(n > 0 && partials && out1, "bad arguments");
+    sum_partials_kernel<<<1, 256, 0, as_stream(stream)>>>(n, partials, out1);
+    HP_LAUNCH_CHECK("sum_partials_kernel");
+    return HP_OK;
+}
+
+extern "C" int hp_segment_integrate(int32_t nseg, const int64_t* seg_offsets, const double* w,
+                                    const double* f, const double* g, double* out, void* stream) {
+    HP_REQUIRE(nseg >= 0, "bad sizes");
+    if (nseg == 0) return HP_OK;
+    HP_REQUIRE(seg_offsets && w && f && out, "null input");
+    int blocks = nseg < sm_count() * 8 ? nseg : sm_count() * 8;
+    segment_integrate_kernel<<<blocks, 256, 0, as_stream(stream)>>>(nseg, seg_offsets, w, f, g, out);
+    HP_LAUNCH_CHECK("segment_integrate_kernel");
+    return HP_OK;
+}
+
+extern "C" int hp_table_mbis(int32_t nshell, const double* propars, double* shell_A,
+                             double* shell_alpha, void* stream) {
+    HP_REQUIRE(nshell > 0 && propars && shell_A && shell_alpha, "bad arguments");
+    table_mbis_kernel<<<(nshell + 127) / 128, 128, 0, as_stream(stream)>>>(nshell, propars, shell_A,
+                                                                           shell_alpha);
+    HP_LAUNCH_CHECK("table_mbis_kernel");
+    return HP_OK;
+}
+
+extern "C" int hp_table_scaled(int32_t nshell, const double* coeffs, const double* norms,
+                               double* shell_A, void* stream) {
+    HP_REQUIRE(nshell > 0 && coeffs && norms && shell_A, "bad arguments");
+    table_scaled_kernel<<<(nshell + 127) / 128, 128, 0, as_stream(stream)>>>(nshell, coeffs, norms,
+                                                                             shell_A);
+    HP_LAUNCH_CHECK("table_scaled_kernel");
+    return HP_OK;
+}
+
+extern "C" int hp_table_nlis(int32_t nshell, const double* propars, const double* inv_gamma,
+                             double* shell_A, double* shell_alpha, double* shell_order,
+                             void* stream) {
+    HP_REQUIRE(nshell > 0 && propars && inv_gamma && shell_A && shell_alpha && shell_order,
+               "bad arguments");
+    table_nlis_kernel<<<(nshell + 127) / 128, 128, 0, as_stream(stream)>>>(
+        nshell, propars, inv_gamma, shell_A, shell_alpha, shell_order);
+    HP_LAUNCH_CHECK("table_nlis_kernel");
+    return HP_OK;
+}
+
+extern "C" int hp_shell_project(int32_t nshell, const int64_t* shell_point_offsets,
+                                const double* at_weights, const double* rho, const double* atgrid_w,
+                                const double* shell_r, const double* shell_r2w, double* out_sph_avg,
+                                void* stream) {
+    HP_REQUIRE(nshell >= 0, "bad sizes");
+    if (nshell == 0) return HP_OK;
+    HP_REQUIRE(shell_point_offsets && at_weights && rho && atgrid_w && shell_r && shell_r2w &&
+                   out_sph_avg, "null input");
+    const int warps_per_block = 8;
+    int64_t blocks = (int64_t(nshell) + warps_per_block - 1) / warps_per_block;
+    const int64_t cap = int64_t(sm_count()) * 16;
+    if (blocks > cap) blocks = cap;
+    shell_project_kernel<<<int(blocks), warps_per_block * 32, 0, as_stream(stream)>>>(
+        nshell, shell_point_offsets, at_weights, rho, atgrid_w, shell_r, shell_r2w, out_sph_avg);
+    HP_LAUNCH_CHECK("shell_project_kernel");
+    return HP_OK;
+}
+
+extern "C" int hp_mbis_radial_solve(int32_t natom, int32_t atom_base, const int32_t* rad_offsets, const double* rad_r,
+                                    const double* rad_w4, const double* sph_avg,
+                                    const int32_t* par_offsets, double* propars,
+                                    const double* pseudo_numbers, double inner_threshold,
+                                    double density_cutoff, int32_t max_inner, double* charges,
+                                    double* msd, int32_t* niter, uint32_t* flags, void* stream) {
+    HP_REQUIRE(natom >= 0, "bad sizes");
+    if (natom == 0) return HP_OK;
+    HP_REQUIRE(rad_offsets && rad_r && rad_w4 && sph_avg && par_offsets && propars &&
+                   pseudo_numbers && charges && msd && niter && flags, "null input");
+    // shared memory: one double per radial point of the largest atom; the caller guarantees
+    // nrad <= 4096 (checked on the Python side where the offsets live on the host)
+    const size_t smem = sizeof(double) * 4096;
+    mbis_radial_kernel<<<natom, 32, smem, as_stream(stream)>>>(
+        natom, atom_base, rad_offsets, rad_r, rad_w4, sph_avg, par_offsets, propars, pseudo_numbers,
+        inner_threshold, density_cutoff, max_inner, charges, msd, niter, flags);
+    HP_LAUNCH_CHECK("mbis_radial_kernel");
+    return HP_OK;
+}
+
+extern "C" int hp_finish_iteration(int32_t npartial, const double* entropy_partials, int32_t natom,
+                                   const double* msd, double* out2, void* stream) {
+    HP_REQUIRE(natom > 0 && msd && out2, "bad arguments");
+    finish_iteration_kernel<<<1, 256, 0, as_stream(stream)>>>(npartial, entropy_partials, natom, msd,
+                                                              out2);
+    HP_LAUNCH_CHECK("finish_iteration_kernel");
+    return HP_OK;
+}

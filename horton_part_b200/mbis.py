@@ -1,0 +1,152 @@
+"""Minimal Basis Iterative Stockholder (MBIS) on the B200.
+
+Drop-in for the reference's ``MBISWPart`` (/root/reference/src/horton_part/mbis.py:206-362): same
+constructor, cache keys and results.  Pro-atoms are sums of Slater shells
+``N_k S_k^3 exp(-S_k r) / (8 pi)`` (mbis.py:286); the per-atom update is the MBIS fixed point
+``N_k <- int rho_a term_k/pro``, ``S_k <- 3 N_k / int r rho_a term_k/pro`` iterated to
+``inner_threshold`` (``opt_mbis_propars``, mbis.py:81-163), here one warp per atom in
+``hp_mbis_radial_solve``.
+"""
+
+from __future__ import annotations
+
+import logging
+
+import numpy as np
+
+from . import _lib
+from .core.iterstock import AbstractISAWPart
+from .core.logging import deflist
+
+__all__ = ["MBISWPart", "get_nshell", "get_initial_mbis_propars"]
+
+logger = logging.getLogger(__name__)
+
+_NOBLE = np.array([2, 10, 18, 36, 54, 86, 118])
+_SHELL_CAPACITY = np.array([2.0, 8.0, 8.0, 18.0, 18.0, 32.0, 32.0])
+
+
+def get_nshell(number: int):
+    """Number of MBIS shells = period of the element (mbis.py:36-46)."""
+    return _NOBLE.searchsorted(number) + 1
+
+
+def get_initial_mbis_propars(number: int):
+    """Initial [N_1, S_1, N_2, S_2, ...]: closed inner shells, the rest in the valence shell;
+    exponents geometric from 2Z down to 2 (mbis.py:49-78)."""
+    nshell = get_nshell(number)
+    propars = np.zeros(2 * nshell, float)
+    s_first = 2.0 * number
+    ratio = (2.0 / s_first) ** (1.0 / (nshell - 1)) if nshell > 1 else 1.0
+    for k in range(nshell):
+        propars[2 * k] = _SHELL_CAPACITY[k]
+        propars[2 * k + 1] = s_first * ratio**k
+    propars[-2] = number - propars[:-2:2].sum()
+    return propars
+
+
+class MBISWPart(AbstractISAWPart):
+    """Minimal Basis Iterative Stockholder (MBIS)"""
+
+    name = "mbis"
+    max_inner = 2000  # mbis.py:123
+
+    def _init_log_scheme(self):
+        logger.info("Initialized: %s" % self.__class__.__name__)
+        deflist(
+            logger,
+            [
+                ("Scheme", "Minimal Basis Iterative Stockholder (MBIS)"),
+                ("Outer loop convergence threshold", "%.1e" % self._threshold),
+                ("Inner loop convergence threshold", "%.1e" % self._inner_threshold),
+                ("Maximum iterations", self._maxiter),
+            ],
+        )
+
+    def get_rgrid(self, iatom):
+        if self.only_use_molgrid:
+            raise NotImplementedError
+        return self.get_grid(iatom).rgrid
+
+    def get_proatom_rho(self, iatom: int, propars=None, **kwargs):
+        """Pro-atom density and radial derivative on the atom's radial grid (host; API helper)."""
+        if propars is None:
+            propars = self.cache.load("propars")
+        r = self.radial_distances[iatom] if self.on_molgrid else self.get_rgrid(iatom).points
+        y = np.zeros(len(r), float)
+        d = np.zeros(len(r), float)
+        mine = propars[self._ranges[iatom] : self._ranges[iatom + 1]]
+        for k in range(self._nshells[iatom]):
+            N, S = mine[2 * k : 2 * k + 2]
+            f = N * S**3 * np.exp(-S * r) / (8 * np.pi)
+            y += f
+            d -= S * f
+        return y, d
+
+    # -- device hooks ---------------------------------------------------------------------------
+    def _init_propars(self):
+        from .core.device import ShellTable, to_device
+
+        if self.on_molgrid:
+            raise NotImplementedError("MBIS with grid_type 2/3 is not built yet")
+        self._nshells = [int(get_nshell(z)) for z in self.numbers]
+        self._ranges = [0]
+        for k in self._nshells:
+            self._ranges.append(self._ranges[-1] + 2 * k)
+        propars = self.cache.load("propars", alloc=self._ranges[-1], tags="o")[0]
+        for a in range(self.natom):
+            propars[self._ranges[a] : self._ranges[a + 1]] = get_initial_mbis_propars(self.numbers[a])
+        slab = self.slab
+        self._table = ShellTable(slab, 1, self._nshells)  # HP_FUNCTOR_SLATER
+        st = self._alloc_state(len(propars))
+        st.propars.copy_(to_device(propars, slab.device))
+        self._par_offsets = to_device(np.asarray(self._ranges, dtype=np.int32), slab.device)
+        self._pseudo = to_device(self.pseudo_numbers, slab.device, np.float64)
+        return propars
+
+    def _refresh_table(self):
+        from .core.device import stream_ptr
+
+        t = self._table
+        _lib.call("hp_table_mbis", t.nshell, self._state.propars, t.A, t.alpha, stream_ptr(self.slab.device))
+
+    def _launch_radial_update(self):
+        from .core.device import stream_ptr
+
+        slab, st = self.slab, self._state
+        slab.shell_project()
+        sh = slab.shard
+        _lib.call(
+            "hp_mbis_radial_solve", sh.nlocal, sh.atom_lo, slab.rad_offsets, slab.rad_r, slab.rad_w4,
+            slab.sph_avg, self._par_offsets, st.propars, self._pseudo, float(self._inner_threshold),
+            float(self.density_cutoff), int(self.max_inner), st.charges, st.msd, st.niter, st.flags,
+            stream_ptr(slab.device),
+        )  # fmt: skip
+
+    def _post_iteration_checks(self):
+        # the reference only *warns* here (mbis.py:158,162); flags are read lazily to avoid a sync
+        pass
+
+    def _finalize_propars(self):
+        AbstractISAWPart._finalize_propars(self)
+        flags = self._state.flags.cpu().numpy()
+        if (flags & 1).any():
+            self.logger.warning("MBIS not converged, but still go ahead!")
+        if (flags & 2).any():
+            self.logger.warning("The sum of propars are not equal to the atomic pop.")
+        propars = self.cache.load("propars")
+        ends = np.asarray(self._ranges[1:])
+        valence_charges = -propars[ends - 2]
+        valence_widths = 1.0 / propars[ends - 1]
+        core_charges = self._cache.load("charges") - valence_charges
+        self.cache.dump("core_charges", core_charges, tags="o")
+        self.cache.dump("valence_charges", valence_charges, tags="o")
+        self.cache.dump("valence_widths", valence_widths, tags="o")
+        # radial projections of the last iteration (mbis.py:185-187)
+        slab = self.slab
+        sph = slab.sph_avg.cpu().numpy()
+        ro = slab.rad_offsets_host
+        for i, a in enumerate(range(slab.shard.atom_lo, slab.shard.atom_hi)):
+            self.cache.dump(f"radial_points_{a}", slab.rad_r_host[ro[i] : ro[i + 1]], tags="o")
+            self.cache.dump(f"spherical_average_{a}", sph[ro[i] : ro[i + 1]], tags="o")
+            self.cache.dump(f"radial_weights_{a}", slab.rad_w_host[ro[i] : ro[i + 1]], tags="o")

@@ -1,0 +1,171 @@
+/*
+ * hp_b200.h -- C ABI of the B200-native stockholder-iteration hot path.
+ *
+ * The reference (horton-part, pure Python) has no FFI: its boundary is the WPart class API
+ * (SURVEY.md section 8b).  These entry points are what a ctypes binding inside the reference's
+ * own classes would call to replace its NumPy passes; each one cites the reference code it
+ * replaces (paths relative to /root/reference/src/horton_part).  INTEGRATION.md shows the stub.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the parameter name ends in _host;
+ *   - the caller (PyTorch on the Python side) owns all buffers, the library allocates nothing;
+ *   - `stream` is a cudaStream_t passed as void*; all work is enqueued on it, nothing synchronises
+ *     unless the function's comment says so;
+ *   - return value: 0 on success, non-zero on failure with a thread-local message available from
+ *     hp_last_error();
+ *   - all floating point data is IEEE binary64; indices are int64_t (grid points) or int32_t
+ *     (atoms, shells).
+ */
+#ifndef HP_B200_H
+#define HP_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#if defined(__GNUC__)
+#define HP_API __attribute__((visibility("default")))
+#else
+#define HP_API
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HP_OK 0
+#define HP_ERR_ARG 1
+#define HP_ERR_CUDA 2
+
+/* radial form of a pro-atom shell  A * exp(-alpha * r^n)  */
+#define HP_FUNCTOR_SLATER 1  /* n = 1 for every shell: MBIS (mbis.py:263-289), slater basis     */
+#define HP_FUNCTOR_GAUSS 2   /* n = 2 for every shell: gauss basis (core/basis.py:161-171)      */
+#define HP_FUNCTOR_GENERAL 3 /* per-shell real n: NLIS/GMBIS (nlis.py:303-328), custom tables   */
+#define HP_FUNCTOR_SPLINE 4  /* piecewise cubic in r: ISA / Hirshfeld(-I) (core/stockholder.py:271-350) */
+
+/* flags returned per atom by the radial solvers */
+#define HP_SOLVE_NOT_CONVERGED 1u /* hit the inner iteration cap (mbis.py:162, alisa.py:290)   */
+#define HP_SOLVE_POP_MISMATCH 2u  /* |sum N_k - pop| > tolerance (mbis.py:157, utils.py:434)   */
+#define HP_SOLVE_NONFINITE 4u
+
+HP_API const char* hp_last_error(void);
+HP_API int hp_abi_version(void);
+/* Number of SMs etc. of the current device: out_host[0]=SM count, [1]=cc major, [2]=cc minor. */
+HP_API int hp_device_props(int32_t* out_host);
+/* Fixed number of per-block partial sums hp_promol_weights writes (size the buffer with it). */
+HP_API int32_t hp_num_partials(void);
+
+/* ------------------------------------------------------------------------------------------
+ * (row L) cut-off local grid index -- replaces Grid.get_localgrid / cKDTree.query_ball_point
+ * (spec: commented block core/stockholder.py:84-112).  Inclusion is the UNFUSED test
+ * ((dx*dx + dy*dy) + dz*dz) <= radius*radius, indices come out sorted ascending.
+ *   points_xyz   (npts,3) row-major, as the reference stores grid.points
+ *   center_host  3 doubles on the host
+ *   begin,end    the centre atom's own slice of the molecular grid (grid.indices[a], [a+1])
+ *   out_indices  (npts)  capacity; first *count entries valid
+ *   out_overlap  (npts)  1 where begin <= index < end            (may be NULL)
+ *   out_dist     (npts)  |r_p - center| for the selected points  (may be NULL)
+ *   out_count    1 int64 on the device
+ *   scratch      at least hp_local_index_scratch_bytes(npts) bytes
+ */
+HP_API size_t hp_local_index_scratch_bytes(int64_t npts);
+HP_API int hp_build_local_index(const double* points_xyz, int64_t npts, const double* center_host,
+                         double radius, int64_t begin, int64_t end, int64_t* out_indices,
+                         uint8_t* out_overlap, double* out_dist, int64_t* out_count, void* scratch,
+                         size_t scratch_bytes, void* stream);
+
+/* (npts,3) row-major -> three contiguous coordinate arrays (the kernels' SoA layout). */
+HP_API int hp_split_points(const double* points_xyz, int64_t npts, double* px, double* py, double* pz,
+                    void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Shell tables: turn pro-atom parameters into (A, alpha, n) per shell.
+ *   MBIS     propars [N,S]*K      -> A = N S^3/(8 pi), alpha = S, n = 1   (mbis.py:284-287)
+ *   exp-basis c_k, fixed (alpha,n) -> A = c_k * norm_k                    (core/basis.py:161)
+ *   NLIS     propars [N,S,n]*K    -> A = N n S^(3/n)/(4 pi Gamma(3/n))    (nlis.py:322-326)
+ * inv_gamma[k] = 1/Gamma(3/n_k) is supplied by the host (n is fixed during the iterations).
+ */
+HP_API int hp_table_mbis(int32_t nshell, const double* propars, double* shell_A, double* shell_alpha,
+                  void* stream);
+HP_API int hp_table_scaled(int32_t nshell, const double* coeffs, const double* norms, double* shell_A,
+                    void* stream);
+HP_API int hp_table_nlis(int32_t nshell, const double* propars, const double* inv_gamma, double* shell_A,
+                  double* shell_alpha, double* shell_order, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * (rows a1-a7 + a10 entropy) fused promolecule / owner-weight pass over a slab of grid points.
+ * Replaces WPart.calc_radial_distances (core/base.py:630-635), eval_proatom (mbis.py:263-289,
+ * gisa.py:224-244, nlis.py:303-328), update_pro (core/stockholder.py:153-175),
+ * update_at_weights (core/stockholder.py:352-384) and _compute_entropy (:145-151).
+ *
+ * For each local point p (global index point_base + p):
+ *     promol = 0;  for a in 0..natom-1 (in order):  promol = (promol + rho0_a(p)) + 1e-100
+ *     w      = clip(rho0_owner(p) / promol, 0, 1)      owner = atom whose slice contains p
+ *     entropy partial += molw*rho*ln(rho/promol) unless rho < cutoff or promol < cutoff
+ * Atoms are streamed through shared memory in tiles (tile_atom_offsets: ntile+1 atom indices,
+ * each tile's shells must fit the kernel's shared-memory budget: hp_tile_limits()).
+ *   promol, at_weights, entropy_partials may each be NULL to skip that output.
+ *   entropy_partials has hp_num_partials() entries; unused ones are written as 0.
+ */
+HP_API void hp_tile_limits(int32_t* max_atoms_host, int32_t* max_shells_host);
+HP_API int hp_promol_weights(int functor, int64_t npts, const double* px, const double* py,
+                      const double* pz, int64_t point_base, int32_t natom, const double* atom_xyz,
+                      const int64_t* atom_point_offsets, const int32_t* atom_shell_offsets,
+                      const double* shell_A, const double* shell_alpha, const double* shell_order,
+                      int32_t ntile, const int32_t* tile_atom_offsets, const double* rho,
+                      const double* molw, double density_cutoff, double* promol,
+                      double* at_weights, double* entropy_partials, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * (row a8) spherical average of w_a*rho over each radial shell of each atom's own atomic grid.
+ * Replaces AtomGrid.spherical_average as called from mbis.py:176-184, gisa.py:283-289,
+ * isa.py:104-110:  out[s] = sum_{j in shell s} at_weights[j]*rho[j]*atgrid_w[j] / r2w[s] / (4 pi),
+ * and 0 where |shell_r[s]| < 1e-8.  shell_point_offsets are LOCAL point indices (nshell+1).
+ */
+HP_API int hp_shell_project(int32_t nshell, const int64_t* shell_point_offsets, const double* at_weights,
+                     const double* rho, const double* atgrid_w, const double* shell_r,
+                     const double* shell_r2w, double* out_sph_avg, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * (rows a9 + a10 change) per-atom radial solves, one warp per atom, all atoms in one launch.
+ * Radial data are concatenated over atoms: atom a owns entries rad_offsets[a]..rad_offsets[a+1]
+ * of rad_r (rgrid.points), rad_w4 (4 pi r^2 w_rad) and sph_avg.
+ *
+ * Sharding: the launch covers `natom` atoms starting at global atom `atom_base`; rad_offsets and
+ * the radial arrays are rank-local (indexed from 0), par_offsets / propars / pseudo_numbers /
+ * charges / msd / niter / flags are global arrays indexed by the global atom.
+ *
+ * hp_mbis_radial_solve -- opt_mbis_propars (mbis.py:81-163) + charge (mbis.py:200-203) +
+ * this atom's term of compute_change (core/iterstock.py:32-45):
+ *     propars  in/out  [N,S]*K per atom at par_offsets[a]
+ *     charges  out     pseudo_numbers[a] - sum rad_w4*sph_avg
+ *     msd      out     int 4 pi r^2 (rho0_new - rho0_old)^2
+ *     niter, flags out per atom
+ */
+HP_API int hp_mbis_radial_solve(int32_t natom, int32_t atom_base, const int32_t* rad_offsets, const double* rad_r,
+                         const double* rad_w4, const double* sph_avg, const int32_t* par_offsets,
+                         double* propars, const double* pseudo_numbers, double inner_threshold,
+                         double density_cutoff, int32_t max_inner, double* charges, double* msd,
+                         int32_t* niter, uint32_t* flags, void* stream);
+
+/* Sum the entropy partials and sqrt(sum msd) in a fixed order: out[0] = change, out[1] = entropy. */
+HP_API int hp_finish_iteration(int32_t npartial, const double* entropy_partials, int32_t natom,
+                        const double* msd, double* out2, void* stream);
+
+/* out1[0] = sum of n partials (fixed order): the rank-local entropy before an all-reduce. */
+HP_API int hp_sum_partials(int32_t n, const double* partials, double* out1, void* stream);
+
+/* (row a13, populations) out[s] = sum over points of segment s of w*f*(g or 1); seg_offsets has
+ * nseg+1 LOCAL point indices.  Replaces grid.integrate(at_weights, dens) per atom
+ * (core/base.py:259-264, 287-298, 320-326, glisa.py:269-278). */
+HP_API int hp_segment_integrate(int32_t nseg, const int64_t* seg_offsets, const double* w,
+                                const double* f, const double* g, double* out, void* stream);
+
+/* FP64 FMA throughput probe used by bench.py for the roofline denominator: runs `iters` dependent
+ * DFMA chains (8 independent per thread) on a full grid; returns elapsed ms in *ms_host and the
+ * flop count in *flops_host.  Synchronises the stream. */
+HP_API int hp_dfma_probe(int32_t iters, double* sink, float* ms_host, double* flops_host, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HP_B200_H */

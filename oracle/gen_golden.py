@@ -1,0 +1,145 @@
+"""Generate tests/golden/* by running the UNMODIFIED reference (/root/reference/src/horton_part)
+through oracle/qcgrid_shim in the build container.  The reference tree does not exist on the GPU
+box, so the vectors are committed; this script is the record of how they were made.
+
+    python oracle/gen_golden.py            # all cases
+    python oracle/gen_golden.py h2o        # one case
+
+Inputs that cannot be regenerated on the GPU box (the water HF/STO-3G density from the
+reference's tests/cached fixture, re-ordered onto the rebuilt grid) are stored alongside.
+"""
+
+from __future__ import annotations
+
+import logging
+import pathlib
+import sys
+import time
+
+import numpy as np
+
+ROOT = pathlib.Path(__file__).resolve().parents[1]
+sys.path[:0] = [str(ROOT / "oracle" / "qcgrid_shim"), "/root/reference/src", str(ROOT)]
+
+import grid as qcgrid  # noqa: E402  (the shim)
+from horton_part.utils import wpart_schemes  # noqa: E402  (the reference itself)
+
+from horton_part_b200 import synthetic  # noqa: E402  (pure-NumPy generators only)
+
+GOLD = ROOT / "tests" / "golden"
+REF_CACHED = pathlib.Path("/root/reference/tests/cached")
+logging.disable(logging.CRITICAL)
+
+
+def run_reference(scheme, coords, numbers, pseudo, grid, rho, **kwargs):
+    t0 = time.time()
+    part = wpart_schemes(scheme)(coords, numbers, pseudo, grid, rho, **kwargs)
+    part.do_charges()
+    out = {
+        "niter": np.int64(part["niter"]),
+        "charges": part["charges"],
+        "propars": part["propars"],
+        "history_changes": part["history_changes"],
+        "history_entropies": part["history_entropies"],
+        "history_charges": part["history_charges"],
+        "promoldens_sample": part["promoldens"][::97].copy(),
+        "seconds": np.float64(time.time() - t0),
+    }
+    for a in range(min(len(numbers), 3)):
+        w = part[f"at_weights_{a}"]
+        if w.shape == grid.weights.shape:
+            w = w[grid.indices[a] : grid.indices[a + 1]]
+        out[f"at_weights_{a}_sample"] = w[::53].copy()
+    for key in ("core_charges", "valence_charges", "valence_widths"):
+        if key in part.cache:
+            out[key] = part[key]
+    if "spherical_average_0" in part.cache:
+        out["spherical_average_0"] = part["spherical_average_0"]
+    return out
+
+
+def save(name, prefix_results, **extra):
+    flat = dict(extra)
+    for prefix, res in prefix_results.items():
+        for k, v in res.items():
+            flat[f"{prefix}/{k}"] = v
+    GOLD.mkdir(parents=True, exist_ok=True)
+    np.savez_compressed(GOLD / name, **flat)
+    print("wrote", GOLD / name, f"{(GOLD / name).stat().st_size / 1024:.0f} KiB")
+
+
+H2O_SCHEMES = {
+    "mbis": ("mbis", {}),
+    "isa": ("is", {}),
+    "lisa_sc_gauss": ("lisa", dict(solver="sc")),
+    "lisa_sc_slater": ("lisa", dict(solver="sc", basis_func="slater")),
+    "nlis": ("nlis", dict(exp_n_dict={})),
+    "gmbis": ("gmbis", dict(exp_n_dict={})),
+    "glisa_sc": ("glisa", dict(solver="sc")),
+    "mbis_gt2": ("mbis", dict(grid_type=2)),
+    "lisa_sc_gt2": ("lisa", dict(solver="sc", grid_type=2)),
+}
+
+
+def case_h2o():
+    """Config 1: water HF/STO-3G, ExpRTransform(5e-4, 2e1, 119) x 110 Lebedev (tests/test_wpart.py:38-56)."""
+    from scipy.spatial import cKDTree
+
+    npz = np.load(REF_CACHED / "water_sto3g_hf_g03_fchk_exp:5e-4:2e1:120:110.npz")
+    coords, numbers, pseudo = npz["coordinates"], npz["numbers"], npz["pseudo_numbers"]
+    rgrid = qcgrid.ExpRTransform(5e-4, 2e1, 119).transform_1d_grid(qcgrid.UniformInteger(120))
+    grid = qcgrid.MolGrid.from_size(numbers, coords, 110, rgrid, qcgrid.BeckeWeights(), rotate=False, store=True)
+    dist, order = cKDTree(npz["points"]).query(grid.points)
+    assert dist.max() < 1e-12 and len(set(order)) == grid.size
+    rho = npz["dens"][order]
+    results = {}
+    for tag, (scheme, kw) in H2O_SCHEMES.items():
+        try:
+            results[tag] = run_reference(scheme, coords, numbers, pseudo, grid, rho, **kw)
+            print(f"  h2o {tag}: niter={results[tag]['niter']} q={results[tag]['charges']}")
+        except Exception as exc:  # reference behaviour on this density (e.g. singular Newton)
+            print(f"  h2o {tag}: reference raised {type(exc).__name__}: {exc}")
+    save(
+        "h2o_hf_sto3g.npz", results, coordinates=coords, numbers=numbers, pseudo_numbers=pseudo,
+        dens=rho, aim_weights=grid.aim_weights, nelec=np.float64(grid.integrate(rho)),
+        grid_spec=np.array("ExpRTransform(5e-4,2e1,119) o UniformInteger(120) x Lebedev110, BeckeWeights()"),
+    )  # fmt: skip
+
+
+def synthetic_grid(coords, numbers, nrad, nang):
+    rgrid = qcgrid.BeckeRTransform(1e-4, 1.5).transform_1d_grid(qcgrid.GaussChebyshev(nrad))
+    return qcgrid.MolGrid.from_size(numbers, coords, nang, rgrid, qcgrid.BeckeWeights(), rotate=0, store=True)
+
+
+def case_water_cluster(natom=6, nrad=40, nang=50, seed=0):
+    """Synthetic Slater promolecule water cluster (BASELINE.md section 2 generator), small grid."""
+    coords, numbers = synthetic.water_cluster(natom, seed)
+    grid = synthetic_grid(coords, numbers, nrad, nang)
+    rho = synthetic.slater_promolecule_host(grid.points, coords, numbers)
+    pseudo = numbers.astype(float)
+    results = {}
+    for tag, (scheme, kw) in {
+        "mbis": ("mbis", {}),
+        "isa": ("is", dict(maxiter=60)),
+        "lisa_sc_gauss": ("lisa", dict(solver="sc")),
+        "nlis": ("nlis", dict(exp_n_dict={})),
+        "glisa_sc": ("glisa", dict(solver="sc", maxiter=500)),
+    }.items():
+        try:
+            results[tag] = run_reference(scheme, coords, numbers, pseudo, grid, rho, **kw)
+            print(f"  water{natom} {tag}: niter={results[tag]['niter']} q={results[tag]['charges'][:3]}")
+        except Exception as exc:
+            print(f"  water{natom} {tag}: reference raised {type(exc).__name__}: {exc}")
+    save(
+        f"water{natom}_slater.npz", results, coordinates=coords, numbers=numbers, pseudo_numbers=pseudo,
+        dens_sample=rho[::101].copy(), nelec=np.float64(grid.integrate(rho)),
+        grid_spec=np.array(f"BeckeRTransform(1e-4,1.5) o GaussChebyshev({nrad}) x Lebedev{nang}, BeckeWeights(); seed={seed}"),
+    )  # fmt: skip
+
+
+CASES = {"h2o": case_h2o, "water6": case_water_cluster}
+
+if __name__ == "__main__":
+    for name in sys.argv[1:] or CASES:
+        print("case", name)
+        CASES[name]()

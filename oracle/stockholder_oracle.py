@@ -1,0 +1,230 @@
+"""ORACLE -- TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+
+CPU (NumPy) restatement of the reference's stockholder-iteration hot path, used only by tests/,
+``__graft_entry__.smoke()`` and bench.py's ``cpu_baseline`` / ``--impl reference`` legs as the
+checker and CPU baseline.  The product package ``horton_part_b200`` never imports it.
+
+Pinning: every scheme function below is checked in tests/test_oracle_golden.py against outputs of
+the UNMODIFIED reference (/root/reference/src/horton_part run here through oracle/qcgrid_shim;
+vectors in tests/golden/, generator oracle/gen_golden.py), including the reference's own golden
+charges (tests/test_wpart.py:90-102).  Each function cites the reference lines it restates; the
+arithmetic ORDER follows the reference (sequential atom order in the promolecule, the 1e-100
+offsets, clip, masks) because the iteration count depends on it.
+
+Paths are relative to /root/reference/src/horton_part.
+"""
+
+from __future__ import annotations
+
+import numpy as np
+from scipy.special import gamma as _gamma
+
+DENSITY_CUTOFF = 1e-15  # data/constants.yaml
+
+
+# ----------------------------------------------------------------------------------------------
+# grid-level helpers (qc-grid semantics)
+# ----------------------------------------------------------------------------------------------
+def distances(points, center):
+    """core/base.py:634  np.linalg.norm(points - R_a, axis=1)."""
+    return np.linalg.norm(points - center, axis=1)
+
+
+def shell_average(atgrid, values):
+    """qc-grid AtomGrid.spherical_average evaluated at its own knots (mbis.py:179-184,
+    gisa.py:287-289): per-shell sums of f*w, divided by r^2 w_rad, zero at r<1e-8, over 4 pi."""
+    prod = values * atgrid.weights
+    idx = np.asarray(atgrid.indices)
+    sums = np.array([prod[idx[i] : idx[i + 1]].sum() for i in range(len(idx) - 1)])
+    r, w = atgrid.rgrid.points, atgrid.rgrid.weights
+    with np.errstate(divide="ignore", invalid="ignore"):
+        sums /= r**2 * w
+    sums[np.abs(r) < 1e-8] = 0.0
+    return sums / (4.0 * np.pi)
+
+
+def entropy(molw, rho, rho0, cutoff=DENSITY_CUTOFF):
+    """core/stockholder.py:145-151."""
+    sick = (rho0 < cutoff) | (rho < cutoff)
+    with np.errstate(all="ignore"):
+        ratio = np.divide(rho, rho0, out=np.zeros_like(rho), where=~sick)
+        ln_ratio = np.log(ratio, out=np.zeros_like(rho), where=~sick)
+    return np.einsum("i,i,i", molw, rho, ln_ratio)
+
+
+def stockholder_weights(grid, proatom_fn, natom, owner_only=True):
+    """core/stockholder.py:352-384 + update_pro :153-175: sequential promolecule accumulation with
+    the 1e-100 offsets, then w_a = clip(rho0_a / rho0, 0, 1) on atom a's own slice
+    (grid_type=1) or on the whole grid."""
+    promol = np.zeros(grid.size)
+    pro = []
+    for a in range(natom):
+        work = proatom_fn(a)
+        promol += work
+        promol += 1e-100
+        lo, hi = grid.indices[a], grid.indices[a + 1]
+        pro.append(work[lo:hi].copy() if owner_only else work.copy())
+    weights = []
+    for a in range(natom):
+        lo, hi = grid.indices[a], grid.indices[a + 1]
+        w = pro[a] / (promol[lo:hi] if owner_only else promol)
+        weights.append(np.clip(w, 0, 1))
+    return promol, weights
+
+
+def local_index(points, center, radius, begin, end):
+    """Row L: Grid.get_localgrid == cKDTree.query_ball_point(center, radius, p=2.0), canonicalised
+    to ascending order; spec core/stockholder.py:84-112."""
+    from scipy.spatial import cKDTree
+
+    idx = np.sort(np.asarray(cKDTree(points).query_ball_point(center, radius, p=2.0), dtype=np.int64))
+    overlap = (begin <= idx) & (idx < end)
+    dist = np.linalg.norm(points[idx] - center, axis=1)
+    return idx, overlap, dist
+
+
+# ----------------------------------------------------------------------------------------------
+# MBIS  (mbis.py)
+# ----------------------------------------------------------------------------------------------
+def mbis_nshell(number):
+    return int(np.array([2, 10, 18, 36, 54, 86, 118]).searchsorted(number) + 1)  # mbis.py:36-46
+
+
+def mbis_initial(number):
+    """mbis.py:49-78."""
+    k = mbis_nshell(number)
+    p = np.zeros(2 * k)
+    s0 = 2.0 * number
+    ratio = (2.0 / s0) ** (1.0 / (k - 1)) if k > 1 else 1.0
+    cap = [2.0, 8.0, 8.0, 18.0, 18.0, 32.0, 32.0]
+    for i in range(k):
+        p[2 * i] = cap[i]
+        p[2 * i + 1] = s0 * ratio**i
+    p[-2] = number - p[:-2:2].sum()
+    return p
+
+
+def mbis_proatom(par, r):
+    """mbis.py:279-289 (eval_proatom) / :253-261 (get_proatom_rho)."""
+    y = np.zeros(len(r))
+    for k in range(len(par) // 2):
+        N, S = par[2 * k : 2 * k + 2]
+        y += N * S**3 * np.exp(-S * r) / (8 * np.pi)
+    return y
+
+
+def mbis_inner(rho, par, weights, r, threshold, cutoff=DENSITY_CUTOFF, max_inner=2000):
+    """opt_mbis_propars, mbis.py:81-163. Returns (propars, inner iterations)."""
+    par = par.copy()
+    k = len(par) // 2
+    terms = np.zeros((k, len(r)))
+    oldpro = None
+    for irep in range(max_inner):
+        for i in range(k):
+            N, S = par[2 * i], par[2 * i + 1]
+            terms[i] = N * S**3 * np.exp(-S * r) / (8 * np.pi)
+        pro = terms.sum(axis=0)
+        sick = (rho < cutoff) | (pro < cutoff)
+        with np.errstate(all="ignore"):
+            ratio = rho / pro
+        ratio[sick] = 0.0
+        terms *= ratio
+        for i in range(k):
+            m0 = np.einsum("p,p->", weights, terms[i])
+            m1 = np.einsum("p,p,p->", weights, terms[i], r)
+            par[2 * i] = m0
+            par[2 * i + 1] = 3 * m0 / m1
+        if oldpro is None:
+            change = 1e100
+        else:
+            err = oldpro - pro
+            change = np.sqrt(np.einsum("p,p,p->", weights, err, err))
+        if change < threshold:
+            return par, irep + 1
+        oldpro = pro
+    return par, max_inner
+
+
+def _radial_change(atgrids, ranges, fn, new, old):
+    """compute_change on radial grids, core/iterstock.py:32-45."""
+    msd = 0.0
+    for a, g in enumerate(atgrids):
+        r = g.rgrid.points
+        d = fn(a, new[ranges[a] : ranges[a + 1]], r) - fn(a, old[ranges[a] : ranges[a + 1]], r)
+        msd += np.einsum("i,i,i,i", g.rgrid.weights, 4 * np.pi * r**2, d, d)
+    return np.sqrt(msd)
+
+
+def _iterate(grid, rho, natom, pseudo, propars, ranges, proatom_on_r, update_atom, threshold, maxiter,
+             cutoff=DENSITY_CUTOFF, coords=None):  # fmt: skip
+    """The outer loop of AbstractISAWPart.do_partitioning (core/iterstock.py:159-193) for
+    grid_type=1: weights from the current propars, per-atom projection + update, entropy of the
+    promolecule that was just used, change between new and old propars."""
+    dist = [distances(grid.points, coords[a]) for a in range(natom)]
+    charges = np.zeros(natom)
+    hist = {"propars": [], "charges": [], "entropies": [], "changes": [], "inner": []}
+    counter = 0
+    while True:
+        counter += 1
+        old = propars.copy()
+        promol, weights = stockholder_weights(
+            grid, lambda a: proatom_on_r(a, propars[ranges[a] : ranges[a + 1]], dist[a]), natom
+        )
+        inner = []
+        for a in range(natom):
+            g = grid.atgrids[a]
+            lo, hi = grid.indices[a], grid.indices[a + 1]
+            sph = shell_average(g, weights[a] * rho[lo:hi])
+            r = g.rgrid.points
+            w4 = 4 * np.pi * r**2 * g.rgrid.weights
+            new_a, nin = update_atom(a, sph, propars[ranges[a] : ranges[a + 1]].copy(), w4, r)
+            propars[ranges[a] : ranges[a + 1]] = new_a
+            charges[a] = pseudo[a] - np.einsum("p,p->", w4, sph)
+            inner.append(nin)
+        hist["propars"].append(propars.copy())
+        hist["charges"].append(charges.copy())
+        hist["entropies"].append(entropy(grid.weights, rho, promol, cutoff))
+        hist["inner"].append(inner)
+        change = _radial_change(grid.atgrids, ranges, proatom_on_r, propars, old)
+        hist["changes"].append(change)
+        if change < threshold or counter >= maxiter:
+            break
+    return {
+        "niter": counter,
+        "change": change,
+        "charges": charges,
+        "propars": propars,
+        "promoldens": promol,
+        "at_weights": weights,
+        "history_propars": np.array(hist["propars"]),
+        "history_charges": np.array(hist["charges"]),
+        "history_entropies": np.array(hist["entropies"]),
+        "history_changes": np.array(hist["changes"]),
+        "history_inner": hist["inner"],
+    }
+
+
+def mbis(coords, numbers, pseudo, grid, rho, threshold=1e-6, inner_threshold=1e-8, maxiter=500,
+         cutoff=DENSITY_CUTOFF):  # fmt: skip
+    """MBISWPart(...).do_partitioning(), grid_type=1 (mbis.py:167-203, 291-305)."""
+    natom = len(numbers)
+    inner_threshold = min(inner_threshold, threshold)  # core/iterstock.py:101
+    ranges = [0]
+    for z in numbers:
+        ranges.append(ranges[-1] + 2 * mbis_nshell(z))
+    propars = np.concatenate([mbis_initial(z) for z in numbers])
+    return _iterate(
+        grid, rho, natom, pseudo, propars, ranges,
+        lambda a, par, r: mbis_proatom(par, r),
+        lambda a, sph, par, w4, r: mbis_inner(sph, par, w4, r, inner_threshold, cutoff),
+        threshold, maxiter, cutoff, coords,
+    )  # fmt: skip
+
+
+# ----------------------------------------------------------------------------------------------
+# exponential basis functions (core/basis.py) -- GISA / aLISA / gLISA / NLIS
+# ----------------------------------------------------------------------------------------------
+def exp_shell(n, population, alpha, r):
+    """evaluate_function, core/basis.py:161-171:  c n alpha^(3/n) / (4 pi Gamma(3/n)) exp(-alpha r^n)."""
+    pref = population * n * alpha ** (3 / n) / (4 * np.pi * _gamma(3 / n))
+    return pref * np.exp(-alpha * r**n)

@@ -1,0 +1,42 @@
+"""Pin the oracle: the NumPy restatement must reproduce the UNMODIFIED reference's outputs
+(tests/golden/*, made by oracle/gen_golden.py) and the reference's own golden charges."""
+
+import numpy as np
+import pytest
+import stockholder_oracle as oracle
+
+
+def _check(res, gold, tag, rtol=1e-10):
+    assert res["niter"] == int(gold[f"{tag}/niter"])
+    np.testing.assert_allclose(res["charges"], gold[f"{tag}/charges"], rtol=0, atol=1e-11)
+    np.testing.assert_allclose(res["propars"], gold[f"{tag}/propars"], rtol=rtol, atol=1e-13)
+    np.testing.assert_allclose(res["history_changes"], gold[f"{tag}/history_changes"], rtol=1e-8)
+    np.testing.assert_allclose(res["history_entropies"], gold[f"{tag}/history_entropies"], rtol=1e-10)
+    np.testing.assert_allclose(res["promoldens"][::97], gold[f"{tag}/promoldens_sample"], rtol=1e-12)
+    np.testing.assert_allclose(res["at_weights"][0][::53], gold[f"{tag}/at_weights_0_sample"], rtol=1e-12, atol=1e-300)
+
+
+def test_mbis_h2o_matches_reference_run(h2o):
+    res = oracle.mbis(h2o["coords"], h2o["numbers"], h2o["pseudo"], h2o["grid"], h2o["rho"])
+    _check(res, h2o["gold"], "mbis")
+    # the reference's own golden vector, tests/test_wpart.py:95-102 (tolerance :61)
+    assert abs(res["charges"] - np.array([-0.61891067, 0.3095756, 0.30932584])).max() < 2e-3
+    assert res["niter"] == 27
+
+
+def test_mbis_water6_matches_reference_run(water6):
+    res = oracle.mbis(water6["coords"], water6["numbers"], water6["pseudo"], water6["grid"], water6["rho"])
+    _check(res, water6["gold"], "mbis")
+    # known answer: MBIS recovers the generating Slater populations
+    assert abs(res["charges"] - np.tile([-0.6, 0.3, 0.3], 2)).max() < 5e-5
+
+
+def test_mbis_known_answers():
+    # reference tests/test_mbis.py:26-41
+    assert [oracle.mbis_nshell(z) for z in (1, 2, 3, 10, 11, 18, 19, 36)] == [1, 1, 2, 2, 3, 3, 4, 4]
+    np.testing.assert_allclose(oracle.mbis_initial(1), [1.0, 2.0])
+    p = oracle.mbis_initial(8)
+    np.testing.assert_allclose(p, [2.0, 16.0, 6.0, 2.0])
+    p = oracle.mbis_initial(14)
+    assert p[0::2].sum() == pytest.approx(14.0)
+    np.testing.assert_allclose(p[1::2], [28.0, np.sqrt(56.0), 2.0])
