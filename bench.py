@@ -1,0 +1,375 @@
+#!/usr/bin/env python
+"""Benchmark of the stockholder-iteration hot path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--natom 2000] [--impl reference]
+
+Workload (config 5 of BASELINE.json): MBIS on a synthetic 2,000-atom water cluster, 150 x 194 grid
+per atom = 58.2 M points, dense all-pairs pro-atom evaluation (the reference's semantics: no
+cut-off), 1.164e11 atom x gridpoint evaluations per stockholder iteration.  A *step* is one outer
+iteration: shell table -> fused promolecule/weights/entropy kernel -> spherical averages ->
+per-atom MBIS solves -> change/entropy -> one small D2H.  Strong scaling: the same system is
+sharded by atom blocks over the ranks (NCCL all-reduce of the per-iteration state vector).
+
+Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for the definition of every field.
+"""
+
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "atom_gridpoint_evals_per_s"
+UNIT = "evals/s"
+NRAD, NANG = 150, 194
+
+
+def flops_per_eval(mean_shells):
+    """SURVEY.md section 8d counting convention for Slater shells: 16 + 36 K flop."""
+    return 16.0 + 36.0 * mean_shells
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")  # fmt: skip
+
+    def __init__(self, index):
+        self.index, self.rows, self._stop, self._thread = index, [], threading.Event(), None
+
+    def _loop(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(
+                    ["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                    capture_output=True, text=True, timeout=5,
+                ).stdout.strip()  # fmt: skip
+                if out:
+                    self.rows.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def __enter__(self):
+        self._thread = threading.Thread(target=self._loop, daemon=True)
+        self._thread.start()
+        return self
+
+    def __exit__(self, *exc):
+        self._stop.set()
+        self._thread.join(timeout=6)
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        for row in self.rows:
+            try:
+                sm.append(float(row[0]))
+                mx.append(float(row[1]))
+            except (ValueError, IndexError):
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), row[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {
+            "sm_mhz": float(np.median(sm)) if sm else None,
+            "sm_max_mhz": float(max(mx)) if mx else None,
+            "reasons": sorted(reasons),
+            "samples": len(sm),
+        }
+
+
+# ------------------------------------------------------------------------------------------------
+# system
+# ------------------------------------------------------------------------------------------------
+def build_system(natom, seed=0, nrad=NRAD, nang=NANG):
+    from horton_part_b200 import gridlite, synthetic
+
+    coords, numbers = synthetic.water_cluster(natom, seed)
+    rgrid = gridlite.BeckeRTransform(1e-4, 1.5).transform_1d_grid(gridlite.GaussChebyshev(nrad))
+    npts = natom * nrad * nang
+    grid = gridlite.MolGrid.from_size(numbers, coords, nang, rgrid, np.ones(npts), store=True)
+    return coords, numbers, grid
+
+
+def mean_shells(numbers):
+    from horton_part_b200.mbis import get_nshell
+
+    return float(np.mean([get_nshell(int(z)) for z in numbers]))
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU baseline (oracle port of the reference's per-iteration dense pass)
+# ------------------------------------------------------------------------------------------------
+def _cpu_worker(args):
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import stockholder_oracle as oracle
+
+    points, owner, coords, ranges, propars, reps = args
+    dist = [oracle.distances(points, c) for c in coords]  # cached by the reference, not timed
+    t0 = time.perf_counter()
+    evals = 0
+    for _ in range(reps):
+        _, _, n = oracle.dense_weights_pass_mbis(points, owner, coords, ranges, propars, dist)
+        evals += n
+    return evals, time.perf_counter() - t0
+
+
+def cpu_baseline(coords, numbers, grid, cores, points_per_core=16384, reps=16):
+    """Time the reference's dense update_at_weights pass (oracle port) on a bounded sample of the
+    SAME workload: every atom of the system, `points_per_core` grid points per worker process."""
+    import multiprocessing as mp
+
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import stockholder_oracle as oracle
+
+    ranges = [0]
+    for z in numbers:
+        ranges.append(ranges[-1] + 2 * oracle.mbis_nshell(int(z)))
+    propars = np.concatenate([oracle.mbis_initial(int(z)) for z in numbers])
+    natom = len(numbers)
+    rng = np.random.default_rng(0)
+    jobs = []
+    for c in range(cores):
+        a = int(rng.integers(0, natom))
+        lo = int(grid.indices[a])
+        sel = lo + np.sort(rng.choice(int(grid.indices[a + 1] - lo), size=points_per_core, replace=False))
+        jobs.append((grid.points[sel].copy(), np.full(points_per_core, a), coords, ranges, propars, reps))
+    t0 = time.perf_counter()
+    if cores == 1:
+        res = [_cpu_worker(jobs[0])]
+    else:
+        with mp.get_context("fork").Pool(cores) as pool:
+            res = pool.map(_cpu_worker, jobs)
+    wall = time.perf_counter() - t0
+    evals = sum(r[0] for r in res)
+    busy = max(r[1] for r in res)
+    return {
+        "value": evals / busy,
+        "unit": UNIT,
+        "cores": cores,
+        "kind": "port",
+        "sample": f"{natom} atoms x {points_per_core} grid points per core x {reps} pass(es), cached distances; "
+                  f"{evals:.3g} evals in {busy:.1f} s (wall {wall:.1f} s incl. process start)",
+    }  # fmt: skip
+
+
+# ------------------------------------------------------------------------------------------------
+def run_reference_arm(args, rank, world):
+    if rank != 0:
+        return
+    coords, numbers, grid = build_system(args.natom)
+    cores = os.cpu_count() or 1
+    ppc = max(1024, int(args.cpu_points))
+    for _ in range(args.warmup):
+        cpu_baseline(coords, numbers, grid, cores, points_per_core=256, reps=1)
+    t0 = time.perf_counter()
+    vals = []
+    for _ in range(args.steps):
+        vals.append(cpu_baseline(coords, numbers, grid, cores, points_per_core=ppc, reps=args.cpu_reps))
+    total = time.perf_counter() - t0
+    value = float(np.mean([v["value"] for v in vals]))
+    base = vals[-1]
+    base["value"] = value
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / max(args.steps, 1),
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic", "config": workload_config(args.natom, numbers),
+        "cpu_baseline": base,
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }  # fmt: skip
+    print(json.dumps(line))
+
+
+def workload_config(natom, numbers):
+    return {
+        "workload": f"MBIS, synthetic {natom}-atom water cluster, {NRAD}x{NANG} grid/atom, "
+                    f"{natom * NRAD * NANG} points, dense all-pairs (no cut-off), grid_type=1",
+        "natom": int(natom), "npts": int(natom * NRAD * NANG),
+        "evals_per_step": float(natom) * natom * NRAD * NANG,
+        "mean_shells_per_atom": mean_shells(numbers),
+        "l2_policy": "inputs_exceed_l2" if natom * NRAD * NANG * 48 > 126e6 else "l2_resident_small_input",
+        "sharding": "atom blocks over ranks, all-reduce of the state vector per step",
+    }  # fmt: skip
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--natom", type=int, default=2000)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--cpu-points", type=int, default=16384, help="grid points per core in the CPU sample")
+    ap.add_argument("--cpu-reps", type=int, default=16, help="passes over the CPU sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 0)
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        run_reference_arm(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    from horton_part_b200 import MBISWPart, _lib, synthetic
+    from horton_part_b200.core.device import Shard
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device; the hot path has no CPU fallback")
+    if args.warmup < 3:
+        print("[bench] note: fewer than 3 warm-up steps requested", file=sys.stderr)
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    comm = None
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+        comm = dist.group.WORLD
+
+    import logging
+
+    logging.disable(logging.INFO)
+
+    # ---- synthetic inputs (untimed): geometry + grid on the host, density / AIM weights on the GPU
+    coords, numbers, grid = build_system(args.natom)
+    natom, npts = args.natom, grid.size
+    shard = Shard(natom, grid.indices, rank, world)
+    rho_loc, w_loc, lo, hi = synthetic.slater_promolecule_device(grid, coords, numbers, device=dev, shard=shard)
+    rho = np.zeros(npts)
+    rho[lo:hi] = rho_loc
+    grid.aim_weights[lo:hi] = w_loc
+    grid.weights[lo:hi] = grid.atweights[lo:hi] * w_loc
+    del rho_loc, w_loc
+    torch.cuda.empty_cache()
+    pseudo = numbers.astype(float)
+    evals_per_step = float(natom) * float(npts)  # whole job (all ranks)
+
+    def barrier():
+        if comm is not None:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def max_over_ranks(x):
+        if comm is None:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- device-resident arm: W warm-up + K timed steps ---------------------------------------
+    nsteps = args.warmup + args.steps
+    part = MBISWPart(coords, numbers, pseudo, grid, rho, device=dev, comm=comm, maxiter=nsteps)
+    part._init_propars()  # uploads the slab, builds tables (inputs resident before timing)
+    for _ in range(args.warmup):
+        part._run_iteration()
+    part._state.events = []
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local_rank) as clocks:
+        e0.record()
+        for _ in range(args.steps):
+            change, entropy = part._run_iteration()
+        e1.record()
+        barrier()
+    ms_total = max_over_ranks(e0.elapsed_time(e1))
+    kernel_ms = [ev[0].elapsed_time(ev[1]) for ev in part._state.events]  # table + fused kernel
+    rest_ms = [ev[1].elapsed_time(ev[2]) for ev in part._state.events]
+    kernel_ms_mean = max_over_ranks(float(np.mean(kernel_ms)))
+    value = evals_per_step * args.steps / (ms_total * 1e-3)
+    charges_resident = part["charges"].copy()
+    h2d_bytes = part.slab.bytes_h2d
+    state_bytes = part._state.host.numel() * 8
+    del part
+    torch.cuda.empty_cache()
+
+    # ---- end-to-end arm: host buffers -> WPart API -> host results, copies inside the timed region
+    barrier()
+    t0 = time.perf_counter()
+    part2 = MBISWPart(coords, numbers, pseudo, grid, rho, device=dev, comm=comm, maxiter=args.steps)
+    part2.do_partitioning()  # uploads, K iterations, downloads weights/promolecule/charges
+    barrier()
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    assert part2["niter"] == args.steps
+    e2e_value = evals_per_step * args.steps / e2e_s
+    d2h_final = (2 * (hi - lo) + part2.slab.nshell) * 8
+    e2e = {
+        "value": e2e_value, "unit": UNIT,
+        "h2d_bytes_per_step": int(h2d_bytes / args.steps),
+        "d2h_bytes_per_step": int(state_bytes + d2h_final / args.steps),
+        "seconds": e2e_s, "includes": "slab upload (pageable host memory), K iterations, download of "
+        "promolecule/at_weights/spherical averages, per-step state D2H",
+    }  # fmt: skip
+    del part2
+
+    # ---- roofline denominators -------------------------------------------------------------------
+    kbar = mean_shells(numbers)
+    F = flops_per_eval(kbar)
+    sink = torch.zeros(1, dtype=torch.float64, device=dev)
+    ms_probe = np.zeros(1, np.float32)
+    fl_probe = np.zeros(1, np.float64)
+    _lib.call("hp_dfma_probe", 4096, sink, ms_probe, fl_probe, torch.cuda.current_stream(dev).cuda_stream)
+    fp64_peak_tflops = float(fl_probe[0] / (ms_probe[0] * 1e-3) / 1e12)
+    local_evals = float(natom) * float(hi - lo)
+    kernel_evals_per_s = local_evals / (kernel_ms_mean * 1e-3)
+    achieved_tflops = kernel_evals_per_s * F / 1e12
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    hbm_bytes = 56.0 * (hi - lo)  # 40 B read (x,y,z,rho,molw) + 16 B written (promol, at_w) per point
+    roofline = {
+        "bound": "fp64", "kernel": "promol_weights_kernel<SLATER>",
+        "achieved": achieved_tflops, "peak": fp64_peak_tflops, "unit": "TFLOP/s",
+        "frac": achieved_tflops / fp64_peak_tflops,
+        "peak_source": "hp_dfma_probe measured live on this GPU (nominal 148 SM x 64 lanes x 2 x 1.965 GHz = 37.2)",
+        "flop_per_eval": F, "kernel_ms": kernel_ms_mean, "kernel_evals_per_s": kernel_evals_per_s,
+        "kernel_share_of_step": kernel_ms_mean / (ms_total / args.steps),
+        "hbm_gbs_achieved": hbm_bytes / (kernel_ms_mean * 1e-3) / 1e9, "hbm_gbs_peak": hbm_peak,
+        "hbm_peak_source": "MEASURED_PEAKS.json" if peaks else "fallback 6650",
+        "traffic": None,
+    }  # fmt: skip
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic (exact Slater promolecule; AIM weights = Hirshfeld weights of the generating promolecule)",
+        "config": workload_config(natom, numbers),
+        "iterations_per_s": args.steps / (ms_total * 1e-3),
+        "clocks": clocks.summary(), "e2e": e2e, "gpu_launches": 5 * args.steps,
+        "roofline": roofline,
+        "other_kernels_ms_per_step": float(np.mean(rest_ms)),
+        "last_change": change, "last_entropy": entropy,
+        "charges_O_H_H": [float(x) for x in charges_resident[:3]],
+    }  # fmt: skip
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_baseline(coords, numbers, grid, os.cpu_count() or 1, points_per_core=args.cpu_points, reps=args.cpu_reps)
+    if rank == 0:
+        print(json.dumps(line))
+    if comm is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -228,3 +228,27 @@ def exp_shell(n, population, alpha, r):
     """evaluate_function, core/basis.py:161-171:  c n alpha^(3/n) / (4 pi Gamma(3/n)) exp(-alpha r^n)."""
     pref = population * n * alpha ** (3 / n) / (4 * np.pi * _gamma(3 / n))
     return pref * np.exp(-alpha * r**n)
+
+
+# ----------------------------------------------------------------------------------------------
+# CPU baseline leg (bench.py): the reference's per-iteration dense pass on a sample of the grid
+# ----------------------------------------------------------------------------------------------
+def dense_weights_pass_mbis(points, owner, coords, ranges, propars, dist=None):
+    """One ``update_at_weights`` of the reference (core/stockholder.py:352-384 with
+    mbis.py:279-289) restricted to ``points``: per atom K+3 NumPy passes with the *cached*
+    distances ``dist[a]`` the reference keeps (core/base.py:630-635), sequential promolecule
+    accumulation, owner weights.  Returns (promol, owner weights, atom x point evaluations)."""
+    natom = len(coords)
+    if dist is None:
+        dist = [distances(points, coords[a]) for a in range(natom)]
+    promol = np.zeros(len(points))
+    own = np.zeros(len(points))
+    for a in range(natom):
+        work = mbis_proatom(propars[ranges[a] : ranges[a + 1]], dist[a])
+        promol += work
+        promol += 1e-100
+        mine = owner == a
+        if mine.any():
+            own[mine] = work[mine]
+    w = np.clip(own / promol, 0, 1)
+    return promol, w, natom * len(points)
