@@ -2,19 +2,26 @@
 //
 // Work decomposition: one thread owns kPts grid points (strided by blockDim so loads coalesce),
 // keeps their running promolecule sums in registers, and walks over ALL atoms in reference order.
-// Atoms are staged through shared memory in tiles (coordinates + shell table), every thread of the
-// block reads the same atom at the same time, so the shared-memory reads are broadcasts.  Distances
-// are recomputed in registers: the reference's cached natom x Npts `radial_distances` table
-// (core/base.py:630-635) is never materialised.
+// Atoms are staged through shared memory in tiles (coordinates + interleaved (A, alpha) shell
+// table); every thread of the block reads the same atom at the same time, so the shared-memory
+// reads are broadcasts.  Distances are recomputed in registers: the reference's cached
+// natom x Npts `radial_distances` table (core/base.py:630-635) is never materialised.
 //
-// Bound: FP64 pipe (no FP64 SFU path for exp): ~16 + 36 K flop per atom x point evaluation for
-// Slater shells against 48 B of HBM traffic per *point*.
+// Bound: the FP64 pipe (there is no FP64 SFU path for exp): ~38 FP64 instructions per
+// atom x point evaluation at K = 4/3 shells, against 56 B of HBM traffic per *point*.  The inner
+// loop is written so that almost every issued instruction is an FP64 FMA:
+//   * sqrt and exp are inlined without library slow-path calls (MUFU.RSQ64H seed + the same
+//     3rd-order/Heron refinement the CUDA math library uses; Cody-Waite reduction + degree-11
+//     polynomial whose coefficients live in the constant bank);
+//   * the owner atom's pro-atom value is recomputed once per point after the loop instead of a
+//     compare/select per pair;
+//   * exp underflow (arg <= -708) is flushed to zero with two selects instead of a branch.
 #include "hp_common.cuh"
 
 namespace hp {
 
 constexpr int kThreads = 256;
-constexpr int kPts = 2;                 // points per thread
+constexpr int kPts = 4;                 // points per thread
 constexpr int kTileAtoms = 128;         // atoms per shared-memory tile
 constexpr int kTileShells = 1024;       // shells per shared-memory tile
 constexpr int kMaxPartials = 4096;      // size of the entropy partial-sum buffer
@@ -24,29 +31,82 @@ struct __align__(16) AtomRec {
     int s0, ns;  // first shell (tile-relative) and shell count
 };
 
-template <int F>
-__device__ __forceinline__ double eval_proatom(double d2, int s0, int ns, const double* __restrict__ sA,
-                                               const double* __restrict__ sAl,
-                                               const double* __restrict__ sN) {
-    double y = 0.0;
-    if (F == HP_FUNCTOR_GAUSS) {
-        for (int k = 0; k < ns; ++k) y += sA[s0 + k] * exp(-sAl[s0 + k] * d2);
-    } else if (F == HP_FUNCTOR_SLATER) {
-        const double r = sqrt(d2);
-        for (int k = 0; k < ns; ++k) y += sA[s0 + k] * exp(-sAl[s0 + k] * r);
-    } else {
-        const double r = sqrt(d2);
-        for (int k = 0; k < ns; ++k) {
-            const double n = sN[s0 + k];
-            const double rn = (n == 1.0) ? r : ((n == 2.0) ? r * r : pow(r, n));
-            y += sA[s0 + k] * exp(-sAl[s0 + k] * rn);
-        }
-    }
+// exp(r) = 1 + r + r^2 g(r) on |r| <= ln2/2; g interpolated at Chebyshev nodes (degree 9),
+// max relative error of the polynomial 1.6e-17 (tools/exp_poly.py).
+__constant__ double c_expg[10] = {
+    0.5000000000000001,     0.16666666666666669,   0.04166666666662413,   0.008333333333330062,
+    0.0013888888917213717,  0.00019841269863053618, 2.4801521295954376e-05, 2.7557268459997064e-06,
+    2.7620088445409746e-07, 2.510038549551032e-08};
+
+__device__ __forceinline__ double rsqrt_seed(double x) {
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
     return y;
 }
 
+// sqrt of a finite d2 >= 0 to within 1 ulp, no slow-path call; d2 below the normal range -> 0.
+__device__ __forceinline__ double sqrt_nocall(double d2) {
+    double y = rsqrt_seed(d2);
+    const double e = fma(d2, -(y * y), 1.0);
+    const double p = fma(e, 0.375, 0.5);
+    y = fma(p, y * e, y);                       // 1/sqrt(d2), ~2^-40
+    const double g = d2 * y;
+    const double h = __hiloint2double(__double2hiint(y) - 0x00100000, __double2loint(y));  // y/2
+    const double r = fma(fma(-g, g, d2), h, g);  // Heron step
+    return (__double2hiint(d2) < 0x00100000) ? 0.0 : r;
+}
+
+// exp(x) for x <= 0 (pro-atom exponents are never positive), branch-free.  Arguments at or below
+// -708 (results below 3.4e-308, i.e. np.exp's last normal binade and its denormals) return exactly
+// 0: such terms are absorbed by the reference's own +1e-100 offsets, so the promolecule is
+// unchanged; the absolute error of any single pro-atom value is < 3.4e-308.
+__device__ __forceinline__ double exp_neg(double x) {
+    const double t = fma(x, 1.4426950408889634, 6755399441055744.0);
+    const int k = __double2loint(t);
+    const double kd = t - 6755399441055744.0;
+    double r = fma(kd, -6.93147180559945286e-01, x);
+    r = fma(kd, -2.31904681384629956e-17, r);
+    double g = c_expg[9];
+#pragma unroll
+    for (int i = 8; i >= 0; --i) g = fma(g, r, c_expg[i]);
+    double p = fma(g, r, 1.0);
+    p = fma(p, r, 1.0);
+    const bool tiny = static_cast<unsigned>(__double2hiint(x)) >= 0xC0862000u;  // x <= -708 (or NaN<0)
+    const int hi = tiny ? 0 : __double2hiint(p) + (k << 20);
+    const int lo = tiny ? 0 : __double2loint(p);
+    return __hiloint2double(hi, lo);
+}
+
+// Pro-atom density of one atom at kP points (squared distances d2[]).  Shell parameters are read
+// once per shell for all points.
+template <int F, int kP>
+__device__ __forceinline__ void eval_proatom(const double (&d2)[kP], int s0, int ns,
+                                             const double2* __restrict__ sAB,
+                                             const double* __restrict__ sN, double (&f)[kP]) {
+    double r[kP];
+#pragma unroll
+    for (int j = 0; j < kP; ++j) {
+        f[j] = 0.0;
+        r[j] = (F == HP_FUNCTOR_GAUSS) ? d2[j] : sqrt_nocall(d2[j]);
+    }
+    for (int k = 0; k < ns; ++k) {
+        const double2 ab = sAB[s0 + k];  // (A, alpha)
+        if (F == HP_FUNCTOR_GENERAL) {
+            const double n = sN[s0 + k];
+#pragma unroll
+            for (int j = 0; j < kP; ++j) {
+                const double rn = (n == 1.0) ? r[j] : ((n == 2.0) ? r[j] * r[j] : pow(r[j], n));
+                f[j] = fma(ab.x, exp(-ab.y * rn), f[j]);
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < kP; ++j) f[j] = fma(ab.x, exp_neg(-ab.y * r[j]), f[j]);
+        }
+    }
+}
+
 template <int F>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, 2)
 promol_weights_kernel(int64_t npts, const double* __restrict__ px, const double* __restrict__ py,
                       const double* __restrict__ pz, int64_t point_base, int natom,
                       const double* __restrict__ atom_xyz, const int64_t* __restrict__ atom_pt_off,
@@ -57,8 +117,7 @@ promol_weights_kernel(int64_t npts, const double* __restrict__ px, const double*
                       double* __restrict__ promol_out, double* __restrict__ w_out,
                       double* __restrict__ entropy_partials) {
     __shared__ AtomRec s_atoms[kTileAtoms];
-    __shared__ double s_A[kTileShells];
-    __shared__ double s_Al[kTileShells];
+    __shared__ double2 s_AB[kTileShells];
     __shared__ double s_N[(F == HP_FUNCTOR_GENERAL) ? kTileShells : 1];
     __shared__ double s_red[32];
 
@@ -67,27 +126,16 @@ promol_weights_kernel(int64_t npts, const double* __restrict__ px, const double*
     double entropy_acc = 0.0;
 
     for (int64_t chunk = blockIdx.x; chunk < nchunk; chunk += gridDim.x) {
-        double x[kPts], y[kPts], z[kPts], pro[kPts], own[kPts];
-        int owner[kPts];
-        bool live[kPts];
+        double x[kPts], y[kPts], z[kPts], pro[kPts];
+        int64_t q[kPts];
 #pragma unroll
         for (int j = 0; j < kPts; ++j) {
             const int64_t p = chunk * span + int64_t(j) * kThreads + threadIdx.x;
-            live[j] = p < npts;
-            const int64_t q = live[j] ? p : (npts - 1);
-            x[j] = px[q];
-            y[j] = py[q];
-            z[j] = pz[q];
+            q[j] = p < npts ? p : (npts - 1);  // tail lanes recompute the last point, never store
+            x[j] = px[q[j]];
+            y[j] = py[q[j]];
+            z[j] = pz[q[j]];
             pro[j] = 0.0;
-            own[j] = 0.0;
-            // owner = last atom whose first point is <= global index (empty slices are skipped)
-            const int64_t g = point_base + q;
-            int lo = 0, hi = natom;  // invariant: atom_pt_off[lo] <= g < atom_pt_off[hi]
-            while (hi - lo > 1) {
-                const int mid = (lo + hi) >> 1;
-                if (atom_pt_off[mid] <= g) lo = mid; else hi = mid;
-            }
-            owner[j] = lo;
         }
 
         for (int t = 0; t < ntile; ++t) {
@@ -104,35 +152,62 @@ promol_weights_kernel(int64_t npts, const double* __restrict__ px, const double*
                 s_atoms[i] = rec;
             }
             for (int i = threadIdx.x; i < sh1 - sh0; i += kThreads) {
-                s_A[i] = shell_A[sh0 + i];
-                s_Al[i] = shell_alpha[sh0 + i];
+                s_AB[i] = make_double2(shell_A[sh0 + i], shell_alpha[sh0 + i]);
                 if (F == HP_FUNCTOR_GENERAL) s_N[i] = shell_order[sh0 + i];
             }
             __syncthreads();
 
             for (int i = 0; i < a1 - a0; ++i) {
                 const AtomRec rec = s_atoms[i];
-                const int a = a0 + i;
+                double d2[kPts], f[kPts];
 #pragma unroll
                 for (int j = 0; j < kPts; ++j) {
                     const double dx = x[j] - rec.x, dy = y[j] - rec.y, dz = z[j] - rec.z;
-                    const double d2 = dx * dx + dy * dy + dz * dz;
-                    const double f = eval_proatom<F>(d2, rec.s0, rec.ns, s_A, s_Al, s_N);
-                    // update_pro, core/stockholder.py:169-170: promoldens += work; += 1e-100
-                    pro[j] = (pro[j] + f) + 1e-100;
-                    if (a == owner[j]) own[j] = f;
+                    d2[j] = fma(dz, dz, fma(dy, dy, dx * dx));
                 }
+                eval_proatom<F, kPts>(d2, rec.s0, rec.ns, s_AB, s_N, f);
+                // update_pro, core/stockholder.py:169-170: promoldens += work; += 1e-100
+#pragma unroll
+                for (int j = 0; j < kPts; ++j) pro[j] = (pro[j] + f[j]) + 1e-100;
             }
         }
 
+        // Epilogue per point: owner atom's pro-atom (recomputed with the same code path, hence
+        // bit-identical to the value that entered the sum), weight, entropy term.
 #pragma unroll
         for (int j = 0; j < kPts; ++j) {
-            if (!live[j]) continue;
             const int64_t p = chunk * span + int64_t(j) * kThreads + threadIdx.x;
+            if (p >= npts) continue;
             if (promol_out) promol_out[p] = pro[j];
             if (w_out) {
+                const int64_t g = point_base + p;
+                int lo = 0, hi = natom;  // invariant: atom_pt_off[lo] <= g < atom_pt_off[hi]
+                while (hi - lo > 1) {
+                    const int mid = (lo + hi) >> 1;
+                    if (atom_pt_off[mid] <= g) lo = mid; else hi = mid;
+                }
+                const double dx = x[j] - atom_xyz[3 * lo + 0], dy = y[j] - atom_xyz[3 * lo + 1],
+                             dz = z[j] - atom_xyz[3 * lo + 2];
+                double d2[1] = {fma(dz, dz, fma(dy, dy, dx * dx))}, own[1];
+                const int s0 = atom_sh_off[lo], ns = atom_sh_off[lo + 1] - s0;
+                // shell parameters straight from global memory (same values as the tile copy)
+                double fo = 0.0;
+                {
+                    const double r = (F == HP_FUNCTOR_GAUSS) ? d2[0] : sqrt_nocall(d2[0]);
+                    for (int k = 0; k < ns; ++k) {
+                        const double A = shell_A[s0 + k], al = shell_alpha[s0 + k];
+                        if (F == HP_FUNCTOR_GENERAL) {
+                            const double n = shell_order[s0 + k];
+                            const double rn = (n == 1.0) ? r : ((n == 2.0) ? r * r : pow(r, n));
+                            fo = fma(A, exp(-al * rn), fo);
+                        } else {
+                            fo = fma(A, exp_neg(-al * r), fo);
+                        }
+                    }
+                }
+                own[0] = fo;
                 // core/stockholder.py:376-377: w /= promol; clip to [0, 1]
-                double w = own[j] / pro[j];
+                double w = own[0] / pro[j];
                 w = fmin(fmax(w, 0.0), 1.0);
                 w_out[p] = w;
             }
