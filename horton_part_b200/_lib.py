@@ -13,7 +13,9 @@ import pathlib
 __all__ = ["lib", "call", "ptr", "EXPORTS", "library_path", "HpError"]
 
 _PKG = pathlib.Path(__file__).resolve().parent
-_LIBPATH = _PKG / "libhp_b200.so"
+import os as _os
+
+_LIBPATH = pathlib.Path(_os.environ.get("HP_B200_LIB", _PKG / "libhp_b200.so"))  # override: tuning builds only
 
 _p = C.c_void_p
 _i32 = C.c_int32

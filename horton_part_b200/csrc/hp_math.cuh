@@ -1,0 +1,62 @@
+// FP64 device math for the hot kernels: no-call sqrt and exp for non-positive arguments.
+// Accuracy of every routine is measured by tools/fp64_probe.cu (run on the B200; results quoted
+// in DESIGN.md).
+#pragma once
+
+#include <cuda_runtime.h>
+
+namespace hp {
+
+// exp(r) = 1 + r + r^2 g(r) on |r| <= ln2/2; g interpolated at Chebyshev nodes (degree 9),
+// max relative error of the polynomial 1.6e-17.
+__constant__ double c_expg[10] = {
+    0.5000000000000001,     0.16666666666666669,   0.04166666666662413,   0.008333333333330062,
+    0.0013888888917213717,  0.00019841269863053618, 2.4801521295954376e-05, 2.7557268459997064e-06,
+    2.7620088445409746e-07, 2.510038549551032e-08};
+
+__device__ __forceinline__ double rsqrt_seed(double x) {
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    return y;
+}
+
+// sqrt of a finite d2 >= 0 without a slow-path call: MUFU.RSQ64H seed (2^-20 measured), one
+// coupled Goldschmidt step, one Heron step = 1 DMUL + 5 DFMA.  d2 below the normal range (a grid
+// point sitting on a nucleus) -> 0.
+__device__ __forceinline__ double sqrt_nocall(double d2) {
+    const double y = rsqrt_seed(d2);
+    double g = d2 * y;                                                               // ~sqrt(d2)
+    double h = __hiloint2double(__double2hiint(y) - 0x00100000, __double2loint(y));  // y/2
+    const double e = fma(-g, h, 0.5);
+    g = fma(g, e, g);
+    h = fma(h, e, h);
+    const double r = fma(fma(-g, g, d2), h, g);  // Heron step
+    return (__double2hiint(d2) < 0x00100000) ? 0.0 : r;
+}
+
+// x <= -708 (or a negative NaN): results at or below 3.4e-308 are flushed to exactly 0.  Such
+// terms are absorbed by the reference's own +1e-100 offsets, so promolecule sums are unchanged;
+// the absolute error of a single pro-atom value is < 3.4e-308.
+__device__ __forceinline__ bool exp_arg_tiny(double x) {
+    return static_cast<unsigned>(__double2hiint(x)) >= 0xC0862000u;
+}
+
+// exp(x) for x <= 0, branch-free: Cody-Waite reduction by ln2, degree-11 polynomial (16 FP64 ops).
+__device__ __forceinline__ double exp_neg_poly(double x) {
+    const double t = fma(x, 1.4426950408889634, 6755399441055744.0);
+    const int k = __double2loint(t);
+    const double kd = t - 6755399441055744.0;
+    double r = fma(kd, -6.93147180559945286e-01, x);
+    r = fma(kd, -2.31904681384629956e-17, r);
+    double g = c_expg[9];
+#pragma unroll
+    for (int i = 8; i >= 0; --i) g = fma(g, r, c_expg[i]);
+    double p = fma(g, r, 1.0);
+    p = fma(p, r, 1.0);
+    const bool tiny = exp_arg_tiny(x);
+    const int hi = tiny ? 0 : __double2hiint(p) + (k << 20);
+    const int lo = tiny ? 0 : __double2loint(p);
+    return __hiloint2double(hi, lo);
+}
+
+}  // namespace hp

@@ -10,18 +10,33 @@
 // Bound: the FP64 pipe (there is no FP64 SFU path for exp): ~38 FP64 instructions per
 // atom x point evaluation at K = 4/3 shells, against 56 B of HBM traffic per *point*.  The inner
 // loop is written so that almost every issued instruction is an FP64 FMA:
-//   * sqrt and exp are inlined without library slow-path calls (MUFU.RSQ64H seed + the same
-//     3rd-order/Heron refinement the CUDA math library uses; Cody-Waite reduction + degree-11
-//     polynomial whose coefficients live in the constant bank);
+//   * sqrt and exp are inlined without library slow-path calls (MUFU.RSQ64H seed + Goldschmidt and
+//     Heron steps; Cody-Waite reduction + degree-11 polynomial with constant-bank coefficients);
 //   * the owner atom's pro-atom value is recomputed once per point after the loop instead of a
 //     compare/select per pair;
 //   * exp underflow (arg <= -708) is flushed to zero with two selects instead of a branch.
 #include "hp_common.cuh"
+#include "hp_math.cuh"
+
+// Tuning notes (B200, config 5, ms per iteration): library sqrt()/exp() with 2 points/thread 491;
+// inlined no-call sqrt/exp, 4 points/thread 316; 6-op sqrt 305; first shell peeled + next atom
+// prefetched from shared memory one iteration ahead ~293.  Table-driven exp variants (16/32/64
+// entries in shared memory, 11-13 FP64 ops instead of 16) were slower (362/352/346): the per-lane
+// 8-byte shared loads and index arithmetic cost more issue slots than the DFMAs they save.
+#ifndef HP_PTS
+#define HP_PTS 4
+#endif
+#ifndef HP_THREADS
+#define HP_THREADS 256
+#endif
+#ifndef HP_MINBLOCKS
+#define HP_MINBLOCKS 2
+#endif
 
 namespace hp {
 
-constexpr int kThreads = 256;
-constexpr int kPts = 4;                 // points per thread
+constexpr int kThreads = HP_THREADS;
+constexpr int kPts = HP_PTS;            // points per thread
 constexpr int kTileAtoms = 128;         // atoms per shared-memory tile
 constexpr int kTileShells = 1024;       // shells per shared-memory tile
 constexpr int kMaxPartials = 4096;      // size of the entropy partial-sum buffer
@@ -31,82 +46,45 @@ struct __align__(16) AtomRec {
     int s0, ns;  // first shell (tile-relative) and shell count
 };
 
-// exp(r) = 1 + r + r^2 g(r) on |r| <= ln2/2; g interpolated at Chebyshev nodes (degree 9),
-// max relative error of the polynomial 1.6e-17 (tools/exp_poly.py).
-__constant__ double c_expg[10] = {
-    0.5000000000000001,     0.16666666666666669,   0.04166666666662413,   0.008333333333330062,
-    0.0013888888917213717,  0.00019841269863053618, 2.4801521295954376e-05, 2.7557268459997064e-06,
-    2.7620088445409746e-07, 2.510038549551032e-08};
-
-__device__ __forceinline__ double rsqrt_seed(double x) {
-    double y;
-    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
-    return y;
-}
-
-// sqrt of a finite d2 >= 0 to within 1 ulp, no slow-path call; d2 below the normal range -> 0.
-__device__ __forceinline__ double sqrt_nocall(double d2) {
-    double y = rsqrt_seed(d2);
-    const double e = fma(d2, -(y * y), 1.0);
-    const double p = fma(e, 0.375, 0.5);
-    y = fma(p, y * e, y);                       // 1/sqrt(d2), ~2^-40
-    const double g = d2 * y;
-    const double h = __hiloint2double(__double2hiint(y) - 0x00100000, __double2loint(y));  // y/2
-    const double r = fma(fma(-g, g, d2), h, g);  // Heron step
-    return (__double2hiint(d2) < 0x00100000) ? 0.0 : r;
-}
-
-// exp(x) for x <= 0 (pro-atom exponents are never positive), branch-free.  Arguments at or below
-// -708 (results below 3.4e-308, i.e. np.exp's last normal binade and its denormals) return exactly
-// 0: such terms are absorbed by the reference's own +1e-100 offsets, so the promolecule is
-// unchanged; the absolute error of any single pro-atom value is < 3.4e-308.
-__device__ __forceinline__ double exp_neg(double x) {
-    const double t = fma(x, 1.4426950408889634, 6755399441055744.0);
-    const int k = __double2loint(t);
-    const double kd = t - 6755399441055744.0;
-    double r = fma(kd, -6.93147180559945286e-01, x);
-    r = fma(kd, -2.31904681384629956e-17, r);
-    double g = c_expg[9];
-#pragma unroll
-    for (int i = 8; i >= 0; --i) g = fma(g, r, c_expg[i]);
-    double p = fma(g, r, 1.0);
-    p = fma(p, r, 1.0);
-    const bool tiny = static_cast<unsigned>(__double2hiint(x)) >= 0xC0862000u;  // x <= -708 (or NaN<0)
-    const int hi = tiny ? 0 : __double2hiint(p) + (k << 20);
-    const int lo = tiny ? 0 : __double2loint(p);
-    return __hiloint2double(hi, lo);
+// Pro-atom density of one atom at kP points (squared distances d2[]).  Shell parameters are read
+// once per shell for all points.
+template <int F>
+__device__ __forceinline__ double shell_value(double2 ab, double n, double r) {
+    if (F == HP_FUNCTOR_GENERAL) {
+        const double rn = (n == 1.0) ? r : ((n == 2.0) ? r * r : pow(r, n));
+        return exp(-ab.y * rn);
+    }
+    return exp_neg_poly(-ab.y * r);
 }
 
 // Pro-atom density of one atom at kP points (squared distances d2[]).  Shell parameters are read
-// once per shell for all points.
+// once per shell for all points; the first shell's (A, alpha) arrives in registers (ab0).
 template <int F, int kP>
 __device__ __forceinline__ void eval_proatom(const double (&d2)[kP], int s0, int ns,
                                              const double2* __restrict__ sAB,
-                                             const double* __restrict__ sN, double (&f)[kP]) {
+                                             const double* __restrict__ sN, double (&f)[kP],
+                                             double2 ab0) {
     double r[kP];
 #pragma unroll
     for (int j = 0; j < kP; ++j) {
         f[j] = 0.0;
         r[j] = (F == HP_FUNCTOR_GAUSS) ? d2[j] : sqrt_nocall(d2[j]);
     }
-    for (int k = 0; k < ns; ++k) {
+    if (ns > 0) {
+        const double n0 = (F == HP_FUNCTOR_GENERAL) ? sN[s0] : 1.0;
+#pragma unroll
+        for (int j = 0; j < kP; ++j) f[j] = fma(ab0.x, shell_value<F>(ab0, n0, r[j]), f[j]);
+    }
+    for (int k = 1; k < ns; ++k) {
         const double2 ab = sAB[s0 + k];  // (A, alpha)
-        if (F == HP_FUNCTOR_GENERAL) {
-            const double n = sN[s0 + k];
+        const double n = (F == HP_FUNCTOR_GENERAL) ? sN[s0 + k] : 1.0;
 #pragma unroll
-            for (int j = 0; j < kP; ++j) {
-                const double rn = (n == 1.0) ? r[j] : ((n == 2.0) ? r[j] * r[j] : pow(r[j], n));
-                f[j] = fma(ab.x, exp(-ab.y * rn), f[j]);
-            }
-        } else {
-#pragma unroll
-            for (int j = 0; j < kP; ++j) f[j] = fma(ab.x, exp_neg(-ab.y * r[j]), f[j]);
-        }
+        for (int j = 0; j < kP; ++j) f[j] = fma(ab.x, shell_value<F>(ab, n, r[j]), f[j]);
     }
 }
 
 template <int F>
-__global__ void __launch_bounds__(kThreads, 2)
+__global__ void __launch_bounds__(kThreads, HP_MINBLOCKS)
 promol_weights_kernel(int64_t npts, const double* __restrict__ px, const double* __restrict__ py,
                       const double* __restrict__ pz, int64_t point_base, int natom,
                       const double* __restrict__ atom_xyz, const int64_t* __restrict__ atom_pt_off,
@@ -116,7 +94,7 @@ promol_weights_kernel(int64_t npts, const double* __restrict__ px, const double*
                       const double* __restrict__ molw, double density_cutoff,
                       double* __restrict__ promol_out, double* __restrict__ w_out,
                       double* __restrict__ entropy_partials) {
-    __shared__ AtomRec s_atoms[kTileAtoms];
+    __shared__ AtomRec s_atoms[kTileAtoms + 1];  // +1: sentinel for the prefetch
     __shared__ double2 s_AB[kTileShells];
     __shared__ double s_N[(F == HP_FUNCTOR_GENERAL) ? kTileShells : 1];
     __shared__ double s_red[32];
@@ -151,21 +129,32 @@ promol_weights_kernel(int64_t npts, const double* __restrict__ px, const double*
                 rec.ns = atom_sh_off[a0 + i + 1] - atom_sh_off[a0 + i];
                 s_atoms[i] = rec;
             }
+            if (threadIdx.x == 0) {
+                AtomRec sentinel = {0.0, 0.0, 0.0, 0, 0};
+                s_atoms[a1 - a0] = sentinel;
+            }
             for (int i = threadIdx.x; i < sh1 - sh0; i += kThreads) {
                 s_AB[i] = make_double2(shell_A[sh0 + i], shell_alpha[sh0 + i]);
                 if (F == HP_FUNCTOR_GENERAL) s_N[i] = shell_order[sh0 + i];
             }
             __syncthreads();
 
+            // software pipelining: the next atom's record and first shell are fetched from shared
+            // memory one iteration ahead so their latency never sits on the FP64 critical path
+            AtomRec nxt = s_atoms[0];
+            double2 nxt_ab = s_AB[nxt.s0];
             for (int i = 0; i < a1 - a0; ++i) {
-                const AtomRec rec = s_atoms[i];
+                const AtomRec rec = nxt;
+                const double2 ab0 = nxt_ab;
+                nxt = s_atoms[i + 1];          // entry [a1-a0] is a sentinel
+                nxt_ab = s_AB[nxt.s0];
                 double d2[kPts], f[kPts];
 #pragma unroll
                 for (int j = 0; j < kPts; ++j) {
                     const double dx = x[j] - rec.x, dy = y[j] - rec.y, dz = z[j] - rec.z;
                     d2[j] = fma(dz, dz, fma(dy, dy, dx * dx));
                 }
-                eval_proatom<F, kPts>(d2, rec.s0, rec.ns, s_AB, s_N, f);
+                eval_proatom<F, kPts>(d2, rec.s0, rec.ns, s_AB, s_N, f, ab0);
                 // update_pro, core/stockholder.py:169-170: promoldens += work; += 1e-100
 #pragma unroll
                 for (int j = 0; j < kPts; ++j) pro[j] = (pro[j] + f[j]) + 1e-100;
@@ -201,7 +190,7 @@ promol_weights_kernel(int64_t npts, const double* __restrict__ px, const double*
                             const double rn = (n == 1.0) ? r : ((n == 2.0) ? r * r : pow(r, n));
                             fo = fma(A, exp(-al * rn), fo);
                         } else {
-                            fo = fma(A, exp_neg(-al * r), fo);
+                            fo = fma(A, exp_neg_poly(-al * r), fo);
                         }
                     }
                 }
