@@ -46,6 +46,14 @@ EXPORTS = {
         _int,
         [_i32, _i32, _p, _p, _p, _p, _p, _p, _p, _f64, _f64, _i32, _p, _p, _p, _p, _p],
     ),
+    "hp_nlis_radial_solve": (
+        _int,
+        [_i32, _i32, _p, _p, _p, _p, _p, _p, _p, _p, _p, _f64, _f64, _i32, _p, _p, _p, _p, _p],
+    ),
+    "hp_lisa_sc_radial_solve": (
+        _int,
+        [_i32, _i32, _p, _p, _p, _p, _p, _p, _p, _p, _f64, _f64, _f64, _i32, _i32, _i32, _i32, _p, _p, _p, _p, _p],
+    ),
     "hp_finish_iteration": (_int, [_i32, _p, _i32, _p, _p, _p]),
     "hp_sum_partials": (_int, [_i32, _p, _p, _p]),
     "hp_segment_integrate": (_int, [_i32, _p, _p, _p, _p, _p, _p]),

@@ -1,0 +1,130 @@
+"""Linear ISA with local (per-atom) solvers: aLISA.
+
+Counterpart of the reference's ``LinearISAWPart`` (alisa.py:1155-1335).  Built-in solvers that run
+as CUDA kernels (one warp per atom, all atoms in one launch):
+
+    "sc"         self-consistent fixed point to ``inner_threshold``        (alisa.py:193-291)
+    "sc-1-iter"  a single fixed-point update per outer iteration           (alisa.py:294-353)
+
+A callable ``solver`` keeps the reference's plug-in signature
+``solver(bs_funcs, rho, propars, points, weights, threshold, logger, density_cutoff=...,
+negative_cutoff=..., population_cutoff=..., **solver_options)`` (alisa.py:1304-1335) and runs on the
+host on the projected radial densities.  The remaining built-in names of the reference ("cvxopt",
+"diis", "newton", ...) are small dense host solvers around third-party packages and are not part
+of the accelerated path; requesting them raises NotImplementedError.
+"""
+
+from __future__ import annotations
+
+import numpy as np
+
+from . import _lib
+from .core.basis import AnalyticBasisFuncHelper, ExpBasisFuncHelper
+from .core.logging import deflist
+from .gisa import GaussianISAWPart
+
+__all__ = ["LinearISAWPart", "setup_bs_helper"]
+
+
+def setup_bs_helper(part):
+    """Resolve ``part.basis_func`` ("gauss", "slater", a file name, or a helper instance)."""
+    if part._bs_helper is None:
+        bf = part.basis_func
+        if isinstance(bf, str):
+            if bf.lower() in ("gauss", "slater"):
+                part.logger.info(f"Load {bf.upper()} basis functions")
+                if part.basis_type != "analytic":
+                    if part.basis_type == "numeric":
+                        raise NotImplementedError("numeric (spline) basis functions are not built yet")
+                    raise RuntimeError("The bs_type should be one of analytic and numeric.")
+                part._bs_helper = ExpBasisFuncHelper.from_function_type(bf.lower())
+            else:
+                part.logger.info(f"Load basis functions from custom json file: {bf}")
+                part._bs_helper = ExpBasisFuncHelper.from_file(bf)
+        elif isinstance(bf, AnalyticBasisFuncHelper):
+            part._bs_helper = bf
+        else:
+            raise NotImplementedError("The type of basis_func should be one of string or class BasisFuncHelper.")
+    return part._bs_helper
+
+
+class LinearISAWPart(GaussianISAWPart):
+    name = "lisa"
+    # name -> (max inner iterations option, single update?)
+    device_solvers = {"sc": ("max_niter_inner", False), "sc-1-iter": (None, True)}
+    reference_solvers = ("cvxopt", "sc", "diis", "newton", "m-newton", "quasi-newton", "trust-region",
+                         "sc-1-iter", "sc-plus-convex", "cdiis")  # fmt: skip
+
+    def __init__(self, coordinates, numbers, pseudo_numbers, grid, moldens, spindens=None, lmax=3,
+                 logger=None, threshold=1e-6, maxiter=500, inner_threshold=1e-8,
+                 radius_cutoff=np.inf, solver="cvxopt", solver_options=None, basis_func="gauss",
+                 basis_type="analytic", grid_type=1, **kwargs):  # fmt: skip
+        self.basis_func = basis_func
+        self._func_type = basis_func.upper() if basis_func in ("gauss", "slater") else "Customized"
+        self.basis_type = basis_type
+        self._bs_helper = None
+        super().__init__(coordinates, numbers, pseudo_numbers, grid, moldens, spindens, lmax, logger,
+                         threshold, maxiter, inner_threshold, radius_cutoff, solver, solver_options,
+                         grid_type, **kwargs)  # fmt: skip
+        if self.grid_type not in [1]:
+            self.logger.info(
+                f"The grid type is {self.grid_type} and please set `check_mono` to `False` when using aLISA+- methods."
+            )
+
+    @property
+    def bs_helper(self):
+        return setup_bs_helper(self)
+
+    def _init_log_scheme(self):
+        info = [
+            ("Scheme", "Linear Iterative Stockholder"),
+            ("Outer loop convergence threshold", "%.1e" % self._threshold),
+            ("Inner loop convergence threshold", "%.1e" % self._inner_threshold),
+            ("Using global ISA", False),
+            ("Maximum outer iterations", self._maxiter),
+            ("lmax", self._lmax),
+            ("Solver", self._solver.__name__ if callable(self._solver) else self._solver.upper()),
+            ("Basis function type", self._func_type),
+            ("Grid type", self.grid_type),
+        ]
+        info += [(f"Solver options -- {k}", str(v)) for k, v in self._solver_options.items()]
+        deflist(self.logger, info)
+        self.logger.info(" ")
+
+    def _launch_device_solver(self, spec):
+        from .core.device import stream_ptr
+
+        opt_name, single = spec
+        max_inner = 1 if single else int(float(self._solver_options.get(opt_name, 100000)))
+        slab, st = self.slab, self._state
+        sh = slab.shard
+        _lib.call(
+            "hp_lisa_sc_radial_solve", sh.nlocal, sh.atom_lo, slab.rad_offsets, slab.rad_w4, slab.sph_avg,
+            self._par_offsets, st.propars, self._bs_offsets, self._bs_flat, self._pseudo,
+            float(self._inner_threshold), float(self.density_cutoff), float(self.population_cutoff),
+            max_inner, int(single), self._nrad_max, self._nshell_max, st.charges, st.msd, st.niter,
+            st.flags, stream_ptr(slab.device),
+        )  # fmt: skip
+
+    def _opt_propars(self, bs_funcs, rho, propars, points, weights, alphas, threshold):
+        if not callable(self._solver):
+            if self._solver in self.reference_solvers:
+                raise NotImplementedError(
+                    f"aLISA solver {self._solver!r} is a host-side solver of the reference that is outside "
+                    "the accelerated path; use 'sc', 'sc-1-iter' or pass a callable"
+                )
+            raise NotImplementedError
+        return self._solver(
+            bs_funcs, rho, propars, points, weights, threshold, self.logger,
+            density_cutoff=self.density_cutoff, negative_cutoff=self.negative_cutoff,
+            population_cutoff=self.population_cutoff, **self._solver_options,
+        )  # fmt: skip
+
+    def _finalize_propars(self):
+        GaussianISAWPart._finalize_propars(self)
+        if not callable(self._solver) and self._solver == "sc":
+            flags = self._state.flags.cpu().numpy()
+            if (flags & 1).any():
+                self.logger.warning("Warning: Inner iteration is not converge!")
+            if (flags & 2).any():
+                self.logger.warning("WARNING: The sum of pro-atom parameters is not equal to reference population.")

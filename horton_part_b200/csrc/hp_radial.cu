@@ -200,6 +200,256 @@ mbis_radial_kernel(int natom, int atom_base, const int* __restrict__ rad_off, co
 }
 
 // ---------------------------------------------------------------------------------------------
+// NLIS / GMBIS radial fixed point (nlis.py:99-194), one warp per atom.  Shells are (N, S, n) with
+// n fixed; inv_gamma[k] = 1/Gamma(3/n_k) comes from the host.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ double pow_order(double r, double n) {
+    return (n == 1.0) ? r : ((n == 2.0) ? r * r : pow(r, n));
+}
+
+__global__ void __launch_bounds__(32)
+nlis_radial_kernel(int natom, int atom_base, const int* __restrict__ rad_off,
+                   const double* __restrict__ rad_r, const double* __restrict__ rad_w4,
+                   const double* __restrict__ sph, const int* __restrict__ par_off,
+                   double* __restrict__ propars, const int* __restrict__ shell_off,
+                   const double* __restrict__ inv_gamma, const double* __restrict__ pseudo,
+                   double threshold, double density_cutoff, int max_inner,
+                   double* __restrict__ charges, double* __restrict__ msd,
+                   int* __restrict__ niter_out, uint32_t* __restrict__ flags_out) {
+    extern __shared__ double smem[];
+    if (int(blockIdx.x) >= natom) return;
+    const int a = atom_base + blockIdx.x;
+    const int lane = threadIdx.x;
+    const int r0 = rad_off[blockIdx.x], nrad = rad_off[blockIdx.x + 1] - r0;
+    const int p0 = par_off[a], K = (par_off[a + 1] - p0) / 3;
+    const double* r = rad_r + r0;
+    const double* w = rad_w4 + r0;
+    const double* rho = sph + r0;
+    const double* ig = inv_gamma + shell_off[a];
+    double* oldpro = smem;
+
+    double N[kMaxMbisShells], S[kMaxMbisShells], n[kMaxMbisShells], N0[kMaxMbisShells],
+        S0[kMaxMbisShells], G[kMaxMbisShells];
+#pragma unroll
+    for (int k = 0; k < kMaxMbisShells; ++k) {
+        N[k] = S[k] = 0.0;
+        n[k] = G[k] = 1.0;
+        if (k < K) {
+            N[k] = propars[p0 + 3 * k];
+            S[k] = propars[p0 + 3 * k + 1];
+            n[k] = propars[p0 + 3 * k + 2];
+            G[k] = ig[k];
+        }
+        N0[k] = N[k];
+        S0[k] = S[k];
+    }
+    double pop = 0.0;
+    for (int i = lane; i < nrad; i += 32) pop += w[i] * rho[i];
+    pop = warp_allsum(pop);
+
+    uint32_t flags = HP_SOLVE_NOT_CONVERGED;
+    int it = 0;
+    for (; it < max_inner; ++it) {
+        double m0[kMaxMbisShells], m1[kMaxMbisShells];
+#pragma unroll
+        for (int k = 0; k < kMaxMbisShells; ++k) m0[k] = m1[k] = 0.0;
+        double chg = 0.0;
+        for (int i = lane; i < nrad; i += 32) {
+            const double ri = r[i];
+            double g[kMaxMbisShells], rn[kMaxMbisShells];
+            double pro = 0.0;
+#pragma unroll
+            for (int k = 0; k < kMaxMbisShells; ++k) {
+                g[k] = rn[k] = 0.0;
+                if (k < K) {
+                    rn[k] = pow_order(ri, n[k]);
+                    // nlis.py:147  n S^(3/n) exp(-S r^n) / (4 pi Gamma(3/n))
+                    g[k] = n[k] * pow(S[k], 3.0 / n[k]) * exp(-S[k] * rn[k]) * G[k] / kFourPi;
+                    pro += g[k] * N[k];  // nlis.py:150
+                }
+            }
+            const double rh = rho[i];
+            const bool sick = (rh < density_cutoff) || (pro < density_cutoff);
+            const double ratio = sick ? 0.0 : rh / pro;
+#pragma unroll
+            for (int k = 0; k < kMaxMbisShells; ++k) {
+                if (k < K) {
+                    const double tr = g[k] * ratio;
+                    m0[k] += w[i] * (tr * N[k]);   // nlis.py:166
+                    m1[k] += w[i] * tr * rn[k];    // nlis.py:167
+                }
+            }
+            if (it > 0) {
+                const double e = oldpro[i] - pro;
+                chg += w[i] * e * e;
+            }
+            oldpro[i] = pro;
+        }
+#pragma unroll
+        for (int k = 0; k < kMaxMbisShells; ++k) {
+            if (k < K) {
+                const double a0 = warp_allsum(m0[k]);
+                const double a1 = warp_allsum(m1[k]);
+                N[k] = a0;
+                // nlis.py:170-176: np.isclose(m1, 0) -> |m1| <= 1e-8
+                S[k] = (fabs(a1) <= 1e-8) ? 1e-5 : 3.0 / (a1 * n[k]);
+            }
+        }
+        const double change = (it == 0) ? 1e100 : sqrt(warp_allsum(chg));
+        if (change < threshold) {
+            flags &= ~HP_SOLVE_NOT_CONVERGED;
+            ++it;
+            break;
+        }
+    }
+    double nsum = 0.0;
+    bool finite = true;
+#pragma unroll
+    for (int k = 0; k < kMaxMbisShells; ++k) {
+        if (k < K) {
+            nsum += N[k];
+            finite = finite && isfinite(N[k]) && isfinite(S[k]);
+        }
+    }
+    if (!(fabs(pop - nsum) <= 1e-4 + 1e-5 * fabs(nsum))) flags |= HP_SOLVE_POP_MISMATCH;
+    if (!finite) flags |= HP_SOLVE_NONFINITE;
+
+    // compute_change term (core/iterstock.py:36-44 with nlis.py:296-299)
+    double dev = 0.0;
+    for (int i = lane; i < nrad; i += 32) {
+        const double ri = r[i];
+        double ynew = 0.0, yold = 0.0;
+#pragma unroll
+        for (int k = 0; k < kMaxMbisShells; ++k) {
+            if (k < K) {
+                const double rn = pow_order(ri, n[k]);
+                ynew += N[k] * n[k] * pow(S[k], 3.0 / n[k]) * exp(-S[k] * rn) * G[k] / kFourPi;
+                yold += N0[k] * n[k] * pow(S0[k], 3.0 / n[k]) * exp(-S0[k] * rn) * G[k] / kFourPi;
+            }
+        }
+        const double d = ynew - yold;
+        dev += w[i] * d * d;
+    }
+    dev = warp_allsum(dev);
+    if (lane == 0) {
+#pragma unroll
+        for (int k = 0; k < kMaxMbisShells; ++k) {
+            if (k < K) {
+                propars[p0 + 3 * k] = N[k];
+                propars[p0 + 3 * k + 1] = S[k];
+            }
+        }
+        charges[a] = pseudo[a] - pop;
+        msd[a] = dev;
+        niter_out[a] = it;
+        flags_out[a] = flags;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// aLISA self-consistent update (alisa.py:193-291 `solver_sc`, :294-353 `solver_sc_1_iter`,
+// utils.py:198-252 `compute_quantities`), one warp per atom.  Basis functions on the radial grid
+// (K x nrad per atom, evaluated once on the host exactly as gisa.py:91-106 does) are read through
+// L1; the coefficient vector lives in shared memory.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(32)
+lisa_sc_radial_kernel(int natom, int atom_base, const int* __restrict__ rad_off,
+                      const double* __restrict__ rad_w4, const double* __restrict__ sph,
+                      const int* __restrict__ par_off, double* __restrict__ propars,
+                      const int64_t* __restrict__ bs_off, const double* __restrict__ bs,
+                      const double* __restrict__ pseudo, double threshold, double density_cutoff,
+                      double population_cutoff, int max_inner, int single_update, int nrad_max,
+                      double* __restrict__ charges, double* __restrict__ msd,
+                      int* __restrict__ niter_out, uint32_t* __restrict__ flags_out) {
+    extern __shared__ double smem[];  // oldpro[nrad_max] | ratio[nrad_max] | c[K] | c0[K]
+    if (int(blockIdx.x) >= natom) return;
+    const int a = atom_base + blockIdx.x;
+    const int lane = threadIdx.x;
+    const int r0 = rad_off[blockIdx.x], nrad = rad_off[blockIdx.x + 1] - r0;
+    const int p0 = par_off[a], K = par_off[a + 1] - p0;
+    const double* w = rad_w4 + r0;
+    const double* rho = sph + r0;
+    const double* g = bs + bs_off[blockIdx.x];  // g[k * nrad + i]
+    double* oldpro = smem;
+    double* ratio = smem + nrad_max;
+    double* c = smem + 2 * nrad_max;
+    double* c0 = c + K;
+    for (int k = lane; k < K; k += 32) c[k] = c0[k] = propars[p0 + k];
+    __syncwarp();
+
+    double pop = 0.0;
+    for (int i = lane; i < nrad; i += 32) pop += w[i] * rho[i];
+    pop = warp_allsum(pop);
+
+    uint32_t flags = single_update ? 0u : HP_SOLVE_NOT_CONVERGED;
+    int it = 0;
+    for (; it < max_inner; ++it) {
+        double chg = 0.0;
+        for (int i = lane; i < nrad; i += 32) {
+            double pro = 0.0;
+            for (int k = 0; k < K; ++k) pro += g[k * nrad + i] * c[k];  // utils.py:236-237
+            const double rh = rho[i];
+            const bool sick = (rh < density_cutoff) || (pro < density_cutoff);
+            ratio[i] = sick ? 0.0 : rh / pro;
+            if (it > 0) {
+                const double e = oldpro[i] - pro;
+                chg += w[i] * e * e;  // alisa.py:273-274
+            }
+            oldpro[i] = pro;
+        }
+        __syncwarp();
+        for (int k = 0; k < K; ++k) {
+            const double ck = c[k];
+            double s = 0.0;
+            for (int i = lane; i < nrad; i += 32) s += w[i] * ((g[k * nrad + i] * ck) * ratio[i]);
+            s = warp_allsum(s);  // alisa.py:268
+            __syncwarp();
+            if (lane == 0) c[k] = s;
+        }
+        __syncwarp();
+        if (single_update) {
+            ++it;
+            break;
+        }
+        const double change = (it == 0) ? 1e100 : sqrt(warp_allsum(chg));
+        if (change < threshold) {
+            flags &= ~HP_SOLVE_NOT_CONVERGED;
+            ++it;
+            break;
+        }
+    }
+    double csum = 0.0;
+    bool finite = true;
+    for (int k = 0; k < K; ++k) {
+        csum += c[k];
+        finite = finite && isfinite(c[k]);
+    }
+    // check_pars_population, utils.py:434: only reached on convergence in the reference
+    if (!single_update && !(flags & HP_SOLVE_NOT_CONVERGED) && fabs(csum - pop) > population_cutoff)
+        flags |= HP_SOLVE_POP_MISMATCH;
+    if (!finite) flags |= HP_SOLVE_NONFINITE;
+
+    double dev = 0.0;
+    for (int i = lane; i < nrad; i += 32) {
+        double ynew = 0.0, yold = 0.0;
+        for (int k = 0; k < K; ++k) {
+            ynew += c[k] * g[k * nrad + i];
+            yold += c0[k] * g[k * nrad + i];
+        }
+        const double d = ynew - yold;
+        dev += w[i] * d * d;
+    }
+    dev = warp_allsum(dev);
+    for (int k = lane; k < K; k += 32) propars[p0 + k] = c[k];
+    if (lane == 0) {
+        charges[a] = pseudo[a] - pop;  // gisa.py:315-318
+        msd[a] = dev;
+        niter_out[a] = it;
+        flags_out[a] = flags;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // End-of-iteration scalars in a fixed summation order
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
@@ -339,5 +589,55 @@ extern "C" int hp_finish_iteration(int32_t npartial, const double* entropy_parti
     finish_iteration_kernel<<<1, 256, 0, as_stream(stream)>>>(npartial, entropy_partials, natom, msd,
                                                               out2);
     HP_LAUNCH_CHECK("finish_iteration_kernel");
+    return HP_OK;
+}
+
+extern "C" int hp_nlis_radial_solve(int32_t natom, int32_t atom_base, const int32_t* rad_offsets,
+                                    const double* rad_r, const double* rad_w4, const double* sph_avg,
+                                    const int32_t* par_offsets, double* propars,
+                                    const int32_t* shell_offsets, const double* inv_gamma,
+                                    const double* pseudo_numbers, double inner_threshold,
+                                    double density_cutoff, int32_t max_inner, double* charges,
+                                    double* msd, int32_t* niter, uint32_t* flags, void* stream) {
+    HP_REQUIRE(natom >= 0, "bad sizes");
+    if (natom == 0) return HP_OK;
+    HP_REQUIRE(rad_offsets && rad_r && rad_w4 && sph_avg && par_offsets && propars &&
+                   shell_offsets && inv_gamma && pseudo_numbers && charges && msd && niter && flags,
+               "null input");
+    nlis_radial_kernel<<<natom, 32, sizeof(double) * 4096, as_stream(stream)>>>(
+        natom, atom_base, rad_offsets, rad_r, rad_w4, sph_avg, par_offsets, propars, shell_offsets,
+        inv_gamma, pseudo_numbers, inner_threshold, density_cutoff, max_inner, charges, msd, niter,
+        flags);
+    HP_LAUNCH_CHECK("nlis_radial_kernel");
+    return HP_OK;
+}
+
+extern "C" int hp_lisa_sc_radial_solve(int32_t natom, int32_t atom_base, const int32_t* rad_offsets,
+                                       const double* rad_w4, const double* sph_avg,
+                                       const int32_t* par_offsets, double* propars,
+                                       const int64_t* bs_offsets, const double* bs_funcs,
+                                       const double* pseudo_numbers, double inner_threshold,
+                                       double density_cutoff, double population_cutoff,
+                                       int32_t max_inner, int32_t single_update, int32_t nrad_max,
+                                       int32_t nshell_max, double* charges, double* msd,
+                                       int32_t* niter, uint32_t* flags, void* stream) {
+    HP_REQUIRE(natom >= 0, "bad sizes");
+    if (natom == 0) return HP_OK;
+    HP_REQUIRE(rad_offsets && rad_w4 && sph_avg && par_offsets && propars && bs_offsets && bs_funcs &&
+                   pseudo_numbers && charges && msd && niter && flags, "null input");
+    HP_REQUIRE(nrad_max > 0 && nshell_max > 0, "bad shared-memory sizes");
+    const size_t smem = sizeof(double) * (2 * size_t(nrad_max) + 2 * size_t(nshell_max));
+    HP_REQUIRE(smem <= 200 * 1024, "radial grid / basis too large for shared memory");
+    if (smem > 48 * 1024) {
+        int rc = check_cuda(cudaFuncSetAttribute(lisa_sc_radial_kernel,
+                                                 cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)),
+                            "cudaFuncSetAttribute");
+        if (rc) return rc;
+    }
+    lisa_sc_radial_kernel<<<natom, 32, smem, as_stream(stream)>>>(
+        natom, atom_base, rad_offsets, rad_w4, sph_avg, par_offsets, propars, bs_offsets, bs_funcs,
+        pseudo_numbers, inner_threshold, density_cutoff, population_cutoff, max_inner, single_update,
+        nrad_max, charges, msd, niter, flags);
+    HP_LAUNCH_CHECK("lisa_sc_radial_kernel");
     return HP_OK;
 }

@@ -1,0 +1,245 @@
+"""Gaussian ISA (GISA): pro-atoms expanded in fixed exponential basis functions.
+
+Counterpart of the reference's ``gisa.py`` (``GaussianISAWPart`` :109-345, ``init_propars`` :68-88,
+``evaluate_basis_functions`` :91-106, QP interface :348-421).  The per-iteration grid passes run on
+the GPU; GISA's own per-atom update is a small quadratic programme solved on the host through the
+third-party ``qpsolvers`` package exactly as in the reference (absent in this image: using it
+raises ImportError; a user-supplied callable solver works).
+"""
+
+from __future__ import annotations
+
+import warnings
+
+import numpy as np
+
+from . import _lib
+from .core.basis import ExpBasisFuncHelper, shell_norm
+from .core.cache import just_once
+from .core.iterstock import AbstractISAWPart
+from .core.logging import deflist
+
+__all__ = ["GaussianISAWPart", "get_proatom_rho", "init_propars", "evaluate_basis_functions"]
+
+
+def get_proatom_rho(part, iatom, propars=None):
+    """Pro-atom density and derivative of atom ``iatom`` on its radial grid (host helper)."""
+    if propars is None:
+        propars = part.cache.load("propars")
+    mine = propars[part._ranges[iatom] : part._ranges[iatom + 1]]
+    points = part.radial_distances[iatom] if part.on_molgrid else part.get_rgrid(iatom).points
+    return part.bs_helper.compute_proatom_dens(part.numbers[iatom], mine, points, 1)
+
+
+def init_propars(part):
+    """Initial coefficients: table initials (floored at 1e-4), scaled per atom to its pseudo
+    number and globally to the number of electrons (gisa.py:68-88)."""
+    part._nshells = [part.bs_helper.get_nshell(z) for z in part.numbers]
+    part._ranges = [0]
+    for k in part._nshells:
+        part._ranges.append(part._ranges[-1] + k)
+    propars = part.cache.load("propars", alloc=part._ranges[-1], tags="o")[0]
+    propars[:] = 1.0
+    for a in range(part.natom):
+        inits = part.bs_helper.get_initial(part.numbers[a])
+        inits[inits < 1e-4] = 1e-4  # in place, as the reference does (mutates the helper's table)
+        propars[part._ranges[a] : part._ranges[a + 1]] = inits / np.sum(inits) * part.pseudo_numbers[a]
+    propars[:] = propars / np.sum(propars) * part.nelec
+    part.initial_propars_modified = propars.copy()
+    return propars
+
+
+def evaluate_basis_functions(part, force_on_molgrid=False):
+    """Unit-population basis functions on each atom's radial grid -> cache ``bs_funcs_{a}``."""
+    if part.on_molgrid or force_on_molgrid:
+        raise NotImplementedError("basis functions on the molecular grid are generated in-kernel")
+    for a in range(part.natom):
+        r = part.get_rgrid(a).points
+        k = part._ranges[a + 1] - part._ranges[a]
+        bs = part.cache.load(f"bs_funcs_{a}", alloc=(k, r.size))[0]
+        bs[:, :] = np.array([part.bs_helper.compute_proshell_dens(part.numbers[a], i, 1.0, r) for i in range(k)])
+
+
+class GaussianISAWPart(AbstractISAWPart):
+    name = "gisa"
+    #: solver names that run as CUDA kernels (subclasses extend this)
+    device_solvers = {}
+
+    def __init__(self, coordinates, numbers, pseudo_numbers, grid, moldens, spindens=None, lmax=3,
+                 logger=None, threshold=1e-6, maxiter=500, inner_threshold=1e-8,
+                 radius_cutoff=np.inf, solver="quadprog", solver_options=None, grid_type=1,
+                 **kwargs):  # fmt: skip
+        self._solver = solver
+        self._solver_options = solver_options or {}
+        if not hasattr(self, "_bs_helper"):
+            self._bs_helper = None
+        self._ranges = None
+        super().__init__(coordinates, numbers, pseudo_numbers, grid, moldens, spindens, lmax=lmax,
+                         logger=logger, threshold=threshold, maxiter=maxiter,
+                         inner_threshold=inner_threshold, radius_cutoff=radius_cutoff,
+                         grid_type=grid_type, **kwargs)  # fmt: skip
+
+    @property
+    def bs_helper(self):
+        if self._bs_helper is None:
+            self._bs_helper = ExpBasisFuncHelper.from_function_type()
+        return self._bs_helper
+
+    def _init_log_scheme(self):
+        deflist(
+            self.logger,
+            [
+                ("Scheme", "Gaussian Iterative Stockholder Analysis (GISA)"),
+                ("Outer loop convergence threshold", "%.1e" % self._threshold),
+                ("Inner loop convergence threshold", "%.1e" % self._inner_threshold),
+                ("Maximum iterations", self._maxiter),
+                ("lmax", self._lmax),
+                ("Solver", self._solver),
+                ("Grid type", self.grid_type),
+            ],
+        )
+        if callable(self._solver):
+            warnings.warn("Customized solver is used, the argument `inner_threshold` is not used.")
+
+    def get_rgrid(self, index):
+        if self.only_use_molgrid:
+            self.logger.debug("rgird is not available when only_use_molgrid is `True`.")
+            raise NotImplementedError
+        return self.get_grid(index).rgrid
+
+    def to_atomic_grid(self, index, data):
+        if self.only_use_molgrid:
+            self.logger.debug("atom grids are not available when only_use_molgrid is `True`.")
+            raise NotImplementedError
+        return super().to_atomic_grid(index, data)
+
+    def get_proatom_rho(self, iatom, propars=None, **kwargs):
+        return get_proatom_rho(self, iatom, propars)
+
+    # -- device hooks ---------------------------------------------------------------------------
+    def _init_propars(self):
+        import torch
+
+        from .core.device import ShellTable, to_device
+
+        if self.on_molgrid:
+            raise NotImplementedError(f"{self.name} with grid_type 2/3 is not built yet")
+        propars = init_propars(self)
+        self._evaluate_basis_functions()
+        slab = self.slab
+        dev = slab.device
+        orders = np.concatenate([np.asarray(self.bs_helper.get_order(z), float) for z in self.numbers])
+        alphas = np.concatenate([np.asarray(self.bs_helper.get_exponent(z), float) for z in self.numbers])
+        if np.all(orders == 2.0):
+            functor = 2
+        elif np.all(orders == 1.0):
+            functor = 1
+        else:
+            functor = 3
+        self._table = ShellTable(slab, functor, self._nshells)
+        self._table.alpha.copy_(to_device(alphas, dev))
+        if functor == 3:
+            self._table.order.copy_(to_device(orders, dev))
+        self._norms = to_device(shell_norm(orders, alphas), dev)
+        st = self._alloc_state(len(propars))
+        st.propars.copy_(to_device(propars, dev))
+        self._par_offsets = to_device(np.asarray(self._ranges, dtype=np.int32), dev)
+        self._pseudo = to_device(self.pseudo_numbers, dev, np.float64)
+        # radial-grid basis functions of the local atoms, concatenated (K_a x nrad_a row-major)
+        sh = slab.shard
+        blocks = [self.cache.load(f"bs_funcs_{a}") for a in range(sh.atom_lo, sh.atom_hi)]
+        offs = np.concatenate([[0], np.cumsum([b.size for b in blocks])]).astype(np.int64)
+        flat = np.concatenate([b.ravel() for b in blocks]) if blocks else np.zeros(0)
+        self._bs_offsets = to_device(offs, dev)
+        self._bs_flat = to_device(flat, dev) if flat.size else torch.zeros(1, dtype=torch.float64, device=dev)
+        self._nrad_max = int(np.max(np.diff(slab.rad_offsets_host))) if sh.nlocal else 1
+        self._nshell_max = max(self._nshells[sh.atom_lo : sh.atom_hi], default=1)
+        return propars
+
+    def _refresh_table(self):
+        from .core.device import stream_ptr
+
+        t = self._table
+        _lib.call("hp_table_scaled", t.nshell, self._state.propars, self._norms, t.A, stream_ptr(self.slab.device))
+
+    def _launch_radial_update(self):
+        self.slab.shell_project()
+        if not callable(self._solver) and self._solver in self.device_solvers:
+            self._launch_device_solver(self.device_solvers[self._solver])
+        else:
+            self._host_radial_update()
+
+    def _launch_device_solver(self, spec):
+        raise NotImplementedError
+
+    def _host_radial_update(self):
+        """Per-atom updates through a host solver (user callable or the QP interface): the
+        spherical averages come back from the device (natom x nrad doubles), parameters go up."""
+        import torch
+
+        slab, st = self.slab, self._state
+        sph = slab.sph_avg.cpu().numpy()
+        propars = self.cache.load("propars")
+        old = propars.copy()
+        sh, ro = slab.shard, slab.rad_offsets_host
+        charges = np.zeros(self.natom)
+        msd = np.zeros(self.natom)
+        for i, a in enumerate(range(sh.atom_lo, sh.atom_hi)):
+            rgrid = self.get_rgrid(a)
+            points = rgrid.points
+            rho_sph = sph[ro[i] : ro[i + 1]]
+            r_weights = 4 * np.pi * points**2 * rgrid.weights
+            alphas = self.bs_helper.get_exponent(self.numbers[a]) if isinstance(self.bs_helper, ExpBasisFuncHelper) else None
+            lo, hi = self._ranges[a], self._ranges[a + 1]
+            propars[lo:hi] = self._opt_propars(
+                self.cache.load(f"bs_funcs_{a}"), rho_sph, propars[lo:hi].copy(), points, r_weights,
+                alphas, self._inner_threshold,
+            )  # fmt: skip
+            charges[a] = self.pseudo_numbers[a] - np.einsum("i,i", r_weights, rho_sph)
+            delta = self.get_proatom_rho(a, propars)[0] - self.get_proatom_rho(a, old)[0]
+            msd[a] = rgrid.integrate(4 * np.pi * points**2, delta, delta)
+        dev = slab.device
+        st.propars[self._ranges[sh.atom_lo] : self._ranges[sh.atom_hi]] = torch.from_numpy(
+            propars[self._ranges[sh.atom_lo] : self._ranges[sh.atom_hi]]
+        ).to(dev)
+        st.charges[sh.atom_lo : sh.atom_hi] = torch.from_numpy(charges[sh.atom_lo : sh.atom_hi]).to(dev)
+        st.msd[sh.atom_lo : sh.atom_hi] = torch.from_numpy(msd[sh.atom_lo : sh.atom_hi]).to(dev)
+
+    def _opt_propars(self, bs_funcs, rho, propars, points, weights, alphas, threshold):
+        if callable(self._solver):
+            return self._solver(bs_funcs, rho, propars, points, weights, alphas, threshold, **self._solver_options)
+        return opt_propars_qp_interface(bs_funcs, rho, propars, weights, alphas, self._solver, **self._solver_options)
+
+    @just_once
+    def _evaluate_basis_functions(self):
+        evaluate_basis_functions(self)
+
+    def _finalize_propars(self):
+        AbstractISAWPart._finalize_propars(self)
+        slab = self.slab
+        sph = slab.sph_avg.cpu().numpy()
+        ro = slab.rad_offsets_host
+        for i, a in enumerate(range(slab.shard.atom_lo, slab.shard.atom_hi)):
+            self.cache.dump(f"radial_points_{a}", slab.rad_r_host[ro[i] : ro[i + 1]], tags="o")
+            self.cache.dump(f"spherical_average_{a}", sph[ro[i] : ro[i + 1]], tags="o")
+            self.cache.dump(f"radial_weights_{a}", slab.rad_w_host[ro[i] : ro[i + 1]], tags="o")
+
+
+def opt_propars_qp_interface(bs_funcs, rho, propars, weights, alphas, solver="quadprog", **solver_options):
+    """GISA's quadratic programme  min c^T P c + q^T c,  c >= 0,  sum c = pop  (gisa.py:348-421),
+    handed to the third-party ``qpsolvers`` package like the reference does."""
+    try:
+        import qpsolvers
+    except ImportError as exc:  # not in this image
+        raise ImportError("GISA's QP solver needs the `qpsolvers` package, as in the reference") from exc
+    nprim = bs_funcs.shape[0]
+    s = alphas[:, None] + alphas[None, :]
+    P = 2 / np.pi**1.5 * (alphas[:, None] * alphas[None, :]) ** 1.5 / s**1.5
+    P = (P + P.T) / 2
+    q = -2 * np.einsum("i,ni,i->n", weights, bs_funcs, rho)
+    pop = np.einsum("i,i", weights, rho)
+    result = qpsolvers.solve_qp(
+        P, q, -np.identity(nprim), np.zeros((nprim, 1)), np.ones((1, nprim)), np.ones((1, 1)) * pop,
+        solver=solver, initvals=np.zeros_like(propars), **solver_options,
+    )  # fmt: skip
+    return result

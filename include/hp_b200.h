@@ -147,6 +147,32 @@ HP_API int hp_mbis_radial_solve(int32_t natom, int32_t atom_base, const int32_t*
                          double density_cutoff, int32_t max_inner, double* charges, double* msd,
                          int32_t* niter, uint32_t* flags, void* stream);
 
+/* hp_nlis_radial_solve -- opt_nlis_propars (nlis.py:99-194): shells (N, S, n) with n fixed,
+ * propars [N,S,n]*K per atom; shell_offsets (natom+1, global) index inv_gamma = 1/Gamma(3/n). */
+HP_API int hp_nlis_radial_solve(int32_t natom, int32_t atom_base, const int32_t* rad_offsets,
+                                const double* rad_r, const double* rad_w4, const double* sph_avg,
+                                const int32_t* par_offsets, double* propars,
+                                const int32_t* shell_offsets, const double* inv_gamma,
+                                const double* pseudo_numbers, double inner_threshold,
+                                double density_cutoff, int32_t max_inner, double* charges,
+                                double* msd, int32_t* niter, uint32_t* flags, void* stream);
+
+/* hp_lisa_sc_radial_solve -- aLISA `solver_sc` (alisa.py:193-291) / `solver_sc_1_iter` (:294-353)
+ * with compute_quantities (utils.py:198-252): c_k <- sum_i w_i c_k g_k(r_i) rho_i / pro_i.
+ *   bs_funcs   basis functions on the radial grids of the LOCAL atoms, K_a x nrad_a row-major per
+ *              atom at bs_offsets[local atom] (gisa.py:91-106)
+ *   single_update != 0 : exactly one update, no convergence test (sc-1-iter)
+ *   nrad_max, nshell_max : largest radial grid / shell count among the local atoms */
+HP_API int hp_lisa_sc_radial_solve(int32_t natom, int32_t atom_base, const int32_t* rad_offsets,
+                                   const double* rad_w4, const double* sph_avg,
+                                   const int32_t* par_offsets, double* propars,
+                                   const int64_t* bs_offsets, const double* bs_funcs,
+                                   const double* pseudo_numbers, double inner_threshold,
+                                   double density_cutoff, double population_cutoff,
+                                   int32_t max_inner, int32_t single_update, int32_t nrad_max,
+                                   int32_t nshell_max, double* charges, double* msd,
+                                   int32_t* niter, uint32_t* flags, void* stream);
+
 /* Sum the entropy partials and sqrt(sum msd) in a fixed order: out[0] = change, out[1] = entropy. */
 HP_API int hp_finish_iteration(int32_t npartial, const double* entropy_partials, int32_t natom,
                         const double* msd, double* out2, void* stream);

@@ -252,3 +252,169 @@ def dense_weights_pass_mbis(points, owner, coords, ranges, propars, dist=None):
             own[mine] = work[mine]
     w = np.clip(own / promol, 0, 1)
     return promol, w, natom * len(points)
+
+
+def load_basis(kind):
+    """Per-element (orders, exponents, initials) of data/gauss.json / slater.json, read from the
+    re-keyed copy shipped with the product (tools/import_basis_tables.py documents the provenance)."""
+    import json
+    import pathlib
+
+    path = pathlib.Path(__file__).resolve().parents[1] / "horton_part_b200" / "data" / "expbasis_tables.json"
+    table = json.loads(path.read_text())[kind]
+    return {int(z): {k: np.asarray(v, dtype=float) for k, v in t.items()} for z, t in table.items()}
+
+
+def lisa_initial(numbers, pseudo, basis, nelec):
+    """gisa.py:68-88: table initials floored at 1e-4, scaled per atom, then to nelec."""
+    parts = []
+    for z, pn in zip(numbers, pseudo):
+        init = basis[int(z)]["initials"].copy()
+        init[init < 1e-4] = 1e-4
+        parts.append(init / np.sum(init) * pn)
+    propars = np.concatenate(parts)
+    return propars / np.sum(propars) * nelec
+
+
+def lisa_proatom(tab, c, r):
+    """core/basis.py:214-232: shells summed in order."""
+    y = 0.0
+    for k in range(len(c)):
+        y = y + exp_shell(tab["orders"][k], c[k], tab["exponents"][k], r)
+    return y
+
+
+def lisa_sc_inner(bs, rho, c, weights, threshold, cutoff=DENSITY_CUTOFF, max_inner=100000, single=False):
+    """solver_sc alisa.py:193-291 (single=True: solver_sc_1_iter :294-353) with
+    compute_quantities utils.py:198-252."""
+    c = c.copy()
+    oldpro = None
+    for irep in range(max_inner):
+        shells = bs * c[:, None]
+        pro = np.einsum("ij->j", shells)
+        sick = (rho < cutoff) | (pro < cutoff)
+        with np.errstate(all="ignore"):
+            ratio = np.divide(rho, pro, out=np.zeros_like(rho), where=~sick)
+        c[:] = np.einsum("p,ip->i", weights, shells * ratio)
+        if single:
+            return c, 1
+        if oldpro is None:
+            change = 1e100
+        else:
+            err = oldpro - pro
+            change = np.sqrt(np.einsum("i,i,i", weights, err, err))
+        if change < threshold:
+            return c, irep + 1
+        oldpro = pro
+    return c, max_inner
+
+
+def alisa(coords, numbers, pseudo, grid, rho, basis_func="gauss", solver="sc", threshold=1e-6,
+          inner_threshold=1e-8, maxiter=500, cutoff=DENSITY_CUTOFF, max_inner=100000):  # fmt: skip
+    """LinearISAWPart(solver='sc' | 'sc-1-iter').do_partitioning(), grid_type=1
+    (gisa.py:281-318, alisa.py:1304-1335)."""
+    natom = len(numbers)
+    basis = load_basis(basis_func)
+    inner_threshold = min(inner_threshold, threshold)
+    ranges = [0]
+    for z in numbers:
+        ranges.append(ranges[-1] + len(basis[int(z)]["exponents"]))
+    nelec = np.einsum("i,i", grid.weights, rho)
+    propars = lisa_initial(numbers, pseudo, basis, nelec)
+    bs = []
+    for a in range(natom):  # gisa.py:91-106
+        t = basis[int(numbers[a])]
+        r = grid.atgrids[a].rgrid.points
+        bs.append(np.array([exp_shell(t["orders"][k], 1.0, t["exponents"][k], r) for k in range(len(t["exponents"]))]))
+    return _iterate(
+        grid, rho, natom, pseudo, propars, ranges,
+        lambda a, par, r: lisa_proatom(basis[int(numbers[a])], par, r),
+        lambda a, sph, par, w4, r: lisa_sc_inner(bs[a], sph, par, w4, inner_threshold, cutoff, max_inner,
+                                                 single=(solver == "sc-1-iter")),
+        threshold, maxiter, cutoff, coords,
+    )  # fmt: skip
+
+
+# ----------------------------------------------------------------------------------------------
+# NLIS / GMBIS  (nlis.py, gmbis.py)
+# ----------------------------------------------------------------------------------------------
+def nlis_initial(number, exp_n_dict, nshell_dict):
+    """nlis.py:58-96."""
+    k = nshell_dict.get(number, mbis_nshell(number))
+    p = np.ones(3 * k)
+    s0 = 2.0 * number
+    ratio = (0.5 / s0) ** (1.0 / (k - 1)) if k > 1 else 1.0
+    for i in range(k):
+        p[3 * i] = number / k
+        p[3 * i + 1] = s0 * ratio**i
+        p[3 * i + 2] = exp_n_dict.get((number, i), 1.0)
+    return p
+
+
+def gmbis_initial(number, exp_n_dict):
+    """gmbis.py:36-72."""
+    k = mbis_nshell(number)
+    p = np.zeros(3 * k)
+    base = mbis_initial(number)
+    p[0::3], p[1::3] = base[0::2], base[1::2]
+    p[2::3] = [exp_n_dict.get((number, i), 1.0) for i in range(k)]
+    return p
+
+
+def nlis_proatom(par, r):
+    """nlis.py:319-328."""
+    y = np.zeros(len(r))
+    for k in range(len(par) // 3):
+        N, S, n = par[3 * k : 3 * k + 3]
+        y += N * n * S ** (3 / n) * np.exp(-S * r**n) / (4 * np.pi * _gamma(3.0 / n))
+    return y
+
+
+def nlis_inner(rho, par, weights, r, threshold, cutoff=DENSITY_CUTOFF, max_inner=2000):
+    """opt_nlis_propars, nlis.py:99-194."""
+    par = par.copy()
+    k = len(par) // 3
+    terms = np.zeros((k, len(r)))
+    oldpro = None
+    for irep in range(max_inner):
+        for i in range(k):
+            S, n = par[3 * i + 1], par[3 * i + 2]
+            terms[i] = n * S ** (3 / n) * np.exp(-S * r**n) / (4 * np.pi * _gamma(3.0 / n))
+        pro = np.sum(terms * par[::3, None], axis=0)
+        sick = (rho < cutoff) | (pro < cutoff)
+        with np.errstate(all="ignore"):
+            ratio = rho / pro
+        ratio[sick] = 0.0
+        tr = terms * ratio
+        for i in range(k):
+            N, n = par[3 * i], par[3 * i + 2]
+            m0 = np.einsum("p,p->", weights, tr[i] * N)
+            m1 = np.einsum("p,p,p->", weights, tr[i], r**n)
+            par[3 * i] = m0
+            par[3 * i + 1] = 1e-5 if np.isclose(m1, 0.0) else 3 / (m1 * n)
+        if oldpro is None:
+            change = 1e100
+        else:
+            err = oldpro - pro
+            change = np.sqrt(np.einsum("p,p,p->", weights, err, err))
+        if change < threshold:
+            return par, irep + 1
+        oldpro = pro
+    return par, max_inner
+
+
+def nlis(coords, numbers, pseudo, grid, rho, exp_n_dict=None, nshell_dict=None, gmbis_start=False,
+         threshold=1e-6, inner_threshold=1e-8, maxiter=500, cutoff=DENSITY_CUTOFF):  # fmt: skip
+    """NLISWPart / GMBISWPart (gmbis_start=True) .do_partitioning(), grid_type=1."""
+    exp_n_dict, nshell_dict = exp_n_dict or {}, nshell_dict or {}
+    natom = len(numbers)
+    inner_threshold = min(inner_threshold, threshold)
+    init = [gmbis_initial(int(z), exp_n_dict) if gmbis_start else nlis_initial(int(z), exp_n_dict, nshell_dict)
+            for z in numbers]  # fmt: skip
+    ranges = np.concatenate([[0], np.cumsum([len(p) for p in init])]).tolist()
+    return _iterate(
+        grid, rho, natom, pseudo, np.concatenate(init), ranges,
+        lambda a, par, r: nlis_proatom(par, r),
+        lambda a, sph, par, w4, r: nlis_inner(sph, par, w4, r, inner_threshold, cutoff),
+        threshold, maxiter, cutoff, coords,
+    )  # fmt: skip

@@ -6,9 +6,9 @@ import pytest
 import stockholder_oracle as oracle
 
 
-def _check(res, gold, tag, rtol=1e-10):
+def _check(res, gold, tag, rtol=1e-10, qtol=1e-11):
     assert res["niter"] == int(gold[f"{tag}/niter"])
-    np.testing.assert_allclose(res["charges"], gold[f"{tag}/charges"], rtol=0, atol=1e-11)
+    np.testing.assert_allclose(res["charges"], gold[f"{tag}/charges"], rtol=0, atol=qtol)
     np.testing.assert_allclose(res["propars"], gold[f"{tag}/propars"], rtol=rtol, atol=1e-13)
     np.testing.assert_allclose(res["history_changes"], gold[f"{tag}/history_changes"], rtol=1e-8)
     np.testing.assert_allclose(res["history_entropies"], gold[f"{tag}/history_entropies"], rtol=1e-10)
@@ -40,3 +40,34 @@ def test_mbis_known_answers():
     p = oracle.mbis_initial(14)
     assert p[0::2].sum() == pytest.approx(14.0)
     np.testing.assert_allclose(p[1::2], [28.0, np.sqrt(56.0), 2.0])
+
+
+@pytest.mark.parametrize("tag,kw", [("lisa_sc_gauss", dict(basis_func="gauss")), ("lisa_sc_slater", dict(basis_func="slater"))])
+def test_alisa_sc_h2o_matches_reference_run(h2o, tag, kw):
+    res = oracle.alisa(h2o["coords"], h2o["numbers"], h2o["pseudo"], h2o["grid"], h2o["rho"], solver="sc", **kw)
+    _check(res, h2o["gold"], tag, rtol=1e-9)
+    assert res["niter"] == {"lisa_sc_gauss": 22, "lisa_sc_slater": 27}[tag]
+
+
+def test_alisa_sc_water6_matches_reference_run(water6):
+    res = oracle.alisa(water6["coords"], water6["numbers"], water6["pseudo"], water6["grid"], water6["rho"])
+    # the near-degenerate Gaussian basis amplifies the 1e-16 grid differences between the shim grid
+    # (golden run) and gridlite (this run) to ~1e-9 in the converged coefficients
+    _check(res, water6["gold"], "lisa_sc_gauss", rtol=1e-6, qtol=5e-9)
+
+
+def test_nlis_gmbis_h2o_match_reference_run(h2o):
+    res = oracle.nlis(h2o["coords"], h2o["numbers"], h2o["pseudo"], h2o["grid"], h2o["rho"])
+    _check(res, h2o["gold"], "nlis", rtol=1e-9)
+    assert res["niter"] == 32
+    res = oracle.nlis(h2o["coords"], h2o["numbers"], h2o["pseudo"], h2o["grid"], h2o["rho"], gmbis_start=True)
+    _check(res, h2o["gold"], "gmbis", rtol=1e-9)
+
+
+def test_nlis_known_answers():
+    # reference tests/test_nlis.py:53-70
+    np.testing.assert_allclose(oracle.nlis_initial(1, {}, {}), [1.0, 2.0, 1.0])
+    p = oracle.nlis_initial(8, {}, {})
+    np.testing.assert_allclose(p, [4.0, 16.0, 1.0, 4.0, 0.5, 1.0])
+    p = oracle.nlis_initial(8, {(8, 1): 2.0}, {8: 3})
+    assert len(p) == 9 and p[5] == 2.0 and p[0] == pytest.approx(8 / 3)
