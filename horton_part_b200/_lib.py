@@ -54,6 +54,12 @@ EXPORTS = {
         _int,
         [_i32, _i32, _p, _p, _p, _p, _p, _p, _p, _p, _f64, _f64, _f64, _i32, _i32, _i32, _i32, _p, _p, _p, _p, _p],
     ),
+    "hp_spline_build": (_int, [_i32, _p, _p, _p, _i32, _p, _p, _p]),
+    "hp_promol_weights_spline": (
+        _int,
+        [_i64, _p, _p, _p, _i64, _i32, _p, _p, _p, _p, _p, _f64, _p, _p, _f64, _p, _p, _p, _p],
+    ),
+    "hp_isa_update": (_int, [_i32, _i32, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
     "hp_finish_iteration": (_int, [_i32, _p, _i32, _p, _p, _p]),
     "hp_sum_partials": (_int, [_i32, _p, _p, _p]),
     "hp_segment_integrate": (_int, [_i32, _p, _p, _p, _p, _p, _p]),

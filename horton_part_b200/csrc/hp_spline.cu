@@ -1,0 +1,273 @@
+// Spline pro-atoms: ISA, Hirshfeld, Hirshfeld-I (row a5 of SURVEY.md section 8a).
+//
+//   hp_spline_build          not-a-knot cubic spline per atom (SciPy CubicSpline semantics,
+//                            core/stockholder.py:259-269), one thread per atom (Thomas solve)
+//   hp_promol_weights_spline fused promolecule / owner-weight / entropy pass with piecewise-cubic
+//                            pro-atoms evaluated at |r_p - R_a| (core/stockholder.py:271-350),
+//                            extrapolating with the end pieces exactly like PPoly
+//   hp_isa_update            ISA's parameter update: propars = clipped spherical average, charge,
+//                            change term (isa.py:102-122, core/iterstock.py:32-45)
+#include "hp_common.cuh"
+#include "hp_math.cuh"
+
+namespace hp {
+
+// ---------------------------------------------------------------------------------------------
+// Spline construction.  For knots x_0..x_{n-1} and values y, solve for the knot derivatives s with
+// the not-a-knot end conditions (the banded system SciPy assembles), then emit PPoly coefficients
+// (c0, c1, c2, c3) per interval:  S(x) = c0 d^3 + c1 d^2 + c2 d + c3,  d = x - x_i.
+// `work` provides 2 doubles of scratch per knot.
+// ---------------------------------------------------------------------------------------------
+__global__ void spline_build_kernel(int natom, const int* __restrict__ knot_off,
+                                    const double* __restrict__ knots, const double* __restrict__ values,
+                                    int clip_negative, double* __restrict__ coef,
+                                    double* __restrict__ work) {
+    const int a = blockIdx.x * blockDim.x + threadIdx.x;
+    if (a >= natom) return;
+    const int o = knot_off[a], n = knot_off[a + 1] - o;
+    const double* x = knots + o;
+    const double* yv = values + o;
+    double* cp = work + 2 * o;       // modified upper diagonal
+    double* s = work + 2 * o + n;    // rhs -> solution (knot derivatives)
+    double* c = coef + 4 * (o - a);  // atom a owns n-1 segments; segments of all atoms are packed
+    auto Y = [&](int i) {
+        const double v = yv[i];
+        return (clip_negative && v < 0.0) ? 0.0 : v;  // fix_proatom_rho, core/stockholder.py:218-219
+    };
+    if (n < 2) return;
+    if (n == 2) {  // straight line
+        const double slope = (Y(1) - Y(0)) / (x[1] - x[0]);
+        c[0] = 0.0; c[1] = 0.0; c[2] = slope; c[3] = Y(0);
+        return;
+    }
+    if (n == 3) {  // parabola through three points (SciPy's special case)
+        const double dx0 = x[1] - x[0], dx1 = x[2] - x[1];
+        const double sl0 = (Y(1) - Y(0)) / dx0, sl1 = (Y(2) - Y(1)) / dx1;
+        // A = [[1,1,0],[dx1, 2(dx0+dx1), dx0],[0,1,1]], b = [2 sl0, 3(dx0 sl1 + dx1 sl0), 2 sl1]
+        const double b0 = 2 * sl0, b1 = 3 * (dx0 * sl1 + dx1 * sl0), b2 = 2 * sl1;
+        // eliminate: s0 = b0 - s1, s2 = b2 - s1
+        const double s1 = (b1 - dx1 * b0 - dx0 * b2) / (2 * (dx0 + dx1) - dx1 - dx0);
+        s[0] = b0 - s1; s[1] = s1; s[2] = b2 - s1;
+    } else {
+        // row 0:  dx1 * s0 + (x2 - x0) * s1 = b0
+        const double dx0 = x[1] - x[0], dx1 = x[2] - x[1];
+        const double sl0 = (Y(1) - Y(0)) / dx0, sl1 = (Y(2) - Y(1)) / dx1;
+        double d = x[2] - x[0];
+        double diag = dx1, upper = d;
+        double rhs = ((dx0 + 2 * d) * dx1 * sl0 + dx0 * dx0 * sl1) / d;
+        cp[0] = upper / diag;
+        s[0] = rhs / diag;
+        // interior rows i:  dx_i * s_{i-1} + 2 (dx_{i-1} + dx_i) * s_i + dx_{i-1} * s_{i+1} = b_i
+        double dxm = dx0, slm = sl0;  // dx_{i-1}, slope_{i-1}
+        for (int i = 1; i < n - 1; ++i) {
+            const double dxi = x[i + 1] - x[i];
+            const double sli = (Y(i + 1) - Y(i)) / dxi;
+            const double lower = dxi;
+            diag = 2 * (dxm + dxi) - lower * cp[i - 1];
+            rhs = 3 * (dxi * slm + dxm * sli) - lower * s[i - 1];
+            cp[i] = dxm / diag;
+            s[i] = rhs / diag;
+            dxm = dxi;
+            slm = sli;
+        }
+        // last row:  (x_{n-1} - x_{n-3}) * s_{n-2} + dx_{n-3} * s_{n-1} = b_{n-1}
+        const double dxl = x[n - 1] - x[n - 2], dxl2 = x[n - 2] - x[n - 3];
+        const double sll = (Y(n - 1) - Y(n - 2)) / dxl, sll2 = (Y(n - 2) - Y(n - 3)) / dxl2;
+        d = x[n - 1] - x[n - 3];
+        const double lower = d;
+        diag = dxl2 - lower * cp[n - 2];
+        rhs = (dxl * dxl * sll2 + (2 * d + dxl) * dxl2 * sll) / d - lower * s[n - 2];
+        s[n - 1] = rhs / diag;
+        for (int i = n - 2; i >= 0; --i) s[i] -= cp[i] * s[i + 1];
+    }
+    for (int i = 0; i < n - 1; ++i) {
+        const double dxi = x[i + 1] - x[i];
+        const double slope = (Y(i + 1) - Y(i)) / dxi;
+        const double t = (s[i] + s[i + 1] - 2 * slope) / dxi;
+        c[4 * i + 0] = t / dxi;
+        c[4 * i + 1] = (slope - s[i]) / dxi - t;
+        c[4 * i + 2] = s[i];
+        c[4 * i + 3] = Y(i);
+    }
+}
+
+// PPoly evaluation with extrapolation (interval = clamp(searchsorted_right(x, r) - 1, 0, n-2)).
+__device__ __forceinline__ double spline_eval(const double* __restrict__ x, const double* __restrict__ c,
+                                              int n, double r) {
+    int lo = 0, hi = n - 1;  // invariant: answer in [lo, hi-1]
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (x[mid] <= r) lo = mid; else hi = mid;
+    }
+    const double d = r - x[lo];
+    const double* ci = c + 4 * lo;
+    double z = d;
+    double res = fma(ci[2], z, ci[3]);
+    z *= d;
+    res = fma(ci[1], z, res);
+    z *= d;
+    return fma(ci[0], z, res);
+}
+
+constexpr int kSplThreads = 256;
+constexpr int kSplPts = 2;
+
+__global__ void __launch_bounds__(kSplThreads)
+promol_weights_spline_kernel(int64_t npts, const double* __restrict__ px, const double* __restrict__ py,
+                             const double* __restrict__ pz, int64_t point_base, int natom,
+                             const double* __restrict__ atom_xyz, const int64_t* __restrict__ atom_pt_off,
+                             const int* __restrict__ knot_off, const double* __restrict__ knots,
+                             const double* __restrict__ coef, double proatom_offset,
+                             const double* __restrict__ rho, const double* __restrict__ molw,
+                             double density_cutoff, double* __restrict__ promol_out,
+                             double* __restrict__ w_out, double* __restrict__ entropy_partials,
+                             int npartial) {
+    __shared__ double s_red[32];
+    const int64_t span = int64_t(kSplThreads) * kSplPts;
+    const int64_t nchunk = (npts + span - 1) / span;
+    double entropy_acc = 0.0;
+    for (int64_t chunk = blockIdx.x; chunk < nchunk; chunk += gridDim.x) {
+        double x[kSplPts], y[kSplPts], z[kSplPts], pro[kSplPts], own[kSplPts];
+        int owner[kSplPts];
+#pragma unroll
+        for (int j = 0; j < kSplPts; ++j) {
+            const int64_t p = chunk * span + int64_t(j) * kSplThreads + threadIdx.x;
+            const int64_t q = p < npts ? p : npts - 1;
+            x[j] = px[q]; y[j] = py[q]; z[j] = pz[q];
+            pro[j] = 0.0; own[j] = 0.0;
+            const int64_t g = point_base + q;
+            int lo = 0, hi = natom;
+            while (hi - lo > 1) {
+                const int mid = (lo + hi) >> 1;
+                if (atom_pt_off[mid] <= g) lo = mid; else hi = mid;
+            }
+            owner[j] = lo;
+        }
+        for (int a = 0; a < natom; ++a) {
+            const double ax = atom_xyz[3 * a], ay = atom_xyz[3 * a + 1], az = atom_xyz[3 * a + 2];
+            const int o = knot_off[a], n = knot_off[a + 1] - o;
+            const double* xk = knots + o;
+            const double* ck = coef + 4 * (o - a);
+#pragma unroll
+            for (int j = 0; j < kSplPts; ++j) {
+                const double dx = x[j] - ax, dy = y[j] - ay, dz = z[j] - az;
+                const double r = sqrt_nocall(fma(dz, dz, fma(dy, dy, dx * dx)));
+                // eval_proatom (core/stockholder.py:343-349): spline(r) + 1e-100 ...
+                const double f = spline_eval(xk, ck, n, r) + proatom_offset;
+                // ... update_pro (:169-170): promoldens += work; promoldens += 1e-100
+                pro[j] = (pro[j] + f) + 1e-100;
+                if (a == owner[j]) own[j] = f;
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < kSplPts; ++j) {
+            const int64_t p = chunk * span + int64_t(j) * kSplThreads + threadIdx.x;
+            if (p >= npts) continue;
+            if (promol_out) promol_out[p] = pro[j];
+            if (w_out) w_out[p] = fmin(fmax(own[j] / pro[j], 0.0), 1.0);
+            if (entropy_partials) {
+                const double r = rho[p];
+                const bool sick = (pro[j] < density_cutoff) || (r < density_cutoff);
+                if (!sick) entropy_acc += molw[p] * r * log(r / pro[j]);
+            }
+        }
+    }
+    if (entropy_partials) {
+        const double total = block_sum(entropy_acc, s_red);
+        if (threadIdx.x == 0) entropy_partials[blockIdx.x] = total;
+        if (blockIdx.x == 0)
+            for (int i = gridDim.x + threadIdx.x; i < npartial; i += kSplThreads) entropy_partials[i] = 0.0;
+    }
+}
+
+// ISA update, one warp per atom (isa.py:102-122).
+__global__ void __launch_bounds__(32)
+isa_update_kernel(int natom, int atom_base, const int* __restrict__ rad_off,
+                  const double* __restrict__ rad_r, const double* __restrict__ rad_w,
+                  const double* __restrict__ sph, const int* __restrict__ par_off,
+                  double* __restrict__ propars, const double* __restrict__ pseudo,
+                  double* __restrict__ charges, double* __restrict__ msd) {
+    if (int(blockIdx.x) >= natom) return;
+    const int a = atom_base + blockIdx.x;
+    const int lane = threadIdx.x;
+    const int r0 = rad_off[blockIdx.x], nrad = rad_off[blockIdx.x + 1] - r0;
+    double* par = propars + par_off[a];
+    double pop = 0.0, dev = 0.0;
+    for (int i = lane; i < nrad; i += 32) {
+        const double r = fmin(fmax(rad_r[r0 + i], 1e-100), 1e10);   // isa.py:108
+        const double v = fmax(sph[r0 + i], 1e-100);                 // isa.py:110
+        const double shell = kFourPi * (r * r);                     // 4 pi r^2
+        pop += rad_w[r0 + i] * (shell * v);                         // isa.py:120
+        const double d = v - par[i];
+        dev += rad_w[r0 + i] * shell * d * d;                       // core/iterstock.py:44
+        par[i] = v;                                                 // isa.py:117
+    }
+    pop = warp_allsum(pop);
+    dev = warp_allsum(dev);
+    if (lane == 0) {
+        charges[a] = pseudo[a] - pop;
+        msd[a] = dev;
+    }
+}
+
+}  // namespace hp
+
+using namespace hp;
+
+extern "C" int hp_spline_build(int32_t natom, const int32_t* knot_offsets, const double* knots,
+                               const double* values, int32_t clip_negative, double* coef,
+                               double* work, void* stream) {
+    HP_REQUIRE(natom > 0 && knot_offsets && knots && values && coef && work, "bad arguments");
+    spline_build_kernel<<<(natom + 63) / 64, 64, 0, as_stream(stream)>>>(natom, knot_offsets, knots,
+                                                                         values, clip_negative, coef, work);
+    HP_LAUNCH_CHECK("spline_build_kernel");
+    return HP_OK;
+}
+
+extern "C" int hp_promol_weights_spline(int64_t npts, const double* px, const double* py,
+                                        const double* pz, int64_t point_base, int32_t natom,
+                                        const double* atom_xyz, const int64_t* atom_point_offsets,
+                                        const int32_t* knot_offsets, const double* knots,
+                                        const double* coef, double proatom_offset, const double* rho,
+                                        const double* molw, double density_cutoff, double* promol,
+                                        double* at_weights, double* entropy_partials, void* stream) {
+    HP_REQUIRE(npts >= 0 && natom > 0, "bad sizes");
+    HP_REQUIRE(px && py && pz && atom_xyz && atom_point_offsets && knot_offsets && knots && coef,
+               "null input");
+    HP_REQUIRE(!entropy_partials || (rho && molw), "entropy needs rho and molw");
+    const int npartial = hp_num_partials();
+    if (npts == 0) {
+        if (entropy_partials)
+            return check_cuda(cudaMemsetAsync(entropy_partials, 0, sizeof(double) * npartial,
+                                              as_stream(stream)), "memset partials");
+        return HP_OK;
+    }
+    int per_sm = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, promol_weights_spline_kernel, kSplThreads, 0);
+    if (per_sm < 1) per_sm = 1;
+    const int64_t span = int64_t(kSplThreads) * kSplPts;
+    int64_t grid = (npts + span - 1) / span;
+    int64_t cap = int64_t(sm_count()) * per_sm;
+    if (cap > npartial) cap = npartial;
+    if (grid > cap) grid = cap;
+    promol_weights_spline_kernel<<<int(grid), kSplThreads, 0, as_stream(stream)>>>(
+        npts, px, py, pz, point_base, natom, atom_xyz, atom_point_offsets, knot_offsets, knots, coef,
+        proatom_offset, rho, molw, density_cutoff, promol, at_weights, entropy_partials, npartial);
+    HP_LAUNCH_CHECK("promol_weights_spline_kernel");
+    return HP_OK;
+}
+
+extern "C" int hp_isa_update(int32_t natom, int32_t atom_base, const int32_t* rad_offsets,
+                             const double* rad_r, const double* rad_w, const double* sph_avg,
+                             const int32_t* par_offsets, double* propars, const double* pseudo_numbers,
+                             double* charges, double* msd, void* stream) {
+    HP_REQUIRE(natom >= 0, "bad sizes");
+    if (natom == 0) return HP_OK;
+    HP_REQUIRE(rad_offsets && rad_r && rad_w && sph_avg && par_offsets && propars && pseudo_numbers &&
+                   charges && msd, "null input");
+    isa_update_kernel<<<natom, 32, 0, as_stream(stream)>>>(natom, atom_base, rad_offsets, rad_r, rad_w,
+                                                           sph_avg, par_offsets, propars,
+                                                           pseudo_numbers, charges, msd);
+    HP_LAUNCH_CHECK("isa_update_kernel");
+    return HP_OK;
+}

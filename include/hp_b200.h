@@ -173,6 +173,32 @@ HP_API int hp_lisa_sc_radial_solve(int32_t natom, int32_t atom_base, const int32
                                    int32_t nshell_max, double* charges, double* msd,
                                    int32_t* niter, uint32_t* flags, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Spline pro-atoms (ISA / Hirshfeld / Hirshfeld-I).
+ * hp_spline_build: SciPy `CubicSpline(x, y)` (not-a-knot, extrapolating) per atom, as built by
+ * get_proatom_spline (core/stockholder.py:259-269).  knot_offsets (natom+1) index `knots` and
+ * `values`; atom a owns n_a-1 segments of 4 coefficients (c0..c3, highest power first) starting at
+ * coef[4*(knot_offsets[a]-a)].  clip_negative != 0 applies fix_proatom_rho (:218-219).  `work`
+ * needs 2 doubles per knot.
+ * hp_promol_weights_spline: like hp_promol_weights with rho0_a(p) = S_a(|r_p-R_a|) + proatom_offset
+ * (eval_spline / eval_proatom, core/stockholder.py:271-350; proatom_offset = 1e-100).
+ * hp_isa_update: propars_a = max(sph_avg_a, 1e-100), charge, change term (isa.py:102-122);
+ * rad_w are the plain radial weights (rgrid.weights). */
+HP_API int hp_spline_build(int32_t natom, const int32_t* knot_offsets, const double* knots,
+                           const double* values, int32_t clip_negative, double* coef, double* work,
+                           void* stream);
+HP_API int hp_promol_weights_spline(int64_t npts, const double* px, const double* py,
+                                    const double* pz, int64_t point_base, int32_t natom,
+                                    const double* atom_xyz, const int64_t* atom_point_offsets,
+                                    const int32_t* knot_offsets, const double* knots,
+                                    const double* coef, double proatom_offset, const double* rho,
+                                    const double* molw, double density_cutoff, double* promol,
+                                    double* at_weights, double* entropy_partials, void* stream);
+HP_API int hp_isa_update(int32_t natom, int32_t atom_base, const int32_t* rad_offsets,
+                         const double* rad_r, const double* rad_w, const double* sph_avg,
+                         const int32_t* par_offsets, double* propars, const double* pseudo_numbers,
+                         double* charges, double* msd, void* stream);
+
 /* Sum the entropy partials and sqrt(sum msd) in a fixed order: out[0] = change, out[1] = entropy. */
 HP_API int hp_finish_iteration(int32_t npartial, const double* entropy_partials, int32_t natom,
                         const double* msd, double* out2, void* stream);

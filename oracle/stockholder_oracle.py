@@ -418,3 +418,35 @@ def nlis(coords, numbers, pseudo, grid, rho, exp_n_dict=None, nshell_dict=None, 
         lambda a, sph, par, w4, r: nlis_inner(sph, par, w4, r, inner_threshold, cutoff),
         threshold, maxiter, cutoff, coords,
     )  # fmt: skip
+
+
+# ----------------------------------------------------------------------------------------------
+# ISA  (isa.py, spline pro-atoms of core/stockholder.py:202-350)
+# ----------------------------------------------------------------------------------------------
+def isa_proatom(rgrid_points, par, r):
+    """get_proatom_spline + eval_spline + eval_proatom: clip negatives, not-a-knot CubicSpline
+    (extrapolating), + 1e-100 (core/stockholder.py:218-219, 266-267, 300-302, 349)."""
+    from scipy.interpolate import CubicSpline
+
+    rho = par.copy()
+    rho[rho < 0] = 0.0
+    return CubicSpline(rgrid_points, rho, True)(r) + 1e-100
+
+
+def isa(coords, numbers, pseudo, grid, rho, threshold=1e-6, maxiter=500, cutoff=DENSITY_CUTOFF):
+    """ISAWPart.do_partitioning(), isa.py:93-122."""
+    natom = len(numbers)
+    sizes = [g.rgrid.size for g in grid.atgrids]
+    ranges = np.concatenate([[0], np.cumsum(sizes)]).tolist()
+    propars = np.zeros(ranges[-1])
+
+    def update(a, sph, par, w4, r):
+        # isa.py:108-110 (the spline of the spherical average is evaluated at its own knots)
+        return np.clip(sph, 1e-100, np.inf), 0
+
+    out = _iterate(
+        grid, rho, natom, pseudo, propars, ranges,
+        lambda a, par, r: isa_proatom(grid.atgrids[a].rgrid.points, par, r),
+        update, threshold, maxiter, cutoff, coords,
+    )  # fmt: skip
+    return out

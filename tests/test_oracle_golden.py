@@ -71,3 +71,13 @@ def test_nlis_known_answers():
     np.testing.assert_allclose(p, [4.0, 16.0, 1.0, 4.0, 0.5, 1.0])
     p = oracle.nlis_initial(8, {(8, 1): 2.0}, {8: 3})
     assert len(p) == 9 and p[5] == 2.0 and p[0] == pytest.approx(8 / 3)
+
+
+def test_isa_matches_reference_run(h2o, water6):
+    res = oracle.isa(h2o["coords"], h2o["numbers"], h2o["pseudo"], h2o["grid"], h2o["rho"])
+    _check(res, h2o["gold"], "isa")
+    assert res["niter"] == 36
+    # reference golden, tests/test_wpart.py:90-92 (tolerance :61)
+    assert abs(res["charges"] - np.array([-0.490017586929, 0.245018706885, 0.244998880045])).max() < 2e-3
+    res = oracle.isa(water6["coords"], water6["numbers"], water6["pseudo"], water6["grid"], water6["rho"], maxiter=60)
+    _check(res, water6["gold"], "isa", rtol=1e-8, qtol=1e-10)
