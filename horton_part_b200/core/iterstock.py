@@ -26,7 +26,51 @@ from .. import _lib
 from .cache import just_once
 from .stockholder import AbstractStockholderWPart
 
-__all__ = ["AbstractISAWPart"]
+__all__ = ["AbstractISAWPart", "IterationState"]
+
+
+class IterationState:
+    """Per-iteration state in ONE contiguous FP64 vector
+
+        [ entropy | msd (natom) | charges (natom) | propars (npar) ]
+
+    so that every run needs a single small D2H per iteration and a sharded run a single
+    all-reduce: each rank zero-fills the vector, writes the entries of the atoms it owns (plus its
+    partial entropy) and the SUM all-reduce then acts as an all-gather (x + 0 = x exactly, so the
+    result is independent of the reduction order) while also summing the entropy."""
+
+    def __init__(self, natom, npar, device):
+        import torch
+
+        n = natom
+        self.natom, self.npar = natom, npar
+        self.vec = torch.zeros(1 + 2 * n + npar, dtype=torch.float64, device=device)
+        self.entropy = self.vec[0:1]
+        self.msd = self.vec[1 : 1 + n]
+        self.charges = self.vec[1 + n : 1 + 2 * n]
+        self.propars = self.vec[1 + 2 * n :]
+        self.out2 = torch.zeros(2, dtype=torch.float64, device=device)
+        self.niter = torch.zeros(n, dtype=torch.int32, device=device)
+        self.flags = torch.zeros(n, dtype=torch.int32, device=device)
+        self.host = torch.empty(self.vec.numel() + 2, dtype=torch.float64)
+        if torch.device(device).type == "cuda":
+            self.host = self.host.pin_memory()
+        self.events = []
+        self.propars_prev = None
+
+    def begin_sharded_update(self, par_lo, par_hi):
+        """Zero everything this iteration will gather; keep the local atoms' parameters, which
+        are the starting point of their solves."""
+        self.propars_prev = self.propars.clone()
+        self.msd.zero_()
+        self.charges.zero_()
+        self.propars.zero_()
+        self.propars[par_lo:par_hi] = self.propars_prev[par_lo:par_hi]
+
+    def gather(self, comm):
+        import torch.distributed as dist
+
+        dist.all_reduce(self.vec, op=dist.ReduceOp.SUM, group=comm)
 
 
 class AbstractISAWPart(AbstractStockholderWPart):
@@ -69,30 +113,8 @@ class AbstractISAWPart(AbstractStockholderWPart):
 
     # -- device state ---------------------------------------------------------------------------
     def _alloc_state(self, npar):
-        """One contiguous device vector [entropy | msd(natom) | charges(natom) | propars(npar)]
-        so that a sharded run needs a single all-reduce and every run a single D2H per iteration."""
-        import torch
-
-        dev = self.slab.device
-        n = self.natom
-        vec = torch.zeros(1 + 2 * n + npar, dtype=torch.float64, device=dev)
-
-        class _State:
-            pass
-
-        st = _State()
-        st.vec = vec
-        st.entropy = vec[0:1]
-        st.msd = vec[1 : 1 + n]
-        st.charges = vec[1 + n : 1 + 2 * n]
-        st.propars = vec[1 + 2 * n :]
-        st.out2 = torch.zeros(2, dtype=torch.float64, device=dev)
-        st.niter = torch.zeros(n, dtype=torch.int32, device=dev)
-        st.flags = torch.zeros(n, dtype=torch.int32, device=dev)
-        st.host = torch.empty(vec.numel() + 2, dtype=torch.float64).pin_memory()
-        st.events = []
-        self._state = st
-        return st
+        self._state = IterationState(self.natom, npar, self.slab.device)
+        return self._state
 
     def _run_iteration(self):
         """One outer iteration on the device; returns (change, entropy) after one host sync."""
@@ -108,17 +130,12 @@ class AbstractISAWPart(AbstractStockholderWPart):
         self._launch_promol_weights(want_entropy=True)
         ev[1].record()
         if sharded:
-            st.msd.zero_()
-            st.charges.zero_()
-            st.propars_prev = st.propars.clone()
-            st.propars.zero_()
-            self._restore_local_propars(st)
+            sh = slab.shard
+            st.begin_sharded_update(self._ranges[sh.atom_lo], self._ranges[sh.atom_hi])
         self._launch_radial_update()
         if sharded:
-            import torch.distributed as dist
-
             _lib.call("hp_sum_partials", slab.npartial, slab.entropy_partials, st.entropy, stream_ptr(dev))
-            dist.all_reduce(st.vec, group=self._comm)
+            st.gather(self._comm)
             _lib.call("hp_finish_iteration", 1, st.entropy, self.natom, st.msd, st.out2, stream_ptr(dev))
         else:
             _lib.call("hp_finish_iteration", slab.npartial, slab.entropy_partials, self.natom, st.msd,
@@ -134,13 +151,6 @@ class AbstractISAWPart(AbstractStockholderWPart):
         self.cache.load("propars")[:] = host[1 + 2 * n : nv]
         self.cache.load("charges", alloc=n, tags="o")[0][:] = host[1 + n : 1 + 2 * n]
         return float(host[nv]), float(host[nv + 1])
-
-    def _restore_local_propars(self, st):
-        """Sharded runs zero the global parameter vector before the solve so that the all-reduce
-        acts as an all-gather; the local atoms' previous values are the solver's starting point."""
-        sh = self.slab.shard
-        lo, hi = self._ranges[sh.atom_lo], self._ranges[sh.atom_hi]
-        st.propars[lo:hi] = st.propars_prev[lo:hi]
 
     # -- the loop -------------------------------------------------------------------------------
     def _finalize_propars(self):

@@ -1,0 +1,72 @@
+"""Sharded (multi-GPU) MBIS equals the single-GPU run: identical iteration count, charges to 1e-12.
+Needs >= 2 GPUs (run with `gpurun --gpus 2`); skipped on a single-GPU box."""
+
+import os
+import socket
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, payload, out):
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, root)
+    import logging
+
+    import torch
+    import torch.distributed as dist
+
+    logging.disable(logging.INFO)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    from horton_part_b200 import ISAWPart, LinearISAWPart, MBISWPart
+
+    coords, numbers, pseudo, grid, rho = payload
+    res = {}
+    for name, cls, kw in (("mbis", MBISWPart, {}), ("lisa", LinearISAWPart, dict(solver="sc", maxiter=15)),
+                          ("isa", ISAWPart, dict(maxiter=10))):
+        part = cls(coords, numbers, pseudo, grid, rho, device=torch.device("cuda", rank), comm=dist.group.WORLD, **kw)
+        part.do_charges()
+        res[name] = (int(part["niter"]), part["charges"].copy(), part["propars"].copy(),
+                     np.array(part["history_entropies"]), np.array(part["history_changes"]))
+    out[rank] = res
+    dist.destroy_process_group()
+
+
+def test_sharded_equals_single_gpu(make_water):
+    import torch
+    import torch.multiprocessing as mp
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    from horton_part_b200 import ISAWPart, LinearISAWPart, MBISWPart
+
+    case = make_water(9, nrad=30, nang=38, seed=2)
+    payload = (case["coords"], case["numbers"], case["pseudo"], case["grid"], case["rho"])
+    manager = mp.Manager()
+    out = manager.dict()
+    mp.spawn(_worker, args=(2, _free_port(), payload, out), nprocs=2, join=True)
+    for name, cls, kw in (("mbis", MBISWPart, {}), ("lisa", LinearISAWPart, dict(solver="sc", maxiter=15)),
+                          ("isa", ISAWPart, dict(maxiter=10))):
+        single = cls(*payload, **kw)
+        single.do_charges()
+        for rank in (0, 1):
+            niter, charges, propars, ent, chg = out[rank][name]
+            assert niter == single["niter"], name
+            np.testing.assert_allclose(charges, single["charges"], rtol=0, atol=1e-12, err_msg=name)
+            np.testing.assert_allclose(propars, single["propars"], rtol=1e-11, atol=1e-14, err_msg=name)
+            np.testing.assert_allclose(ent, single["history_entropies"], rtol=1e-12, atol=1e-14, err_msg=name)
+            np.testing.assert_allclose(chg, single["history_changes"], rtol=1e-9, err_msg=name)
+        assert np.array_equal(out[0][name][1], out[1][name][1])  # ranks agree bit for bit
