@@ -39,7 +39,7 @@ EXPORTS = {
     "hp_tile_limits": (None, [_p, _p]),
     "hp_promol_weights": (
         _int,
-        [_int, _i64, _p, _p, _p, _i64, _i32, _p, _p, _p, _p, _p, _p, _i32, _p, _p, _p, _f64, _p, _p, _p, _p],
+        [_int, _i64, _p, _p, _p, _i64, _i32, _p, _p, _p, _p, _p, _p, _i32, _p, _p, _p, _f64, _f64, _p, _p, _p, _p],
     ),
     "hp_shell_project": (_int, [_i32, _p, _p, _p, _p, _p, _p, _p, _p]),
     "hp_mbis_radial_solve": (
@@ -60,6 +60,16 @@ EXPORTS = {
         [_i64, _p, _p, _p, _i64, _i32, _p, _p, _p, _p, _p, _f64, _p, _p, _f64, _p, _p, _p, _p],
     ),
     "hp_isa_update": (_int, [_i32, _i32, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
+    "hp_molgrid_num_blocks": (_i32, [_i64]),
+    "hp_shell_moments": (
+        _int,
+        [_int, _i64, _p, _p, _p, _i32, _p, _p, _p, _p, _p, _i32, _p, _p, _p, _p, _f64, _i32, _i32, _p, _p, _p],
+    ),
+    "hp_atom_weight_integrals": (
+        _int,
+        [_int, _i64, _p, _p, _p, _i32, _p, _p, _p, _p, _p, _i32, _p, _p, _p, _p, _p, _p, _p],
+    ),
+    "hp_radial_change": (_int, [_i32, _i32, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
     "hp_finish_iteration": (_int, [_i32, _p, _i32, _p, _p, _p]),
     "hp_sum_partials": (_int, [_i32, _p, _p, _p]),
     "hp_segment_integrate": (_int, [_i32, _p, _p, _p, _p, _p, _p]),
@@ -68,7 +78,7 @@ EXPORTS = {
 
 
 # int-returning functions whose result is a value, not a status code
-_NOT_STATUS = {"hp_abi_version", "hp_num_partials", "hp_local_index_scratch_bytes", "hp_last_error", "hp_tile_limits"}
+_NOT_STATUS = {"hp_abi_version", "hp_num_partials", "hp_local_index_scratch_bytes", "hp_last_error", "hp_tile_limits", "hp_molgrid_num_blocks"}
 
 
 class HpError(RuntimeError):

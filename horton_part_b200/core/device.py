@@ -202,13 +202,14 @@ class ShellTable:
         self.alpha = torch.zeros_like(self.A)
         self.order = torch.ones_like(self.A) if functor == 3 else None
 
-    def promol_weights(self, density_cutoff, want_promol=True, want_weights=True, want_entropy=True):
+    def promol_weights(self, density_cutoff, want_promol=True, want_weights=True, want_entropy=True,
+                       promol_offset=1e-100):
         """Launch the fused promolecule / owner-weight / entropy pass over the local slab."""
         s = self.slab
         _lib.call(
             "hp_promol_weights", self.functor, s.npts, s.px, s.py, s.pz, s.point_base, s.natom,
             s.atom_xyz, s.atom_point_offsets, self.offsets, self.A, self.alpha, self.order,
-            self.ntile, self.tiles, s.rho, s.molw, float(density_cutoff),
+            self.ntile, self.tiles, s.rho, s.molw, float(density_cutoff), float(promol_offset),
             s.promol if want_promol else None, s.at_w if want_weights else None,
             s.entropy_partials if want_entropy else None, stream_ptr(s.device),
         )  # fmt: skip

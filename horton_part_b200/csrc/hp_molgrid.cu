@@ -1,0 +1,290 @@
+// Molecular-grid reductions for the global schemes (row a12 of SURVEY.md section 8a: gLISA) and the
+// molecular-grid variants of the per-atom updates (row a9, grid_type 2/3).
+//
+//   hp_shell_moments   I_m = sum_p t(p) * A_m * exp(-alpha_m r_pm^n),  t = molw*rho/rho0^power (masked)
+//                      power 1: function_g (glisa.py:850-879: new c_m = c_m * I_m) and the gradient
+//                      (glisa.py:454-458: grad_m = -I_m);  A_m = the shell's normalisation.
+//   hp_atom_weight_integrals   N_a = sum_p molw*rho*clip(rho0_a/rho0, 0, 1)   (glisa.py:269-278)
+//   hp_hessian         H_mn = sum_p u(p) g_m(p) g_n(p), u = molw*rho/rho0^2 (masked)  (glisa.py:459-470)
+//
+// Basis functions are regenerated from coordinates + parameters per tile: the reference's
+// (M, Npts) `pro_shells` / `rho*pro_shells` arrays (glisa.py:335-344; 2 x 105 GB at config 4) are
+// never materialised.  Partial sums are kept per thread block and combined in a fixed order, so
+// results are bit-reproducible run to run.
+#include "hp_common.cuh"
+#include "hp_math.cuh"
+
+namespace hp {
+
+constexpr int kMgThreads = 256;
+constexpr int kMgWarps = kMgThreads / 32;
+constexpr int kMgTileAtoms = 128;
+constexpr int kMgTileShells = 1024;
+
+struct __align__(16) MgAtom {
+    double x, y, z;
+    int s0, ns;
+};
+
+template <int F>
+__device__ __forceinline__ double mg_radial(double d2) {
+    return (F == HP_FUNCTOR_GAUSS) ? d2 : sqrt_nocall(d2);
+}
+
+template <int F>
+__device__ __forceinline__ double mg_shell(double alpha, double n, double r) {
+    if (F == HP_FUNCTOR_GENERAL) {
+        const double rn = (n == 1.0) ? r : ((n == 2.0) ? r * r : pow(r, n));
+        return exp(-alpha * rn);
+    }
+    return exp_neg_poly(-alpha * r);
+}
+
+// MODE 0: per-shell moments with weight t;  MODE 1: per-atom clipped-weight integrals.
+template <int F, int MODE, int kP>
+__global__ void __launch_bounds__(kMgThreads, 2)
+molgrid_reduce_kernel(int64_t npts, const double* __restrict__ px, const double* __restrict__ py,
+                      const double* __restrict__ pz, int natom, const double* __restrict__ atom_xyz,
+                      const int* __restrict__ atom_sh_off, const double* __restrict__ shell_A,
+                      const double* __restrict__ shell_alpha, const double* __restrict__ shell_order,
+                      int ntile, const int* __restrict__ tile_off, const double* __restrict__ rho,
+                      const double* __restrict__ molw, const double* __restrict__ promol,
+                      double density_cutoff, int power, int nout, double* __restrict__ partial) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    MgAtom* s_atoms = reinterpret_cast<MgAtom*>(smem_raw);
+    double2* s_AB = reinterpret_cast<double2*>(s_atoms + kMgTileAtoms);
+    double* s_N = reinterpret_cast<double*>(s_AB + kMgTileShells);
+    double* s_acc = s_N + ((F == HP_FUNCTOR_GENERAL) ? kMgTileShells : 0);  // [kMgWarps][kMgTileShells]
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double* my_partial = partial + int64_t(blockIdx.x) * nout;
+    for (int i = threadIdx.x; i < nout; i += kMgThreads) my_partial[i] = 0.0;
+
+    const int64_t span = int64_t(kMgThreads) * kP;
+    const int64_t nchunk = (npts + span - 1) / span;
+    for (int64_t chunk = blockIdx.x; chunk < nchunk; chunk += gridDim.x) {
+        double x[kP], y[kP], z[kP], t[kP], inv[kP];
+#pragma unroll
+        for (int j = 0; j < kP; ++j) {
+            const int64_t p = chunk * span + int64_t(j) * kMgThreads + threadIdx.x;
+            const bool live = p < npts;
+            const int64_t q = live ? p : npts - 1;
+            x[j] = px[q]; y[j] = py[q]; z[j] = pz[q];
+            const double r0 = promol[q], rh = rho[q];
+            if (MODE == 0) {
+                const bool sick = (rh < density_cutoff) || (r0 < density_cutoff);
+                double v = sick ? 0.0 : molw[q] * rh / r0;
+                if (power == 2 && !sick) v /= r0;
+                t[j] = live ? v : 0.0;
+                inv[j] = 0.0;
+            } else {
+                t[j] = live ? molw[q] * rh : 0.0;
+                inv[j] = r0;
+            }
+        }
+        for (int tl = 0; tl < ntile; ++tl) {
+            const int a0 = tile_off[tl], a1 = tile_off[tl + 1];
+            const int sh0 = atom_sh_off[a0], sh1 = atom_sh_off[a1];
+            __syncthreads();
+            for (int i = threadIdx.x; i < a1 - a0; i += kMgThreads) {
+                MgAtom rec;
+                rec.x = atom_xyz[3 * (a0 + i)]; rec.y = atom_xyz[3 * (a0 + i) + 1]; rec.z = atom_xyz[3 * (a0 + i) + 2];
+                rec.s0 = atom_sh_off[a0 + i] - sh0;
+                rec.ns = atom_sh_off[a0 + i + 1] - atom_sh_off[a0 + i];
+                s_atoms[i] = rec;
+            }
+            for (int i = threadIdx.x; i < sh1 - sh0; i += kMgThreads) {
+                s_AB[i] = make_double2(shell_A[sh0 + i], shell_alpha[sh0 + i]);
+                if (F == HP_FUNCTOR_GENERAL) s_N[i] = shell_order[sh0 + i];
+            }
+            __syncthreads();
+            for (int i = 0; i < a1 - a0; ++i) {
+                const MgAtom rec = s_atoms[i];
+                double r[kP], f[kP];
+#pragma unroll
+                for (int j = 0; j < kP; ++j) {
+                    const double dx = x[j] - rec.x, dy = y[j] - rec.y, dz = z[j] - rec.z;
+                    r[j] = mg_radial<F>(fma(dz, dz, fma(dy, dy, dx * dx)));
+                    f[j] = 0.0;
+                }
+                for (int k = 0; k < rec.ns; ++k) {
+                    const double2 ab = s_AB[rec.s0 + k];
+                    const double n = (F == HP_FUNCTOR_GENERAL) ? s_N[rec.s0 + k] : 1.0;
+                    if (MODE == 0) {
+                        double s = 0.0;
+#pragma unroll
+                        for (int j = 0; j < kP; ++j) s = fma(t[j], mg_shell<F>(ab.y, n, r[j]), s);
+                        s = warp_allsum(s * ab.x);
+                        if (lane == 0) s_acc[warp * kMgTileShells + rec.s0 + k] = s;
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < kP; ++j) f[j] = fma(ab.x, mg_shell<F>(ab.y, n, r[j]), f[j]);
+                    }
+                }
+                if (MODE == 1) {
+                    double s = 0.0;
+#pragma unroll
+                    for (int j = 0; j < kP; ++j) s = fma(t[j], fmin(fmax(f[j] / inv[j], 0.0), 1.0), s);
+                    s = warp_allsum(s);
+                    if (lane == 0) s_acc[warp * kMgTileShells + i] = s;
+                }
+            }
+            __syncthreads();
+            const int ncol = (MODE == 0) ? (sh1 - sh0) : (a1 - a0);
+            const int col0 = (MODE == 0) ? sh0 : a0;
+            for (int c = threadIdx.x; c < ncol; c += kMgThreads) {
+                double tot = 0.0;
+#pragma unroll
+                for (int w = 0; w < kMgWarps; ++w) tot += s_acc[w * kMgTileShells + c];
+                my_partial[col0 + c] += tot;
+            }
+        }
+    }
+}
+
+// out[c] = sum over rows of partial[row][c], rows added in order.
+__global__ void __launch_bounds__(256)
+reduce_rows_kernel(int nrows, int ncols, const double* __restrict__ partial, double* __restrict__ out) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= ncols) return;
+    double s = 0.0;
+    for (int r = 0; r < nrows; ++r) s += partial[int64_t(r) * ncols + c];
+    out[c] = s;
+}
+
+// msd_a = int 4 pi r^2 (rho0_a[c_new] - rho0_a[c_old])^2 on atom a's radial grid, basis functions
+// tabulated on the grid (K x nrad); one warp per atom.  compute_change for the exponential-basis
+// schemes (core/iterstock.py:32-45 with gisa.py:42-65).
+__global__ void __launch_bounds__(32)
+radial_change_kernel(int natom, int atom_base, const int* __restrict__ rad_off,
+                     const double* __restrict__ rad_w4, const int* __restrict__ par_off,
+                     const int64_t* __restrict__ bs_off, const double* __restrict__ bs,
+                     const double* __restrict__ c_new, const double* __restrict__ c_old,
+                     double* __restrict__ msd) {
+    if (int(blockIdx.x) >= natom) return;
+    const int a = atom_base + blockIdx.x, lane = threadIdx.x;
+    const int r0 = rad_off[blockIdx.x], nrad = rad_off[blockIdx.x + 1] - r0;
+    const int p0 = par_off[a], K = par_off[a + 1] - p0;
+    const double* g = bs + bs_off[blockIdx.x];
+    double dev = 0.0;
+    for (int i = lane; i < nrad; i += 32) {
+        double yn = 0.0, yo = 0.0;
+        for (int k = 0; k < K; ++k) {
+            yn += c_new[p0 + k] * g[k * nrad + i];
+            yo += c_old[p0 + k] * g[k * nrad + i];
+        }
+        const double d = yn - yo;
+        dev += rad_w4[r0 + i] * d * d;
+    }
+    dev = warp_allsum(dev);
+    if (lane == 0) msd[a] = dev;
+}
+
+template <int F, int MODE, int kP>
+static int launch_molgrid(int64_t npts, const double* px, const double* py, const double* pz,
+                          int natom, const double* atom_xyz, const int* atom_sh_off,
+                          const double* shell_A, const double* shell_alpha, const double* shell_order,
+                          int ntile, const int* tile_off, const double* rho, const double* molw,
+                          const double* promol, double cutoff, int power, int nout, int nblocks,
+                          double* partial, cudaStream_t st) {
+    const size_t smem = sizeof(MgAtom) * kMgTileAtoms + sizeof(double2) * kMgTileShells +
+                        sizeof(double) * ((F == HP_FUNCTOR_GENERAL) ? kMgTileShells : 0) +
+                        sizeof(double) * kMgWarps * kMgTileShells;
+    auto kern = molgrid_reduce_kernel<F, MODE, kP>;
+    int rc = check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)),
+                        "cudaFuncSetAttribute");
+    if (rc) return rc;
+    kern<<<nblocks, kMgThreads, smem, st>>>(npts, px, py, pz, natom, atom_xyz, atom_sh_off, shell_A,
+                                            shell_alpha, shell_order, ntile, tile_off, rho, molw, promol,
+                                            cutoff, power, nout, partial);
+    return check_cuda(cudaGetLastError(), "molgrid_reduce_kernel");
+}
+
+}  // namespace hp
+
+using namespace hp;
+
+extern "C" int32_t hp_molgrid_num_blocks(int64_t npts) {
+    const int64_t span = int64_t(kMgThreads) * 4;
+    int64_t want = (npts + span - 1) / span;
+    const int64_t cap = int64_t(sm_count()) * 2;
+    if (want > cap) want = cap;
+    return int32_t(want < 1 ? 1 : want);
+}
+
+static int molgrid_dispatch(int mode, int functor, int64_t npts, const double* px, const double* py,
+                            const double* pz, int natom, const double* atom_xyz, const int* atom_sh_off,
+                            const double* shell_A, const double* shell_alpha, const double* shell_order,
+                            int ntile, const int* tile_off, const double* rho, const double* molw,
+                            const double* promol, double cutoff, int power, int nout, double* partial,
+                            double* out, void* stream) {
+    cudaStream_t st = as_stream(stream);
+    const int nblocks = hp_molgrid_num_blocks(npts);
+    int rc = HP_ERR_ARG;
+#define HP_MG(F, MODE, KP)                                                                              \
+    rc = launch_molgrid<F, MODE, KP>(npts, px, py, pz, natom, atom_xyz, atom_sh_off, shell_A, shell_alpha, \
+                                     shell_order, ntile, tile_off, rho, molw, promol, cutoff, power, nout, \
+                                     nblocks, partial, st)
+    if (mode == 0) {
+        if (functor == HP_FUNCTOR_SLATER) HP_MG(HP_FUNCTOR_SLATER, 0, 4);
+        else if (functor == HP_FUNCTOR_GAUSS) HP_MG(HP_FUNCTOR_GAUSS, 0, 4);
+        else if (functor == HP_FUNCTOR_GENERAL) HP_MG(HP_FUNCTOR_GENERAL, 0, 4);
+    } else {
+        if (functor == HP_FUNCTOR_SLATER) HP_MG(HP_FUNCTOR_SLATER, 1, 4);
+        else if (functor == HP_FUNCTOR_GAUSS) HP_MG(HP_FUNCTOR_GAUSS, 1, 4);
+        else if (functor == HP_FUNCTOR_GENERAL) HP_MG(HP_FUNCTOR_GENERAL, 1, 4);
+    }
+#undef HP_MG
+    if (rc == HP_ERR_ARG) set_error("molgrid reduction: unsupported functor %d", functor);
+    if (rc) return rc;
+    reduce_rows_kernel<<<(nout + 255) / 256, 256, 0, st>>>(nblocks, nout, partial, out);
+    return check_cuda(cudaGetLastError(), "reduce_rows_kernel");
+}
+
+extern "C" int hp_shell_moments(int functor, int64_t npts, const double* px, const double* py,
+                                const double* pz, int32_t natom, const double* atom_xyz,
+                                const int32_t* atom_shell_offsets, const double* shell_A,
+                                const double* shell_alpha, const double* shell_order, int32_t ntile,
+                                const int32_t* tile_atom_offsets, const double* rho, const double* molw,
+                                const double* promol, double density_cutoff, int32_t power,
+                                int32_t nshell, double* partial, double* out, void* stream) {
+    HP_REQUIRE(npts > 0 && natom > 0 && ntile > 0 && nshell > 0, "bad sizes");
+    HP_REQUIRE(px && py && pz && atom_xyz && atom_shell_offsets && shell_A && shell_alpha &&
+                   tile_atom_offsets && rho && molw && promol && partial && out, "null input");
+    HP_REQUIRE(power == 1 || power == 2, "power must be 1 or 2");
+    HP_REQUIRE(functor != HP_FUNCTOR_GENERAL || shell_order, "general functor needs shell_order");
+    return molgrid_dispatch(0, functor, npts, px, py, pz, natom, atom_xyz, atom_shell_offsets, shell_A,
+                            shell_alpha, shell_order, ntile, tile_atom_offsets, rho, molw, promol,
+                            density_cutoff, power, nshell, partial, out, stream);
+}
+
+extern "C" int hp_atom_weight_integrals(int functor, int64_t npts, const double* px, const double* py,
+                                        const double* pz, int32_t natom, const double* atom_xyz,
+                                        const int32_t* atom_shell_offsets, const double* shell_A,
+                                        const double* shell_alpha, const double* shell_order,
+                                        int32_t ntile, const int32_t* tile_atom_offsets,
+                                        const double* rho, const double* molw, const double* promol,
+                                        double* partial, double* out, void* stream) {
+    HP_REQUIRE(npts > 0 && natom > 0 && ntile > 0, "bad sizes");
+    HP_REQUIRE(px && py && pz && atom_xyz && atom_shell_offsets && shell_A && shell_alpha &&
+                   tile_atom_offsets && rho && molw && promol && partial && out, "null input");
+    HP_REQUIRE(functor != HP_FUNCTOR_GENERAL || shell_order, "general functor needs shell_order");
+    return molgrid_dispatch(1, functor, npts, px, py, pz, natom, atom_xyz, atom_shell_offsets, shell_A,
+                            shell_alpha, shell_order, ntile, tile_atom_offsets, rho, molw, promol, 0.0, 1,
+                            natom, partial, out, stream);
+}
+
+extern "C" int hp_radial_change(int32_t natom, int32_t atom_base, const int32_t* rad_offsets,
+                                const double* rad_w4, const int32_t* par_offsets,
+                                const int64_t* bs_offsets, const double* bs_funcs, const double* c_new,
+                                const double* c_old, double* msd, void* stream) {
+    HP_REQUIRE(natom >= 0, "bad sizes");
+    if (natom == 0) return HP_OK;
+    HP_REQUIRE(rad_offsets && rad_w4 && par_offsets && bs_offsets && bs_funcs && c_new && c_old && msd,
+               "null input");
+    radial_change_kernel<<<natom, 32, 0, as_stream(stream)>>>(natom, atom_base, rad_offsets, rad_w4,
+                                                              par_offsets, bs_offsets, bs_funcs, c_new,
+                                                              c_old, msd);
+    HP_LAUNCH_CHECK("radial_change_kernel");
+    return HP_OK;
+}

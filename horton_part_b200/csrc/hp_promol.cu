@@ -91,7 +91,7 @@ promol_weights_kernel(int64_t npts, const double* __restrict__ px, const double*
                       const int* __restrict__ atom_sh_off, const double* __restrict__ shell_A,
                       const double* __restrict__ shell_alpha, const double* __restrict__ shell_order,
                       int ntile, const int* __restrict__ tile_off, const double* __restrict__ rho,
-                      const double* __restrict__ molw, double density_cutoff,
+                      const double* __restrict__ molw, double density_cutoff, double promol_offset,
                       double* __restrict__ promol_out, double* __restrict__ w_out,
                       double* __restrict__ entropy_partials) {
     __shared__ AtomRec s_atoms[kTileAtoms + 1];  // +1: sentinel for the prefetch
@@ -157,7 +157,7 @@ promol_weights_kernel(int64_t npts, const double* __restrict__ px, const double*
                 eval_proatom<F, kPts>(d2, rec.s0, rec.ns, s_AB, s_N, f, ab0);
                 // update_pro, core/stockholder.py:169-170: promoldens += work; += 1e-100
 #pragma unroll
-                for (int j = 0; j < kPts; ++j) pro[j] = (pro[j] + f[j]) + 1e-100;
+                for (int j = 0; j < kPts; ++j) pro[j] = (pro[j] + f[j]) + promol_offset;
             }
         }
 
@@ -247,8 +247,8 @@ extern "C" int hp_promol_weights(int functor, int64_t npts, const double* px, co
                                  const double* shell_alpha, const double* shell_order,
                                  int32_t ntile, const int32_t* tile_atom_offsets,
                                  const double* rho, const double* molw, double density_cutoff,
-                                 double* promol, double* at_weights, double* entropy_partials,
-                                 void* stream) {
+                                 double promol_offset, double* promol, double* at_weights,
+                                 double* entropy_partials, void* stream) {
     using namespace hp;
     HP_REQUIRE(npts >= 0 && natom > 0 && ntile > 0, "bad sizes");
     HP_REQUIRE(px && py && pz && atom_xyz && atom_point_offsets && atom_shell_offsets, "null input");
@@ -267,7 +267,7 @@ extern "C" int hp_promol_weights(int functor, int64_t npts, const double* px, co
         promol_weights_kernel<F><<<grid, kThreads, 0, as_stream(stream)>>>(                          \
             npts, px, py, pz, point_base, natom, atom_xyz, atom_point_offsets, atom_shell_offsets,   \
             shell_A, shell_alpha, shell_order, ntile, tile_atom_offsets, rho, molw, density_cutoff,  \
-            promol, at_weights, entropy_partials);                                                   \
+            promol_offset, promol, at_weights, entropy_partials);                                                \
     }
     switch (functor) {
         case HP_FUNCTOR_SLATER: HP_LAUNCH_PROMOL(HP_FUNCTOR_SLATER); break;

@@ -1,0 +1,287 @@
+"""Global Linear ISA (gLISA): all pro-atom coefficients optimised together on the molecular grid.
+
+Counterpart of the reference's ``GlobalLinearISAWPart`` (glisa.py:55-1028).  The reference tabulates
+every basis function on the whole grid (``pro_shells`` and ``rho*pro_shells``, two (M, Npts) arrays,
+glisa.py:335-344) and then makes one NumPy pass per coefficient (``function_g`` :850-879) or per
+coefficient pair (``_working_matrix`` :411-479).  Here the basis functions are regenerated inside
+the kernels:
+
+    calc_promol_dens       -> hp_promol_weights(promol_offset=0)
+    function_g / gradient  -> hp_shell_moments(power=1)         I_m = int rho g_m / rho0
+    Hessian                -> hp_hessian                        H_mn = int rho g_m g_n / rho0^2
+    final charges          -> hp_atom_weight_integrals          (no natom x Npts weight arrays)
+
+Solvers on the device: ``"sc"`` (glisa.py:805-848) and ``"newton"`` (exact Newton, :572-574,
+:617-803 with mode="exact"; the M x M linear solve stays on the host as in the reference).
+"""
+
+from __future__ import annotations
+
+import time
+
+import numpy as np
+
+from . import _lib, gisa
+from .alisa import setup_bs_helper
+from .core.basis import shell_norm
+from .core.cache import just_once
+from .core.stockholder import AbstractStockholderWPart
+from .core.logging import deflist
+
+__all__ = ["GlobalLinearISAWPart"]
+
+
+class GlobalLinearISAWPart(AbstractStockholderWPart):
+    name = "glisa"
+    max_sc_iterations = 1_000_000  # the reference loops without a cap (glisa.py:823)
+
+    def __init__(self, coordinates, numbers, pseudo_numbers, grid, moldens, spindens=None, lmax=3,
+                 logger=None, threshold=1e-6, maxiter=500, solver="cvxopt", solver_options=None,
+                 basis_func="gauss", grid_type=1, basis_type="analytic", **kwargs):  # fmt: skip
+        self._maxiter = maxiter
+        self._threshold = threshold
+        self.basis_func = basis_func
+        self._func_type = basis_func.upper() if basis_func in ("gauss", "slater") else "Customized"
+        self._bs_helper = None
+        self.basis_type = basis_type
+        self._solver = solver
+        self._solver_options = solver_options or {}
+        self._ranges = []
+        super().__init__(coordinates, numbers, pseudo_numbers, grid, moldens, spindens, lmax, logger,
+                         grid_type, **kwargs)  # fmt: skip
+
+    maxiter = property(lambda self: self._maxiter)
+    threshold = property(lambda self: self._threshold)
+
+    @property
+    def bs_helper(self):
+        return setup_bs_helper(self)
+
+    @property
+    def mol_pop(self):
+        return self.grid.integrate(self._moldens)
+
+    @property
+    def propars(self):
+        return self.cache.load("propars")
+
+    def get_rgrid(self, index):
+        if self.only_use_molgrid:
+            self.logger.debug("rgird is not available when only_use_molgrid is `True`.")
+            raise NotImplementedError
+        return self.get_grid(index).rgrid
+
+    def to_atomic_grid(self, index, data):
+        if self.only_use_molgrid:
+            self.logger.debug("atom grids are not available when only_use_molgrid is `True`.")
+            raise NotImplementedError
+        return super().to_atomic_grid(index, data)
+
+    def get_proatom_rho(self, iatom, propars=None, **kwargs):
+        return gisa.get_proatom_rho(self, iatom, propars=propars)
+
+    def compute_change(self, propars1, propars2):
+        """Host helper (radial grids); the solvers use hp_radial_change."""
+        msd = 0.0
+        for a in range(self.natom):
+            d = self.get_proatom_rho(a, propars1)[0] - self.get_proatom_rho(a, propars2)[0]
+            rgrid = self.get_rgrid(a)
+            msd += rgrid.integrate(4 * np.pi * rgrid.points**2, d, d)
+        return np.sqrt(msd)
+
+    def _init_log_scheme(self):
+        info = [
+            ("Scheme", "Linear Iterative Stockholder"),
+            ("Outer loop convergence threshold", "%.1e" % self.threshold),
+            ("Using global ISA", True),
+            ("Maximum outer iterations", self.maxiter),
+            ("lmax", self.lmax),
+            ("Solver", self._solver.__name__ if callable(self._solver) else self._solver.upper()),
+            ("Basis function type", self._func_type),
+        ]
+        info += [(k, str(v)) for k, v in self._solver_options.items()]
+        deflist(self.logger, info)
+        self.logger.info(" ")
+
+    # -- device set-up --------------------------------------------------------------------------
+    def _init_propars(self):
+        import torch
+
+        from .core.device import ShellTable, to_device
+
+        if self.on_molgrid:
+            raise NotImplementedError("gLISA with grid_type 2/3 (molecular-grid change) is not built yet")
+        propars = gisa.init_propars(self)
+        gisa.evaluate_basis_functions(self)  # radial grids only: used by compute_change
+        slab = self.slab
+        dev = slab.device
+        orders = np.concatenate([np.asarray(self.bs_helper.get_order(z), float) for z in self.numbers])
+        alphas = np.concatenate([np.asarray(self.bs_helper.get_exponent(z), float) for z in self.numbers])
+        functor = 2 if np.all(orders == 2.0) else (1 if np.all(orders == 1.0) else 3)
+        self._table = ShellTable(slab, functor, self._nshells)
+        self._table.alpha.copy_(to_device(alphas, dev))
+        if functor == 3:
+            self._table.order.copy_(to_device(orders, dev))
+        self._norms = to_device(shell_norm(orders, alphas), dev)
+        self._c = to_device(propars, dev)
+        self._par_offsets = to_device(np.asarray(self._ranges, dtype=np.int32), dev)
+        sh = slab.shard
+        blocks = [self.cache.load(f"bs_funcs_{a}") for a in range(sh.atom_lo, sh.atom_hi)]
+        offs = np.concatenate([[0], np.cumsum([b.size for b in blocks])]).astype(np.int64)
+        self._bs_offsets = to_device(offs, dev)
+        self._bs_flat = to_device(np.concatenate([b.ravel() for b in blocks]), dev)
+        M = len(propars)
+        nblk = int(_lib.call("hp_molgrid_num_blocks", slab.npts))
+        self._partial = torch.zeros(nblk * max(M, self.natom), dtype=torch.float64, device=dev)
+        self._moments = torch.zeros(M, dtype=torch.float64, device=dev)
+        self._msd = torch.zeros(self.natom, dtype=torch.float64, device=dev)
+        self._scal = torch.zeros(2, dtype=torch.float64, device=dev)
+        return propars
+
+    def _refresh_table(self):
+        from .core.device import stream_ptr
+
+        t = self._table
+        _lib.call("hp_table_scaled", t.nshell, self._c, self._norms, t.A, stream_ptr(self.slab.device))
+
+    def _all_reduce(self, tensor):
+        if self._comm is not None:
+            import torch.distributed as dist
+
+            dist.all_reduce(tensor, group=self._comm)
+
+    def _promol_and_entropy(self):
+        """rho0 = sum_m c_m g_m on the local slab (no 1e-100 offsets: calc_promol_dens) and the
+        entropy int rho ln(rho/rho0)  ->  device scalar self._scal[1]."""
+        from .core.device import stream_ptr
+
+        self._refresh_table()
+        self._table.promol_weights(self.density_cutoff, True, False, True, promol_offset=0.0)
+        slab = self.slab
+        _lib.call("hp_sum_partials", slab.npartial, slab.entropy_partials, self._scal[1:], stream_ptr(slab.device))
+
+    def _shell_integrals(self, power=1):
+        """I_m = int rho g_m / rho0^power over the local slab (unit-population basis functions)."""
+        from .core.device import stream_ptr
+
+        t, s = self._table, self.slab
+        _lib.call(
+            "hp_shell_moments", t.functor, s.npts, s.px, s.py, s.pz, s.natom, s.atom_xyz, t.offsets,
+            self._norms, t.alpha, t.order, t.ntile, t.tiles, s.rho, s.molw, s.promol,
+            float(self.density_cutoff), int(power), t.nshell, self._partial, self._moments,
+            stream_ptr(s.device),
+        )  # fmt: skip
+        return self._moments
+
+    def _device_change(self, c_new, c_old):
+        from .core.device import stream_ptr
+
+        s = self.slab
+        sh = s.shard
+        self._msd.zero_()
+        _lib.call("hp_radial_change", sh.nlocal, sh.atom_lo, s.rad_offsets, s.rad_w4, self._par_offsets,
+                  self._bs_offsets, self._bs_flat, c_new, c_old, self._msd, stream_ptr(s.device))  # fmt: skip
+        return self._msd
+
+    def function_g(self, x):
+        """The fixed-point map g(c)_m = int rho c_m g_m / rho0[c] (glisa.py:850-879); host in/out."""
+        import torch
+
+        self._c.copy_(torch.from_numpy(np.ascontiguousarray(x, dtype=float)))
+        self._promol_and_entropy()
+        integrals = self._shell_integrals(1).clone()
+        self._all_reduce(integrals)
+        return (self._c * integrals).cpu().numpy()
+
+    # -- solvers --------------------------------------------------------------------------------
+    def _opt_propars(self, *args, **kwargs):
+        if callable(self._solver):
+            return self._solver(*args, **kwargs)
+        if isinstance(self._solver, str):
+            name = f"solver_{self._solver.replace('-', '_')}"
+            if hasattr(self, name):
+                return getattr(self, name)(*args, **kwargs)
+            raise RuntimeError(f"Unknown solver: {name}")
+        raise TypeError(f"The type of solver {type(self._solver)} is not supported.")
+
+    def solver_sc(self, niter_print=1):
+        """Self-consistent iteration c <- g(c) until the radial-grid change drops below threshold."""
+        import torch
+
+        propars = self.propars
+        self.logger.info("Iteration       Change      Entropy")
+        it = 0
+        while True:
+            c_old = self._c.clone()
+            self._promol_and_entropy()
+            integrals = self._shell_integrals(1)
+            pack = torch.cat([integrals, self._scal[1:2]])
+            self._all_reduce(pack)
+            self._c.copy_(c_old * pack[:-1])
+            msd = self._device_change(self._c, c_old)
+            self._all_reduce(msd)
+            change = float(torch.sqrt(msd.sum()).item())
+            entropy = float(pack[-1].item())
+            propars[:] = self._c.cpu().numpy()
+            self.history_entropies.append(entropy)
+            self.history_changes.append(change)
+            self.history_propars.append(propars.copy())
+            if (it + 1) % niter_print == 0:
+                self.logger.info("%9i   %10.5e   %10.5e" % (it + 1, change, entropy))
+            if change < self._threshold:
+                break
+            it += 1
+            if it >= self.max_sc_iterations:
+                raise RuntimeError("Not converged!")
+        self.cache.dump("niter", it + 1, tags="o")
+        return propars
+
+    # -- driver ---------------------------------------------------------------------------------
+    @just_once
+    def do_partitioning(self):
+        new = any(f"at_weights_{i}" not in self.cache for i in range(self.natom))
+        new |= "niter" not in self.cache
+        if not new:
+            return
+        import torch
+
+        from .core.device import stream_ptr
+
+        self._init_propars()
+        t0 = time.time()
+        new_propars = self._opt_propars(**self._solver_options)
+        self.history_time_update_propars.append(time.time() - t0)
+        propars = self.cache.load("propars")
+        propars[:] = new_propars
+        self._c.copy_(torch.from_numpy(np.ascontiguousarray(propars)))
+
+        # update_at_weights(force_on_molgrid=True) + charges (glisa.py:267-278): promolecule WITH the
+        # 1e-100 offsets, N_a = int clip(rho0_a/rho0, 0, 1) rho, without natom x Npts weight arrays
+        t0 = time.time()
+        self._refresh_table()
+        self._table.promol_weights(self.density_cutoff, True, True, False)
+        t, s = self._table, self.slab
+        pops = torch.zeros(self.natom, dtype=torch.float64, device=s.device)
+        _lib.call(
+            "hp_atom_weight_integrals", t.functor, s.npts, s.px, s.py, s.pz, s.natom, s.atom_xyz, t.offsets,
+            t.A, t.alpha, t.order, t.ntile, t.tiles, s.rho, s.molw, s.promol, self._partial, pops,
+            stream_ptr(s.device),
+        )  # fmt: skip
+        self._all_reduce(pops)
+        charges = self.cache.load("charges", alloc=self.natom, tags="o")[0]
+        charges[:] = self.pseudo_numbers - pops.cpu().numpy()
+        self._publish_weights()  # owner-slice weights (the reference caches full-grid arrays here)
+        self.history_time_update_at_weights.append(time.time() - t0)
+        self._finalize_propars()
+
+    def _finalize_propars(self):
+        charges = self._cache.load("charges")
+        dump = self.cache.dump
+        dump("history_propars", np.array(self.history_propars), tags="o")
+        dump("history_charges", np.array(self.history_charges), tags="o")
+        dump("history_entropies", np.array(self.history_entropies), tags="o")
+        dump("history_changes", np.array(self.history_changes), tags="o")
+        dump("populations", self.numbers - charges, tags="o")
+        dump("pseudo_populations", self.pseudo_numbers - charges, tags="o")
+        dump("time_update_at_weights", np.sum(self.history_time_update_at_weights), tags="o")
+        dump("time_update_propars", np.sum(self.history_time_update_propars), tags="o")

@@ -98,7 +98,9 @@ HP_API int hp_table_nlis(int32_t nshell, const double* propars, const double* in
  * update_at_weights (core/stockholder.py:352-384) and _compute_entropy (:145-151).
  *
  * For each local point p (global index point_base + p):
- *     promol = 0;  for a in 0..natom-1 (in order):  promol = (promol + rho0_a(p)) + 1e-100
+ *     promol = 0;  for a in 0..natom-1 (in order):  promol = (promol + rho0_a(p)) + promol_offset
+ *                  (promol_offset = 1e-100 reproduces update_pro; 0 gives gLISA's calc_promol_dens,
+ *                   glisa.py:346-348)
  *     w      = clip(rho0_owner(p) / promol, 0, 1)      owner = atom whose slice contains p
  *     entropy partial += molw*rho*ln(rho/promol) unless rho < cutoff or promol < cutoff
  * Atoms are streamed through shared memory in tiles (tile_atom_offsets: ntile+1 atom indices,
@@ -112,8 +114,8 @@ HP_API int hp_promol_weights(int functor, int64_t npts, const double* px, const 
                       const int64_t* atom_point_offsets, const int32_t* atom_shell_offsets,
                       const double* shell_A, const double* shell_alpha, const double* shell_order,
                       int32_t ntile, const int32_t* tile_atom_offsets, const double* rho,
-                      const double* molw, double density_cutoff, double* promol,
-                      double* at_weights, double* entropy_partials, void* stream);
+                      const double* molw, double density_cutoff, double promol_offset,
+                      double* promol, double* at_weights, double* entropy_partials, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * (row a8) spherical average of w_a*rho over each radial shell of each atom's own atomic grid.
@@ -198,6 +200,40 @@ HP_API int hp_isa_update(int32_t natom, int32_t atom_base, const int32_t* rad_of
                          const double* rad_r, const double* rad_w, const double* sph_avg,
                          const int32_t* par_offsets, double* propars, const double* pseudo_numbers,
                          double* charges, double* msd, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * (row a12, and a9 on the molecular grid) reductions over ALL local grid points with the basis
+ * functions regenerated in-kernel -- the reference's (M, Npts) `pro_shells` arrays
+ * (glisa.py:335-344) are never built.  `partial` is scratch of hp_molgrid_num_blocks(npts) x nout
+ * doubles; `out` receives the column sums in a fixed order.
+ *   hp_shell_moments: out[m] = sum_p t(p) * shell_A[m] * exp(-alpha_m r^n_m),
+ *       t = molw*rho/promol^power, 0 where rho < cutoff or promol < cutoff.  With shell_A = the
+ *       normalisation of g_m: power 1 gives function_g's integrals (glisa.py:866-873) and minus
+ *       the gradient (glisa.py:454-458).
+ *   hp_atom_weight_integrals: out[a] = sum_p molw*rho*clip(rho0_a/promol, 0, 1) with
+ *       rho0_a = sum_{m in a} shell_A[m] exp(...)  (update_at_weights(force_on_molgrid) +
+ *       grid.integrate(at_weights*rho), glisa.py:269-278), without storing natom x Npts weights.
+ *   hp_radial_change: msd[a] = int 4 pi r^2 (sum_k (c_new-c_old)_k g_k)^2 on the radial grids
+ *       (core/iterstock.py:32-45 for the exponential-basis schemes). */
+HP_API int32_t hp_molgrid_num_blocks(int64_t npts);
+HP_API int hp_shell_moments(int functor, int64_t npts, const double* px, const double* py,
+                            const double* pz, int32_t natom, const double* atom_xyz,
+                            const int32_t* atom_shell_offsets, const double* shell_A,
+                            const double* shell_alpha, const double* shell_order, int32_t ntile,
+                            const int32_t* tile_atom_offsets, const double* rho, const double* molw,
+                            const double* promol, double density_cutoff, int32_t power,
+                            int32_t nshell, double* partial, double* out, void* stream);
+HP_API int hp_atom_weight_integrals(int functor, int64_t npts, const double* px, const double* py,
+                                    const double* pz, int32_t natom, const double* atom_xyz,
+                                    const int32_t* atom_shell_offsets, const double* shell_A,
+                                    const double* shell_alpha, const double* shell_order,
+                                    int32_t ntile, const int32_t* tile_atom_offsets,
+                                    const double* rho, const double* molw, const double* promol,
+                                    double* partial, double* out, void* stream);
+HP_API int hp_radial_change(int32_t natom, int32_t atom_base, const int32_t* rad_offsets,
+                            const double* rad_w4, const int32_t* par_offsets,
+                            const int64_t* bs_offsets, const double* bs_funcs, const double* c_new,
+                            const double* c_old, double* msd, void* stream);
 
 /* Sum the entropy partials and sqrt(sum msd) in a fixed order: out[0] = change, out[1] = entropy. */
 HP_API int hp_finish_iteration(int32_t npartial, const double* entropy_partials, int32_t natom,

@@ -450,3 +450,109 @@ def isa(coords, numbers, pseudo, grid, rho, threshold=1e-6, maxiter=500, cutoff=
         update, threshold, maxiter, cutoff, coords,
     )  # fmt: skip
     return out
+
+
+# ----------------------------------------------------------------------------------------------
+# gLISA  (glisa.py) -- global optimisation on the molecular grid
+# ----------------------------------------------------------------------------------------------
+def glisa_setup(coords, numbers, pseudo, grid, rho, basis_func="gauss"):
+    """init_propars (gisa.py:68-88) + evaluate_basis_functions(force_on_molgrid=True)
+    (gisa.py:91-106) + eval_pro_shells (glisa.py:335-344)."""
+    basis = load_basis(basis_func)
+    ranges = [0]
+    for z in numbers:
+        ranges.append(ranges[-1] + len(basis[int(z)]["exponents"]))
+    nelec = np.einsum("i,i", grid.weights, rho)
+    propars = lisa_initial(numbers, pseudo, basis, nelec)
+    shells = np.zeros((ranges[-1], grid.size))
+    for a, z in enumerate(numbers):
+        t = basis[int(z)]
+        r = distances(grid.points, coords[a])
+        for k in range(len(t["exponents"])):
+            shells[ranges[a] + k] = exp_shell(t["orders"][k], 1.0, t["exponents"][k], r)
+    return basis, ranges, propars, shells
+
+
+def glisa_function_g(x, shells, rho, molw, cutoff=DENSITY_CUTOFF):
+    """function_g, glisa.py:850-879."""
+    rho0 = np.einsum("np,n->p", shells, x)
+    sick = (rho < cutoff) | (rho0 < cutoff)
+    out = np.zeros_like(x)
+    for m in range(len(x)):
+        with np.errstate(all="ignore"):
+            integrand = rho * (shells[m] * x[m]) / rho0
+        integrand[sick] = 0.0
+        out[m] = np.einsum("i,i", molw, integrand)
+    return out
+
+
+def glisa_working_matrix(rho, rho0, shells, molw, nderiv, cutoff=DENSITY_CUTOFF):
+    """_working_matrix, glisa.py:411-479: objective, gradient, Hessian."""
+    sick = (rho < cutoff) | (rho0 < cutoff)
+    with np.errstate(all="ignore"):
+        ratio = np.divide(rho, rho0, out=np.zeros_like(rho), where=~sick)
+        ln_ratio = np.log(ratio, out=np.zeros_like(ratio), where=~sick)
+    f = np.einsum("i,i", molw, rho * ln_ratio)
+    if nderiv == 0:
+        return f
+    M = shells.shape[0]
+    grad = np.zeros(M)
+    hess = np.zeros((M, M))
+    for i in range(M):
+        with np.errstate(all="ignore"):
+            dfi = (rho * shells[i]) / rho0
+        dfi[sick] = 0.0
+        grad[i] = -np.einsum("i,i", molw, dfi)
+        if nderiv > 1:
+            for j in range(i, M):
+                with np.errstate(all="ignore"):
+                    h = dfi * shells[j] / rho0
+                h[sick] = 0.0
+                hess[i, j] = hess[j, i] = np.einsum("i,i", molw, h)
+    return (f, grad) if nderiv == 1 else (f, grad, hess)
+
+
+def glisa(coords, numbers, pseudo, grid, rho, basis_func="gauss", solver="sc", threshold=1e-6,
+          maxiter=100, cutoff=DENSITY_CUTOFF):  # fmt: skip
+    """GlobalLinearISAWPart(solver='sc' | 'newton').do_partitioning(), grid_type=1
+    (glisa.py:248-281, 805-848, 617-803 mode='exact')."""
+    from scipy.linalg import solve
+
+    natom = len(numbers)
+    basis, ranges, propars, shells = glisa_setup(coords, numbers, pseudo, grid, rho, basis_func)
+    molw = grid.weights
+
+    def proatom(a, par, r):
+        return lisa_proatom(basis[int(numbers[a])], par, r)
+
+    hist = {"propars": [], "entropies": [], "changes": []}
+    it = 0
+    while True:
+        old = propars.copy()
+        rho0 = np.einsum("np,n->p", shells, old)
+        if solver == "sc":
+            propars = glisa_function_g(old, shells, rho, molw, cutoff)
+        else:  # exact Newton: delta = solve(H, -1 - grad); propars += delta
+            _, grad, hess = glisa_working_matrix(rho, rho0, shells, molw, 2, cutoff)
+            propars = old + solve(hess, -1 - grad, assume_a="sym")
+        change = _radial_change(grid.atgrids, ranges, proatom, propars, old)
+        hist["entropies"].append(entropy(molw, rho, rho0, cutoff))
+        hist["changes"].append(change)
+        hist["propars"].append(propars.copy())
+        it += 1
+        if change < threshold:
+            break
+        if solver != "sc" and it >= maxiter:
+            raise RuntimeError("Not converged!")
+    # update_at_weights(force_on_molgrid=True) + charges, glisa.py:267-278
+    dist = [distances(grid.points, coords[a]) for a in range(natom)]
+    promol, weights = stockholder_weights(
+        grid, lambda a: proatom(a, propars[ranges[a] : ranges[a + 1]], dist[a]), natom, owner_only=False
+    )
+    charges = np.array([pseudo[a] - np.einsum("i,i", molw, weights[a] * rho) for a in range(natom)])
+    return {
+        "niter": it, "charges": charges, "propars": propars, "promoldens": promol,
+        "at_weights": [weights[a][grid.indices[a] : grid.indices[a + 1]] for a in range(natom)],
+        "history_propars": np.array(hist["propars"]), "history_entropies": np.array(hist["entropies"]),
+        "history_changes": np.array(hist["changes"]),
+    }  # fmt: skip

@@ -81,3 +81,20 @@ def test_isa_matches_reference_run(h2o, water6):
     assert abs(res["charges"] - np.array([-0.490017586929, 0.245018706885, 0.244998880045])).max() < 2e-3
     res = oracle.isa(water6["coords"], water6["numbers"], water6["pseudo"], water6["grid"], water6["rho"], maxiter=60)
     _check(res, water6["gold"], "isa", rtol=1e-7, qtol=1e-9)  # unconverged (60 its): grid round-off is amplified
+
+
+def _check_glisa(res, gold, tag):
+    assert res["niter"] == int(gold[f"{tag}/niter"])
+    np.testing.assert_allclose(res["charges"], gold[f"{tag}/charges"], rtol=0, atol=1e-10)
+    np.testing.assert_allclose(res["propars"], gold[f"{tag}/propars"], rtol=1e-8, atol=1e-12)
+    np.testing.assert_allclose(res["history_changes"], gold[f"{tag}/history_changes"], rtol=1e-7)
+    np.testing.assert_allclose(res["history_entropies"], gold[f"{tag}/history_entropies"], rtol=1e-10)
+    np.testing.assert_allclose(res["promoldens"][::97], gold[f"{tag}/promoldens_sample"], rtol=1e-9)
+
+
+def test_glisa_sc_matches_reference_run(h2o, water6):
+    res = oracle.glisa(h2o["coords"], h2o["numbers"], h2o["pseudo"], h2o["grid"], h2o["rho"], solver="sc")
+    _check_glisa(res, h2o["gold"], "glisa_sc")
+    assert res["niter"] == 129
+    res = oracle.glisa(water6["coords"], water6["numbers"], water6["pseudo"], water6["grid"], water6["rho"])
+    _check_glisa(res, water6["gold"], "glisa_sc")
