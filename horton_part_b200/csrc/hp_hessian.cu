@@ -1,0 +1,219 @@
+// gLISA Hessian  H_mn = sum_p u(p) g_m(p) g_n(p),  u = molw*rho/rho0^2 masked  (glisa.py:459-470).
+//
+// The reference makes M(M+1)/2 NumPy passes over (M, Npts) tables.  Here the contraction
+// B^T diag(u) B is done chunk by chunk over the grid points:
+//   1. basis_chunk_kernel  regenerates  Gu[p][m] = sqrt(u_p) * g_m(p)  for one chunk of points into
+//      a point-major scratch panel (row length Mpad = M rounded up to 128), so panel rows are
+//      contiguous and the SYRK loads are fully coalesced;
+//   2. syrk_panel_kernel   C_s += Gu_s^T Gu_s  on 128x128 tiles of the upper triangle, 8x8 register
+//      micro-tiles of FP64 FMAs, the chunk split over `nsplit` sub-panels with one partial matrix
+//      each so that >= 2 blocks per SM are in flight without atomics;
+//   3. hessian_finish_kernel  H = sum_s C_s in a fixed order, mirrored to the lower triangle.
+// Every element of every partial matrix is owned by exactly one block, so the result is
+// bit-reproducible.  Bound: FP64 pipe, M(M+1) Npts flop (unit U2); B200 has no
+// tcgen05 FP64 kind and its DMMA rate equals the vector rate, so plain DFMA is used.
+#include "hp_common.cuh"
+#include "hp_math.cuh"
+
+namespace hp {
+
+constexpr int kHT = 128;   // tile edge
+constexpr int kHK = 8;     // points per shared-memory step
+constexpr int kHSplit = 4; // sub-panels per chunk (partial matrices)
+
+template <int F>
+__global__ void __launch_bounds__(256)
+basis_chunk_kernel(int64_t p0, int pc, int M, int Mpad, const double* __restrict__ px,
+                   const double* __restrict__ py, const double* __restrict__ pz,
+                   const double* __restrict__ rho, const double* __restrict__ molw,
+                   const double* __restrict__ promol, double cutoff,
+                   const int* __restrict__ shell_atom, const double* __restrict__ atom_xyz,
+                   const double* __restrict__ shell_norm, const double* __restrict__ shell_alpha,
+                   const double* __restrict__ shell_order, int64_t npts, double* __restrict__ Gu) {
+    // one block per point, threads over shells (coalesced stores along m)
+    const int lp = blockIdx.x;
+    if (lp >= pc) return;
+    const int64_t p = p0 + lp;
+    double su = 0.0, x = 0.0, y = 0.0, z = 0.0;
+    if (p < npts) {
+        const double r0 = promol[p], rh = rho[p];
+        const bool sick = (rh < cutoff) || (r0 < cutoff);
+        su = sick ? 0.0 : sqrt(molw[p] * rh / r0 / r0);
+        x = px[p]; y = py[p]; z = pz[p];
+    }
+    double* row = Gu + int64_t(lp) * Mpad;
+    for (int m = threadIdx.x; m < Mpad; m += blockDim.x) {
+        double v = 0.0;
+        if (m < M && su != 0.0) {
+            const int a = shell_atom[m];
+            const double dx = x - atom_xyz[3 * a], dy = y - atom_xyz[3 * a + 1], dz = z - atom_xyz[3 * a + 2];
+            const double d2 = fma(dz, dz, fma(dy, dy, dx * dx));
+            double e;
+            if (F == HP_FUNCTOR_GAUSS) {
+                e = exp_neg_poly(-shell_alpha[m] * d2);
+            } else if (F == HP_FUNCTOR_SLATER) {
+                e = exp_neg_poly(-shell_alpha[m] * sqrt_nocall(d2));
+            } else {
+                const double r = sqrt(d2), n = shell_order[m];
+                const double rn = (n == 1.0) ? r : ((n == 2.0) ? r * r : pow(r, n));
+                e = exp(-shell_alpha[m] * rn);
+            }
+            v = su * shell_norm[m] * e;
+        }
+        row[m] = v;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+syrk_panel_kernel(const double* __restrict__ Gu, int Mpad, int pc_sub, const int2* __restrict__ tiles,
+                  double* __restrict__ Cpart) {
+    __shared__ __align__(16) double As[kHK][kHT];
+    __shared__ __align__(16) double Bs[kHK][kHT];
+    const int2 tile = tiles[blockIdx.x];
+    const int s = blockIdx.y;
+    const double* panel = Gu + int64_t(s) * pc_sub * Mpad;
+    double* C = Cpart + int64_t(s) * Mpad * Mpad;
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    double acc[8][8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = 0.0;
+
+    for (int k0 = 0; k0 < pc_sub; k0 += kHK) {
+#pragma unroll
+        for (int j = 0; j < (kHK * kHT) / 256; ++j) {
+            const int idx = threadIdx.x + j * 256;
+            const int kk = idx / kHT, mm = idx % kHT;
+            const double* src = panel + int64_t(k0 + kk) * Mpad;
+            As[kk][mm] = src[tile.x * kHT + mm];
+            Bs[kk][mm] = src[tile.y * kHT + mm];
+        }
+        __syncthreads();
+#pragma unroll
+        for (int kk = 0; kk < kHK; ++kk) {
+            double a[8], b[8];
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+                const double2 av = *reinterpret_cast<const double2*>(&As[kk][ty * 2 + 32 * g]);
+                const double2 bv = *reinterpret_cast<const double2*>(&Bs[kk][tx * 2 + 32 * g]);
+                a[2 * g] = av.x; a[2 * g + 1] = av.y;
+                b[2 * g] = bv.x; b[2 * g + 1] = bv.y;
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc[i][j] = fma(a[i], b[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int row = tile.x * kHT + ty * 2 + 32 * (i >> 1) + (i & 1);
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+            const int col = tile.y * kHT + tx * 2 + 32 * g;
+            double2* dst = reinterpret_cast<double2*>(&C[int64_t(row) * Mpad + col]);
+            double2 v = *dst;
+            v.x += acc[i][2 * g];
+            v.y += acc[i][2 * g + 1];
+            *dst = v;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256)
+hessian_finish_kernel(int M, int Mpad, int nsplit, const double* __restrict__ Cpart,
+                      double* __restrict__ H) {
+    const int64_t idx = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (idx >= int64_t(M) * M) return;
+    const int m = int(idx / M), n = int(idx % M);
+    const int r = m < n ? m : n, c = m < n ? n : m;  // upper triangle holds the data
+    double s = 0.0;
+    for (int k = 0; k < nsplit; ++k) s += Cpart[int64_t(k) * Mpad * Mpad + int64_t(r) * Mpad + c];
+    H[idx] = s;
+}
+
+static int hessian_mpad(int M) { return ((M + kHT - 1) / kHT) * kHT; }
+
+// points per chunk: bounded panel size (<= 512 MB) and a multiple of kHSplit * kHK
+static int hessian_chunk_points(int Mpad) {
+    int64_t pc = (int64_t(512) << 20) / (int64_t(Mpad) * 8);
+    if (pc > 65536) pc = 65536;
+    const int q = kHSplit * kHK;
+    pc = (pc / q) * q;
+    return int(pc < q ? q : pc);
+}
+
+}  // namespace hp
+
+using namespace hp;
+
+extern "C" size_t hp_hessian_scratch_bytes(int32_t M) {
+    const int Mpad = hessian_mpad(M);
+    const int nt = Mpad / kHT;
+    const size_t panel = size_t(hessian_chunk_points(Mpad)) * Mpad * sizeof(double);
+    const size_t parts = size_t(kHSplit) * Mpad * Mpad * sizeof(double);
+    const size_t tiles = size_t(nt) * (nt + 1) / 2 * sizeof(int2);
+    return panel + parts + ((tiles + 255) / 256) * 256;
+}
+
+extern "C" int hp_hessian(int functor, int64_t npts, const double* px, const double* py,
+                          const double* pz, const double* atom_xyz, const int32_t* shell_atom,
+                          const double* shell_norm, const double* shell_alpha,
+                          const double* shell_order, const double* rho, const double* molw,
+                          const double* promol, double density_cutoff, int32_t M, void* scratch,
+                          size_t scratch_bytes, double* H, void* stream) {
+    HP_REQUIRE(npts > 0 && M > 0, "bad sizes");
+    HP_REQUIRE(px && py && pz && atom_xyz && shell_atom && shell_norm && shell_alpha && rho && molw &&
+                   promol && scratch && H, "null input");
+    HP_REQUIRE(functor != HP_FUNCTOR_GENERAL || shell_order, "general functor needs shell_order");
+    HP_REQUIRE(scratch_bytes >= hp_hessian_scratch_bytes(M), "scratch too small");
+    cudaStream_t st = as_stream(stream);
+    const int Mpad = hessian_mpad(M), nt = Mpad / kHT, ntile = nt * (nt + 1) / 2;
+    const int pc = hessian_chunk_points(Mpad), pc_sub = pc / kHSplit;
+    double* panel = static_cast<double*>(scratch);
+    double* parts = panel + size_t(pc) * Mpad;
+    int2* tiles = reinterpret_cast<int2*>(parts + size_t(kHSplit) * Mpad * Mpad);
+    // tile list (upper triangle), built on the host
+    int2* host_tiles = new int2[ntile];
+    int k = 0;
+    for (int i = 0; i < nt; ++i)
+        for (int j = i; j < nt; ++j) host_tiles[k++] = make_int2(i, j);
+    int rc = check_cuda(cudaMemcpyAsync(tiles, host_tiles, sizeof(int2) * ntile, cudaMemcpyHostToDevice, st),
+                        "tile list copy");
+    if (rc == HP_OK) rc = check_cuda(cudaStreamSynchronize(st), "tile list sync");
+    delete[] host_tiles;
+    if (rc) return rc;
+    rc = check_cuda(cudaMemsetAsync(parts, 0, sizeof(double) * kHSplit * size_t(Mpad) * Mpad, st), "memset");
+    if (rc) return rc;
+    for (int64_t p0 = 0; p0 < npts; p0 += pc) {
+        switch (functor) {
+            case HP_FUNCTOR_SLATER:
+                basis_chunk_kernel<HP_FUNCTOR_SLATER><<<pc, 256, 0, st>>>(
+                    p0, pc, M, Mpad, px, py, pz, rho, molw, promol, density_cutoff, shell_atom, atom_xyz,
+                    shell_norm, shell_alpha, shell_order, npts, panel);
+                break;
+            case HP_FUNCTOR_GAUSS:
+                basis_chunk_kernel<HP_FUNCTOR_GAUSS><<<pc, 256, 0, st>>>(
+                    p0, pc, M, Mpad, px, py, pz, rho, molw, promol, density_cutoff, shell_atom, atom_xyz,
+                    shell_norm, shell_alpha, shell_order, npts, panel);
+                break;
+            case HP_FUNCTOR_GENERAL:
+                basis_chunk_kernel<HP_FUNCTOR_GENERAL><<<pc, 256, 0, st>>>(
+                    p0, pc, M, Mpad, px, py, pz, rho, molw, promol, density_cutoff, shell_atom, atom_xyz,
+                    shell_norm, shell_alpha, shell_order, npts, panel);
+                break;
+            default:
+                set_error("hp_hessian: unsupported functor %d", functor);
+                return HP_ERR_ARG;
+        }
+        HP_LAUNCH_CHECK("basis_chunk_kernel");
+        syrk_panel_kernel<<<dim3(ntile, kHSplit), 256, 0, st>>>(panel, Mpad, pc_sub, tiles, parts);
+        HP_LAUNCH_CHECK("syrk_panel_kernel");
+    }
+    const int64_t total = int64_t(M) * M;
+    hessian_finish_kernel<<<int((total + 255) / 256), 256, 0, st>>>(M, Mpad, kHSplit, parts, H);
+    HP_LAUNCH_CHECK("hessian_finish_kernel");
+    return HP_OK;
+}

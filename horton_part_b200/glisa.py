@@ -236,6 +236,74 @@ class GlobalLinearISAWPart(AbstractStockholderWPart):
         self.cache.dump("niter", it + 1, tags="o")
         return propars
 
+    def hessian(self):
+        """Dense Hessian H_mn = int rho g_m g_n / rho0^2 for the promolecule currently in
+        slab.promol (device tensor, M x M)."""
+        import torch
+
+        from .core.device import stream_ptr, to_device
+
+        t, s = self._table, self.slab
+        M = t.nshell
+        if getattr(self, "_hess", None) is None:
+            nbytes = int(_lib.call("hp_hessian_scratch_bytes", M))
+            self._hess_scratch = torch.empty(nbytes, dtype=torch.uint8, device=s.device)
+            self._hess = torch.zeros((M, M), dtype=torch.float64, device=s.device)
+            shell_atom = np.repeat(np.arange(self.natom, dtype=np.int32), self._nshells)
+            self._shell_atom = to_device(shell_atom, s.device)
+        _lib.call(
+            "hp_hessian", t.functor, s.npts, s.px, s.py, s.pz, s.atom_xyz, self._shell_atom, self._norms,
+            t.alpha, t.order, s.rho, s.molw, s.promol, float(self.density_cutoff), M, self._hess_scratch,
+            self._hess_scratch.numel(), self._hess, stream_ptr(s.device),
+        )  # fmt: skip
+        return self._hess
+
+    def solver_newton(self, maxiter=100):
+        """Exact Newton (glisa.py:572-574 -> _solver_general_newton mode="exact", :617-803):
+        delta = solve(H, -1 - grad) on the host, full step, change on the radial grids."""
+        import torch
+        from scipy.linalg import solve
+
+        propars = self.propars
+        pop = self.mol_pop
+        self.logger.info("            Iter.    Change    Entropy")
+        self.logger.info("            -----    ------    -------")
+        for irep in range(maxiter):
+            c_old = self._c.clone()
+            self._promol_and_entropy()
+            grad = -self._shell_integrals(1).clone()
+            hess = self.hessian().clone()
+            pack = torch.cat([grad, self._scal[1:2]])
+            self._all_reduce(pack)
+            self._all_reduce(hess)
+            g_host = pack[:-1].cpu().numpy()
+            try:
+                delta = solve(hess.cpu().numpy(), -1 - g_host, assume_a="sym")
+            except np.linalg.LinAlgError as exc:
+                raise RuntimeError(exc)
+            propars[:] = c_old.cpu().numpy() + delta
+            self._c.copy_(torch.from_numpy(np.ascontiguousarray(propars)))
+            msd = self._device_change(self._c, c_old)
+            self._all_reduce(msd)
+            change = float(torch.sqrt(msd.sum()).item())
+            entropy = float(pack[-1].item())
+            self.history_entropies.append(entropy)
+            self.history_propars.append(propars.copy())
+            self.history_changes.append(change)
+            self.logger.info(f"            {irep+1:<4}    {change:.5e}    {entropy:.5e}")
+            if change < self.threshold:
+                # check_pro_atom_parameters (utils.py:304-401) on the promolecule of the old propars
+                pmin = self.slab.promol.min() if self.slab.npts else torch.tensor(0.0)
+                if float(pmin.item()) < self.negative_cutoff:
+                    raise RuntimeError("Negative pro-atom density found!")
+                if abs(np.sum(propars) - pop) > self.population_cutoff:
+                    self.logger.warning(
+                        "WARNING: The sum of pro-atom parameters is not equal to reference population."
+                    )
+                self.cache.dump("niter", irep + 1, tags="o")
+                return propars
+        raise RuntimeError("Not converged!")
+
     # -- driver ---------------------------------------------------------------------------------
     @just_once
     def do_partitioning(self):

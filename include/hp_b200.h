@@ -235,6 +235,18 @@ HP_API int hp_radial_change(int32_t natom, int32_t atom_base, const int32_t* rad
                             const int64_t* bs_offsets, const double* bs_funcs, const double* c_new,
                             const double* c_old, double* msd, void* stream);
 
+/* hp_hessian: H[m][n] = sum_p molw*rho*g_m*g_n/promol^2 (masked like hp_shell_moments), the dense
+ * M x M gLISA Hessian of _working_matrix(nderiv=2) (glisa.py:459-470), row-major, both triangles
+ * filled.  shell_atom[m] = atom of shell m; g_m = shell_norm[m]*exp(-alpha_m r^n).  `scratch` needs
+ * hp_hessian_scratch_bytes(M) bytes.  The function enqueues one basis-panel kernel and one SYRK
+ * kernel per chunk of <= 65,536 grid points and synchronises the stream once at the start. */
+HP_API size_t hp_hessian_scratch_bytes(int32_t M);
+HP_API int hp_hessian(int functor, int64_t npts, const double* px, const double* py, const double* pz,
+                      const double* atom_xyz, const int32_t* shell_atom, const double* shell_norm,
+                      const double* shell_alpha, const double* shell_order, const double* rho,
+                      const double* molw, const double* promol, double density_cutoff, int32_t M,
+                      void* scratch, size_t scratch_bytes, double* H, void* stream);
+
 /* Sum the entropy partials and sqrt(sum msd) in a fixed order: out[0] = change, out[1] = entropy. */
 HP_API int hp_finish_iteration(int32_t npartial, const double* entropy_partials, int32_t natom,
                         const double* msd, double* out2, void* stream);

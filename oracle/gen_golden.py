@@ -137,7 +137,35 @@ def case_water_cluster(natom=6, nrad=40, nang=50, seed=0):
     )  # fmt: skip
 
 
-CASES = {"h2o": case_h2o, "water6": case_water_cluster}
+def case_water_gauss(natom=6, nrad=40, nang=50, seed=0):
+    """Synthetic Gaussian promolecule (sum_a sum_k c_ak g_ak, c from the gauss table's initials scaled
+    to 8.6 / 0.7 electrons): the exact-Newton gLISA solver converges on it."""
+    from horton_part.core.basis import ExpBasisFuncHelper
+
+    coords, numbers = synthetic.water_cluster(natom, seed)
+    grid = synthetic_grid(coords, numbers, nrad, nang)
+    helper = ExpBasisFuncHelper.from_function_type("gauss")
+    rho = synthetic.expbasis_promolecule_host(grid.points, coords, numbers, helper, scale={8: 8.6, 1: 0.7})
+    pseudo = numbers.astype(float)
+    results = {}
+    for tag, (scheme, kw) in {
+        "glisa_newton": ("glisa", dict(solver="newton")),
+        "glisa_sc": ("glisa", dict(solver="sc")),
+        "lisa_sc_gauss": ("lisa", dict(solver="sc")),
+    }.items():
+        try:
+            results[tag] = run_reference(scheme, coords, numbers, pseudo, grid, rho, **kw)
+            print(f"  water{natom}g {tag}: niter={results[tag]['niter']} q={results[tag]['charges'][:3]}")
+        except Exception as exc:
+            print(f"  water{natom}g {tag}: reference raised {type(exc).__name__}: {exc}")
+    save(
+        f"water{natom}_gauss.npz", results, coordinates=coords, numbers=numbers, pseudo_numbers=pseudo,
+        dens_sample=rho[::101].copy(), nelec=np.float64(grid.integrate(rho)),
+        grid_spec=np.array(f"BeckeRTransform(1e-4,1.5) o GaussChebyshev({nrad}) x Lebedev{nang}, BeckeWeights(); seed={seed}"),
+    )  # fmt: skip
+
+
+CASES = {"h2o": case_h2o, "water6": case_water_cluster, "water6g": case_water_gauss}
 
 if __name__ == "__main__":
     for name in sys.argv[1:] or CASES:

@@ -71,3 +71,16 @@ def make_water():
     from horton_part_b200 import gridlite
 
     return lambda natom, nrad=40, nang=50, seed=0: _water_case(gridlite, natom, nrad, nang, seed)
+
+
+@pytest.fixture(scope="session")
+def water6g():
+    """Synthetic Gaussian promolecule (gauss table initials scaled to 8.6 / 0.7 electrons)."""
+    from horton_part_b200 import gridlite, synthetic
+    from horton_part_b200.core.basis import ExpBasisFuncHelper
+
+    case = _water_case(gridlite, 6, 40, 50, gold=np.load(GOLDEN / "water6_gauss.npz"))
+    helper = ExpBasisFuncHelper.from_function_type("gauss")
+    case["rho"] = synthetic.expbasis_promolecule_host(case["grid"].points, case["coords"], case["numbers"],
+                                                      helper, scale={8: 8.6, 1: 0.7})
+    return case

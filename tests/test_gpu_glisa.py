@@ -59,3 +59,36 @@ def test_glisa_sc_h2o_against_reference_run(h2o):
 def test_glisa_sc_water6_against_reference_run(water6):
     part = _glisa(water6, solver="sc")
     _compare(part, _gold(water6["gold"], "glisa_sc"), ptol=1e-5)
+
+
+def test_hessian_against_oracle(water6g):
+    from horton_part_b200 import GlobalLinearISAWPart
+
+    c = water6g
+    part = GlobalLinearISAWPart(c["coords"], c["numbers"], c["pseudo"], c["grid"], c["rho"], solver="newton")
+    x = part._init_propars().copy()
+    _, _, x_ref, shells = oracle.glisa_setup(c["coords"], c["numbers"], c["pseudo"], c["grid"], c["rho"])
+    part._promol_and_entropy()
+    H = part.hessian().cpu().numpy()
+    rho0 = np.einsum("np,n->p", shells, x_ref)
+    f, grad, hess = oracle.glisa_working_matrix(c["rho"], rho0, shells, c["grid"].weights, 2)
+    assert np.array_equal(H, H.T)
+    np.testing.assert_allclose(H, hess, rtol=1e-10, atol=1e-12 * np.abs(hess).max())
+    np.testing.assert_allclose(-part._shell_integrals(1).cpu().numpy(), grad, rtol=1e-10)
+    assert float(part._scal[1].item()) == pytest.approx(f, rel=1e-10)
+
+
+def test_glisa_newton_against_reference_run(water6g):
+    part = _glisa(water6g, solver="newton")
+    ref = _gold(water6g["gold"], "glisa_newton")
+    assert part["niter"] == int(ref["niter"]) == 5
+    np.testing.assert_allclose(part["charges"], ref["charges"], rtol=1e-8, atol=1e-9)
+    np.testing.assert_allclose(part["history_entropies"], ref["history_entropies"], rtol=1e-8, atol=1e-12)
+    np.testing.assert_allclose(part["history_changes"][:3], ref["history_changes"][:3], rtol=1e-5)
+    # the basis is nearly linearly dependent: individual coefficients are loose, the density is not
+    np.testing.assert_allclose(part["promoldens"][::97], ref["promoldens_sample"], rtol=1e-7)
+
+
+def test_glisa_sc_gauss_promolecule(water6g):
+    part = _glisa(water6g, solver="sc")
+    _compare(part, _gold(water6g["gold"], "glisa_sc"), ptol=1e-4)

@@ -98,3 +98,13 @@ def test_glisa_sc_matches_reference_run(h2o, water6):
     assert res["niter"] == 129
     res = oracle.glisa(water6["coords"], water6["numbers"], water6["pseudo"], water6["grid"], water6["rho"])
     _check_glisa(res, water6["gold"], "glisa_sc")
+
+
+def test_glisa_newton_matches_reference_run(water6g):
+    c = water6g
+    np.testing.assert_allclose(c["rho"][::101], c["gold"]["dens_sample"], rtol=1e-12)
+    res = oracle.glisa(c["coords"], c["numbers"], c["pseudo"], c["grid"], c["rho"], solver="newton")
+    assert res["niter"] == int(c["gold"]["glisa_newton/niter"]) == 5
+    np.testing.assert_allclose(res["charges"], c["gold"]["glisa_newton/charges"], rtol=0, atol=1e-9)
+    np.testing.assert_allclose(res["history_changes"][:3], c["gold"]["glisa_newton/history_changes"][:3], rtol=1e-6)
+    np.testing.assert_allclose(res["history_entropies"], c["gold"]["glisa_newton/history_entropies"], rtol=1e-9, atol=1e-13)
