@@ -78,6 +78,7 @@ EXPORTS = {
     "hp_finish_iteration": (_int, [_i32, _p, _i32, _p, _p, _p]),
     "hp_sum_partials": (_int, [_i32, _p, _p, _p]),
     "hp_segment_integrate": (_int, [_i32, _p, _p, _p, _p, _p, _p]),
+    "hp_atom_moments": (_int, [_i32, _i32, _i32, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
     "hp_dfma_probe": (_int, [_i32, _p, _p, _p, _p]),
 }
 

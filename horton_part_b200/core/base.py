@@ -169,6 +169,29 @@ class Part(JustOnceClass):
         """int w_a * density over each atom's own grid (core/base.py:287-298, 320-326)."""
         raise NotImplementedError
 
+    @just_once
+    def do_moments(self):
+        """Cartesian / pure multipoles and radial moments of every atom-in-molecule density
+        (core/base.py:329-402); sign conventions as in the reference: multipoles carry the electron's
+        negative charge plus the pseudo number in the monopole, radial moments do not."""
+        ncart = get_ncart_cumul(self.lmax)
+        cartesian, new1 = self._cache.load("cartesian_multipoles", alloc=(self.natom, ncart), tags="o")
+        npure = get_npure_cumul(self.lmax)
+        pure, new1 = self._cache.load("pure_multipoles", alloc=(self.natom, npure), tags="o")
+        nrad = self.lmax + 1
+        radial, new2 = self._cache.load("radial_moments", alloc=(self.natom, nrad), tags="o")
+        if new1 or new2:
+            self.do_partitioning()
+            raw = self._atom_moments()
+            cartesian[:] = -raw[:, :ncart]
+            cartesian[:, 0] += self.pseudo_numbers
+            pure[:] = -raw[:, ncart : ncart + npure]
+            pure[:, 0] += self.pseudo_numbers
+            radial[:] = raw[:, ncart + npure :]
+
+    def _atom_moments(self):
+        raise NotImplementedError
+
     def do_all(self):
         for attr_name in dir(self):
             attr = getattr(self, attr_name)

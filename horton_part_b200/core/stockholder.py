@@ -96,6 +96,27 @@ class AbstractStockholderWPart(WPart):
             ln_ratio = np.where(sick, 0.0, np.log(np.where(sick, 1.0, rho / np.where(sick, 1.0, rho0))))
         return self._grid.integrate(rho, ln_ratio)
 
+    def _atom_moments(self):
+        import torch
+
+        from .device import stream_ptr
+
+        if not self.local:
+            raise NotImplementedError("moments need atomic grids (grid_type 1 or 2)")
+        slab = self.slab
+        sh = slab.shard
+        lmax = int(self.lmax)
+        nmom = (lmax + 1) * (lmax + 2) * (lmax + 3) // 6 + (lmax + 1) ** 2 + lmax + 1
+        seg = (slab.atom_point_offsets[sh.atom_lo : sh.atom_hi + 1] - slab.point_base).contiguous()
+        out = torch.zeros((self.natom, nmom), dtype=torch.float64, device=slab.device)
+        _lib.call("hp_atom_moments", sh.nlocal, sh.atom_lo, lmax, seg, slab.px, slab.py, slab.pz, slab.atw,
+                  slab.at_w, slab.rho, slab.atom_xyz, out, stream_ptr(slab.device))  # fmt: skip
+        if self._comm is not None:
+            import torch.distributed as dist
+
+            dist.all_reduce(out, group=self._comm)
+        return out.cpu().numpy()
+
     def _atom_integrals(self, density):
         import torch
 

@@ -450,6 +450,89 @@ lisa_sc_radial_kernel(int natom, int atom_base, const int* __restrict__ rad_off,
 }
 
 // ---------------------------------------------------------------------------------------------
+// Row a13: multipole moments of w_a*rho about R_a on atom a's own atomic grid (core/base.py:329-402
+// with qc-grid Grid.moments): Cartesian monomials in HORTON order, real regular solid harmonics
+// (Racah normalisation, order C_l0 C_l1 S_l1 C_l2 S_l2 ...), radial moments r^n.  One block per
+// atom; out row = [ncart | npure | nrad] raw integrals (signs/offsets are applied by the caller).
+// ---------------------------------------------------------------------------------------------
+constexpr int kMaxL = 4;
+constexpr int kMaxMom = 35 + 25 + 5;
+
+__device__ __forceinline__ int fill_moment_basis(int lmax, double x, double y, double z, double* b) {
+    double xp[kMaxL + 1], yp[kMaxL + 1], zp[kMaxL + 1];
+    xp[0] = yp[0] = zp[0] = 1.0;
+    for (int i = 1; i <= lmax; ++i) {
+        xp[i] = xp[i - 1] * x;
+        yp[i] = yp[i - 1] * y;
+        zp[i] = zp[i - 1] * z;
+    }
+    int n = 0;
+    for (int l = 0; l <= lmax; ++l)
+        for (int nx = l; nx >= 0; --nx)
+            for (int ny = l - nx; ny >= 0; --ny) b[n++] = xp[nx] * yp[ny] * zp[l - nx - ny];
+    // solid harmonics: A_m + i B_m = (x + i y)^m, Pi_l^m(z, r^2) by the Legendre-type recursion
+    const double r2 = x * x + y * y + z * z;
+    double A[kMaxL + 1], B[kMaxL + 1];
+    A[0] = 1.0;
+    B[0] = 0.0;
+    for (int m = 1; m <= lmax; ++m) {
+        A[m] = x * A[m - 1] - y * B[m - 1];
+        B[m] = x * B[m - 1] + y * A[m - 1];
+    }
+    double Pi[kMaxL + 1][kMaxL + 1];
+    for (int m = 0; m <= lmax; ++m) {
+        double df = 1.0;
+        for (int k = 1; k < 2 * m; k += 2) df *= k;
+        Pi[m][m] = df;
+        if (m + 1 <= lmax) Pi[m + 1][m] = (2 * m + 1) * z * Pi[m][m];
+        for (int l = m + 2; l <= lmax; ++l)
+            Pi[l][m] = ((2 * l - 1) * z * Pi[l - 1][m] - (l + m - 1) * r2 * Pi[l - 2][m]) / (l - m);
+    }
+    for (int l = 0; l <= lmax; ++l) {
+        b[n++] = Pi[l][0];
+        double ratio = 1.0;  // (l-m)!/(l+m)!
+        for (int m = 1; m <= l; ++m) {
+            ratio /= double(l + m) * double(l - m + 1);
+            const double norm = sqrt(2.0 * ratio);
+            b[n++] = norm * Pi[l][m] * A[m];
+            b[n++] = norm * Pi[l][m] * B[m];
+        }
+    }
+    const double r = sqrt(r2);
+    double rp = 1.0;
+    for (int k = 0; k <= lmax; ++k) {
+        b[n++] = rp;
+        rp *= r;
+    }
+    return n;
+}
+
+__global__ void __launch_bounds__(128)
+atom_moments_kernel(int natom, int atom_base, int lmax, const int64_t* __restrict__ seg_off,
+                    const double* __restrict__ px, const double* __restrict__ py,
+                    const double* __restrict__ pz, const double* __restrict__ atw,
+                    const double* __restrict__ at_w, const double* __restrict__ dens,
+                    const double* __restrict__ atom_xyz, int nmom, double* __restrict__ out) {
+    __shared__ double red[32];
+    const int la = blockIdx.x;
+    if (la >= natom) return;
+    const int a = atom_base + la;
+    const double cx = atom_xyz[3 * a], cy = atom_xyz[3 * a + 1], cz = atom_xyz[3 * a + 2];
+    double acc[kMaxMom];
+    for (int i = 0; i < kMaxMom; ++i) acc[i] = 0.0;
+    for (int64_t p = seg_off[la] + threadIdx.x; p < seg_off[la + 1]; p += blockDim.x) {
+        double b[kMaxMom];
+        fill_moment_basis(lmax, px[p] - cx, py[p] - cy, pz[p] - cz, b);
+        const double f = atw[p] * (dens[p] * at_w[p]);
+        for (int i = 0; i < nmom; ++i) acc[i] = fma(b[i], f, acc[i]);
+    }
+    for (int i = 0; i < nmom; ++i) {
+        const double t = block_sum(acc[i], red);
+        if (threadIdx.x == 0) out[int64_t(a) * nmom + i] = t;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // End-of-iteration scalars in a fixed summation order
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
@@ -639,5 +722,22 @@ extern "C" int hp_lisa_sc_radial_solve(int32_t natom, int32_t atom_base, const i
         pseudo_numbers, inner_threshold, density_cutoff, population_cutoff, max_inner, single_update,
         nrad_max, charges, msd, niter, flags);
     HP_LAUNCH_CHECK("lisa_sc_radial_kernel");
+    return HP_OK;
+}
+
+extern "C" int hp_atom_moments(int32_t natom, int32_t atom_base, int32_t lmax,
+                               const int64_t* seg_offsets, const double* px, const double* py,
+                               const double* pz, const double* atgrid_w, const double* at_weights,
+                               const double* dens, const double* atom_xyz, double* out, void* stream) {
+    HP_REQUIRE(natom >= 0, "bad sizes");
+    HP_REQUIRE(lmax >= 0 && lmax <= kMaxL, "lmax must be in 0..4");
+    if (natom == 0) return HP_OK;
+    HP_REQUIRE(seg_offsets && px && py && pz && atgrid_w && at_weights && dens && atom_xyz && out,
+               "null input");
+    const int nmom = (lmax + 1) * (lmax + 2) * (lmax + 3) / 6 + (lmax + 1) * (lmax + 1) + (lmax + 1);
+    atom_moments_kernel<<<natom, 128, 0, as_stream(stream)>>>(natom, atom_base, lmax, seg_offsets, px, py,
+                                                              pz, atgrid_w, at_weights, dens, atom_xyz,
+                                                              nmom, out);
+    HP_LAUNCH_CHECK("atom_moments_kernel");
     return HP_OK;
 }

@@ -260,6 +260,16 @@ HP_API int hp_sum_partials(int32_t n, const double* partials, double* out1, void
 HP_API int hp_segment_integrate(int32_t nseg, const int64_t* seg_offsets, const double* w,
                                 const double* f, const double* g, double* out, void* stream);
 
+/* (row a13, multipoles) out[a][:] = integrals over atom a's own slice of atgrid_w*dens*at_weights
+ * times [Cartesian monomials l<=lmax (HORTON order) | real regular solid harmonics (C_l0, C_l1,
+ * S_l1, ...) | r^n, n<=lmax] about R_a: the raw moments behind do_moments (core/base.py:329-402,
+ * qc-grid Grid.moments).  out is (natom_global, ncart+npure+nrad) row-major; rows of the local
+ * atoms atom_base..atom_base+natom-1 are written.  lmax <= 4. */
+HP_API int hp_atom_moments(int32_t natom, int32_t atom_base, int32_t lmax, const int64_t* seg_offsets,
+                           const double* px, const double* py, const double* pz,
+                           const double* atgrid_w, const double* at_weights, const double* dens,
+                           const double* atom_xyz, double* out, void* stream);
+
 /* FP64 FMA throughput probe used by bench.py for the roofline denominator: runs `iters` dependent
  * DFMA chains (8 independent per thread) on a full grid; returns elapsed ms in *ms_host and the
  * flop count in *flops_host.  Synchronises the stream. */

@@ -55,6 +55,14 @@ def run_reference(scheme, coords, numbers, pseudo, grid, rho, **kwargs):
             out[key] = part[key]
     if "spherical_average_0" in part.cache:
         out["spherical_average_0"] = part["spherical_average_0"]
+    if scheme == "mbis" and kwargs.get("grid_type", 1) == 1:
+        import contextlib
+        import io
+
+        with contextlib.redirect_stdout(io.StringIO()):
+            part.do_moments()  # core/base.py:329-402 (prints a progress line)
+        for key in ("cartesian_multipoles", "pure_multipoles", "radial_moments"):
+            out[key] = part[key]
     return out
 
 

@@ -93,3 +93,17 @@ def test_maxiter_and_threshold(water6):
     ref = oracle.mbis(water6["coords"], water6["numbers"], water6["pseudo"], water6["grid"], water6["rho"], threshold=1e-3)
     assert part["niter"] == ref["niter"]
     np.testing.assert_allclose(part["charges"], ref["charges"], rtol=RTOL, atol=1e-10)
+
+
+def test_multipole_moments_against_reference_run(h2o):
+    """do_moments (row a13) vs the reference's own do_moments run through the qc-grid shim."""
+    part = _mbis(h2o)
+    part.do_moments()
+    ref = _gold(h2o["gold"], "mbis")
+    for key in ("cartesian_multipoles", "pure_multipoles", "radial_moments"):
+        scale = np.abs(ref[key]).max()
+        np.testing.assert_allclose(part[key], ref[key], rtol=1e-8, atol=1e-10 * scale, err_msg=key)
+    # tests/test_wpart.py:62-63
+    part.do_charges()
+    assert abs(part["charges"] - part["cartesian_multipoles"][:, 0]).max() < 1e-3
+    assert abs(part["charges"] - part["pure_multipoles"][:, 0]).max() < 1e-3
