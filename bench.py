@@ -46,30 +46,37 @@ class ClockSampler:
               "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
               "clocks_event_reasons.sw_power_cap")  # fmt: skip
 
-    def __init__(self, index):
-        self.index, self.rows, self._stop, self._thread = index, [], threading.Event(), None
+    def __init__(self, index, period_ms=50):
+        self.index, self.rows, self.period_ms, self._proc, self._thread = index, [], period_ms, None, None
 
     def _loop(self):
-        while not self._stop.is_set():
-            try:
-                out = subprocess.run(
-                    ["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-i", str(self.index)],
-                    capture_output=True, text=True, timeout=5,
-                ).stdout.strip()  # fmt: skip
-                if out:
-                    self.rows.append([c.strip() for c in out.split(",")])
-            except Exception:
-                pass
-            self._stop.wait(0.2)
+        for line in self._proc.stdout:
+            line = line.strip()
+            if line:
+                self.rows.append([c.strip() for c in line.split(",")])
 
     def __enter__(self):
-        self._thread = threading.Thread(target=self._loop, daemon=True)
-        self._thread.start()
+        try:
+            self._proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-i", str(self.index),
+                 "-lms", str(self.period_ms)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True,
+            )  # fmt: skip
+            self._thread = threading.Thread(target=self._loop, daemon=True)
+            self._thread.start()
+            time.sleep(0.15)  # first sample lands before the timed region starts
+        except Exception:
+            self._proc = None
         return self
 
     def __exit__(self, *exc):
-        self._stop.set()
-        self._thread.join(timeout=6)
+        if self._proc is not None:
+            time.sleep(0.06)
+            self._proc.terminate()
+            try:
+                self._proc.wait(timeout=3)
+            except Exception:
+                self._proc.kill()
+            self._thread.join(timeout=3)
 
     def summary(self):
         sm, mx, reasons = [], [], set()

@@ -76,17 +76,20 @@ class AbstractStockholderWPart(WPart):
         self._publish_weights()
 
     def _publish_weights(self):
-        """Download promolecule and owner weights of this rank's slab into the cache."""
+        """Download promolecule and owner weights of this rank's slab into the cache: one D2H copy
+        each; the per-atom ``at_weights_{a}`` entries are views into the downloaded array."""
         slab = self.slab
-        promol = self.cache.load("promoldens", alloc=self.grid.size)[0]
         lo = slab.point_base
-        promol[lo : lo + slab.npts] = slab.promol.cpu().numpy()
+        promol_h = slab.promol.cpu().numpy()
+        if slab.npts == self.grid.size:
+            self.cache.dump("promoldens", promol_h)
+        else:  # sharded: only this rank's slice is known
+            promol = self.cache.load("promoldens", alloc=self.grid.size)[0]
+            promol[lo : lo + slab.npts] = promol_h
         at_w = slab.at_w.cpu().numpy()
         off = slab.atom_point_offsets_host
         for a in range(slab.shard.atom_lo, slab.shard.atom_hi):
-            size = int(off[a + 1] - off[a])
-            dst = self.cache.load(f"at_weights_{a}", alloc=size)[0]
-            dst[:] = at_w[off[a] - lo : off[a + 1] - lo]
+            self.cache.dump(f"at_weights_{a}", at_w[off[a] - lo : off[a + 1] - lo])
 
     def _compute_entropy(self, rho, rho0):
         """Host restatement for API users (core/stockholder.py:145-151); the iteration loop gets
