@@ -114,6 +114,48 @@ def case_h2o():
     )  # fmt: skip
 
 
+def load_proatom_records(level="hf_sto3g", numbers=(1, 6, 8)):
+    """The reference's cached isolated-atom records (tests/common.py:64-111, PowerRTransform grids)."""
+    from horton_part.core.proatomdb import ProAtomRecord
+
+    records, raw = [], {}
+    for z in numbers:
+        for path in sorted(REF_CACHED.glob(f"atom_{level}_Z{z:02d}_N*_pow.npz")):
+            with np.load(path) as f:
+                number, charge, energy = int(f["number"]), int(f["charge"]), float(f["energy"])
+                rmin, rmax, npoint = f["rgrid"]
+                rgrid = qcgrid.PowerRTransform(rmin, rmax, int(npoint) - 1).transform_1d_grid(qcgrid.UniformInteger(int(npoint)))
+                records.append(ProAtomRecord(number, charge, energy, rgrid, f["dens"], f["deriv"]))
+                raw[f"Z{number}_q{charge}"] = np.concatenate([[number, charge, energy, rmin, rmax, npoint], f["dens"], f["deriv"]])
+    return records, raw
+
+
+def case_hirshfeld():
+    """Hirshfeld and Hirshfeld-I on water (tests/test_wpart.py:70-87) with the reference's database."""
+    from horton_part.core.proatomdb import ProAtomDB
+    from scipy.spatial import cKDTree
+
+    npz = np.load(REF_CACHED / "water_sto3g_hf_g03_fchk_exp:5e-4:2e1:120:110.npz")
+    coords, numbers, pseudo = npz["coordinates"], npz["numbers"], npz["pseudo_numbers"]
+    rgrid = qcgrid.ExpRTransform(5e-4, 2e1, 119).transform_1d_grid(qcgrid.UniformInteger(120))
+    grid = qcgrid.MolGrid.from_size(numbers, coords, 110, rgrid, qcgrid.BeckeWeights(), rotate=False, store=True)
+    _, order = cKDTree(npz["points"]).query(grid.points)
+    rho = npz["dens"][order]
+    records, raw = load_proatom_records()
+    results = {}
+    for tag, scheme in (("h", "h"), ("hi", "hi")):
+        part = wpart_schemes(scheme)(coords, numbers, pseudo, grid, rho, proatomdb=ProAtomDB(records))
+        part.do_charges()
+        out = {"charges": part["charges"], "promoldens_sample": part["promoldens"][::97].copy(),
+               "at_weights_0_sample": part["at_weights_0"][::53].copy()}
+        if scheme == "hi":
+            out.update(niter=np.int64(part["niter"]), history_changes=part["history_changes"],
+                       history_charges=part["history_charges"], history_entropies=part["history_entropies"])
+        results[tag] = out
+        print(f"  h2o {tag}: q={part['charges']} niter={out.get('niter')}")
+    save("h2o_hirshfeld.npz", results, **{f"record/{k}": v for k, v in raw.items()})
+
+
 def synthetic_grid(coords, numbers, nrad, nang):
     rgrid = qcgrid.BeckeRTransform(1e-4, 1.5).transform_1d_grid(qcgrid.GaussChebyshev(nrad))
     return qcgrid.MolGrid.from_size(numbers, coords, nang, rgrid, qcgrid.BeckeWeights(), rotate=0, store=True)
@@ -173,7 +215,7 @@ def case_water_gauss(natom=6, nrad=40, nang=50, seed=0):
     )  # fmt: skip
 
 
-CASES = {"h2o": case_h2o, "water6": case_water_cluster, "water6g": case_water_gauss}
+CASES = {"h2o": case_h2o, "water6": case_water_cluster, "water6g": case_water_gauss, "hirshfeld": case_hirshfeld}
 
 if __name__ == "__main__":
     for name in sys.argv[1:] or CASES:

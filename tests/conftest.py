@@ -84,3 +84,22 @@ def water6g():
     case["rho"] = synthetic.expbasis_promolecule_host(case["grid"].points, case["coords"], case["numbers"],
                                                       helper, scale={8: 8.6, 1: 0.7})
     return case
+
+
+@pytest.fixture(scope="session")
+def h2o_proatomdb():
+    """The reference's HF/STO-3G isolated-atom records (packed by oracle/gen_golden.py) as a
+    product-side ProAtomDB on PowerRTransform radial grids (tests/common.py:64-111)."""
+    from horton_part_b200 import gridlite
+    from horton_part_b200.core.proatomdb import ProAtomDB, ProAtomRecord
+
+    z = np.load(GOLDEN / "h2o_hirshfeld.npz")
+    records = []
+    for key in z.files:
+        if not key.startswith("record/"):
+            continue
+        v = z[key]
+        number, charge, energy, rmin, rmax, npoint = int(v[0]), int(v[1]), float(v[2]), v[3], v[4], int(v[5])
+        rgrid = gridlite.PowerRTransform(rmin, rmax, npoint - 1).transform_1d_grid(gridlite.UniformInteger(npoint))
+        records.append(ProAtomRecord(number, charge, energy, rgrid, v[6 : 6 + npoint].copy(), v[6 + npoint :].copy()))
+    return ProAtomDB(records), z
