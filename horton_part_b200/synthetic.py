@@ -154,3 +154,42 @@ def slater_promolecule_device(grid, coordinates, numbers, shells=SLATER_SHELLS, 
     rho = slab.promol.cpu().numpy()
     w = slab.at_w.cpu().numpy()
     return rho, w, slab.point_base, slab.point_base + slab.npts
+
+
+def shell_promolecule_device(grid, coordinates, functor, counts, A, alpha, order=None, device=None, shard=None):
+    """Promolecule sum_shells A exp(-alpha r^n) and its Hirshfeld owner weights on this rank's slab for
+    an arbitrary shell table (used to synthesise Gaussian / Slater-basis test densities on the GPU)."""
+    import numpy as _np
+
+    from .core.device import GridSlab, ShellTable, to_device
+
+    slab = GridSlab(grid, _np.zeros(grid.size), _np.asarray(coordinates, float), device, shard, need_atgrids=False)
+    table = ShellTable(slab, functor, counts)
+    table.A.copy_(to_device(_np.asarray(A, float), slab.device))
+    table.alpha.copy_(to_device(_np.asarray(alpha, float), slab.device))
+    if functor == 3:
+        table.order.copy_(to_device(_np.asarray(order, float), slab.device))
+    table.promol_weights(1e-15, True, True, False)
+    return slab.promol.cpu().numpy(), slab.at_w.cpu().numpy(), slab.point_base, slab.point_base + slab.npts
+
+
+def expbasis_promolecule_device(grid, coordinates, numbers, helper, scale=None, device=None, shard=None):
+    """Device version of ``expbasis_promolecule_host``; returns (rho, owner weights) on the slab."""
+    from .core.basis import shell_norm
+
+    counts, A, alpha, order = [], [], [], []
+    for z in numbers:
+        z = int(z)
+        c = np.asarray(helper.get_initial(z), dtype=float)
+        c = c / c.sum() * (float(z) if scale is None else scale[z])
+        n = np.asarray(helper.get_order(z), dtype=float)
+        al = np.asarray(helper.get_exponent(z), dtype=float)
+        counts.append(len(al))
+        A.append(c * shell_norm(n, al))
+        alpha.append(al)
+        order.append(n)
+    order = np.concatenate(order)
+    functor = 2 if np.all(order == 2.0) else (1 if np.all(order == 1.0) else 3)
+    rho, w, lo, hi = shell_promolecule_device(grid, coordinates, functor, counts, np.concatenate(A),
+                                              np.concatenate(alpha), order, device, shard)
+    return rho, w
