@@ -70,6 +70,11 @@ EXPORTS = {
         [_int, _i64, _p, _p, _p, _i32, _p, _p, _p, _p, _p, _i32, _p, _p, _p, _p, _p, _p, _p],
     ),
     "hp_radial_change": (_int, [_i32, _i32, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
+    "hp_molgrid_update_tile_limits": (None, [_p, _p]),
+    "hp_molgrid_update_pass": (
+        _int,
+        [_int, _i64, _p, _p, _p, _i32, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i32, _p, _p, _p, _p, _f64, _i32, _p, _p, _p],
+    ),
     "hp_hessian_scratch_bytes": (_sz, [_i32]),
     "hp_hessian": (
         _int,
@@ -84,7 +89,8 @@ EXPORTS = {
 
 
 # int-returning functions whose result is a value, not a status code
-_NOT_STATUS = {"hp_abi_version", "hp_num_partials", "hp_local_index_scratch_bytes", "hp_last_error", "hp_tile_limits", "hp_molgrid_num_blocks", "hp_hessian_scratch_bytes"}
+_NOT_STATUS = {"hp_abi_version", "hp_num_partials", "hp_local_index_scratch_bytes", "hp_last_error", "hp_tile_limits", "hp_molgrid_num_blocks", "hp_hessian_scratch_bytes",
+               "hp_molgrid_update_tile_limits"}
 
 
 class HpError(RuntimeError):

@@ -122,7 +122,7 @@ class LinearISAWPart(GaussianISAWPart):
 
     def _finalize_propars(self):
         GaussianISAWPart._finalize_propars(self)
-        if not callable(self._solver) and self._solver == "sc":
+        if not callable(self._solver) and self._solver == "sc" and not self.on_molgrid:
             flags = self._state.flags.cpu().numpy()
             if (flags & 1).any():
                 self.logger.warning("Warning: Inner iteration is not converge!")

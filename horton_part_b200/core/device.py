@@ -187,20 +187,27 @@ class ShellTable:
         _lib.call("hp_tile_limits", max_atoms, max_shells)
         if counts.max(initial=0) > int(max_shells[0]):
             raise ValueError("an atom has more shells than one shared-memory tile can hold")
-        tiles, a = [0], 0
-        while a < slab.natom:
-            b, nsh = a, 0
-            while b < slab.natom and b - a < int(max_atoms[0]) and nsh + counts[b] <= int(max_shells[0]):
-                nsh += counts[b]
-                b += 1
-            tiles.append(b)
-            a = b
-        self.ntile = len(tiles) - 1
-        self.tiles = to_device(np.asarray(tiles, dtype=np.int32), dev)
+        self._counts = counts
+        self.ntile, self.tiles = self.make_tiles(int(max_atoms[0]), int(max_shells[0]))
         self.offsets = to_device(self.offsets_host, dev)
         self.A = torch.zeros(max(self.nshell, 1), dtype=torch.float64, device=dev)
         self.alpha = torch.zeros_like(self.A)
         self.order = torch.ones_like(self.A) if functor == 3 else None
+
+    def make_tiles(self, max_atoms, max_shells):
+        """Greedy split of the atom list into shared-memory tiles: (ntile, device int32 offsets)."""
+        counts, natom = self._counts, self.slab.natom
+        if counts.max(initial=0) > max_shells:
+            raise ValueError("an atom has more shells than one shared-memory tile can hold")
+        tiles, a = [0], 0
+        while a < natom:
+            b, nsh = a, 0
+            while b < natom and b - a < max_atoms and nsh + counts[b] <= max_shells:
+                nsh += counts[b]
+                b += 1
+            tiles.append(b)
+            a = b
+        return len(tiles) - 1, to_device(np.asarray(tiles, dtype=np.int32), self.slab.device)
 
     def promol_weights(self, density_cutoff, want_promol=True, want_weights=True, want_entropy=True,
                        promol_offset=1e-100):

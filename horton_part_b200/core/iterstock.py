@@ -116,11 +116,123 @@ class AbstractISAWPart(AbstractStockholderWPart):
         self._state = IterationState(self.natom, npar, self.slab.device)
         return self._state
 
+    # -- grid_type 2/3: per-atom fixed points on the molecular grid ------------------------------
+    def _molgrid_shell_params(self, propars):
+        """(A, alpha) device tensors of the shell table for a device parameter vector."""
+        raise NotImplementedError(f"{self.name} with grid_type 2/3 is not built yet")
+
+    def _molgrid_apply(self, propars, s0, s1, shell_active):
+        """New parameter vector from the shell sums S0, S1 (only where shell_active)."""
+        raise NotImplementedError
+
+    molgrid_max_inner = 2000
+    molgrid_single_update = False
+
+    def _molgrid_pass(self, out_par, in_par, prev_par, active):
+        from .device import stream_ptr
+
+        t, s = self._table, self.slab
+        if getattr(self, "_mg", None) is None:
+            import torch
+
+            lim_a, lim_s = np.zeros(1, np.int32), np.zeros(1, np.int32)
+            _lib.call("hp_molgrid_update_tile_limits", lim_a, lim_s)
+            ntile, tiles = t.make_tiles(int(lim_a[0]), int(lim_s[0]))
+            nout = 2 * t.nshell + 2 * self.natom
+            nblk = int(_lib.call("hp_molgrid_num_blocks", s.npts))
+            self._mg = dict(
+                ntile=ntile, tiles=tiles, nout=nout,
+                partial=torch.zeros(nblk * nout, dtype=torch.float64, device=s.device),
+                out=torch.zeros(nout, dtype=torch.float64, device=s.device),
+                shell_atom=torch.from_numpy(np.repeat(np.arange(self.natom), t._counts)).to(s.device),
+            )
+        mg = self._mg
+        (Ao, alo), (Ai, ali), (Ap, alp) = out_par, in_par, prev_par
+        _lib.call(
+            "hp_molgrid_update_pass", t.functor, s.npts, s.px, s.py, s.pz, s.natom, s.atom_xyz, t.offsets,
+            Ao, alo, Ai, ali, Ap, alp, t.order, active, mg["ntile"], mg["tiles"], s.rho, s.molw, s.promol,
+            float(self.density_cutoff), t.nshell, mg["partial"], mg["out"], stream_ptr(s.device),
+        )  # fmt: skip
+        out = mg["out"]
+        if self._comm is not None:
+            import torch.distributed as dist
+
+            out = out.clone()
+            dist.all_reduce(out, group=self._comm)
+        M = t.nshell
+        return out[0 : 2 * M : 2], out[1 : 2 * M : 2], out[2 * M :: 2], out[2 * M + 1 :: 2]
+
+    def _run_iteration_molgrid(self):
+        """One outer iteration with grid_type 2/3 (mbis.py:170-173, gisa.py:257-279): the inner
+        fixed point of every atom runs on the whole molecular grid, all atoms batched per pass."""
+        import torch
+
+        from .device import stream_ptr
+
+        st, slab = self._state, self.slab
+        dev = slab.device
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+        ev[0].record()
+        self._refresh_table()
+        self._table.promol_weights(self.density_cutoff, True, True, True)
+        ev[1].record()
+        old = st.propars.clone()
+        out_par = self._molgrid_shell_params(old)
+        inner, prev = old.clone(), old.clone()
+        active = torch.ones(self.natom, dtype=torch.int32, device=dev)
+        pop = None
+        flags_not_converged = True
+        max_inner = 1 if self.molgrid_single_update else int(self.molgrid_max_inner)
+        for it in range(max_inner):
+            s0, s1, chg, p = self._molgrid_pass(out_par, self._molgrid_shell_params(inner),
+                                                self._molgrid_shell_params(prev), active)  # fmt: skip
+            if pop is None:
+                pop = p.clone()
+            shell_active = active[self._mg["shell_atom"]].bool()
+            prev = inner
+            inner = self._molgrid_apply(inner, s0, s1, shell_active)
+            if self.molgrid_single_update:
+                flags_not_converged = False
+                break
+            if it > 0:
+                converged = torch.sqrt(chg) < self._inner_threshold
+                active = active * (~converged).to(torch.int32)
+                if not bool(active.any().item()):
+                    flags_not_converged = False
+                    break
+        self._molgrid_not_converged = flags_not_converged
+        st.propars.copy_(inner)
+        st.charges.copy_(torch.from_numpy(np.ascontiguousarray(self.pseudo_numbers)).to(dev) - pop)
+        # compute_change on the molecular grid: chg column with in = new, prev = old outer parameters
+        _, _, msd, _ = self._molgrid_pass(out_par, self._molgrid_shell_params(inner),
+                                          self._molgrid_shell_params(old), None)  # fmt: skip
+        st.msd.copy_(msd)
+        _lib.call("hp_sum_partials", slab.npartial, slab.entropy_partials, st.entropy, stream_ptr(dev))
+        if self._comm is not None:
+            import torch.distributed as dist
+
+            dist.all_reduce(st.entropy, group=self._comm)
+        _lib.call("hp_finish_iteration", 1, st.entropy, self.natom, st.msd, st.out2, stream_ptr(dev))
+        ev[2].record()
+        nv = st.vec.numel()
+        st.host[:nv].copy_(st.vec, non_blocking=True)
+        st.host[nv:].copy_(st.out2, non_blocking=True)
+        torch.cuda.current_stream(dev).synchronize()
+        st.events.append(ev)
+        host = st.host.numpy()
+        n = self.natom
+        self.cache.load("propars")[:] = host[1 + 2 * n : nv]
+        self.cache.load("charges", alloc=n, tags="o")[0][:] = host[1 + n : 1 + 2 * n]
+        return float(host[nv]), float(host[nv + 1])
+
     def _run_iteration(self):
         """One outer iteration on the device; returns (change, entropy) after one host sync."""
         import torch
 
         from .device import stream_ptr
+
+        if self.on_molgrid:
+            return self._run_iteration_molgrid()
 
         st, slab = self._state, self.slab
         dev = slab.device

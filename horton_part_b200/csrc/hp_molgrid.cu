@@ -142,6 +142,154 @@ molgrid_reduce_kernel(int64_t npts, const double* __restrict__ px, const double*
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// grid_type 2/3 (row a9 on the molecular grid): one inner iteration of the per-atom fixed points
+// for ALL atoms at once.  Three shell-parameter sets over the same (alpha-order) structure:
+//   out  : outer parameters -> w_a = clip(rho0_a/promol, 0, 1), rhoa = w_a*rho  (fixed during the
+//          inner loop; mbis.py:170-173, gisa.py:257-260)
+//   in   : current inner parameters -> terms t_k = A_k exp(-alpha_k r^n), pro = sum_k t_k
+//   prev : previous inner parameters -> oldpro (the reference keeps the array, we recompute it)
+// Per shell:  S0_k = sum molw t_k ratio,  S1_k = sum molw t_k ratio r^n   (ratio = rhoa/pro, masked)
+// Per atom :  chg = sum molw (oldpro - pro)^2,  pop = sum molw rhoa
+// (mbis.py:128-152, alisa.py:262-274 with weights = grid.weights, r = radial_distances[a]).
+// Atoms with active[a] == 0 are skipped.  With in = new and prev = old outer parameters the chg
+// column is the atom's term of compute_change on the molecular grid (core/iterstock.py:40-41).
+// ---------------------------------------------------------------------------------------------
+constexpr int kUpTileAtoms = 32;
+constexpr int kUpTileShells = 128;
+constexpr int kUpCols = 2 * kUpTileShells + 2 * kUpTileAtoms;
+
+struct __align__(16) UpAtom {
+    double x, y, z;
+    int s0, ns;
+};
+
+template <int F>
+__global__ void __launch_bounds__(kMgThreads, 2)
+molgrid_update_kernel(int64_t npts, const double* __restrict__ px, const double* __restrict__ py,
+                      const double* __restrict__ pz, int natom, const double* __restrict__ atom_xyz,
+                      const int* __restrict__ atom_sh_off, const double* __restrict__ A_out,
+                      const double* __restrict__ al_out, const double* __restrict__ A_in,
+                      const double* __restrict__ al_in, const double* __restrict__ A_prev,
+                      const double* __restrict__ al_prev, const double* __restrict__ shell_order,
+                      const int* __restrict__ active, int ntile, const int* __restrict__ tile_off,
+                      const double* __restrict__ rho, const double* __restrict__ molw,
+                      const double* __restrict__ promol, double density_cutoff, int nshell,
+                      double* __restrict__ partial) {
+    constexpr int kP = 2;
+    __shared__ UpAtom s_atoms[kUpTileAtoms];
+    __shared__ int s_active[kUpTileAtoms];
+    __shared__ double s_par[6][kUpTileShells];  // A_out al_out A_in al_in A_prev al_prev
+    __shared__ double s_N[kUpTileShells];
+    __shared__ double s_acc[kMgWarps][kUpCols];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int nout = 2 * nshell + 2 * natom;
+    double* my_partial = partial + int64_t(blockIdx.x) * nout;
+    for (int i = threadIdx.x; i < nout; i += kMgThreads) my_partial[i] = 0.0;
+
+    const int64_t span = int64_t(kMgThreads) * kP;
+    const int64_t nchunk = (npts + span - 1) / span;
+    for (int64_t chunk = blockIdx.x; chunk < nchunk; chunk += gridDim.x) {
+        double x[kP], y[kP], z[kP], rh[kP], mw[kP], pm[kP];
+#pragma unroll
+        for (int j = 0; j < kP; ++j) {
+            const int64_t p = chunk * span + int64_t(j) * kMgThreads + threadIdx.x;
+            const bool live = p < npts;
+            const int64_t q = live ? p : npts - 1;
+            x[j] = px[q]; y[j] = py[q]; z[j] = pz[q];
+            rh[j] = rho[q]; pm[j] = promol[q];
+            mw[j] = live ? molw[q] : 0.0;
+        }
+        for (int tl = 0; tl < ntile; ++tl) {
+            const int a0 = tile_off[tl], a1 = tile_off[tl + 1];
+            const int sh0 = atom_sh_off[a0], sh1 = atom_sh_off[a1];
+            __syncthreads();
+            for (int i = threadIdx.x; i < a1 - a0; i += kMgThreads) {
+                UpAtom rec;
+                rec.x = atom_xyz[3 * (a0 + i)]; rec.y = atom_xyz[3 * (a0 + i) + 1]; rec.z = atom_xyz[3 * (a0 + i) + 2];
+                rec.s0 = atom_sh_off[a0 + i] - sh0;
+                rec.ns = atom_sh_off[a0 + i + 1] - atom_sh_off[a0 + i];
+                s_atoms[i] = rec;
+                s_active[i] = active ? active[a0 + i] : 1;
+            }
+            for (int i = threadIdx.x; i < sh1 - sh0; i += kMgThreads) {
+                s_par[0][i] = A_out[sh0 + i]; s_par[1][i] = al_out[sh0 + i];
+                s_par[2][i] = A_in[sh0 + i];  s_par[3][i] = al_in[sh0 + i];
+                s_par[4][i] = A_prev[sh0 + i]; s_par[5][i] = al_prev[sh0 + i];
+                s_N[i] = (F == HP_FUNCTOR_GENERAL) ? shell_order[sh0 + i] : 1.0;
+            }
+            for (int i = threadIdx.x; i < kUpCols; i += kMgThreads)
+                for (int w = 0; w < kMgWarps; ++w) s_acc[w][i] = 0.0;
+            __syncthreads();
+            for (int i = 0; i < a1 - a0; ++i) {
+                if (!s_active[i]) continue;
+                const UpAtom rec = s_atoms[i];
+                double r[kP], rhoa[kP], pro[kP], old[kP];
+#pragma unroll
+                for (int j = 0; j < kP; ++j) {
+                    const double dx = x[j] - rec.x, dy = y[j] - rec.y, dz = z[j] - rec.z;
+                    r[j] = mg_radial<F>(fma(dz, dz, fma(dy, dy, dx * dx)));
+                    double yo = 0.0;
+                    pro[j] = old[j] = 0.0;
+                    for (int k = 0; k < rec.ns; ++k) {
+                        const int c = rec.s0 + k;
+                        yo = fma(s_par[0][c], mg_shell<F>(s_par[1][c], s_N[c], r[j]), yo);
+                        pro[j] += s_par[2][c] * mg_shell<F>(s_par[3][c], s_N[c], r[j]);
+                        old[j] += s_par[4][c] * mg_shell<F>(s_par[5][c], s_N[c], r[j]);
+                    }
+                    rhoa[j] = fmin(fmax(yo / pm[j], 0.0), 1.0) * rh[j];
+                }
+                double chg = 0.0, pop = 0.0;
+#pragma unroll
+                for (int j = 0; j < kP; ++j) {
+                    const double e = old[j] - pro[j];
+                    chg = fma(mw[j] * e, e, chg);
+                    pop = fma(mw[j], rhoa[j], pop);
+                }
+                chg = warp_allsum(chg);
+                pop = warp_allsum(pop);
+                if (lane == 0) {
+                    s_acc[warp][2 * kUpTileShells + 2 * i] = chg;
+                    s_acc[warp][2 * kUpTileShells + 2 * i + 1] = pop;
+                }
+                for (int k = 0; k < rec.ns; ++k) {
+                    const int c = rec.s0 + k;
+                    double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+                    for (int j = 0; j < kP; ++j) {
+                        const bool sick = (rhoa[j] < density_cutoff) || (pro[j] < density_cutoff);
+                        const double ratio = sick ? 0.0 : rhoa[j] / pro[j];
+                        const double t = s_par[2][c] * mg_shell<F>(s_par[3][c], s_N[c], r[j]) * ratio;
+                        const double rn = (F == HP_FUNCTOR_GAUSS) ? r[j]
+                                          : ((s_N[c] == 1.0) ? r[j] : pow(r[j], s_N[c]));
+                        s0 = fma(mw[j], t, s0);
+                        s1 = fma(mw[j] * t, rn, s1);
+                    }
+                    s0 = warp_allsum(s0);
+                    s1 = warp_allsum(s1);
+                    if (lane == 0) {
+                        s_acc[warp][2 * c] = s0;
+                        s_acc[warp][2 * c + 1] = s1;
+                    }
+                }
+            }
+            __syncthreads();
+            for (int c = threadIdx.x; c < 2 * (sh1 - sh0); c += kMgThreads) {
+                double tot = 0.0;
+#pragma unroll
+                for (int w = 0; w < kMgWarps; ++w) tot += s_acc[w][c];
+                my_partial[2 * sh0 + c] += tot;
+            }
+            for (int c = threadIdx.x; c < 2 * (a1 - a0); c += kMgThreads) {
+                double tot = 0.0;
+#pragma unroll
+                for (int w = 0; w < kMgWarps; ++w) tot += s_acc[w][2 * kUpTileShells + c];
+                my_partial[2 * nshell + 2 * a0 + c] += tot;
+            }
+        }
+    }
+}
+
 // out[c] = sum over rows of partial[row][c], rows added in order.
 __global__ void __launch_bounds__(256)
 reduce_rows_kernel(int nrows, int ncols, const double* __restrict__ partial, double* __restrict__ out) {
@@ -287,4 +435,43 @@ extern "C" int hp_radial_change(int32_t natom, int32_t atom_base, const int32_t*
                                                               c_old, msd);
     HP_LAUNCH_CHECK("radial_change_kernel");
     return HP_OK;
+}
+
+extern "C" void hp_molgrid_update_tile_limits(int32_t* max_atoms_host, int32_t* max_shells_host) {
+    *max_atoms_host = kUpTileAtoms;
+    *max_shells_host = kUpTileShells;
+}
+
+extern "C" int hp_molgrid_update_pass(int functor, int64_t npts, const double* px, const double* py,
+                                      const double* pz, int32_t natom, const double* atom_xyz,
+                                      const int32_t* atom_shell_offsets, const double* A_out,
+                                      const double* alpha_out, const double* A_in, const double* alpha_in,
+                                      const double* A_prev, const double* alpha_prev,
+                                      const double* shell_order, const int32_t* active, int32_t ntile,
+                                      const int32_t* tile_atom_offsets, const double* rho,
+                                      const double* molw, const double* promol, double density_cutoff,
+                                      int32_t nshell, double* partial, double* out, void* stream) {
+    HP_REQUIRE(npts > 0 && natom > 0 && ntile > 0 && nshell > 0, "bad sizes");
+    HP_REQUIRE(px && py && pz && atom_xyz && atom_shell_offsets && A_out && alpha_out && A_in && alpha_in &&
+                   A_prev && alpha_prev && tile_atom_offsets && rho && molw && promol && partial && out,
+               "null input");
+    HP_REQUIRE(functor != HP_FUNCTOR_GENERAL || shell_order, "general functor needs shell_order");
+    cudaStream_t st = as_stream(stream);
+    const int nblocks = hp_molgrid_num_blocks(npts);
+    const int nout = 2 * nshell + 2 * natom;
+#define HP_UP(F)                                                                                        \
+    molgrid_update_kernel<F><<<nblocks, kMgThreads, 0, st>>>(                                           \
+        npts, px, py, pz, natom, atom_xyz, atom_shell_offsets, A_out, alpha_out, A_in, alpha_in, A_prev, \
+        alpha_prev, shell_order, active, ntile, tile_atom_offsets, rho, molw, promol, density_cutoff,    \
+        nshell, partial)
+    switch (functor) {
+        case HP_FUNCTOR_SLATER: HP_UP(HP_FUNCTOR_SLATER); break;
+        case HP_FUNCTOR_GAUSS: HP_UP(HP_FUNCTOR_GAUSS); break;
+        case HP_FUNCTOR_GENERAL: HP_UP(HP_FUNCTOR_GENERAL); break;
+        default: set_error("hp_molgrid_update_pass: unsupported functor %d", functor); return HP_ERR_ARG;
+    }
+#undef HP_UP
+    HP_LAUNCH_CHECK("molgrid_update_kernel");
+    reduce_rows_kernel<<<(nout + 255) / 256, 256, 0, st>>>(nblocks, nout, partial, out);
+    return check_cuda(cudaGetLastError(), "reduce_rows_kernel");
 }

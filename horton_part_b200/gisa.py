@@ -122,10 +122,9 @@ class GaussianISAWPart(AbstractISAWPart):
 
         from .core.device import ShellTable, to_device
 
-        if self.on_molgrid:
-            raise NotImplementedError(f"{self.name} with grid_type 2/3 is not built yet")
         propars = init_propars(self)
-        self._evaluate_basis_functions()
+        if not self.on_molgrid:
+            self._evaluate_basis_functions()
         slab = self.slab
         dev = slab.device
         orders = np.concatenate([np.asarray(self.bs_helper.get_order(z), float) for z in self.numbers])
@@ -145,6 +144,13 @@ class GaussianISAWPart(AbstractISAWPart):
         st.propars.copy_(to_device(propars, dev))
         self._par_offsets = to_device(np.asarray(self._ranges, dtype=np.int32), dev)
         self._pseudo = to_device(self.pseudo_numbers, dev, np.float64)
+        if self.on_molgrid:
+            if callable(self._solver) or self._solver not in self.device_solvers:
+                raise NotImplementedError("grid_type 2/3 needs one of the device solvers " + str(list(self.device_solvers)))
+            self.molgrid_single_update = bool(self.device_solvers[self._solver][1])
+            opt = self.device_solvers[self._solver][0]
+            self.molgrid_max_inner = int(float(self._solver_options.get(opt, 100000))) if opt else 1
+            return propars
         # radial-grid basis functions of the local atoms, concatenated (K_a x nrad_a row-major)
         sh = slab.shard
         blocks = [self.cache.load(f"bs_funcs_{a}") for a in range(sh.atom_lo, sh.atom_hi)]
@@ -161,6 +167,14 @@ class GaussianISAWPart(AbstractISAWPart):
 
         t = self._table
         _lib.call("hp_table_scaled", t.nshell, self._state.propars, self._norms, t.A, stream_ptr(self.slab.device))
+
+    def _molgrid_shell_params(self, propars):
+        return propars * self._norms, self._table.alpha
+
+    def _molgrid_apply(self, propars, s0, s1, shell_active):
+        import torch
+
+        return torch.where(shell_active, s0, propars)  # alisa.py:268
 
     def _launch_radial_update(self):
         self.slab.shell_project()
@@ -216,6 +230,8 @@ class GaussianISAWPart(AbstractISAWPart):
 
     def _finalize_propars(self):
         AbstractISAWPart._finalize_propars(self)
+        if self.on_molgrid:
+            return
         slab = self.slab
         sph = slab.sph_avg.cpu().numpy()
         ro = slab.rad_offsets_host

@@ -87,8 +87,6 @@ class MBISWPart(AbstractISAWPart):
     def _init_propars(self):
         from .core.device import ShellTable, to_device
 
-        if self.on_molgrid:
-            raise NotImplementedError("MBIS with grid_type 2/3 is not built yet")
         self._nshells = [int(get_nshell(z)) for z in self.numbers]
         self._ranges = [0]
         for k in self._nshells:
@@ -110,6 +108,25 @@ class MBISWPart(AbstractISAWPart):
         t = self._table
         _lib.call("hp_table_mbis", t.nshell, self._state.propars, t.A, t.alpha, stream_ptr(self.slab.device))
 
+    def _molgrid_shell_params(self, propars):
+        import torch
+
+        from .core.device import stream_ptr
+
+        n = self._table.nshell
+        A = torch.empty(n, dtype=torch.float64, device=propars.device)
+        alpha = torch.empty_like(A)
+        _lib.call("hp_table_mbis", n, propars, A, alpha, stream_ptr(self.slab.device))
+        return A, alpha
+
+    def _molgrid_apply(self, propars, s0, s1, shell_active):
+        import torch
+
+        new = propars.clone().view(-1, 2)
+        new[:, 0] = torch.where(shell_active, s0, new[:, 0])                 # mbis.py:145
+        new[:, 1] = torch.where(shell_active, 3.0 * s0 / s1, new[:, 1])      # mbis.py:146
+        return new.view(-1)
+
     def _launch_radial_update(self):
         from .core.device import stream_ptr
 
@@ -130,7 +147,7 @@ class MBISWPart(AbstractISAWPart):
     def _finalize_propars(self):
         AbstractISAWPart._finalize_propars(self)
         flags = self._state.flags.cpu().numpy()
-        if (flags & 1).any():
+        if (flags & 1).any() or getattr(self, "_molgrid_not_converged", False):
             self.logger.warning("MBIS not converged, but still go ahead!")
         if (flags & 2).any():
             self.logger.warning("The sum of propars are not equal to the atomic pop.")
@@ -142,6 +159,8 @@ class MBISWPart(AbstractISAWPart):
         self.cache.dump("core_charges", core_charges, tags="o")
         self.cache.dump("valence_charges", valence_charges, tags="o")
         self.cache.dump("valence_widths", valence_widths, tags="o")
+        if self.on_molgrid:
+            return
         # radial projections of the last iteration (mbis.py:185-187)
         slab = self.slab
         sph = slab.sph_avg.cpu().numpy()

@@ -235,6 +235,28 @@ HP_API int hp_radial_change(int32_t natom, int32_t atom_base, const int32_t* rad
                             const int64_t* bs_offsets, const double* bs_funcs, const double* c_new,
                             const double* c_old, double* msd, void* stream);
 
+/* (row a9, grid_type 2/3) one inner iteration of the per-atom fixed points on the MOLECULAR grid for
+ * all atoms at once (mbis.py:128-152 / alisa.py:262-274 with rhoa = at_weights*moldens,
+ * weights = grid.weights, r = radial_distances[a]; mbis.py:170-173, gisa.py:257-279).
+ * Three parameter sets share the shell structure: `out` (outer iteration: defines
+ * w_a = clip(rho0_a/promol,0,1)), `in` (current inner parameters), `prev` (previous inner
+ * parameters, to recompute `oldpro`).  out (2*nshell + 2*natom doubles):
+ *   [2m]   = sum_p molw t_m ratio        [2m+1] = sum_p molw t_m ratio r^n_m     (t_m = A_in exp(..))
+ *   [2*nshell + 2a] = sum_p molw (oldpro_a - pro_a)^2      [.. + 2a + 1] = sum_p molw rhoa
+ * Atoms with active[a] == 0 are skipped (NULL = all active).  `partial`: scratch of
+ * hp_molgrid_num_blocks(npts) x (2*nshell + 2*natom) doubles.  Tiles must respect
+ * hp_molgrid_update_tile_limits(). */
+HP_API void hp_molgrid_update_tile_limits(int32_t* max_atoms_host, int32_t* max_shells_host);
+HP_API int hp_molgrid_update_pass(int functor, int64_t npts, const double* px, const double* py,
+                                  const double* pz, int32_t natom, const double* atom_xyz,
+                                  const int32_t* atom_shell_offsets, const double* A_out,
+                                  const double* alpha_out, const double* A_in, const double* alpha_in,
+                                  const double* A_prev, const double* alpha_prev,
+                                  const double* shell_order, const int32_t* active, int32_t ntile,
+                                  const int32_t* tile_atom_offsets, const double* rho,
+                                  const double* molw, const double* promol, double density_cutoff,
+                                  int32_t nshell, double* partial, double* out, void* stream);
+
 /* hp_hessian: H[m][n] = sum_p molw*rho*g_m*g_n/promol^2 (masked like hp_shell_moments), the dense
  * M x M gLISA Hessian of _working_matrix(nderiv=2) (glisa.py:459-470), row-major, both triangles
  * filled.  shell_atom[m] = atom of shell m; g_m = shell_norm[m]*exp(-alpha_m r^n).  `scratch` needs
