@@ -6,6 +6,9 @@ per-point work is done by CUDA kernels on a device-resident :class:`GridSlab`; N
 cache are downloads of device results.  Additional keyword arguments of this implementation:
 
     device     torch device / index of the B200 to use (default: current CUDA device)
+    local_radius   cut-off radius (bohr) of the local-grid mode: atom a contributes only to points
+               with |r - R_a| <= local_radius (the reference's removed `radius_cutoff` design,
+               core/stockholder.py:45-112; None/inf = dense = the reference's live behaviour)
     comm       a ``torch.distributed`` process group: the grid is sharded by atom blocks over its
                ranks and per-iteration results are exchanged with NCCL
 """
@@ -206,7 +209,7 @@ class WPart(Part):
     def __init__(self, coordinates, numbers, pseudo_numbers, grid, moldens, spindens=None, lmax=3,
                  logger=None, grid_type=1, density_cutoff=DENSITY_CUTOFF,
                  negative_cutoff=NEGATIVE_CUTOFF, population_cutoff=POPULATION_CUTOFF,
-                 device=None, comm=None, **kwargs):  # fmt: skip
+                 device=None, comm=None, local_radius=None, **kwargs):  # fmt: skip
         self._grid_type = grid_type
         self._on_molgrid = None
         self._only_use_molgrid = None
@@ -222,6 +225,7 @@ class WPart(Part):
             setup_logger(logger)
         self._device = device
         self._comm = comm
+        self._local_radius = None if (local_radius is None or np.isinf(local_radius)) else float(local_radius)
         self._slab = None
         self._density_cutoff = density_cutoff
         self._population_cutoff = population_cutoff

@@ -209,10 +209,32 @@ class ShellTable:
             a = b
         return len(tiles) - 1, to_device(np.asarray(tiles, dtype=np.int32), self.slab.device)
 
+    #: cut-off radius of the local-grid mode (None = dense, the reference's semantics)
+    local_radius = None
+    pair_partials = None
+
+    def pairs_evaluated(self):
+        """atom x point pairs evaluated by the last cut-off launch on this rank."""
+        return int(self.pair_partials.sum().item()) if self.pair_partials is not None else None
+
     def promol_weights(self, density_cutoff, want_promol=True, want_weights=True, want_entropy=True,
                        promol_offset=1e-100):
         """Launch the fused promolecule / owner-weight / entropy pass over the local slab."""
         s = self.slab
+        if self.local_radius is not None:
+            import torch
+
+            if self.pair_partials is None:
+                self.pair_partials = torch.zeros(s.npartial, dtype=torch.int64, device=s.device)
+            _lib.call(
+                "hp_promol_weights_local", self.functor, s.npts, s.px, s.py, s.pz, s.point_base, s.natom,
+                s.atom_xyz, s.atom_point_offsets, self.offsets, self.A, self.alpha, self.order,
+                self.ntile, self.tiles, s.rho, s.molw, float(density_cutoff), float(promol_offset),
+                float(self.local_radius), s.promol if want_promol else None,
+                s.at_w if want_weights else None, s.entropy_partials if want_entropy else None,
+                self.pair_partials, stream_ptr(s.device),
+            )  # fmt: skip
+            return
         _lib.call(
             "hp_promol_weights", self.functor, s.npts, s.px, s.py, s.pz, s.point_base, s.natom,
             s.atom_xyz, s.atom_point_offsets, self.offsets, self.A, self.alpha, self.order,

@@ -64,6 +64,10 @@ class AbstractStockholderWPart(WPart):
     def _launch_promol_weights(self, want_entropy=True):
         """Enqueue the fused promolecule / owner-weight / entropy kernel (no synchronisation)."""
         self._refresh_table()
+        if self._local_radius is not None:
+            if not hasattr(self._table, "local_radius"):
+                raise NotImplementedError("local_radius is only available for exponential pro-atoms")
+            self._table.local_radius = self._local_radius
         self._table.promol_weights(self.density_cutoff, True, True, want_entropy)
 
     def update_at_weights(self, force_on_molgrid=False):

@@ -1,0 +1,288 @@
+// Cut-off ("local grid") variant of the fused promolecule / owner-weight / entropy pass.
+//
+// Semantics = the reference's local-grid design (commented block core/stockholder.py:45-112 +
+// qc-grid Grid.get_localgrid): atom a contributes only to the points with
+//     ((dx*dx + dy*dy) + dz*dz) <= radius*radius        (unfused FP64, exactly row L's rule)
+// and its own weight is zero outside that ball.  With radius = inf this is the dense pass.
+//
+// Work skipping happens per block and is conservative; the per-pair test above is exact:
+//   a chunk of consecutive grid points almost always lies on a few radial shells of ONE owner atom,
+//   r_min <= |p - R_o| <= r_max, so atom a can reach it only if
+//   r_min - radius <= |R_a - R_o| <= r_max + radius.  Atoms passing this annulus test are compacted
+//   IN ATOM ORDER into the shared-memory tile (warp ballots), so the sequential summation order of
+//   the reference is preserved.  Evaluated pairs are counted for the benchmark's "evals" metric.
+#include "hp_promol_common.cuh"
+
+namespace hp {
+
+constexpr int kLocThreads = 256;
+constexpr int kLocPts = 4;
+
+__device__ __forceinline__ double dist2_unfused3(double dx, double dy, double dz) {
+    return __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+}
+
+template <int F>
+__global__ void __launch_bounds__(kLocThreads, 2)
+promol_weights_local_kernel(int64_t npts, const double* __restrict__ px, const double* __restrict__ py,
+                            const double* __restrict__ pz, int64_t point_base, int natom,
+                            const double* __restrict__ atom_xyz, const int64_t* __restrict__ atom_pt_off,
+                            const int* __restrict__ atom_sh_off, const double* __restrict__ shell_A,
+                            const double* __restrict__ shell_alpha, const double* __restrict__ shell_order,
+                            int ntile, const int* __restrict__ tile_off, const double* __restrict__ rho,
+                            const double* __restrict__ molw, double density_cutoff, double promol_offset,
+                            double radius, double* __restrict__ promol_out, double* __restrict__ w_out,
+                            double* __restrict__ entropy_partials,
+                            unsigned long long* __restrict__ pair_partials) {
+    __shared__ AtomRec s_atoms[kTileAtoms];
+    __shared__ double2 s_AB[kTileShells];
+    __shared__ double s_N[(F == HP_FUNCTOR_GENERAL) ? kTileShells : 1];
+    __shared__ double s_red[32];
+    __shared__ double s_geom[5];  // owner centre x,y,z, r_min, r_max
+    __shared__ int s_flags[2];    // same-owner flag, owner index
+    __shared__ int s_wcnt[kTileAtoms / 32];
+    __shared__ int s_ncand;
+
+    const double rc2 = radius * radius;
+    const int64_t span = int64_t(kLocThreads) * kLocPts;
+    const int64_t nchunk = (npts + span - 1) / span;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double entropy_acc = 0.0;
+    unsigned long long pairs = 0;
+
+    for (int64_t chunk = blockIdx.x; chunk < nchunk; chunk += gridDim.x) {
+        double x[kLocPts], y[kLocPts], z[kLocPts], pro[kLocPts];
+        int nlive = 0;
+#pragma unroll
+        for (int j = 0; j < kLocPts; ++j) {
+            const int64_t p = chunk * span + int64_t(j) * kLocThreads + threadIdx.x;
+            const int64_t q = p < npts ? p : (npts - 1);
+            nlive += p < npts;
+            x[j] = px[q]; y[j] = py[q]; z[j] = pz[q];
+            pro[j] = 0.0;
+        }
+        // ---- chunk geometry: one owner? radial extent around it ---------------------------------
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const int64_t first = point_base + chunk * span;
+            int64_t last = point_base + chunk * span + span - 1;
+            if (last > point_base + npts - 1) last = point_base + npts - 1;
+            int own[2];
+            const int64_t g2[2] = {first, last};
+            for (int e = 0; e < 2; ++e) {
+                int lo = 0, hi = natom;
+                while (hi - lo > 1) {
+                    const int mid = (lo + hi) >> 1;
+                    if (atom_pt_off[mid] <= g2[e]) lo = mid; else hi = mid;
+                }
+                own[e] = lo;
+            }
+            s_flags[0] = own[0] == own[1];
+            s_flags[1] = own[0];
+            s_geom[0] = atom_xyz[3 * own[0]];
+            s_geom[1] = atom_xyz[3 * own[0] + 1];
+            s_geom[2] = atom_xyz[3 * own[0] + 2];
+        }
+        __syncthreads();
+        const bool same_owner = s_flags[0] != 0;
+        double rmin = 0.0, rmax = 0.0;
+        if (same_owner) {
+            double lo = 1e300, hi = 0.0;
+#pragma unroll
+            for (int j = 0; j < kLocPts; ++j) {
+                const double d = sqrt(dist2_unfused3(x[j] - s_geom[0], y[j] - s_geom[1], z[j] - s_geom[2]));
+                lo = fmin(lo, d);
+                hi = fmax(hi, d);
+            }
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) {
+                lo = fmin(lo, __shfl_xor_sync(0xffffffffu, lo, off));
+                hi = fmax(hi, __shfl_xor_sync(0xffffffffu, hi, off));
+            }
+            if (lane == 0) {
+                s_red[warp] = lo;
+                s_red[8 + warp] = hi;
+            }
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                double a = s_red[0], b = s_red[8];
+                for (int w = 1; w < kLocThreads / 32; ++w) {
+                    a = fmin(a, s_red[w]);
+                    b = fmax(b, s_red[8 + w]);
+                }
+                s_geom[3] = a;
+                s_geom[4] = b;
+            }
+            __syncthreads();
+            rmin = s_geom[3];
+            rmax = s_geom[4];
+        }
+        const double slack = 1e-9 * (1.0 + rmax + radius);
+
+        for (int t = 0; t < ntile; ++t) {
+            const int a0 = tile_off[t], a1 = tile_off[t + 1];
+            const int sh0 = atom_sh_off[a0], sh1 = atom_sh_off[a1];
+            __syncthreads();  // previous tile fully consumed
+            // ---- ordered compaction of the atoms that can reach this chunk -----------------------
+            AtomRec rec;
+            bool cand = false;
+            unsigned m = 0;
+            if (threadIdx.x < kTileAtoms) {  // warps 0..3, warp-uniform
+                const int i = threadIdx.x;
+                if (i < a1 - a0) {
+                    rec.x = atom_xyz[3 * (a0 + i) + 0];
+                    rec.y = atom_xyz[3 * (a0 + i) + 1];
+                    rec.z = atom_xyz[3 * (a0 + i) + 2];
+                    rec.s0 = atom_sh_off[a0 + i] - sh0;
+                    rec.ns = atom_sh_off[a0 + i + 1] - atom_sh_off[a0 + i];
+                    cand = true;
+                    if (same_owner) {
+                        const double D = sqrt(dist2_unfused3(rec.x - s_geom[0], rec.y - s_geom[1], rec.z - s_geom[2]));
+                        cand = (D >= rmin - radius - slack) && (D <= rmax + radius + slack);
+                    }
+                }
+                m = __ballot_sync(0xffffffffu, cand);
+                if (lane == 0) s_wcnt[warp] = __popc(m);
+            }
+            __syncthreads();
+            if (threadIdx.x < kTileAtoms) {
+                int off = 0;
+                for (int w = 0; w < warp; ++w) off += s_wcnt[w];
+                if (cand) s_atoms[off + __popc(m & ((1u << lane) - 1u))] = rec;
+                if (threadIdx.x == 0) {
+                    int tot = 0;
+                    for (int w = 0; w < kTileAtoms / 32; ++w) tot += s_wcnt[w];
+                    s_ncand = tot;
+                }
+            }
+            for (int i = threadIdx.x; i < sh1 - sh0; i += kLocThreads) {
+                s_AB[i] = make_double2(shell_A[sh0 + i], shell_alpha[sh0 + i]);
+                if (F == HP_FUNCTOR_GENERAL) s_N[i] = shell_order[sh0 + i];
+            }
+            __syncthreads();
+            const int ncand = s_ncand;
+            pairs += static_cast<unsigned long long>(ncand) * nlive;
+
+            for (int i = 0; i < ncand; ++i) {
+                const AtomRec ar = s_atoms[i];
+                double d2[kLocPts], f[kLocPts];
+#pragma unroll
+                for (int j = 0; j < kLocPts; ++j)
+                    d2[j] = dist2_unfused3(x[j] - ar.x, y[j] - ar.y, z[j] - ar.z);
+                eval_proatom<F, kLocPts>(d2, ar.s0, ar.ns, s_AB, s_N, f, s_AB[ar.s0]);
+#pragma unroll
+                for (int j = 0; j < kLocPts; ++j)
+                    pro[j] = (d2[j] <= rc2) ? (pro[j] + f[j]) + promol_offset : pro[j];
+            }
+        }
+
+#pragma unroll
+        for (int j = 0; j < kLocPts; ++j) {
+            const int64_t p = chunk * span + int64_t(j) * kLocThreads + threadIdx.x;
+            if (p >= npts) continue;
+            if (promol_out) promol_out[p] = pro[j];
+            if (w_out) {
+                const int64_t g = point_base + p;
+                int lo = 0, hi = natom;
+                while (hi - lo > 1) {
+                    const int mid = (lo + hi) >> 1;
+                    if (atom_pt_off[mid] <= g) lo = mid; else hi = mid;
+                }
+                const double d2 = dist2_unfused3(x[j] - atom_xyz[3 * lo], y[j] - atom_xyz[3 * lo + 1],
+                                                 z[j] - atom_xyz[3 * lo + 2]);
+                double w = 0.0;
+                if (d2 <= rc2) {
+                    const int s0 = atom_sh_off[lo], ns = atom_sh_off[lo + 1] - s0;
+                    const double r = (F == HP_FUNCTOR_GAUSS) ? d2 : sqrt_nocall(d2);
+                    double fo = 0.0;
+                    for (int k = 0; k < ns; ++k) {
+                        const double2 ab = make_double2(shell_A[s0 + k], shell_alpha[s0 + k]);
+                        const double n = (F == HP_FUNCTOR_GENERAL) ? shell_order[s0 + k] : 1.0;
+                        fo = fma(ab.x, shell_value<F>(ab, n, r), fo);
+                    }
+                    w = fmin(fmax(fo / pro[j], 0.0), 1.0);
+                }
+                w_out[p] = w;
+            }
+            if (entropy_partials) {
+                const double r = rho[p];
+                const bool sick = (pro[j] < density_cutoff) || (r < density_cutoff);
+                if (!sick) entropy_acc += molw[p] * r * log(r / pro[j]);
+            }
+        }
+    }
+
+    if (entropy_partials) {
+        const double total = block_sum(entropy_acc, s_red);
+        if (threadIdx.x == 0) entropy_partials[blockIdx.x] = total;
+        if (blockIdx.x == 0)
+            for (int i = gridDim.x + threadIdx.x; i < kMaxPartials; i += kLocThreads) entropy_partials[i] = 0.0;
+    }
+    if (pair_partials) {
+        // each thread tallied (candidates x its own live points): the block total is the sum
+        unsigned long long v = pairs;
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+        __shared__ unsigned long long s_pairs[kLocThreads / 32];
+        if (lane == 0) s_pairs[warp] = v;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            unsigned long long tot = 0;
+            for (int w = 0; w < kLocThreads / 32; ++w) tot += s_pairs[w];
+            pair_partials[blockIdx.x] = tot;
+        }
+        if (blockIdx.x == 0)
+            for (int i = gridDim.x + threadIdx.x; i < kMaxPartials; i += kLocThreads) pair_partials[i] = 0ull;
+    }
+}
+
+}  // namespace hp
+
+using namespace hp;
+
+extern "C" int hp_promol_weights_local(int functor, int64_t npts, const double* px, const double* py,
+                                       const double* pz, int64_t point_base, int32_t natom,
+                                       const double* atom_xyz, const int64_t* atom_point_offsets,
+                                       const int32_t* atom_shell_offsets, const double* shell_A,
+                                       const double* shell_alpha, const double* shell_order,
+                                       int32_t ntile, const int32_t* tile_atom_offsets,
+                                       const double* rho, const double* molw, double density_cutoff,
+                                       double promol_offset, double radius, double* promol,
+                                       double* at_weights, double* entropy_partials,
+                                       uint64_t* pair_partials, void* stream) {
+    HP_REQUIRE(npts >= 0 && natom > 0 && ntile > 0, "bad sizes");
+    HP_REQUIRE(px && py && pz && atom_xyz && atom_point_offsets && atom_shell_offsets, "null input");
+    HP_REQUIRE(shell_A && shell_alpha && tile_atom_offsets, "null shell table");
+    HP_REQUIRE(functor != HP_FUNCTOR_GENERAL || shell_order, "general functor needs shell_order");
+    HP_REQUIRE(!entropy_partials || (rho && molw), "entropy needs rho and molw");
+    HP_REQUIRE(radius >= 0.0, "negative radius");
+    cudaStream_t st = as_stream(stream);
+    if (npts == 0) {
+        if (entropy_partials) {
+            int rc = check_cuda(cudaMemsetAsync(entropy_partials, 0, sizeof(double) * kMaxPartials, st), "memset");
+            if (rc) return rc;
+        }
+        if (pair_partials)
+            return check_cuda(cudaMemsetAsync(pair_partials, 0, sizeof(uint64_t) * kMaxPartials, st), "memset");
+        return HP_OK;
+    }
+    const int64_t span = int64_t(kLocThreads) * kLocPts;
+    int64_t grid = (npts + span - 1) / span;
+    int64_t cap = int64_t(sm_count()) * 2;
+    if (cap > kMaxPartials) cap = kMaxPartials;
+    if (grid > cap) grid = cap;
+#define HP_LOC(F)                                                                                        \
+    promol_weights_local_kernel<F><<<int(grid), kLocThreads, 0, st>>>(                                   \
+        npts, px, py, pz, point_base, natom, atom_xyz, atom_point_offsets, atom_shell_offsets, shell_A,  \
+        shell_alpha, shell_order, ntile, tile_atom_offsets, rho, molw, density_cutoff, promol_offset,    \
+        radius, promol, at_weights, entropy_partials, reinterpret_cast<unsigned long long*>(pair_partials))
+    switch (functor) {
+        case HP_FUNCTOR_SLATER: HP_LOC(HP_FUNCTOR_SLATER); break;
+        case HP_FUNCTOR_GAUSS: HP_LOC(HP_FUNCTOR_GAUSS); break;
+        case HP_FUNCTOR_GENERAL: HP_LOC(HP_FUNCTOR_GENERAL); break;
+        default: set_error("hp_promol_weights_local: unsupported functor %d", functor); return HP_ERR_ARG;
+    }
+#undef HP_LOC
+    HP_LAUNCH_CHECK("promol_weights_local_kernel");
+    return HP_OK;
+}

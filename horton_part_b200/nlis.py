@@ -53,7 +53,7 @@ class NLISWPart(AbstractISAWPart):
                  nshell_dict=None, grid_type=1, **kwargs):  # fmt: skip
         self._exp_n_dict = exp_n_dict
         self._nshell_dict = nshell_dict or {}
-        device_kw = {k: kwargs[k] for k in ("device", "comm") if k in kwargs}
+        device_kw = {k: kwargs[k] for k in ("device", "comm", "local_radius") if k in kwargs}
         super().__init__(coordinates, numbers, pseudo_numbers, grid, moldens, spindens, lmax=lmax,
                          logger=logger, threshold=threshold, maxiter=maxiter,
                          inner_threshold=inner_threshold, grid_type=grid_type, **device_kw)  # fmt: skip

@@ -117,6 +117,24 @@ HP_API int hp_promol_weights(int functor, int64_t npts, const double* px, const 
                       const double* molw, double density_cutoff, double promol_offset,
                       double* promol, double* at_weights, double* entropy_partials, void* stream);
 
+/* Cut-off ("local grid") variant: atom a contributes to point p only if
+ * ((dx*dx+dy*dy)+dz*dz) <= radius*radius (the bit-exact rule of hp_build_local_index / qc-grid
+ * Grid.get_localgrid), and the owner's weight is 0 outside its own ball -- the semantics of the
+ * reference's local-grid design (commented block core/stockholder.py:45-112).  Blocks skip atoms
+ * that cannot reach their chunk of points (conservative annulus test around the owner atom) while
+ * keeping the atom order.  pair_partials (hp_num_partials() uint64, may be NULL) receives per-block
+ * counts of the atom x point pairs actually evaluated. */
+HP_API int hp_promol_weights_local(int functor, int64_t npts, const double* px, const double* py,
+                                   const double* pz, int64_t point_base, int32_t natom,
+                                   const double* atom_xyz, const int64_t* atom_point_offsets,
+                                   const int32_t* atom_shell_offsets, const double* shell_A,
+                                   const double* shell_alpha, const double* shell_order,
+                                   int32_t ntile, const int32_t* tile_atom_offsets,
+                                   const double* rho, const double* molw, double density_cutoff,
+                                   double promol_offset, double radius, double* promol,
+                                   double* at_weights, double* entropy_partials,
+                                   uint64_t* pair_partials, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * (row a8) spherical average of w_a*rho over each radial shell of each atom's own atomic grid.
  * Replaces AtomGrid.spherical_average as called from mbis.py:176-184, gisa.py:283-289,

@@ -72,6 +72,30 @@ def stockholder_weights(grid, proatom_fn, natom, owner_only=True):
     return promol, weights
 
 
+def stockholder_weights_local(grid, proatom_on_r, coords, natom, radius):
+    """The reference's local-grid design (commented block core/stockholder.py:45-112): atom a is
+    evaluated only on Grid.get_localgrid(R_a, radius); promolecule and the 1e-100 offsets are
+    accumulated on those points only; w_a lives on the overlap of the local grid with atom a's own
+    slice and is zero elsewhere."""
+    promol = np.zeros(grid.size)
+    local = []
+    for a in range(natom):
+        lo, hi = grid.indices[a], grid.indices[a + 1]
+        idx, overlap, dist = local_index(grid.points, coords[a], radius, lo, hi)
+        work = proatom_on_r(a, dist)
+        promol[idx] += work
+        promol[idx] += 1e-100
+        local.append((idx[overlap] - lo, work[overlap]))
+    weights = []
+    for a in range(natom):
+        lo, hi = grid.indices[a], grid.indices[a + 1]
+        w = np.zeros(hi - lo)
+        rel, pro = local[a]
+        w[rel] = np.clip(pro / promol[lo:hi][rel], 0, 1)
+        weights.append(w)
+    return promol, weights
+
+
 def local_index(points, center, radius, begin, end):
     """Row L: Grid.get_localgrid == cKDTree.query_ball_point(center, radius, p=2.0), canonicalised
     to ascending order; spec core/stockholder.py:84-112."""
@@ -156,7 +180,7 @@ def _radial_change(atgrids, ranges, fn, new, old):
 
 
 def _iterate(grid, rho, natom, pseudo, propars, ranges, proatom_on_r, update_atom, threshold, maxiter,
-             cutoff=DENSITY_CUTOFF, coords=None):  # fmt: skip
+             cutoff=DENSITY_CUTOFF, coords=None, local_radius=None):  # fmt: skip
     """The outer loop of AbstractISAWPart.do_partitioning (core/iterstock.py:159-193) for
     grid_type=1: weights from the current propars, per-atom projection + update, entropy of the
     promolecule that was just used, change between new and old propars."""
@@ -167,9 +191,15 @@ def _iterate(grid, rho, natom, pseudo, propars, ranges, proatom_on_r, update_ato
     while True:
         counter += 1
         old = propars.copy()
-        promol, weights = stockholder_weights(
-            grid, lambda a: proatom_on_r(a, propars[ranges[a] : ranges[a + 1]], dist[a]), natom
-        )
+        if local_radius is None:
+            promol, weights = stockholder_weights(
+                grid, lambda a: proatom_on_r(a, propars[ranges[a] : ranges[a + 1]], dist[a]), natom
+            )
+        else:
+            promol, weights = stockholder_weights_local(
+                grid, lambda a, r: proatom_on_r(a, propars[ranges[a] : ranges[a + 1]], r), coords, natom,
+                local_radius,
+            )
         inner = []
         for a in range(natom):
             g = grid.atgrids[a]
@@ -205,7 +235,7 @@ def _iterate(grid, rho, natom, pseudo, propars, ranges, proatom_on_r, update_ato
 
 
 def mbis(coords, numbers, pseudo, grid, rho, threshold=1e-6, inner_threshold=1e-8, maxiter=500,
-         cutoff=DENSITY_CUTOFF):  # fmt: skip
+         cutoff=DENSITY_CUTOFF, local_radius=None):  # fmt: skip
     """MBISWPart(...).do_partitioning(), grid_type=1 (mbis.py:167-203, 291-305)."""
     natom = len(numbers)
     inner_threshold = min(inner_threshold, threshold)  # core/iterstock.py:101
@@ -217,7 +247,7 @@ def mbis(coords, numbers, pseudo, grid, rho, threshold=1e-6, inner_threshold=1e-
         grid, rho, natom, pseudo, propars, ranges,
         lambda a, par, r: mbis_proatom(par, r),
         lambda a, sph, par, w4, r: mbis_inner(sph, par, w4, r, inner_threshold, cutoff),
-        threshold, maxiter, cutoff, coords,
+        threshold, maxiter, cutoff, coords, local_radius,
     )  # fmt: skip
 
 
