@@ -223,6 +223,8 @@ def main():
     ap.add_argument("--cpu-points", type=int, default=16384, help="grid points per core in the CPU sample")
     ap.add_argument("--cpu-reps", type=int, default=16, help="passes over the CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--local-radius", type=float, default=16.0,
+                    help="cut-off radius (bohr) of the extra local-grid measurement; 0 disables it")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
 
@@ -308,6 +310,37 @@ def main():
     del part
     torch.cuda.empty_cache()
 
+    # ---- extra: the same iterations in cut-off (local grid) mode, credited for evaluated pairs only
+    cutoff = None
+    if args.local_radius > 0:
+        part_c = MBISWPart(coords, numbers, pseudo, grid, rho, device=dev, comm=comm, maxiter=nsteps,
+                           local_radius=args.local_radius)
+        part_c._init_propars()
+        for _ in range(args.warmup):
+            part_c._run_iteration()
+        barrier()
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        c0.record()
+        for _ in range(args.steps):
+            part_c._run_iteration()
+        c1.record()
+        barrier()
+        ms_c = max_over_ranks(c0.elapsed_time(c1))
+        pairs = float(part_c._table.pairs_evaluated())
+        if comm is not None:
+            tp = torch.tensor([pairs], dtype=torch.float64, device=dev)
+            dist.all_reduce(tp)
+            pairs = float(tp.item())
+        cutoff = {
+            "local_radius_bohr": args.local_radius, "ms_per_step": ms_c / args.steps,
+            "iterations_per_s": args.steps / (ms_c * 1e-3),
+            "pairs_evaluated_per_step": pairs, "fraction_of_dense_pairs": pairs / evals_per_step,
+            "evals_per_s_credited": pairs * args.steps / (ms_c * 1e-3),
+            "max_abs_charge_diff_vs_dense_same_iterations": float(np.abs(part_c["charges"] - charges_resident).max()),
+        }
+        del part_c
+        torch.cuda.empty_cache()
+
     # ---- end-to-end arm: host buffers -> WPart API -> host results, copies inside the timed region
     barrier()
     t0 = time.perf_counter()
@@ -369,6 +402,7 @@ def main():
         "other_kernels_ms_per_step": float(np.mean(rest_ms)),
         "last_change": change, "last_entropy": entropy,
         "charges_O_H_H": [float(x) for x in charges_resident[:3]],
+        "cutoff_mode": cutoff,
     }  # fmt: skip
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(coords, numbers, grid, os.cpu_count() or 1, points_per_core=args.cpu_points, reps=args.cpu_reps)
