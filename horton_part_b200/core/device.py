@@ -17,6 +17,8 @@ Config 5 (2,000 atoms, 58.2 M points): 8 x 8 B x 58.2 M = 3.7 GB on one GPU, 0.4
 
 from __future__ import annotations
 
+import os
+
 import numpy as np
 
 from .. import _lib
@@ -212,6 +214,11 @@ class ShellTable:
     #: cut-off radius of the local-grid mode (None = dense, the reference's semantics)
     local_radius = None
     pair_partials = None
+    #: shell screening: a shell is dropped for a chunk of points when it is below 2^-screen_bits of
+    #: the atom's most diffuse shell there (cannot change the FP64 sum); None = evaluate every shell
+    #: with the plain dense kernel.  Env HP_B200_SCREEN_BITS overrides (0 disables).
+    screen_bits = 100.0
+    skip = None
 
     def pairs_evaluated(self):
         """atom x point pairs evaluated by the last cut-off launch on this rank."""
@@ -221,16 +228,28 @@ class ShellTable:
                        promol_offset=1e-100):
         """Launch the fused promolecule / owner-weight / entropy pass over the local slab."""
         s = self.slab
-        if self.local_radius is not None:
+        bits = self.screen_bits
+        env = os.environ.get("HP_B200_SCREEN_BITS")
+        if env is not None:
+            bits = float(env) or None
+        if self.functor == 3:
+            bits = None  # mixed orders: no common radial variable to screen on
+        if self.local_radius is not None or bits:
             import torch
 
             if self.pair_partials is None:
                 self.pair_partials = torch.zeros(s.npartial, dtype=torch.int64, device=s.device)
+            if bits:
+                if self.skip is None:
+                    self.skip = torch.empty_like(self.A)
+                _lib.call("hp_shell_screen", s.natom, self.offsets, self.A, self.alpha, float(bits), self.skip,
+                          stream_ptr(s.device))  # fmt: skip
+            radius = float("inf") if self.local_radius is None else float(self.local_radius)
             _lib.call(
                 "hp_promol_weights_local", self.functor, s.npts, s.px, s.py, s.pz, s.point_base, s.natom,
                 s.atom_xyz, s.atom_point_offsets, self.offsets, self.A, self.alpha, self.order,
                 self.ntile, self.tiles, s.rho, s.molw, float(density_cutoff), float(promol_offset),
-                float(self.local_radius), s.promol if want_promol else None,
+                radius, self.skip if bits else None, s.promol if want_promol else None,
                 s.at_w if want_weights else None, s.entropy_partials if want_entropy else None,
                 self.pair_partials, stream_ptr(s.device),
             )  # fmt: skip

@@ -5,6 +5,12 @@
 //     ((dx*dx + dy*dy) + dz*dz) <= radius*radius        (unfused FP64, exactly row L's rule)
 // and its own weight is zero outside that ball.  With radius = inf this is the dense pass.
 //
+// Shell screening (optional, `shell_skip`): shell k of an atom is dropped for a whole chunk when, at
+// the chunk's minimum distance to that atom, it is below 2^-nbits (default 2^-100) of the atom's most
+// diffuse shell -- it could not change the FP64 value of the atom's pro-atom sum (the chance of a
+// last-bit flip is 2^(53-nbits) per evaluation).  The thresholds come from hp_shell_screen.  This is
+// what makes far-away core shells and tight Gaussians free.
+//
 // Work skipping happens per block and is conservative; the per-pair test above is exact:
 //   a chunk of consecutive grid points almost always lies on a few radial shells of ONE owner atom,
 //   r_min <= |p - R_o| <= r_max, so atom a can reach it only if
@@ -22,7 +28,7 @@ __device__ __forceinline__ double dist2_unfused3(double dx, double dy, double dz
     return __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
 }
 
-template <int F>
+template <int F, bool LOCAL>
 __global__ void __launch_bounds__(kLocThreads, 2)
 promol_weights_local_kernel(int64_t npts, const double* __restrict__ px, const double* __restrict__ py,
                             const double* __restrict__ pz, int64_t point_base, int natom,
@@ -31,16 +37,18 @@ promol_weights_local_kernel(int64_t npts, const double* __restrict__ px, const d
                             const double* __restrict__ shell_alpha, const double* __restrict__ shell_order,
                             int ntile, const int* __restrict__ tile_off, const double* __restrict__ rho,
                             const double* __restrict__ molw, double density_cutoff, double promol_offset,
-                            double radius, double* __restrict__ promol_out, double* __restrict__ w_out,
+                            double radius, const double* __restrict__ shell_skip,
+                            double* __restrict__ promol_out, double* __restrict__ w_out,
                             double* __restrict__ entropy_partials,
                             unsigned long long* __restrict__ pair_partials) {
-    __shared__ AtomRec s_atoms[kTileAtoms];
+    __shared__ AtomRec s_atoms[kTileAtoms + 1];  // +1: sentinel for the prefetch
     __shared__ double2 s_AB[kTileShells];
     __shared__ double s_N[(F == HP_FUNCTOR_GENERAL) ? kTileShells : 1];
     __shared__ double s_red[32];
     __shared__ double s_geom[5];  // owner centre x,y,z, r_min, r_max
     __shared__ int s_flags[2];    // same-owner flag, owner index
     __shared__ int s_wcnt[kTileAtoms / 32];
+    __shared__ int s_wsh[kTileAtoms / 32];
     __shared__ int s_ncand;
 
     const double rc2 = radius * radius;
@@ -127,52 +135,93 @@ promol_weights_local_kernel(int64_t npts, const double* __restrict__ px, const d
             AtomRec rec;
             bool cand = false;
             unsigned m = 0;
+            int nkeep = 0, shell_incl = 0, gs0 = 0;
+            double xmin = 0.0;
             if (threadIdx.x < kTileAtoms) {  // warps 0..3, warp-uniform
                 const int i = threadIdx.x;
                 if (i < a1 - a0) {
                     rec.x = atom_xyz[3 * (a0 + i) + 0];
                     rec.y = atom_xyz[3 * (a0 + i) + 1];
                     rec.z = atom_xyz[3 * (a0 + i) + 2];
-                    rec.s0 = atom_sh_off[a0 + i] - sh0;
-                    rec.ns = atom_sh_off[a0 + i + 1] - atom_sh_off[a0 + i];
+                    gs0 = atom_sh_off[a0 + i];
+                    rec.ns = atom_sh_off[a0 + i + 1] - gs0;
                     cand = true;
                     if (same_owner) {
                         const double D = sqrt(dist2_unfused3(rec.x - s_geom[0], rec.y - s_geom[1], rec.z - s_geom[2]));
-                        cand = (D >= rmin - radius - slack) && (D <= rmax + radius + slack);
+                        if (LOCAL) cand = (D >= rmin - radius - slack) && (D <= rmax + radius + slack);
+                        const double dmin = fmax(0.0, fmax(D - rmax, rmin - D) - slack);
+                        xmin = (F == HP_FUNCTOR_GAUSS) ? dmin * dmin : dmin;
+                    }
+                    if (cand) {
+                        nkeep = rec.ns;
+                        if (shell_skip && F != HP_FUNCTOR_GENERAL) {
+                            nkeep = 0;
+                            for (int k = 0; k < rec.ns; ++k) nkeep += !(xmin > shell_skip[gs0 + k]);
+                        }
                     }
                 }
                 m = __ballot_sync(0xffffffffu, cand);
+                // inclusive warp scan of the kept-shell counts (atom order)
+                shell_incl = nkeep;
+#pragma unroll
+                for (int off = 1; off < 32; off <<= 1) {
+                    const int v = __shfl_up_sync(0xffffffffu, shell_incl, off);
+                    if (lane >= off) shell_incl += v;
+                }
+                if (lane == 31) s_wsh[warp] = shell_incl;
                 if (lane == 0) s_wcnt[warp] = __popc(m);
             }
             __syncthreads();
             if (threadIdx.x < kTileAtoms) {
-                int off = 0;
-                for (int w = 0; w < warp; ++w) off += s_wcnt[w];
-                if (cand) s_atoms[off + __popc(m & ((1u << lane) - 1u))] = rec;
+                int off = 0, shoff = 0;
+                for (int w = 0; w < warp; ++w) {
+                    off += s_wcnt[w];
+                    shoff += s_wsh[w];
+                }
+                if (cand) {
+                    int dst = shoff + shell_incl - nkeep;
+                    rec.s0 = dst;
+                    const bool screen = shell_skip && F != HP_FUNCTOR_GENERAL;
+                    for (int k = 0; k < rec.ns; ++k) {
+                        if (screen && xmin > shell_skip[gs0 + k]) continue;
+                        s_AB[dst] = make_double2(shell_A[gs0 + k], shell_alpha[gs0 + k]);
+                        if (F == HP_FUNCTOR_GENERAL) s_N[dst] = shell_order[gs0 + k];
+                        ++dst;
+                    }
+                    rec.ns = nkeep;
+                    s_atoms[off + __popc(m & ((1u << lane) - 1u))] = rec;
+                }
                 if (threadIdx.x == 0) {
                     int tot = 0;
                     for (int w = 0; w < kTileAtoms / 32; ++w) tot += s_wcnt[w];
                     s_ncand = tot;
+                    AtomRec sentinel = {0.0, 0.0, 0.0, 0, 0};
+                    s_atoms[tot] = sentinel;
                 }
-            }
-            for (int i = threadIdx.x; i < sh1 - sh0; i += kLocThreads) {
-                s_AB[i] = make_double2(shell_A[sh0 + i], shell_alpha[sh0 + i]);
-                if (F == HP_FUNCTOR_GENERAL) s_N[i] = shell_order[sh0 + i];
             }
             __syncthreads();
             const int ncand = s_ncand;
             pairs += static_cast<unsigned long long>(ncand) * nlive;
 
+            AtomRec nxt = s_atoms[0];
+            double2 nxt_ab = s_AB[nxt.s0];
             for (int i = 0; i < ncand; ++i) {
-                const AtomRec ar = s_atoms[i];
+                const AtomRec ar = nxt;
+                const double2 ab0 = nxt_ab;
+                nxt = s_atoms[i + 1];  // entry [ncand] is a sentinel
+                nxt_ab = s_AB[nxt.s0];
                 double d2[kLocPts], f[kLocPts];
 #pragma unroll
-                for (int j = 0; j < kLocPts; ++j)
-                    d2[j] = dist2_unfused3(x[j] - ar.x, y[j] - ar.y, z[j] - ar.z);
-                eval_proatom<F, kLocPts>(d2, ar.s0, ar.ns, s_AB, s_N, f, s_AB[ar.s0]);
+                for (int j = 0; j < kLocPts; ++j) {
+                    const double dx = x[j] - ar.x, dy = y[j] - ar.y, dz = z[j] - ar.z;
+                    d2[j] = LOCAL ? dist2_unfused3(dx, dy, dz) : fma(dz, dz, fma(dy, dy, dx * dx));
+                }
+                eval_proatom<F, kLocPts>(d2, ar.s0, ar.ns, s_AB, s_N, f, ab0);
 #pragma unroll
-                for (int j = 0; j < kLocPts; ++j)
-                    pro[j] = (d2[j] <= rc2) ? (pro[j] + f[j]) + promol_offset : pro[j];
+                for (int j = 0; j < kLocPts; ++j) {
+                    if (LOCAL) pro[j] = (d2[j] <= rc2) ? (pro[j] + f[j]) + promol_offset : pro[j];
+                    else pro[j] = (pro[j] + f[j]) + promol_offset;
+                }
             }
         }
 
@@ -188,10 +237,11 @@ promol_weights_local_kernel(int64_t npts, const double* __restrict__ px, const d
                     const int mid = (lo + hi) >> 1;
                     if (atom_pt_off[mid] <= g) lo = mid; else hi = mid;
                 }
-                const double d2 = dist2_unfused3(x[j] - atom_xyz[3 * lo], y[j] - atom_xyz[3 * lo + 1],
-                                                 z[j] - atom_xyz[3 * lo + 2]);
+                const double odx = x[j] - atom_xyz[3 * lo], ody = y[j] - atom_xyz[3 * lo + 1],
+                             odz = z[j] - atom_xyz[3 * lo + 2];
+                const double d2 = LOCAL ? dist2_unfused3(odx, ody, odz) : fma(odz, odz, fma(ody, ody, odx * odx));
                 double w = 0.0;
-                if (d2 <= rc2) {
+                if (!LOCAL || d2 <= rc2) {
                     const int s0 = atom_sh_off[lo], ns = atom_sh_off[lo + 1] - s0;
                     const double r = (F == HP_FUNCTOR_GAUSS) ? d2 : sqrt_nocall(d2);
                     double fo = 0.0;
@@ -236,9 +286,52 @@ promol_weights_local_kernel(int64_t npts, const double* __restrict__ px, const d
     }
 }
 
+// Screening thresholds: shell_skip[k] = largest value of the radial variable (r for Slater, r^2 for
+// Gaussian shells) at which shell k is still >= 2^-nbits of the atom's most diffuse shell with a
+// non-zero amplitude.  +inf = never dropped, -1 = always negligible (zero amplitude).
+__global__ void shell_screen_kernel(int natom, const int* __restrict__ atom_sh_off,
+                                    const double* __restrict__ A, const double* __restrict__ alpha,
+                                    double nbits, double* __restrict__ skip) {
+    const int a = blockIdx.x * blockDim.x + threadIdx.x;
+    if (a >= natom) return;
+    const int s0 = atom_sh_off[a], s1 = atom_sh_off[a + 1];
+    int ref = -1;
+    bool clean = true;
+    for (int k = s0; k < s1; ++k) {
+        clean = clean && isfinite(A[k]) && isfinite(alpha[k]) && alpha[k] >= 0.0;
+        if (A[k] != 0.0 && (ref < 0 || alpha[k] < alpha[ref])) ref = k;
+    }
+    const double inf = __longlong_as_double(0x7ff0000000000000ll);
+    for (int k = s0; k < s1; ++k) {
+        double t = inf;
+        if (clean && ref >= 0) {
+            if (A[k] == 0.0) {
+                t = -1.0;
+            } else if (k != ref) {
+                const double lr = log(fabs(A[k] / A[ref])) + nbits * 0.6931471805599453;
+                const double da = alpha[k] - alpha[ref];
+                if (da > 0.0) t = lr / da;
+                else if (lr < 0.0) t = -1.0;  // same exponent, amplitude below the threshold
+            }
+        }
+        skip[k] = t;
+    }
+}
+
 }  // namespace hp
 
 using namespace hp;
+
+extern "C" int hp_shell_screen(int32_t natom, const int32_t* atom_shell_offsets, const double* shell_A,
+                               const double* shell_alpha, double nbits, double* shell_skip,
+                               void* stream) {
+    HP_REQUIRE(natom > 0 && atom_shell_offsets && shell_A && shell_alpha && shell_skip, "bad arguments");
+    HP_REQUIRE(nbits >= 60.0, "nbits must be >= 60");
+    shell_screen_kernel<<<(natom + 127) / 128, 128, 0, as_stream(stream)>>>(natom, atom_shell_offsets, shell_A,
+                                                                            shell_alpha, nbits, shell_skip);
+    HP_LAUNCH_CHECK("shell_screen_kernel");
+    return HP_OK;
+}
 
 extern "C" int hp_promol_weights_local(int functor, int64_t npts, const double* px, const double* py,
                                        const double* pz, int64_t point_base, int32_t natom,
@@ -247,15 +340,15 @@ extern "C" int hp_promol_weights_local(int functor, int64_t npts, const double* 
                                        const double* shell_alpha, const double* shell_order,
                                        int32_t ntile, const int32_t* tile_atom_offsets,
                                        const double* rho, const double* molw, double density_cutoff,
-                                       double promol_offset, double radius, double* promol,
-                                       double* at_weights, double* entropy_partials,
+                                       double promol_offset, double radius, const double* shell_skip,
+                                       double* promol, double* at_weights, double* entropy_partials,
                                        uint64_t* pair_partials, void* stream) {
     HP_REQUIRE(npts >= 0 && natom > 0 && ntile > 0, "bad sizes");
     HP_REQUIRE(px && py && pz && atom_xyz && atom_point_offsets && atom_shell_offsets, "null input");
     HP_REQUIRE(shell_A && shell_alpha && tile_atom_offsets, "null shell table");
     HP_REQUIRE(functor != HP_FUNCTOR_GENERAL || shell_order, "general functor needs shell_order");
     HP_REQUIRE(!entropy_partials || (rho && molw), "entropy needs rho and molw");
-    HP_REQUIRE(radius >= 0.0, "negative radius");
+    HP_REQUIRE(radius >= 0.0, "negative radius (use +inf for the dense pass)");
     cudaStream_t st = as_stream(stream);
     if (npts == 0) {
         if (entropy_partials) {
@@ -271,11 +364,15 @@ extern "C" int hp_promol_weights_local(int functor, int64_t npts, const double* 
     int64_t cap = int64_t(sm_count()) * 2;
     if (cap > kMaxPartials) cap = kMaxPartials;
     if (grid > cap) grid = cap;
-#define HP_LOC(F)                                                                                        \
-    promol_weights_local_kernel<F><<<int(grid), kLocThreads, 0, st>>>(                                   \
-        npts, px, py, pz, point_base, natom, atom_xyz, atom_point_offsets, atom_shell_offsets, shell_A,  \
+    const bool local = !isinf(radius);
+#define HP_LOC_ARGS                                                                                      \
+    npts, px, py, pz, point_base, natom, atom_xyz, atom_point_offsets, atom_shell_offsets, shell_A,      \
         shell_alpha, shell_order, ntile, tile_atom_offsets, rho, molw, density_cutoff, promol_offset,    \
-        radius, promol, at_weights, entropy_partials, reinterpret_cast<unsigned long long*>(pair_partials))
+        radius, shell_skip, promol, at_weights, entropy_partials,                                        \
+        reinterpret_cast<unsigned long long*>(pair_partials)
+#define HP_LOC(F)                                                                                        \
+    if (local) promol_weights_local_kernel<F, true><<<int(grid), kLocThreads, 0, st>>>(HP_LOC_ARGS);     \
+    else promol_weights_local_kernel<F, false><<<int(grid), kLocThreads, 0, st>>>(HP_LOC_ARGS)
     switch (functor) {
         case HP_FUNCTOR_SLATER: HP_LOC(HP_FUNCTOR_SLATER); break;
         case HP_FUNCTOR_GAUSS: HP_LOC(HP_FUNCTOR_GAUSS); break;
@@ -283,6 +380,7 @@ extern "C" int hp_promol_weights_local(int functor, int64_t npts, const double* 
         default: set_error("hp_promol_weights_local: unsupported functor %d", functor); return HP_ERR_ARG;
     }
 #undef HP_LOC
+#undef HP_LOC_ARGS
     HP_LAUNCH_CHECK("promol_weights_local_kernel");
     return HP_OK;
 }

@@ -122,8 +122,15 @@ HP_API int hp_promol_weights(int functor, int64_t npts, const double* px, const 
  * Grid.get_localgrid), and the owner's weight is 0 outside its own ball -- the semantics of the
  * reference's local-grid design (commented block core/stockholder.py:45-112).  Blocks skip atoms
  * that cannot reach their chunk of points (conservative annulus test around the owner atom) while
- * keeping the atom order.  pair_partials (hp_num_partials() uint64, may be NULL) receives per-block
- * counts of the atom x point pairs actually evaluated. */
+ * keeping the atom order.  radius = +inf gives the dense pass (fused distances, no inclusion test).
+ * pair_partials (hp_num_partials() uint64, may be NULL) receives per-block counts of the
+ * atom x point pairs actually evaluated.
+ * shell_skip (may be NULL; SLATER/GAUSS functors): per-shell thresholds from hp_shell_screen; a shell
+ * is dropped for a chunk of points when the chunk's minimum distance to the atom (r, or r^2 for
+ * Gaussians) exceeds its threshold, i.e. when it is below 2^-nbits of the atom's most diffuse shell
+ * and cannot change the FP64 pro-atom sum. */
+HP_API int hp_shell_screen(int32_t natom, const int32_t* atom_shell_offsets, const double* shell_A,
+                           const double* shell_alpha, double nbits, double* shell_skip, void* stream);
 HP_API int hp_promol_weights_local(int functor, int64_t npts, const double* px, const double* py,
                                    const double* pz, int64_t point_base, int32_t natom,
                                    const double* atom_xyz, const int64_t* atom_point_offsets,
@@ -131,8 +138,8 @@ HP_API int hp_promol_weights_local(int functor, int64_t npts, const double* px, 
                                    const double* shell_alpha, const double* shell_order,
                                    int32_t ntile, const int32_t* tile_atom_offsets,
                                    const double* rho, const double* molw, double density_cutoff,
-                                   double promol_offset, double radius, double* promol,
-                                   double* at_weights, double* entropy_partials,
+                                   double promol_offset, double radius, const double* shell_skip,
+                                   double* promol, double* at_weights, double* entropy_partials,
                                    uint64_t* pair_partials, void* stream);
 
 /* ------------------------------------------------------------------------------------------
