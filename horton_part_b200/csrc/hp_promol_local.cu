@@ -125,7 +125,7 @@ promol_weights_local_kernel(int64_t npts, const double* __restrict__ px, const d
             rmin = s_geom[3];
             rmax = s_geom[4];
         }
-        const double slack = 1e-9 * (1.0 + rmax + radius);
+        const double slack = LOCAL ? 1e-9 * (1.0 + rmax + radius) : 0.0;
 
         for (int t = 0; t < ntile; ++t) {
             const int a0 = tile_off[t], a1 = tile_off[t + 1];
@@ -149,7 +149,8 @@ promol_weights_local_kernel(int64_t npts, const double* __restrict__ px, const d
                     if (same_owner) {
                         const double D = sqrt(dist2_unfused3(rec.x - s_geom[0], rec.y - s_geom[1], rec.z - s_geom[2]));
                         if (LOCAL) cand = (D >= rmin - radius - slack) && (D <= rmax + radius + slack);
-                        const double dmin = fmax(0.0, fmax(D - rmax, rmin - D) - slack);
+                        // conservative lower bound of the chunk's distance to this atom
+                        const double dmin = fmax(0.0, fmax(D - rmax, rmin - D) - 1e-9 * (1.0 + rmax + D));
                         xmin = (F == HP_FUNCTOR_GAUSS) ? dmin * dmin : dmin;
                     }
                     if (cand) {
