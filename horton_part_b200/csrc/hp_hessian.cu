@@ -6,8 +6,9 @@
 //      a point-major scratch panel (row length Mpad = M rounded up to 128), so panel rows are
 //      contiguous and the SYRK loads are fully coalesced;
 //   2. syrk_panel_kernel   C_s += Gu_s^T Gu_s  on 128x128 tiles of the upper triangle, 8x8 register
-//      micro-tiles of FP64 FMAs, the chunk split over `nsplit` sub-panels with one partial matrix
-//      each so that >= 2 blocks per SM are in flight without atomics;
+//      micro-tiles of FP64 FMAs fed by a two-stage cp.async pipeline; the chunk is split over
+//      `nsplit` sub-panels with one partial matrix each, nsplit chosen so that tiles x nsplit fills
+//      whole waves of SMs, without atomics;
 //   3. hessian_finish_kernel  H = sum_s C_s in a fixed order, mirrored to the lower triangle.
 // Every element of every partial matrix is owned by exactly one block, so the result is
 // bit-reproducible.  Bound: FP64 pipe, M(M+1) Npts flop (unit U2); B200 has no
@@ -18,8 +19,8 @@
 namespace hp {
 
 constexpr int kHT = 128;   // tile edge
-constexpr int kHK = 8;     // points per shared-memory step
-constexpr int kHSplit = 4; // sub-panels per chunk (partial matrices)
+constexpr int kHK = 16;        // points per shared-memory slab
+constexpr int kHMaxSplit = 24; // upper bound on sub-panels per chunk (partial matrices)
 
 template <int F>
 __global__ void __launch_bounds__(256)
@@ -64,11 +65,22 @@ basis_chunk_kernel(int64_t p0, int pc, int M, int Mpad, const double* __restrict
     }
 }
 
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+    const unsigned sa = static_cast<unsigned>(__cvta_generic_to_shared(smem_dst));
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(gmem_src));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
+
+// C_s(tile) += Gu_s(:, tile.x)^T Gu_s(:, tile.y): 128x128 tile, 8x8 micro-tiles, the panel streamed
+// through a two-stage cp.async pipeline of kHK-point slabs.
 __global__ void __launch_bounds__(256)
 syrk_panel_kernel(const double* __restrict__ Gu, int Mpad, int pc_sub, const int2* __restrict__ tiles,
                   double* __restrict__ Cpart) {
-    __shared__ __align__(16) double As[kHK][kHT];
-    __shared__ __align__(16) double Bs[kHK][kHT];
+    extern __shared__ __align__(16) double smem_syrk[];  // [2 stages][A|B][kHK][kHT]
+    auto As = [&](int st, int kk) { return smem_syrk + ((st * 2 + 0) * kHK + kk) * kHT; };
+    auto Bs = [&](int st, int kk) { return smem_syrk + ((st * 2 + 1) * kHK + kk) * kHT; };
     const int2 tile = tiles[blockIdx.x];
     const int s = blockIdx.y;
     const double* panel = Gu + int64_t(s) * pc_sub * Mpad;
@@ -80,23 +92,39 @@ syrk_panel_kernel(const double* __restrict__ Gu, int Mpad, int pc_sub, const int
 #pragma unroll
         for (int j = 0; j < 8; ++j) acc[i][j] = 0.0;
 
-    for (int k0 = 0; k0 < pc_sub; k0 += kHK) {
+    // each thread moves (kHK*kHT*2 doubles)/256 threads in 16-byte pieces per slab
+    auto issue = [&](int st, int k0) {
 #pragma unroll
-        for (int j = 0; j < (kHK * kHT) / 256; ++j) {
-            const int idx = threadIdx.x + j * 256;
+        for (int j = 0; j < (kHK * kHT) / (2 * 256); ++j) {
+            const int idx = (threadIdx.x + j * 256) * 2;  // double index within the slab
             const int kk = idx / kHT, mm = idx % kHT;
             const double* src = panel + int64_t(k0 + kk) * Mpad;
-            As[kk][mm] = src[tile.x * kHT + mm];
-            Bs[kk][mm] = src[tile.y * kHT + mm];
+            cp_async16(As(st, kk) + mm, src + tile.x * kHT + mm);
+            cp_async16(Bs(st, kk) + mm, src + tile.y * kHT + mm);
+        }
+        cp_async_commit();
+    };
+
+    const int nslab = pc_sub / kHK;
+    issue(0, 0);
+    for (int sl = 0; sl < nslab; ++sl) {
+        const int st = sl & 1;
+        if (sl + 1 < nslab) {
+            issue(st ^ 1, (sl + 1) * kHK);
+            cp_async_wait<1>();
+        } else {
+            cp_async_wait<0>();
         }
         __syncthreads();
 #pragma unroll
         for (int kk = 0; kk < kHK; ++kk) {
             double a[8], b[8];
+            const double* ar = As(st, kk);
+            const double* br = Bs(st, kk);
 #pragma unroll
             for (int g = 0; g < 4; ++g) {
-                const double2 av = *reinterpret_cast<const double2*>(&As[kk][ty * 2 + 32 * g]);
-                const double2 bv = *reinterpret_cast<const double2*>(&Bs[kk][tx * 2 + 32 * g]);
+                const double2 av = *reinterpret_cast<const double2*>(ar + ty * 2 + 32 * g);
+                const double2 bv = *reinterpret_cast<const double2*>(br + tx * 2 + 32 * g);
                 a[2 * g] = av.x; a[2 * g + 1] = av.y;
                 b[2 * g] = bv.x; b[2 * g + 1] = bv.y;
             }
@@ -105,7 +133,7 @@ syrk_panel_kernel(const double* __restrict__ Gu, int Mpad, int pc_sub, const int
 #pragma unroll
                 for (int j = 0; j < 8; ++j) acc[i][j] = fma(a[i], b[j], acc[i][j]);
         }
-        __syncthreads();
+        __syncthreads();  // slab consumed before it is overwritten two iterations later
     }
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
@@ -136,11 +164,28 @@ hessian_finish_kernel(int M, int Mpad, int nsplit, const double* __restrict__ Cp
 
 static int hessian_mpad(int M) { return ((M + kHT - 1) / kHT) * kHT; }
 
-// points per chunk: bounded panel size (<= 512 MB) and a multiple of kHSplit * kHK
-static int hessian_chunk_points(int Mpad) {
+// Number of sub-panels: the (tiles x splits) grid should fill whole waves of SMs (1 block per SM).
+static int hessian_split(int ntile) {
+    const int sms = sm_count();
+    int best = 2;
+    double best_eff = 0.0;
+    for (int s = 2; s <= kHMaxSplit; ++s) {
+        const int blocks = ntile * s;
+        const int waves = (blocks + sms - 1) / sms;
+        const double eff = double(blocks) / (double(waves) * sms);
+        if (eff > best_eff + 1e-9) {
+            best_eff = eff;
+            best = s;
+        }
+    }
+    return best;
+}
+
+// points per chunk: bounded panel size (<= 512 MB) and a multiple of nsplit * kHK
+static int hessian_chunk_points(int Mpad, int nsplit) {
     int64_t pc = (int64_t(512) << 20) / (int64_t(Mpad) * 8);
     if (pc > 65536) pc = 65536;
-    const int q = kHSplit * kHK;
+    const int q = nsplit * kHK;
     pc = (pc / q) * q;
     return int(pc < q ? q : pc);
 }
@@ -152,8 +197,9 @@ using namespace hp;
 extern "C" size_t hp_hessian_scratch_bytes(int32_t M) {
     const int Mpad = hessian_mpad(M);
     const int nt = Mpad / kHT;
-    const size_t panel = size_t(hessian_chunk_points(Mpad)) * Mpad * sizeof(double);
-    const size_t parts = size_t(kHSplit) * Mpad * Mpad * sizeof(double);
+    const int nsplit = hessian_split(nt * (nt + 1) / 2);
+    const size_t panel = size_t(hessian_chunk_points(Mpad, nsplit)) * Mpad * sizeof(double);
+    const size_t parts = size_t(nsplit) * Mpad * Mpad * sizeof(double);
     const size_t tiles = size_t(nt) * (nt + 1) / 2 * sizeof(int2);
     return panel + parts + ((tiles + 255) / 256) * 256;
 }
@@ -171,10 +217,17 @@ extern "C" int hp_hessian(int functor, int64_t npts, const double* px, const dou
     HP_REQUIRE(scratch_bytes >= hp_hessian_scratch_bytes(M), "scratch too small");
     cudaStream_t st = as_stream(stream);
     const int Mpad = hessian_mpad(M), nt = Mpad / kHT, ntile = nt * (nt + 1) / 2;
-    const int pc = hessian_chunk_points(Mpad), pc_sub = pc / kHSplit;
+    const int nsplit = hessian_split(ntile);
+    const int pc = hessian_chunk_points(Mpad, nsplit), pc_sub = pc / nsplit;
     double* panel = static_cast<double*>(scratch);
     double* parts = panel + size_t(pc) * Mpad;
-    int2* tiles = reinterpret_cast<int2*>(parts + size_t(kHSplit) * Mpad * Mpad);
+    int2* tiles = reinterpret_cast<int2*>(parts + size_t(nsplit) * Mpad * Mpad);
+    const size_t syrk_smem = sizeof(double) * 2 * 2 * kHK * kHT;
+    {
+        int rc0 = check_cuda(cudaFuncSetAttribute(syrk_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                  int(syrk_smem)), "cudaFuncSetAttribute");
+        if (rc0) return rc0;
+    }
     // tile list (upper triangle), built on the host
     int2* host_tiles = new int2[ntile];
     int k = 0;
@@ -185,7 +238,7 @@ extern "C" int hp_hessian(int functor, int64_t npts, const double* px, const dou
     if (rc == HP_OK) rc = check_cuda(cudaStreamSynchronize(st), "tile list sync");
     delete[] host_tiles;
     if (rc) return rc;
-    rc = check_cuda(cudaMemsetAsync(parts, 0, sizeof(double) * kHSplit * size_t(Mpad) * Mpad, st), "memset");
+    rc = check_cuda(cudaMemsetAsync(parts, 0, sizeof(double) * nsplit * size_t(Mpad) * Mpad, st), "memset");
     if (rc) return rc;
     for (int64_t p0 = 0; p0 < npts; p0 += pc) {
         switch (functor) {
@@ -209,11 +262,11 @@ extern "C" int hp_hessian(int functor, int64_t npts, const double* px, const dou
                 return HP_ERR_ARG;
         }
         HP_LAUNCH_CHECK("basis_chunk_kernel");
-        syrk_panel_kernel<<<dim3(ntile, kHSplit), 256, 0, st>>>(panel, Mpad, pc_sub, tiles, parts);
+        syrk_panel_kernel<<<dim3(ntile, nsplit), 256, syrk_smem, st>>>(panel, Mpad, pc_sub, tiles, parts);
         HP_LAUNCH_CHECK("syrk_panel_kernel");
     }
     const int64_t total = int64_t(M) * M;
-    hessian_finish_kernel<<<int((total + 255) / 256), 256, 0, st>>>(M, Mpad, kHSplit, parts, H);
+    hessian_finish_kernel<<<int((total + 255) / 256), 256, 0, st>>>(M, Mpad, nsplit, parts, H);
     HP_LAUNCH_CHECK("hessian_finish_kernel");
     return HP_OK;
 }

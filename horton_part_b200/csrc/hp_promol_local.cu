@@ -129,7 +129,6 @@ promol_weights_local_kernel(int64_t npts, const double* __restrict__ px, const d
 
         for (int t = 0; t < ntile; ++t) {
             const int a0 = tile_off[t], a1 = tile_off[t + 1];
-            const int sh0 = atom_sh_off[a0], sh1 = atom_sh_off[a1];
             __syncthreads();  // previous tile fully consumed
             // ---- ordered compaction of the atoms that can reach this chunk -----------------------
             AtomRec rec;
