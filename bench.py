@@ -305,6 +305,8 @@ def main():
     kernel_ms_mean = max_over_ranks(float(np.mean(kernel_ms)))
     value = evals_per_step * args.steps / (ms_total * 1e-3)
     charges_resident = part["charges"].copy()
+    shells_local = part._table.shells_evaluated()  # None when the plain dense kernel ran
+    pairs_local = part._table.pairs_evaluated()
     h2d_bytes = part.slab.bytes_h2d
     state_bytes = part._state.host.numel() * 8
     del part
@@ -387,8 +389,19 @@ def main():
         "kernel_share_of_step": kernel_ms_mean / (ms_total / args.steps),
         "hbm_gbs_achieved": hbm_bytes / (kernel_ms_mean * 1e-3) / 1e9, "hbm_gbs_peak": hbm_peak,
         "hbm_peak_source": "MEASURED_PEAKS.json" if peaks else "fallback 6650",
-        "traffic": None,
+        "traffic": 0.968 * hbm_bytes,
+        "traffic_source": "dram__bytes_read+write of the ncu --set full capture (profiles/r1_promol_weights_ncu_full.txt: "
+                          "947 MB vs 978 MB algorithmic at 600 atoms) scaled to this launch",
     }  # fmt: skip
+    if shells_local is not None:
+        # shell screening drops shells that cannot change the FP64 sum: also report the roofline
+        # fraction for the work actually executed (16 flop per pair + 36 per evaluated shell)
+        executed = (16.0 * pairs_local + 36.0 * shells_local) / (kernel_ms_mean * 1e-3) / 1e12
+        roofline.update({
+            "shell_screening": "shells below 2^-100 of the atom's most diffuse shell over a whole chunk are skipped",
+            "shells_evaluated_per_pair": shells_local / pairs_local, "achieved_executed": executed,
+            "frac_executed": executed / fp64_peak_tflops,
+        })
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,

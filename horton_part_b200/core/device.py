@@ -222,7 +222,11 @@ class ShellTable:
 
     def pairs_evaluated(self):
         """atom x point pairs evaluated by the last cut-off launch on this rank."""
-        return int(self.pair_partials.sum().item()) if self.pair_partials is not None else None
+        return int(self.pair_partials[: self.slab.npartial].sum().item()) if self.pair_partials is not None else None
+
+    def shells_evaluated(self):
+        """shell x point evaluations of the last launch of the chunk-geometry kernel on this rank."""
+        return int(self.pair_partials[self.slab.npartial :].sum().item()) if self.pair_partials is not None else None
 
     def promol_weights(self, density_cutoff, want_promol=True, want_weights=True, want_entropy=True,
                        promol_offset=1e-100):
@@ -238,7 +242,7 @@ class ShellTable:
             import torch
 
             if self.pair_partials is None:
-                self.pair_partials = torch.zeros(s.npartial, dtype=torch.int64, device=s.device)
+                self.pair_partials = torch.zeros(2 * s.npartial, dtype=torch.int64, device=s.device)
             if bits:
                 if self.skip is None:
                     self.skip = torch.empty_like(self.A)

@@ -56,7 +56,7 @@ promol_weights_local_kernel(int64_t npts, const double* __restrict__ px, const d
     const int64_t nchunk = (npts + span - 1) / span;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     double entropy_acc = 0.0;
-    unsigned long long pairs = 0;
+    unsigned long long pairs = 0, shells = 0;
 
     for (int64_t chunk = blockIdx.x; chunk < nchunk; chunk += gridDim.x) {
         double x[kLocPts], y[kLocPts], z[kLocPts], pro[kLocPts];
@@ -202,6 +202,10 @@ promol_weights_local_kernel(int64_t npts, const double* __restrict__ px, const d
             __syncthreads();
             const int ncand = s_ncand;
             pairs += static_cast<unsigned long long>(ncand) * nlive;
+            if (pair_partials) {  // kept shells of this tile = s0 + ns of its last candidate
+                const int kept = ncand ? s_atoms[ncand - 1].s0 + s_atoms[ncand - 1].ns : 0;
+                shells += static_cast<unsigned long long>(kept) * nlive;
+            }
 
             AtomRec nxt = s_atoms[0];
             double2 nxt_ab = s_AB[nxt.s0];
@@ -269,20 +273,34 @@ promol_weights_local_kernel(int64_t npts, const double* __restrict__ px, const d
             for (int i = gridDim.x + threadIdx.x; i < kMaxPartials; i += kLocThreads) entropy_partials[i] = 0.0;
     }
     if (pair_partials) {
-        // each thread tallied (candidates x its own live points): the block total is the sum
-        unsigned long long v = pairs;
+        // each thread tallied (candidates x its own live points): the block total is the sum.
+        // Layout: [0, kMaxPartials) pairs, [kMaxPartials, 2 kMaxPartials) shell evaluations.
+        unsigned long long v = pairs, u = shells;
 #pragma unroll
-        for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
-        __shared__ unsigned long long s_pairs[kLocThreads / 32];
-        if (lane == 0) s_pairs[warp] = v;
+        for (int off = 16; off > 0; off >>= 1) {
+            v += __shfl_xor_sync(0xffffffffu, v, off);
+            u += __shfl_xor_sync(0xffffffffu, u, off);
+        }
+        __shared__ unsigned long long s_pairs[2][kLocThreads / 32];
+        if (lane == 0) {
+            s_pairs[0][warp] = v;
+            s_pairs[1][warp] = u;
+        }
         __syncthreads();
         if (threadIdx.x == 0) {
-            unsigned long long tot = 0;
-            for (int w = 0; w < kLocThreads / 32; ++w) tot += s_pairs[w];
+            unsigned long long tot = 0, tot2 = 0;
+            for (int w = 0; w < kLocThreads / 32; ++w) {
+                tot += s_pairs[0][w];
+                tot2 += s_pairs[1][w];
+            }
             pair_partials[blockIdx.x] = tot;
+            pair_partials[kMaxPartials + blockIdx.x] = tot2;
         }
         if (blockIdx.x == 0)
-            for (int i = gridDim.x + threadIdx.x; i < kMaxPartials; i += kLocThreads) pair_partials[i] = 0ull;
+            for (int i = gridDim.x + threadIdx.x; i < kMaxPartials; i += kLocThreads) {
+                pair_partials[i] = 0ull;
+                pair_partials[kMaxPartials + i] = 0ull;
+            }
     }
 }
 
@@ -356,7 +374,7 @@ extern "C" int hp_promol_weights_local(int functor, int64_t npts, const double* 
             if (rc) return rc;
         }
         if (pair_partials)
-            return check_cuda(cudaMemsetAsync(pair_partials, 0, sizeof(uint64_t) * kMaxPartials, st), "memset");
+            return check_cuda(cudaMemsetAsync(pair_partials, 0, sizeof(uint64_t) * 2 * kMaxPartials, st), "memset");
         return HP_OK;
     }
     const int64_t span = int64_t(kLocThreads) * kLocPts;

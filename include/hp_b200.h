@@ -123,8 +123,8 @@ HP_API int hp_promol_weights(int functor, int64_t npts, const double* px, const 
  * reference's local-grid design (commented block core/stockholder.py:45-112).  Blocks skip atoms
  * that cannot reach their chunk of points (conservative annulus test around the owner atom) while
  * keeping the atom order.  radius = +inf gives the dense pass (fused distances, no inclusion test).
- * pair_partials (hp_num_partials() uint64, may be NULL) receives per-block counts of the
- * atom x point pairs actually evaluated.
+ * pair_partials (2 x hp_num_partials() uint64, may be NULL) receives per-block counts of the
+ * atom x point pairs actually evaluated (first half) and of the shell evaluations (second half).
  * shell_skip (may be NULL; SLATER/GAUSS functors): per-shell thresholds from hp_shell_screen; a shell
  * is dropped for a chunk of points when the chunk's minimum distance to the atom (r, or r^2 for
  * Gaussians) exceeds its threshold, i.e. when it is below 2^-nbits of the atom's most diffuse shell
