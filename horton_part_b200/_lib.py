@@ -89,6 +89,7 @@ EXPORTS = {
     "hp_sum_partials": (_int, [_i32, _p, _p, _p]),
     "hp_segment_integrate": (_int, [_i32, _p, _p, _p, _p, _p, _p]),
     "hp_atom_moments": (_int, [_i32, _i32, _i32, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
+    "hp_becke_weights": (_int, [_i64, _p, _p, _p, _i64, _i32, _p, _p, _p, _p, _i32, _p, _p]),
     "hp_dfma_probe": (_int, [_i32, _p, _p, _p, _p]),
 }
 

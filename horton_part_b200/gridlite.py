@@ -30,6 +30,7 @@ __all__ = [
     "AtomGrid",
     "MolGrid",
     "BeckeWeights",
+    "DeviceBeckeWeights",
     "lebedev_size_to_degree",
     "LEBEDEV_DEGREES",
 ]
@@ -246,6 +247,48 @@ class BeckeWeights:
                 s[np.isnan(s)] = 1.0
                 cell = s.prod(axis=-1)
                 out[lo:hi] = cell[:, owner] / cell.sum(axis=-1)
+        return out
+
+
+class DeviceBeckeWeights(BeckeWeights):
+    """Becke weights computed by the CUDA kernel ``hp_becke_weights`` (same formula as
+    :class:`BeckeWeights`; one thread per point, negligible cells pruned against the nearest atom).
+    Use as the ``aim_weights`` callable of :class:`MolGrid` for systems where the O(natom^2 Npts)
+    NumPy version is out of reach."""
+
+    def __init__(self, radii=None, order=3, device=None, chunk=1 << 24):
+        super().__init__(radii, order)
+        self._device, self._chunk = device, chunk
+
+    def __call__(self, points, atcoords, atnums, pt_ind):
+        import torch
+
+        from . import _lib
+        from .core.device import require_cuda, stream_ptr, to_device
+
+        dev = require_cuda(self._device)
+        atcoords = np.ascontiguousarray(atcoords, dtype=np.float64)
+        natom = len(atnums)
+        R = np.array([self._radii[int(z)] for z in atnums])
+        chi = R[:, None] / R[None, :]
+        u = (chi - 1) / (chi + 1)
+        aab = np.clip(u / (u * u - 1), -0.45, 0.45)
+        rab = np.sqrt(((atcoords[:, None, :] - atcoords[None, :, :]) ** 2).sum(-1))
+        with np.errstate(divide="ignore"):
+            inv_rab = 1.0 / rab
+        d_inv, d_aab = to_device(inv_rab, dev), to_device(aab, dev)
+        d_xyz = to_device(atcoords, dev)
+        d_off = to_device(np.asarray(pt_ind, dtype=np.int64), dev)
+        out = np.empty(len(points))
+        for lo in range(0, len(points), self._chunk):
+            hi = min(lo + self._chunk, len(points))
+            n = hi - lo
+            aos = to_device(points[lo:hi], dev, np.float64)
+            px, py, pz, w = (torch.empty(n, dtype=torch.float64, device=dev) for _ in range(4))
+            _lib.call("hp_split_points", aos, n, px, py, pz, stream_ptr(dev))
+            _lib.call("hp_becke_weights", n, px, py, pz, lo, natom, d_xyz, d_off, d_inv, d_aab,
+                      int(self._order), w, stream_ptr(dev))  # fmt: skip
+            out[lo:hi] = w.cpu().numpy()
         return out
 
 

@@ -317,6 +317,15 @@ HP_API int hp_atom_moments(int32_t natom, int32_t atom_base, int32_t lmax, const
                            const double* atgrid_w, const double* at_weights, const double* dens,
                            const double* atom_xyz, double* out, void* stream);
 
+/* (section 8f-2) Becke fuzzy-cell weight of the OWNER atom at each local grid point, replacing qc-grid's
+ * BeckeWeights.__call__ (call sites scripts/generate_density.py:102-111, becke.py:107-116).
+ * inv_rab[a][b] = 1/|R_a-R_b| and aab[a][b] = size-adjustment parameter (clipped to +-0.45), both
+ * natom x natom row-major, diagonal ignored; `order` = number of switching-polynomial iterations. */
+HP_API int hp_becke_weights(int64_t npts, const double* px, const double* py, const double* pz,
+                            int64_t point_base, int32_t natom, const double* atom_xyz,
+                            const int64_t* atom_point_offsets, const double* inv_rab, const double* aab,
+                            int32_t order, double* out, void* stream);
+
 /* FP64 FMA throughput probe used by bench.py for the roofline denominator: runs `iters` dependent
  * DFMA chains (8 independent per thread) on a full grid; returns elapsed ms in *ms_host and the
  * flop count in *flops_host.  Synchronises the stream. */
