@@ -381,7 +381,8 @@ def main():
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     hbm_bytes = 56.0 * (hi - lo)  # 40 B read (x,y,z,rho,molw) + 16 B written (promol, at_w) per point
     roofline = {
-        "bound": "fp64", "kernel": "promol_weights_kernel<SLATER>",
+        "bound": "fp64",
+        "kernel": "promol_weights_local_kernel<SLATER,dense>" if shells_local is not None else "promol_weights_kernel<SLATER>",
         "achieved": achieved_tflops, "peak": fp64_peak_tflops, "unit": "TFLOP/s",
         "frac": achieved_tflops / fp64_peak_tflops,
         "peak_source": "hp_dfma_probe measured live on this GPU (nominal 148 SM x 64 lanes x 2 x 1.965 GHz = 37.2)",
