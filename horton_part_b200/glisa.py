@@ -109,10 +109,9 @@ class GlobalLinearISAWPart(AbstractStockholderWPart):
 
         from .core.device import ShellTable, to_device
 
-        if self.on_molgrid:
-            raise NotImplementedError("gLISA with grid_type 2/3 (molecular-grid change) is not built yet")
         propars = gisa.init_propars(self)
-        gisa.evaluate_basis_functions(self)  # radial grids only: used by compute_change
+        if not self.on_molgrid:
+            gisa.evaluate_basis_functions(self)  # radial grids only: used by compute_change
         slab = self.slab
         dev = slab.device
         orders = np.concatenate([np.asarray(self.bs_helper.get_order(z), float) for z in self.numbers])
@@ -126,10 +125,11 @@ class GlobalLinearISAWPart(AbstractStockholderWPart):
         self._c = to_device(propars, dev)
         self._par_offsets = to_device(np.asarray(self._ranges, dtype=np.int32), dev)
         sh = slab.shard
-        blocks = [self.cache.load(f"bs_funcs_{a}") for a in range(sh.atom_lo, sh.atom_hi)]
-        offs = np.concatenate([[0], np.cumsum([b.size for b in blocks])]).astype(np.int64)
-        self._bs_offsets = to_device(offs, dev)
-        self._bs_flat = to_device(np.concatenate([b.ravel() for b in blocks]), dev)
+        if not self.on_molgrid:
+            blocks = [self.cache.load(f"bs_funcs_{a}") for a in range(sh.atom_lo, sh.atom_hi)]
+            offs = np.concatenate([[0], np.cumsum([b.size for b in blocks])]).astype(np.int64)
+            self._bs_offsets = to_device(offs, dev)
+            self._bs_flat = to_device(np.concatenate([b.ravel() for b in blocks]), dev)
         M = len(propars)
         nblk = int(_lib.call("hp_molgrid_num_blocks", slab.npts))
         self._partial = torch.zeros(nblk * max(M, self.natom), dtype=torch.float64, device=dev)
@@ -178,6 +178,31 @@ class GlobalLinearISAWPart(AbstractStockholderWPart):
 
         s = self.slab
         sh = s.shard
+        if self.on_molgrid:
+            # compute_change on the molecular grid (core/iterstock.py:40-41): the `chg` column of
+            # the update pass with in = new and prev = old coefficients
+            import torch
+
+            t = self._table
+            if getattr(self, "_mg", None) is None:
+                lim_a, lim_s = np.zeros(1, np.int32), np.zeros(1, np.int32)
+                _lib.call("hp_molgrid_update_tile_limits", lim_a, lim_s)
+                ntile, tiles = t.make_tiles(int(lim_a[0]), int(lim_s[0]))
+                nout = 2 * t.nshell + 2 * self.natom
+                nblk = int(_lib.call("hp_molgrid_num_blocks", s.npts))
+                self._mg = dict(ntile=ntile, tiles=tiles,
+                                partial=torch.zeros(nblk * nout, dtype=torch.float64, device=s.device),
+                                out=torch.zeros(nout, dtype=torch.float64, device=s.device))  # fmt: skip
+            mg = self._mg
+            a_new, a_old = c_new * self._norms, c_old * self._norms
+            _lib.call(
+                "hp_molgrid_update_pass", t.functor, s.npts, s.px, s.py, s.pz, s.natom, s.atom_xyz, t.offsets,
+                a_old, t.alpha, a_new, t.alpha, a_old, t.alpha, t.order, None, mg["ntile"], mg["tiles"], s.rho,
+                s.molw, s.promol, float(self.density_cutoff), t.nshell, mg["partial"], mg["out"],
+                stream_ptr(s.device),
+            )  # fmt: skip
+            self._msd.copy_(mg["out"][2 * t.nshell :: 2])
+            return self._msd
         self._msd.zero_()
         _lib.call("hp_radial_change", sh.nlocal, sh.atom_lo, s.rad_offsets, s.rad_w4, self._par_offsets,
                   self._bs_offsets, self._bs_flat, c_new, c_old, self._msd, stream_ptr(s.device))  # fmt: skip

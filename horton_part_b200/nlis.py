@@ -98,8 +98,6 @@ class NLISWPart(AbstractISAWPart):
     def _init_propars(self):
         from .core.device import ShellTable, to_device
 
-        if self.on_molgrid:
-            raise NotImplementedError(f"{self.name} with grid_type 2/3 is not built yet")
         self._nshells = [self._atom_nshell(z) for z in self.numbers]
         if max(self._nshells) > 7:
             raise ValueError("more than 7 shells per atom are not supported")
@@ -126,6 +124,28 @@ class NLISWPart(AbstractISAWPart):
         _lib.call("hp_table_nlis", t.nshell, self._state.propars, self._inv_gamma, t.A, t.alpha, t.order,
                   stream_ptr(self.slab.device))  # fmt: skip
 
+    def _molgrid_shell_params(self, propars):
+        import torch
+
+        from .core.device import stream_ptr
+
+        n = self._table.nshell
+        A, alpha, order = (torch.empty(n, dtype=torch.float64, device=propars.device) for _ in range(3))
+        _lib.call("hp_table_nlis", n, propars, self._inv_gamma, A, alpha, order, stream_ptr(self.slab.device))
+        return A, alpha
+
+    def _molgrid_apply(self, propars, s0, s1, shell_active):
+        """nlis.py:160-176 on the molecular grid: N <- m0, S <- 3/(m1 n) (1e-5 if m1 ~ 0), where the
+        kernel's sums are S0 = m0 and S1 = N_old * m1."""
+        import torch
+
+        new = propars.clone().view(-1, 3)
+        m1 = s1 / new[:, 0]
+        s_new = torch.where(m1.abs() <= 1e-8, torch.full_like(m1, 1e-5), 3.0 / (m1 * new[:, 2]))
+        new[:, 1] = torch.where(shell_active, s_new, new[:, 1])
+        new[:, 0] = torch.where(shell_active, s0, new[:, 0])
+        return new.view(-1)
+
     def _launch_radial_update(self):
         from .core.device import stream_ptr
 
@@ -142,7 +162,7 @@ class NLISWPart(AbstractISAWPart):
     def _finalize_propars(self):
         AbstractISAWPart._finalize_propars(self)
         flags = self._state.flags.cpu().numpy()
-        if (flags & 1).any():
+        if (flags & 1).any() or getattr(self, "_molgrid_not_converged", False):
             self.logger.warning("NLIS not converged, but still go ahead!")
         if (flags & 2).any():
             self.logger.warning("The sum of propars are not equal to the atomic pop.")
@@ -153,6 +173,8 @@ class NLISWPart(AbstractISAWPart):
         self.cache.dump("core_charges", self._cache.load("charges") - valence_charges, tags="o")
         self.cache.dump("valence_charges", valence_charges, tags="o")
         self.cache.dump("valence_widths", valence_widths, tags="o")
+        if self.on_molgrid:
+            return
         slab = self.slab
         sph = slab.sph_avg.cpu().numpy()
         ro = slab.rad_offsets_host

@@ -86,6 +86,8 @@ H2O_SCHEMES = {
     "glisa_sc": ("glisa", dict(solver="sc")),
     "mbis_gt2": ("mbis", dict(grid_type=2)),
     "lisa_sc_gt2": ("lisa", dict(solver="sc", grid_type=2)),
+    "nlis_gt2": ("nlis", dict(exp_n_dict={}, grid_type=2)),
+    "glisa_sc_gt2": ("glisa", dict(solver="sc", grid_type=2)),
 }
 
 

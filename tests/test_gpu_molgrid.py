@@ -50,3 +50,21 @@ def test_mbis_grid_type_3_equals_2(water6):
     p3.do_partitioning()
     np.testing.assert_allclose(p3["charges"], p2["charges"], rtol=0, atol=1e-13)
     np.testing.assert_allclose(p3["history_changes"], p2["history_changes"], rtol=1e-12)
+
+
+def test_nlis_grid_type_2_h2o(h2o):
+    from horton_part_b200 import NLISWPart
+
+    part = NLISWPart(h2o["coords"], h2o["numbers"], h2o["pseudo"], h2o["grid"], h2o["rho"], exp_n_dict={},
+                     grid_type=2)
+    part.do_partitioning()
+    _compare(part, _gold(h2o["gold"], "nlis_gt2"))
+
+
+def test_glisa_sc_grid_type_2_h2o(h2o):
+    from horton_part_b200 import GlobalLinearISAWPart
+
+    part = GlobalLinearISAWPart(h2o["coords"], h2o["numbers"], h2o["pseudo"], h2o["grid"], h2o["rho"],
+                                solver="sc", grid_type=2)
+    part.do_partitioning()
+    _compare(part, _gold(h2o["gold"], "glisa_sc_gt2"), ptol=1e-5)
