@@ -75,6 +75,7 @@ EXPORTS = {
         [_int, _i64, _p, _p, _p, _i32, _p, _p, _p, _p, _p, _i32, _p, _p, _p, _p, _p, _p, _p],
     ),
     "hp_radial_change": (_int, [_i32, _i32, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
+    "hp_radial_valid": (_int, [_i32, _i32, _p, _p, _p, _p, _p, _i32, _i32, _f64, _i32, _p, _p]),
     "hp_molgrid_update_tile_limits": (None, [_p, _p]),
     "hp_molgrid_update_pass": (
         _int,

@@ -9,9 +9,11 @@ as CUDA kernels (one warp per atom, all atoms in one launch):
 A callable ``solver`` keeps the reference's plug-in signature
 ``solver(bs_funcs, rho, propars, points, weights, threshold, logger, density_cutoff=...,
 negative_cutoff=..., population_cutoff=..., **solver_options)`` (alisa.py:1304-1335) and runs on the
-host on the projected radial densities.  The remaining built-in names of the reference ("cvxopt",
-"diis", "newton", ...) are small dense host solvers around third-party packages and are not part
-of the accelerated path; requesting them raises NotImplementedError.
+host on the projected radial densities (natom x nrad doubles come back from the device per outer
+iteration).  The remaining built-in names of the reference ("diis", "cdiis", "newton", "m-newton",
+"quasi-newton", "trust-region", "cvxopt", "sc-plus-convex") are shipped as exactly such plug-ins
+(``lisa_solvers.py``): small dense algebra per atom on K x nrad arrays, while promolecule, weights
+and projection stay in the CUDA kernels.
 """
 
 from __future__ import annotations
@@ -22,8 +24,21 @@ from . import _lib
 from .core.basis import AnalyticBasisFuncHelper, ExpBasisFuncHelper
 from .core.logging import deflist
 from .gisa import GaussianISAWPart
+from .lisa_solvers import (  # noqa: F401  (re-exported like the reference's alisa module)
+    HOST_SOLVERS,
+    solver_cdiis,
+    solver_cvxopt,
+    solver_diis,
+    solver_m_newton,
+    solver_newton,
+    solver_quasi_newton,
+    solver_sc,
+    solver_sc_1_iter,
+    solver_sc_plus_cvxopt,
+    solver_trust_region,
+)
 
-__all__ = ["LinearISAWPart", "setup_bs_helper"]
+__all__ = ["LinearISAWPart", "setup_bs_helper"] + [f.__name__ for f in HOST_SOLVERS.values()] + ["solver_sc", "solver_sc_1_iter"]
 
 
 def setup_bs_helper(part):
@@ -52,8 +67,9 @@ class LinearISAWPart(GaussianISAWPart):
     name = "lisa"
     # name -> (max inner iterations option, single update?)
     device_solvers = {"sc": ("max_niter_inner", False), "sc-1-iter": (None, True)}
-    reference_solvers = ("cvxopt", "sc", "diis", "newton", "m-newton", "quasi-newton", "trust-region",
-                         "sc-1-iter", "sc-plus-convex", "cdiis")  # fmt: skip
+    #: every built-in name of the reference (alisa.py:1168-1203); those not in device_solvers run
+    #: as host plug-ins on the projected radial problem
+    builtin_solvers = {"sc": solver_sc, "sc-1-iter": solver_sc_1_iter, **HOST_SOLVERS}
 
     def __init__(self, coordinates, numbers, pseudo_numbers, grid, moldens, spindens=None, lmax=3,
                  logger=None, threshold=1e-6, maxiter=500, inner_threshold=1e-8,
@@ -107,14 +123,13 @@ class LinearISAWPart(GaussianISAWPart):
         )  # fmt: skip
 
     def _opt_propars(self, bs_funcs, rho, propars, points, weights, alphas, threshold):
-        if not callable(self._solver):
-            if self._solver in self.reference_solvers:
-                raise NotImplementedError(
-                    f"aLISA solver {self._solver!r} is a host-side solver of the reference that is outside "
-                    "the accelerated path; use 'sc', 'sc-1-iter' or pass a callable"
-                )
+        if callable(self._solver):
+            solver = self._solver
+        elif self._solver in self.builtin_solvers:
+            solver = self.builtin_solvers[self._solver]
+        else:
             raise NotImplementedError
-        return self._solver(
+        return solver(
             bs_funcs, rho, propars, points, weights, threshold, self.logger,
             density_cutoff=self.density_cutoff, negative_cutoff=self.negative_cutoff,
             population_cutoff=self.population_cutoff, **self._solver_options,

@@ -328,6 +328,39 @@ radial_change_kernel(int natom, int atom_base, const int* __restrict__ rad_off,
     if (lane == 0) msd[a] = dev;
 }
 
+// Line-search admissibility of candidate coefficient vectors (glisa.py:283-307 is_promol_valid /
+// is_proatom_valid on the radial grids): for candidate j and atom a
+//   flag = 1 if any rho0_a(r_i) < negative_cutoff, else
+//   flag = 2 if check_mono and any rho0_a(r_i) - rho0_a(r_{i+1}) < negative_cutoff, else 0.
+// grid = (local atoms, candidates), one warp each; candidates are rows of `cand` (ncand x npar).
+__global__ void __launch_bounds__(32)
+radial_valid_kernel(int natom, int atom_base, const int* __restrict__ rad_off,
+                    const int* __restrict__ par_off, const int64_t* __restrict__ bs_off,
+                    const double* __restrict__ bs, const double* __restrict__ cand, int npar,
+                    double negative_cutoff, int check_mono, int* __restrict__ flags) {
+    if (int(blockIdx.x) >= natom) return;
+    const int a = atom_base + blockIdx.x, lane = threadIdx.x, j = blockIdx.y;
+    const int r0 = rad_off[blockIdx.x], nrad = rad_off[blockIdx.x + 1] - r0;
+    const int p0 = par_off[a], K = par_off[a + 1] - p0;
+    const double* g = bs + bs_off[blockIdx.x];
+    const double* c = cand + int64_t(j) * npar + p0;
+    bool negative = false, rising = false;
+    // lane handles i = lane, lane+32, ...; the value at i+1 is recomputed (K is small)
+    for (int i = lane; i < nrad; i += 32) {
+        double y = 0.0, ynext = 0.0;
+        const bool has_next = i + 1 < nrad;
+        for (int k = 0; k < K; ++k) {
+            y += c[k] * g[k * nrad + i];
+            if (has_next) ynext += c[k] * g[k * nrad + i + 1];
+        }
+        negative |= y < negative_cutoff;
+        if (has_next) rising |= (y - ynext) < negative_cutoff;
+    }
+    negative = __any_sync(0xffffffffu, negative);
+    rising = __any_sync(0xffffffffu, rising);
+    if (lane == 0) flags[int64_t(j) * natom + blockIdx.x] = negative ? 1 : ((check_mono && rising) ? 2 : 0);
+}
+
 template <int F, int MODE, int kP>
 static int launch_molgrid(int64_t npts, const double* px, const double* py, const double* pz,
                           int natom, const double* atom_xyz, const int* atom_sh_off,
@@ -434,6 +467,22 @@ extern "C" int hp_radial_change(int32_t natom, int32_t atom_base, const int32_t*
                                                               par_offsets, bs_offsets, bs_funcs, c_new,
                                                               c_old, msd);
     HP_LAUNCH_CHECK("radial_change_kernel");
+    return HP_OK;
+}
+
+extern "C" int hp_radial_valid(int32_t natom, int32_t atom_base, const int32_t* rad_offsets,
+                               const int32_t* par_offsets, const int64_t* bs_offsets,
+                               const double* bs_funcs, const double* candidates, int32_t ncand,
+                               int32_t npar, double negative_cutoff, int32_t check_mono, int32_t* flags,
+                               void* stream) {
+    HP_REQUIRE(natom >= 0 && ncand >= 0 && npar > 0, "bad sizes");
+    if (natom == 0 || ncand == 0) return HP_OK;
+    HP_REQUIRE(ncand <= 65535, "too many candidates");
+    HP_REQUIRE(rad_offsets && par_offsets && bs_offsets && bs_funcs && candidates && flags, "null input");
+    radial_valid_kernel<<<dim3(natom, ncand), 32, 0, as_stream(stream)>>>(
+        natom, atom_base, rad_offsets, par_offsets, bs_offsets, bs_funcs, candidates, npar, negative_cutoff,
+        check_mono, flags);
+    HP_LAUNCH_CHECK("radial_valid_kernel");
     return HP_OK;
 }
 

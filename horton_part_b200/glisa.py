@@ -11,8 +11,16 @@ the kernels:
     Hessian                -> hp_hessian                        H_mn = int rho g_m g_n / rho0^2
     final charges          -> hp_atom_weight_integrals          (no natom x Npts weight arrays)
 
-Solvers on the device: ``"sc"`` (glisa.py:805-848) and ``"newton"`` (exact Newton, :572-574,
-:617-803 with mode="exact"; the M x M linear solve stays on the host as in the reference).
+Solvers (every O(Npts) pass is a kernel; the host holds vectors of length M and M x M matrices):
+
+    "sc"                            fixed point c <- g(c)                       glisa.py:805-848
+    "newton" / "m-newton" / "quasi-newton"   exact / back-tracking / BFGS       glisa.py:572-803
+                                    (M x M solve on the host as in the reference, line-search
+                                    admissibility of all step lengths in one hp_radial_valid launch)
+    "diis" / "cdiis"                Anderson-Pulay acceleration of g            glisa.py:883-925, 993-1028
+    "trust-region"                  SciPy trust-constr on (f, grad) from the device   glisa.py:927-987
+
+The third-party convex solver ("cvxopt", glisa.py:488-570) is not in this image.
 """
 
 from __future__ import annotations
@@ -22,11 +30,13 @@ import time
 import numpy as np
 
 from . import _lib, gisa
+from .algo import bfgs, cdiis, diis
 from .alisa import setup_bs_helper
-from .core.basis import shell_norm
+from .core.basis import ExpBasisFuncHelper, shell_norm
 from .core.cache import just_once
 from .core.stockholder import AbstractStockholderWPart
 from .core.logging import deflist
+from .utils import check_pro_atom_parameters, fix_propars
 
 __all__ = ["GlobalLinearISAWPart"]
 
@@ -283,43 +293,187 @@ class GlobalLinearISAWPart(AbstractStockholderWPart):
         )  # fmt: skip
         return self._hess
 
-    def solver_newton(self, maxiter=100):
-        """Exact Newton (glisa.py:572-574 -> _solver_general_newton mode="exact", :617-803):
-        delta = solve(H, -1 - grad) on the host, full step, change on the radial grids."""
+    def _objective(self, x=None, nderiv=1):
+        """(f, grad[, hess]) of  f(c) = int rho ln(rho/rho0[c])  (glisa.py:411-479) from the device;
+        x=None evaluates at the coefficients already in self._c.  Host NumPy out."""
         import torch
+
+        if x is not None:
+            self._c.copy_(torch.from_numpy(np.ascontiguousarray(x, dtype=float)))
+        self._promol_and_entropy()
+        if nderiv == 0:
+            f = self._scal[1:2].clone()
+            self._all_reduce(f)
+            return float(f.item())
+        pack = torch.cat([-self._shell_integrals(1), self._scal[1:2]])
+        self._all_reduce(pack)
+        host = pack.cpu().numpy()
+        if nderiv == 1:
+            return float(host[-1]), host[:-1].copy()
+        hess = self.hessian().clone()
+        self._all_reduce(hess)
+        return float(host[-1]), host[:-1].copy(), hess.cpu().numpy()
+
+    def _promol_population(self):
+        """int rho0 over the molecular grid for the promolecule currently in slab.promol."""
+        import torch
+
+        from .core.device import stream_ptr
+
+        s = self.slab
+        sh = s.shard
+        seg = (s.atom_point_offsets[sh.atom_lo : sh.atom_hi + 1] - s.point_base).contiguous()
+        per_atom = torch.zeros(max(sh.nlocal, 1), dtype=torch.float64, device=s.device)
+        _lib.call("hp_segment_integrate", sh.nlocal, seg, s.molw, s.promol, None, per_atom, stream_ptr(s.device))
+        total = torch.zeros(1, dtype=torch.float64, device=s.device)
+        _lib.call("hp_sum_partials", max(sh.nlocal, 1), per_atom, total, stream_ptr(s.device))
+        self._all_reduce(total)
+        return float(total.item())
+
+    def _change(self, new, old):
+        """compute_change(new, old) on the device from host coefficient vectors."""
+        import torch
+
+        dev = self.slab.device
+        c_new = torch.from_numpy(np.ascontiguousarray(new, dtype=float)).to(dev)
+        c_old = torch.from_numpy(np.ascontiguousarray(old, dtype=float)).to(dev)
+        msd = self._device_change(c_new, c_old)
+        self._all_reduce(msd)
+        return float(torch.sqrt(msd.sum()).item())
+
+    def _candidate_validity(self, candidates, check_mono):
+        """is_promol_valid (glisa.py:283-307) for a stack of coefficient vectors in one launch:
+        bool per candidate (all atoms admissible on their radial grids)."""
+        import torch
+
+        from .core.device import stream_ptr
+
+        if self.on_molgrid:
+            raise NotImplementedError("line searches with grid_type 2/3 are not built")
+        s = self.slab
+        sh = s.shard
+        cand = torch.from_numpy(np.ascontiguousarray(candidates, dtype=float)).to(s.device)
+        ncand, npar = cand.shape
+        flags = torch.zeros((ncand, max(sh.nlocal, 1)), dtype=torch.int32, device=s.device)
+        _lib.call("hp_radial_valid", sh.nlocal, sh.atom_lo, s.rad_offsets, self._par_offsets, self._bs_offsets,
+                  self._bs_flat, cand, ncand, npar, float(self.negative_cutoff), int(bool(check_mono)), flags,
+                  stream_ptr(s.device))  # fmt: skip
+        bad = (flags != 0).any(dim=1).to(torch.int32)
+        if self._comm is not None:
+            import torch.distributed as dist
+
+            dist.all_reduce(bad, op=dist.ReduceOp.MAX, group=self._comm)
+        return ~bad.bool().cpu().numpy()
+
+    def is_promol_valid(self, propars, check_mono):
+        return bool(self._candidate_validity(np.asarray(propars, dtype=float)[None, :], check_mono)[0])
+
+    def calc_promol_dens(self, propars):
+        """rho0 = sum_m c_m g_m on this rank's slab, downloaded (API helper; the solvers keep it
+        on the device)."""
+        import torch
+
+        self._c.copy_(torch.from_numpy(np.ascontiguousarray(propars, dtype=float)))
+        self._promol_and_entropy()
+        return self.slab.promol.cpu().numpy()
+
+    def solver_newton(self, maxiter=100):
+        """Exact Newton: full steps (glisa.py:573-575)."""
+        return self._solver_general_newton(maxiter=maxiter, mode="exact")
+
+    def solver_m_newton(self, maxiter=100, linspace_size=40, tau=1.0, linesearch_mode="valid-promol", **kwargs):
+        """Newton direction with a back-tracking line search (glisa.py:577-593)."""
+        return self._solver_general_newton(mode="modified", maxiter=maxiter, linesearch_mode=linesearch_mode,
+                                           tau=tau, linspace_size=linspace_size, **kwargs)  # fmt: skip
+
+    def solver_quasi_newton(self, mode="bfgs", maxiter=1000, niter_exact_newton=0,
+                            linesearch_mode="valid-promol", tau=1.0, linspace_size=40, **kwargs):  # fmt: skip
+        """BFGS inverse-Hessian updates, optionally started by exact Newton steps (glisa.py:595-615)."""
+        assert mode in ["bfgs"]
+        return self._solver_general_newton(mode=mode, maxiter=maxiter, niter_exact_newton=niter_exact_newton,
+                                           linesearch_mode=linesearch_mode, tau=tau,
+                                           linspace_size=linspace_size, **kwargs)  # fmt: skip
+
+    def _frozen_mask(self, propars, delta):
+        """1 for free coefficients, 0 for the most diffuse functions that sit at zero while the
+        step pushes them negative (glisa.py:696-706 with utils.fix_propars)."""
+        mask = np.ones_like(delta)
+        if isinstance(self.bs_helper, ExpBasisFuncHelper):
+            for a in range(self.natom):
+                lo, hi = self._ranges[a], self._ranges[a + 1]
+                for k in fix_propars(self.bs_helper.get_exponent(self.numbers[a]), propars[lo:hi], delta[lo:hi]):
+                    mask[k + lo] = 0
+        return mask
+
+    def _line_search(self, mode, linesearch_mode, delta, propars, tau, linspace_size, check_mono, old_f):
+        if mode == "exact":
+            return propars + delta, delta
+        mask = self._frozen_mask(propars, delta)
+        scales = np.linspace(tau, 0, linspace_size, endpoint=False)
+        steps = scales[:, None] * delta[None, :]
+        candidates = propars[None, :] + mask[None, :] * steps
+        valid = self._candidate_validity(candidates, check_mono)
+        old_extended = None
+        for j in np.flatnonzero(valid):
+            if linesearch_mode == "valid-promol":
+                return candidates[j], steps[j]
+            if old_extended is None:  # extended KL of the current point: promolecule is still on the device
+                old_extended = old_f + self._promol_population()
+            f = self._objective(candidates[j], nderiv=0)
+            if (f + self._promol_population()) - old_extended < self.negative_cutoff:
+                return candidates[j], steps[j]
+        raise RuntimeError("Line search failed!")
+
+    def _solver_general_newton(self, mode="bfgs", maxiter=1000, niter_exact_newton=0,
+                               linesearch_mode="valid-promol", tau=1.0, linspace_size=40, check_mono=False):  # fmt: skip
+        """Newton-type minimisation of  int rho ln(rho/rho0) + int rho0  (glisa.py:617-803):
+        step = solve(H, -1 - grad) with H exact ("exact", "modified") or BFGS-updated ("bfgs")."""
         from scipy.linalg import solve
 
+        if mode not in ("exact", "modified", "bfgs"):
+            raise RuntimeError(f"Wrong Newton mode :{mode}. It should be one of ['exact', 'modified', 'bfgs']")
+        if linesearch_mode not in ("valid-promol", "with-extended-kl"):
+            raise RuntimeError(
+                f"Wrong linesearch_mode {linesearch_mode}. It should be one of ['valid-promol', 'with-extended-kl']"
+            )
+        assert tau >= 0
         propars = self.propars
         pop = self.mol_pop
+        H = olddf = oldH = step = None
         self.logger.info("            Iter.    Change    Entropy")
         self.logger.info("            -----    ------    -------")
         for irep in range(maxiter):
-            c_old = self._c.clone()
-            self._promol_and_entropy()
-            grad = -self._shell_integrals(1).clone()
-            hess = self.hessian().clone()
-            pack = torch.cat([grad, self._scal[1:2]])
-            self._all_reduce(pack)
-            self._all_reduce(hess)
-            g_host = pack[:-1].cpu().numpy()
-            try:
-                delta = solve(hess.cpu().numpy(), -1 - g_host, assume_a="sym")
-            except np.linalg.LinAlgError as exc:
-                raise RuntimeError(exc)
-            propars[:] = c_old.cpu().numpy() + delta
-            self._c.copy_(torch.from_numpy(np.ascontiguousarray(propars)))
-            msd = self._device_change(self._c, c_old)
-            self._all_reduce(msd)
-            change = float(torch.sqrt(msd.sum()).item())
-            entropy = float(pack[-1].item())
+            old_propars = propars.copy()
+            if mode == "bfgs":
+                if irep == 0 or irep <= niter_exact_newton - 1:
+                    if niter_exact_newton == 0:
+                        f, df = self._objective(propars, 1)
+                        hess = np.identity(len(df))
+                    else:
+                        f, df, hess = self._objective(propars, 2)
+                    H = np.linalg.inv(hess)
+                else:
+                    f, df = self._objective(propars, 1)
+                    H = bfgs(df, step, olddf, oldH)
+                delta = H @ (-1 - df)
+            else:
+                f, df, hess = self._objective(propars, 2)
+                try:
+                    delta = solve(hess, -1 - df, assume_a="sym")
+                except np.linalg.LinAlgError as exc:
+                    raise RuntimeError(exc)
+            pmin = float(self.slab.promol.min().item()) if self.slab.npts else 0.0
+            propars[:], step = self._line_search(mode, linesearch_mode, delta, propars, tau, linspace_size,
+                                                 check_mono, f)  # fmt: skip
+            entropy = f  # _compute_entropy(rho, pro) is the objective at the old coefficients
+            change = self._change(propars, old_propars)
             self.history_entropies.append(entropy)
             self.history_propars.append(propars.copy())
             self.history_changes.append(change)
             self.logger.info(f"            {irep+1:<4}    {change:.5e}    {entropy:.5e}")
             if change < self.threshold:
-                # check_pro_atom_parameters (utils.py:304-401) on the promolecule of the old propars
-                pmin = self.slab.promol.min() if self.slab.npts else torch.tensor(0.0)
-                if float(pmin.item()) < self.negative_cutoff:
+                # check_pro_atom_parameters on the promolecule of the old coefficients (glisa.py:786-796)
+                if pmin < self.negative_cutoff:
                     raise RuntimeError("Negative pro-atom density found!")
                 if abs(np.sum(propars) - pop) > self.population_cutoff:
                     self.logger.warning(
@@ -327,7 +481,119 @@ class GlobalLinearISAWPart(AbstractStockholderWPart):
                     )
                 self.cache.dump("niter", irep + 1, tags="o")
                 return propars
+            olddf, oldH = df, H
         raise RuntimeError("Not converged!")
+
+    def _molgrid_l2_change(self, x, old_x):
+        """sqrt(int (rho0[x] - rho0[old_x])^2) on the molecular grid (conv_func of solver_diis,
+        glisa.py:886-893): two promolecule passes and one weighted reduction, all on the device."""
+        import torch
+
+        from .core.device import stream_ptr
+
+        s = self.slab
+        self._c.copy_(torch.from_numpy(np.ascontiguousarray(old_x, dtype=float)))
+        self._promol_and_entropy()
+        old = s.promol.clone()
+        self._c.copy_(torch.from_numpy(np.ascontiguousarray(x, dtype=float)))
+        self._promol_and_entropy()
+        diff = s.promol - old
+        sh = s.shard
+        seg = (s.atom_point_offsets[sh.atom_lo : sh.atom_hi + 1] - s.point_base).contiguous()
+        per_atom = torch.zeros(max(sh.nlocal, 1), dtype=torch.float64, device=s.device)
+        _lib.call("hp_segment_integrate", sh.nlocal, seg, s.molw, diff, diff, per_atom, stream_ptr(s.device))
+        total = per_atom.sum().reshape(1)
+        self._all_reduce(total)
+        return float(torch.sqrt(total).item())
+
+    def _entropies_of(self, history):
+        return [self._objective(x, nderiv=0) for x in history]
+
+    def _final_check(self, propars, check_mono):
+        """check_pro_atom_parameters(propars, pro_atom_density=rho0[propars], ...) with the
+        reference's defaults (negativity of coefficients warns, negative promolecule raises)."""
+        import warnings
+
+        import torch
+
+        self._c.copy_(torch.from_numpy(np.ascontiguousarray(propars, dtype=float)))
+        self._promol_and_entropy()
+        if (propars < -1e-12).any():
+            warnings.warn("WARNING: Not all pro-atom parameters are positive!")
+        pmin = self.slab.promol.min().reshape(1) if self.slab.npts else torch.zeros(1, device=self.slab.device)
+        if self._comm is not None:
+            import torch.distributed as dist
+
+            dist.all_reduce(pmin, op=dist.ReduceOp.MIN, group=self._comm)
+        if float(pmin.item()) < -1e-12:
+            raise RuntimeError("Negative pro-atom density found!")
+        if abs(np.sum(propars) - self.mol_pop) > 1e-4:
+            self.logger.warning("WARNING: The sum of pro-atom parameters is not equal to reference population.")
+
+    def solver_diis(self, use_dmrs=False, **diis_options):
+        """DIIS on the fixed-point map (glisa.py:883-925)."""
+
+        def conv_func(residual, x, old_x):
+            return np.linalg.norm(residual) if use_dmrs else self._molgrid_l2_change(x, old_x)
+
+        propars = self.propars
+        propars[:], niter, history = diis(propars, self.function_g, self.threshold, conv_func=conv_func,
+                                          verbose=True, logger=self.logger, **diis_options)  # fmt: skip
+        self._final_check(propars, False)
+        self.cache.dump("niter", niter, tags="o")
+        self.history_entropies.extend(self._entropies_of(history[1:]))
+        self.history_propars = history[1:]
+        return propars
+
+    def residual(self, x):
+        return self.function_g(x) - x
+
+    def solver_cdiis(self, **cdiis_options):
+        """Restarted / adaptive-depth CDIIS on the fixed-point map (glisa.py:993-1028)."""
+        conv, nbiter, rnormlist, _, _, propars, history = cdiis(
+            self.propars, self.function_g, self.threshold, self.maxiter, logger=self.logger, verbose=True,
+            **cdiis_options)  # fmt: skip
+        if not conv:
+            raise RuntimeError("Not converged!")
+        self._final_check(propars, False)
+        self.cache.dump("niter", nbiter, tags="o")
+        self.history_entropies.extend(self._entropies_of(history[1:]))
+        self.history_propars = history[1:]
+        self.history_changes = rnormlist
+        return propars
+
+    def solver_trust_region(self, allow_neg_pars=False):
+        """SciPy ``trust-constr`` with SR1 updates on the extended objective
+        f + int rho0 - N  (glisa.py:927-987); f and its gradient come from the device."""
+        from scipy.optimize import SR1, LinearConstraint, minimize
+
+        pars0 = self.propars
+        pop = self.mol_pop
+        nb_par = len(pars0)
+
+        def cost_grad(x):
+            f, df = self._objective(x, 1)
+            return f + (self._promol_population() - pop), df + 1
+
+        if allow_neg_pars:
+            bounds, constraint = None, LinearConstraint(np.ones((1, nb_par)), pop, pop)
+        else:
+            bounds, constraint = [(0.0, 200)] * nb_par, None
+        previous = []
+
+        def callback(current, state):
+            previous.append(np.array(current, copy=True))
+            if len(previous) >= 2:
+                change = self._molgrid_l2_change(previous[-1], previous[-2])
+                return change < self._threshold and state["status"]
+
+        result = minimize(cost_grad, pars0, method="trust-constr", jac=True, hess=SR1(), bounds=bounds,
+                          constraints=constraint, callback=callback,
+                          options={"gtol": self._threshold, "maxiter": self._maxiter, "verbose": 0})  # fmt: skip
+        self.logger.info(f'Optimizer message: "{result.message}"')
+        if not result.success:
+            raise RuntimeError("Convergence failure.")
+        return result.x
 
     # -- driver ---------------------------------------------------------------------------------
     @just_once

@@ -193,3 +193,27 @@ def expbasis_promolecule_device(grid, coordinates, numbers, helper, scale=None, 
     rho, w, lo, hi = shell_promolecule_device(grid, coordinates, functor, counts, np.concatenate(A),
                                               np.concatenate(alpha), order, device, shard)
     return rho, w
+
+
+def contraction_map(n=12, seed=1):
+    """Seeded linear part (A, b) of a contraction x -> A x + b + 0.05 sin(x) with ||A||_2 = 0.4:
+    the toy fixed-point problem of the DIIS / CDIIS known-answer tests."""
+    rng = np.random.default_rng(seed)
+    A = rng.normal(size=(n, n))
+    A = 0.4 * A / np.linalg.norm(A, 2)
+    return A, rng.normal(size=n)
+
+
+def radial_problem(helper, number, population, nrad=120):
+    """A seeded 1-D aLISA problem on an exponential radial grid: tabulated unit-population basis
+    functions (K, nrad), a target density (random non-negative coefficients plus a Slater tail that
+    is outside the basis), start coefficients, radial points and 4 pi r^2 weights."""
+    r = 5e-4 * np.exp(np.arange(nrad) * np.log(2e1 / 5e-4) / (nrad - 1))
+    w = 4 * np.pi * r**2 * np.gradient(r)
+    K = helper.get_nshell(number)
+    bs = np.array([helper.compute_proshell_dens(number, k, 1.0, r) for k in range(K)])
+    rng = np.random.default_rng(int(number))
+    c = rng.random(K)
+    c *= population / c.sum()
+    rho = c @ bs + 1e-3 * np.exp(-1.3 * r)
+    return bs, rho, np.full(K, population / K), r, w

@@ -1,10 +1,13 @@
 """Constants, geometry type checks and the scheme registry.
 
 Mirrors /root/reference/src/horton_part/utils.py:51-59 (cut-offs from data/constants.yaml),
-:62-104 (``wpart_schemes``) and :107-186 (``typecheck_geo``).
+:62-104 (``wpart_schemes``), :107-186 (``typecheck_geo``), :198-252 (``compute_quantities``, the
+1-D radial helper of the host plug-in solvers) and :255-577 (validity checks, ``fix_propars``).
 """
 
 from __future__ import annotations
+
+import warnings
 
 import numpy as np
 
@@ -15,6 +18,15 @@ __all__ = [
     "NEGATIVE_CUTOFF",
     "POPULATION_CUTOFF",
     "ANGSTROM",
+    "compute_quantities",
+    "check_pro_atom_parameters",
+    "check_pro_atom_parameters_neg_pars",
+    "check_pro_atom_parameters_non_neg_pars",
+    "check_pars_population",
+    "check_pars_negativity",
+    "check_dens_negativity",
+    "check_dens_monotonicity",
+    "fix_propars",
 ]
 
 # data/constants.yaml of the reference
@@ -91,3 +103,126 @@ def typecheck_geo(coordinates=None, numbers=None, pseudo_numbers=None, need_coor
     if need_pseudo_numbers:
         out.append(pseudo_numbers)
     return out
+
+
+# -- helpers of the host plug-in solvers (1-D radial problems, K x nrad arrays) -------------------
+def compute_quantities(density, pro_atom_params, basis_functions, density_cutoff, do_sick=True,
+                       do_ratio=True, do_ln_ratio=True):  # fmt: skip
+    """(pro_shells, pro_density, sick, ratio, ln_ratio) for coefficients ``pro_atom_params`` of
+    the tabulated ``basis_functions`` (K, N); ratio = density / pro_density and its logarithm are
+    0 where either density is below ``density_cutoff`` (utils.py:198-252)."""
+    c = np.asarray(pro_atom_params).flatten()
+    pro_shells = basis_functions * c[:, None]
+    pro_density = np.einsum("ij->j", pro_shells)
+    sick = ratio = ln_ratio = None
+    if do_sick:
+        sick = (density < density_cutoff) | (pro_density < density_cutoff)
+    with np.errstate(all="ignore"):
+        if do_ratio:
+            ratio = np.divide(density, pro_density, out=np.zeros_like(density), where=~sick)
+        if do_ln_ratio:
+            ln_ratio = np.log(ratio, out=np.zeros_like(density), where=~sick)
+    return pro_shells, pro_density, sick, ratio, ln_ratio
+
+
+def _report(message, as_warn, logger, error, level="warning"):
+    if not as_warn:
+        raise RuntimeError(error)
+    if logger is not None:
+        getattr(logger, level)(message)
+    else:
+        warnings.warn(message)
+
+
+def check_pars_population(propars, ref_pop, as_warn=True, logger=None, population_cutoff=POPULATION_CUTOFF):
+    diff = np.sum(propars) - ref_pop
+    if np.abs(diff) > population_cutoff:
+        tag = "WARNING" if as_warn else "ERROR"
+        text = (f"{tag}: The sum of pro-atom parameters is not equal to reference population.\n"
+                f"{tag}: The difference is {diff:.5E}")  # fmt: skip
+        _report(text, as_warn, logger, text)
+
+
+def check_pars_negativity(pars, as_warn=True, logger=None, negative_cutoff=NEGATIVE_CUTOFF):
+    assert np.ndim(pars) == 1
+    if (pars < negative_cutoff).any():
+        _report("WARNING: Not all pro-atom parameters are positive!", as_warn, logger,
+                "Negative pro-atom parameters found!")  # fmt: skip
+
+
+def check_dens_negativity(dens, as_warn=False, logger=None, negative_cutoff=NEGATIVE_CUTOFF):
+    assert np.ndim(dens) in [1, 3]
+    if (dens < negative_cutoff).any():
+        _report("WARNING: Not all pro-atom density are positive!", as_warn, logger,
+                "Negative pro-atom density found!")  # fmt: skip
+
+
+def check_dens_monotonicity(dens, as_warn=True, logger=None, negative_cutoff=NEGATIVE_CUTOFF):
+    assert np.ndim(dens) == 1
+    if (dens[:-1] - dens[1:] < negative_cutoff).any():
+        text = "WARNING: Pro-atom density should be monotonically decreasing."
+        _report(text, as_warn, logger, "Pro-atom density should be monotonically decreasing.", level="info")
+        warnings.warn(text)
+
+
+def check_pro_atom_parameters(pro_atom_params, basis_functions=None, total_population=None,
+                              pro_atom_density=None, check_monotonicity=True, check_negativity=True,
+                              check_propars_negativity=True, logger=None,
+                              negative_cutoff=NEGATIVE_CUTOFF, population_cutoff=POPULATION_CUTOFF):  # fmt: skip
+    """Validity of a set of pro-atom coefficients (utils.py:304-401): negative density raises,
+    negative coefficients / population mismatch warn, non-monotonic density raises if requested."""
+    if np.asarray(pro_atom_params).ndim != 1:
+        raise ValueError("pro_atom_params must be a 1D array")
+    if basis_functions is not None and np.asarray(basis_functions).ndim != 2:
+        raise ValueError("basis_functions must be a 2D array")
+    if pro_atom_density is not None and np.asarray(pro_atom_density).ndim != 1:
+        raise ValueError("pro_atom_density must be a 1D array")
+    if check_propars_negativity:
+        check_pars_negativity(pro_atom_params, negative_cutoff=negative_cutoff)
+    if basis_functions is not None and pro_atom_density is None:
+        if pro_atom_params.size != basis_functions.shape[0]:
+            raise ValueError("Length of pro_atom_params does not match the number of basis functions")
+        pro_atom_density = (basis_functions * pro_atom_params[:, None]).sum(axis=0)
+    if check_negativity and pro_atom_density is not None:
+        check_dens_negativity(pro_atom_density, logger=logger, negative_cutoff=negative_cutoff)
+    if total_population is not None:
+        check_pars_population(pro_atom_params, total_population, logger=logger, population_cutoff=population_cutoff)
+    if check_monotonicity and pro_atom_density is not None:
+        check_dens_monotonicity(pro_atom_density, as_warn=False, logger=logger, negative_cutoff=negative_cutoff)
+
+
+def check_pro_atom_parameters_non_neg_pars(pro_atom_params, basis_functions=None, total_population=None,
+                                           pro_atom_density=None, logger=None,
+                                           negative_cutoff=NEGATIVE_CUTOFF,
+                                           population_cutoff=POPULATION_CUTOFF):  # fmt: skip
+    return check_pro_atom_parameters(
+        pro_atom_params, basis_functions, total_population, pro_atom_density, check_monotonicity=False,
+        check_negativity=False, check_propars_negativity=False, logger=logger,
+        negative_cutoff=negative_cutoff, population_cutoff=population_cutoff,
+    )  # fmt: skip
+
+
+def check_pro_atom_parameters_neg_pars(pro_atom_params, basis_functions=None, total_population=None,
+                                       pro_atom_density=None, check_monotonicity=True,
+                                       check_negativity=True, logger=None,
+                                       negative_cutoff=NEGATIVE_CUTOFF,
+                                       population_cutoff=POPULATION_CUTOFF):  # fmt: skip
+    return check_pro_atom_parameters(
+        pro_atom_params, basis_functions, total_population, pro_atom_density,
+        check_monotonicity=check_monotonicity, check_negativity=check_negativity,
+        check_propars_negativity=False, logger=logger, negative_cutoff=negative_cutoff,
+        population_cutoff=population_cutoff,
+    )  # fmt: skip
+
+
+def fix_propars(exp_array, propars, delta):
+    """Indices of the most diffuse functions whose coefficient is (numerically) zero while the
+    Newton step wants to push it negative: walking up from the smallest exponent, stop at the
+    first function that does not qualify (utils.py:555-577)."""
+    frozen = []
+    for k in np.argsort(exp_array):
+        if np.abs(propars[k]) < 1e-4 and delta[k] < 0.0:
+            frozen.append(k)
+        else:
+            break
+    return frozen

@@ -260,6 +260,17 @@ HP_API int hp_radial_change(int32_t natom, int32_t atom_base, const int32_t* rad
                             const int64_t* bs_offsets, const double* bs_funcs, const double* c_new,
                             const double* c_old, double* msd, void* stream);
 
+/* (row a12, line search of the modified / quasi-Newton gLISA solvers: glisa.py:283-307
+ * is_promol_valid / is_proatom_valid on the radial grids)  candidates = ncand x npar coefficient
+ * vectors (global shell indexing); flags[j*natom + a_local] = 1 if candidate j makes atom a's
+ * pro-atom < negative_cutoff somewhere, 2 if check_mono and it is not monotonically decaying,
+ * else 0. */
+HP_API int hp_radial_valid(int32_t natom, int32_t atom_base, const int32_t* rad_offsets,
+                           const int32_t* par_offsets, const int64_t* bs_offsets,
+                           const double* bs_funcs, const double* candidates, int32_t ncand,
+                           int32_t npar, double negative_cutoff, int32_t check_mono, int32_t* flags,
+                           void* stream);
+
 /* (row a9, grid_type 2/3) one inner iteration of the per-atom fixed points on the MOLECULAR grid for
  * all atoms at once (mbis.py:128-152 / alisa.py:262-274 with rhoa = at_weights*moldens,
  * weights = grid.weights, r = radial_distances[a]; mbis.py:170-173, gisa.py:257-279).

@@ -217,7 +217,138 @@ def case_water_gauss(natom=6, nrad=40, nang=50, seed=0):
     )  # fmt: skip
 
 
-CASES = {"h2o": case_h2o, "water6": case_water_cluster, "water6g": case_water_gauss, "hirshfeld": case_hirshfeld}
+def run_reference_light(scheme, coords, numbers, pseudo, grid, rho, **kwargs):
+    """Reference run keeping only what the solver parity tests compare."""
+    import contextlib
+    import io
+    import warnings
+
+    with contextlib.redirect_stdout(io.StringIO()), warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        part = wpart_schemes(scheme)(coords, numbers, pseudo, grid, rho, **kwargs)
+        part.do_charges()
+    out = {"charges": part["charges"], "propars": part["propars"],
+           "promoldens_sample": part["promoldens"][::97].copy()}
+    for key in ("niter", "history_changes", "history_entropies"):
+        if key in part.cache:
+            out[key] = np.asarray(part[key])
+    return out
+
+
+SOLVER_CASES = {
+    # aLISA host plug-ins (alisa.py:460-1127) on the Slater promolecule
+    "s/lisa_diis": ("lisa", "s", dict(solver="diis")),
+    "s/lisa_diis_A": ("lisa", "s", dict(solver="diis", solver_options=dict(version="A"))),
+    "s/lisa_cdiis": ("lisa", "s", dict(solver="cdiis")),
+    "s/lisa_cdiis_ad": ("lisa", "s", dict(solver="cdiis", solver_options=dict(mode="AD-CDIIS"))),
+    "s/lisa_newton": ("lisa", "s", dict(solver="newton")),
+    "s/lisa_m_newton": ("lisa", "s", dict(solver="m-newton")),
+    "s/lisa_quasi_newton": ("lisa", "s", dict(solver="quasi-newton")),
+    "s/lisa_trust_region": ("lisa", "s", dict(solver="trust-region", maxiter=6)),
+    "s/lisa_sc_1_iter": ("lisa", "s", dict(solver="sc-1-iter")),
+    # gLISA solver family (glisa.py:572-1028) on both promolecules
+    "g/glisa_diis": ("glisa", "g", dict(solver="diis")),
+    "g/glisa_diis_A": ("glisa", "g", dict(solver="diis", solver_options=dict(version="A"))),
+    "g/glisa_diis_dmrs": ("glisa", "g", dict(solver="diis", solver_options=dict(use_dmrs=True))),
+    "g/glisa_cdiis": ("glisa", "g", dict(solver="cdiis")),
+    "g/glisa_cdiis_ad": ("glisa", "g", dict(solver="cdiis", solver_options=dict(mode="AD-CDIIS"))),
+    "g/glisa_cdiis_fd": ("glisa", "g", dict(solver="cdiis", solver_options=dict(mode="FD-CDIIS"))),
+    "g/glisa_m_newton": ("glisa", "g", dict(solver="m-newton")),
+    "g/glisa_m_newton_kl": ("glisa", "g", dict(solver="m-newton", solver_options=dict(linesearch_mode="with-extended-kl"))),
+    "g/glisa_quasi_newton": ("glisa", "g", dict(solver="quasi-newton")),
+    "g/glisa_quasi_newton_2": ("glisa", "g", dict(solver="quasi-newton", solver_options=dict(niter_exact_newton=2))),
+    "g/glisa_trust_region": ("glisa", "g", dict(solver="trust-region")),
+    "s/glisa_diis": ("glisa", "s", dict(solver="diis")),
+    "s/glisa_cdiis": ("glisa", "s", dict(solver="cdiis")),
+    "s/glisa_newton": ("glisa", "s", dict(solver="newton")),
+    "s/glisa_m_newton": ("glisa", "s", dict(solver="m-newton")),
+    "s/glisa_quasi_newton": ("glisa", "s", dict(solver="quasi-newton")),
+}
+
+
+def case_water6_solvers(natom=6, nrad=40, nang=50, seed=0):
+    """Every built-in solver of aLISA / gLISA that runs without third-party packages, on the two
+    synthetic 6-atom promolecules of the cases above ("s" Slater, "g" Gaussian)."""
+    from horton_part.core.basis import ExpBasisFuncHelper
+
+    coords, numbers = synthetic.water_cluster(natom, seed)
+    grid = synthetic_grid(coords, numbers, nrad, nang)
+    helper = ExpBasisFuncHelper.from_function_type("gauss")
+    rhos = {"s": synthetic.slater_promolecule_host(grid.points, coords, numbers),
+            "g": synthetic.expbasis_promolecule_host(grid.points, coords, numbers, helper, scale={8: 8.6, 1: 0.7})}
+    pseudo = numbers.astype(float)
+    results = {}
+    for tag, (scheme, dens, kw) in SOLVER_CASES.items():
+        try:
+            t0 = time.time()
+            results[tag] = run_reference_light(scheme, coords, numbers, pseudo, grid, rhos[dens], **kw)
+            print(f"  {tag}: niter={results[tag].get('niter')} q={results[tag]['charges'][:3]} {time.time()-t0:.1f}s")
+        except Exception as exc:
+            results[tag] = {"raised": np.array(f"{type(exc).__name__}: {exc}")}
+            print(f"  {tag}: reference raised {type(exc).__name__}: {exc}")
+    save("water6_solvers.npz", results, coordinates=coords, numbers=numbers)
+
+
+def case_algo():
+    """Known-answer vectors for the host algebra modules (algo/diis.py, algo/cdiis.py,
+    algo/quasi_newton.py) and the aLISA radial plug-in solvers (alisa.py), from the reference
+    itself on a seeded contraction map / seeded radial problems.  CPU-only tests use these."""
+    import warnings
+
+    import horton_part.alisa as ra
+    from horton_part.algo.cdiis import cdiis
+    from horton_part.algo.diis import diis, lstsq_solver_dyn
+    from horton_part.algo.quasi_newton import bfgs
+    from horton_part.core.basis import ExpBasisFuncHelper
+    import contextlib
+    import io
+
+    from horton_part_b200 import synthetic as syn
+
+    out = {}
+    A, b = syn.contraction_map(12, seed=1)
+    f = lambda x: A @ x + b + 0.05 * np.sin(x)  # noqa: E731
+    x0 = np.zeros(12)
+    with contextlib.redirect_stdout(io.StringIO()), warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        for mode in ("R-CDIIS", "AD-CDIIS", "FD-CDIIS", "Roothaan"):
+            for qr in ("full", "economic"):
+                conv, n, rn, mk, cn, xl, hist = cdiis(x0.copy(), f, 1e-10, 200, modeQR=qr, mode=mode)
+                out[f"cdiis/{mode}/{qr}/x"] = xl
+                out[f"cdiis/{mode}/{qr}/niter"] = np.int64(n)
+                out[f"cdiis/{mode}/{qr}/rnorm"] = np.asarray(rn)
+                out[f"cdiis/{mode}/{qr}/mk"] = np.asarray(mk)
+        for ver in "PA":
+            for name, ls in (("sp", None), ("dyn", lstsq_solver_dyn)):
+                x, n, hist = diis(x0.copy(), f, 1e-10, version=ver, lstsq_solver=ls)
+                out[f"diis/{ver}/{name}/x"] = x
+                out[f"diis/{ver}/{name}/niter"] = np.int64(n)
+                out[f"diis/{ver}/{name}/history"] = np.asarray(hist)
+        rng = np.random.default_rng(5)
+        s, d0, d1 = rng.normal(size=5), rng.normal(size=5), rng.normal(size=5)
+        H0 = np.eye(5) + 0.1 * np.outer(s, s)
+        out["bfgs/s"], out["bfgs/d0"], out["bfgs/d1"], out["bfgs/H0"] = s, d0, d1, H0
+        out["bfgs/H1"] = bfgs(d1, s, d0, H0)
+        lg = logging.getLogger("golden")
+        for func_type in ("gauss", "slater"):
+            h = ExpBasisFuncHelper.from_function_type(func_type)
+            for Z, pop in ((8, 8.5), (1, 0.7), (6, 6.1)):
+                bs, rho, c0, r, w = syn.radial_problem(h, Z, pop)
+                for name in ("solver_sc", "solver_sc_1_iter", "solver_diis", "solver_cdiis", "solver_m_newton",
+                             "solver_quasi_newton", "solver_newton", "solver_trust_region"):
+                    key = f"radial/{func_type}/{Z}/{name}"
+                    try:
+                        res = getattr(ra, name)(bs, rho, c0.copy(), r, w, 1e-8, lg, 1e-15, -1e-12, 1e-4)
+                        out[key] = np.asarray(res)
+                    except Exception as exc:
+                        out[key + "/raised"] = np.array(type(exc).__name__)
+    GOLD.mkdir(parents=True, exist_ok=True)
+    np.savez_compressed(GOLD / "algo_host.npz", **out)
+    print("wrote", GOLD / "algo_host.npz", len(out), "entries")
+
+
+CASES = {"h2o": case_h2o, "water6": case_water_cluster, "water6g": case_water_gauss, "hirshfeld": case_hirshfeld,
+         "solvers": case_water6_solvers, "algo": case_algo}
 
 if __name__ == "__main__":
     for name in sys.argv[1:] or CASES:
