@@ -19,6 +19,7 @@ _LAZY = {
     "GMBISWPart": "gmbis",
     "HirshfeldWPart": "hirshfeld",
     "HirshfeldIWPart": "hirshfeld_i",
+    "BeckeWPart": "becke",
 }
 
 

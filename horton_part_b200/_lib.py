@@ -47,6 +47,7 @@ EXPORTS = {
     ),
     "hp_shell_screen": (_int, [_i32, _p, _p, _p, _f64, _p, _p]),
     "hp_shell_project": (_int, [_i32, _p, _p, _p, _p, _p, _p, _p, _p]),
+    "hp_shell_harmonics": (_int, [_i32, _i32, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
     "hp_mbis_radial_solve": (
         _int,
         [_i32, _i32, _p, _p, _p, _p, _p, _p, _p, _f64, _f64, _i32, _p, _p, _p, _p, _p],

@@ -19,6 +19,7 @@ import logging
 
 import numpy as np
 
+from .. import _lib
 from ..utils import DENSITY_CUTOFF, NEGATIVE_CUTOFF, POPULATION_CUTOFF, typecheck_geo
 from .cache import Cache, JustOnceClass, just_once
 from .logging import deflist, setup_logger
@@ -195,6 +196,48 @@ class Part(JustOnceClass):
     def _atom_moments(self):
         raise NotImplementedError
 
+    @just_once
+    def do_density_decomposition(self):
+        """Real-spherical-harmonic radial components of every atom-in-molecule density as splines
+        (core/base.py:637-659 with qc-grid ``AtomGrid.radial_component_splines``): the projection
+        onto Y_lm on every radial shell runs on the device for all atoms at once
+        (``hp_shell_harmonics``), the cache gets the same ``{"spline_%05i": CubicSpline}``
+        dictionaries under ("density_decomposition", index)."""
+        import torch
+        from scipy.interpolate import CubicSpline
+
+        from .. import _lib
+        from .device import stream_ptr, to_device
+
+        if not self.local:
+            self.logger.warning("Skip density decomposition because no local grids were found.")
+            return
+        if all(("density_decomposition", a) in self.cache for a in range(self.natom)):
+            return
+        self.do_partitioning()
+        slab = self.slab
+        sh = slab.shard
+        degrees = [int(self.get_grid(a).l_max) for a in range(sh.atom_lo, sh.atom_hi)]
+        assert min(degrees, default=self.lmax) >= self.lmax
+        nrad = np.diff(slab.rad_offsets_host)
+        shell_atom = to_device(np.repeat(np.arange(sh.atom_lo, sh.atom_hi, dtype=np.int32), nrad), slab.device)
+        ro = slab.rad_offsets_host
+        for lhalf in sorted(set(d // 2 for d in degrees)):
+            # one launch per distinct angular order (normally a single one)
+            nlm = (lhalf + 1) ** 2
+            out = torch.zeros((slab.nshell, nlm), dtype=torch.float64, device=slab.device)
+            _lib.call("hp_shell_harmonics", slab.nshell, lhalf, slab.shell_point_offsets, shell_atom, slab.px,
+                      slab.py, slab.pz, slab.atom_xyz, slab.at_w, slab.rho, slab.atw, slab.rad_r, slab.rad_r2w,
+                      out, stream_ptr(slab.device))  # fmt: skip
+            comps = out.cpu().numpy()
+            for i, a in enumerate(range(sh.atom_lo, sh.atom_hi)):
+                if degrees[i] // 2 != lhalf:
+                    continue
+                r = slab.rad_r_host[ro[i] : ro[i + 1]]
+                block = comps[ro[i] : ro[i + 1]]
+                splines = {"spline_%05i" % j: CubicSpline(r, block[:, j]) for j in range(nlm)}
+                self.cache.dump(("density_decomposition", a), splines, tags="o")
+
     def do_all(self):
         for attr_name in dir(self):
             attr = getattr(self, attr_name)
@@ -299,3 +342,45 @@ class WPart(Part):
             self._slab = GridSlab(self._grid, self._moldens, self.coordinates, self._device, shard,
                                   need_atgrids=self.local)  # fmt: skip
         return self._slab
+
+    def _atom_moments(self):
+        import torch
+
+        from .device import stream_ptr
+
+        if not self.local:
+            raise NotImplementedError("moments need atomic grids (grid_type 1 or 2)")
+        slab = self.slab
+        sh = slab.shard
+        lmax = int(self.lmax)
+        nmom = (lmax + 1) * (lmax + 2) * (lmax + 3) // 6 + (lmax + 1) ** 2 + lmax + 1
+        seg = (slab.atom_point_offsets[sh.atom_lo : sh.atom_hi + 1] - slab.point_base).contiguous()
+        out = torch.zeros((self.natom, nmom), dtype=torch.float64, device=slab.device)
+        _lib.call("hp_atom_moments", sh.nlocal, sh.atom_lo, lmax, seg, slab.px, slab.py, slab.pz, slab.atw,
+                  slab.at_w, slab.rho, slab.atom_xyz, out, stream_ptr(slab.device))  # fmt: skip
+        if self._comm is not None:
+            import torch.distributed as dist
+
+            dist.all_reduce(out, group=self._comm)
+        return out.cpu().numpy()
+
+    def _atom_integrals(self, density):
+        import torch
+
+        from .device import stream_ptr, to_device
+
+        slab = self.slab
+        if density is self._moldens:
+            dens = slab.rho
+        else:
+            dens = to_device(np.asarray(density)[slab.point_base : slab.point_base + slab.npts], slab.device)
+        sh = slab.shard
+        seg = slab.atom_point_offsets[sh.atom_lo : sh.atom_hi + 1] - slab.point_base
+        out = torch.zeros(self.natom, dtype=torch.float64, device=slab.device)
+        _lib.call("hp_segment_integrate", sh.nlocal, seg.contiguous(), slab.atw, slab.at_w, dens,
+                  out[sh.atom_lo : sh.atom_hi], stream_ptr(slab.device))  # fmt: skip
+        if self._comm is not None:
+            import torch.distributed as dist
+
+            dist.all_reduce(out, group=self._comm)
+        return out.cpu().numpy()

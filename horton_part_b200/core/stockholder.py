@@ -95,6 +95,49 @@ class AbstractStockholderWPart(WPart):
         for a in range(slab.shard.atom_lo, slab.shard.atom_hi):
             self.cache.dump(f"at_weights_{a}", at_w[off[a] - lo : off[a + 1] - lo])
 
+    # -- host helpers of the reference API (spline objects for user code) --------------------------
+    def fix_proatom_rho(self, index, rho, deriv):
+        """Clip negative parts of a tabulated pro-atom (core/stockholder.py:202-224)."""
+        rgrid = self.get_rgrid(index)
+        original = rgrid.integrate(rho)
+        if rho.min() < 0:
+            rho[rho < 0] = 0.0
+            deriv = None
+            error = rgrid.integrate(rho) - original
+            self.logger.info("                Pro-atom not positive everywhere. Lost %.1e electrons" % error)
+        return rho, deriv
+
+    def get_proatom_spline(self, index, *args, **kwargs):
+        """SciPy spline of the pro-atom's radial density on its radial grid
+        (core/stockholder.py:226-269): Hermite if derivatives are available, not-a-knot otherwise."""
+        from scipy.interpolate import CubicHermiteSpline, CubicSpline
+
+        rho, deriv = self.get_proatom_rho(index, *args, **kwargs)
+        rho, deriv = self.fix_proatom_rho(index, rho, deriv)
+        rgrid = self.get_rgrid(index)
+        if deriv is None:
+            return CubicSpline(rgrid.points, rho, True)
+        return CubicHermiteSpline(rgrid.points, rho, deriv, True)
+
+    def eval_spline(self, index, spline, output, grid, label="noname"):
+        """output[:] = spline(|r - R_index|) on ``grid`` (core/stockholder.py:271-302); API helper
+        for user code, the partitioning itself evaluates pro-atoms in the kernels."""
+        output[:] = spline(np.linalg.norm(self.coordinates[index] - grid.points, axis=1))
+
+    def eval_proatom(self, index, output, grid):
+        """Pro-atom of atom ``index`` on an arbitrary grid, + 1e-100 (core/stockholder.py:304-350)."""
+        self.eval_spline(index, self.get_proatom_spline(index), output, grid, label="proatom")
+        output += 1e-100
+        assert np.isfinite(output).all()
+
+    def do_prosplines(self):
+        """Store the pro-atom density splines (core/stockholder.py:386-393)."""
+        for index in range(self.natom):
+            key = ("spline_prodensity", index)
+            if key not in self.cache:
+                self.logger.info("Storing proatom density spline for atom %i." % index)
+                self.cache.dump(key, self.get_proatom_spline(index), tags="o")
+
     def _compute_entropy(self, rho, rho0):
         """Host restatement for API users (core/stockholder.py:145-151); the iteration loop gets
         the same number from the fused kernel's partial sums."""
@@ -102,45 +145,3 @@ class AbstractStockholderWPart(WPart):
         with np.errstate(all="ignore"):
             ln_ratio = np.where(sick, 0.0, np.log(np.where(sick, 1.0, rho / np.where(sick, 1.0, rho0))))
         return self._grid.integrate(rho, ln_ratio)
-
-    def _atom_moments(self):
-        import torch
-
-        from .device import stream_ptr
-
-        if not self.local:
-            raise NotImplementedError("moments need atomic grids (grid_type 1 or 2)")
-        slab = self.slab
-        sh = slab.shard
-        lmax = int(self.lmax)
-        nmom = (lmax + 1) * (lmax + 2) * (lmax + 3) // 6 + (lmax + 1) ** 2 + lmax + 1
-        seg = (slab.atom_point_offsets[sh.atom_lo : sh.atom_hi + 1] - slab.point_base).contiguous()
-        out = torch.zeros((self.natom, nmom), dtype=torch.float64, device=slab.device)
-        _lib.call("hp_atom_moments", sh.nlocal, sh.atom_lo, lmax, seg, slab.px, slab.py, slab.pz, slab.atw,
-                  slab.at_w, slab.rho, slab.atom_xyz, out, stream_ptr(slab.device))  # fmt: skip
-        if self._comm is not None:
-            import torch.distributed as dist
-
-            dist.all_reduce(out, group=self._comm)
-        return out.cpu().numpy()
-
-    def _atom_integrals(self, density):
-        import torch
-
-        from .device import stream_ptr, to_device
-
-        slab = self.slab
-        if density is self._moldens:
-            dens = slab.rho
-        else:
-            dens = to_device(np.asarray(density)[slab.point_base : slab.point_base + slab.npts], slab.device)
-        sh = slab.shard
-        seg = slab.atom_point_offsets[sh.atom_lo : sh.atom_hi + 1] - slab.point_base
-        out = torch.zeros(self.natom, dtype=torch.float64, device=slab.device)
-        _lib.call("hp_segment_integrate", sh.nlocal, seg.contiguous(), slab.atw, slab.at_w, dens,
-                  out[sh.atom_lo : sh.atom_hi], stream_ptr(slab.device))  # fmt: skip
-        if self._comm is not None:
-            import torch.distributed as dist
-
-            dist.all_reduce(out, group=self._comm)
-        return out.cpu().numpy()

@@ -61,6 +61,76 @@ shell_project_kernel(int nshell, const int64_t* __restrict__ shell_off, const do
 }
 
 // ---------------------------------------------------------------------------------------------
+// Real-spherical-harmonic components of w_a*rho on every radial shell (do_density_decomposition,
+// core/base.py:637-659 with qc-grid AtomGrid.radial_component_splines): one warp per shell,
+//   out[s][lm] = sum_j atw_j f_j Y_lm(Omega_j) / (r_s^2 w_rad_s),   0 at the nucleus,
+// Y_lm = sqrt((2l+1)/4pi) R_lm(unit vector), R_lm the Racah-normalised real solid harmonics in
+// HORTON-2 order (C_l0, C_l1, S_l1, ...), l <= lmax <= kMaxHarmL.  The harmonics are generated per
+// point by the (z, r^2) recursion, m outermost so that only two Legendre-type values are live.
+// ---------------------------------------------------------------------------------------------
+constexpr int kMaxHarmL = 16;
+
+__global__ void __launch_bounds__(128)
+shell_harmonics_kernel(int nshell, int lmax, const int64_t* __restrict__ shell_off,
+                       const int* __restrict__ shell_atom, const double* __restrict__ px,
+                       const double* __restrict__ py, const double* __restrict__ pz,
+                       const double* __restrict__ atom_xyz, const double* __restrict__ w,
+                       const double* __restrict__ rho, const double* __restrict__ atw,
+                       const double* __restrict__ shell_r, const double* __restrict__ r2w,
+                       double* __restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const int s = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (s >= nshell) return;
+    const int nlm = (lmax + 1) * (lmax + 1);
+    double acc[(kMaxHarmL + 1) * (kMaxHarmL + 1)];
+    for (int i = 0; i < nlm; ++i) acc[i] = 0.0;
+    const int a = shell_atom[s];
+    const double cx = atom_xyz[3 * a], cy = atom_xyz[3 * a + 1], cz = atom_xyz[3 * a + 2];
+    const int64_t lo = shell_off[s], hi = shell_off[s + 1];
+    for (int64_t p = lo + lane; p < hi; p += 32) {
+        const double dx = px[p] - cx, dy = py[p] - cy, dz = pz[p] - cz;
+        const double r = sqrt((dx * dx + dy * dy) + dz * dz);
+        const double x = r > 0.0 ? dx / r : 0.0, y = r > 0.0 ? dy / r : 0.0, z = r > 0.0 ? dz / r : 0.0;
+        const double r2 = x * x + y * y + z * z;
+        const double f = (w[p] * rho[p]) * atw[p];
+        double A = 1.0, B = 0.0, dfact = 1.0, inv_2m_fact = 1.0;
+        for (int m = 0; m <= lmax; ++m) {
+            if (m > 0) {
+                const double An = x * A - y * B;
+                B = x * B + y * A;
+                A = An;
+                dfact *= double(2 * m - 1);
+                inv_2m_fact /= double(2 * m - 1) * double(2 * m);
+            }
+            double pim2 = 0.0, pim1 = 0.0, ratio = inv_2m_fact;  // (l-m)!/(l+m)! at l = m
+            for (int l = m; l <= lmax; ++l) {
+                double pi;
+                if (l == m) pi = dfact;
+                else if (l == m + 1) pi = double(2 * m + 1) * z * pim1;
+                else pi = (double(2 * l - 1) * z * pim1 - double(l + m - 1) * r2 * pim2) / double(l - m);
+                if (l > m) ratio *= double(l - m) / double(l + m);
+                pim2 = pim1;
+                pim1 = pi;
+                const double ynorm = sqrt(double(2 * l + 1) / kFourPi);
+                if (m == 0) {
+                    acc[l * l] += f * (ynorm * pi);
+                } else {
+                    const double nrm = sqrt(2.0 * ratio) * ynorm;
+                    acc[l * l + 2 * m - 1] += f * (nrm * pi * A);
+                    acc[l * l + 2 * m] += f * (nrm * pi * B);
+                }
+            }
+        }
+    }
+    const bool nucleus = fabs(shell_r[s]) < 1e-8;
+    const double scale = r2w[s];
+    for (int i = 0; i < nlm; ++i) {
+        const double v = warp_allsum(acc[i]);
+        if (lane == 0) out[int64_t(s) * nlm + i] = nucleus ? 0.0 : v / scale;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // MBIS radial fixed point, one warp per atom
 // ---------------------------------------------------------------------------------------------
 constexpr int kMaxMbisShells = 7;  // periodic table: get_nshell <= 7 (mbis.py:36-46)
@@ -643,6 +713,25 @@ extern "C" int hp_shell_project(int32_t nshell, const int64_t* shell_point_offse
     shell_project_kernel<<<int(blocks), warps_per_block * 32, 0, as_stream(stream)>>>(
         nshell, shell_point_offsets, at_weights, rho, atgrid_w, shell_r, shell_r2w, out_sph_avg);
     HP_LAUNCH_CHECK("shell_project_kernel");
+    return HP_OK;
+}
+
+extern "C" int hp_shell_harmonics(int32_t nshell, int32_t lmax, const int64_t* shell_point_offsets,
+                                  const int32_t* shell_atom, const double* px, const double* py,
+                                  const double* pz, const double* atom_xyz, const double* at_weights,
+                                  const double* rho, const double* atgrid_w, const double* shell_r,
+                                  const double* shell_r2w, double* out, void* stream) {
+    HP_REQUIRE(nshell >= 0, "bad sizes");
+    HP_REQUIRE(lmax >= 0 && lmax <= kMaxHarmL, "lmax must be in 0..16");
+    if (nshell == 0) return HP_OK;
+    HP_REQUIRE(shell_point_offsets && shell_atom && px && py && pz && atom_xyz && at_weights && rho &&
+                   atgrid_w && shell_r && shell_r2w && out, "null input");
+    const int warps_per_block = 4;
+    const int blocks = (nshell + warps_per_block - 1) / warps_per_block;
+    shell_harmonics_kernel<<<blocks, warps_per_block * 32, 0, as_stream(stream)>>>(
+        nshell, lmax, shell_point_offsets, shell_atom, px, py, pz, atom_xyz, at_weights, rho, atgrid_w,
+        shell_r, shell_r2w, out);
+    HP_LAUNCH_CHECK("shell_harmonics_kernel");
     return HP_OK;
 }
 

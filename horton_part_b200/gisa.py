@@ -2,9 +2,9 @@
 
 Counterpart of the reference's ``gisa.py`` (``GaussianISAWPart`` :109-345, ``init_propars`` :68-88,
 ``evaluate_basis_functions`` :91-106, QP interface :348-421).  The per-iteration grid passes run on
-the GPU; GISA's own per-atom update is a small quadratic programme solved on the host through the
-third-party ``qpsolvers`` package exactly as in the reference (absent in this image: using it
-raises ImportError; a user-supplied callable solver works).
+the GPU; GISA's own per-atom update is a small strictly convex quadratic programme (K <= 12
+unknowns) that stays on the host as in the reference: through the third-party ``qpsolvers``
+package when it is installed, otherwise through the exact active-set solver in ``algo/qp.py``.
 """
 
 from __future__ import annotations
@@ -14,10 +14,12 @@ import warnings
 import numpy as np
 
 from . import _lib
+from .algo.qp import solve_qp_simplex
 from .core.basis import ExpBasisFuncHelper, shell_norm
 from .core.cache import just_once
 from .core.iterstock import AbstractISAWPart
 from .core.logging import deflist
+from .utils import check_pro_atom_parameters
 
 __all__ = ["GaussianISAWPart", "get_proatom_rho", "init_propars", "evaluate_basis_functions"]
 
@@ -242,20 +244,30 @@ class GaussianISAWPart(AbstractISAWPart):
 
 
 def opt_propars_qp_interface(bs_funcs, rho, propars, weights, alphas, solver="quadprog", **solver_options):
-    """GISA's quadratic programme  min c^T P c + q^T c,  c >= 0,  sum c = pop  (gisa.py:348-421),
-    handed to the third-party ``qpsolvers`` package like the reference does."""
-    try:
-        import qpsolvers
-    except ImportError as exc:  # not in this image
-        raise ImportError("GISA's QP solver needs the `qpsolvers` package, as in the reference") from exc
+    """GISA's quadratic programme  min 1/2 c^T P c + q^T c,  c >= 0,  sum c = pop  (gisa.py:348-421).
+
+    With the third-party ``qpsolvers`` package installed the call is handed to it exactly like the
+    reference does.  The package is not in this image; the programme is strictly convex, hence its
+    minimiser unique, and ``algo.qp.solve_qp_simplex`` (exact active-set method) returns it.
+    ``solver="active-set"`` selects the built-in solver unconditionally."""
     nprim = bs_funcs.shape[0]
     s = alphas[:, None] + alphas[None, :]
     P = 2 / np.pi**1.5 * (alphas[:, None] * alphas[None, :]) ** 1.5 / s**1.5
     P = (P + P.T) / 2
     q = -2 * np.einsum("i,ni,i->n", weights, bs_funcs, rho)
     pop = np.einsum("i,i", weights, rho)
-    result = qpsolvers.solve_qp(
-        P, q, -np.identity(nprim), np.zeros((nprim, 1)), np.ones((1, nprim)), np.ones((1, 1)) * pop,
-        solver=solver, initvals=np.zeros_like(propars), **solver_options,
-    )  # fmt: skip
+    result = None
+    if solver != "active-set":
+        try:
+            import qpsolvers
+        except ImportError:
+            qpsolvers = None
+        if qpsolvers is not None:
+            result = qpsolvers.solve_qp(
+                P, q, -np.identity(nprim), np.zeros((nprim, 1)), np.ones((1, nprim)), np.ones((1, 1)) * pop,
+                solver=solver, initvals=np.zeros_like(propars), **solver_options,
+            )  # fmt: skip
+    if result is None:
+        result = solve_qp_simplex(P, q, float(pop))
+    check_pro_atom_parameters(result, total_population=float(pop))
     return result

@@ -36,7 +36,7 @@ from .core.basis import ExpBasisFuncHelper, shell_norm
 from .core.cache import just_once
 from .core.stockholder import AbstractStockholderWPart
 from .core.logging import deflist
-from .utils import check_pro_atom_parameters, fix_propars
+from .utils import fix_propars
 
 __all__ = ["GlobalLinearISAWPart"]
 

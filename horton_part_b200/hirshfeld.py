@@ -13,7 +13,7 @@ import numpy as np
 from .core.logging import deflist
 from .core.stockholder import AbstractStockholderWPart
 
-__all__ = ["HirshfeldWPart", "check_proatomdb"]
+__all__ = ["HirshfeldWPart", "check_proatomdb", "do_dispersion"]
 
 
 def check_proatomdb(numbers, pseudo_numbers, proatomdb):
@@ -27,8 +27,41 @@ def check_proatomdb(numbers, pseudo_numbers, proatomdb):
             )
 
 
+# C6 coefficients of the isolated atoms in atomic units (Chu & Dalgarno 2004; H: Yan et al. 1996),
+# the reference data of the Tkatchenko-Scheffler rescaling (hirshfeld.py:59-103), by atomic number.
+_REFERENCE_C6 = dict(zip(
+    list(range(1, 39)) + [49, 50, 51, 52, 53],
+    [6.499, 1.42, 1392.0, 227.0, 99.5, 46.6, 24.2, 15.6, 9.52, 6.20, 1518.0, 626.0, 528.0, 305.0, 185.0,
+     134.0, 94.6, 64.2, 3923.0, 2163.0, 1383.0, 1044.0, 832.0, 602.0, 552.0, 482.0, 408.0, 373.0, 253.0,
+     284.0, 498.0, 354.0, 246.0, 210.0, 162.0, 130.0, 4769.0, 3175.0, 779.0, 659.0, 492.0, 445.0, 385.0],
+))  # fmt: skip
+
+
+def do_dispersion(part):
+    """Atoms-in-molecules C6 coefficients by volume rescaling (hirshfeld.py:48-124):
+    V_a = <r^3> of the AIM density (radial moment 3 from ``do_moments``, computed on the device),
+    C6_a = (V_a / V_a^free)^2 C6_a^free; -1 where no free-atom value is tabulated."""
+    if part.lmax < 3:
+        part.logger.warning("Skip computing dispersion coefficients because lmax=%i<3" % part.lmax)
+    volumes, new1 = part._cache.load("volumes", alloc=part.natom, tags="o")
+    volume_ratios, new2 = part._cache.load("volume_ratios", alloc=part.natom, tags="o")
+    c6s, new3 = part._cache.load("c6s", alloc=part.natom, tags="o")
+    if new1 or new2 or new3:
+        part.do_moments()
+        radial_moments = part._cache.load("radial_moments")
+        part.logger.info("Computing atomic dispersion coefficients.")
+        for i in range(part.natom):
+            n = int(part.numbers[i])
+            volumes[i] = radial_moments[i, 3]
+            volume_ratios[i] = volumes[i] / part.proatomdb.get_record(n, 0).get_moment(3)
+            c6s[i] = volume_ratios[i] ** 2 * _REFERENCE_C6[n] if n in _REFERENCE_C6 else -1
+
+
 class DatabaseSplineMixin:
     """Device spline table fed with SciPy PPoly coefficients of database pro-atoms."""
+
+    def do_dispersion(self):
+        do_dispersion(self)
 
     def _setup_spline_table(self):
         from .isa import SplineTable

@@ -45,6 +45,7 @@ _SCHEMES = {
     "gmbis": ("gmbis", "GMBISWPart"),
     "h": ("hirshfeld", "HirshfeldWPart"),
     "hi": ("hirshfeld_i", "HirshfeldIWPart"),
+    "b": ("becke", "BeckeWPart"),
 }
 
 

@@ -152,6 +152,17 @@ HP_API int hp_shell_project(int32_t nshell, const int64_t* shell_point_offsets, 
                      const double* rho, const double* atgrid_w, const double* shell_r,
                      const double* shell_r2w, double* out_sph_avg, void* stream);
 
+/* (row a13 / f3: do_density_decomposition, core/base.py:637-659 with qc-grid
+ * AtomGrid.radial_component_splines)  real-spherical-harmonic components of at_weights*rho on every
+ * radial shell:  out[s*(lmax+1)^2 + lm] = sum_j atgrid_w_j f_j Y_lm(Omega_j) / shell_r2w[s]
+ * (0 where |shell_r| < 1e-8), Y_lm orthonormal, HORTON-2 order (C_l0, C_l1, S_l1, ...), lmax <= 16.
+ * shell_atom[s] = GLOBAL index of the atom that owns shell s (centre = atom_xyz[3*atom..]). */
+HP_API int hp_shell_harmonics(int32_t nshell, int32_t lmax, const int64_t* shell_point_offsets,
+                              const int32_t* shell_atom, const double* px, const double* py,
+                              const double* pz, const double* atom_xyz, const double* at_weights,
+                              const double* rho, const double* atgrid_w, const double* shell_r,
+                              const double* shell_r2w, double* out, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * (rows a9 + a10 change) per-atom radial solves, one warp per atom, all atoms in one launch.
  * Radial data are concatenated over atoms: atom a owns entries rad_offsets[a]..rad_offsets[a+1]

@@ -246,6 +246,9 @@ SOLVER_CASES = {
     "s/lisa_quasi_newton": ("lisa", "s", dict(solver="quasi-newton")),
     "s/lisa_trust_region": ("lisa", "s", dict(solver="trust-region", maxiter=6)),
     "s/lisa_sc_1_iter": ("lisa", "s", dict(solver="sc-1-iter")),
+    # GISA: the reference's qpsolvers call answered by the shim's brute-force KKT enumeration
+    "s/gisa": ("gisa", "s", dict()),
+    "g/gisa": ("gisa", "g", dict()),
     # gLISA solver family (glisa.py:572-1028) on both promolecules
     "g/glisa_diis": ("glisa", "g", dict(solver="diis")),
     "g/glisa_diis_A": ("glisa", "g", dict(solver="diis", solver_options=dict(version="A"))),
@@ -347,8 +350,60 @@ def case_algo():
     print("wrote", GOLD / "algo_host.npz", len(out), "entries")
 
 
+def case_postproc():
+    """Post-processing beyond charges on water HF/STO-3G: Becke scheme
+    (becke.py), density decomposition splines (core/base.py:637-659), pro-atom splines
+    (core/stockholder.py:386-393), Tkatchenko-Scheffler dispersion (hirshfeld.py:48-124)."""
+    import contextlib
+    import io
+
+    from horton_part.core.proatomdb import ProAtomDB
+    from scipy.spatial import cKDTree
+
+    npz = np.load(REF_CACHED / "water_sto3g_hf_g03_fchk_exp:5e-4:2e1:120:110.npz")
+    coords, numbers, pseudo = npz["coordinates"], npz["numbers"], npz["pseudo_numbers"]
+    rgrid = qcgrid.ExpRTransform(5e-4, 2e1, 119).transform_1d_grid(qcgrid.UniformInteger(120))
+    grid = qcgrid.MolGrid.from_size(numbers, coords, 110, rgrid, qcgrid.BeckeWeights(), rotate=False, store=True)
+    _, order = cKDTree(npz["points"]).query(grid.points)
+    rho = npz["dens"][order]
+    out = {}
+    r_mid = np.sqrt(rgrid.points[:-1] * rgrid.points[1:])
+    with contextlib.redirect_stdout(io.StringIO()):
+        part = wpart_schemes("b")(coords, numbers, pseudo, grid, rho)
+        part.do_charges()
+        out["becke/charges"] = part["charges"]
+        out["becke/populations"] = part["populations"]
+        out["becke/at_weights_0_sample"] = part["at_weights_0"][::53].copy()
+        part.do_moments()
+        out["becke/cartesian_multipoles"] = part["cartesian_multipoles"]
+
+        part = wpart_schemes("mbis")(coords, numbers, pseudo, grid, rho)
+        part.do_density_decomposition()
+        for a in range(3):
+            dec = part.cache.load("density_decomposition", a)
+            keys = sorted(dec)
+            out[f"mbis/decomp_{a}_knots"] = np.array([dec[k](rgrid.points) for k in keys])
+            out[f"mbis/decomp_{a}_mid"] = np.array([dec[k](r_mid) for k in keys])
+        part.do_prosplines()
+        for a in range(3):
+            out[f"mbis/prospline_{a}_mid"] = part.cache.load("spline_prodensity", a)(r_mid)
+
+        records, _ = load_proatom_records()
+        part = wpart_schemes("hi")(coords, numbers, pseudo, grid, rho, proatomdb=ProAtomDB(records))
+        part.do_dispersion()
+        for key in ("volumes", "volume_ratios", "c6s", "radial_moments"):
+            out[f"hi/{key}"] = part[key]
+        part.do_prosplines()
+        pts = ProAtomDB(records).get_rgrid(8).points
+        out["hi/prospline_0_mid"] = part.cache.load("spline_prodensity", 0)(np.sqrt(pts[:-1] * pts[1:]))
+    GOLD.mkdir(parents=True, exist_ok=True)
+    np.savez_compressed(GOLD / "h2o_postproc.npz", **out)
+    print("wrote", GOLD / "h2o_postproc.npz", {k: v.shape for k, v in out.items()})
+    print("  becke q", out["becke/charges"], " c6", out["hi/c6s"])
+
+
 CASES = {"h2o": case_h2o, "water6": case_water_cluster, "water6g": case_water_gauss, "hirshfeld": case_hirshfeld,
-         "solvers": case_water6_solvers, "algo": case_algo}
+         "solvers": case_water6_solvers, "algo": case_algo, "postproc": case_postproc}
 
 if __name__ == "__main__":
     for name in sys.argv[1:] or CASES:

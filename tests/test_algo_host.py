@@ -115,3 +115,36 @@ def test_cvxopt_solver_needs_the_package():
     with pytest.raises(ImportError, match="cvxopt"):
         lisa_solvers.solver_cvxopt(np.ones((2, 3)), np.ones(3), np.ones(2), None, np.ones(3), 1e-8,
                                    logging.getLogger("x"), 1e-15, -1e-12, 1e-4)  # fmt: skip
+
+
+def test_active_set_qp_against_brute_force_enumeration():
+    """algo/qp.py against the oracle shim's independent solver (every support set enumerated) on
+    GISA-shaped problems: Gaussian overlap matrices and random SPD matrices."""
+    import sys
+
+    from conftest import ROOT
+
+    sys.path.insert(0, str(ROOT / "oracle" / "qcgrid_shim"))
+    try:
+        import qpsolvers as shim
+    finally:
+        sys.path.pop(0)
+    from horton_part_b200.algo import solve_qp_simplex
+
+    rng = np.random.default_rng(0)
+    for trial in range(60):
+        n = int(rng.integers(2, 8))
+        if trial % 2:
+            a = np.sort(10 ** rng.uniform(-1.5, 2.5, size=n))
+            P = 2 / np.pi**1.5 * (a[:, None] * a[None, :]) ** 1.5 / (a[:, None] + a[None, :]) ** 1.5
+        else:
+            B = rng.normal(size=(n, n))
+            P = B @ B.T + 0.1 * np.eye(n)
+        q = 3 * rng.normal(size=n)
+        total = float(rng.uniform(0.1, 9))
+        x = solve_qp_simplex(P, q, total)
+        ref = shim.solve_qp(P, q, -np.identity(n), np.zeros((n, 1)), np.ones((1, n)), np.ones((1, 1)) * total)
+        assert (x >= 0).all() and abs(x.sum() - total) < 1e-10
+        np.testing.assert_allclose(x, ref, atol=1e-6 * max(1.0, total))
+        cost = lambda y: 0.5 * y @ P @ y + q @ y  # noqa: E731
+        assert cost(x) <= cost(ref) + 1e-9 * max(1.0, abs(cost(ref)))
