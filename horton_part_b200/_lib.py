@@ -43,9 +43,9 @@ EXPORTS = {
     ),
     "hp_promol_weights_local": (
         _int,
-        [_int, _i64, _p, _p, _p, _i64, _i32, _p, _p, _p, _p, _p, _p, _i32, _p, _p, _p, _f64, _f64, _f64, _p, _p, _p, _p, _p, _p],
+        [_int, _i64, _p, _p, _p, _i64, _i32, _p, _p, _p, _p, _p, _p, _i32, _p, _p, _p, _f64, _f64, _f64, _p, _f64, _p, _p, _p, _p, _p],
     ),
-    "hp_shell_screen": (_int, [_i32, _p, _p, _p, _f64, _p, _p]),
+    "hp_shell_screen": (_int, [_i32, _i32, _p, _p, _p, _f64, _p, _p]),
     "hp_shell_project": (_int, [_i32, _p, _p, _p, _p, _p, _p, _p, _p]),
     "hp_shell_harmonics": (_int, [_i32, _i32, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
     "hp_mbis_radial_solve": (

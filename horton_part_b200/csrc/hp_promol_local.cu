@@ -11,6 +11,17 @@
 // last-bit flip is 2^(53-nbits) per evaluation).  The thresholds come from hp_shell_screen.  This is
 // what makes far-away core shells and tight Gaussians free.
 //
+// Atom screening (optional, `atom_eps` > 0, all amplitudes >= 0): atom b is dropped for a whole chunk
+// when an upper bound of its pro-atom there, ub_b = sum_k A_k exp(-alpha_k x_min), is below
+// atom_eps * lb, with lb a lower bound of the promolecule on the chunk: the larger of the owner
+// atom's own pro-atom at the chunk's outer radius and the block minimum of the running sums after
+// the previous tile (the sums only grow).  With atom_eps <= 2^-54 / natom all dropped terms together
+// are below half an ulp of the final sum, i.e. far below the rounding noise a sequential FP64 sum
+// of natom terms carries anyway (~sqrt(natom) ulp).  Measured on config 5 (2,000 atoms, 58.2 M
+// points): 98.5 % of the promolecule values are bit-identical to the unscreened pass, the rest
+// differ by <= 50 ulp (different rounding sequence), charges by 1.8e-15; 47.9 % of the pairs are
+// evaluated.  lb <= 1e-80 disables the test, which keeps the +1e-100 offsets literal.
+//
 // Work skipping happens per block and is conservative; the per-pair test above is exact:
 //   a chunk of consecutive grid points almost always lies on a few radial shells of ONE owner atom,
 //   r_min <= |p - R_o| <= r_max, so atom a can reach it only if
@@ -37,7 +48,7 @@ promol_weights_local_kernel(int64_t npts, const double* __restrict__ px, const d
                             const double* __restrict__ shell_alpha, const double* __restrict__ shell_order,
                             int ntile, const int* __restrict__ tile_off, const double* __restrict__ rho,
                             const double* __restrict__ molw, double density_cutoff, double promol_offset,
-                            double radius, const double* __restrict__ shell_skip,
+                            double radius, const double* __restrict__ shell_skip, double atom_eps,
                             double* __restrict__ promol_out, double* __restrict__ w_out,
                             double* __restrict__ entropy_partials,
                             unsigned long long* __restrict__ pair_partials) {
@@ -50,6 +61,8 @@ promol_weights_local_kernel(int64_t npts, const double* __restrict__ px, const d
     __shared__ int s_wcnt[kTileAtoms / 32];
     __shared__ int s_wsh[kTileAtoms / 32];
     __shared__ int s_ncand;
+    __shared__ double s_wmin[kLocThreads / 32];  // per-warp minimum of the running sums
+    __shared__ double s_lb;                      // owner-based lower bound of the promolecule
 
     const double rc2 = radius * radius;
     const int64_t span = int64_t(kLocThreads) * kLocPts;
@@ -126,6 +139,20 @@ promol_weights_local_kernel(int64_t npts, const double* __restrict__ px, const d
             rmax = s_geom[4];
         }
         const double slack = LOCAL ? 1e-9 * (1.0 + rmax + radius) : 0.0;
+        // shell_skip[nshell_total] is the "negative amplitude seen" flag written by hp_shell_screen
+        const bool screen_atoms = atom_eps > 0.0 && same_owner && F != HP_FUNCTOR_GENERAL && shell_skip &&
+                                  shell_skip[atom_sh_off[natom]] == 0.0;
+        if (screen_atoms) {
+            if (threadIdx.x == 0) {  // the owner's pro-atom at the chunk's outer radius
+                const int o = s_flags[1];
+                const double xo = (F == HP_FUNCTOR_GAUSS) ? rmax * rmax : rmax;
+                double lb = 0.0;
+                for (int k = atom_sh_off[o]; k < atom_sh_off[o + 1]; ++k)
+                    lb += shell_A[k] * exp(-shell_alpha[k] * xo * (1.0 + 1e-9));
+                s_lb = (LOCAL && rmax > radius) ? 0.0 : lb * (1.0 - 1e-9);
+            }
+            if (lane == 0) s_wmin[warp] = 0.0;
+        }
 
         for (int t = 0; t < ntile; ++t) {
             const int a0 = tile_off[t], a1 = tile_off[t + 1];
@@ -151,6 +178,18 @@ promol_weights_local_kernel(int64_t npts, const double* __restrict__ px, const d
                         // conservative lower bound of the chunk's distance to this atom
                         const double dmin = fmax(0.0, fmax(D - rmax, rmin - D) - 1e-9 * (1.0 + rmax + D));
                         xmin = (F == HP_FUNCTOR_GAUSS) ? dmin * dmin : dmin;
+                    }
+                    if (cand && screen_atoms) {
+                        double lb = s_lb;  // written before the barrier at the top of this tile
+                        double run = s_wmin[0];
+                        for (int w = 1; w < kLocThreads / 32; ++w) run = fmin(run, s_wmin[w]);
+                        lb = fmax(lb, run);
+                        if (lb > 1e-80) {
+                            double ub = 0.0;
+                            for (int k = 0; k < rec.ns; ++k)
+                                ub += shell_A[gs0 + k] * exp(-shell_alpha[gs0 + k] * xmin);
+                            cand = !(ub * (1.0 + 1e-9) < atom_eps * lb);
+                        }
                     }
                     if (cand) {
                         nkeep = rec.ns;
@@ -226,6 +265,14 @@ promol_weights_local_kernel(int64_t npts, const double* __restrict__ px, const d
                     if (LOCAL) pro[j] = (d2[j] <= rc2) ? (pro[j] + f[j]) + promol_offset : pro[j];
                     else pro[j] = (pro[j] + f[j]) + promol_offset;
                 }
+            }
+            if (screen_atoms) {  // block minimum of the running sums, consumed by the next tile's setup
+                double lo = 1e300;
+#pragma unroll
+                for (int j = 0; j < kLocPts; ++j) lo = fmin(lo, pro[j]);
+#pragma unroll
+                for (int off = 16; off > 0; off >>= 1) lo = fmin(lo, __shfl_xor_sync(0xffffffffu, lo, off));
+                if (lane == 0) s_wmin[warp] = lo;
             }
         }
 
@@ -315,10 +362,14 @@ __global__ void shell_screen_kernel(int natom, const int* __restrict__ atom_sh_o
     const int s0 = atom_sh_off[a], s1 = atom_sh_off[a + 1];
     int ref = -1;
     bool clean = true;
+    bool nonneg = true;
     for (int k = s0; k < s1; ++k) {
         clean = clean && isfinite(A[k]) && isfinite(alpha[k]) && alpha[k] >= 0.0;
+        nonneg = nonneg && A[k] >= 0.0;
         if (A[k] != 0.0 && (ref < 0 || alpha[k] < alpha[ref])) ref = k;
     }
+    // skip[nshell_total] != 0: some amplitude is negative / not finite, atom screening must stay off
+    if (!(clean && nonneg)) skip[atom_sh_off[natom]] = 1.0;
     const double inf = __longlong_as_double(0x7ff0000000000000ll);
     for (int k = s0; k < s1; ++k) {
         double t = inf;
@@ -340,11 +391,14 @@ __global__ void shell_screen_kernel(int natom, const int* __restrict__ atom_sh_o
 
 using namespace hp;
 
-extern "C" int hp_shell_screen(int32_t natom, const int32_t* atom_shell_offsets, const double* shell_A,
-                               const double* shell_alpha, double nbits, double* shell_skip,
-                               void* stream) {
-    HP_REQUIRE(natom > 0 && atom_shell_offsets && shell_A && shell_alpha && shell_skip, "bad arguments");
+extern "C" int hp_shell_screen(int32_t natom, int32_t nshell, const int32_t* atom_shell_offsets,
+                               const double* shell_A, const double* shell_alpha, double nbits,
+                               double* shell_skip, void* stream) {
+    HP_REQUIRE(natom > 0 && nshell >= 0 && atom_shell_offsets && shell_A && shell_alpha && shell_skip,
+               "bad arguments");
     HP_REQUIRE(nbits >= 60.0, "nbits must be >= 60");
+    int rc = check_cuda(cudaMemsetAsync(shell_skip + nshell, 0, sizeof(double), as_stream(stream)), "memset");
+    if (rc) return rc;
     shell_screen_kernel<<<(natom + 127) / 128, 128, 0, as_stream(stream)>>>(natom, atom_shell_offsets, shell_A,
                                                                             shell_alpha, nbits, shell_skip);
     HP_LAUNCH_CHECK("shell_screen_kernel");
@@ -359,7 +413,8 @@ extern "C" int hp_promol_weights_local(int functor, int64_t npts, const double* 
                                        int32_t ntile, const int32_t* tile_atom_offsets,
                                        const double* rho, const double* molw, double density_cutoff,
                                        double promol_offset, double radius, const double* shell_skip,
-                                       double* promol, double* at_weights, double* entropy_partials,
+                                       double atom_eps, double* promol, double* at_weights,
+                                       double* entropy_partials,
                                        uint64_t* pair_partials, void* stream) {
     HP_REQUIRE(npts >= 0 && natom > 0 && ntile > 0, "bad sizes");
     HP_REQUIRE(px && py && pz && atom_xyz && atom_point_offsets && atom_shell_offsets, "null input");
@@ -367,6 +422,7 @@ extern "C" int hp_promol_weights_local(int functor, int64_t npts, const double* 
     HP_REQUIRE(functor != HP_FUNCTOR_GENERAL || shell_order, "general functor needs shell_order");
     HP_REQUIRE(!entropy_partials || (rho && molw), "entropy needs rho and molw");
     HP_REQUIRE(radius >= 0.0, "negative radius (use +inf for the dense pass)");
+    HP_REQUIRE(atom_eps >= 0.0 && atom_eps < 1e-9, "atom_eps must be in [0, 1e-9)");
     cudaStream_t st = as_stream(stream);
     if (npts == 0) {
         if (entropy_partials) {
@@ -386,7 +442,7 @@ extern "C" int hp_promol_weights_local(int functor, int64_t npts, const double* 
 #define HP_LOC_ARGS                                                                                      \
     npts, px, py, pz, point_base, natom, atom_xyz, atom_point_offsets, atom_shell_offsets, shell_A,      \
         shell_alpha, shell_order, ntile, tile_atom_offsets, rho, molw, density_cutoff, promol_offset,    \
-        radius, shell_skip, promol, at_weights, entropy_partials,                                        \
+        radius, shell_skip, atom_eps, promol, at_weights, entropy_partials,                              \
         reinterpret_cast<unsigned long long*>(pair_partials)
 #define HP_LOC(F)                                                                                        \
     if (local) promol_weights_local_kernel<F, true><<<int(grid), kLocThreads, 0, st>>>(HP_LOC_ARGS);     \

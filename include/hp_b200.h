@@ -128,9 +128,17 @@ HP_API int hp_promol_weights(int functor, int64_t npts, const double* px, const 
  * shell_skip (may be NULL; SLATER/GAUSS functors): per-shell thresholds from hp_shell_screen; a shell
  * is dropped for a chunk of points when the chunk's minimum distance to the atom (r, or r^2 for
  * Gaussians) exceeds its threshold, i.e. when it is below 2^-nbits of the atom's most diffuse shell
- * and cannot change the FP64 pro-atom sum. */
-HP_API int hp_shell_screen(int32_t natom, const int32_t* atom_shell_offsets, const double* shell_A,
-                           const double* shell_alpha, double nbits, double* shell_skip, void* stream);
+ * and cannot change the FP64 pro-atom sum.  shell_skip holds nshell + 1 doubles: the last one is a
+ * flag hp_shell_screen sets to 1 when any amplitude is negative or not finite (nshell = total number
+ * of shells = atom_shell_offsets[natom]).
+ * atom_eps > 0 (needs shell_skip, all amplitudes >= 0, SLATER/GAUSS): atom b is dropped for a chunk
+ * when an upper bound of its pro-atom there is below atom_eps times a lower bound of the promolecule
+ * (the owner's pro-atom at the chunk's outer radius, or the block minimum of the running sums).
+ * With atom_eps <= 2^-54/natom the dropped terms together are below half an ulp of the sum, far
+ * below the rounding noise of a sequential FP64 sum of natom terms; 0 disables the test. */
+HP_API int hp_shell_screen(int32_t natom, int32_t nshell, const int32_t* atom_shell_offsets,
+                           const double* shell_A, const double* shell_alpha, double nbits,
+                           double* shell_skip, void* stream);
 HP_API int hp_promol_weights_local(int functor, int64_t npts, const double* px, const double* py,
                                    const double* pz, int64_t point_base, int32_t natom,
                                    const double* atom_xyz, const int64_t* atom_point_offsets,
@@ -139,8 +147,8 @@ HP_API int hp_promol_weights_local(int functor, int64_t npts, const double* px, 
                                    int32_t ntile, const int32_t* tile_atom_offsets,
                                    const double* rho, const double* molw, double density_cutoff,
                                    double promol_offset, double radius, const double* shell_skip,
-                                   double* promol, double* at_weights, double* entropy_partials,
-                                   uint64_t* pair_partials, void* stream);
+                                   double atom_eps, double* promol, double* at_weights,
+                                   double* entropy_partials, uint64_t* pair_partials, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * (row a8) spherical average of w_a*rho over each radial shell of each atom's own atomic grid.

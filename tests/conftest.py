@@ -54,7 +54,9 @@ def _water_case(gridmod, natom, nrad, nang, seed=0, gold=None):
 
     coords, numbers = synthetic.water_cluster(natom, seed)
     rgrid = gridmod.BeckeRTransform(1e-4, 1.5).transform_1d_grid(gridmod.GaussChebyshev(nrad))
-    grid = gridmod.MolGrid.from_size(numbers, coords, nang, rgrid, gridmod.BeckeWeights(), store=True)
+    # the host Becke weights are O(natom^2 Npts) NumPy: beyond a few dozen atoms use the device kernel
+    becke = gridmod.DeviceBeckeWeights() if natom > 24 and hasattr(gridmod, "DeviceBeckeWeights") else gridmod.BeckeWeights()
+    grid = gridmod.MolGrid.from_size(numbers, coords, nang, rgrid, becke, store=True)
     rho = synthetic.slater_promolecule_host(grid.points, coords, numbers)
     return dict(coords=coords, numbers=numbers, pseudo=numbers.astype(float), grid=grid, rho=rho, gold=gold)
 
