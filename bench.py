@@ -4,8 +4,11 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--natom 2000] [--impl reference]
 
 Workload (config 5 of BASELINE.json): MBIS on a synthetic 2,000-atom water cluster, 150 x 194 grid
-per atom = 58.2 M points, dense all-pairs pro-atom evaluation (the reference's semantics: no
-cut-off), 1.164e11 atom x gridpoint evaluations per stockholder iteration.  A *step* is one outer
+per atom = 58.2 M points, dense all-pairs semantics (the reference's: no cut-off), 1.164e11
+atom x gridpoint pairs per stockholder iteration.  The kernel drops pairs that provably cannot
+change the FP64 promolecule (atom / shell screening); `value` counts the job's
+pairs per second, the roofline block reports the work actually executed, and `unscreened` holds
+the same steps with every pair evaluated.  A *step* is one outer
 iteration: shell table -> fused promolecule/weights/entropy kernel -> spherical averages ->
 per-atom MBIS solves -> change/entropy -> one small D2H.  Strong scaling: the same system is
 sharded by atom blocks over the ranks (NCCL all-reduce of the per-iteration state vector).
@@ -204,7 +207,7 @@ def run_reference_arm(args, rank, world):
 def workload_config(natom, numbers):
     return {
         "workload": f"MBIS, synthetic {natom}-atom water cluster, {NRAD}x{NANG} grid/atom, "
-                    f"{natom * NRAD * NANG} points, dense all-pairs (no cut-off), grid_type=1",
+                    f"{natom * NRAD * NANG} points, dense all-pairs semantics (no cut-off), grid_type=1",
         "natom": int(natom), "npts": int(natom * NRAD * NANG),
         "evals_per_step": float(natom) * natom * NRAD * NANG,
         "mean_shells_per_atom": mean_shells(numbers),
@@ -223,6 +226,9 @@ def main():
     ap.add_argument("--cpu-points", type=int, default=16384, help="grid points per core in the CPU sample")
     ap.add_argument("--cpu-reps", type=int, default=16, help="passes over the CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-unscreened", action="store_true", help="skip the extra run with atom screening off")
+    ap.add_argument("--pinned-inputs", action="store_true",
+                    help="keep the host input arrays of the end-to-end arm in page-locked memory")
     ap.add_argument("--local-radius", type=float, default=16.0,
                     help="cut-off radius (bohr) of the extra local-grid measurement; 0 disables it")
     args = ap.parse_args()
@@ -311,6 +317,40 @@ def main():
     state_bytes = part._state.host.numel() * 8
     del part
     torch.cuda.empty_cache()
+    if pairs_local is not None and comm is not None:
+        tp = torch.tensor([float(pairs_local), float(shells_local)], dtype=torch.float64, device=dev)
+        dist.all_reduce(tp)
+        pairs_job, shells_job = float(tp[0].item()), float(tp[1].item())
+    else:
+        pairs_job = float(pairs_local) if pairs_local is not None else evals_per_step
+        shells_job = float(shells_local) if shells_local is not None else evals_per_step * mean_shells(numbers)
+
+    # ---- extra: the same steps with atom screening off (every pair evaluated) -------------------
+    unscreened = None
+    if not args.no_unscreened:
+        os.environ["HP_B200_ATOM_SCREEN"] = "0"
+        part_u = MBISWPart(coords, numbers, pseudo, grid, rho, device=dev, comm=comm, maxiter=nsteps)
+        part_u._init_propars()
+        for _ in range(args.warmup):
+            part_u._run_iteration()
+        part_u._state.events = []
+        barrier()
+        u0, u1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        u0.record()
+        for _ in range(args.steps):
+            part_u._run_iteration()
+        u1.record()
+        barrier()
+        ms_u = max_over_ranks(u0.elapsed_time(u1))
+        k_u = max_over_ranks(float(np.mean([ev[0].elapsed_time(ev[1]) for ev in part_u._state.events])))
+        unscreened = {
+            "ms_per_step": ms_u / args.steps, "evals_per_s": evals_per_step * args.steps / (ms_u * 1e-3),
+            "kernel_ms": k_u,
+            "max_abs_charge_diff_vs_screened": float(np.abs(part_u["charges"] - charges_resident).max()),
+        }
+        del part_u
+        os.environ.pop("HP_B200_ATOM_SCREEN", None)
+        torch.cuda.empty_cache()
 
     # ---- extra: the same iterations in cut-off (local grid) mode, credited for evaluated pairs only
     cutoff = None
@@ -344,23 +384,47 @@ def main():
         torch.cuda.empty_cache()
 
     # ---- end-to-end arm: host buffers -> WPart API -> host results, copies inside the timed region
-    barrier()
-    t0 = time.perf_counter()
-    part2 = MBISWPart(coords, numbers, pseudo, grid, rho, device=dev, comm=comm, maxiter=args.steps)
-    part2.do_partitioning()  # uploads, K iterations, downloads weights/promolecule/charges
-    barrier()
-    e2e_s = max_over_ranks(time.perf_counter() - t0)
-    assert part2["niter"] == args.steps
+    from horton_part_b200.core import hostmem
+
+    if args.pinned_inputs:  # the caller's arrays page-locked from the start (hostmem.pinned_empty)
+        for name in ("points", "weights"):
+            arr = getattr(grid, name)
+            pin = hostmem.pinned_empty(arr.shape, arr.dtype)
+            pin[...] = arr
+            setattr(grid, name, pin)
+        pin = hostmem.pinned_empty(grid.atweights.shape)
+        pin[...] = grid.atweights
+        grid.atweights = pin
+        pin = hostmem.pinned_empty(rho.shape)
+        pin[...] = rho
+        rho = pin
+    e2e_runs = []
+    for rep in range(2):  # first pass = warm-up (page-locked staging / result buffers get allocated)
+        barrier()
+        t0 = time.perf_counter()
+        part2 = MBISWPart(coords, numbers, pseudo, grid, rho, device=dev, comm=comm, maxiter=args.steps)
+        part2.do_partitioning()  # uploads, K iterations, downloads weights/promolecule/charges
+        barrier()
+        e2e_runs.append(max_over_ranks(time.perf_counter() - t0))
+        assert part2["niter"] == args.steps
+        d2h_final = (2 * (hi - lo) + part2.slab.nshell) * 8
+        e2e_charges = part2["charges"].copy()
+        del part2
+    e2e_s = e2e_runs[-1]
     e2e_value = evals_per_step * args.steps / e2e_s
-    d2h_final = (2 * (hi - lo) + part2.slab.nshell) * 8
     e2e = {
         "value": e2e_value, "unit": UNIT,
         "h2d_bytes_per_step": int(h2d_bytes / args.steps),
         "d2h_bytes_per_step": int(state_bytes + d2h_final / args.steps),
-        "seconds": e2e_s, "includes": "slab upload (pageable host memory), K iterations, download of "
-        "promolecule/at_weights/spherical averages, per-step state D2H",
+        "seconds": e2e_s, "seconds_first_call": e2e_runs[0],
+        "host_inputs": "page-locked NumPy arrays" if args.pinned_inputs else
+        "pageable NumPy arrays, pipelined through page-locked staging by hp_host_to_device",
+        "includes": "MBISWPart(...).do_partitioning() from host arrays: slab upload, K iterations with per-step "
+        "state D2H, download of promolecule / at_weights / spherical averages into page-locked result arrays; "
+        "second call in the process (the first one also allocates the page-locked buffers)",
+        "max_abs_charge_diff_vs_resident_arm": float(np.abs(e2e_charges - charges_resident).max()),
+        "hostmem": hostmem.pool_stats(),
     }  # fmt: skip
-    del part2
 
     # ---- roofline denominators -------------------------------------------------------------------
     kbar = mean_shells(numbers)
@@ -371,8 +435,10 @@ def main():
     _lib.call("hp_dfma_probe", 4096, sink, ms_probe, fl_probe, torch.cuda.current_stream(dev).cuda_stream)
     fp64_peak_tflops = float(fl_probe[0] / (ms_probe[0] * 1e-3) / 1e12)
     local_evals = float(natom) * float(hi - lo)
-    kernel_evals_per_s = local_evals / (kernel_ms_mean * 1e-3)
-    achieved_tflops = kernel_evals_per_s * F / 1e12
+    kernel_evals_per_s = local_evals / (kernel_ms_mean * 1e-3)  # job pairs of this rank per second
+    executed_local = 16.0 * float(pairs_local if pairs_local is not None else local_evals) + 36.0 * float(
+        shells_local if shells_local is not None else local_evals * kbar)
+    achieved_tflops = executed_local / (kernel_ms_mean * 1e-3) / 1e12
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -386,23 +452,29 @@ def main():
         "achieved": achieved_tflops, "peak": fp64_peak_tflops, "unit": "TFLOP/s",
         "frac": achieved_tflops / fp64_peak_tflops,
         "peak_source": "hp_dfma_probe measured live on this GPU (nominal 148 SM x 64 lanes x 2 x 1.965 GHz = 37.2)",
+        "work_counted": "executed: 16 flop per evaluated atom x point pair + 36 per evaluated shell (in-kernel counters); "
+                        "SURVEY 8d convention, cut-off rule: only evaluated pairs are credited",
         "flop_per_eval": F, "kernel_ms": kernel_ms_mean, "kernel_evals_per_s": kernel_evals_per_s,
         "kernel_share_of_step": kernel_ms_mean / (ms_total / args.steps),
         "hbm_gbs_achieved": hbm_bytes / (kernel_ms_mean * 1e-3) / 1e9, "hbm_gbs_peak": hbm_peak,
+        "hbm_bytes_algorithmic": hbm_bytes,
         "hbm_peak_source": "MEASURED_PEAKS.json" if peaks else "fallback 6650",
         "traffic": 0.968 * hbm_bytes,
         "traffic_source": "dram__bytes_read+write of the ncu --set full capture (profiles/r1_promol_weights_ncu_full.txt: "
                           "947 MB vs 978 MB algorithmic at 600 atoms) scaled to this launch",
     }  # fmt: skip
     if shells_local is not None:
-        # shell screening drops shells that cannot change the FP64 sum: also report the roofline
-        # fraction for the work actually executed (16 flop per pair + 36 per evaluated shell)
-        executed = (16.0 * pairs_local + 36.0 * shells_local) / (kernel_ms_mean * 1e-3) / 1e12
+        dense_equiv = kernel_evals_per_s * F / 1e12
         roofline.update({
             "shell_screening": "shells below 2^-100 of the atom's most diffuse shell over a whole chunk are skipped",
-            "shells_evaluated_per_pair": shells_local / pairs_local, "achieved_executed": executed,
-            "frac_executed": executed / fp64_peak_tflops,
+            "atom_screening": "atoms whose pro-atom bound is below 2^-(55+log2 natom) of the chunk's promolecule lower bound are skipped",
+            "pairs_evaluated_fraction": pairs_job / evals_per_step,
+            "shells_evaluated_per_pair": shells_job / pairs_job,
+            "achieved_dense_equivalent": dense_equiv, "frac_dense_equivalent": dense_equiv / fp64_peak_tflops,
         })
+        if unscreened is not None:
+            un = local_evals * F / (unscreened["kernel_ms"] * 1e-3) / 1e12
+            unscreened.update({"achieved_algorithmic": un, "frac_algorithmic": un / fp64_peak_tflops})
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -416,7 +488,7 @@ def main():
         "other_kernels_ms_per_step": float(np.mean(rest_ms)),
         "last_change": change, "last_entropy": entropy,
         "charges_O_H_H": [float(x) for x in charges_resident[:3]],
-        "cutoff_mode": cutoff,
+        "cutoff_mode": cutoff, "unscreened": unscreened,
     }  # fmt: skip
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(coords, numbers, grid, os.cpu_count() or 1, points_per_core=args.cpu_points, reps=args.cpu_reps)

@@ -92,13 +92,15 @@ EXPORTS = {
     "hp_segment_integrate": (_int, [_i32, _p, _p, _p, _p, _p, _p]),
     "hp_atom_moments": (_int, [_i32, _i32, _i32, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
     "hp_becke_weights": (_int, [_i64, _p, _p, _p, _i64, _i32, _p, _p, _p, _p, _i32, _p, _p]),
+    "hp_host_is_pinned": (_int, [_p]),
+    "hp_host_to_device": (_int, [_p, _p, _sz, _p, _sz, _i32, _p]),
     "hp_dfma_probe": (_int, [_i32, _p, _p, _p, _p]),
 }
 
 
 # int-returning functions whose result is a value, not a status code
 _NOT_STATUS = {"hp_abi_version", "hp_num_partials", "hp_local_index_scratch_bytes", "hp_last_error", "hp_tile_limits", "hp_molgrid_num_blocks", "hp_hessian_scratch_bytes",
-               "hp_molgrid_update_tile_limits"}
+               "hp_molgrid_update_tile_limits", "hp_host_is_pinned"}
 
 
 class HpError(RuntimeError):

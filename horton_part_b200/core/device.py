@@ -100,8 +100,10 @@ class GridSlab:
             raise ValueError("grid.points must have shape (Npts, 3)")
         self.bytes_h2d = 0
 
+        from .hostmem import upload
+
         def up(a, dtype=np.float64):
-            t = to_device(a, dev, dtype)
+            t = upload(a, dev, dtype)  # pipelined through page-locked staging when `a` is pageable
             self.bytes_h2d += t.numel() * t.element_size()
             return t
 

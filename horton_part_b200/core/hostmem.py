@@ -1,0 +1,121 @@
+"""Host-side buffers of the device path: page-locked staging, uploads from NumPy arrays, downloads
+into pooled page-locked arrays.
+
+The class API takes and returns NumPy arrays (pageable memory).  At config 5 the slab is 2.8 GB up
+and 0.93 GB down per job, so how those bytes move decides the end-to-end rate:
+
+* ``upload``      NumPy -> device.  Page-locked sources (``pinned_empty``) go out as one async copy;
+                  pageable sources are pipelined through a pooled page-locked staging buffer by
+                  ``hp_host_to_device`` (multi-threaded memcpy overlapped with the DMA).
+* ``download``    device -> a pooled page-locked buffer, returned as a NumPy array without a second
+                  copy.  The pool re-issues a buffer only when nothing refers to it any more.
+* ``pinned_empty``  for callers who want their input arrays page-locked from the start.
+"""
+
+from __future__ import annotations
+
+import os
+
+import numpy as np
+
+from .. import _lib
+
+__all__ = ["pinned_empty", "is_pinned", "upload", "download", "pool_stats"]
+
+_STAGING_BYTES = 128 << 20
+_staging = None
+_pool = []  # page-locked uint8 tensors handed out by download()
+_stats = {"pinned_allocs": 0, "pinned_reuses": 0, "staged_uploads": 0, "direct_uploads": 0}
+
+
+def _threads():
+    return max(1, min(16, (os.cpu_count() or 2) // 2))
+
+
+def pinned_empty(shape, dtype=np.float64):
+    """Uninitialised page-locked NumPy array (owned by a torch tensor kept alive through
+    ``ndarray.base``): uploads from it run at PCIe speed."""
+    import torch
+
+    dtype = np.dtype(dtype)
+    n = int(np.prod(shape)) * dtype.itemsize
+    buf = torch.empty(max(n, 1), dtype=torch.uint8, pin_memory=True)
+    return buf.numpy()[:n].view(dtype).reshape(shape)
+
+
+def is_pinned(array) -> bool:
+    return bool(_lib.call("hp_host_is_pinned", int(array.ctypes.data)))
+
+
+def _staging_buffer():
+    global _staging
+    if _staging is None:
+        import torch
+
+        _staging = torch.empty(_STAGING_BYTES, dtype=torch.uint8, pin_memory=True)
+    return _staging
+
+
+def upload(array, device, dtype=None):
+    """Device tensor holding a copy of ``array`` (C-contiguous, optionally converted to ``dtype``)."""
+    import torch
+
+    a = np.ascontiguousarray(array, dtype=dtype)
+    src = torch.from_numpy(a)
+    nbytes = a.nbytes
+    if nbytes < (8 << 20):
+        return src.to(device)
+    out = torch.empty(src.shape, dtype=src.dtype, device=device)
+    stream = torch.cuda.current_stream(device).cuda_stream
+    if is_pinned(a):
+        _stats["direct_uploads"] += 1
+        _lib.call("hp_host_to_device", out, int(a.ctypes.data), nbytes, None, 0, 1, stream)
+        out._hp_source = src  # keep the page-locked source alive until the async copy is consumed
+        return out
+    stage = _staging_buffer()
+    _stats["staged_uploads"] += 1
+    _lib.call("hp_host_to_device", out, int(a.ctypes.data), nbytes, stage, stage.numel(), _threads(), stream)
+    return out
+
+
+def _take(nbytes):
+    """Pool entry [buffer, weakref-to-the-array-handed-out] whose array is gone (or a new one)."""
+    import torch
+
+    for entry in _pool:
+        buf, ref = entry
+        if ref is not None and ref() is not None:
+            continue  # the array (or a view of it: views keep their base alive) is still in use
+        if nbytes <= buf.numel() <= 2 * nbytes + 4096:
+            _stats["pinned_reuses"] += 1
+            return entry
+    _pool[:] = [e for e in _pool if e[1] is not None and e[1]() is not None][-16:]  # drop idle misfits
+    entry = [torch.empty(max(nbytes, 1), dtype=torch.uint8, pin_memory=True), None]
+    _stats["pinned_allocs"] += 1
+    _pool.append(entry)
+    return entry
+
+
+def download(tensor):
+    """NumPy array with the contents of a device tensor.  Large tensors land in a pooled page-locked
+    buffer (no second copy).  The buffer is re-issued only after the returned array and every view
+    of it have been garbage-collected."""
+    import weakref
+
+    import torch
+
+    t = tensor.contiguous()
+    nbytes = t.numel() * t.element_size()
+    if nbytes < (8 << 20):
+        return t.cpu().numpy()
+    entry = _take(nbytes)
+    host = entry[0][:nbytes].view(t.dtype).reshape(t.shape)
+    host.copy_(t, non_blocking=True)
+    torch.cuda.current_stream(t.device).synchronize()
+    array = host.numpy()
+    entry[1] = weakref.ref(array)
+    return array
+
+
+def pool_stats():
+    return dict(_stats, pool_buffers=len(_pool), pool_bytes=sum(e[0].numel() for e in _pool))

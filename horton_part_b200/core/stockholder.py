@@ -82,15 +82,17 @@ class AbstractStockholderWPart(WPart):
     def _publish_weights(self):
         """Download promolecule and owner weights of this rank's slab into the cache: one D2H copy
         each; the per-atom ``at_weights_{a}`` entries are views into the downloaded array."""
+        from .hostmem import download
+
         slab = self.slab
         lo = slab.point_base
-        promol_h = slab.promol.cpu().numpy()
+        promol_h = download(slab.promol)
         if slab.npts == self.grid.size:
             self.cache.dump("promoldens", promol_h)
         else:  # sharded: only this rank's slice is known
             promol = self.cache.load("promoldens", alloc=self.grid.size)[0]
             promol[lo : lo + slab.npts] = promol_h
-        at_w = slab.at_w.cpu().numpy()
+        at_w = download(slab.at_w)
         off = slab.atom_point_offsets_host
         for a in range(slab.shard.atom_lo, slab.shard.atom_hi):
             self.cache.dump(f"at_weights_{a}", at_w[off[a] - lo : off[a + 1] - lo])

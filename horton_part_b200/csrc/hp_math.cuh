@@ -34,6 +34,17 @@ __device__ __forceinline__ double sqrt_nocall(double d2) {
     return (__double2hiint(d2) < 0x00100000) ? 0.0 : r;
 }
 
+// Same seed, two Heron steps with the seed's y/2 as the (approximate) reciprocal: errors 2^-20 ->
+// 2^-40 -> 2^-60 before the final rounding = 1 DMUL + 4 DFMA.  Only for d2 in the normal range
+// (callers guarantee a non-zero distance): no zero/denormal guard.
+__device__ __forceinline__ double sqrt_fast(double d2) {
+    const double y = rsqrt_seed(d2);
+    const double h = __hiloint2double(__double2hiint(y) - 0x00100000, __double2loint(y));  // y/2
+    double g = d2 * y;
+    g = fma(fma(-g, g, d2), h, g);
+    return fma(fma(-g, g, d2), h, g);
+}
+
 // x <= -708 (or a negative NaN): results at or below 3.4e-308 are flushed to exactly 0.  Such
 // terms are absorbed by the reference's own +1e-100 offsets, so promolecule sums are unchanged;
 // the absolute error of a single pro-atom value is < 3.4e-308.
@@ -42,6 +53,8 @@ __device__ __forceinline__ bool exp_arg_tiny(double x) {
 }
 
 // exp(x) for x <= 0, branch-free: Cody-Waite reduction by ln2, degree-11 polynomial (16 FP64 ops).
+// GUARD=false drops the underflow guard: only for -700 < x <= 0.
+template <bool GUARD = true>
 __device__ __forceinline__ double exp_neg_poly(double x) {
     const double t = fma(x, 1.4426950408889634, 6755399441055744.0);
     const int k = __double2loint(t);
@@ -53,6 +66,7 @@ __device__ __forceinline__ double exp_neg_poly(double x) {
     for (int i = 8; i >= 0; --i) g = fma(g, r, c_expg[i]);
     double p = fma(g, r, 1.0);
     p = fma(p, r, 1.0);
+    if (!GUARD) return __hiloint2double(__double2hiint(p) + (k << 20), __double2loint(p));
     const bool tiny = exp_arg_tiny(x);
     const int hi = tiny ? 0 : __double2hiint(p) + (k << 20);
     const int lo = tiny ? 0 : __double2loint(p);

@@ -159,10 +159,10 @@ promol_weights_local_kernel(int64_t npts, const double* __restrict__ px, const d
             __syncthreads();  // previous tile fully consumed
             // ---- ordered compaction of the atoms that can reach this chunk -----------------------
             AtomRec rec;
-            bool cand = false;
+            bool cand = false, fast = false;
             unsigned m = 0;
             int nkeep = 0, shell_incl = 0, gs0 = 0;
-            double xmin = 0.0;
+            double xmin = 0.0, xmax = 0.0;
             if (threadIdx.x < kTileAtoms) {  // warps 0..3, warp-uniform
                 const int i = threadIdx.x;
                 if (i < a1 - a0) {
@@ -178,6 +178,8 @@ promol_weights_local_kernel(int64_t npts, const double* __restrict__ px, const d
                         // conservative lower bound of the chunk's distance to this atom
                         const double dmin = fmax(0.0, fmax(D - rmax, rmin - D) - 1e-9 * (1.0 + rmax + D));
                         xmin = (F == HP_FUNCTOR_GAUSS) ? dmin * dmin : dmin;
+                        const double dmax = (D + rmax) * (1.0 + 1e-9);
+                        xmax = (F == HP_FUNCTOR_GAUSS) ? dmax * dmax : dmax;
                     }
                     if (cand && screen_atoms) {
                         double lb = s_lb;  // written before the barrier at the top of this tile
@@ -193,10 +195,20 @@ promol_weights_local_kernel(int64_t npts, const double* __restrict__ px, const d
                     }
                     if (cand) {
                         nkeep = rec.ns;
+                        double amax = 0.0;  // largest exponent among the shells that are evaluated
                         if (shell_skip && F != HP_FUNCTOR_GENERAL) {
                             nkeep = 0;
-                            for (int k = 0; k < rec.ns; ++k) nkeep += !(xmin > shell_skip[gs0 + k]);
+                            for (int k = 0; k < rec.ns; ++k) {
+                                const bool keep = !(xmin > shell_skip[gs0 + k]);
+                                nkeep += keep;
+                                if (keep) amax = fmax(amax, shell_alpha[gs0 + k]);
+                            }
+                        } else if (F != HP_FUNCTOR_GENERAL) {
+                            for (int k = 0; k < rec.ns; ++k) amax = fmax(amax, shell_alpha[gs0 + k]);
                         }
+                        // guards can go when no point of the chunk can sit on this nucleus and no
+                        // exponent argument can reach the underflow range
+                        if (same_owner && F != HP_FUNCTOR_GENERAL) fast = xmin > 1e-100 && amax * xmax < 700.0;
                     }
                 }
                 m = __ballot_sync(0xffffffffu, cand);
@@ -219,7 +231,7 @@ promol_weights_local_kernel(int64_t npts, const double* __restrict__ px, const d
                 }
                 if (cand) {
                     int dst = shoff + shell_incl - nkeep;
-                    rec.s0 = dst;
+                    rec.s0 = fast ? dst : (dst | int(0x80000000));  // sign bit = guarded evaluation
                     const bool screen = shell_skip && F != HP_FUNCTOR_GENERAL;
                     for (int k = 0; k < rec.ns; ++k) {
                         if (screen && xmin > shell_skip[gs0 + k]) continue;
@@ -242,24 +254,27 @@ promol_weights_local_kernel(int64_t npts, const double* __restrict__ px, const d
             const int ncand = s_ncand;
             pairs += static_cast<unsigned long long>(ncand) * nlive;
             if (pair_partials) {  // kept shells of this tile = s0 + ns of its last candidate
-                const int kept = ncand ? s_atoms[ncand - 1].s0 + s_atoms[ncand - 1].ns : 0;
+                const int kept = ncand ? (s_atoms[ncand - 1].s0 & 0x7fffffff) + s_atoms[ncand - 1].ns : 0;
                 shells += static_cast<unsigned long long>(kept) * nlive;
             }
 
             AtomRec nxt = s_atoms[0];
-            double2 nxt_ab = s_AB[nxt.s0];
+            double2 nxt_ab = s_AB[nxt.s0 & 0x7fffffff];
             for (int i = 0; i < ncand; ++i) {
                 const AtomRec ar = nxt;
                 const double2 ab0 = nxt_ab;
                 nxt = s_atoms[i + 1];  // entry [ncand] is a sentinel
-                nxt_ab = s_AB[nxt.s0];
+                nxt_ab = s_AB[nxt.s0 & 0x7fffffff];
                 double d2[kLocPts], f[kLocPts];
 #pragma unroll
                 for (int j = 0; j < kLocPts; ++j) {
                     const double dx = x[j] - ar.x, dy = y[j] - ar.y, dz = z[j] - ar.z;
                     d2[j] = LOCAL ? dist2_unfused3(dx, dy, dz) : fma(dz, dz, fma(dy, dy, dx * dx));
                 }
-                eval_proatom<F, kLocPts>(d2, ar.s0, ar.ns, s_AB, s_N, f, ab0);
+                // block-uniform branch: zero-distance / underflow guards dropped where the chunk
+                // geometry rules both out
+                if (ar.s0 >= 0) eval_proatom<F, kLocPts, true>(d2, ar.s0, ar.ns, s_AB, s_N, f, ab0);
+                else eval_proatom<F, kLocPts>(d2, ar.s0 & 0x7fffffff, ar.ns, s_AB, s_N, f, ab0);
 #pragma unroll
                 for (int j = 0; j < kLocPts; ++j) {
                     if (LOCAL) pro[j] = (d2[j] <= rc2) ? (pro[j] + f[j]) + promol_offset : pro[j];

@@ -356,6 +356,17 @@ HP_API int hp_becke_weights(int64_t npts, const double* px, const double* py, co
                             const int64_t* atom_point_offsets, const double* inv_rab, const double* aab,
                             int32_t order, double* out, void* stream);
 
+/* Slab upload helpers (the boundary takes NumPy arrays = pageable host memory; the reference never
+ * leaves the host, core/base.py:416-431 keeps `grid.points`, `grid.weights`, `moldens` as given).
+ * hp_host_is_pinned: 1 if the host pointer is page-locked (registered with CUDA), else 0.
+ * hp_host_to_device: copy `bytes` from host to device on `stream`.  Page-locked sources go out as one
+ * asynchronous copy.  Pageable sources are pipelined through the caller's page-locked `staging`
+ * buffer (two halves; `nthreads` host threads fill one half while the DMA engine drains the other)
+ * and the call returns when the last chunk has left the staging buffer. */
+HP_API int hp_host_is_pinned(const void* host_ptr);
+HP_API int hp_host_to_device(void* dst_dev, const void* src_host, size_t bytes, void* staging,
+                             size_t staging_bytes, int32_t nthreads, void* stream);
+
 /* FP64 FMA throughput probe used by bench.py for the roofline denominator: runs `iters` dependent
  * DFMA chains (8 independent per thread) on a full grid; returns elapsed ms in *ms_host and the
  * flop count in *flops_host.  Synchronises the stream. */
