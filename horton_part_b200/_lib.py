@@ -43,8 +43,11 @@ EXPORTS = {
     ),
     "hp_promol_weights_local": (
         _int,
-        [_int, _i64, _p, _p, _p, _i64, _i32, _p, _p, _p, _p, _p, _p, _i32, _p, _p, _p, _f64, _f64, _f64, _p, _f64, _p, _p, _p, _p, _p],
+        [_int, _i64, _p, _p, _p, _i64, _i32, _p, _p, _p, _p, _p, _p, _i32, _p, _p, _p, _f64, _f64, _f64, _p, _f64,
+         _i32, _i32, _p, _i64, _p, _p, _p, _p, _p, _p],
     ),
+    "hp_local_tile_limits": (None, [_p, _p]),
+    "hp_local_chunk_points": (_i32, []),
     "hp_shell_screen": (_int, [_i32, _i32, _p, _p, _p, _f64, _p, _p]),
     "hp_shell_project": (_int, [_i32, _p, _p, _p, _p, _p, _p, _p, _p]),
     "hp_shell_harmonics": (_int, [_i32, _i32, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
@@ -100,7 +103,7 @@ EXPORTS = {
 
 # int-returning functions whose result is a value, not a status code
 _NOT_STATUS = {"hp_abi_version", "hp_num_partials", "hp_local_index_scratch_bytes", "hp_last_error", "hp_tile_limits", "hp_molgrid_num_blocks", "hp_hessian_scratch_bytes",
-               "hp_molgrid_update_tile_limits", "hp_host_is_pinned"}
+               "hp_molgrid_update_tile_limits", "hp_host_is_pinned", "hp_local_tile_limits", "hp_local_chunk_points"}
 
 
 class HpError(RuntimeError):

@@ -251,6 +251,17 @@ class ShellTable:
 
             if self.pair_partials is None:
                 self.pair_partials = torch.zeros(2 * s.npartial, dtype=torch.int64, device=s.device)
+                lim_a, lim_s = np.zeros(1, np.int32), np.zeros(1, np.int32)
+                _lib.call("hp_local_tile_limits", lim_a, lim_s)
+                self._loc_ntile, self._loc_tiles = self.make_tiles(int(lim_a[0]), int(lim_s[0]))
+                # chunks never straddle atom blocks: per-atom chunk counts of this rank's atoms
+                span = int(_lib.call("hp_local_chunk_points"))
+                sh = s.shard
+                npt = np.diff(s.atom_point_offsets_host[sh.atom_lo : sh.atom_hi + 1])
+                coff = np.concatenate([[0], np.cumsum((npt + span - 1) // span)]).astype(np.int64)
+                self._loc_nchunk = int(coff[-1])
+                self._loc_chunk_off = to_device(coff, s.device, np.int64)
+                self._loc_scratch = torch.zeros(max(self._loc_nchunk, 1), dtype=torch.float64, device=s.device)
             atom_eps = 0.0
             if bits:
                 if self.skip is None:
@@ -263,8 +274,9 @@ class ShellTable:
             _lib.call(
                 "hp_promol_weights_local", self.functor, s.npts, s.px, s.py, s.pz, s.point_base, s.natom,
                 s.atom_xyz, s.atom_point_offsets, self.offsets, self.A, self.alpha, self.order,
-                self.ntile, self.tiles, s.rho, s.molw, float(density_cutoff), float(promol_offset),
-                radius, self.skip if bits else None, atom_eps, s.promol if want_promol else None,
+                self._loc_ntile, self._loc_tiles, s.rho, s.molw, float(density_cutoff), float(promol_offset),
+                radius, self.skip if bits else None, atom_eps, s.shard.atom_lo, s.shard.nlocal,
+                self._loc_chunk_off, self._loc_nchunk, self._loc_scratch, s.promol if want_promol else None,
                 s.at_w if want_weights else None, s.entropy_partials if want_entropy else None,
                 self.pair_partials, stream_ptr(s.device),
             )  # fmt: skip

@@ -9,10 +9,18 @@ namespace hp {
 
 // exp(r) = 1 + r + r^2 g(r) on |r| <= ln2/2; g interpolated at Chebyshev nodes (degree 9),
 // max relative error of the polynomial 1.6e-17.
-__constant__ double c_expg[10] = {
-    0.5000000000000001,     0.16666666666666669,   0.04166666666662413,   0.008333333333330062,
-    0.0013888888917213717,  0.00019841269863053618, 2.4801521295954376e-05, 2.7557268459997064e-06,
-    2.7620088445409746e-07, 2.510038549551032e-08};
+// Literals (not a __constant__ array): ptxas then feeds them to DFMA straight from the immediate
+// constant bank instead of re-loading them into registers in every iteration of the atom loop.
+#define HP_EXPG0 0.5000000000000001
+#define HP_EXPG1 0.16666666666666669
+#define HP_EXPG2 0.04166666666662413
+#define HP_EXPG3 0.008333333333330062
+#define HP_EXPG4 0.0013888888917213717
+#define HP_EXPG5 0.00019841269863053618
+#define HP_EXPG6 2.4801521295954376e-05
+#define HP_EXPG7 2.7557268459997064e-06
+#define HP_EXPG8 2.7620088445409746e-07
+#define HP_EXPG9 2.510038549551032e-08
 
 __device__ __forceinline__ double rsqrt_seed(double x) {
     double y;
@@ -45,6 +53,47 @@ __device__ __forceinline__ double sqrt_fast(double d2) {
     return fma(fma(-g, g, d2), h, g);
 }
 
+// Polynomial / reduction constants of the atom loop, pinned in registers: they are read once per
+// thread through an opaque (asm volatile) global load, which makes them run-time values to ptxas.
+// Spelled as literals each one is re-materialised with two moves at every use, and read from a
+// __constant__ table they are re-fetched (13 LDC.64) in every iteration of the atom loop.
+// c_exp_regs keeps a __constant__ copy for the probes in tools/.
+#define HP_EXP_TABLE                                                                                   \
+    {HP_EXPG0, HP_EXPG1, HP_EXPG2, HP_EXPG3, HP_EXPG4, HP_EXPG5, HP_EXPG6, HP_EXPG7, HP_EXPG8, HP_EXPG9, \
+     1.4426950408889634, -6.93147180559945286e-01, -2.31904681384629956e-17}
+__constant__ double c_exp_regs[13] = HP_EXP_TABLE;
+__device__ double d_exp_regs[13] = HP_EXP_TABLE;
+
+struct ExpConsts {
+    double g[10], log2e, ln2hi, ln2lo;
+    __device__ __forceinline__ void load() {
+        double v[13];
+        const unsigned long long base = static_cast<unsigned long long>(__cvta_generic_to_global(d_exp_regs));
+#pragma unroll
+        for (int i = 0; i < 13; ++i) asm volatile("ld.global.f64 %0, [%1];" : "=d"(v[i]) : "l"(base + 8ull * i));
+#pragma unroll
+        for (int i = 0; i < 10; ++i) g[i] = v[i];
+        log2e = v[10];
+        ln2hi = v[11];
+        ln2lo = v[12];
+    }
+};
+
+// Unguarded exp(x), -700 < x <= 0, constants from registers (same arithmetic as exp_neg_poly).
+__device__ __forceinline__ double exp_neg_poly_regs(double x, const ExpConsts& c) {
+    const double t = fma(x, c.log2e, 6755399441055744.0);
+    const int k = __double2loint(t);
+    const double kd = t - 6755399441055744.0;
+    double r = fma(kd, c.ln2hi, x);
+    r = fma(kd, c.ln2lo, r);
+    double g = fma(c.g[9], r, c.g[8]);
+#pragma unroll
+    for (int i = 7; i >= 0; --i) g = fma(g, r, c.g[i]);
+    double p = fma(g, r, 1.0);
+    p = fma(p, r, 1.0);
+    return __hiloint2double(__double2hiint(p) + (k << 20), __double2loint(p));
+}
+
 // x <= -708 (or a negative NaN): results at or below 3.4e-308 are flushed to exactly 0.  Such
 // terms are absorbed by the reference's own +1e-100 offsets, so promolecule sums are unchanged;
 // the absolute error of a single pro-atom value is < 3.4e-308.
@@ -61,9 +110,15 @@ __device__ __forceinline__ double exp_neg_poly(double x) {
     const double kd = t - 6755399441055744.0;
     double r = fma(kd, -6.93147180559945286e-01, x);
     r = fma(kd, -2.31904681384629956e-17, r);
-    double g = c_expg[9];
-#pragma unroll
-    for (int i = 8; i >= 0; --i) g = fma(g, r, c_expg[i]);
+    double g = fma(HP_EXPG9, r, HP_EXPG8);
+    g = fma(g, r, HP_EXPG7);
+    g = fma(g, r, HP_EXPG6);
+    g = fma(g, r, HP_EXPG5);
+    g = fma(g, r, HP_EXPG4);
+    g = fma(g, r, HP_EXPG3);
+    g = fma(g, r, HP_EXPG2);
+    g = fma(g, r, HP_EXPG1);
+    g = fma(g, r, HP_EXPG0);
     double p = fma(g, r, 1.0);
     p = fma(p, r, 1.0);
     if (!GUARD) return __hiloint2double(__double2hiint(p) + (k << 20), __double2loint(p));

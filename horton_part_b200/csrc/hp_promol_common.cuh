@@ -37,14 +37,14 @@ __device__ __forceinline__ void eval_proatom(const double (&d2)[kP], int s0, int
                                              double2 ab0) {
     double r[kP];
 #pragma unroll
-    for (int j = 0; j < kP; ++j) {
-        f[j] = 0.0;
-        r[j] = (F == HP_FUNCTOR_GAUSS) ? d2[j] : (FAST ? sqrt_fast(d2[j]) : sqrt_nocall(d2[j]));
-    }
+    for (int j = 0; j < kP; ++j) r[j] = (F == HP_FUNCTOR_GAUSS) ? d2[j] : (FAST ? sqrt_fast(d2[j]) : sqrt_nocall(d2[j]));
     if (ns > 0) {
         const double n0 = (F == HP_FUNCTOR_GENERAL) ? sN[s0] : 1.0;
 #pragma unroll
-        for (int j = 0; j < kP; ++j) f[j] = fma(ab0.x, shell_value<F, FAST>(ab0, n0, r[j]), f[j]);
+        for (int j = 0; j < kP; ++j) f[j] = ab0.x * shell_value<F, FAST>(ab0, n0, r[j]);
+    } else {
+#pragma unroll
+        for (int j = 0; j < kP; ++j) f[j] = 0.0;
     }
     for (int k = 1; k < ns; ++k) {
         const double2 ab = sAB[s0 + k];  // (A, alpha)

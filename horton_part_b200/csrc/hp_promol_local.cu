@@ -23,24 +23,74 @@
 // evaluated.  lb <= 1e-80 disables the test, which keeps the +1e-100 offsets literal.
 //
 // Work skipping happens per block and is conservative; the per-pair test above is exact:
-//   a chunk of consecutive grid points almost always lies on a few radial shells of ONE owner atom,
-//   r_min <= |p - R_o| <= r_max, so atom a can reach it only if
+//   a chunk is up to 1,024 consecutive grid points of ONE owner atom (chunks never straddle atom
+//   blocks), i.e. a few radial shells, r_min <= |p - R_o| <= r_max, so atom a can reach it only if
 //   r_min - radius <= |R_a - R_o| <= r_max + radius.  Atoms passing this annulus test are compacted
 //   IN ATOM ORDER into the shared-memory tile (warp ballots), so the sequential summation order of
 //   the reference is preserved.  Evaluated pairs are counted for the benchmark's "evals" metric.
+//
+// Scheduling: chunks cost between a few dozen and natom atom evaluations, so blocks take them from
+// a global work counter instead of a fixed stride (the slowest block of a static split was ~10 %
+// behind the mean on config 5).  Reductions stay bit-reproducible: every chunk writes its entropy
+// term to its own slot, a second kernel folds the slots into the partial-sum buffer in a fixed
+// order, and the pair counters are integers.
+//
+// Inner loop (one candidate atom x 4 points per thread): the atom record (centre, first shell,
+// shell range, guard flag) is three LDS.128 issued from PTX into the registers of the record they
+// replace, right after their last use -- no rotation moves; the exp constants sit in registers.
 #include "hp_promol_common.cuh"
 
 namespace hp {
 
-constexpr int kLocThreads = 256;
-constexpr int kLocPts = 4;
+#ifndef HP_LOC_THREADS
+#define HP_LOC_THREADS 128
+#endif
+#ifndef HP_LOC_BLOCKS
+#define HP_LOC_BLOCKS 2
+#endif
+constexpr int kLocThreads = HP_LOC_THREADS;      // 128 threads x 2 blocks/SM: 255 registers per thread
+constexpr int kLocBlocksPerSM = HP_LOC_BLOCKS;
+#ifndef HP_LOC_PTS
+#define HP_LOC_PTS 8
+#endif
+constexpr int kLocPts = HP_LOC_PTS;
+constexpr int kLocSpan = kLocThreads * kLocPts;  // points per chunk
+constexpr int kLocTileAtoms = kLocThreads;       // candidate atoms per shared-memory tile (one per thread)
+constexpr int kLocTileShells = 1024;
+
+// Candidate record in shared memory: 48 bytes = three 16-byte loads.
+struct __align__(16) LocAtom {
+    double x, y;
+    double z;
+    int s0;  // first kept shell in s_AB (tile-relative); sign bit set = guarded evaluation
+    int ns;  // kept shells
+    double A0, alpha0;  // first kept shell (0, 0 if none)
+};
+
+__device__ unsigned long long g_loc_work_counter;
 
 __device__ __forceinline__ double dist2_unfused3(double dx, double dy, double dz) {
     return __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
 }
 
+__device__ __forceinline__ void lds_f64x2(unsigned addr, double& a, double& b) {
+    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(a), "=d"(b) : "r"(addr));
+}
+__device__ __forceinline__ void lds_z_pack(unsigned addr, double& z, int& s0, int& ns) {
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(z) : "r"(addr));
+    asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(s0), "=r"(ns) : "r"(addr + 8));
+}
+
+// exp(x) for x <= 0 with the constants in registers; GUARD adds the underflow flush of exp_neg_poly.
+template <bool GUARD>
+__device__ __forceinline__ double exp_regs(double x, const ExpConsts& c) {
+    const double e = exp_neg_poly_regs(x, c);
+    if (!GUARD) return e;
+    return exp_arg_tiny(x) ? 0.0 : e;
+}
+
 template <int F, bool LOCAL>
-__global__ void __launch_bounds__(kLocThreads, 2)
+__global__ void __launch_bounds__(kLocThreads, kLocBlocksPerSM)
 promol_weights_local_kernel(int64_t npts, const double* __restrict__ px, const double* __restrict__ py,
                             const double* __restrict__ pz, int64_t point_base, int natom,
                             const double* __restrict__ atom_xyz, const int64_t* __restrict__ atom_pt_off,
@@ -49,65 +99,76 @@ promol_weights_local_kernel(int64_t npts, const double* __restrict__ px, const d
                             int ntile, const int* __restrict__ tile_off, const double* __restrict__ rho,
                             const double* __restrict__ molw, double density_cutoff, double promol_offset,
                             double radius, const double* __restrict__ shell_skip, double atom_eps,
+                            int atom_lo, int natom_local, const int64_t* __restrict__ chunk_off,
                             double* __restrict__ promol_out, double* __restrict__ w_out,
-                            double* __restrict__ entropy_partials,
-                            unsigned long long* __restrict__ pair_partials) {
-    __shared__ AtomRec s_atoms[kTileAtoms + 1];  // +1: sentinel for the prefetch
-    __shared__ double2 s_AB[kTileShells];
-    __shared__ double s_N[(F == HP_FUNCTOR_GENERAL) ? kTileShells : 1];
+                            double* __restrict__ chunk_entropy,
+                            unsigned long long* __restrict__ pair_counters) {
+    __shared__ LocAtom s_atoms[kLocTileAtoms + 1];  // +1: sentinel for the prefetch
+    __shared__ double2 s_AB[kLocTileShells];
+    __shared__ double s_N[(F == HP_FUNCTOR_GENERAL) ? kLocTileShells : 1];
     __shared__ double s_red[32];
     __shared__ double s_geom[5];  // owner centre x,y,z, r_min, r_max
-    __shared__ int s_flags[2];    // same-owner flag, owner index
-    __shared__ int s_wcnt[kTileAtoms / 32];
-    __shared__ int s_wsh[kTileAtoms / 32];
+    __shared__ long long s_chunk[3];  // chunk id, first local point, one past the last local point
+    __shared__ int s_owner;
+    __shared__ int s_wcnt[kLocThreads / 32];
+    __shared__ int s_wsh[kLocThreads / 32];
     __shared__ int s_ncand;
     __shared__ double s_wmin[kLocThreads / 32];  // per-warp minimum of the running sums
     __shared__ double s_lb;                      // owner-based lower bound of the promolecule
 
     const double rc2 = radius * radius;
-    const int64_t span = int64_t(kLocThreads) * kLocPts;
-    const int64_t nchunk = (npts + span - 1) / span;
+    const long long nchunk = chunk_off[natom_local];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    double entropy_acc = 0.0;
+    const unsigned atoms_addr = static_cast<unsigned>(__cvta_generic_to_shared(s_atoms));
+    const unsigned ab_addr = static_cast<unsigned>(__cvta_generic_to_shared(s_AB));
     unsigned long long pairs = 0, shells = 0;
+    ExpConsts ec;
+    ec.load();
+    // shell_skip[nshell_total] is the "negative amplitude seen" flag written by hp_shell_screen
+    const bool may_screen_atoms = atom_eps > 0.0 && F != HP_FUNCTOR_GENERAL && shell_skip &&
+                                  shell_skip[atom_sh_off[natom]] == 0.0;
 
-    for (int64_t chunk = blockIdx.x; chunk < nchunk; chunk += gridDim.x) {
+    for (;;) {
+        __syncthreads();  // everybody is done with the previous chunk's shared state
+        if (threadIdx.x == 0) {
+            const long long c = static_cast<long long>(atomicAdd(&g_loc_work_counter, 1ull));
+            s_chunk[0] = c;
+            if (c < nchunk) {
+                int lo = 0, hi = natom_local;  // owner: last local atom with chunk_off[a] <= c
+                while (hi - lo > 1) {
+                    const int mid = (lo + hi) >> 1;
+                    if (chunk_off[mid] <= c) lo = mid; else hi = mid;
+                }
+                const int o = atom_lo + lo;
+                const long long first = (atom_pt_off[o] - point_base) + (c - chunk_off[lo]) * kLocSpan;
+                const long long end = atom_pt_off[o + 1] - point_base;
+                s_chunk[1] = first;
+                s_chunk[2] = end < first + kLocSpan ? end : first + kLocSpan;
+                s_owner = o;
+                s_geom[0] = atom_xyz[3 * o];
+                s_geom[1] = atom_xyz[3 * o + 1];
+                s_geom[2] = atom_xyz[3 * o + 2];
+            }
+        }
+        __syncthreads();
+        const long long chunk = s_chunk[0];
+        if (chunk >= nchunk) break;
+        const long long p_first = s_chunk[1], p_end = s_chunk[2];
+        const int owner = s_owner;
+
         double x[kLocPts], y[kLocPts], z[kLocPts], pro[kLocPts];
         int nlive = 0;
 #pragma unroll
         for (int j = 0; j < kLocPts; ++j) {
-            const int64_t p = chunk * span + int64_t(j) * kLocThreads + threadIdx.x;
-            const int64_t q = p < npts ? p : (npts - 1);
-            nlive += p < npts;
+            const long long p = p_first + j * kLocThreads + threadIdx.x;
+            const long long q = p < p_end ? p : (p_end - 1);
+            nlive += p < p_end;
             x[j] = px[q]; y[j] = py[q]; z[j] = pz[q];
             pro[j] = 0.0;
         }
-        // ---- chunk geometry: one owner? radial extent around it ---------------------------------
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            const int64_t first = point_base + chunk * span;
-            int64_t last = point_base + chunk * span + span - 1;
-            if (last > point_base + npts - 1) last = point_base + npts - 1;
-            int own[2];
-            const int64_t g2[2] = {first, last};
-            for (int e = 0; e < 2; ++e) {
-                int lo = 0, hi = natom;
-                while (hi - lo > 1) {
-                    const int mid = (lo + hi) >> 1;
-                    if (atom_pt_off[mid] <= g2[e]) lo = mid; else hi = mid;
-                }
-                own[e] = lo;
-            }
-            s_flags[0] = own[0] == own[1];
-            s_flags[1] = own[0];
-            s_geom[0] = atom_xyz[3 * own[0]];
-            s_geom[1] = atom_xyz[3 * own[0] + 1];
-            s_geom[2] = atom_xyz[3 * own[0] + 2];
-        }
-        __syncthreads();
-        const bool same_owner = s_flags[0] != 0;
-        double rmin = 0.0, rmax = 0.0;
-        if (same_owner) {
+        // ---- chunk geometry: radial extent around the owner -------------------------------------
+        double rmin, rmax;
+        {
             double lo = 1e300, hi = 0.0;
 #pragma unroll
             for (int j = 0; j < kLocPts; ++j) {
@@ -122,96 +183,84 @@ promol_weights_local_kernel(int64_t npts, const double* __restrict__ px, const d
             }
             if (lane == 0) {
                 s_red[warp] = lo;
-                s_red[8 + warp] = hi;
+                s_red[16 + warp] = hi;
             }
             __syncthreads();
             if (threadIdx.x == 0) {
-                double a = s_red[0], b = s_red[8];
+                double a = s_red[0], b = s_red[16];
                 for (int w = 1; w < kLocThreads / 32; ++w) {
                     a = fmin(a, s_red[w]);
-                    b = fmax(b, s_red[8 + w]);
+                    b = fmax(b, s_red[16 + w]);
                 }
                 s_geom[3] = a;
                 s_geom[4] = b;
+                if (may_screen_atoms) {  // the owner's pro-atom at the chunk's outer radius
+                    const double xo = (F == HP_FUNCTOR_GAUSS) ? b * b : b;
+                    double lb = 0.0;
+                    for (int k = atom_sh_off[owner]; k < atom_sh_off[owner + 1]; ++k)
+                        lb += shell_A[k] * exp(-shell_alpha[k] * xo * (1.0 + 1e-9));
+                    s_lb = (LOCAL && b > radius) ? 0.0 : lb * (1.0 - 1e-9);
+                }
             }
+            if (lane == 0) s_wmin[warp] = 0.0;
             __syncthreads();
             rmin = s_geom[3];
             rmax = s_geom[4];
         }
         const double slack = LOCAL ? 1e-9 * (1.0 + rmax + radius) : 0.0;
-        // shell_skip[nshell_total] is the "negative amplitude seen" flag written by hp_shell_screen
-        const bool screen_atoms = atom_eps > 0.0 && same_owner && F != HP_FUNCTOR_GENERAL && shell_skip &&
-                                  shell_skip[atom_sh_off[natom]] == 0.0;
-        if (screen_atoms) {
-            if (threadIdx.x == 0) {  // the owner's pro-atom at the chunk's outer radius
-                const int o = s_flags[1];
-                const double xo = (F == HP_FUNCTOR_GAUSS) ? rmax * rmax : rmax;
-                double lb = 0.0;
-                for (int k = atom_sh_off[o]; k < atom_sh_off[o + 1]; ++k)
-                    lb += shell_A[k] * exp(-shell_alpha[k] * xo * (1.0 + 1e-9));
-                s_lb = (LOCAL && rmax > radius) ? 0.0 : lb * (1.0 - 1e-9);
-            }
-            if (lane == 0) s_wmin[warp] = 0.0;
-        }
 
         for (int t = 0; t < ntile; ++t) {
             const int a0 = tile_off[t], a1 = tile_off[t + 1];
             __syncthreads();  // previous tile fully consumed
-            // ---- ordered compaction of the atoms that can reach this chunk -----------------------
-            AtomRec rec;
+            // ---- ordered compaction of the atoms that can matter for this chunk ------------------
+            LocAtom rec;
             bool cand = false, fast = false;
-            unsigned m = 0;
-            int nkeep = 0, shell_incl = 0, gs0 = 0;
-            double xmin = 0.0, xmax = 0.0;
-            if (threadIdx.x < kTileAtoms) {  // warps 0..3, warp-uniform
+            int nkeep = 0, shell_incl = 0, gs0 = 0, ns_all = 0;
+            double xmin = 0.0;
+            {
                 const int i = threadIdx.x;
                 if (i < a1 - a0) {
                     rec.x = atom_xyz[3 * (a0 + i) + 0];
                     rec.y = atom_xyz[3 * (a0 + i) + 1];
                     rec.z = atom_xyz[3 * (a0 + i) + 2];
                     gs0 = atom_sh_off[a0 + i];
-                    rec.ns = atom_sh_off[a0 + i + 1] - gs0;
-                    cand = true;
-                    if (same_owner) {
-                        const double D = sqrt(dist2_unfused3(rec.x - s_geom[0], rec.y - s_geom[1], rec.z - s_geom[2]));
-                        if (LOCAL) cand = (D >= rmin - radius - slack) && (D <= rmax + radius + slack);
-                        // conservative lower bound of the chunk's distance to this atom
-                        const double dmin = fmax(0.0, fmax(D - rmax, rmin - D) - 1e-9 * (1.0 + rmax + D));
-                        xmin = (F == HP_FUNCTOR_GAUSS) ? dmin * dmin : dmin;
-                        const double dmax = (D + rmax) * (1.0 + 1e-9);
-                        xmax = (F == HP_FUNCTOR_GAUSS) ? dmax * dmax : dmax;
-                    }
-                    if (cand && screen_atoms) {
-                        double lb = s_lb;  // written before the barrier at the top of this tile
-                        double run = s_wmin[0];
+                    ns_all = atom_sh_off[a0 + i + 1] - gs0;
+                    const double D = sqrt(dist2_unfused3(rec.x - s_geom[0], rec.y - s_geom[1], rec.z - s_geom[2]));
+                    cand = !LOCAL || ((D >= rmin - radius - slack) && (D <= rmax + radius + slack));
+                    // conservative bounds of the chunk's distance to this atom
+                    const double dmin = fmax(0.0, fmax(D - rmax, rmin - D) - 1e-9 * (1.0 + rmax + D));
+                    const double dmax = (D + rmax) * (1.0 + 1e-9);
+                    xmin = (F == HP_FUNCTOR_GAUSS) ? dmin * dmin : dmin;
+                    const double xmax = (F == HP_FUNCTOR_GAUSS) ? dmax * dmax : dmax;
+                    if (cand && may_screen_atoms) {
+                        double lb = s_lb, run = s_wmin[0];
                         for (int w = 1; w < kLocThreads / 32; ++w) run = fmin(run, s_wmin[w]);
                         lb = fmax(lb, run);
                         if (lb > 1e-80) {
                             double ub = 0.0;
-                            for (int k = 0; k < rec.ns; ++k)
-                                ub += shell_A[gs0 + k] * exp(-shell_alpha[gs0 + k] * xmin);
+                            for (int k = 0; k < ns_all; ++k) ub += shell_A[gs0 + k] * exp(-shell_alpha[gs0 + k] * xmin);
                             cand = !(ub * (1.0 + 1e-9) < atom_eps * lb);
                         }
                     }
                     if (cand) {
-                        nkeep = rec.ns;
+                        nkeep = ns_all;
                         double amax = 0.0;  // largest exponent among the shells that are evaluated
                         if (shell_skip && F != HP_FUNCTOR_GENERAL) {
                             nkeep = 0;
-                            for (int k = 0; k < rec.ns; ++k) {
+                            for (int k = 0; k < ns_all; ++k) {
                                 const bool keep = !(xmin > shell_skip[gs0 + k]);
                                 nkeep += keep;
                                 if (keep) amax = fmax(amax, shell_alpha[gs0 + k]);
                             }
                         } else if (F != HP_FUNCTOR_GENERAL) {
-                            for (int k = 0; k < rec.ns; ++k) amax = fmax(amax, shell_alpha[gs0 + k]);
+                            for (int k = 0; k < ns_all; ++k) amax = fmax(amax, shell_alpha[gs0 + k]);
                         }
                         // guards can go when no point of the chunk can sit on this nucleus and no
                         // exponent argument can reach the underflow range
-                        if (same_owner && F != HP_FUNCTOR_GENERAL) fast = xmin > 1e-100 && amax * xmax < 700.0;
+                        if (F != HP_FUNCTOR_GENERAL) fast = xmin > 1e-100 && amax * xmax < 700.0;
                     }
                 }
-                m = __ballot_sync(0xffffffffu, cand);
+                const unsigned m = __ballot_sync(0xffffffffu, cand);
                 // inclusive warp scan of the kept-shell counts (atom order)
                 shell_incl = nkeep;
 #pragma unroll
@@ -221,67 +270,113 @@ promol_weights_local_kernel(int64_t npts, const double* __restrict__ px, const d
                 }
                 if (lane == 31) s_wsh[warp] = shell_incl;
                 if (lane == 0) s_wcnt[warp] = __popc(m);
-            }
-            __syncthreads();
-            if (threadIdx.x < kTileAtoms) {
-                int off = 0, shoff = 0;
-                for (int w = 0; w < warp; ++w) {
-                    off += s_wcnt[w];
-                    shoff += s_wsh[w];
+                __syncthreads();
+                int off = 0, shoff = 0, tot = 0;
+                for (int w = 0; w < kLocThreads / 32; ++w) {
+                    if (w < warp) {
+                        off += s_wcnt[w];
+                        shoff += s_wsh[w];
+                    }
+                    tot += s_wcnt[w];
                 }
                 if (cand) {
                     int dst = shoff + shell_incl - nkeep;
                     rec.s0 = fast ? dst : (dst | int(0x80000000));  // sign bit = guarded evaluation
+                    rec.ns = nkeep;
+                    rec.A0 = 0.0;
+                    rec.alpha0 = 0.0;
                     const bool screen = shell_skip && F != HP_FUNCTOR_GENERAL;
-                    for (int k = 0; k < rec.ns; ++k) {
+                    bool first = true;
+                    for (int k = 0; k < ns_all; ++k) {
                         if (screen && xmin > shell_skip[gs0 + k]) continue;
-                        s_AB[dst] = make_double2(shell_A[gs0 + k], shell_alpha[gs0 + k]);
+                        const double2 ab = make_double2(shell_A[gs0 + k], shell_alpha[gs0 + k]);
+                        if (first) {
+                            rec.A0 = ab.x;
+                            rec.alpha0 = ab.y;
+                            first = false;
+                        }
+                        s_AB[dst] = ab;
                         if (F == HP_FUNCTOR_GENERAL) s_N[dst] = shell_order[gs0 + k];
                         ++dst;
                     }
-                    rec.ns = nkeep;
                     s_atoms[off + __popc(m & ((1u << lane) - 1u))] = rec;
                 }
                 if (threadIdx.x == 0) {
-                    int tot = 0;
-                    for (int w = 0; w < kTileAtoms / 32; ++w) tot += s_wcnt[w];
                     s_ncand = tot;
-                    AtomRec sentinel = {0.0, 0.0, 0.0, 0, 0};
+                    const LocAtom sentinel = {0.0, 0.0, 0.0, 0, 0, 0.0, 0.0};
                     s_atoms[tot] = sentinel;
                 }
             }
             __syncthreads();
-            const int ncand = s_ncand;
+            const int ncand = __shfl_sync(0xffffffffu, s_ncand, 0);
             pairs += static_cast<unsigned long long>(ncand) * nlive;
-            if (pair_partials) {  // kept shells of this tile = s0 + ns of its last candidate
-                const int kept = ncand ? (s_atoms[ncand - 1].s0 & 0x7fffffff) + s_atoms[ncand - 1].ns : 0;
+            if (ncand) {  // kept shells of this tile = s0 + ns of its last candidate
+                const int kept = (s_atoms[ncand - 1].s0 & 0x7fffffff) + s_atoms[ncand - 1].ns;
                 shells += static_cast<unsigned long long>(kept) * nlive;
             }
 
-            AtomRec nxt = s_atoms[0];
-            double2 nxt_ab = s_AB[nxt.s0 & 0x7fffffff];
+            // ---- evaluation: every thread, 4 points, all candidates in atom order ---------------
+            double ax, ay, az, A0, al0;
+            int s0, ns;
+            lds_f64x2(atoms_addr, ax, ay);
+            lds_z_pack(atoms_addr + 16, az, s0, ns);
+            lds_f64x2(atoms_addr + 32, A0, al0);
             for (int i = 0; i < ncand; ++i) {
-                const AtomRec ar = nxt;
-                const double2 ab0 = nxt_ab;
-                nxt = s_atoms[i + 1];  // entry [ncand] is a sentinel
-                nxt_ab = s_AB[nxt.s0 & 0x7fffffff];
+                const unsigned next = atoms_addr + unsigned(i + 1) * unsigned(sizeof(LocAtom));  // [ncand] = sentinel
                 double d2[kLocPts], f[kLocPts];
 #pragma unroll
                 for (int j = 0; j < kLocPts; ++j) {
-                    const double dx = x[j] - ar.x, dy = y[j] - ar.y, dz = z[j] - ar.z;
+                    const double dx = x[j] - ax, dy = y[j] - ay, dz = z[j] - az;
                     d2[j] = LOCAL ? dist2_unfused3(dx, dy, dz) : fma(dz, dz, fma(dy, dy, dx * dx));
                 }
-                // block-uniform branch: zero-distance / underflow guards dropped where the chunk
-                // geometry rules both out
-                if (ar.s0 >= 0) eval_proatom<F, kLocPts, true>(d2, ar.s0, ar.ns, s_AB, s_N, f, ab0);
-                else eval_proatom<F, kLocPts>(d2, ar.s0 & 0x7fffffff, ar.ns, s_AB, s_N, f, ab0);
+                lds_f64x2(next, ax, ay);  // the centre is dead from here on: fetch the next one
+                const int cs0 = s0 & 0x7fffffff, cns = ns;
+                const bool guarded = __any_sync(0xffffffffu, s0 < 0);  // uniform by construction; the vote tells ptxas
+                if (F == HP_FUNCTOR_GENERAL) {
+                    const double2 ab0 = make_double2(A0, al0);
+                    eval_proatom<F, kLocPts>(d2, cs0, cns, s_AB, s_N, f, ab0);
+                    lds_z_pack(next + 16, az, s0, ns);
+                    lds_f64x2(next + 32, A0, al0);
+                } else if (!guarded) {  // block-uniform branch
+                    double r[kLocPts];
+#pragma unroll
+                    for (int j = 0; j < kLocPts; ++j) r[j] = (F == HP_FUNCTOR_GAUSS) ? d2[j] : sqrt_fast(d2[j]);
+                    const double na = -al0;
+#pragma unroll
+                    for (int j = 0; j < kLocPts; ++j) f[j] = A0 * exp_regs<false>(na * r[j], ec);
+                    lds_z_pack(next + 16, az, s0, ns);
+                    lds_f64x2(next + 32, A0, al0);
+                    for (int k = 1; k < cns; ++k) {
+                        double A, al;
+                        lds_f64x2(ab_addr + unsigned(cs0 + k) * 16u, A, al);
+                        al = -al;
+#pragma unroll
+                        for (int j = 0; j < kLocPts; ++j) f[j] = fma(A, exp_regs<false>(al * r[j], ec), f[j]);
+                    }
+                } else {
+                    double r[kLocPts];
+#pragma unroll
+                    for (int j = 0; j < kLocPts; ++j) r[j] = (F == HP_FUNCTOR_GAUSS) ? d2[j] : sqrt_nocall(d2[j]);
+                    const double na = -al0;
+#pragma unroll
+                    for (int j = 0; j < kLocPts; ++j) f[j] = A0 * exp_regs<true>(na * r[j], ec);
+                    lds_z_pack(next + 16, az, s0, ns);
+                    lds_f64x2(next + 32, A0, al0);
+                    for (int k = 1; k < cns; ++k) {
+                        double A, al;
+                        lds_f64x2(ab_addr + unsigned(cs0 + k) * 16u, A, al);
+                        al = -al;
+#pragma unroll
+                        for (int j = 0; j < kLocPts; ++j) f[j] = fma(A, exp_regs<true>(al * r[j], ec), f[j]);
+                    }
+                }
 #pragma unroll
                 for (int j = 0; j < kLocPts; ++j) {
                     if (LOCAL) pro[j] = (d2[j] <= rc2) ? (pro[j] + f[j]) + promol_offset : pro[j];
                     else pro[j] = (pro[j] + f[j]) + promol_offset;
                 }
             }
-            if (screen_atoms) {  // block minimum of the running sums, consumed by the next tile's setup
+            if (may_screen_atoms) {  // block minimum of the running sums, consumed by the next tile's setup
                 double lo = 1e300;
 #pragma unroll
                 for (int j = 0; j < kLocPts; ++j) lo = fmin(lo, pro[j]);
@@ -291,79 +386,66 @@ promol_weights_local_kernel(int64_t npts, const double* __restrict__ px, const d
             }
         }
 
+        // ---- epilogue: promolecule, owner weight, entropy term of this chunk -------------------------
+        double entropy_acc = 0.0;
+        const double ox = s_geom[0], oy = s_geom[1], oz = s_geom[2];
+        const int os0 = atom_sh_off[owner], ons = atom_sh_off[owner + 1] - os0;
 #pragma unroll
         for (int j = 0; j < kLocPts; ++j) {
-            const int64_t p = chunk * span + int64_t(j) * kLocThreads + threadIdx.x;
-            if (p >= npts) continue;
+            const long long p = p_first + j * kLocThreads + threadIdx.x;
+            if (p >= p_end) continue;
             if (promol_out) promol_out[p] = pro[j];
             if (w_out) {
-                const int64_t g = point_base + p;
-                int lo = 0, hi = natom;
-                while (hi - lo > 1) {
-                    const int mid = (lo + hi) >> 1;
-                    if (atom_pt_off[mid] <= g) lo = mid; else hi = mid;
-                }
-                const double odx = x[j] - atom_xyz[3 * lo], ody = y[j] - atom_xyz[3 * lo + 1],
-                             odz = z[j] - atom_xyz[3 * lo + 2];
+                const double odx = x[j] - ox, ody = y[j] - oy, odz = z[j] - oz;
                 const double d2 = LOCAL ? dist2_unfused3(odx, ody, odz) : fma(odz, odz, fma(ody, ody, odx * odx));
                 double w = 0.0;
                 if (!LOCAL || d2 <= rc2) {
-                    const int s0 = atom_sh_off[lo], ns = atom_sh_off[lo + 1] - s0;
                     const double r = (F == HP_FUNCTOR_GAUSS) ? d2 : sqrt_nocall(d2);
                     double fo = 0.0;
-                    for (int k = 0; k < ns; ++k) {
-                        const double2 ab = make_double2(shell_A[s0 + k], shell_alpha[s0 + k]);
-                        const double n = (F == HP_FUNCTOR_GENERAL) ? shell_order[s0 + k] : 1.0;
+                    for (int k = 0; k < ons; ++k) {
+                        const double2 ab = make_double2(shell_A[os0 + k], shell_alpha[os0 + k]);
+                        const double n = (F == HP_FUNCTOR_GENERAL) ? shell_order[os0 + k] : 1.0;
                         fo = fma(ab.x, shell_value<F>(ab, n, r), fo);
                     }
                     w = fmin(fmax(fo / pro[j], 0.0), 1.0);
                 }
                 w_out[p] = w;
             }
-            if (entropy_partials) {
+            if (chunk_entropy) {
                 const double r = rho[p];
                 const bool sick = (pro[j] < density_cutoff) || (r < density_cutoff);
                 if (!sick) entropy_acc += molw[p] * r * log(r / pro[j]);
             }
         }
+        if (chunk_entropy) {
+            const double total = block_sum(entropy_acc, s_red);
+            if (threadIdx.x == 0) chunk_entropy[chunk] = total;
+        }
     }
 
-    if (entropy_partials) {
-        const double total = block_sum(entropy_acc, s_red);
-        if (threadIdx.x == 0) entropy_partials[blockIdx.x] = total;
-        if (blockIdx.x == 0)
-            for (int i = gridDim.x + threadIdx.x; i < kMaxPartials; i += kLocThreads) entropy_partials[i] = 0.0;
-    }
-    if (pair_partials) {
-        // each thread tallied (candidates x its own live points): the block total is the sum.
-        // Layout: [0, kMaxPartials) pairs, [kMaxPartials, 2 kMaxPartials) shell evaluations.
+    if (pair_counters) {
+        // each thread tallied (candidates x its own live points): integers, so the atomics are exact
         unsigned long long v = pairs, u = shells;
 #pragma unroll
         for (int off = 16; off > 0; off >>= 1) {
             v += __shfl_xor_sync(0xffffffffu, v, off);
             u += __shfl_xor_sync(0xffffffffu, u, off);
         }
-        __shared__ unsigned long long s_pairs[2][kLocThreads / 32];
         if (lane == 0) {
-            s_pairs[0][warp] = v;
-            s_pairs[1][warp] = u;
+            atomicAdd(&pair_counters[0], v);
+            atomicAdd(&pair_counters[kMaxPartials], u);
         }
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            unsigned long long tot = 0, tot2 = 0;
-            for (int w = 0; w < kLocThreads / 32; ++w) {
-                tot += s_pairs[0][w];
-                tot2 += s_pairs[1][w];
-            }
-            pair_partials[blockIdx.x] = tot;
-            pair_partials[kMaxPartials + blockIdx.x] = tot2;
-        }
-        if (blockIdx.x == 0)
-            for (int i = gridDim.x + threadIdx.x; i < kMaxPartials; i += kLocThreads) {
-                pair_partials[i] = 0ull;
-                pair_partials[kMaxPartials + i] = 0ull;
-            }
     }
+}
+
+// entropy_partials[i] = sum over chunks c = i, i + kMaxPartials, ... (ascending) of chunk_entropy[c]
+__global__ void fold_chunk_entropy_kernel(long long nchunk, const double* __restrict__ chunk_entropy,
+                                          double* __restrict__ partials) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= kMaxPartials) return;
+    double s = 0.0;
+    for (long long c = i; c < nchunk; c += kMaxPartials) s += chunk_entropy[c];
+    partials[i] = s;
 }
 
 // Screening thresholds: shell_skip[k] = largest value of the radial variable (r for Slater, r^2 for
@@ -420,6 +502,13 @@ extern "C" int hp_shell_screen(int32_t natom, int32_t nshell, const int32_t* ato
     return HP_OK;
 }
 
+extern "C" void hp_local_tile_limits(int32_t* max_atoms_host, int32_t* max_shells_host) {
+    *max_atoms_host = kLocTileAtoms;
+    *max_shells_host = kLocTileShells;
+}
+
+extern "C" int32_t hp_local_chunk_points(void) { return kLocSpan; }
+
 extern "C" int hp_promol_weights_local(int functor, int64_t npts, const double* px, const double* py,
                                        const double* pz, int64_t point_base, int32_t natom,
                                        const double* atom_xyz, const int64_t* atom_point_offsets,
@@ -428,8 +517,9 @@ extern "C" int hp_promol_weights_local(int functor, int64_t npts, const double* 
                                        int32_t ntile, const int32_t* tile_atom_offsets,
                                        const double* rho, const double* molw, double density_cutoff,
                                        double promol_offset, double radius, const double* shell_skip,
-                                       double atom_eps, double* promol, double* at_weights,
-                                       double* entropy_partials,
+                                       double atom_eps, int32_t atom_lo, int32_t natom_local,
+                                       const int64_t* chunk_offsets, int64_t nchunk, double* chunk_scratch,
+                                       double* promol, double* at_weights, double* entropy_partials,
                                        uint64_t* pair_partials, void* stream) {
     HP_REQUIRE(npts >= 0 && natom > 0 && ntile > 0, "bad sizes");
     HP_REQUIRE(px && py && pz && atom_xyz && atom_point_offsets && atom_shell_offsets, "null input");
@@ -438,27 +528,34 @@ extern "C" int hp_promol_weights_local(int functor, int64_t npts, const double* 
     HP_REQUIRE(!entropy_partials || (rho && molw), "entropy needs rho and molw");
     HP_REQUIRE(radius >= 0.0, "negative radius (use +inf for the dense pass)");
     HP_REQUIRE(atom_eps >= 0.0 && atom_eps < 1e-9, "atom_eps must be in [0, 1e-9)");
+    HP_REQUIRE(atom_lo >= 0 && natom_local >= 0 && atom_lo + natom_local <= natom, "bad local atom range");
+    HP_REQUIRE(nchunk >= 0 && (nchunk == 0 || chunk_offsets), "chunk offsets missing");
+    HP_REQUIRE(!entropy_partials || nchunk == 0 || chunk_scratch, "entropy needs chunk_scratch (nchunk doubles)");
     cudaStream_t st = as_stream(stream);
-    if (npts == 0) {
-        if (entropy_partials) {
-            int rc = check_cuda(cudaMemsetAsync(entropy_partials, 0, sizeof(double) * kMaxPartials, st), "memset");
-            if (rc) return rc;
-        }
-        if (pair_partials)
-            return check_cuda(cudaMemsetAsync(pair_partials, 0, sizeof(uint64_t) * 2 * kMaxPartials, st), "memset");
+    int rc = HP_OK;
+    if (pair_partials) {
+        rc = check_cuda(cudaMemsetAsync(pair_partials, 0, sizeof(uint64_t) * 2 * kMaxPartials, st), "memset");
+        if (rc) return rc;
+    }
+    if (npts == 0 || nchunk == 0) {
+        if (entropy_partials)
+            return check_cuda(cudaMemsetAsync(entropy_partials, 0, sizeof(double) * kMaxPartials, st), "memset");
         return HP_OK;
     }
-    const int64_t span = int64_t(kLocThreads) * kLocPts;
-    int64_t grid = (npts + span - 1) / span;
-    int64_t cap = int64_t(sm_count()) * 2;
-    if (cap > kMaxPartials) cap = kMaxPartials;
-    if (grid > cap) grid = cap;
+    void* counter = nullptr;
+    rc = check_cuda(cudaGetSymbolAddress(&counter, g_loc_work_counter), "cudaGetSymbolAddress");
+    if (rc) return rc;
+    rc = check_cuda(cudaMemsetAsync(counter, 0, sizeof(unsigned long long), st), "memset");
+    if (rc) return rc;
+    int64_t grid = int64_t(sm_count()) * kLocBlocksPerSM;
+    if (grid > nchunk) grid = nchunk;
     const bool local = !isinf(radius);
+    double* chunk_entropy = entropy_partials ? chunk_scratch : nullptr;
 #define HP_LOC_ARGS                                                                                      \
     npts, px, py, pz, point_base, natom, atom_xyz, atom_point_offsets, atom_shell_offsets, shell_A,      \
         shell_alpha, shell_order, ntile, tile_atom_offsets, rho, molw, density_cutoff, promol_offset,    \
-        radius, shell_skip, atom_eps, promol, at_weights, entropy_partials,                              \
-        reinterpret_cast<unsigned long long*>(pair_partials)
+        radius, shell_skip, atom_eps, atom_lo, natom_local, chunk_offsets, promol, at_weights,           \
+        chunk_entropy, reinterpret_cast<unsigned long long*>(pair_partials)
 #define HP_LOC(F)                                                                                        \
     if (local) promol_weights_local_kernel<F, true><<<int(grid), kLocThreads, 0, st>>>(HP_LOC_ARGS);     \
     else promol_weights_local_kernel<F, false><<<int(grid), kLocThreads, 0, st>>>(HP_LOC_ARGS)
@@ -471,5 +568,9 @@ extern "C" int hp_promol_weights_local(int functor, int64_t npts, const double* 
 #undef HP_LOC
 #undef HP_LOC_ARGS
     HP_LAUNCH_CHECK("promol_weights_local_kernel");
+    if (entropy_partials) {
+        fold_chunk_entropy_kernel<<<kMaxPartials / 256, 256, 0, st>>>(nchunk, chunk_scratch, entropy_partials);
+        HP_LAUNCH_CHECK("fold_chunk_entropy_kernel");
+    }
     return HP_OK;
 }

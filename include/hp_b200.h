@@ -139,6 +139,15 @@ HP_API int hp_promol_weights(int functor, int64_t npts, const double* px, const 
 HP_API int hp_shell_screen(int32_t natom, int32_t nshell, const int32_t* atom_shell_offsets,
                            const double* shell_A, const double* shell_alpha, double nbits,
                            double* shell_skip, void* stream);
+/* Chunks: the local points of atom a (atom_point_offsets[a..a+1] - point_base) are cut into pieces of
+ * hp_local_chunk_points() points; chunk_offsets[i] (natom_local + 1 entries, device) = number of chunks
+ * of the local atoms before atom atom_lo + i, nchunk = chunk_offsets[natom_local].  Blocks take chunks
+ * from a global work counter (not re-entrant across streams of one device); chunk_scratch (nchunk
+ * doubles) receives the per-chunk entropy terms, which are folded into entropy_partials in a fixed
+ * order.  pair_partials must hold 2 x hp_num_partials() uint64 ([0] = pairs, [hp_num_partials()] =
+ * shell evaluations of the launch; the rest is zeroed).  Tiles must respect hp_local_tile_limits(). */
+HP_API void hp_local_tile_limits(int32_t* max_atoms_host, int32_t* max_shells_host);
+HP_API int32_t hp_local_chunk_points(void);
 HP_API int hp_promol_weights_local(int functor, int64_t npts, const double* px, const double* py,
                                    const double* pz, int64_t point_base, int32_t natom,
                                    const double* atom_xyz, const int64_t* atom_point_offsets,
@@ -147,8 +156,10 @@ HP_API int hp_promol_weights_local(int functor, int64_t npts, const double* px, 
                                    int32_t ntile, const int32_t* tile_atom_offsets,
                                    const double* rho, const double* molw, double density_cutoff,
                                    double promol_offset, double radius, const double* shell_skip,
-                                   double atom_eps, double* promol, double* at_weights,
-                                   double* entropy_partials, uint64_t* pair_partials, void* stream);
+                                   double atom_eps, int32_t atom_lo, int32_t natom_local,
+                                   const int64_t* chunk_offsets, int64_t nchunk, double* chunk_scratch,
+                                   double* promol, double* at_weights, double* entropy_partials,
+                                   uint64_t* pair_partials, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * (row a8) spherical average of w_a*rho over each radial shell of each atom's own atomic grid.

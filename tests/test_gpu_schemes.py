@@ -72,9 +72,19 @@ def test_alisa_callable_solver_plugin(water6):
     np.testing.assert_allclose(part["history_changes"], ref["history_changes"], rtol=1e-6)
 
 
-def test_alisa_unaccelerated_solver_raises(water6):
-    with pytest.raises(NotImplementedError):
+def test_alisa_third_party_solver_raises_without_the_package(water6):
+    """The default solver name of the reference ("cvxopt") needs the third-party package, exactly
+    like the reference; an unknown name is NotImplementedError (alisa.py:1304-1320)."""
+    try:
+        import cvxopt  # noqa: F401
+
+        pytest.skip("cvxopt present")
+    except ImportError:
+        pass
+    with pytest.raises(ImportError, match="cvxopt"):
         _run("LinearISAWPart", water6, solver="cvxopt")
+    with pytest.raises(NotImplementedError):
+        _run("LinearISAWPart", water6, solver="no-such-solver")
 
 
 def test_nlis_gmbis_h2o_against_reference_run(h2o):

@@ -82,7 +82,9 @@ def test_gisa_against_reference_run(water6, water6g, tag):
     np.testing.assert_allclose(part["propars"], ref["propars"], rtol=1e-6, atol=1e-8)
     # near convergence the changes (1e-6) carry the 1e-11 noise of two different exact QP solvers
     np.testing.assert_allclose(part["history_changes"], ref["history_changes"], rtol=1e-5, atol=1e-10)
-    assert (part["propars"] >= 0).all() and (part["propars"] == 0).any()  # active bounds are exact zeros
+    assert (part["propars"] >= 0).all()
+    if tag == "s/gisa":  # some Gaussians are switched off entirely: active bounds are exact zeros
+        assert (part["propars"] == 0).any()
 
 
 GLISA = {
