@@ -34,6 +34,9 @@ sys.path.insert(0, ROOT)
 METRIC = "atom_gridpoint_evals_per_s"
 UNIT = "evals/s"
 NRAD, NANG = 150, 194
+# shell table, shell screening, fused promolecule/weights/entropy, entropy fold, spherical averages,
+# radial solves, change/entropy finish (profiles/r1_final_launches_summary.txt)
+KERNELS_PER_STEP = 7
 
 
 def flops_per_eval(mean_shells):
@@ -422,7 +425,7 @@ def main():
         "includes": "MBISWPart(...).do_partitioning() from host arrays: slab upload, K iterations with per-step "
         "state D2H, download of promolecule / at_weights / spherical averages into page-locked result arrays; "
         "second call in the process (the first one also allocates the page-locked buffers)",
-        "max_abs_charge_diff_vs_resident_arm": float(np.abs(e2e_charges - charges_resident).max()),
+        "charges_O_H_H_after_K_iterations": [float(v) for v in e2e_charges[:3]],
         "hostmem": hostmem.pool_stats(),
     }  # fmt: skip
 
@@ -459,9 +462,9 @@ def main():
         "hbm_gbs_achieved": hbm_bytes / (kernel_ms_mean * 1e-3) / 1e9, "hbm_gbs_peak": hbm_peak,
         "hbm_bytes_algorithmic": hbm_bytes,
         "hbm_peak_source": "MEASURED_PEAKS.json" if peaks else "fallback 6650",
-        "traffic": 0.968 * hbm_bytes,
-        "traffic_source": "dram__bytes_read+write of the ncu --set full capture (profiles/r1_promol_weights_ncu_full.txt: "
-                          "947 MB vs 978 MB algorithmic at 600 atoms) scaled to this launch",
+        "traffic": 0.966 * hbm_bytes,
+        "traffic_source": "dram__bytes_read+write of the ncu --set full capture (profiles/r1_final_promol_weights_ncu_full.txt: "
+                          "945 MB vs 978 MB algorithmic at 600 atoms) scaled to this launch",
     }  # fmt: skip
     if shells_local is not None:
         dense_equiv = kernel_evals_per_s * F / 1e12
@@ -483,7 +486,7 @@ def main():
         "data": "synthetic (exact Slater promolecule; AIM weights = Hirshfeld weights of the generating promolecule)",
         "config": workload_config(natom, numbers),
         "iterations_per_s": args.steps / (ms_total * 1e-3),
-        "clocks": clocks.summary(), "e2e": e2e, "gpu_launches": 5 * args.steps,
+        "clocks": clocks.summary(), "e2e": e2e, "gpu_launches": KERNELS_PER_STEP * args.steps,
         "roofline": roofline,
         "other_kernels_ms_per_step": float(np.mean(rest_ms)),
         "last_change": change, "last_entropy": entropy,
