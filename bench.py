@@ -245,6 +245,12 @@ def main():
         run_reference_arm(args, rank, world)
         return
 
+    # Only the JSON line may reach stdout: libraries (NCCL's version banner) write to fd 1 directly,
+    # so fd 1 points at stderr until the line is printed.
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
+
     import torch
     import torch.distributed as dist
 
@@ -270,7 +276,10 @@ def main():
     # ---- synthetic inputs (untimed): geometry + grid on the host, density / AIM weights on the GPU
     coords, numbers, grid = build_system(args.natom)
     natom, npts = args.natom, grid.size
-    shard = Shard(natom, grid.indices, rank, world)
+    from horton_part_b200.mbis import mbis_atom_work
+
+    # the same work-balanced atom-block split MBISWPart makes (cut-off mode balances by points)
+    shard = Shard(natom, grid.indices, rank, world, work=mbis_atom_work(coords, numbers, grid) if world > 1 else None)
     rho_loc, w_loc, lo, hi = synthetic.slater_promolecule_device(grid, coords, numbers, device=dev, shard=shard)
     rho = np.zeros(npts)
     rho[lo:hi] = rho_loc
@@ -357,7 +366,7 @@ def main():
 
     # ---- extra: the same iterations in cut-off (local grid) mode, credited for evaluated pairs only
     cutoff = None
-    if args.local_radius > 0:
+    if args.local_radius > 0 and world == 1:  # (sharded runs balance the dense pass; extra skipped there)
         part_c = MBISWPart(coords, numbers, pseudo, grid, rho, device=dev, comm=comm, maxiter=nsteps,
                            local_radius=args.local_radius)
         part_c._init_propars()
@@ -496,7 +505,8 @@ def main():
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(coords, numbers, grid, os.cpu_count() or 1, points_per_core=args.cpu_points, reps=args.cpu_reps)
     if rank == 0:
-        print(json.dumps(line))
+        os.write(json_fd, (json.dumps(line) + "\n").encode())
+    os.close(json_fd)
     if comm is not None:
         dist.destroy_process_group()
 

@@ -327,6 +327,10 @@ class WPart(Part):
         return data[begin:end]
 
     # -- device plumbing -----------------------------------------------------------------------
+    def _estimate_atom_work(self):
+        """Per-atom load-balancing weights of a sharded run (None = balance by point count)."""
+        return None
+
     @property
     def slab(self):
         """Device-resident grid slab of this rank (uploaded on first use)."""
@@ -338,7 +342,7 @@ class WPart(Part):
                 import torch.distributed as dist
 
                 shard = Shard(self.natom, self._grid.indices, dist.get_rank(self._comm),
-                              dist.get_world_size(self._comm))  # fmt: skip
+                              dist.get_world_size(self._comm), work=self._estimate_atom_work())  # fmt: skip
             self._slab = GridSlab(self._grid, self._moldens, self.coordinates, self._device, shard,
                                   need_atgrids=self.local)  # fmt: skip
         return self._slab

@@ -23,7 +23,7 @@ import numpy as np
 
 from .. import _lib
 
-__all__ = ["Shard", "GridSlab", "ShellTable", "require_cuda", "to_device", "stream_ptr"]
+__all__ = ["Shard", "GridSlab", "ShellTable", "require_cuda", "to_device", "stream_ptr", "estimate_dense_work"]
 
 
 def require_cuda(device=None):
@@ -52,20 +52,80 @@ def stream_ptr(device):
     return torch.cuda.current_stream(device).cuda_stream
 
 
+def estimate_dense_work(coordinates, grid, shells, gaussian=False, chunk_points=1024, eps=None):
+    """Atom x point pairs the screened dense pass will evaluate in each atom's block (host, geometry
+    only): the load-balancing weight of the sharding.
+
+    For every chunk of an atom's points (``chunk_points`` consecutive points = a few radial shells,
+    outer radius r_c) the kernel keeps atom b if an upper bound of its pro-atom at distance
+    D_ab - r_c is above ``eps`` times the owner's pro-atom at r_c (hp_promol_local.cu).  With every
+    atom's pro-atom bounded by its total amplitude on its most diffuse exponent this becomes a
+    neighbour count inside a radius, done with a k-d tree.  ``shells[a] = (A_k, alpha_k)`` arrays.
+    """
+    from scipy.spatial import cKDTree
+
+    xyz = np.asarray(coordinates, float)
+    natom = len(xyz)
+    if eps is None:
+        eps = 2.0 ** -(55 + int(np.ceil(np.log2(max(natom, 2)))))
+    a_sum = max(float(np.sum(np.abs(A))) for A, _ in shells)
+    al_min = min(float(np.min(al)) for _, al in shells if len(al))
+    tree = cKDTree(xyz)
+    work = np.zeros(natom)
+    cache = {}
+    for a in range(natom):
+        atgrid = grid.atgrids[a]
+        key = (id(atgrid.rgrid), tuple(np.asarray(atgrid.indices)[[0, -1]]), tuple(shells[a][0]), tuple(shells[a][1]))
+        plan = cache.get(key)
+        if plan is None:
+            r = np.asarray(atgrid.rgrid.points, float)
+            idx = np.asarray(atgrid.indices, dtype=np.int64)
+            npts = int(idx[-1])
+            r_of_point = np.repeat(r, np.diff(idx))
+            radii, counts = [], []
+            for lo in range(0, npts, chunk_points):
+                hi = min(lo + chunk_points, npts)
+                rc = float(r_of_point[lo:hi].max())
+                x = rc * rc if gaussian else rc
+                lb = float(np.sum(shells[a][0] * np.exp(-shells[a][1] * x)))
+                if lb <= 1e-80:
+                    radii.append(np.inf)
+                else:
+                    reach = np.log(a_sum / (eps * lb)) / al_min
+                    radii.append(rc + (np.sqrt(reach) if gaussian else reach))
+                counts.append(hi - lo)
+            plan = cache[key] = (np.asarray(radii), np.asarray(counts))
+        radii, counts = plan
+        finite = np.isfinite(radii)
+        near = np.zeros(len(radii))
+        if finite.any():
+            near[finite] = tree.query_ball_point(np.repeat(xyz[a][None, :], finite.sum(), axis=0), radii[finite],
+                                                 return_length=True)
+        near[~finite] = natom
+        work[a] = float(np.sum(np.minimum(near, natom) * counts))
+    return work
+
+
 class Shard:
     """Contiguous range of atom blocks [atom_lo, atom_hi) owned by one rank.
 
     The molecular grid is the concatenation of per-atom grids, so whole atom blocks are assigned to
-    ranks, balanced by point count (dense mode: work per point is identical).  SURVEY.md 8(e).
+    ranks.  Balanced by point count, or -- when ``work`` gives an estimate of the
+    pairs each atom's block will evaluate (``estimate_dense_work``: the screened dense pass does less
+    work for atoms at the surface of a cluster) -- by that estimate.
     """
 
-    def __init__(self, natom, atom_point_offsets, rank=0, world=1):
+    def __init__(self, natom, atom_point_offsets, rank=0, world=1, work=None):
         self.rank, self.world, self.natom = rank, world, natom
         off = np.asarray(atom_point_offsets, dtype=np.int64)
-        total = int(off[-1])
-        # boundary b_k = first atom whose start offset >= k/world of the points
+        if work is not None and world > 1:
+            cum = np.concatenate([[0.0], np.cumsum(np.asarray(work, float))])
+        else:
+            cum = off.astype(float)
+        total = float(cum[-1])
+        # boundary b_k = first atom whose start offset >= k/world of the points (or of the work)
         targets = (np.arange(1, world) * total) / world
-        cuts = np.searchsorted(off[:-1], targets, side="left") if world > 1 else np.array([], int)
+        cuts = np.searchsorted(cum[:-1], targets, side="left") if world > 1 else np.array([], int)
         bounds = np.concatenate([[0], cuts, [natom]]).astype(np.int64)
         bounds = np.maximum.accumulate(bounds)
         self.bounds = bounds

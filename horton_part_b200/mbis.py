@@ -45,6 +45,18 @@ def get_initial_mbis_propars(number: int):
     return propars
 
 
+def mbis_atom_work(coordinates, numbers, grid):
+    """Pairs the screened dense pass evaluates per atom block, estimated from the initial MBIS
+    parameters: the load-balancing weights of a sharded run (``core.device.Shard(work=...)``)."""
+    from .core.device import estimate_dense_work
+
+    shells = []
+    for z in numbers:
+        p = get_initial_mbis_propars(z)
+        shells.append((p[0::2] * p[1::2] ** 3 / (8 * np.pi), p[1::2]))
+    return estimate_dense_work(coordinates, grid, shells)
+
+
 class MBISWPart(AbstractISAWPart):
     """Minimal Basis Iterative Stockholder (MBIS)"""
 
@@ -84,6 +96,12 @@ class MBISWPart(AbstractISAWPart):
         return y, d
 
     # -- device hooks ---------------------------------------------------------------------------
+    def _estimate_atom_work(self):
+        """Pairs the screened dense pass evaluates per atom block, from the initial parameters."""
+        if self.on_molgrid or self._local_radius is not None or self._grid.atgrids is None:
+            return None
+        return mbis_atom_work(self.coordinates, self.numbers, self._grid)
+
     def _init_propars(self):
         from .core.device import ShellTable, to_device
 

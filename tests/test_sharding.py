@@ -29,6 +29,35 @@ def test_shard_partition_covers_all_atoms():
                 assert max(s.nlocal for s in shards) - min(s.nlocal for s in shards) <= 1
 
 
+def test_work_balanced_sharding_of_the_screened_dense_pass():
+    """The screened dense pass does less work for atoms at the surface of a cluster: balancing atom
+    blocks by the geometric work estimate evens out the ranks (by points they differ by ~10 %)."""
+    from horton_part_b200 import gridlite, synthetic
+    from horton_part_b200.core.device import Shard
+    from horton_part_b200.mbis import mbis_atom_work
+
+    natom = 1200
+    coords, numbers = synthetic.water_cluster(natom, 0)
+    rgrid = gridlite.BeckeRTransform(1e-4, 1.5).transform_1d_grid(gridlite.GaussChebyshev(150))
+    grid = gridlite.MolGrid.from_size(numbers, coords, 194, rgrid, np.ones(natom * 150 * 194), store=True)
+    work = mbis_atom_work(coords, numbers, grid)
+    npts = np.diff(grid.indices)
+    assert work.shape == (natom,) and (work > 0).all() and (work <= natom * npts).all()
+    assert work.min() < 0.8 * work.max()  # surface vs interior
+    for world in (2, 4, 8):
+        by_work = [Shard(natom, grid.indices, r, world, work=work) for r in range(world)]
+        by_points = [Shard(natom, grid.indices, r, world) for r in range(world)]
+        assert by_work[0].atom_lo == 0 and by_work[-1].atom_hi == natom
+        for a, b in zip(by_work[:-1], by_work[1:]):
+            assert a.atom_hi == b.atom_lo and a.point_hi == b.point_lo
+        load = lambda shards: np.array([work[s.atom_lo : s.atom_hi].sum() for s in shards])  # noqa: E731
+        lw, lp = load(by_work), load(by_points)
+        assert lw.max() / lw.mean() < 1.02
+        assert lw.max() / lw.mean() <= lp.max() / lp.mean() + 1e-12
+    # one rank: the estimate is not needed and ignored
+    assert Shard(natom, grid.indices, 0, 1, work=work).nlocal == natom
+
+
 def _free_port():
     with socket.socket() as s:
         s.bind(("127.0.0.1", 0))
