@@ -279,7 +279,7 @@ def main():
     from horton_part_b200.mbis import mbis_atom_work
 
     # the same work-balanced atom-block split MBISWPart makes (cut-off mode balances by points)
-    shard = Shard(natom, grid.indices, rank, world, work=mbis_atom_work(coords, numbers, grid) if world > 1 else None)
+    shard = Shard(natom, grid.indices, rank, world, work=mbis_atom_work(coords, numbers, grid, dev) if world > 1 else None)
     rho_loc, w_loc, lo, hi = synthetic.slater_promolecule_device(grid, coords, numbers, device=dev, shard=shard)
     rho = np.zeros(npts)
     rho[lo:hi] = rho_loc

@@ -95,6 +95,7 @@ EXPORTS = {
     "hp_segment_integrate": (_int, [_i32, _p, _p, _p, _p, _p, _p]),
     "hp_atom_moments": (_int, [_i32, _i32, _i32, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
     "hp_becke_weights": (_int, [_i64, _p, _p, _p, _i64, _i32, _p, _p, _p, _p, _i32, _p, _p]),
+    "hp_neighbor_counts": (_int, [_i32, _p, _p, _i32, _i32, _p, _p, _p]),
     "hp_host_is_pinned": (_int, [_p]),
     "hp_host_to_device": (_int, [_p, _p, _sz, _p, _sz, _i32, _p]),
     "hp_dfma_probe": (_int, [_i32, _p, _p, _p, _p]),

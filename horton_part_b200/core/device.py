@@ -52,57 +52,85 @@ def stream_ptr(device):
     return torch.cuda.current_stream(device).cuda_stream
 
 
-def estimate_dense_work(coordinates, grid, shells, gaussian=False, chunk_points=1024, eps=None):
-    """Atom x point pairs the screened dense pass will evaluate in each atom's block (host, geometry
-    only): the load-balancing weight of the sharding.
+def _reach(A, alpha, targets, gaussian):
+    """Distances d at which sum_k A_k exp(-alpha_k x(d)) has fallen to each of ``targets`` (x = d or
+    d^2): vectorised bisection on the monotone pro-atom bound; 0 where it is below the target at 0."""
+    A, alpha = np.abs(np.asarray(A, float))[None, :], np.asarray(alpha, float)[None, :]
+    t = np.asarray(targets, float)
+    f = lambda d: np.sum(A * np.exp(-alpha * ((d * d) if gaussian else d)[:, None]), axis=1)  # noqa: E731
+    lo, hi = np.zeros_like(t), np.ones_like(t)
+    for _ in range(40):  # bracket
+        grow = f(hi) > t
+        if not grow.any():
+            break
+        lo = np.where(grow, hi, lo)
+        hi = np.where(grow, 2.0 * hi, hi)
+    for _ in range(50):
+        mid = 0.5 * (lo + hi)
+        above = f(mid) > t
+        lo, hi = np.where(above, mid, lo), np.where(above, hi, mid)
+    return np.where(f(np.zeros_like(t)) <= t, 0.0, hi)
+
+
+def estimate_dense_work(coordinates, grid, shells, gaussian=False, chunk_points=1024, eps=None, kinds=None,
+                        device=None):
+    """Atom x point pairs the screened dense pass will evaluate in each atom's block: the
+    load-balancing weight of the sharding (geometry only, a few milliseconds).
 
     For every chunk of an atom's points (``chunk_points`` consecutive points = a few radial shells,
     outer radius r_c) the kernel keeps atom b if an upper bound of its pro-atom at distance
-    D_ab - r_c is above ``eps`` times the owner's pro-atom at r_c (hp_promol_local.cu).  With every
-    atom's pro-atom bounded by its total amplitude on its most diffuse exponent this becomes a
-    neighbour count inside a radius, done with a k-d tree.  ``shells[a] = (A_k, alpha_k)`` arrays.
+    D_ab - r_c is above ``eps`` times the owner's pro-atom at r_c (hp_promol_local.cu).  Per kind of
+    atom (same radial grid and shells) that is a neighbour count inside one radius per chunk and
+    neighbour kind; the radii are solved on the host, the counting runs on the device
+    (``hp_neighbor_counts``).  ``shells[a] = (A_k, alpha_k)``; ``kinds[a]`` labels atoms with identical
+    grids and shells (default: derived from both).  Returns None when an atom block has more than
+    128 chunks (the caller then balances by points).
     """
-    from scipy.spatial import cKDTree
+    import torch
 
-    xyz = np.asarray(coordinates, float)
+    xyz = np.ascontiguousarray(coordinates, dtype=np.float64)
     natom = len(xyz)
     if eps is None:
         eps = 2.0 ** -(55 + int(np.ceil(np.log2(max(natom, 2)))))
-    a_sum = max(float(np.sum(np.abs(A))) for A, _ in shells)
-    al_min = min(float(np.min(al)) for _, al in shells if len(al))
-    tree = cKDTree(xyz)
+    if kinds is None:
+        kinds = []
+        for a in range(natom):
+            g = grid.atgrids[a]
+            kinds.append((id(g.rgrid), int(g.size), tuple(shells[a][0]), tuple(shells[a][1])))
+    labels = {}
+    kind_of = np.array([labels.setdefault(k, len(labels)) for k in kinds], dtype=np.int32)
+    nkind = len(labels)
+    first = [int(np.flatnonzero(kind_of == k)[0]) for k in range(nkind)]
+    plans = []
+    for a0 in first:
+        atgrid = grid.atgrids[a0]
+        idx = np.asarray(atgrid.indices, dtype=np.int64)
+        r_of_point = np.repeat(np.asarray(atgrid.rgrid.points, float), np.diff(idx))
+        starts = np.arange(0, int(idx[-1]), chunk_points)
+        sizes = np.minimum(starts + chunk_points, int(idx[-1])) - starts
+        rc = np.maximum.reduceat(r_of_point, starts)  # outer radius of every chunk
+        x = rc * rc if gaussian else rc
+        lb = np.sum(shells[a0][0][None, :] * np.exp(-shells[a0][1][None, :] * x[:, None]), axis=1)
+        plans.append((rc, lb, sizes.astype(float)))
+    nrad = max(len(p[0]) for p in plans)
+    if nrad > 128:
+        return None
+    radii2 = np.full((nkind, nkind, nrad), -1.0)  # -1: no such chunk (never matched)
+    for k, (rc, lb, _) in enumerate(plans):
+        live = lb > 1e-80
+        for k2, b0 in enumerate(first):
+            reach = _reach(shells[b0][0], shells[b0][1], eps * np.where(live, lb, 1.0), gaussian)
+            radii2[k, k2, : len(rc)] = np.where(live, (rc + reach) ** 2, np.inf)
+    dev = require_cuda(device)
+    counts = torch.zeros((natom, nrad), dtype=torch.float64, device=dev)
+    _lib.call("hp_neighbor_counts", natom, to_device(xyz, dev), to_device(kind_of, dev, np.int32), nkind, nrad,
+              to_device(radii2, dev), counts, stream_ptr(dev))  # fmt: skip
+    counts = counts.cpu().numpy()
+    setup_points = 16.0  # cost of screening one atom for one chunk, in point evaluations
     work = np.zeros(natom)
-    cache = {}
-    for a in range(natom):
-        atgrid = grid.atgrids[a]
-        key = (id(atgrid.rgrid), tuple(np.asarray(atgrid.indices)[[0, -1]]), tuple(shells[a][0]), tuple(shells[a][1]))
-        plan = cache.get(key)
-        if plan is None:
-            r = np.asarray(atgrid.rgrid.points, float)
-            idx = np.asarray(atgrid.indices, dtype=np.int64)
-            npts = int(idx[-1])
-            r_of_point = np.repeat(r, np.diff(idx))
-            radii, counts = [], []
-            for lo in range(0, npts, chunk_points):
-                hi = min(lo + chunk_points, npts)
-                rc = float(r_of_point[lo:hi].max())
-                x = rc * rc if gaussian else rc
-                lb = float(np.sum(shells[a][0] * np.exp(-shells[a][1] * x)))
-                if lb <= 1e-80:
-                    radii.append(np.inf)
-                else:
-                    reach = np.log(a_sum / (eps * lb)) / al_min
-                    radii.append(rc + (np.sqrt(reach) if gaussian else reach))
-                counts.append(hi - lo)
-            plan = cache[key] = (np.asarray(radii), np.asarray(counts))
-        radii, counts = plan
-        finite = np.isfinite(radii)
-        near = np.zeros(len(radii))
-        if finite.any():
-            near[finite] = tree.query_ball_point(np.repeat(xyz[a][None, :], finite.sum(), axis=0), radii[finite],
-                                                 return_length=True)
-        near[~finite] = natom
-        work[a] = float(np.sum(np.minimum(near, natom) * counts))
+    for k, (rc, _, sizes) in enumerate(plans):
+        own = kind_of == k
+        work[own] = counts[own, : len(rc)] @ sizes + setup_points * natom * len(rc)
     return work
 
 

@@ -144,6 +144,31 @@ split_points_kernel(const double* __restrict__ pts, int64_t npts, double* __rest
     }
 }
 
+// Neighbour counts for the sharding work estimate (core/device.py estimate_dense_work): for atom a
+// and threshold c,  counts[a][c] = #{ b : |R_a - R_b|^2 <= radii2[kind_a][kind_b][c] }.
+// One block per atom, atoms b strided over the threads; nrad <= kMaxCountRadii.
+constexpr int kMaxCountRadii = 128;
+
+__global__ void __launch_bounds__(128)
+neighbor_counts_kernel(int natom, const double* __restrict__ xyz, const int* __restrict__ kind, int nkind,
+                       int nrad, const double* __restrict__ radii2, double* __restrict__ counts) {
+    __shared__ int s_cnt[kMaxCountRadii];
+    const int a = blockIdx.x;
+    for (int c = threadIdx.x; c < nrad; c += blockDim.x) s_cnt[c] = 0;
+    __syncthreads();
+    const double ax = xyz[3 * a], ay = xyz[3 * a + 1], az = xyz[3 * a + 2];
+    const double* row = radii2 + size_t(kind[a]) * nkind * nrad;
+    for (int b = threadIdx.x; b < natom; b += blockDim.x) {
+        const double dx = xyz[3 * b] - ax, dy = xyz[3 * b + 1] - ay, dz = xyz[3 * b + 2] - az;
+        const double d2 = dx * dx + dy * dy + dz * dz;
+        const double* r2 = row + size_t(kind[b]) * nrad;
+        for (int c = 0; c < nrad; ++c)
+            if (d2 <= r2[c]) atomicAdd(&s_cnt[c], 1);
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < nrad; c += blockDim.x) counts[size_t(a) * nrad + c] = double(s_cnt[c]);
+}
+
 }  // namespace hp
 
 using namespace hp;
@@ -190,5 +215,16 @@ extern "C" int hp_split_points(const double* points_xyz, int64_t npts, double* p
     HP_REQUIRE(blocks < (int64_t(1) << 31), "grid too large for one launch");
     split_points_kernel<<<int(blocks), 256, 0, as_stream(stream)>>>(points_xyz, npts, px, py, pz);
     HP_LAUNCH_CHECK("split_points_kernel");
+    return HP_OK;
+}
+
+extern "C" int hp_neighbor_counts(int32_t natom, const double* atom_xyz, const int32_t* kind, int32_t nkind,
+                                  int32_t nrad, const double* radii2, double* counts, void* stream) {
+    HP_REQUIRE(natom >= 0 && nkind > 0 && nrad > 0, "bad sizes");
+    HP_REQUIRE(nrad <= kMaxCountRadii, "too many radii (max 128)");
+    if (natom == 0) return HP_OK;
+    HP_REQUIRE(atom_xyz && kind && radii2 && counts, "null buffer");
+    neighbor_counts_kernel<<<natom, 128, 0, as_stream(stream)>>>(natom, atom_xyz, kind, nkind, nrad, radii2, counts);
+    HP_LAUNCH_CHECK("neighbor_counts_kernel");
     return HP_OK;
 }

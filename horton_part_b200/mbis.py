@@ -45,16 +45,18 @@ def get_initial_mbis_propars(number: int):
     return propars
 
 
-def mbis_atom_work(coordinates, numbers, grid):
+def mbis_atom_work(coordinates, numbers, grid, device=None):
     """Pairs the screened dense pass evaluates per atom block, estimated from the initial MBIS
     parameters: the load-balancing weights of a sharded run (``core.device.Shard(work=...)``)."""
     from .core.device import estimate_dense_work
 
-    shells = []
-    for z in numbers:
-        p = get_initial_mbis_propars(z)
-        shells.append((p[0::2] * p[1::2] ** 3 / (8 * np.pi), p[1::2]))
-    return estimate_dense_work(coordinates, grid, shells)
+    per_element = {}
+    for z in np.unique(numbers):
+        p = get_initial_mbis_propars(int(z))
+        per_element[int(z)] = (p[0::2] * p[1::2] ** 3 / (8 * np.pi), p[1::2])
+    shells = [per_element[int(z)] for z in numbers]
+    kinds = [(int(z), id(grid.atgrids[a].rgrid), int(grid.atgrids[a].size)) for a, z in enumerate(numbers)]
+    return estimate_dense_work(coordinates, grid, shells, kinds=kinds, device=device)
 
 
 class MBISWPart(AbstractISAWPart):
@@ -100,7 +102,7 @@ class MBISWPart(AbstractISAWPart):
         """Pairs the screened dense pass evaluates per atom block, from the initial parameters."""
         if self.on_molgrid or self._local_radius is not None or self._grid.atgrids is None:
             return None
-        return mbis_atom_work(self.coordinates, self.numbers, self._grid)
+        return mbis_atom_work(self.coordinates, self.numbers, self._grid, self._device)
 
     def _init_propars(self):
         from .core.device import ShellTable, to_device

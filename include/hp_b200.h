@@ -367,6 +367,13 @@ HP_API int hp_becke_weights(int64_t npts, const double* px, const double* py, co
                             const int64_t* atom_point_offsets, const double* inv_rab, const double* aab,
                             int32_t order, double* out, void* stream);
 
+/* (section 8e) Neighbour counts behind the work-balanced sharding of the screened dense pass:
+ * counts[a*nrad + c] = number of atoms b with |R_a - R_b|^2 <= radii2[(kind[a]*nkind + kind[b])*nrad + c]
+ * (kind = class of atoms sharing radial grid and shells; nrad <= 128 thresholds = the chunks of an
+ * atom block).  Everything on the device; counts as doubles. */
+HP_API int hp_neighbor_counts(int32_t natom, const double* atom_xyz, const int32_t* kind, int32_t nkind,
+                              int32_t nrad, const double* radii2, double* counts, void* stream);
+
 /* Slab upload helpers (the boundary takes NumPy arrays = pageable host memory; the reference never
  * leaves the host, core/base.py:416-431 keeps `grid.points`, `grid.weights`, `moldens` as given).
  * hp_host_is_pinned: 1 if the host pointer is page-locked (registered with CUDA), else 0.

@@ -29,33 +29,42 @@ def test_shard_partition_covers_all_atoms():
                 assert max(s.nlocal for s in shards) - min(s.nlocal for s in shards) <= 1
 
 
-def test_work_balanced_sharding_of_the_screened_dense_pass():
-    """The screened dense pass does less work for atoms at the surface of a cluster: balancing atom
-    blocks by the geometric work estimate evens out the ranks (by points they differ by ~10 %)."""
-    from horton_part_b200 import gridlite, synthetic
+def test_work_balanced_shard_boundaries():
+    """Shard(work=...) cuts the atom list at equal cumulative work; without weights at equal points."""
     from horton_part_b200.core.device import Shard
-    from horton_part_b200.mbis import mbis_atom_work
 
-    natom = 1200
-    coords, numbers = synthetic.water_cluster(natom, 0)
-    rgrid = gridlite.BeckeRTransform(1e-4, 1.5).transform_1d_grid(gridlite.GaussChebyshev(150))
-    grid = gridlite.MolGrid.from_size(numbers, coords, 194, rgrid, np.ones(natom * 150 * 194), store=True)
-    work = mbis_atom_work(coords, numbers, grid)
-    npts = np.diff(grid.indices)
-    assert work.shape == (natom,) and (work > 0).all() and (work <= natom * npts).all()
-    assert work.min() < 0.8 * work.max()  # surface vs interior
+    natom = 1000
+    off = np.arange(natom + 1) * 29100
+    rng = np.random.default_rng(2)
+    work = 1.0 + np.sin(np.linspace(0, np.pi, natom)) + 0.05 * rng.random(natom)  # light ends, heavy middle
     for world in (2, 4, 8):
-        by_work = [Shard(natom, grid.indices, r, world, work=work) for r in range(world)]
-        by_points = [Shard(natom, grid.indices, r, world) for r in range(world)]
+        by_work = [Shard(natom, off, r, world, work=work) for r in range(world)]
+        by_points = [Shard(natom, off, r, world) for r in range(world)]
         assert by_work[0].atom_lo == 0 and by_work[-1].atom_hi == natom
         for a, b in zip(by_work[:-1], by_work[1:]):
             assert a.atom_hi == b.atom_lo and a.point_hi == b.point_lo
         load = lambda shards: np.array([work[s.atom_lo : s.atom_hi].sum() for s in shards])  # noqa: E731
         lw, lp = load(by_work), load(by_points)
         assert lw.max() / lw.mean() < 1.02
-        assert lw.max() / lw.mean() <= lp.max() / lp.mean() + 1e-12
-    # one rank: the estimate is not needed and ignored
-    assert Shard(natom, grid.indices, 0, 1, work=work).nlocal == natom
+        if world > 2:  # (two ranks: the profile is symmetric, both splits are even)
+            assert lw.max() / lw.mean() < lp.max() / lp.mean()
+            assert by_work[0].nlocal > by_points[0].nlocal  # the light end gets more atoms
+    assert Shard(natom, off, 0, 1, work=work).nlocal == natom  # one rank: weights ignored
+
+
+def test_proatom_reach_solver():
+    """Radius at which a pro-atom bound has decayed to a target (used by the work estimate)."""
+    from horton_part_b200.core.device import _reach
+
+    A, alpha = np.array([326.0, 1.9]), np.array([16.0, 2.0])
+    targets = np.array([1e3, 1.0, 1e-10, 1e-25])
+    for gaussian in (False, True):
+        d = _reach(A, alpha, targets, gaussian)
+        x = d * d if gaussian else d
+        val = (A[None, :] * np.exp(-alpha[None, :] * x[:, None])).sum(1)
+        assert d[0] == 0.0  # already below the target at the nucleus
+        np.testing.assert_allclose(val[1:], targets[1:], rtol=1e-9)
+        assert (np.diff(d) > 0).all()
 
 
 def _free_port():
