@@ -402,8 +402,77 @@ def case_postproc():
     print("  becke q", out["becke/charges"], " c6", out["hi/c6s"])
 
 
+def _load_molecule(name, rgrid):
+    """A molecule of the reference's test suite on its own grid (tests/common.py:38-61): density
+    re-ordered onto the rebuilt Becke-Lebedev grid."""
+    from scipy.spatial import cKDTree
+
+    npz = np.load(REF_CACHED / name)
+    coords, numbers, pseudo = npz["coordinates"], npz["numbers"], npz["pseudo_numbers"]
+    grid = qcgrid.MolGrid.from_size(numbers, coords, 110, rgrid, qcgrid.BeckeWeights(), rotate=False, store=True)
+    dist, order = cKDTree(npz["points"]).query(grid.points)
+    assert dist.max() < 1e-6 and len(set(order)) == grid.size
+    return coords, numbers, pseudo, grid, npz["dens"][order]
+
+
+def case_molecules():
+    """Two more molecules of the reference's own tests: N2 (tests/test_becke.py:31-57) and
+    monosilicic acid with LANL effective core potentials, i.e. pseudo_numbers != numbers
+    (tests/test_wpart.py:104-217), with the hf_lan pro-atom database."""
+    import contextlib
+    import io
+
+    from horton_part.core.proatomdb import ProAtomDB, ProAtomRecord
+
+    out = {}
+    rg = qcgrid.ExpRTransform(1e-3, 1e1, 99).transform_1d_grid(qcgrid.UniformInteger(100))
+    coords, numbers, pseudo, grid, rho = _load_molecule("n2_hfs_sto3g_fchk_exp:1e-3:1e1:100:110.npz", rg)
+    out.update({"n2/coordinates": coords, "n2/numbers": numbers, "n2/pseudo_numbers": pseudo, "n2/dens": rho,
+                "n2/aim_weights_sample": grid.aim_weights[::211].copy()})
+    for tag, scheme in (("becke", "b"), ("mbis", "mbis"), ("isa", "is")):
+        with contextlib.redirect_stdout(io.StringIO()):
+            part = wpart_schemes(scheme)(coords, numbers, pseudo, grid, rho)
+            part.do_charges()
+        out[f"n2/{tag}/charges"] = part["charges"]
+        out[f"n2/{tag}/populations"] = part["populations"]
+        if "niter" in part.cache:
+            out[f"n2/{tag}/niter"] = np.int64(part["niter"])
+        print(f"  n2 {tag}: q={part['charges']} niter={out.get(f'n2/{tag}/niter')}")
+
+    rg = qcgrid.ExpRTransform(5e-4, 2e1, 119).transform_1d_grid(qcgrid.UniformInteger(120))
+    coords, numbers, pseudo, grid, rho = _load_molecule("monosilicic_acid_hf_lan_fchk_exp:5e-4:2e1:120:110.npz", rg)
+    out.update({"msa/coordinates": coords, "msa/numbers": numbers, "msa/pseudo_numbers": pseudo, "msa/dens": rho,
+                "msa/aim_weights_sample": grid.aim_weights[::211].copy()})
+    records = []
+    for z in (14, 8, 1):
+        for path in sorted(REF_CACHED.glob(f"atom_hf_lan_Z{z:02d}_N*_pow.npz")):
+            with np.load(path) as f:
+                number, charge, energy = int(f["number"]), int(f["charge"]), float(f["energy"])
+                rmin, rmax, npoint = f["rgrid"]
+                pn = float(f["pseudo_number"]) if "pseudo_number" in f.files else float(number)
+                r = qcgrid.PowerRTransform(rmin, rmax, int(npoint) - 1).transform_1d_grid(qcgrid.UniformInteger(int(npoint)))
+                records.append(ProAtomRecord(number, charge, energy, r, f["dens"], f["deriv"], pseudo_number=pn))
+                out[f"msa/record/Z{number}_q{charge}"] = np.concatenate(
+                    [[number, charge, energy, rmin, rmax, npoint, pn], f["dens"], f["deriv"]])
+    for tag, scheme, kw in (("h", "h", dict(proatomdb=ProAtomDB(records))), ("hi", "hi", dict(proatomdb=ProAtomDB(records))),
+                            ("isa", "is", {}), ("mbis", "mbis", {})):
+        with contextlib.redirect_stdout(io.StringIO()):
+            part = wpart_schemes(scheme)(coords, numbers, pseudo, grid, rho, **kw)
+            part.do_charges()
+        out[f"msa/{tag}/charges"] = part["charges"]
+        out[f"msa/{tag}/populations"] = part["populations"]
+        out[f"msa/{tag}/pseudo_populations"] = part["pseudo_populations"]
+        if "niter" in part.cache:
+            out[f"msa/{tag}/niter"] = np.int64(part["niter"])
+        print(f"  msa {tag}: q={np.round(part['charges'], 5)} niter={out.get(f'msa/{tag}/niter')}")
+    GOLD.mkdir(parents=True, exist_ok=True)
+    np.savez_compressed(GOLD / "ref_molecules.npz", **out)
+    print("wrote", GOLD / "ref_molecules.npz", f"{(GOLD / 'ref_molecules.npz').stat().st_size / 1024:.0f} KiB")
+
+
 CASES = {"h2o": case_h2o, "water6": case_water_cluster, "water6g": case_water_gauss, "hirshfeld": case_hirshfeld,
-         "solvers": case_water6_solvers, "algo": case_algo, "postproc": case_postproc}
+         "solvers": case_water6_solvers, "algo": case_algo, "postproc": case_postproc,
+         "molecules": case_molecules}
 
 if __name__ == "__main__":
     for name in sys.argv[1:] or CASES:

@@ -108,3 +108,23 @@ def test_glisa_newton_matches_reference_run(water6g):
     np.testing.assert_allclose(res["charges"], c["gold"]["glisa_newton/charges"], rtol=0, atol=1e-9)
     np.testing.assert_allclose(res["history_changes"][:3], c["gold"]["glisa_newton/history_changes"][:3], rtol=1e-6)
     np.testing.assert_allclose(res["history_entropies"], c["gold"]["glisa_newton/history_entropies"], rtol=1e-9, atol=1e-13)
+
+
+def test_oracle_on_a_second_molecule_of_the_reference_suite():
+    """N2 on the reference's own grid (tests/test_becke.py:31-57): MBIS and ISA restatements against
+    reference runs stored in ref_molecules.npz -- the oracle is not tuned to water."""
+    from conftest import GOLDEN
+
+    from horton_part_b200 import gridlite as qcgrid
+
+    g = np.load(GOLDEN / "ref_molecules.npz")
+    coords, numbers, pseudo = g["n2/coordinates"], g["n2/numbers"], g["n2/pseudo_numbers"]
+    rgrid = qcgrid.ExpRTransform(1e-3, 1e1, 99).transform_1d_grid(qcgrid.UniformInteger(100))
+    grid = qcgrid.MolGrid.from_size(numbers, coords, 110, rgrid, qcgrid.BeckeWeights(), store=True)
+    np.testing.assert_allclose(grid.aim_weights[::211], g["n2/aim_weights_sample"], rtol=1e-12, atol=1e-15)
+    res = oracle.mbis(coords, numbers, pseudo, grid, g["n2/dens"])
+    assert res["niter"] == int(g["n2/mbis/niter"]) == 7
+    np.testing.assert_allclose(res["charges"], g["n2/mbis/charges"], rtol=1e-9, atol=1e-11)
+    res = oracle.isa(coords, numbers, pseudo, grid, g["n2/dens"])
+    assert res["niter"] == int(g["n2/isa/niter"]) == 11
+    np.testing.assert_allclose(res["charges"], g["n2/isa/charges"], rtol=1e-9, atol=1e-11)
