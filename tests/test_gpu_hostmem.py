@@ -1,0 +1,87 @@
+"""Host <-> device transfer helpers: pipelined uploads from pageable NumPy arrays, direct uploads
+from page-locked ones, pooled page-locked result arrays that are never re-issued while in use."""
+
+import gc
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def test_upload_pageable_and_pinned_are_exact():
+    import torch
+
+    from horton_part_b200.core import hostmem
+
+    dev = torch.device("cuda", 0)
+    rng = np.random.default_rng(0)
+    n = (40 << 20) // 8 + 12345  # below one staging half (64 MB); the last size spans several chunks
+    for size in (1000, n, 3 * (64 << 20) // 8 + 7):
+        a = rng.random(size)
+        t = hostmem.upload(a, dev)
+        torch.cuda.synchronize()
+        assert t.dtype == torch.float64 and t.shape == (size,)
+        assert np.array_equal(t.cpu().numpy(), a)
+        p = hostmem.pinned_empty(size)
+        assert hostmem.is_pinned(p) and not hostmem.is_pinned(a)
+        p[:] = a
+        t2 = hostmem.upload(p, dev)
+        torch.cuda.synchronize()
+        assert np.array_equal(t2.cpu().numpy(), a)
+    # dtype conversion and non-contiguous input
+    m = rng.integers(0, 100, size=(2000, 3000)).astype(np.int32)
+    t = hostmem.upload(m[:, ::2], dev, np.float64)
+    assert np.array_equal(t.cpu().numpy(), m[:, ::2].astype(np.float64))
+    stats = hostmem.pool_stats()
+    assert stats["staged_uploads"] >= 2 and stats["direct_uploads"] >= 2
+
+
+def test_download_pool_never_reissues_a_buffer_in_use():
+    import torch
+
+    from horton_part_b200.core import hostmem
+
+    dev = torch.device("cuda", 0)
+    n = (16 << 20) // 8
+    a = torch.arange(n, dtype=torch.float64, device=dev)
+    b = -torch.arange(n, dtype=torch.float64, device=dev)
+    ha = hostmem.download(a)
+    view = ha[100:200]  # a view keeps the whole buffer busy
+    hb = hostmem.download(b)
+    assert ha.ctypes.data != hb.ctypes.data
+    assert ha[12345] == 12345.0 and hb[12345] == -12345.0
+    addr_a = ha.ctypes.data
+    del ha
+    gc.collect()
+    hc = hostmem.download(b)  # the view is still alive: buffer a must not be reused
+    assert hc.ctypes.data != addr_a
+    assert view[5] == 105.0
+    del view
+    gc.collect()
+    before = hostmem.pool_stats()["pinned_reuses"]
+    hd = hostmem.download(a)  # now it may be
+    assert hostmem.pool_stats()["pinned_reuses"] == before + 1
+    assert hd.ctypes.data == addr_a and hd[7] == 7.0
+    assert hb[3] == -3.0 and hc[3] == -3.0  # untouched
+    assert hostmem.is_pinned(hd)
+    # small tensors take the plain path
+    small = hostmem.download(a[:10])
+    assert np.array_equal(small, np.arange(10.0))
+
+
+def test_results_survive_a_second_job(make_water):
+    """Arrays published by one partitioning job stay intact when another job runs afterwards."""
+    from horton_part_b200 import MBISWPart
+
+    case = make_water(12, nrad=30, nang=38, seed=3)
+    args = (case["coords"], case["numbers"], case["pseudo"], case["grid"], case["rho"])
+    first = MBISWPart(*args, maxiter=3)
+    first.do_partitioning()
+    promol = first["promoldens"]
+    w0 = first["at_weights_0"]
+    keep_p, keep_w = promol.copy(), w0.copy()
+    second = MBISWPart(*args, maxiter=5)
+    second.do_partitioning()
+    assert np.array_equal(promol, keep_p) and np.array_equal(w0, keep_w)
+    assert not np.array_equal(second["promoldens"], promol)
