@@ -44,7 +44,7 @@ EXPORTS = {
     "hp_promol_weights_local": (
         _int,
         [_int, _i64, _p, _p, _p, _i64, _i32, _p, _p, _p, _p, _p, _p, _i32, _p, _p, _p, _f64, _f64, _f64, _p, _f64,
-         _i32, _i32, _p, _i64, _p, _p, _p, _p, _p, _p],
+         _i32, _i32, _p, _p, _i64, _p, _p, _p, _p, _p, _p],
     ),
     "hp_local_tile_limits": (None, [_p, _p]),
     "hp_local_chunk_points": (_i32, []),

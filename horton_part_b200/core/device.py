@@ -126,7 +126,7 @@ def estimate_dense_work(coordinates, grid, shells, gaussian=False, chunk_points=
     _lib.call("hp_neighbor_counts", natom, to_device(xyz, dev), to_device(kind_of, dev, np.int32), nkind, nrad,
               to_device(radii2, dev), counts, stream_ptr(dev))  # fmt: skip
     counts = counts.cpu().numpy()
-    setup_points = 16.0  # cost of screening one atom for one chunk, in point evaluations
+    setup_points = 55.0  # cost of screening one atom for one chunk, in point evaluations (tools/calibrate_work_model.py)
     work = np.zeros(natom)
     for k, (rc, _, sizes) in enumerate(plans):
         own = kind_of == k
@@ -349,6 +349,12 @@ class ShellTable:
                 coff = np.concatenate([[0], np.cumsum((npt + span - 1) // span)]).astype(np.int64)
                 self._loc_nchunk = int(coff[-1])
                 self._loc_chunk_off = to_device(coff, s.device, np.int64)
+                # hand-out order: outermost chunks of every atom first (they see all atoms, nothing
+                # can be screened), the cheap inner ones last, so the launch does not end on a long chunk
+                counts = np.diff(coff)
+                sub = np.arange(self._loc_nchunk) - np.repeat(coff[:-1], counts)
+                from_end = np.repeat(counts, counts) - 1 - sub
+                self._loc_chunk_order = to_device(np.argsort(from_end, kind="stable"), s.device, np.int64)
                 self._loc_scratch = torch.zeros(max(self._loc_nchunk, 1), dtype=torch.float64, device=s.device)
             atom_eps = 0.0
             if bits:
@@ -364,7 +370,8 @@ class ShellTable:
                 s.atom_xyz, s.atom_point_offsets, self.offsets, self.A, self.alpha, self.order,
                 self._loc_ntile, self._loc_tiles, s.rho, s.molw, float(density_cutoff), float(promol_offset),
                 radius, self.skip if bits else None, atom_eps, s.shard.atom_lo, s.shard.nlocal,
-                self._loc_chunk_off, self._loc_nchunk, self._loc_scratch, s.promol if want_promol else None,
+                self._loc_chunk_off, self._loc_chunk_order, self._loc_nchunk, self._loc_scratch,
+                s.promol if want_promol else None,
                 s.at_w if want_weights else None, s.entropy_partials if want_entropy else None,
                 self.pair_partials, stream_ptr(s.device),
             )  # fmt: skip

@@ -100,7 +100,7 @@ promol_weights_local_kernel(int64_t npts, const double* __restrict__ px, const d
                             const double* __restrict__ molw, double density_cutoff, double promol_offset,
                             double radius, const double* __restrict__ shell_skip, double atom_eps,
                             int atom_lo, int natom_local, const int64_t* __restrict__ chunk_off,
-                            double* __restrict__ promol_out, double* __restrict__ w_out,
+                            const int64_t* __restrict__ chunk_order, double* __restrict__ promol_out, double* __restrict__ w_out,
                             double* __restrict__ chunk_entropy,
                             unsigned long long* __restrict__ pair_counters) {
     __shared__ LocAtom s_atoms[kLocTileAtoms + 1];  // +1: sentinel for the prefetch
@@ -131,7 +131,10 @@ promol_weights_local_kernel(int64_t npts, const double* __restrict__ px, const d
     for (;;) {
         __syncthreads();  // everybody is done with the previous chunk's shared state
         if (threadIdx.x == 0) {
-            const long long c = static_cast<long long>(atomicAdd(&g_loc_work_counter, 1ull));
+            const long long ticket = static_cast<long long>(atomicAdd(&g_loc_work_counter, 1ull));
+            // expensive chunks (outer radial shells: nothing can be screened) are handed out first,
+            // so that the last blocks finish on cheap ones
+            const long long c = (ticket < nchunk && chunk_order) ? chunk_order[ticket] : ticket;
             s_chunk[0] = c;
             if (c < nchunk) {
                 int lo = 0, hi = natom_local;  // owner: last local atom with chunk_off[a] <= c
@@ -518,8 +521,9 @@ extern "C" int hp_promol_weights_local(int functor, int64_t npts, const double* 
                                        const double* rho, const double* molw, double density_cutoff,
                                        double promol_offset, double radius, const double* shell_skip,
                                        double atom_eps, int32_t atom_lo, int32_t natom_local,
-                                       const int64_t* chunk_offsets, int64_t nchunk, double* chunk_scratch,
-                                       double* promol, double* at_weights, double* entropy_partials,
+                                       const int64_t* chunk_offsets, const int64_t* chunk_order,
+                                       int64_t nchunk, double* chunk_scratch, double* promol,
+                                       double* at_weights, double* entropy_partials,
                                        uint64_t* pair_partials, void* stream) {
     HP_REQUIRE(npts >= 0 && natom > 0 && ntile > 0, "bad sizes");
     HP_REQUIRE(px && py && pz && atom_xyz && atom_point_offsets && atom_shell_offsets, "null input");
@@ -554,7 +558,8 @@ extern "C" int hp_promol_weights_local(int functor, int64_t npts, const double* 
 #define HP_LOC_ARGS                                                                                      \
     npts, px, py, pz, point_base, natom, atom_xyz, atom_point_offsets, atom_shell_offsets, shell_A,      \
         shell_alpha, shell_order, ntile, tile_atom_offsets, rho, molw, density_cutoff, promol_offset,    \
-        radius, shell_skip, atom_eps, atom_lo, natom_local, chunk_offsets, promol, at_weights,           \
+        radius, shell_skip, atom_eps, atom_lo, natom_local, chunk_offsets, chunk_order, promol,          \
+        at_weights,                                                                                      \
         chunk_entropy, reinterpret_cast<unsigned long long*>(pair_partials)
 #define HP_LOC(F)                                                                                        \
     if (local) promol_weights_local_kernel<F, true><<<int(grid), kLocThreads, 0, st>>>(HP_LOC_ARGS);     \

@@ -142,7 +142,9 @@ HP_API int hp_shell_screen(int32_t natom, int32_t nshell, const int32_t* atom_sh
 /* Chunks: the local points of atom a (atom_point_offsets[a..a+1] - point_base) are cut into pieces of
  * hp_local_chunk_points() points; chunk_offsets[i] (natom_local + 1 entries, device) = number of chunks
  * of the local atoms before atom atom_lo + i, nchunk = chunk_offsets[natom_local].  Blocks take chunks
- * from a global work counter (not re-entrant across streams of one device); chunk_scratch (nchunk
+ * from a global work counter (not re-entrant across streams of one device) in the order given by
+ * chunk_order (a permutation of 0..nchunk-1, may be NULL = ascending; the host puts the expensive
+ * chunks, the outer radial shells, first so that the launch does not end on them); chunk_scratch (nchunk
  * doubles) receives the per-chunk entropy terms, which are folded into entropy_partials in a fixed
  * order.  pair_partials must hold 2 x hp_num_partials() uint64 ([0] = pairs, [hp_num_partials()] =
  * shell evaluations of the launch; the rest is zeroed).  Tiles must respect hp_local_tile_limits(). */
@@ -157,8 +159,9 @@ HP_API int hp_promol_weights_local(int functor, int64_t npts, const double* px, 
                                    const double* rho, const double* molw, double density_cutoff,
                                    double promol_offset, double radius, const double* shell_skip,
                                    double atom_eps, int32_t atom_lo, int32_t natom_local,
-                                   const int64_t* chunk_offsets, int64_t nchunk, double* chunk_scratch,
-                                   double* promol, double* at_weights, double* entropy_partials,
+                                   const int64_t* chunk_offsets, const int64_t* chunk_order,
+                                   int64_t nchunk, double* chunk_scratch, double* promol,
+                                   double* at_weights, double* entropy_partials,
                                    uint64_t* pair_partials, void* stream);
 
 /* ------------------------------------------------------------------------------------------
