@@ -62,6 +62,32 @@ def evaluate_basis_functions(part, force_on_molgrid=False):
         bs[:, :] = np.array([part.bs_helper.compute_proshell_dens(part.numbers[a], i, 1.0, r) for i in range(k)])
 
 
+def expbasis_atom_work(coordinates, numbers, pseudo_numbers, grid, bs_helper, device=None):
+    """Load-balancing weights of a sharded run of the exponential-basis schemes: pairs the screened
+    dense pass evaluates per atom block, estimated from the table's initial coefficients (scaled per
+    atom like ``init_propars``; the global normalisation to the electron count cancels in the
+    screening test).  None for bases with mixed orders (no screening there)."""
+    from .core.device import estimate_dense_work
+
+    per_element = {}
+    for z in np.unique(numbers):
+        z = int(z)
+        order = np.asarray(bs_helper.get_order(z), float)
+        alpha = np.asarray(bs_helper.get_exponent(z), float)
+        inits = np.maximum(np.asarray(bs_helper.get_initial(z), float), 1e-4)
+        per_element[z] = (order, alpha, inits / inits.sum() * shell_norm(order, alpha))
+    orders = np.concatenate([v[0] for v in per_element.values()])
+    if not (np.all(orders == 2.0) or np.all(orders == 1.0)):
+        return None
+    shells, kinds = [], []
+    for a, z in enumerate(numbers):
+        _, alpha, amp = per_element[int(z)]
+        shells.append((amp * float(pseudo_numbers[a]), alpha))
+        kinds.append((int(z), float(pseudo_numbers[a]), id(grid.atgrids[a].rgrid), int(grid.atgrids[a].size)))
+    return estimate_dense_work(coordinates, grid, shells, gaussian=bool(np.all(orders == 2.0)), kinds=kinds,
+                               device=device)
+
+
 class GaussianISAWPart(AbstractISAWPart):
     name = "gisa"
     #: solver names that run as CUDA kernels (subclasses extend this)
@@ -119,6 +145,12 @@ class GaussianISAWPart(AbstractISAWPart):
         return get_proatom_rho(self, iatom, propars)
 
     # -- device hooks ---------------------------------------------------------------------------
+    def _estimate_atom_work(self):
+        if self.on_molgrid or self._local_radius is not None or self._grid.atgrids is None:
+            return None
+        return expbasis_atom_work(self.coordinates, self.numbers, self.pseudo_numbers, self._grid, self.bs_helper,
+                                  self._device)
+
     def _init_propars(self):
         import torch
 

@@ -61,7 +61,14 @@ def main():
     npts = grid.size
     pseudo = numbers.astype(float)
     # synthetic density on this rank's points only (untimed); MBIS shards by estimated work
-    work = mbis_atom_work(coords, numbers, grid, dev) if (world > 1 and args.scheme == "mbis") else None
+    # the synthetic density is needed on the points this rank will own: replicate the class's split
+    work = None
+    if world > 1 and args.scheme == "mbis":
+        work = mbis_atom_work(coords, numbers, grid, dev)
+    elif world > 1:
+        from horton_part_b200.gisa import expbasis_atom_work
+
+        work = expbasis_atom_work(coords, numbers, pseudo, grid, ExpBasisFuncHelper.from_function_type("gauss"), dev)
     shard = Shard(natom, grid.indices, rank, world, work=work)
     rho = np.zeros(npts)
     if args.scheme == "mbis":
