@@ -19,7 +19,7 @@ from .core.basis import ExpBasisFuncHelper, shell_norm
 from .core.cache import just_once
 from .core.iterstock import AbstractISAWPart
 from .core.logging import deflist
-from .utils import check_pro_atom_parameters
+from .utils import check_pro_atom_parameters, optional_package
 
 __all__ = ["GaussianISAWPart", "get_proatom_rho", "init_propars", "evaluate_basis_functions"]
 
@@ -290,10 +290,7 @@ def opt_propars_qp_interface(bs_funcs, rho, propars, weights, alphas, solver="qu
     pop = np.einsum("i,i", weights, rho)
     result = None
     if solver != "active-set":
-        try:
-            import qpsolvers
-        except ImportError:
-            qpsolvers = None
+        qpsolvers = optional_package("qpsolvers")
         if qpsolvers is not None:
             result = qpsolvers.solve_qp(
                 P, q, -np.identity(nprim), np.zeros((nprim, 1)), np.ones((1, nprim)), np.ones((1, 1)) * pop,

@@ -20,7 +20,9 @@ Solvers (every O(Npts) pass is a kernel; the host holds vectors of length M and 
     "diis" / "cdiis"                Anderson-Pulay acceleration of g            glisa.py:883-925, 993-1028
     "trust-region"                  SciPy trust-constr on (f, grad) from the device   glisa.py:927-987
 
-The third-party convex solver ("cvxopt", glisa.py:488-570) is not in this image.
+    "cvxopt" (the default)          the convex programme through the built-in interior-point
+                                    method of algo/cp.py (the third-party package the reference
+                                    calls is not in this image)                 glisa.py:488-570
 """
 
 from __future__ import annotations
@@ -560,6 +562,46 @@ class GlobalLinearISAWPart(AbstractStockholderWPart):
         self.history_entropies.extend(self._entropies_of(history[1:]))
         self.history_propars = history[1:]
         self.history_changes = rnormlist
+        return propars
+
+    def solver_cvxopt(self, allow_neg_pars=False, verbose=False, **cvxopt_options):
+        """The global convex programme  min f(c)  s.t.  c >= 0 (optional), sum c = N  of
+        glisa.py:488-570.  The reference hands it to the third-party ``cvxopt.solvers.cp``; here it
+        goes to the interior-point method of ``algo/cp.py`` (unique minimiser, see there) with f, its
+        gradient and its Hessian from the device kernels.  ``niter`` counts the distinct points at
+        which the Hessian was evaluated, as in the reference."""
+        from .algo.cp import cp
+
+        propars = self.propars
+        nb_par = len(propars)
+        mol_pop = self.mol_pop
+        history = [propars.copy()]
+
+        def objective(x=None, z=None):
+            if x is None:
+                return 0, propars.copy()
+            x = np.asarray(x, dtype=float).ravel()
+            if z is None:
+                return self._objective(x, 1)
+            f, df, hess = self._objective(x, 2)
+            if not np.allclose(x, history[-1]):
+                history.append(x.copy())
+            return f, df, z[0] * hess
+
+        G = h = None
+        if not allow_neg_pars:
+            G, h = -np.identity(nb_par), np.zeros(nb_par)
+        options = dict(cvxopt_options)
+        options.setdefault("show_progress", bool(verbose))
+        options.setdefault("printer", self.logger.info)
+        sol = cp(objective, G=G, h=h, A=np.ones((1, nb_par)), b=np.array([mol_pop]), options=options)
+        propars[:] = sol["x"]
+        self._final_check(propars, check_mono=False)
+        if sol["status"] != "optimal":
+            raise RuntimeError("CVXOPT not converged!")
+        self.cache.dump("niter", len(history) - 1, tags="o")
+        self.history_entropies.extend(self._entropies_of(history[:-1]))
+        self.history_propars = history[1:]
         return propars
 
     def solver_trust_region(self, allow_neg_pars=False):

@@ -16,8 +16,10 @@ here is the small dense algebra the reference also delegates to LAPACK / SciPy:
     solver_sc, solver_sc_1_iter            host versions of the device kernels, for callers that
                                            use the functions directly   (alisa.py:193-353)
 
-The third-party convex solver of the reference (``cvxopt``, alisa.py:67-190) is not in this image;
-``solver_cvxopt`` raises ImportError when the package is missing, like the reference itself.
+    solver_cvxopt, solver_sc_plus_cvxopt   the convex programme (alisa.py:67-190, 356-457) through
+                                           the built-in interior-point method of algo/cp.py (the
+                                           third-party ``cvxopt`` package is not in this image;
+                                           ``engine="cvxopt"`` selects it where it is installed)
 """
 
 from __future__ import annotations
@@ -29,6 +31,7 @@ from .utils import (
     check_pro_atom_parameters_neg_pars,
     check_pro_atom_parameters_non_neg_pars,
     compute_quantities,
+    optional_package,
 )
 
 __all__ = [
@@ -220,45 +223,74 @@ def solver_trust_region(bs_funcs, rho, propars, points, weights, threshold, logg
 
 
 def solver_cvxopt(bs_funcs, rho, propars, points, weights, threshold, logger, density_cutoff,
-                  negative_cutoff, population_cutoff, allow_neg_params=False, **cvxopt_options):  # fmt: skip
-    """Convex programme through the third-party ``cvxopt`` package (alisa.py:67-190):
-    min int rho ln(rho/pro)  s.t.  sum c = pop  (and c >= 0 unless ``allow_neg_params``)."""
+                  negative_cutoff, population_cutoff, allow_neg_params=False, engine=None,
+                  **cvxopt_options):  # fmt: skip
+    """The convex programme of alisa.py:67-190:
+    min int rho ln(rho/pro)  s.t.  sum c = pop  (and c >= 0 unless ``allow_neg_params``).
+
+    The reference solves it with the third-party ``cvxopt.solvers.cp``.  As with GISA's
+    ``qpsolvers`` call (gisa.py), the programme is handed to that package when it is installed;
+    it is not in this image, and then -- or always with ``engine="builtin"`` -- the interior-point
+    method of ``algo/cp.py`` runs on the same objective, gradient and Hessian callbacks (the
+    minimiser is unique, see there).  ``engine="cvxopt"`` insists on the package and raises
+    ImportError when it is missing.  Remaining keyword arguments are solver options under cvxopt's
+    names (``feastol``, ``abstol``, ``reltol``, ``maxiters``, ``show_progress``); without any,
+    ``feastol=threshold`` as in the reference."""
     import logging
 
-    try:
-        import cvxopt
-    except ImportError as exc:  # not in this image
-        raise ImportError("solver 'cvxopt' needs the `cvxopt` package, as in the reference") from exc
-
+    if engine not in (None, "builtin", "cvxopt"):
+        raise ValueError(f"unknown engine {engine!r}: None, 'builtin' or 'cvxopt'")
+    cvxopt = None if engine == "builtin" else optional_package("cvxopt")
+    if engine == "cvxopt" and cvxopt is None:
+        raise ImportError("engine='cvxopt' needs the `cvxopt` package")
     nprim = len(propars)
-    G = h = None
-    if not allow_neg_params:
-        G = -cvxopt.matrix(np.identity(nprim))
-        h = cvxopt.matrix(0.0, (nprim, 1))
     pop = np.einsum("i,i", weights, rho)
-    A = cvxopt.matrix(1.0, (1, nprim))
-    b = cvxopt.matrix(pop, (1, 1))
 
     def objective(x=None, z=None):
         if x is None:
-            return 0, cvxopt.matrix(propars[:])
+            return 0, np.array(propars, dtype=float)
+        x = np.asarray(x, dtype=float).ravel()
         _, pro, sick, ratio, ln_ratio = compute_quantities(rho, x, bs_funcs, density_cutoff)
         f = np.einsum("i,i,i", weights, rho, ln_ratio)
         first = weights * ratio
-        df = cvxopt.matrix((-np.einsum("j,ij->i", first, bs_funcs)).reshape((1, nprim)))
+        df = -np.einsum("j,ij->i", first, bs_funcs)
         if z is None:
             return f, df
         second = np.divide(first, pro, out=np.zeros_like(first), where=~sick)
-        return f, df, z[0] * cvxopt.matrix(np.einsum("k,ik,jk->ij", second, bs_funcs, bs_funcs))
+        return f, df, z[0] * np.einsum("k,ik,jk->ij", second, bs_funcs, bs_funcs)
 
-    options = cvxopt_options
+    options = dict(cvxopt_options)
     if not options:
         options = {"show_progress": 3 if logger.level <= logging.DEBUG else 0, "feastol": threshold}
-    sol = cvxopt.solvers.cp(objective, G=G, h=h, A=A, b=b, options=options)
+
+    if cvxopt is None:
+        from .algo.cp import cp
+
+        G = h = None
+        if not allow_neg_params:
+            G, h = -np.identity(nprim), np.zeros(nprim)
+        options.setdefault("printer", logger.debug)
+        sol = cp(objective, G=G, h=h, A=np.ones((1, nprim)), b=np.array([pop]), options=options)
+        c = sol["x"]
+    else:
+
+        def objective_cvx(x=None, z=None):
+            if x is None:
+                return 0, cvxopt.matrix(propars[:])
+            res = objective(x, z)
+            out = (res[0], cvxopt.matrix(res[1].reshape((1, nprim))))
+            return out if z is None else out + (cvxopt.matrix(res[2]),)
+
+        G = h = None
+        if not allow_neg_params:
+            G = -cvxopt.matrix(np.identity(nprim))
+            h = cvxopt.matrix(0.0, (nprim, 1))
+        sol = cvxopt.solvers.cp(objective_cvx, G=G, h=h, A=cvxopt.matrix(1.0, (1, nprim)),
+                                b=cvxopt.matrix(pop, (1, 1)), options=options)  # fmt: skip
+        c = np.asarray(sol["x"]).flatten()
     if sol["status"] != "optimal":
         logger.error("CVXOPT not converged!")
         return None
-    c = np.asarray(sol["x"]).flatten()
     check_pro_atom_parameters_non_neg_pars(
         c, basis_functions=np.asarray(bs_funcs), logger=logger, total_population=float(pop),
         negative_cutoff=negative_cutoff, population_cutoff=population_cutoff)  # fmt: skip

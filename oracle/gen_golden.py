@@ -292,6 +292,39 @@ def case_water6_solvers(natom=6, nrad=40, nang=50, seed=0):
     save("water6_solvers.npz", results, coordinates=coords, numbers=numbers)
 
 
+CONVEX_CASES = {
+    # the reference's DEFAULT aLISA / gLISA solver (cvxopt.solvers.cp, alisa.py:67-190,
+    # glisa.py:488-570), answered by the shim's SciPy trust-constr + active-set polish
+    "g/lisa_cvxopt": ("lisa", "g", dict()),
+    "s/lisa_cvxopt": ("lisa", "s", dict()),
+    "s/lisa_cvxopt_slater": ("lisa", "s", dict(basis_func="slater")),
+    # ("sc-plus-convex" cannot be generated: its fall-back call omits `population_cutoff`,
+    # alisa.py:446-457, and raises TypeError in the reference itself)
+    "g/lisa_cvxopt_gt2": ("lisa", "g", dict(grid_type=2)),
+    "g/glisa_cvxopt": ("glisa", "g", dict()),
+    "s/glisa_cvxopt": ("glisa", "s", dict()),
+}
+
+
+def case_water6_convex(natom=6, nrad=40, nang=50, seed=0):
+    """The convex-programme solvers on the two synthetic 6-atom promolecules.  cvxopt itself is
+    absent: these runs pin the product up to the choice of convex solver (unique minimiser)."""
+    from horton_part.core.basis import ExpBasisFuncHelper
+
+    coords, numbers = synthetic.water_cluster(natom, seed)
+    grid = synthetic_grid(coords, numbers, nrad, nang)
+    helper = ExpBasisFuncHelper.from_function_type("gauss")
+    rhos = {"s": synthetic.slater_promolecule_host(grid.points, coords, numbers),
+            "g": synthetic.expbasis_promolecule_host(grid.points, coords, numbers, helper, scale={8: 8.6, 1: 0.7})}
+    pseudo = numbers.astype(float)
+    results = {}
+    for tag, (scheme, dens, kw) in CONVEX_CASES.items():
+        t0 = time.time()
+        results[tag] = run_reference_light(scheme, coords, numbers, pseudo, grid, rhos[dens], **kw)
+        print(f"  {tag}: niter={results[tag].get('niter')} q={results[tag]['charges'][:3]} {time.time()-t0:.1f}s")
+    save("water6_convex.npz", results, coordinates=coords, numbers=numbers)
+
+
 def case_algo():
     """Known-answer vectors for the host algebra modules (algo/diis.py, algo/cdiis.py,
     algo/quasi_newton.py) and the aLISA radial plug-in solvers (alisa.py), from the reference
@@ -348,6 +381,29 @@ def case_algo():
     GOLD.mkdir(parents=True, exist_ok=True)
     np.savez_compressed(GOLD / "algo_host.npz", **out)
     print("wrote", GOLD / "algo_host.npz", len(out), "entries")
+
+
+def case_convex_radial():
+    """The reference's ``solver_cvxopt`` (alisa.py:67-190) on the seeded radial problems of
+    case_algo, its ``cvxopt.solvers.cp`` call answered by the shim.  CPU-only tests use these."""
+    import horton_part.alisa as ra
+    from horton_part.core.basis import ExpBasisFuncHelper
+
+    from horton_part_b200 import synthetic as syn
+
+    out = {}
+    lg = logging.getLogger("golden")
+    lg.setLevel(logging.INFO)
+    for func_type in ("gauss", "slater"):
+        h = ExpBasisFuncHelper.from_function_type(func_type)
+        for Z, pop in ((8, 8.5), (1, 0.7), (6, 6.1)):
+            bs, rho, c0, r, w = syn.radial_problem(h, Z, pop)
+            out[f"{func_type}/{Z}/nonneg"] = ra.solver_cvxopt(bs, rho, c0.copy(), r, w, 1e-8, lg, 1e-15, -1e-12, 1e-4)
+            if func_type == "gauss":  # (sign-free Slater fits leave the region where f is convex)
+                out[f"{func_type}/{Z}/free"] = ra.solver_cvxopt(bs, rho, c0.copy(), r, w, 1e-8, lg, 1e-15, -1e-12,
+                                                                1e-4, allow_neg_params=True)  # fmt: skip
+    np.savez_compressed(GOLD / "convex_radial.npz", **out)
+    print("wrote", GOLD / "convex_radial.npz", len(out), "entries")
 
 
 def case_postproc():
@@ -471,7 +527,7 @@ def case_molecules():
 
 
 CASES = {"h2o": case_h2o, "water6": case_water_cluster, "water6g": case_water_gauss, "hirshfeld": case_hirshfeld,
-         "solvers": case_water6_solvers, "algo": case_algo, "postproc": case_postproc,
+         "solvers": case_water6_solvers, "convex": case_water6_convex, "convex_radial": case_convex_radial, "algo": case_algo, "postproc": case_postproc,
          "molecules": case_molecules}
 
 if __name__ == "__main__":

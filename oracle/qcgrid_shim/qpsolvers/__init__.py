@@ -13,6 +13,8 @@ import itertools
 
 import numpy as np
 
+__oracle_shim__ = True  # the product refuses modules carrying this mark (utils.optional_package)
+
 
 def solve_qp(P, q, G=None, h=None, A=None, b=None, solver=None, initvals=None, **_options):
     P = np.asarray(P, float)

@@ -14,7 +14,10 @@ def test_device_becke_matches_host_and_oracle(make_water):
     from horton_part_b200 import gridlite, synthetic
 
     sys.path.insert(0, str(ROOT / "oracle" / "qcgrid_shim"))
-    import grid as qcgrid  # the oracle's qc-grid restatement
+    try:
+        import grid as qcgrid  # the oracle's qc-grid restatement
+    finally:
+        sys.path.pop(0)
 
     for coords, numbers in (synthetic.water_cluster(12, seed=5), synthetic.organic_like(20, seed=1)):
         rgrid = gridlite.BeckeRTransform(1e-4, 1.5).transform_1d_grid(gridlite.GaussChebyshev(30))
