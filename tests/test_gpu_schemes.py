@@ -72,17 +72,16 @@ def test_alisa_callable_solver_plugin(water6):
     np.testing.assert_allclose(part["history_changes"], ref["history_changes"], rtol=1e-6)
 
 
-def test_alisa_third_party_solver_raises_without_the_package(water6):
-    """The default solver name of the reference ("cvxopt") needs the third-party package, exactly
-    like the reference; an unknown name is NotImplementedError (alisa.py:1304-1320)."""
-    try:
-        import cvxopt  # noqa: F401
+def test_alisa_third_party_engine_raises_without_the_package(water6):
+    """The convex programme runs on the built-in interior-point method when the third-party
+    package is missing (tests/test_gpu_solvers.py); insisting on the package raises, and an unknown
+    solver name is NotImplementedError (alisa.py:1304-1320)."""
+    from horton_part_b200.utils import optional_package
 
+    if optional_package("cvxopt") is not None:
         pytest.skip("cvxopt present")
-    except ImportError:
-        pass
     with pytest.raises(ImportError, match="cvxopt"):
-        _run("LinearISAWPart", water6, solver="cvxopt")
+        _run("LinearISAWPart", water6, solver="cvxopt", solver_options=dict(engine="cvxopt"))
     with pytest.raises(NotImplementedError):
         _run("LinearISAWPart", water6, solver="no-such-solver")
 
