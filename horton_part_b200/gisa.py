@@ -52,11 +52,11 @@ def init_propars(part):
 
 
 def evaluate_basis_functions(part, force_on_molgrid=False):
-    """Unit-population basis functions on each atom's radial grid -> cache ``bs_funcs_{a}``."""
-    if part.on_molgrid or force_on_molgrid:
-        raise NotImplementedError("basis functions on the molecular grid are generated in-kernel")
+    """Unit-population basis functions -> cache ``bs_funcs_{a}`` (gisa.py:91-106): on each atom's
+    radial grid, or -- only for host plug-in solvers with grid_type 2/3, the device solvers
+    regenerate them in-kernel -- on the whole molecular grid."""
     for a in range(part.natom):
-        r = part.get_rgrid(a).points
+        r = part.radial_distances[a] if (part.on_molgrid or force_on_molgrid) else part.get_rgrid(a).points
         k = part._ranges[a + 1] - part._ranges[a]
         bs = part.cache.load(f"bs_funcs_{a}", alloc=(k, r.size))[0]
         bs[:, :] = np.array([part.bs_helper.compute_proshell_dens(part.numbers[a], i, 1.0, r) for i in range(k)])
@@ -86,6 +86,32 @@ def expbasis_atom_work(coordinates, numbers, pseudo_numbers, grid, bs_helper, de
         kinds.append((int(z), float(pseudo_numbers[a]), id(grid.atgrids[a].rgrid), int(grid.atgrids[a].size)))
     return estimate_dense_work(coordinates, grid, shells, gaussian=bool(np.all(orders == 2.0)), kinds=kinds,
                                device=device)
+
+
+def molgrid_host_update(promol, rho, points, weights, bs_funcs, ranges, propars, pseudo_numbers, opt_propars):
+    """Per-atom parameter updates of ONE outer iteration on the molecular grid, through a host
+    solver (gisa.py:257-279 with core/stockholder.py:352-384 and core/iterstock.py:32-45).
+
+    ``promol`` is the promolecule the device pass built from ``propars`` (with the reference's
+    1e-100 offsets); everything here is the K_a x Npts dense algebra the reference also does on
+    the host for a plug-in solver.  ``opt_propars(a, bs_funcs_a, rho_a, propars_a)`` returns the new
+    coefficients of atom ``a``.  Returns (new propars, charges, per-atom change terms)."""
+    natom = len(ranges) - 1
+    new = propars.copy()
+    charges = np.zeros(natom)
+    msd = np.zeros(natom)
+    for a in range(natom):
+        lo, hi = ranges[a], ranges[a + 1]
+        bs = bs_funcs[a]
+        at_weights = np.einsum("k,kp->p", propars[lo:hi], bs)
+        at_weights /= promol
+        np.clip(at_weights, 0, 1, out=at_weights)
+        rho_a = at_weights * rho
+        new[lo:hi] = opt_propars(a, bs, rho_a, propars[lo:hi].copy())
+        charges[a] = pseudo_numbers[a] - np.einsum("i,i", weights, rho_a)
+        delta = np.einsum("k,kp->p", new[lo:hi] - propars[lo:hi], bs)
+        msd[a] = np.einsum("i,i,i", weights, delta, delta)
+    return new, charges, msd
 
 
 class GaussianISAWPart(AbstractISAWPart):
@@ -178,9 +204,16 @@ class GaussianISAWPart(AbstractISAWPart):
         st.propars.copy_(to_device(propars, dev))
         self._par_offsets = to_device(np.asarray(self._ranges, dtype=np.int32), dev)
         self._pseudo = to_device(self.pseudo_numbers, dev, np.float64)
+        self._molgrid_host = False
+        if self.on_molgrid and (callable(self._solver) or self._solver not in self.device_solvers):
+            # host plug-in on the molecular grid: K_a x Npts basis tables on the host, as in the reference
+            if self._comm is not None:
+                raise NotImplementedError("host plug-in solvers with grid_type 2/3 run on one GPU (the "
+                                          "device solvers " + str(list(self.device_solvers)) + " shard)")  # fmt: skip
+            self._molgrid_host = True
+            self._evaluate_basis_functions()
+            return propars
         if self.on_molgrid:
-            if callable(self._solver) or self._solver not in self.device_solvers:
-                raise NotImplementedError("grid_type 2/3 needs one of the device solvers " + str(list(self.device_solvers)))
             self.molgrid_single_update = bool(self.device_solvers[self._solver][1])
             opt = self.device_solvers[self._solver][0]
             self.molgrid_max_inner = int(float(self._solver_options.get(opt, 100000))) if opt else 1
@@ -209,6 +242,49 @@ class GaussianISAWPart(AbstractISAWPart):
         import torch
 
         return torch.where(shell_active, s0, propars)  # alisa.py:268
+
+    def _run_iteration_molgrid(self):
+        if not self._molgrid_host:
+            return super()._run_iteration_molgrid()
+        return self._run_iteration_molgrid_host()
+
+    def _run_iteration_molgrid_host(self):
+        """One outer iteration with grid_type 2/3 and a host solver: promolecule and entropy on the
+        device, the per-atom K_a x Npts problems on the host (``molgrid_host_update``)."""
+        import torch
+
+        from .core.device import stream_ptr
+
+        st, slab = self._state, self.slab
+        dev = slab.device
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+        ev[0].record()
+        self._refresh_table()
+        self._table.promol_weights(self.density_cutoff, True, True, True)
+        ev[1].record()
+        promol = slab.promol.cpu().numpy()
+        propars = self.cache.load("propars")
+        grid = self.grid
+        alphas = [self.bs_helper.get_exponent(z) if isinstance(self.bs_helper, ExpBasisFuncHelper) else None
+                  for z in self.numbers]  # fmt: skip
+
+        def opt(a, bs, rho_a, start):
+            return self._opt_propars(bs, rho_a, start, grid.points, grid.weights, alphas[a], self._inner_threshold)
+
+        new, charges, msd = molgrid_host_update(
+            promol, self._moldens, grid.points, grid.weights, [self.cache.load(f"bs_funcs_{a}") for a in range(self.natom)],
+            self._ranges, propars, self.pseudo_numbers, opt)  # fmt: skip
+        st.propars.copy_(torch.from_numpy(new).to(dev))
+        st.charges.copy_(torch.from_numpy(charges).to(dev))
+        st.msd.copy_(torch.from_numpy(msd).to(dev))
+        _lib.call("hp_finish_iteration", slab.npartial, slab.entropy_partials, self.natom, st.msd, st.out2,
+                  stream_ptr(dev))  # fmt: skip
+        ev[2].record()
+        out2 = st.out2.cpu().numpy()
+        st.events.append(ev)
+        propars[:] = new
+        self.cache.load("charges", alloc=self.natom, tags="o")[0][:] = charges
+        return float(out2[0]), float(out2[1])
 
     def _launch_radial_update(self):
         self.slab.shell_project()

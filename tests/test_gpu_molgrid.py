@@ -68,3 +68,52 @@ def test_glisa_sc_grid_type_2_h2o(h2o):
                                 solver="sc", grid_type=2)
     part.do_partitioning()
     _compare(part, _gold(h2o["gold"], "glisa_sc_gt2"), ptol=1e-5)
+
+
+def test_alisa_default_solver_grid_type_2(water6g):
+    """grid_type 2 with a HOST plug-in (the reference's default aLISA solver, the convex programme):
+    promolecule and entropy from the device, the K_a x Npts per-atom problems on the host exactly
+    as the reference does them (gisa.py:257-279).  Golden: reference run through the oracle's
+    cvxopt stand-in (tests/golden/water6_convex.npz)."""
+    from conftest import GOLDEN
+
+    from horton_part_b200 import LinearISAWPart
+
+    gold = np.load(GOLDEN / "water6_convex.npz")
+    ref = _gold(gold, "g/lisa_cvxopt_gt2")
+    c = water6g
+    part = LinearISAWPart(c["coords"], c["numbers"], c["pseudo"], c["grid"], c["rho"], grid_type=2)
+    part.do_partitioning()
+    assert part["niter"] == int(ref["niter"])
+    np.testing.assert_allclose(part["charges"], ref["charges"], rtol=1e-8, atol=1e-9)
+    np.testing.assert_allclose(part["propars"], ref["propars"], rtol=1e-6, atol=1e-8)
+    np.testing.assert_allclose(part["history_changes"], ref["history_changes"], rtol=1e-5, atol=1e-10)
+    np.testing.assert_allclose(part["history_entropies"], ref["history_entropies"], rtol=1e-8, atol=1e-11)
+    np.testing.assert_allclose(part["promoldens"][::97], ref["promoldens_sample"], rtol=1e-8)
+
+
+def test_alisa_callable_solver_grid_type_3(water6g):
+    """A user callable with the reference's plug-in signature on grid_type 3 gets the molecular-grid
+    arrays (K_a x Npts basis table, w_a*rho, grid points and weights) and reproduces the device
+    fixed point when it performs the same update."""
+    from horton_part_b200 import LinearISAWPart
+
+    c = water6g
+    seen = []
+
+    def one_sc_step(bs_funcs, rho, propars, points, weights, threshold, logger, density_cutoff, **kw):
+        seen.append((bs_funcs.shape, rho.shape, points.shape, weights.shape))
+        pro = propars @ bs_funcs
+        ok = (rho >= density_cutoff) & (pro >= density_cutoff)
+        ratio = np.divide(rho, pro, out=np.zeros_like(rho), where=ok)
+        return np.einsum("kp,p,p->k", bs_funcs * propars[:, None], ratio, weights)
+
+    args = (c["coords"], c["numbers"], c["pseudo"], c["grid"], c["rho"])
+    host = LinearISAWPart(*args, grid_type=3, solver=one_sc_step, maxiter=5)
+    host.do_partitioning()
+    dev = LinearISAWPart(*args, grid_type=3, solver="sc-1-iter", maxiter=5)
+    dev.do_partitioning()
+    npts = c["grid"].size
+    assert seen[0][1:] == ((npts,), (npts, 3), (npts,)) and seen[0][0][1] == npts
+    np.testing.assert_allclose(host["charges"], dev["charges"], rtol=1e-9, atol=1e-10)
+    np.testing.assert_allclose(host["history_changes"], dev["history_changes"], rtol=1e-6)
