@@ -21,7 +21,7 @@ from __future__ import annotations
 import numpy as np
 
 from . import _lib
-from .core.basis import AnalyticBasisFuncHelper, ExpBasisFuncHelper
+from .core.basis import AnalyticBasisFuncHelper, ExpBasisFuncHelper, NumericBasisFuncHelper
 from .core.logging import deflist
 from .gisa import GaussianISAWPart
 from .lisa_solvers import (  # noqa: F401  (re-exported like the reference's alisa module)
@@ -48,15 +48,16 @@ def setup_bs_helper(part):
         if isinstance(bf, str):
             if bf.lower() in ("gauss", "slater"):
                 part.logger.info(f"Load {bf.upper()} basis functions")
-                if part.basis_type != "analytic":
-                    if part.basis_type == "numeric":
-                        raise NotImplementedError("numeric (spline) basis functions are not built yet")
+                if part.basis_type == "analytic":
+                    part._bs_helper = ExpBasisFuncHelper.from_function_type(bf.lower())
+                elif part.basis_type == "numeric":
+                    part._bs_helper = NumericBasisFuncHelper.from_function_type(bf.lower())
+                else:
                     raise RuntimeError("The bs_type should be one of analytic and numeric.")
-                part._bs_helper = ExpBasisFuncHelper.from_function_type(bf.lower())
             else:
                 part.logger.info(f"Load basis functions from custom json file: {bf}")
                 part._bs_helper = ExpBasisFuncHelper.from_file(bf)
-        elif isinstance(bf, AnalyticBasisFuncHelper):
+        elif isinstance(bf, (AnalyticBasisFuncHelper, NumericBasisFuncHelper)):
             part._bs_helper = bf
         else:
             raise NotImplementedError("The type of basis_func should be one of string or class BasisFuncHelper.")

@@ -22,6 +22,7 @@ __all__ = [
     "BasisFuncHelper",
     "AnalyticBasisFuncHelper",
     "ExpBasisFuncHelper",
+    "NumericBasisFuncHelper",
     "evaluate_function",
     "load_params",
     "shell_norm",
@@ -166,3 +167,68 @@ class ExpBasisFuncHelper(AnalyticBasisFuncHelper):
 
     from_yaml = from_file
     from_json = from_file
+
+
+class NumericBasisFuncHelper(BasisFuncHelper):
+    """Basis functions tabulated as cubic splines (core/basis.py:330-390): every shell of the
+    exponential table is sampled on BeckeRTransform(1e-4, 1.5) o GaussChebyshev(nrad) and replaced by
+    the not-a-knot, extrapolating ``CubicSpline`` through the samples.
+
+    All shells of an element share one set of knots, so a pro-atom sum_k c_k S_k(r) is itself a
+    piecewise cubic on those knots with coefficients sum_k c_k coef_k: that is how the device
+    evaluates it (``ppoly_coefficients`` feeds ``hp_promol_weights_spline``)."""
+
+    def __init__(self, splines_dict, initials):
+        super().__init__(initials)
+        self._splines_dict = splines_dict
+
+    splines_dict = property(lambda self: self._splines_dict)
+
+    def get_nshell(self, number):
+        return len(self.splines_dict[number])
+
+    def compute_proshell_dens(self, number, ishell, population, points, nderiv=0):
+        y = population * self.splines_dict[number][ishell](points)
+        if nderiv == 0:
+            return y
+        if nderiv == 1:
+            return y, np.zeros_like(y)  # the reference returns a zero derivative (core/basis.py:356)
+        raise NotImplementedError
+
+    def get_knots(self, number):
+        """Break points shared by the shells of element ``number``."""
+        return np.asarray(self.splines_dict[number][0].x)
+
+    def ppoly_coefficients(self, number):
+        """(nshell, nseg, 4) SciPy PPoly coefficients, highest power first within a segment."""
+        shells = self.splines_dict[number]
+        return np.stack([np.ascontiguousarray(shells[k].c.T) for k in range(len(shells))])
+
+    @classmethod
+    def from_file(cls, filename, nrad=150):
+        from scipy.interpolate import CubicSpline
+
+        from ..gridlite import BeckeRTransform, GaussChebyshev
+
+        helper = ExpBasisFuncHelper.from_file(filename)
+        return cls._from_exp_helper(helper, nrad, CubicSpline, BeckeRTransform, GaussChebyshev)
+
+    @classmethod
+    def from_function_type(cls, func_type="gauss", nrad=150):
+        from scipy.interpolate import CubicSpline
+
+        from ..gridlite import BeckeRTransform, GaussChebyshev
+
+        helper = ExpBasisFuncHelper.from_function_type(func_type)
+        return cls._from_exp_helper(helper, nrad, CubicSpline, BeckeRTransform, GaussChebyshev)
+
+    @classmethod
+    def _from_exp_helper(cls, helper, nrad, CubicSpline, BeckeRTransform, GaussChebyshev):
+        rgrid = BeckeRTransform(1e-4, 1.5).transform_1d_grid(GaussChebyshev(nrad))
+        splines = {}
+        for number, exps in helper.exponents.items():
+            splines[number] = {
+                k: CubicSpline(rgrid.points, helper.compute_proshell_dens(number, k, 1.0, rgrid.points), 0)
+                for k in range(len(exps))
+            }
+        return cls(splines, helper.initials)

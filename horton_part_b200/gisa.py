@@ -174,6 +174,8 @@ class GaussianISAWPart(AbstractISAWPart):
     def _estimate_atom_work(self):
         if self.on_molgrid or self._local_radius is not None or self._grid.atgrids is None:
             return None
+        if not isinstance(self.bs_helper, ExpBasisFuncHelper):
+            return None  # spline basis: no screening, blocks are balanced by point count
         return expbasis_atom_work(self.coordinates, self.numbers, self.pseudo_numbers, self._grid, self.bs_helper,
                                   self._device)
 
@@ -187,26 +189,29 @@ class GaussianISAWPart(AbstractISAWPart):
             self._evaluate_basis_functions()
         slab = self.slab
         dev = slab.device
-        orders = np.concatenate([np.asarray(self.bs_helper.get_order(z), float) for z in self.numbers])
-        alphas = np.concatenate([np.asarray(self.bs_helper.get_exponent(z), float) for z in self.numbers])
-        if np.all(orders == 2.0):
-            functor = 2
-        elif np.all(orders == 1.0):
-            functor = 1
+        self._numeric = not isinstance(self.bs_helper, ExpBasisFuncHelper)
+        if self._numeric:
+            # tabulated basis functions (basis_type="numeric"): the pro-atom sum_k c_k S_k(r) is one
+            # piecewise cubic per atom on the element's knots; coefficients are mixed per iteration
+            from .isa import SplineTable
+
+            class _Knots:  # the SplineTable only needs .points / .size
+                def __init__(self, x):
+                    self.points, self.size = x, x.size
+
+            self._table = SplineTable(slab, [_Knots(self.bs_helper.get_knots(z)) for z in self.numbers],
+                                      proatom_offset=0.0)  # gisa.py:224-244: no offset on the pro-atom
+            self._ppoly = {int(z): self.bs_helper.ppoly_coefficients(int(z)) for z in np.unique(self.numbers)}
         else:
-            functor = 3
-        self._table = ShellTable(slab, functor, self._nshells)
-        self._table.alpha.copy_(to_device(alphas, dev))
-        if functor == 3:
-            self._table.order.copy_(to_device(orders, dev))
-        self._norms = to_device(shell_norm(orders, alphas), dev)
+            self._init_shell_table(slab, dev)
         st = self._alloc_state(len(propars))
         st.propars.copy_(to_device(propars, dev))
         self._par_offsets = to_device(np.asarray(self._ranges, dtype=np.int32), dev)
         self._pseudo = to_device(self.pseudo_numbers, dev, np.float64)
         self._molgrid_host = False
-        if self.on_molgrid and (callable(self._solver) or self._solver not in self.device_solvers):
+        if self.on_molgrid and (callable(self._solver) or self._solver not in self.device_solvers or self._numeric):
             # host plug-in on the molecular grid: K_a x Npts basis tables on the host, as in the reference
+            # (also for tabulated basis functions, which the molecular-grid kernels do not regenerate)
             if self._comm is not None:
                 raise NotImplementedError("host plug-in solvers with grid_type 2/3 run on one GPU (the "
                                           "device solvers " + str(list(self.device_solvers)) + " shard)")  # fmt: skip
@@ -229,9 +234,34 @@ class GaussianISAWPart(AbstractISAWPart):
         self._nshell_max = max(self._nshells[sh.atom_lo : sh.atom_hi], default=1)
         return propars
 
+    def _init_shell_table(self, slab, dev):
+        from .core.device import ShellTable, to_device
+
+        orders = np.concatenate([np.asarray(self.bs_helper.get_order(z), float) for z in self.numbers])
+        alphas = np.concatenate([np.asarray(self.bs_helper.get_exponent(z), float) for z in self.numbers])
+        if np.all(orders == 2.0):
+            functor = 2
+        elif np.all(orders == 1.0):
+            functor = 1
+        else:
+            functor = 3
+        self._table = ShellTable(slab, functor, self._nshells)
+        self._table.alpha.copy_(to_device(alphas, dev))
+        if functor == 3:
+            self._table.order.copy_(to_device(orders, dev))
+        self._norms = to_device(shell_norm(orders, alphas), dev)
+
     def _refresh_table(self):
         from .core.device import stream_ptr
 
+        if self._numeric:
+            import torch
+
+            propars = self.cache.load("propars")
+            mixed = [np.einsum("k,ksc->sc", propars[self._ranges[a] : self._ranges[a + 1]], self._ppoly[int(z)])
+                     for a, z in enumerate(self.numbers)]  # fmt: skip
+            self._table.coef.copy_(torch.from_numpy(np.concatenate([m.ravel() for m in mixed])))
+            return
         t = self._table
         _lib.call("hp_table_scaled", t.nshell, self._state.propars, self._norms, t.A, stream_ptr(self.slab.device))
 

@@ -121,6 +121,9 @@ class GlobalLinearISAWPart(AbstractStockholderWPart):
 
         from .core.device import ShellTable, to_device
 
+        if not isinstance(self.bs_helper, ExpBasisFuncHelper):
+            raise NotImplementedError('gLISA with basis_type="numeric" is not built: the moment and Hessian '
+                                      "kernels regenerate exponential basis functions (aLISA has it)")  # fmt: skip
         propars = gisa.init_propars(self)
         if not self.on_molgrid:
             gisa.evaluate_basis_functions(self)  # radial grids only: used by compute_change

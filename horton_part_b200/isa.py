@@ -26,7 +26,7 @@ logger = logging.getLogger(__name__)
 class SplineTable:
     """Knots of every atom's radial grid (replicated on every rank) and the coefficient buffer."""
 
-    def __init__(self, slab, rgrids):
+    def __init__(self, slab, rgrids, proatom_offset=1e-100):
         import torch
 
         from .core.device import to_device
@@ -40,6 +40,9 @@ class SplineTable:
         self.coef = torch.zeros(4 * (self.nknot - len(rgrids)), dtype=torch.float64, device=dev)
         self.work = torch.zeros(2 * self.nknot, dtype=torch.float64, device=dev)
         self.slab = slab
+        #: added to every spline value: base eval_proatom does ``spline(r) + 1e-100``
+        #: (core/stockholder.py:349); 0 for pro-atoms that are plain sums of tabulated shells
+        self.proatom_offset = proatom_offset
 
     def build(self, values, clip_negative=True):
         from .core.device import stream_ptr
@@ -48,10 +51,12 @@ class SplineTable:
                   int(clip_negative), self.coef, self.work, stream_ptr(self.slab.device))  # fmt: skip
 
     def promol_weights(self, density_cutoff, want_promol=True, want_weights=True, want_entropy=True,
-                       proatom_offset=1e-100):  # fmt: skip
+                       proatom_offset=None):  # fmt: skip
         from .core.device import stream_ptr
 
         s = self.slab
+        if proatom_offset is None:
+            proatom_offset = self.proatom_offset
         _lib.call(
             "hp_promol_weights_spline", s.npts, s.px, s.py, s.pz, s.point_base, s.natom, s.atom_xyz,
             s.atom_point_offsets, self.offsets, self.knots, self.coef, float(proatom_offset), s.rho,

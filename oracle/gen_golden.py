@@ -406,6 +406,36 @@ def case_convex_radial():
     print("wrote", GOLD / "convex_radial.npz", len(out), "entries")
 
 
+def case_numeric(natom=6, nrad=40, nang=50, seed=0):
+    """basis_type="numeric" (tabulated basis functions, core/basis.py:330-390): helper values for the
+    CPU test and aLISA runs on the 6-atom Slater promolecule."""
+    from horton_part.core.basis import NumericBasisFuncHelper
+
+    coords, numbers = synthetic.water_cluster(natom, seed)
+    grid = synthetic_grid(coords, numbers, nrad, nang)
+    rho = synthetic.slater_promolecule_host(grid.points, coords, numbers)
+    pseudo = numbers.astype(float)
+    results = {}
+    for tag, kw in {
+        "lisa_sc": dict(solver="sc"),
+        "lisa_sc_slater": dict(solver="sc", basis_func="slater"),
+        "lisa_cvxopt": dict(),
+        # (grid_type 2/3 raise AttributeError in the reference: gisa.py:265 asks the helper for exponents)
+    }.items():
+        t0 = time.time()
+        results[tag] = run_reference_light("lisa", coords, numbers, pseudo, grid, rho, basis_type="numeric", **kw)
+        print(f"  {tag}: niter={results[tag].get('niter')} q={results[tag]['charges'][:3]} {time.time()-t0:.1f}s")
+    r = np.concatenate([[0.0, 1e-6], np.geomspace(1e-5, 60.0, 300)])  # incl. both extrapolation sides
+    extra = {"helper/r": r}
+    for ft in ("gauss", "slater"):
+        h = NumericBasisFuncHelper.from_function_type(ft)
+        for z in (1, 6, 8):
+            extra[f"helper/{ft}/{z}"] = np.array([h.compute_proshell_dens(z, k, 1.0, r) for k in range(h.get_nshell(z))])
+            pops = np.linspace(0.3, 1.1, h.get_nshell(z))
+            extra[f"helper/{ft}/{z}/proatom"] = h.compute_proatom_dens(z, pops, r, 0)
+    save("water6_numeric.npz", results, coordinates=coords, numbers=numbers, **extra)
+
+
 def case_postproc():
     """Post-processing beyond charges on water HF/STO-3G: Becke scheme
     (becke.py), density decomposition splines (core/base.py:637-659), pro-atom splines
@@ -527,7 +557,7 @@ def case_molecules():
 
 
 CASES = {"h2o": case_h2o, "water6": case_water_cluster, "water6g": case_water_gauss, "hirshfeld": case_hirshfeld,
-         "solvers": case_water6_solvers, "convex": case_water6_convex, "convex_radial": case_convex_radial, "algo": case_algo, "postproc": case_postproc,
+         "solvers": case_water6_solvers, "convex": case_water6_convex, "convex_radial": case_convex_radial, "numeric": case_numeric, "algo": case_algo, "postproc": case_postproc,
          "molecules": case_molecules}
 
 if __name__ == "__main__":

@@ -111,3 +111,30 @@ def test_nlis_default_exp_n_dict_raises_like_reference(water6):
     # the reference's default exp_n_dict=1.0 is not a dict: `(Z, k) in 1.0` raises TypeError
     with pytest.raises(TypeError):
         _run("NLISWPart", water6)
+
+
+@pytest.mark.parametrize("tag,kw", [
+    ("lisa_sc", dict(solver="sc")),
+    ("lisa_sc_slater", dict(solver="sc", basis_func="slater")),
+    ("lisa_cvxopt", dict()),
+])  # fmt: skip
+def test_alisa_numeric_basis_against_reference_run(water6, tag, kw):
+    """basis_type="numeric" (tabulated basis functions, core/basis.py:330-390): the pro-atom of an
+    atom is one piecewise cubic on the element's knots, evaluated by hp_promol_weights_spline from
+    coefficients mixed per iteration; radial solves use the tabulated K x nrad functions."""
+    from conftest import GOLDEN
+
+    gold = np.load(GOLDEN / "water6_numeric.npz")
+    ref = _gold(gold, tag)
+    part = _run("LinearISAWPart", water6, basis_type="numeric", **kw)
+    assert part["niter"] == int(ref["niter"])
+    np.testing.assert_allclose(part["charges"], ref["charges"], rtol=1e-8, atol=1e-9)
+    np.testing.assert_allclose(part["history_changes"], ref["history_changes"], rtol=1e-5, atol=1e-10)
+    np.testing.assert_allclose(part["promoldens"][::97], ref["promoldens_sample"], rtol=1e-8, atol=1e-16)
+    if "slater" not in tag:
+        np.testing.assert_allclose(part["propars"], ref["propars"], rtol=1e-6, atol=1e-8)
+
+
+def test_glisa_numeric_basis_is_refused(water6):
+    with pytest.raises(NotImplementedError, match="numeric"):
+        _run("GlobalLinearISAWPart", water6, basis_type="numeric", solver="sc")
