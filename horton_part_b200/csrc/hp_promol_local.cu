@@ -53,6 +53,9 @@ constexpr int kLocBlocksPerSM = HP_LOC_BLOCKS;
 #ifndef HP_LOC_PTS
 #define HP_LOC_PTS 8
 #endif
+#ifndef HP_LOC_FUSED_SUM
+#define HP_LOC_FUSED_SUM 1  // dense guard-free path: shells accumulate straight into the running sum
+#endif
 constexpr int kLocPts = HP_LOC_PTS;
 constexpr int kLocSpan = kLocThreads * kLocPts;  // points per chunk
 constexpr int kLocTileAtoms = kLocThreads;       // candidate atoms per shared-memory tile (one per thread)
@@ -318,6 +321,16 @@ promol_weights_local_kernel(int64_t npts, const double* __restrict__ px, const d
                 shells += static_cast<unsigned long long>(kept) * nlive;
             }
 
+            // the reference's `promoldens += 1e-100` per atom (core/stockholder.py:170) is a no-op in
+            // FP64 once every running sum of the block is >= 1e-80 (1e-100 < 2^-54 * 1e-80) and the
+            // terms are non-negative (sums only grow): decided per tile from the block minimum
+            bool offset_is_void = false;
+            if (HP_LOC_FUSED_SUM && !LOCAL && may_screen_atoms && t > 0) {
+                double run = s_wmin[0];
+                for (int w = 1; w < kLocThreads / 32; ++w) run = fmin(run, s_wmin[w]);
+                offset_is_void = run >= 1e-80 && promol_offset <= 1e-100 && promol_offset >= 0.0;
+            }
+
             // ---- evaluation: every thread, 4 points, all candidates in atom order ---------------
             double ax, ay, az, A0, al0;
             int s0, ns;
@@ -340,6 +353,30 @@ promol_weights_local_kernel(int64_t npts, const double* __restrict__ px, const d
                     eval_proatom<F, kLocPts>(d2, cs0, cns, s_AB, s_N, f, ab0);
                     lds_z_pack(next + 16, az, s0, ns);
                     lds_f64x2(next + 32, A0, al0);
+                } else if (HP_LOC_FUSED_SUM && !LOCAL && !guarded) {  // block-uniform branch
+                    // dense pass, guard-free: every shell goes straight into the running sum with
+                    // one DFMA (no separate pro-atom value, no final add), and the +1e-100 of
+                    // update_pro is skipped once it cannot change the sum any more
+                    double r[kLocPts];
+#pragma unroll
+                    for (int j = 0; j < kLocPts; ++j) r[j] = (F == HP_FUNCTOR_GAUSS) ? d2[j] : sqrt_fast(d2[j]);
+                    const double na = -al0;
+#pragma unroll
+                    for (int j = 0; j < kLocPts; ++j) pro[j] = fma(A0, exp_regs<false>(na * r[j], ec), pro[j]);
+                    lds_z_pack(next + 16, az, s0, ns);
+                    lds_f64x2(next + 32, A0, al0);
+                    for (int k = 1; k < cns; ++k) {
+                        double A, al;
+                        lds_f64x2(ab_addr + unsigned(cs0 + k) * 16u, A, al);
+                        al = -al;
+#pragma unroll
+                        for (int j = 0; j < kLocPts; ++j) pro[j] = fma(A, exp_regs<false>(al * r[j], ec), pro[j]);
+                    }
+                    if (!offset_is_void) {
+#pragma unroll
+                        for (int j = 0; j < kLocPts; ++j) pro[j] += promol_offset;
+                    }
+                    continue;
                 } else if (!guarded) {  // block-uniform branch
                     double r[kLocPts];
 #pragma unroll

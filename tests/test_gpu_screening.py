@@ -33,16 +33,21 @@ def test_atom_screening_is_exact(make_water, monkeypatch):
     plain, _ = _run(case, monkeypatch, False, shell_bits=0)  # the plain dense kernel, nothing skipped
     assert pairs_off == natom * npts * 1 or pairs_off == natom * npts  # last launch, all pairs
     assert pairs_on < 0.99 * pairs_off, (pairs_on, pairs_off)  # skips work even in a 30-bohr cluster
-    for other in (off, plain):
+    # `off` is the same kernel with every pair evaluated: same operation sequence except for the
+    # dropped terms.  `plain` is the reference-ordered kernel (each pro-atom summed over its shells
+    # first, then added): the chunk kernel feeds every shell straight into the running sum with one
+    # FMA, an equally valid but different rounding sequence of ~natom*K additions (random walk of
+    # half-ulp steps: a few hundred ulp at worst over 768,000 points).
+    for other, max_ulp, same, wtol in ((off, 64, 0.9, 1e-15), (plain, 512, 0.0, 1e-13)):
         a, b = on["promoldens"], other["promoldens"]
         ulp = np.spacing(np.abs(b))
-        assert (np.abs(a - b) <= 64 * ulp).all()
-        assert (a == b).mean() > 0.9
+        assert (np.abs(a - b) <= max_ulp * ulp).all(), float((np.abs(a - b) / ulp).max())
+        assert (a == b).mean() >= same
         np.testing.assert_allclose(on["charges"], other["charges"], rtol=0, atol=5e-14)
         np.testing.assert_allclose(on["propars"], other["propars"], rtol=1e-13)
         np.testing.assert_allclose(on["history_entropies"], other["history_entropies"], rtol=1e-13)
         for atom in (0, 17, natom - 1):
-            np.testing.assert_allclose(on[f"at_weights_{atom}"], other[f"at_weights_{atom}"], rtol=1e-15, atol=1e-300)
+            np.testing.assert_allclose(on[f"at_weights_{atom}"], other[f"at_weights_{atom}"], rtol=wtol, atol=1e-300)
     # far outside the cluster the promolecule is tiny: the test must have stayed off there
     assert on["promoldens"].min() < 1e-60
 

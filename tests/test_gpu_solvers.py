@@ -147,7 +147,8 @@ def test_alisa_convex_programme_against_reference_run(water6, water6g, tag, kw):
     assert part["niter"] == int(ref["niter"])
     np.testing.assert_allclose(part["charges"], ref["charges"], rtol=1e-8, atol=1e-9)
     np.testing.assert_allclose(part["history_changes"], ref["history_changes"], rtol=1e-5, atol=1e-10)
-    np.testing.assert_allclose(part["promoldens"][::97], ref["promoldens_sample"], rtol=1e-8)
+    # (far tails, below 1e-20 of the peak, carry the looseness of single Slater coefficients)
+    np.testing.assert_allclose(part["promoldens"][::97], ref["promoldens_sample"], rtol=1e-8, atol=1e-18)
     if "slater" not in tag:  # (Slater coefficients are loose along flat directions, see test_algo_host)
         np.testing.assert_allclose(part["propars"], ref["propars"], rtol=1e-6, atol=1e-8)
     assert (part["propars"] >= 0).all()
