@@ -363,7 +363,7 @@ class ShellTable:
                 _lib.call("hp_shell_screen", s.natom, self.nshell, self.offsets, self.A, self.alpha, float(bits),
                           self.skip, stream_ptr(s.device))  # fmt: skip
                 if self.atom_screen and os.environ.get("HP_B200_ATOM_SCREEN", "1") != "0":
-                    atom_eps = 2.0 ** -(55 + int(np.ceil(np.log2(max(s.natom, 2)))))
+                    atom_eps = 2.0 ** -(float(os.environ.get("HP_B200_ATOM_BITS", 55)) + int(np.ceil(np.log2(max(s.natom, 2)))))
             radius = float("inf") if self.local_radius is None else float(self.local_radius)
             _lib.call(
                 "hp_promol_weights_local", self.functor, s.npts, s.px, s.py, s.pz, s.point_base, s.natom,

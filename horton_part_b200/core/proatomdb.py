@@ -2,8 +2,9 @@
 
 API of the reference's ``ProAtomRecord`` / ``ProAtomDB`` (core/proatomdb.py:34-447) as far as the
 partitioning path uses it: records keyed by (number, charge), one radial grid per element, linear
-(or geometric) combinations of charge states, spline construction.  ``compact`` / ``normalize`` /
-dispersion helpers are post-processing utilities outside the accelerated path.
+(or geometric) combinations of charge states, spline construction, and the database preparation
+helpers ``compact`` / ``normalize`` (:390-447) with the record methods they use (``compute_radii``,
+``chop``, equality).  All of it is host-side set-up; the device sees PPoly coefficients only.
 """
 
 from __future__ import annotations
@@ -48,6 +49,49 @@ class ProAtomRecord:
 
     def get_moment(self, order):
         return self.rgrid.integrate(self.rho, self.rgrid.points**order)
+
+    def compute_radii(self, populations):
+        """Radii (and grid indices) at which the running integral of the density reaches the
+        given populations, by linear interpolation between grid points (core/proatomdb.py:154-179)."""
+        radii = self.rgrid.points
+        running = np.cumsum(4 * np.pi * radii**2 * self.rho * self.rgrid.weights)
+        indexes = running.searchsorted(populations)
+        result = []
+        for pop, i in zip(populations, indexes):
+            if i == len(running):
+                result.append(radii[-1])
+            else:
+                x = (pop - running[i]) / (running[i - 1] - running[i])
+                result.append(x * radii[i - 1] + (1 - x) * radii[i])
+        return indexes, result
+
+    def chop(self, npoint):
+        """Keep the first ``npoint`` radial points."""
+        from ..gridlite import OneDGrid
+
+        self._rho = self._rho[:npoint]
+        if self._deriv is not None:
+            self._deriv = self._deriv[:npoint]
+        self._rgrid = OneDGrid(self._rgrid.points[:npoint], self._rgrid.weights[:npoint])
+
+    def __eq__(self, other):
+        if not isinstance(other, ProAtomRecord):
+            return NotImplemented
+        same_grid = (self.rgrid.size == other.rgrid.size and np.array_equal(self.rgrid.points, other.rgrid.points)
+                     and np.array_equal(self.rgrid.weights, other.rgrid.weights))  # fmt: skip
+        same_deriv = (self.deriv is None and other.deriv is None) or (
+            self.deriv is not None and other.deriv is not None and np.array_equal(self.deriv, other.deriv))
+        return bool(
+            self.number == other.number and self.charge == other.charge and self.energy == other.energy
+            and same_grid and np.array_equal(self.rho, other.rho) and same_deriv
+            and self.pseudo_number == other.pseudo_number and self.ipot_energy == other.ipot_energy
+        )  # fmt: skip
+
+    def __ne__(self, other):
+        result = self.__eq__(other)
+        return result if result is NotImplemented else not result
+
+    __hash__ = None
 
 
 class ProAtomDB:
@@ -123,3 +167,28 @@ class ProAtomDB:
         rho, deriv = self.get_rho(number, parameters, combine, do_deriv=True)
         x = self.get_rgrid(number).points
         return CubicSpline(x, rho, True) if deriv is None else CubicHermiteSpline(x, rho, deriv, True)
+
+    def compact(self, nel_lost):
+        """Cut the radial grids where the tail of every *safe* state holds at most ``nel_lost``
+        electrons (core/proatomdb.py:390-431); all states of an element keep a common grid."""
+        from ..gridlite import OneDGrid
+
+        for number in self.get_numbers():
+            npoint = 0
+            for charge in self.get_charges(number, safe=True):
+                rec = self.get_record(number, charge)
+                nel = rec.pseudo_number - charge
+                npoint = max(npoint, int(rec.compute_radii([nel - nel_lost])[0][0]) + 1)
+            for charge in self.get_charges(number):
+                self.get_record(number, charge).chop(npoint)
+            old = self._rgrid_map[number]
+            self._rgrid_map[number] = OneDGrid(old.points[:npoint], old.weights[:npoint])
+
+    def normalize(self):
+        """Scale every density to its integer (pseudo-)population on its radial grid, in place
+        (core/proatomdb.py:433-447; the integral is the reference's plain ``rgrid.integrate(rho)``)."""
+        for number in self.get_numbers():
+            rgrid = self.get_rgrid(number)
+            for charge in self.get_charges(number):
+                rec = self.get_record(number, charge)
+                rec.rho[:] *= (rec.pseudo_number - charge) / rgrid.integrate(rec.rho)

@@ -436,6 +436,32 @@ def case_numeric(natom=6, nrad=40, nang=50, seed=0):
     save("water6_numeric.npz", results, coordinates=coords, numbers=numbers, **extra)
 
 
+def case_proatomdb():
+    """ProAtomDB.compact / normalize / compute_radii of the reference (core/proatomdb.py:154-190,
+    390-447) on its cached HF/STO-3G records (the ones packed into h2o_hirshfeld.npz)."""
+    from horton_part.core.proatomdb import ProAtomDB
+
+    records, _ = load_proatom_records()
+    db = ProAtomDB(records)
+    out = {}
+    for z in db.get_numbers():
+        out[f"charges/{z}"] = np.array(db.get_charges(z))
+        out[f"safe/{z}"] = np.array(db.get_charges(z, safe=True))
+        for q in db.get_charges(z):
+            rec = db.get_record(z, q)
+            idx, radii = rec.compute_radii([0.5 * rec.pseudo_population, rec.pseudo_population - 0.1, 1e3])
+            out[f"radii/{z}/{q}"] = np.concatenate([idx, radii])
+    db.compact(0.1)
+    for z in db.get_numbers():
+        out[f"compact_size/{z}"] = np.int64(db.get_rgrid(z).size)
+    db.normalize()
+    for z in db.get_numbers():
+        for q in db.get_charges(z):
+            out[f"normalized/{z}/{q}"] = db.get_record(z, q).rho
+    np.savez_compressed(GOLD / "proatomdb.npz", **out)
+    print("wrote", GOLD / "proatomdb.npz", len(out), "entries")
+
+
 def case_postproc():
     """Post-processing beyond charges on water HF/STO-3G: Becke scheme
     (becke.py), density decomposition splines (core/base.py:637-659), pro-atom splines
@@ -557,7 +583,7 @@ def case_molecules():
 
 
 CASES = {"h2o": case_h2o, "water6": case_water_cluster, "water6g": case_water_gauss, "hirshfeld": case_hirshfeld,
-         "solvers": case_water6_solvers, "convex": case_water6_convex, "convex_radial": case_convex_radial, "numeric": case_numeric, "algo": case_algo, "postproc": case_postproc,
+         "solvers": case_water6_solvers, "convex": case_water6_convex, "convex_radial": case_convex_radial, "numeric": case_numeric, "proatomdb": case_proatomdb, "algo": case_algo, "postproc": case_postproc,
          "molecules": case_molecules}
 
 if __name__ == "__main__":
