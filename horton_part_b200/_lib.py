@@ -69,6 +69,11 @@ EXPORTS = {
         [_i64, _p, _p, _p, _i64, _i32, _p, _p, _p, _p, _p, _f64, _p, _p, _f64, _p, _p, _p, _p],
     ),
     "hp_isa_update": (_int, [_i32, _i32, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
+    "hp_spline_integral_blocks": (_i32, [_i64]),
+    "hp_atom_weight_integrals_spline": (
+        _int,
+        [_i64, _p, _p, _p, _i32, _p, _p, _p, _p, _f64, _p, _p, _p, _p, _p, _p],
+    ),
     "hp_molgrid_num_blocks": (_i32, [_i64]),
     "hp_shell_moments": (
         _int,

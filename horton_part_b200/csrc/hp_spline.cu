@@ -180,6 +180,46 @@ promol_weights_spline_kernel(int64_t npts, const double* __restrict__ px, const 
     }
 }
 
+// N_a = sum_p molw[p] * dens[p] * clip((S_a(|r_p - R_a|) + offset) / promol[p], 0, 1) over ALL points of
+// the slab: populations on the molecular grid for spline pro-atoms (grid_type 2/3; core/base.py:
+// 287-298 with on_molgrid weights) without storing natom x Npts weight arrays.  blockIdx.y = atom,
+// blockIdx.x strides over the points; the per-block sums are folded per atom in a fixed order.
+constexpr int kAwiThreads = 256;
+
+__global__ void __launch_bounds__(kAwiThreads)
+atom_weight_integrals_spline_kernel(int64_t npts, const double* __restrict__ px, const double* __restrict__ py,
+                                    const double* __restrict__ pz, const double* __restrict__ atom_xyz,
+                                    const int* __restrict__ knot_off, const double* __restrict__ knots,
+                                    const double* __restrict__ coef, double proatom_offset,
+                                    const double* __restrict__ dens, const double* __restrict__ molw,
+                                    const double* __restrict__ promol, double* __restrict__ partial) {
+    __shared__ double s_red[32];
+    const int a = blockIdx.y;
+    const double ax = atom_xyz[3 * a], ay = atom_xyz[3 * a + 1], az = atom_xyz[3 * a + 2];
+    const int o = knot_off[a], n = knot_off[a + 1] - o;
+    const double* xk = knots + o;
+    const double* ck = coef + 4 * (o - a);
+    double acc = 0.0;
+    for (int64_t p = int64_t(blockIdx.x) * kAwiThreads + threadIdx.x; p < npts; p += int64_t(gridDim.x) * kAwiThreads) {
+        const double dx = px[p] - ax, dy = py[p] - ay, dz = pz[p] - az;
+        const double r = sqrt_nocall(fma(dz, dz, fma(dy, dy, dx * dx)));
+        const double f = spline_eval(xk, ck, n, r) + proatom_offset;
+        const double w = fmin(fmax(f / promol[p], 0.0), 1.0);
+        acc += molw[p] * (w * dens[p]);
+    }
+    const double total = block_sum(acc, s_red);
+    if (threadIdx.x == 0) partial[int64_t(a) * gridDim.x + blockIdx.x] = total;
+}
+
+__global__ void fold_atom_partials_kernel(int natom, int nblk, const double* __restrict__ partial,
+                                          double* __restrict__ out) {
+    const int a = blockIdx.x * blockDim.x + threadIdx.x;
+    if (a >= natom) return;
+    double s = 0.0;
+    for (int b = 0; b < nblk; ++b) s += partial[int64_t(a) * nblk + b];
+    out[a] = s;
+}
+
 // ISA update, one warp per atom (isa.py:102-122).
 __global__ void __launch_bounds__(32)
 isa_update_kernel(int natom, int atom_base, const int* __restrict__ rad_off,
@@ -269,5 +309,35 @@ extern "C" int hp_isa_update(int32_t natom, int32_t atom_base, const int32_t* ra
                                                            sph_avg, par_offsets, propars,
                                                            pseudo_numbers, charges, msd);
     HP_LAUNCH_CHECK("isa_update_kernel");
+    return HP_OK;
+}
+
+extern "C" int32_t hp_spline_integral_blocks(int64_t npts) {
+    const int64_t want = (npts + kAwiThreads - 1) / kAwiThreads;
+    return int32_t(want < 1 ? 1 : (want > 64 ? 64 : want));
+}
+
+extern "C" int hp_atom_weight_integrals_spline(int64_t npts, const double* px, const double* py,
+                                               const double* pz, int32_t natom, const double* atom_xyz,
+                                               const int32_t* knot_offsets, const double* knots,
+                                               const double* coef, double proatom_offset,
+                                               const double* dens, const double* molw,
+                                               const double* promol, double* partial, double* out,
+                                               void* stream) {
+    HP_REQUIRE(npts >= 0 && natom > 0 && atom_xyz && knot_offsets && knots && coef && partial && out,
+               "bad arguments");
+    HP_REQUIRE(npts == 0 || (px && py && pz && dens && molw && promol), "bad arguments");
+    const int nblk = hp_spline_integral_blocks(npts);
+    if (npts > 0) {
+        atom_weight_integrals_spline_kernel<<<dim3(nblk, natom), kAwiThreads, 0, as_stream(stream)>>>(
+            npts, px, py, pz, atom_xyz, knot_offsets, knots, coef, proatom_offset, dens, molw, promol, partial);
+        HP_LAUNCH_CHECK("atom_weight_integrals_spline_kernel");
+    } else {
+        const int rc = check_cuda(cudaMemsetAsync(partial, 0, sizeof(double) * size_t(natom) * nblk,
+                                                  as_stream(stream)), "memset partials");
+        if (rc != HP_OK) return rc;
+    }
+    fold_atom_partials_kernel<<<(natom + 127) / 128, 128, 0, as_stream(stream)>>>(natom, nblk, partial, out);
+    HP_LAUNCH_CHECK("fold_atom_partials_kernel");
     return HP_OK;
 }

@@ -92,6 +92,30 @@ class DatabaseSplineMixin:
         flat = np.concatenate([c.ravel() for c in per_atom])
         self._table.coef.copy_(torch.from_numpy(flat))
 
+    def _atom_integrals(self, density):
+        """int w_a * density.  grid_type 1 and 2 integrate every atom on its own atomic grid
+        (core/base.py:287-298: the full-grid weights are cut back to the owner block); grid_type 3
+        has no atomic grids and integrates w_a over the whole molecular grid, which
+        ``hp_atom_weight_integrals_spline`` does without natom x Npts weight arrays."""
+        if not self.only_use_molgrid:
+            return super()._atom_integrals(density)
+        import torch
+
+        from . import _lib
+        from .core.device import stream_ptr, to_device
+
+        slab, t = self.slab, self._table
+        if self._comm is not None:
+            raise NotImplementedError("grid_type 3 populations of spline pro-atoms run on one GPU")
+        dens = slab.rho if density is self._moldens else to_device(np.asarray(density, dtype=float), slab.device)
+        nblk = int(_lib.call("hp_spline_integral_blocks", slab.npts))
+        partial = torch.zeros(self.natom * nblk, dtype=torch.float64, device=slab.device)
+        out = torch.zeros(self.natom, dtype=torch.float64, device=slab.device)
+        _lib.call("hp_atom_weight_integrals_spline", slab.npts, slab.px, slab.py, slab.pz, self.natom,
+                  slab.atom_xyz, t.offsets, t.knots, t.coef, float(t.proatom_offset), dens, slab.molw,
+                  slab.promol, partial, out, stream_ptr(slab.device))  # fmt: skip
+        return out.cpu().numpy()
+
 
 class HirshfeldWPart(DatabaseSplineMixin, AbstractStockholderWPart):
     """Hirshfeld partitioning with Becke-Lebedev grids"""
@@ -121,8 +145,6 @@ class HirshfeldWPart(DatabaseSplineMixin, AbstractStockholderWPart):
 
     def _refresh_table(self):
         if getattr(self, "_table", None) is None:
-            if self.on_molgrid:
-                raise NotImplementedError("Hirshfeld with grid_type 2/3 is not built yet")
             self._setup_spline_table()
             self._upload_coefficients([self._state_coefficients(z, 0) for z in self.numbers])
 

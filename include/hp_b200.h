@@ -259,6 +259,22 @@ HP_API int hp_isa_update(int32_t natom, int32_t atom_base, const int32_t* rad_of
                          const int32_t* par_offsets, double* propars, const double* pseudo_numbers,
                          double* charges, double* msd, void* stream);
 
+/* hp_atom_weight_integrals_spline -- populations on the MOLECULAR grid for spline pro-atoms
+ * (Hirshfeld with grid_type 2/3: do_populations, core/base.py:287-298, with the full-grid weights
+ * of update_at_weights, core/stockholder.py:352-384):
+ *     out[a] = sum_p molw[p] * dens[p] * clip((S_a(|r_p - R_a|) + proatom_offset) / promol[p], 0, 1)
+ * over all npts points, without storing natom x Npts weight arrays.  `promol` comes from
+ * hp_promol_weights_spline on the same coefficients; `partial` is scratch of
+ * natom x hp_spline_integral_blocks(npts) doubles, folded per atom in a fixed order. */
+HP_API int32_t hp_spline_integral_blocks(int64_t npts);
+HP_API int hp_atom_weight_integrals_spline(int64_t npts, const double* px, const double* py,
+                                           const double* pz, int32_t natom, const double* atom_xyz,
+                                           const int32_t* knot_offsets, const double* knots,
+                                           const double* coef, double proatom_offset,
+                                           const double* dens, const double* molw,
+                                           const double* promol, double* partial, double* out,
+                                           void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * (row a12, and a9 on the molecular grid) reductions over ALL local grid points with the basis
  * functions regenerated in-kernel -- the reference's (M, Npts) `pro_shells` arrays

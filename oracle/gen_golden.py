@@ -155,6 +155,11 @@ def case_hirshfeld():
                        history_charges=part["history_charges"], history_entropies=part["history_entropies"])
         results[tag] = out
         print(f"  h2o {tag}: q={part['charges']} niter={out.get('niter')}")
+    for gt in (2, 3):  # Hirshfeld on the molecular grid (Hirshfeld-I raises ValueError there in the reference)
+        part = wpart_schemes("h")(coords, numbers, pseudo, grid, rho, proatomdb=ProAtomDB(records), grid_type=gt)
+        part.do_charges()
+        results[f"h_gt{gt}"] = {"charges": part["charges"], "promoldens_sample": part["promoldens"][::97].copy()}
+        print(f"  h2o h grid_type {gt}: q={part['charges']}")
     save("h2o_hirshfeld.npz", results, **{f"record/{k}": v for k, v in raw.items()})
 
 

@@ -42,3 +42,26 @@ def test_proatomdb_pseudo_number_mismatch(h2o, h2o_proatomdb):
     db, _ = h2o_proatomdb
     with pytest.raises(ValueError, match="pseudo number"):
         HirshfeldWPart(h2o["coords"], h2o["numbers"], np.array([6.0, 1.0, 1.0]), h2o["grid"], h2o["rho"], db)
+
+
+@pytest.mark.parametrize("grid_type", [2, 3])
+def test_hirshfeld_on_the_molecular_grid(h2o, h2o_proatomdb, grid_type):
+    """grid_type 2 integrates every atom on its own atomic grid like grid_type 1 (core/base.py:
+    287-298 cuts the full-grid weights back to the owner block); grid_type 3 integrates the weight
+    function over the WHOLE molecular grid (hp_atom_weight_integrals_spline).  Goldens: reference
+    runs.  (Hirshfeld-I raises ValueError there in the reference and is not offered.)"""
+    from horton_part_b200 import HirshfeldIWPart, HirshfeldWPart
+
+    db, gold = h2o_proatomdb
+    args = (h2o["coords"], h2o["numbers"], h2o["pseudo"], h2o["grid"], h2o["rho"], db)
+    part = HirshfeldWPart(*args, grid_type=grid_type)
+    part.do_charges()
+    np.testing.assert_allclose(part["charges"], gold[f"h_gt{grid_type}/charges"], rtol=1e-8, atol=1e-10)
+    np.testing.assert_allclose(part["promoldens"][::97], gold[f"h_gt{grid_type}/promoldens_sample"], rtol=1e-9)
+    if grid_type == 2:
+        np.testing.assert_allclose(part["charges"], gold["h/charges"], rtol=1e-8, atol=1e-10)
+    else:
+        assert np.abs(part["charges"] - gold["h/charges"]).max() > 1e-5  # a different quadrature
+        assert abs(part["charges"].sum() - (h2o["pseudo"].sum() - h2o["grid"].integrate(h2o["rho"]))) < 1e-9
+    with pytest.raises(NotImplementedError):
+        HirshfeldIWPart(*args, grid_type=grid_type).do_charges()
