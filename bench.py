@@ -227,7 +227,7 @@ def main():
     ap.add_argument("--natom", type=int, default=2000)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--cpu-points", type=int, default=16384, help="grid points per core in the CPU sample")
-    ap.add_argument("--cpu-reps", type=int, default=16, help="passes over the CPU sample")
+    ap.add_argument("--cpu-reps", type=int, default=48, help="passes over the CPU sample (48: about 15 s of CPU work)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-unscreened", action="store_true", help="skip the extra run with atom screening off")
     ap.add_argument("--pinned-inputs", action="store_true",

@@ -151,3 +151,11 @@ class HirshfeldWPart(DatabaseSplineMixin, AbstractStockholderWPart):
     def _launch_promol_weights(self, want_entropy=True):
         self._refresh_table()
         self._table.promol_weights(self.density_cutoff, True, True, want_entropy)
+
+    def update_at_weights(self, force_on_molgrid=False):
+        """One pass: promolecule and weights from the fixed database pro-atoms.  With grid_type 2/3
+        the reference caches full-grid weight arrays (natom x Npts); here the cache holds every
+        atom's weights on its own block and grid_type 3 populations integrate the weight function
+        over the whole grid inside ``hp_atom_weight_integrals_spline``."""
+        self._launch_promol_weights(want_entropy=False)
+        self._publish_weights()
