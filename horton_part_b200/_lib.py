@@ -109,7 +109,8 @@ EXPORTS = {
 
 # int-returning functions whose result is a value, not a status code
 _NOT_STATUS = {"hp_abi_version", "hp_num_partials", "hp_local_index_scratch_bytes", "hp_last_error", "hp_tile_limits", "hp_molgrid_num_blocks", "hp_hessian_scratch_bytes",
-               "hp_molgrid_update_tile_limits", "hp_host_is_pinned", "hp_local_tile_limits", "hp_local_chunk_points"}
+               "hp_molgrid_update_tile_limits", "hp_host_is_pinned", "hp_local_tile_limits", "hp_local_chunk_points",
+               "hp_spline_integral_blocks"}
 
 
 class HpError(RuntimeError):

@@ -19,6 +19,16 @@ def test_header_symbols_exported(built_lib):
     assert _lib.call("hp_num_partials") >= 148
 
 
+def test_value_returning_symbols_are_not_treated_as_status_codes():
+    """Entry points whose C return type is not plain ``int`` return a value (a count, a size, a
+    string); _lib.call must not map their non-zero results to exceptions."""
+    from horton_part_b200 import _lib
+
+    header = (ROOT / "include" / "hp_b200.h").read_text()
+    valued = set(re.findall(r"HP_API\s+(?:int32_t|size_t|const char\*|void)\s+(hp_[a-z0-9_]+)\s*\(", header))
+    assert valued and valued <= _lib._NOT_STATUS, valued - _lib._NOT_STATUS
+
+
 def test_argument_errors_map_to_exceptions(built_lib):
     import pytest
 

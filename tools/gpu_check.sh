@@ -7,7 +7,7 @@ python -c "import torch; print(torch.cuda.get_device_name(0))" > gpurun_out/${ta
 timeout 200 python -m pytest -q -p no:cacheprovider --timeout 120 \
     tests/test_gpu_solvers.py -k "convex" \
     tests/test_gpu_molgrid.py \
-    tests/test_gpu_schemes.py \
+    tests/test_gpu_schemes.py tests/test_gpu_hirshfeld.py tests/test_gpu_ragged.py \
     > gpurun_out/${tag}_new_tests.log 2>&1
 echo "rc=$?" >> gpurun_out/${tag}_new_tests.log
 tail -25 gpurun_out/${tag}_new_tests.log
