@@ -60,6 +60,7 @@ constexpr int kLocPts = HP_LOC_PTS;
 constexpr int kLocSpan = kLocThreads * kLocPts;  // points per chunk
 constexpr int kLocTileAtoms = kLocThreads;       // candidate atoms per shared-memory tile (one per thread)
 constexpr int kLocTileShells = 1024;
+constexpr double kDist2Bias = 1e-300;  // see the distance computation of the candidate loop
 
 // Candidate record in shared memory: 48 bytes = three 16-byte loads.
 struct __align__(16) LocAtom {
@@ -261,9 +262,9 @@ promol_weights_local_kernel(int64_t npts, const double* __restrict__ px, const d
                         } else if (F != HP_FUNCTOR_GENERAL) {
                             for (int k = 0; k < ns_all; ++k) amax = fmax(amax, shell_alpha[gs0 + k]);
                         }
-                        // guards can go when no point of the chunk can sit on this nucleus and no
-                        // exponent argument can reach the underflow range
-                        if (F != HP_FUNCTOR_GENERAL) fast = xmin > 1e-100 && amax * xmax < 700.0;
+                        // guards can go when no exponent argument can reach the underflow range (and,
+                        // in cut-off mode where distances are exact, no point can sit on this nucleus)
+                        if (F != HP_FUNCTOR_GENERAL) fast = (!LOCAL || xmin > 1e-100) && amax * xmax < 700.0;
                     }
                 }
                 const unsigned m = __ballot_sync(0xffffffffu, cand);
@@ -343,7 +344,11 @@ promol_weights_local_kernel(int64_t npts, const double* __restrict__ px, const d
 #pragma unroll
                 for (int j = 0; j < kLocPts; ++j) {
                     const double dx = x[j] - ax, dy = y[j] - ay, dz = z[j] - az;
-                    d2[j] = LOCAL ? dist2_unfused3(dx, dy, dz) : fma(dz, dz, fma(dy, dy, dx * dx));
+                    // dense pass: the squared distance carries a bias of 1e-300 (the DMUL of dx*dx
+                    // becomes a DFMA), absorbed without trace by any d2 above 1e-284 and turning a grid
+                    // point that sits exactly on a nucleus into r = 1e-150 (exp(-alpha r) is still
+                    // exactly 1): the guard-free sqrt then needs no zero-distance test
+                    d2[j] = LOCAL ? dist2_unfused3(dx, dy, dz) : fma(dz, dz, fma(dy, dy, fma(dx, dx, kDist2Bias)));
                 }
                 lds_f64x2(next, ax, ay);  // the centre is dead from here on: fetch the next one
                 const int cs0 = s0 & 0x7fffffff, cns = ns;

@@ -62,6 +62,7 @@ def test_hirshfeld_on_the_molecular_grid(h2o, h2o_proatomdb, grid_type):
         np.testing.assert_allclose(part["charges"], gold["h/charges"], rtol=1e-8, atol=1e-10)
     else:
         assert np.abs(part["charges"] - gold["h/charges"]).max() > 1e-5  # a different quadrature
-        assert abs(part["charges"].sum() - (h2o["pseudo"].sum() - h2o["grid"].integrate(h2o["rho"]))) < 1e-9
+        # the weights sum to one except where a database spline undershoots below zero and is clipped
+        assert abs(part["charges"].sum() - (h2o["pseudo"].sum() - h2o["grid"].integrate(h2o["rho"]))) < 1e-6
     with pytest.raises(NotImplementedError):
         HirshfeldIWPart(*args, grid_type=grid_type).do_charges()
