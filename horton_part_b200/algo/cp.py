@@ -153,6 +153,8 @@ def cp(F, G=None, h=None, A=None, b=None, options=None):
         if mi and feasible and (gap <= opts["abstol"] or relgap <= opts["reltol"]):
             status = "optimal"
             break
+        if mi and it == int(opts["maxiters"]):
+            break  # (without inequalities the stopping rule needs one more Newton direction)
         _, _, H = F(x, one)
         H = np.asarray(H, dtype=float).reshape(n, n)
         newton = _Newton(H, G, A, s, z)
