@@ -36,7 +36,7 @@ from __future__ import annotations
 import numpy as np
 from scipy.linalg import lu_factor, lu_solve
 
-__all__ = ["cp"]
+__all__ = ["cp", "cp_simplex_batched"]
 
 
 def _as_matrix(M, n):
@@ -217,3 +217,157 @@ def cp(F, G=None, h=None, A=None, b=None, options=None):
         "status": status, "x": x, "y": y, "zl": z, "sl": s, "primal objective": float(f),
         "iterations": it, **info,
     }  # fmt: skip
+
+
+def cp_simplex_batched(bs, rho, weights, x0, density_cutoff, options=None):
+    """The aLISA programme for a BATCH of atoms with identical shapes, all atoms advanced together:
+
+        min_c  sum_i w_i rho_i ln(rho_i / (c . g)_i)     s.t.  c >= 0,  sum c = sum_i w_i rho_i
+
+    ``bs`` (B, K, N) basis functions, ``rho`` / ``weights`` (B, N), ``x0`` (B, K).  Same method, same
+    arithmetic and same stopping rule as :func:`cp` with G = -I, h = 0, A = 1^T (objective, masks and
+    derivatives as in the reference's ``obj_func``, alisa.py:141-160, with ``compute_quantities``,
+    utils.py:198-252), but every dense operation is one stacked NumPy call over the atoms that are
+    still iterating -- the per-atom Python loop is what limits the host plug-in path on large systems
+    (2,000 atoms: ~10 s per outer iteration one by one, ~0.1 s batched).
+
+    Returns ``(x (B, K), optimal (B,) bool, iterations (B,) int)``.
+    """
+    opts = {"abstol": 1e-14, "reltol": 1e-13, "feastol": 1e-9, "maxiters": 100}
+    opts.update({k: v for k, v in (options or {}).items() if k in opts})
+    bs = np.asarray(bs, dtype=float)
+    rho = np.asarray(rho, dtype=float)
+    w = np.asarray(weights, dtype=float)
+    nb, K, _ = bs.shape
+    pop = np.einsum("bn,bn->b", w, rho)
+    wr = w * rho
+
+    def objective(idx, x, second=False):
+        """f, grad (and Hessian) for the atoms ``idx`` at coefficients ``x`` (len(idx), K)."""
+        g_, rho_ = bs[idx], rho[idx]
+        pro = np.einsum("bk,bkn->bn", x, g_)
+        sick = (rho_ < density_cutoff) | (pro < density_cutoff)
+        with np.errstate(all="ignore"):
+            ratio = np.where(sick, 0.0, rho_ / np.where(sick, 1.0, pro))
+            ln_ratio = np.where(sick, 0.0, np.log(np.where(sick, 1.0, ratio)))
+        f = np.einsum("bn,bn->b", wr[idx], ln_ratio)
+        first = w[idx] * ratio
+        grad = -np.einsum("bn,bkn->bk", first, g_)
+        if not second:
+            return f, grad
+        with np.errstate(all="ignore"):
+            scnd = np.where(sick, 0.0, first / np.where(sick, 1.0, pro))
+        return f, grad, np.einsum("bn,bkn,bln->bkl", scnd, g_, g_)
+
+    x = np.array(x0, dtype=float).reshape(nb, K).copy()
+    everyone = np.arange(nb)
+    f, g = objective(everyone, x)
+    if not (np.isfinite(f).all() and np.isfinite(g).all()):
+        raise ValueError("the objective is not finite at the starting point")
+    y = np.zeros(nb)
+    s = np.maximum(x, 1e-3 * np.maximum(1.0, np.abs(x).max(axis=1))[:, None])
+    z = (0.1 * np.maximum(1.0, np.abs(g).max(axis=1)) * s.mean(axis=1))[:, None] / s
+    scale_d = np.maximum(1.0, np.linalg.norm(g, axis=1))
+    scale_e = np.maximum(1.0, np.abs(pop))
+    optimal = np.zeros(nb, dtype=bool)
+    iterations = np.zeros(nb, dtype=int)
+    active = np.ones(nb, dtype=bool)
+
+    def max_step(v, dv):
+        with np.errstate(all="ignore"):
+            ratio = np.where(dv < 0, -v / np.where(dv < 0, dv, -1.0), np.inf)
+        return ratio.min(axis=1)
+
+    for it in range(int(opts["maxiters"]) + 1):
+        idx = np.flatnonzero(active)
+        if idx.size == 0:
+            break
+        xa, ya, sa, za, ga, fa = x[idx], y[idx], s[idx], z[idx], g[idx], f[idx]
+        r_d = ga - za + ya[:, None]
+        r_p = sa - xa
+        r_e = xa.sum(axis=1) - pop[idx]
+        gap = np.einsum("bk,bk->b", sa, za)
+        pres = np.maximum(np.abs(r_p).max(axis=1), np.abs(r_e) / scale_e[idx])
+        dres = np.linalg.norm(r_d, axis=1) / scale_d[idx]
+        with np.errstate(all="ignore"):
+            relgap = np.where(fa != 0, gap / np.abs(fa), np.inf)
+        feasible = (pres <= opts["feastol"]) & (dres <= opts["feastol"])
+        done = feasible & ((gap <= opts["abstol"]) | (relgap <= opts["reltol"]))
+        iterations[idx] = it
+        optimal[idx[done]] = True
+        active[idx[done]] = False
+        if it == int(opts["maxiters"]):
+            break
+        keep = ~done
+        if not keep.any():
+            break
+        idx, xa, ya, sa, za, fa = idx[keep], xa[keep], ya[keep], sa[keep], za[keep], fa[keep]
+        r_d, r_p, r_e, gap, feasible, relgap = r_d[keep], r_p[keep], r_e[keep], gap[keep], feasible[keep], relgap[keep]
+        m = idx.size
+
+        _, _, H = objective(idx, xa, second=True)
+        kkt = np.zeros((m, K + 1, K + 1))
+        kkt[:, :K, :K] = H
+        kkt[:, np.arange(K), np.arange(K)] += za / sa
+        kkt[:, :K, K] = 1.0
+        kkt[:, K, :K] = 1.0
+
+        def solve(r_c):
+            rhs = np.empty((m, K + 1))
+            rhs[:, :K] = -r_d + (za * r_p - r_c) / sa
+            rhs[:, K] = -r_e
+            sol = np.linalg.solve(kkt, rhs[:, :, None])[:, :, 0]
+            dx, dy = sol[:, :K], sol[:, K]
+            ds = -r_p + dx
+            dz = (-r_c - za * ds) / sa
+            return dx, dy, ds, dz
+
+        mu = gap / K
+        _, _, ds_a, dz_a = solve(sa * za)
+        a_s = np.minimum(1.0, max_step(sa, ds_a))
+        a_z = np.minimum(1.0, max_step(za, dz_a))
+        mu_aff = np.einsum("bk,bk->b", sa + a_s[:, None] * ds_a, za + a_z[:, None] * dz_a) / K
+        with np.errstate(all="ignore"):
+            sigma = np.where(mu > 0, np.minimum(1.0, np.maximum(1e-8, (mu_aff / mu) ** 3)), 0.0)
+        target = sigma * mu
+        dx, dy, ds, dz = solve(sa * za - target[:, None])
+
+        def merit(r_d, r_p, r_e, s_, z_):
+            return np.sqrt((r_d * r_d).sum(axis=1) + (r_p * r_p).sum(axis=1) + r_e * r_e
+                           + ((s_ * z_ - target[:, None]) ** 2).sum(axis=1))  # fmt: skip
+
+        m0 = merit(r_d, r_p, r_e, sa, za)
+        alpha = np.minimum(1.0, np.minimum(0.99 * max_step(sa, ds), 0.99 * max_step(za, dz)))
+        accepted = np.zeros(m, dtype=bool)
+        xn, yn, sn, zn = xa.copy(), ya.copy(), sa.copy(), za.copy()
+        fn, gn = fa.copy(), g[idx].copy()
+        for _ in range(60):
+            todo = np.flatnonzero(~accepted & (alpha >= 1e-12))
+            if todo.size == 0:
+                break
+            a = alpha[todo][:, None]
+            xt, st, zt = xa[todo] + a * dx[todo], sa[todo] + a * ds[todo], za[todo] + a * dz[todo]
+            yt = ya[todo] + alpha[todo] * dy[todo]
+            with np.errstate(all="ignore"):
+                ft, gt = objective(idx[todo], xt)
+            finite = np.isfinite(ft) & np.isfinite(gt).all(axis=1)
+            rd_t = gt - zt + yt[:, None]
+            rp_t = st - xt
+            re_t = xt.sum(axis=1) - pop[idx[todo]]
+            tgt = target[todo][:, None]
+            mt = np.sqrt((rd_t * rd_t).sum(axis=1) + (rp_t * rp_t).sum(axis=1) + re_t * re_t
+                         + ((st * zt - tgt) ** 2).sum(axis=1))  # fmt: skip
+            with np.errstate(all="ignore"):
+                ok = finite & (mt <= (1.0 - 0.01 * alpha[todo]) * m0[todo])
+            hit = todo[ok]
+            xn[hit], yn[hit], sn[hit], zn[hit], fn[hit], gn[hit] = xt[ok], yt[ok], st[ok], zt[ok], ft[ok], gt[ok]
+            accepted[hit] = True
+            alpha[todo[~ok]] *= 0.5
+        # atoms whose residual norm cannot be lowered any further: rounding floor (see cp)
+        stuck = ~accepted
+        if stuck.any():
+            fine = stuck & feasible & ((gap <= 1e-8) | (relgap <= 1e-7))
+            optimal[idx[fine]] = True
+            active[idx[stuck]] = False
+        x[idx], y[idx], s[idx], z[idx], f[idx], g[idx] = xn, yn, sn, zn, fn, gn
+    return x, optimal, iterations

@@ -24,10 +24,12 @@ from . import _lib
 from .core.basis import AnalyticBasisFuncHelper, ExpBasisFuncHelper, NumericBasisFuncHelper
 from .core.logging import deflist
 from .gisa import GaussianISAWPart
+from .utils import optional_package
 from .lisa_solvers import (  # noqa: F401  (re-exported like the reference's alisa module)
     HOST_SOLVERS,
     solver_cdiis,
     solver_cvxopt,
+    solver_cvxopt_batched,
     solver_diis,
     solver_m_newton,
     solver_newton,
@@ -122,6 +124,24 @@ class LinearISAWPart(GaussianISAWPart):
             max_inner, int(single), self._nrad_max, self._nshell_max, st.charges, st.msd, st.niter,
             st.flags, stream_ptr(slab.device),
         )  # fmt: skip
+
+    def _batched_host_solver(self):
+        """The built-in convex programme (the default solver) has a stacked version; it is used
+        unless the caller asks for the third-party engine, sign-free coefficients or the package is
+        installed (then the per-atom call hands the programme to it, as the reference does)."""
+        opts = self._solver_options
+        if callable(self._solver) or self._solver != "cvxopt" or opts.get("allow_neg_params", False):
+            return None
+        if opts.get("engine") == "cvxopt" or (opts.get("engine") is None and optional_package("cvxopt") is not None):
+            return None
+        engine_free = {k: v for k, v in opts.items() if k not in ("engine", "allow_neg_params")}
+
+        def solve(problems):
+            return solver_cvxopt_batched(
+                problems, self._inner_threshold, self.logger, density_cutoff=self.density_cutoff,
+                negative_cutoff=self.negative_cutoff, population_cutoff=self.population_cutoff, **engine_free)
+
+        return solve
 
     def _opt_propars(self, bs_funcs, rho, propars, points, weights, alphas, threshold):
         if callable(self._solver):

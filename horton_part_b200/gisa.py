@@ -338,6 +338,16 @@ class GaussianISAWPart(AbstractISAWPart):
         sh, ro = slab.shard, slab.rad_offsets_host
         charges = np.zeros(self.natom)
         msd = np.zeros(self.natom)
+        batched = self._batched_host_solver()
+        solved = None
+        if batched is not None:  # all local atoms in stacked NumPy calls instead of one by one
+            problems = []
+            for i, a in enumerate(range(sh.atom_lo, sh.atom_hi)):
+                rgrid = self.get_rgrid(a)
+                problems.append((self.cache.load(f"bs_funcs_{a}"), sph[ro[i] : ro[i + 1]],
+                                 propars[self._ranges[a] : self._ranges[a + 1]].copy(), rgrid.points,
+                                 4 * np.pi * rgrid.points**2 * rgrid.weights))  # fmt: skip
+            solved = batched(problems)
         for i, a in enumerate(range(sh.atom_lo, sh.atom_hi)):
             rgrid = self.get_rgrid(a)
             points = rgrid.points
@@ -345,10 +355,13 @@ class GaussianISAWPart(AbstractISAWPart):
             r_weights = 4 * np.pi * points**2 * rgrid.weights
             alphas = self.bs_helper.get_exponent(self.numbers[a]) if isinstance(self.bs_helper, ExpBasisFuncHelper) else None
             lo, hi = self._ranges[a], self._ranges[a + 1]
-            propars[lo:hi] = self._opt_propars(
-                self.cache.load(f"bs_funcs_{a}"), rho_sph, propars[lo:hi].copy(), points, r_weights,
-                alphas, self._inner_threshold,
-            )  # fmt: skip
+            if solved is not None:
+                propars[lo:hi] = solved[i]
+            else:
+                propars[lo:hi] = self._opt_propars(
+                    self.cache.load(f"bs_funcs_{a}"), rho_sph, propars[lo:hi].copy(), points, r_weights,
+                    alphas, self._inner_threshold,
+                )  # fmt: skip
             charges[a] = self.pseudo_numbers[a] - np.einsum("i,i", r_weights, rho_sph)
             delta = self.get_proatom_rho(a, propars)[0] - self.get_proatom_rho(a, old)[0]
             msd[a] = rgrid.integrate(4 * np.pi * points**2, delta, delta)
@@ -358,6 +371,11 @@ class GaussianISAWPart(AbstractISAWPart):
         ).to(dev)
         st.charges[sh.atom_lo : sh.atom_hi] = torch.from_numpy(charges[sh.atom_lo : sh.atom_hi]).to(dev)
         st.msd[sh.atom_lo : sh.atom_hi] = torch.from_numpy(msd[sh.atom_lo : sh.atom_hi]).to(dev)
+
+    def _batched_host_solver(self):
+        """A callable solving the radial problems of ALL local atoms at once, or None when the
+        solver has to be called atom by atom (user callables, solvers without a stacked version)."""
+        return None
 
     def _opt_propars(self, bs_funcs, rho, propars, points, weights, alphas, threshold):
         if callable(self._solver):

@@ -44,6 +44,7 @@ __all__ = [
     "solver_quasi_newton",
     "solver_trust_region",
     "solver_cvxopt",
+    "solver_cvxopt_batched",
     "solver_sc_plus_cvxopt",
     "HOST_SOLVERS",
 ]
@@ -295,6 +296,39 @@ def solver_cvxopt(bs_funcs, rho, propars, points, weights, threshold, logger, de
         c, basis_functions=np.asarray(bs_funcs), logger=logger, total_population=float(pop),
         negative_cutoff=negative_cutoff, population_cutoff=population_cutoff)  # fmt: skip
     return c
+
+
+def solver_cvxopt_batched(problems, threshold, logger, density_cutoff, negative_cutoff, population_cutoff,
+                          **cvxopt_options):  # fmt: skip
+    """``solver_cvxopt`` (built-in engine, non-negative coefficients) for many atoms at once.
+
+    ``problems`` is a list of ``(bs_funcs, rho, propars, points, weights)`` tuples, one per atom, as
+    the per-atom plug-in receives them.  Atoms with equal shapes (same element on the same radial
+    grid) are stacked and advanced together by ``algo.cp.cp_simplex_batched``; the result of every
+    atom equals the per-atom call up to the rounding of the stacked LAPACK solves.  Returns the list
+    of new coefficient vectors (None where the programme did not converge, as ``solver_cvxopt``)."""
+    from .algo.cp import cp_simplex_batched
+
+    options = dict(cvxopt_options) or {"feastol": threshold}
+    groups = {}
+    for i, (bs, rho, *_rest) in enumerate(problems):
+        groups.setdefault((np.shape(bs), np.shape(rho)), []).append(i)
+    out = [None] * len(problems)
+    for members in groups.values():
+        bs = np.stack([np.asarray(problems[i][0], dtype=float) for i in members])
+        rho = np.stack([np.asarray(problems[i][1], dtype=float) for i in members])
+        x0 = np.stack([np.asarray(problems[i][2], dtype=float) for i in members])
+        w = np.stack([np.asarray(problems[i][4], dtype=float) for i in members])
+        x, optimal, _ = cp_simplex_batched(bs, rho, w, x0, density_cutoff, options)
+        for j, i in enumerate(members):
+            if not optimal[j]:
+                logger.error("CVXOPT not converged!")
+                continue
+            check_pro_atom_parameters_non_neg_pars(
+                x[j], basis_functions=bs[j], logger=logger, total_population=float(np.einsum("i,i", w[j], rho[j])),
+                negative_cutoff=negative_cutoff, population_cutoff=population_cutoff)  # fmt: skip
+            out[i] = x[j]
+    return out
 
 
 def solver_sc_plus_cvxopt(bs_funcs, rho, propars, points, weights, threshold, logger, density_cutoff,

@@ -174,6 +174,46 @@ def test_convex_programme_solver_matches_reference_through_shim(key):
     np.testing.assert_allclose(got, ref, atol=1e-9 if func_type == "gauss" else 1e-7)
 
 
+def test_batched_convex_programme_equals_the_per_atom_solver():
+    """solver_cvxopt_batched (atoms of equal shape stacked, mixed shapes grouped) against per-atom
+    solver_cvxopt calls and against the reference-through-shim vectors."""
+    log = logging.getLogger("test_algo_host")
+    for func_type in ("gauss", "slater"):
+        helper = ExpBasisFuncHelper.from_function_type(func_type)
+        problems, keys = [], []
+        for number, pops in ((8, (8.5, 8.1, 8.9)), (1, (0.7, 0.55)), (6, (6.1,)), (8, (7.6,))):
+            for pop in pops:
+                bs, rho, c0, r, w = synthetic.radial_problem(helper, number, pop)
+                problems.append((bs, rho, c0, r, w))
+                keys.append((number, pop))
+        got = lisa_solvers.solver_cvxopt_batched(problems, 1e-8, log, 1e-15, -1e-12, 1e-4)
+        assert len(got) == len(problems)
+        for (number, pop), prob, x in zip(keys, problems, got):
+            bs, rho, c0, r, w = prob
+            one = lisa_solvers.solver_cvxopt(bs, rho, c0.copy(), r, w, 1e-8, log, 1e-15, -1e-12, 1e-4, engine="builtin")
+            assert abs(x.sum() - np.einsum("i,i", w, rho)) < 1e-12 and (x >= 0).all()
+            pro_a, pro_b = x @ bs, one @ bs
+            assert np.sqrt(np.einsum("i,i,i", w, pro_a - pro_b, pro_a - pro_b)) < 1e-10
+            np.testing.assert_allclose(x, one, atol=1e-12 if func_type == "gauss" else 1e-6)
+            key = f"{func_type}/{number}/nonneg"
+            if (number, pop) in ((8, 8.5), (1, 0.7), (6, 6.1)):
+                np.testing.assert_allclose(x, CONVEX[key], atol=1e-9 if func_type == "gauss" else 1e-6)
+
+
+def test_batched_convex_programme_reports_non_convergence():
+    helper = ExpBasisFuncHelper.from_function_type("gauss")
+    bs, rho, c0, r, w = synthetic.radial_problem(helper, 8, 8.5)
+    log = logging.getLogger("test_algo_host")
+    log.disabled = True
+    try:
+        got = lisa_solvers.solver_cvxopt_batched([(bs, rho, c0, r, w)] * 2, 1e-8, log, 1e-15, -1e-12, 1e-4, maxiters=2)
+    finally:
+        log.disabled = False
+    assert got == [None, None]
+    with pytest.raises(ValueError, match="not finite"):
+        lisa_solvers.solver_cvxopt_batched([(bs, rho * np.nan, c0, r, w)], 1e-8, log, 1e-15, -1e-12, 1e-4)
+
+
 def test_sc_plus_convex_falls_back_to_the_programme():
     """With too few self-consistent iterations allowed, "sc-plus-convex" hands over to the convex
     programme (alisa.py:356-457; the reference's own hand-over call omits `population_cutoff` and
