@@ -83,6 +83,11 @@ def config3():
         ev = np.sum(part.history_time_update_at_weights)
         print(json.dumps({"run": f"config3 {basis} kernel", "evals_per_s_in_weights_kernel":
                           out["niter"] * 100 * grid.size / ev, "weights_kernel_s": ev}), flush=True)
+    # the reference's DEFAULT aLISA solver (the convex programme): host plug-in on the projected
+    # radial problems, all atoms stacked per outer iteration (lisa_solvers.solver_cvxopt_batched)
+    part = LinearISAWPart(coords, numbers, pseudo, grid, rho, device=DEV)
+    timed("config3 aLISA default solver (convex programme, batched host plug-in) gauss 100 atoms", part,
+          {"seconds_in_host_solver": float(np.sum(part.history_time_update_propars))})
 
 
 def config4():
