@@ -306,6 +306,9 @@ CONVEX_CASES = {
     # ("sc-plus-convex" cannot be generated: its fall-back call omits `population_cutoff`,
     # alisa.py:446-457, and raises TypeError in the reference itself)
     "g/lisa_cvxopt_gt2": ("lisa", "g", dict(grid_type=2)),
+    # GISA's quadratic programme on the molecular grid (gisa.py:257-279; QP answered by the qpsolvers stand-in)
+    "g/gisa_gt2": ("gisa", "g", dict(grid_type=2)),
+    "s/lisa_diis_gt2": ("lisa", "s", dict(solver="diis", grid_type=2, maxiter=8, solver_options=dict(check_mono=False))),
     "g/glisa_cvxopt": ("glisa", "g", dict()),
     "s/glisa_cvxopt": ("glisa", "s", dict()),
 }

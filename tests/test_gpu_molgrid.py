@@ -118,3 +118,31 @@ def test_alisa_callable_solver_grid_type_3(water6g):
     assert seen[0][1:] == ((npts,), (npts, 3), (npts,)) and seen[0][0][1] == npts
     np.testing.assert_allclose(host["charges"], dev["charges"], rtol=1e-9, atol=1e-10)
     np.testing.assert_allclose(host["history_changes"], dev["history_changes"], rtol=1e-6)
+
+
+@pytest.mark.parametrize("tag,scheme,case_name,kw,rtol", [
+    ("g/gisa_gt2", "GaussianISAWPart", "water6g", dict(), 1e-8),
+    ("s/lisa_diis_gt2", "LinearISAWPart", "water6", dict(solver="diis", maxiter=8, solver_options=dict(check_mono=False)), 2e-6),
+])  # fmt: skip
+def test_host_plugins_on_the_molecular_grid(request, tag, scheme, case_name, kw, rtol):
+    """GISA's quadratic programme and an aLISA host plug-in (DIIS) with grid_type 2 against reference
+    runs (tests/golden/water6_convex.npz); DIIS tolerance as in tests/test_gpu_solvers.py."""
+    import contextlib
+    import io
+    import warnings
+
+    from conftest import GOLDEN
+
+    import horton_part_b200 as hp
+
+    gold = np.load(GOLDEN / "water6_convex.npz")
+    ref = {k[len(tag) + 1 :]: gold[k] for k in gold.files if k.startswith(tag + "/")}
+    c = request.getfixturevalue(case_name)
+    with contextlib.redirect_stdout(io.StringIO()), warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        part = getattr(hp, scheme)(c["coords"], c["numbers"], c["pseudo"], c["grid"], c["rho"], grid_type=2, **kw)
+        part.do_partitioning()
+    assert part["niter"] == int(ref["niter"])
+    np.testing.assert_allclose(part["charges"], ref["charges"], rtol=rtol, atol=1e-9)
+    np.testing.assert_allclose(part["history_changes"], ref["history_changes"], rtol=max(1e-5, 5e3 * rtol), atol=1e-11)
+    np.testing.assert_allclose(part["promoldens"][::97], ref["promoldens_sample"], rtol=max(1e-8, rtol))

@@ -1,27 +1,63 @@
-"""Host half of the grid_type 2/3 plug-in path (gisa.molgrid_host_update) against a reference run:
+"""Host half of the grid_type 2/3 plug-in path (gisa.molgrid_host_update) against reference runs:
 the promolecule, which the product gets from the device pass, is built here with NumPy so that the
-per-atom K_a x Npts algebra and the convex-programme plug-in are checked on CPU.  Golden:
-tests/golden/water6_convex.npz (reference LinearISAWPart(grid_type=2), default solver, its
-cvxopt.solvers.cp call answered by the oracle's stand-in)."""
+per-atom K_a x Npts algebra and the host solvers are checked on CPU.  Goldens:
+tests/golden/water6_convex.npz (reference runs with grid_type=2: aLISA with the default convex
+programme, aLISA with DIIS, GISA with its quadratic programme; third-party solver calls answered
+by the oracle's stand-ins)."""
 
+import contextlib
+import io
 import logging
+import warnings
 
 import numpy as np
+import pytest
 from conftest import GOLDEN
 
 from horton_part_b200 import gridlite, lisa_solvers, synthetic
 from horton_part_b200.core.basis import ExpBasisFuncHelper
-from horton_part_b200.gisa import molgrid_host_update
+from horton_part_b200.gisa import molgrid_host_update, opt_propars_qp_interface
+
+LOG = logging.getLogger("test_molgrid_host")
 
 
-def test_molgrid_host_update_reproduces_reference_run():
+def _convex(helper, z):
+    return lambda bs, rho_a, start, grid: lisa_solvers.solver_cvxopt(
+        bs, rho_a, start, grid.points, grid.weights, 1e-8, LOG, 1e-15, -1e-12, 1e-4, engine="builtin")
+
+
+def _diis(helper, z):
+    return lambda bs, rho_a, start, grid: lisa_solvers.solver_diis(
+        bs, rho_a, start, grid.points, grid.weights, 1e-8, LOG, 1e-15, -1e-12, 1e-4, check_mono=False)
+
+
+def _qp(helper, z):
+    alphas = helper.get_exponent(z)
+    return lambda bs, rho_a, start, grid: opt_propars_qp_interface(bs, rho_a, start, grid.weights, alphas, "quadprog")
+
+
+CASES = {
+    "g/lisa_cvxopt_gt2": ("g", _convex, 500, 1e-8),
+    # DIIS stops each per-atom solve at ||g(c) - c|| < 1e-8 and restarts from the newest vector when its
+    # bordered system is singular: its answer per outer iteration is only defined to about the inner
+    # threshold, and eight outer iterations amplify that to ~1e-6 on the charges (tests/test_gpu_solvers.py)
+    "s/lisa_diis_gt2": ("s", _diis, 8, 2e-6),
+    "g/gisa_gt2": ("g", _qp, 500, 1e-8),
+}
+
+
+@pytest.mark.parametrize("tag", list(CASES))
+def test_molgrid_host_update_reproduces_reference_run(tag):
     gold = np.load(GOLDEN / "water6_convex.npz")
-    tag = "g/lisa_cvxopt_gt2"
+    dens, make_solver, maxiter, rtol = CASES[tag]
     coords, numbers = synthetic.water_cluster(6, 0)
     rgrid = gridlite.BeckeRTransform(1e-4, 1.5).transform_1d_grid(gridlite.GaussChebyshev(40))
     grid = gridlite.MolGrid.from_size(numbers, coords, 50, rgrid, gridlite.BeckeWeights(), store=True)
     helper = ExpBasisFuncHelper.from_function_type("gauss")
-    rho = synthetic.expbasis_promolecule_host(grid.points, coords, numbers, helper, scale={8: 8.6, 1: 0.7})
+    if dens == "g":
+        rho = synthetic.expbasis_promolecule_host(grid.points, coords, numbers, helper, scale={8: 8.6, 1: 0.7})
+    else:
+        rho = synthetic.slater_promolecule_host(grid.points, coords, numbers)
     pseudo = numbers.astype(float)
     ranges = np.concatenate([[0], np.cumsum([helper.get_nshell(z) for z in numbers])])
     propars = np.ones(ranges[-1])
@@ -33,24 +69,25 @@ def test_molgrid_host_update_reproduces_reference_run():
     for a, z in enumerate(numbers):
         r = np.linalg.norm(grid.points - coords[a], axis=1)
         bs.append(np.array([helper.compute_proshell_dens(z, k, 1.0, r) for k in range(helper.get_nshell(z))]))
-    log = logging.getLogger("test_molgrid_host")
+    solvers = [make_solver(helper, z) for z in numbers]
 
     def opt(a, bs_a, rho_a, start):
-        return lisa_solvers.solver_cvxopt(bs_a, rho_a, start, grid.points, grid.weights, 1e-8, log, 1e-15, -1e-12,
-                                          1e-4, engine="builtin")  # fmt: skip
+        return solvers[a](bs_a, rho_a, start, grid)
 
     changes = []
-    for niter in range(1, 200):
-        promol = np.zeros(grid.size)
-        for a in range(len(numbers)):  # core/stockholder.py:153-175
-            promol += propars[ranges[a] : ranges[a + 1]] @ bs[a]
-            promol += 1e-100
-        propars, charges, msd = molgrid_host_update(promol, rho, grid.points, grid.weights, bs, ranges, propars,
-                                                    pseudo, opt)  # fmt: skip
-        changes.append(np.sqrt(msd.sum()))
-        if changes[-1] < 1e-6:
-            break
+    with contextlib.redirect_stdout(io.StringIO()), warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        for niter in range(1, maxiter + 1):
+            promol = np.zeros(grid.size)
+            for a in range(len(numbers)):  # core/stockholder.py:153-175
+                promol += propars[ranges[a] : ranges[a + 1]] @ bs[a]
+                promol += 1e-100
+            propars, charges, msd = molgrid_host_update(promol, rho, grid.points, grid.weights, bs, ranges, propars,
+                                                        pseudo, opt)  # fmt: skip
+            changes.append(np.sqrt(msd.sum()))
+            if changes[-1] < 1e-6:
+                break
     assert niter == int(gold[f"{tag}/niter"])
-    np.testing.assert_allclose(charges, gold[f"{tag}/charges"], rtol=1e-8, atol=1e-10)
-    np.testing.assert_allclose(propars, gold[f"{tag}/propars"], rtol=1e-7, atol=1e-9)
-    np.testing.assert_allclose(changes, gold[f"{tag}/history_changes"], rtol=1e-6, atol=1e-12)
+    np.testing.assert_allclose(charges, gold[f"{tag}/charges"], rtol=rtol, atol=1e-9)
+    np.testing.assert_allclose(propars, gold[f"{tag}/propars"], rtol=10 * rtol, atol=1e-8)
+    np.testing.assert_allclose(changes, gold[f"{tag}/history_changes"], rtol=max(1e-5, 5e3 * rtol), atol=1e-11)
