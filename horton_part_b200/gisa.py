@@ -339,32 +339,32 @@ class GaussianISAWPart(AbstractISAWPart):
         charges = np.zeros(self.natom)
         msd = np.zeros(self.natom)
         batched = self._batched_host_solver()
-        solved = None
-        if batched is not None:  # all local atoms in stacked NumPy calls instead of one by one
-            problems = []
-            for i, a in enumerate(range(sh.atom_lo, sh.atom_hi)):
-                rgrid = self.get_rgrid(a)
-                problems.append((self.cache.load(f"bs_funcs_{a}"), sph[ro[i] : ro[i + 1]],
-                                 propars[self._ranges[a] : self._ranges[a + 1]].copy(), rgrid.points,
-                                 4 * np.pi * rgrid.points**2 * rgrid.weights))  # fmt: skip
-            solved = batched(problems)
+        exp_basis = isinstance(self.bs_helper, ExpBasisFuncHelper)
+        atoms = []  # (atom, bs_funcs, spherical average, radial points, 4 pi r^2 w) of the local atoms
+        shell_weights = {}  # 4 pi r^2 w per distinct radial grid
         for i, a in enumerate(range(sh.atom_lo, sh.atom_hi)):
             rgrid = self.get_rgrid(a)
-            points = rgrid.points
-            rho_sph = sph[ro[i] : ro[i + 1]]
-            r_weights = 4 * np.pi * points**2 * rgrid.weights
-            alphas = self.bs_helper.get_exponent(self.numbers[a]) if isinstance(self.bs_helper, ExpBasisFuncHelper) else None
+            if id(rgrid) not in shell_weights:
+                shell_weights[id(rgrid)] = 4 * np.pi * rgrid.points**2 * rgrid.weights
+            atoms.append((a, self.cache.load(f"bs_funcs_{a}"), sph[ro[i] : ro[i + 1]], rgrid.points,
+                          shell_weights[id(rgrid)]))  # fmt: skip
+        solved = None
+        if batched is not None:  # all local atoms in stacked NumPy calls instead of one by one
+            solved = batched([(bs, rho_sph, propars[self._ranges[a] : self._ranges[a + 1]].copy(), points, r_weights)
+                              for a, bs, rho_sph, points, r_weights in atoms])  # fmt: skip
+        for i, (a, bs, rho_sph, points, r_weights) in enumerate(atoms):
             lo, hi = self._ranges[a], self._ranges[a + 1]
             if solved is not None:
                 propars[lo:hi] = solved[i]
             else:
-                propars[lo:hi] = self._opt_propars(
-                    self.cache.load(f"bs_funcs_{a}"), rho_sph, propars[lo:hi].copy(), points, r_weights,
-                    alphas, self._inner_threshold,
-                )  # fmt: skip
+                alphas = self.bs_helper.get_exponent(self.numbers[a]) if exp_basis else None
+                propars[lo:hi] = self._opt_propars(bs, rho_sph, propars[lo:hi].copy(), points, r_weights, alphas,
+                                                   self._inner_threshold)  # fmt: skip
             charges[a] = self.pseudo_numbers[a] - np.einsum("i,i", r_weights, rho_sph)
-            delta = self.get_proatom_rho(a, propars)[0] - self.get_proatom_rho(a, old)[0]
-            msd[a] = rgrid.integrate(4 * np.pi * points**2, delta, delta)
+            # the atom's term of compute_change (core/iterstock.py:32-45) from the tabulated unit shells,
+            # like the device solvers: rho0_a[new] - rho0_a[old] = sum_k (new - old)_k g_k
+            delta = np.einsum("k,kp->p", propars[lo:hi], bs) - np.einsum("k,kp->p", old[lo:hi], bs)
+            msd[a] = np.einsum("i,i,i", r_weights, delta, delta)
         dev = slab.device
         st.propars[self._ranges[sh.atom_lo] : self._ranges[sh.atom_hi]] = torch.from_numpy(
             propars[self._ranges[sh.atom_lo] : self._ranges[sh.atom_hi]]
