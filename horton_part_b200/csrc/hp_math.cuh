@@ -94,6 +94,50 @@ __device__ __forceinline__ double exp_neg_poly_regs(double x, const ExpConsts& c
     return __hiloint2double(__double2hiint(p) + (k << 20), __double2loint(p));
 }
 
+// ---- base-2 variant (HP_LOC_EXP2, tools/exp2_coeffs.py) -----------------------------------------
+// exp(-alpha r) = 2^y with y = -(alpha log2 e) r: the reduction y = k + s is exact without
+// Cody-Waite constants, 2^s = 1 + s (ln2 + s G(s)) with G_i = g_i ln2^(i+2).  15 FP64 operations
+// instead of 16; <= 0.87 ulp for an exact argument, and the argument carries a second rounding
+// (beta = fl(alpha log2 e)).  Off by default: kept for A/B runs on the GPU.
+#define HP_EXP2_TABLE                                                                                  \
+    {0.24022650695910078, 0.05550410866482158, 0.009618129107618658, 0.0013333558146423209,            \
+     0.0001540353042479538, 1.5252733820805852e-05, 1.3215451619146607e-06, 1.0178067259946989e-07,   \
+     7.0709810833657675e-09, 4.454105125293416e-10, 0.6931471805599453, 1.4426950408889634}
+__device__ double d_exp2_regs[12] = HP_EXP2_TABLE;
+
+struct Exp2Consts {
+    double g[10], ln2, log2e;
+    __device__ __forceinline__ void load() {
+        double v[12];
+        const unsigned long long base = static_cast<unsigned long long>(__cvta_generic_to_global(d_exp2_regs));
+#pragma unroll
+        for (int i = 0; i < 12; ++i) asm volatile("ld.global.f64 %0, [%1];" : "=d"(v[i]) : "l"(base + 8ull * i));
+#pragma unroll
+        for (int i = 0; i < 10; ++i) g[i] = v[i];
+        ln2 = v[10];
+        log2e = v[11];
+    }
+};
+
+// 2^y for -1021 < y <= 0, constants from registers.
+__device__ __forceinline__ double exp2_neg_poly_regs(double y, const Exp2Consts& c) {
+    const double t = y + 6755399441055744.0;
+    const int k = __double2loint(t);
+    const double kd = t - 6755399441055744.0;
+    const double s = y - kd;  // exact
+    double g = fma(c.g[9], s, c.g[8]);
+#pragma unroll
+    for (int i = 7; i >= 0; --i) g = fma(g, s, c.g[i]);
+    double p = fma(g, s, c.ln2);
+    p = fma(p, s, 1.0);
+    return __hiloint2double(__double2hiint(p) + (k << 20), __double2loint(p));
+}
+
+// y <= -1021 (or a negative NaN): 2^y at or below 4.5e-308 is flushed to exactly 0 (see exp_arg_tiny).
+__device__ __forceinline__ bool exp2_arg_tiny(double y) {
+    return static_cast<unsigned>(__double2hiint(y)) >= 0xC08FE800u;
+}
+
 // x <= -708 (or a negative NaN): results at or below 3.4e-308 are flushed to exactly 0.  Such
 // terms are absorbed by the reference's own +1e-100 offsets, so promolecule sums are unchanged;
 // the absolute error of a single pro-atom value is < 3.4e-308.

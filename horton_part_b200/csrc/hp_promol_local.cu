@@ -85,13 +85,31 @@ __device__ __forceinline__ void lds_z_pack(unsigned addr, double& z, int& s0, in
     asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(s0), "=r"(ns) : "r"(addr + 8));
 }
 
+#ifndef HP_LOC_EXP2
+#define HP_LOC_EXP2 0  // 1: base-2 exponential in the candidate loop (hp_math.cuh), for A/B runs
+#endif
+
+#if HP_LOC_EXP2
+using LocExpConsts = Exp2Consts;
+// the loop's exponent argument is y = -(alpha log2 e) * r
+__device__ __forceinline__ double loc_neg_exponent(double alpha, const LocExpConsts& c) { return -alpha * c.log2e; }
+template <bool GUARD>
+__device__ __forceinline__ double exp_regs(double y, const LocExpConsts& c) {
+    const double e = exp2_neg_poly_regs(y, c);
+    if (!GUARD) return e;
+    return exp2_arg_tiny(y) ? 0.0 : e;
+}
+#else
+using LocExpConsts = ExpConsts;
+__device__ __forceinline__ double loc_neg_exponent(double alpha, const LocExpConsts&) { return -alpha; }
 // exp(x) for x <= 0 with the constants in registers; GUARD adds the underflow flush of exp_neg_poly.
 template <bool GUARD>
-__device__ __forceinline__ double exp_regs(double x, const ExpConsts& c) {
+__device__ __forceinline__ double exp_regs(double x, const LocExpConsts& c) {
     const double e = exp_neg_poly_regs(x, c);
     if (!GUARD) return e;
     return exp_arg_tiny(x) ? 0.0 : e;
 }
+#endif
 
 template <int F, bool LOCAL>
 __global__ void __launch_bounds__(kLocThreads, kLocBlocksPerSM)
@@ -126,7 +144,7 @@ promol_weights_local_kernel(int64_t npts, const double* __restrict__ px, const d
     const unsigned atoms_addr = static_cast<unsigned>(__cvta_generic_to_shared(s_atoms));
     const unsigned ab_addr = static_cast<unsigned>(__cvta_generic_to_shared(s_AB));
     unsigned long long pairs = 0, shells = 0;
-    ExpConsts ec;
+    LocExpConsts ec;
     ec.load();
     // shell_skip[nshell_total] is the "negative amplitude seen" flag written by hp_shell_screen
     const bool may_screen_atoms = atom_eps > 0.0 && F != HP_FUNCTOR_GENERAL && shell_skip &&
@@ -365,7 +383,7 @@ promol_weights_local_kernel(int64_t npts, const double* __restrict__ px, const d
                     double r[kLocPts];
 #pragma unroll
                     for (int j = 0; j < kLocPts; ++j) r[j] = (F == HP_FUNCTOR_GAUSS) ? d2[j] : sqrt_fast(d2[j]);
-                    const double na = -al0;
+                    const double na = loc_neg_exponent(al0, ec);
 #pragma unroll
                     for (int j = 0; j < kLocPts; ++j) pro[j] = fma(A0, exp_regs<false>(na * r[j], ec), pro[j]);
                     lds_z_pack(next + 16, az, s0, ns);
@@ -373,7 +391,7 @@ promol_weights_local_kernel(int64_t npts, const double* __restrict__ px, const d
                     for (int k = 1; k < cns; ++k) {
                         double A, al;
                         lds_f64x2(ab_addr + unsigned(cs0 + k) * 16u, A, al);
-                        al = -al;
+                        al = loc_neg_exponent(al, ec);
 #pragma unroll
                         for (int j = 0; j < kLocPts; ++j) pro[j] = fma(A, exp_regs<false>(al * r[j], ec), pro[j]);
                     }
@@ -386,7 +404,7 @@ promol_weights_local_kernel(int64_t npts, const double* __restrict__ px, const d
                     double r[kLocPts];
 #pragma unroll
                     for (int j = 0; j < kLocPts; ++j) r[j] = (F == HP_FUNCTOR_GAUSS) ? d2[j] : sqrt_fast(d2[j]);
-                    const double na = -al0;
+                    const double na = loc_neg_exponent(al0, ec);
 #pragma unroll
                     for (int j = 0; j < kLocPts; ++j) f[j] = A0 * exp_regs<false>(na * r[j], ec);
                     lds_z_pack(next + 16, az, s0, ns);
@@ -394,7 +412,7 @@ promol_weights_local_kernel(int64_t npts, const double* __restrict__ px, const d
                     for (int k = 1; k < cns; ++k) {
                         double A, al;
                         lds_f64x2(ab_addr + unsigned(cs0 + k) * 16u, A, al);
-                        al = -al;
+                        al = loc_neg_exponent(al, ec);
 #pragma unroll
                         for (int j = 0; j < kLocPts; ++j) f[j] = fma(A, exp_regs<false>(al * r[j], ec), f[j]);
                     }
@@ -402,7 +420,7 @@ promol_weights_local_kernel(int64_t npts, const double* __restrict__ px, const d
                     double r[kLocPts];
 #pragma unroll
                     for (int j = 0; j < kLocPts; ++j) r[j] = (F == HP_FUNCTOR_GAUSS) ? d2[j] : sqrt_nocall(d2[j]);
-                    const double na = -al0;
+                    const double na = loc_neg_exponent(al0, ec);
 #pragma unroll
                     for (int j = 0; j < kLocPts; ++j) f[j] = A0 * exp_regs<true>(na * r[j], ec);
                     lds_z_pack(next + 16, az, s0, ns);
@@ -410,7 +428,7 @@ promol_weights_local_kernel(int64_t npts, const double* __restrict__ px, const d
                     for (int k = 1; k < cns; ++k) {
                         double A, al;
                         lds_f64x2(ab_addr + unsigned(cs0 + k) * 16u, A, al);
-                        al = -al;
+                        al = loc_neg_exponent(al, ec);
 #pragma unroll
                         for (int j = 0; j < kLocPts; ++j) f[j] = fma(A, exp_regs<true>(al * r[j], ec), f[j]);
                     }
