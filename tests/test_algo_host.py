@@ -330,3 +330,54 @@ def test_active_set_qp_against_brute_force_enumeration():
         np.testing.assert_allclose(x, ref, atol=1e-6 * max(1.0, total))
         cost = lambda y: 0.5 * y @ P @ y + q @ y  # noqa: E731
         assert cost(x) <= cost(ref) + 1e-9 * max(1.0, abs(cost(ref)))
+
+
+def test_interior_point_against_scipy_on_random_entropy_programmes():
+    """algo/cp.py on random programmes of the aLISA form  min -sum_i a_i ln((B x)_i)  s.t.  x >= 0,
+    sum x = N  (B > 0, a > 0; some columns dominated so that bounds become active) against SciPy's
+    SLSQP started from several points: an independent method on the same unique minimiser."""
+    from scipy.optimize import minimize
+
+    from horton_part_b200.algo import cp
+
+    rng = np.random.default_rng(17)
+    for trial in range(12):
+        n, m = int(rng.integers(3, 9)), int(rng.integers(20, 60))
+        B = rng.uniform(0.05, 1.0, size=(m, n)) * np.exp(-rng.uniform(0, 3, size=(m, 1)) * np.arange(n)[None, :])
+        if trial % 3 == 0:
+            B[:, -1] = 0.5 * B[:, 0]  # a dominated column: its coefficient must end on the bound
+        a = rng.uniform(0.1, 2.0, size=m)
+        total = float(rng.uniform(0.5, 8.0))
+
+        def F(x=None, z=None):
+            if x is None:
+                return 0, np.full(n, total / n)
+            p = B @ x
+            if (p <= 0).any():
+                return np.inf, np.full(n, np.nan)
+            f = -(a * np.log(p)).sum()
+            g = -B.T @ (a / p)
+            return (f, g) if z is None else (f, g, z[0] * (B.T * (a / p**2)) @ B)
+
+        sol = cp(F, G=-np.identity(n), h=np.zeros(n), A=np.ones((1, n)), b=[total])
+        assert sol["status"] == "optimal"
+        x = sol["x"]
+        assert abs(x.sum() - total) < 1e-10 and (x > -1e-14).all()
+        best = None
+        for start in (np.full(n, total / n), total * rng.dirichlet(np.ones(n))):
+            res = minimize(lambda v: F(np.maximum(v, 1e-300))[0], start, jac=lambda v: F(np.maximum(v, 1e-300))[1],
+                           method="SLSQP", bounds=[(0, None)] * n, constraints={"type": "eq", "fun": lambda v: v.sum() - total,
+                                                                               "jac": lambda v: np.ones(n)},
+                           options={"ftol": 1e-15, "maxiter": 500})  # fmt: skip
+            if best is None or res.fun < best.fun:
+                best = res
+        assert F(x)[0] <= best.fun + 1e-9 * max(1.0, abs(best.fun))  # at least as good as SLSQP's point
+        np.testing.assert_allclose(B @ x, B @ best.x, rtol=2e-4)  # and the same fitted function
+        # KKT at the interior-point answer: gradient + multiplier is zero on the support, >= 0 off it
+        g = F(x)[1]
+        mult = g + sol["y"][0]
+        support = x > 1e-8 * total
+        assert np.abs(mult[support]).max() < 1e-6 * max(1.0, np.abs(g).max())
+        assert (mult[~support] > -1e-6 * max(1.0, np.abs(g).max())).all()
+        if trial % 3 == 0:
+            assert x[-1] < 1e-8 * total
