@@ -72,7 +72,7 @@ def wpart_schemes(scheme: str):
     try:
         module, name = _SCHEMES[scheme]
     except KeyError:
-        raise NotImplementedError(f"scheme {scheme!r} is outside the accelerated hot path") from None
+        raise NotImplementedError(f"unknown scheme {scheme!r}: one of {sorted(_SCHEMES)}") from None
     try:
         return getattr(importlib.import_module(f"{__package__}.{module}"), name)
     except ModuleNotFoundError:
