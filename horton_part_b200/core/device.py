@@ -355,7 +355,7 @@ class ShellTable:
                 sub = np.arange(self._loc_nchunk) - np.repeat(coff[:-1], counts)
                 from_end = np.repeat(counts, counts) - 1 - sub
                 self._loc_chunk_order = to_device(np.argsort(from_end, kind="stable"), s.device, np.int64)
-                self._loc_scratch = torch.zeros(max(self._loc_nchunk, 1), dtype=torch.float64, device=s.device)
+                self._loc_scratch = torch.zeros(self._loc_nchunk + 1, dtype=torch.float64, device=s.device)
             atom_eps = 0.0
             if bits:
                 if self.skip is None:

@@ -30,7 +30,8 @@
 //   the reference is preserved.  Evaluated pairs are counted for the benchmark's "evals" metric.
 //
 // Scheduling: chunks cost between a few dozen and natom atom evaluations, so blocks take them from
-// a global work counter instead of a fixed stride (the slowest block of a static split was ~10 %
+// a per-launch work counter (the last slot of the caller's chunk_scratch, zeroed on the launch
+// stream: launches of different tables / streams never share it) instead of a fixed stride (the slowest block of a static split was ~10 %
 // behind the mean on config 5).  Reductions stay bit-reproducible: every chunk writes its entropy
 // term to its own slot, a second kernel folds the slots into the partial-sum buffer in a fixed
 // order, and the pair counters are integers.
@@ -70,8 +71,6 @@ struct __align__(16) LocAtom {
     int ns;  // kept shells
     double A0, alpha0;  // first kept shell (0, 0 if none)
 };
-
-__device__ unsigned long long g_loc_work_counter;
 
 __device__ __forceinline__ double dist2_unfused3(double dx, double dy, double dz) {
     return __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
@@ -124,6 +123,7 @@ promol_weights_local_kernel(int64_t npts, const double* __restrict__ px, const d
                             int atom_lo, int natom_local, const int64_t* __restrict__ chunk_off,
                             const int64_t* __restrict__ chunk_order, double* __restrict__ promol_out, double* __restrict__ w_out,
                             double* __restrict__ chunk_entropy,
+                            unsigned long long* __restrict__ work_counter,
                             unsigned long long* __restrict__ pair_counters) {
     __shared__ LocAtom s_atoms[kLocTileAtoms + 1];  // +1: sentinel for the prefetch
     __shared__ double2 s_AB[kLocTileShells];
@@ -153,7 +153,7 @@ promol_weights_local_kernel(int64_t npts, const double* __restrict__ px, const d
     for (;;) {
         __syncthreads();  // everybody is done with the previous chunk's shared state
         if (threadIdx.x == 0) {
-            const long long ticket = static_cast<long long>(atomicAdd(&g_loc_work_counter, 1ull));
+            const long long ticket = static_cast<long long>(atomicAdd(work_counter, 1ull));
             // expensive chunks (outer radial shells: nothing can be screened) are handed out first,
             // so that the last blocks finish on cheap ones
             const long long c = (ticket < nchunk && chunk_order) ? chunk_order[ticket] : ticket;
@@ -594,7 +594,7 @@ extern "C" int hp_promol_weights_local(int functor, int64_t npts, const double* 
     HP_REQUIRE(atom_eps >= 0.0 && atom_eps < 1e-9, "atom_eps must be in [0, 1e-9)");
     HP_REQUIRE(atom_lo >= 0 && natom_local >= 0 && atom_lo + natom_local <= natom, "bad local atom range");
     HP_REQUIRE(nchunk >= 0 && (nchunk == 0 || chunk_offsets), "chunk offsets missing");
-    HP_REQUIRE(!entropy_partials || nchunk == 0 || chunk_scratch, "entropy needs chunk_scratch (nchunk doubles)");
+    HP_REQUIRE(nchunk == 0 || chunk_scratch, "chunk_scratch (nchunk + 1 doubles) is required");
     cudaStream_t st = as_stream(stream);
     int rc = HP_OK;
     if (pair_partials) {
@@ -606,9 +606,8 @@ extern "C" int hp_promol_weights_local(int functor, int64_t npts, const double* 
             return check_cuda(cudaMemsetAsync(entropy_partials, 0, sizeof(double) * kMaxPartials, st), "memset");
         return HP_OK;
     }
-    void* counter = nullptr;
-    rc = check_cuda(cudaGetSymbolAddress(&counter, g_loc_work_counter), "cudaGetSymbolAddress");
-    if (rc) return rc;
+    // the launch's own work counter: slot [nchunk] of chunk_scratch
+    unsigned long long* counter = reinterpret_cast<unsigned long long*>(chunk_scratch + nchunk);
     rc = check_cuda(cudaMemsetAsync(counter, 0, sizeof(unsigned long long), st), "memset");
     if (rc) return rc;
     int64_t grid = int64_t(sm_count()) * kLocBlocksPerSM;
@@ -620,7 +619,7 @@ extern "C" int hp_promol_weights_local(int functor, int64_t npts, const double* 
         shell_alpha, shell_order, ntile, tile_atom_offsets, rho, molw, density_cutoff, promol_offset,    \
         radius, shell_skip, atom_eps, atom_lo, natom_local, chunk_offsets, chunk_order, promol,          \
         at_weights,                                                                                      \
-        chunk_entropy, reinterpret_cast<unsigned long long*>(pair_partials)
+        chunk_entropy, counter, reinterpret_cast<unsigned long long*>(pair_partials)
 #define HP_LOC(F)                                                                                        \
     if (local) promol_weights_local_kernel<F, true><<<int(grid), kLocThreads, 0, st>>>(HP_LOC_ARGS);     \
     else promol_weights_local_kernel<F, false><<<int(grid), kLocThreads, 0, st>>>(HP_LOC_ARGS)

@@ -1,4 +1,6 @@
 // Per-atom projection and radial pro-atom solves (rows a8, a9, a10 of SURVEY.md section 8a).
+#include <cstdlib>
+
 #include "hp_common.cuh"
 
 namespace hp {
@@ -520,6 +522,196 @@ lisa_sc_radial_kernel(int natom, int atom_base, const int* __restrict__ rad_off,
 }
 
 // ---------------------------------------------------------------------------------------------
+// aLISA self-consistent update, one BLOCK of kScWarps warps per atom (the inner fixed point runs
+// ~10^4 strictly sequential steps for the Slater basis, so the step LATENCY is what counts).
+//
+// Registers: warp v owns the shells k = v, v + kScWarps, ... (at most KPW of them) for ALL radial
+// points; lane l holds the points i = l + 32 j (j < NPL).  g[k][i] of the owned shells, the
+// coefficients c[k] and nothing else live in registers for the whole solve -- no global or
+// shared-memory traffic for the K x nrad table inside the loop.
+// One step = two barriers:
+//   1. every warp: partial pro-atom sum over its shells for all points        -> s_part[v][i]
+//   2. the thread that owns point i (i = tid, tid + 128): pro = sum_v s_part[v][i] (fixed order),
+//      ratio = rho / pro (masked, utils.py:238-245), w * ratio and the change term w (oldpro - pro)^2
+//                                                                            -> s_rw[i], s_chg[i]
+//   3. every warp: c_k <- c_k * sum_i g_k(i) (w ratio)(i) for its shells (alisa.py:268) and,
+//      redundantly, the change (alisa.py:273-274): all warps read the same numbers in the same order,
+//      so the stopping decision is uniform without another barrier.
+// Arithmetic differs from the one-warp kernel only in the association of the products
+// (c_k * sum g (w ratio) instead of sum w ((g c_k) ratio)) and in the order of the K-term sum.
+// ---------------------------------------------------------------------------------------------
+constexpr int kScWarps = 4;
+constexpr int kScThreads = kScWarps * 32;
+
+template <int KPW, int NPL>
+__global__ void __launch_bounds__(kScThreads)
+lisa_sc_block_kernel(int natom, int atom_base, const int* __restrict__ rad_off,
+                     const double* __restrict__ rad_w4, const double* __restrict__ sph,
+                     const int* __restrict__ par_off, double* __restrict__ propars,
+                     const int64_t* __restrict__ bs_off, const double* __restrict__ bs,
+                     const double* __restrict__ pseudo, double threshold, double density_cutoff,
+                     double population_cutoff, int max_inner, int single_update,
+                     double* __restrict__ charges, double* __restrict__ msd,
+                     int* __restrict__ niter_out, uint32_t* __restrict__ flags_out) {
+    constexpr int NRP = NPL * 32;            // padded radial size
+    constexpr int NOWN = (NRP + kScThreads - 1) / kScThreads;  // points owned per thread in step 2
+    __shared__ double s_part[kScWarps][NRP];
+    __shared__ double s_rw[NRP];
+    __shared__ double s_chg[NRP];
+    __shared__ double s_red[32];
+    __shared__ double s_c[KPW * kScWarps];
+    if (int(blockIdx.x) >= natom) return;
+    const int a = atom_base + blockIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int r0 = rad_off[blockIdx.x], nrad = rad_off[blockIdx.x + 1] - r0;
+    const int p0 = par_off[a], K = par_off[a + 1] - p0;
+    const double* w = rad_w4 + r0;
+    const double* rho = sph + r0;
+    const double* gsrc = bs + bs_off[blockIdx.x];  // g[k * nrad + i]
+
+    double g[KPW][NPL], c[KPW], c0[KPW];
+#pragma unroll
+    for (int kk = 0; kk < KPW; ++kk) {
+        const int k = warp + kk * kScWarps;
+        c[kk] = c0[kk] = (k < K) ? propars[p0 + k] : 0.0;
+#pragma unroll
+        for (int j = 0; j < NPL; ++j) {
+            const int i = lane + 32 * j;
+            g[kk][j] = (k < K && i < nrad) ? gsrc[int64_t(k) * nrad + i] : 0.0;
+        }
+    }
+    double wo[NOWN], ro[NOWN], oldpro[NOWN];
+    double pop = 0.0;
+#pragma unroll
+    for (int q = 0; q < NOWN; ++q) {
+        const int i = tid + q * kScThreads;
+        wo[q] = (i < nrad) ? w[i] : 0.0;
+        ro[q] = (i < nrad) ? rho[i] : 0.0;
+        oldpro[q] = 0.0;
+        pop += wo[q] * ro[q];
+    }
+    pop = block_sum(pop, s_red);  // thread 0 only
+    if (tid == 0) s_red[0] = pop;
+    __syncthreads();
+    pop = s_red[0];
+    __syncthreads();
+
+    uint32_t flags = single_update ? 0u : HP_SOLVE_NOT_CONVERGED;
+    int it = 0;
+    for (; it < max_inner; ++it) {
+        // 1. partial pro-atom sums of this warp's shells
+#pragma unroll
+        for (int j = 0; j < NPL; ++j) {
+            double p = 0.0;
+#pragma unroll
+            for (int kk = 0; kk < KPW; ++kk) p = fma(g[kk][j], c[kk], p);
+            s_part[warp][lane + 32 * j] = p;
+        }
+        __syncthreads();
+        // 2. point owners: pro-atom, masked ratio, change term
+#pragma unroll
+        for (int q = 0; q < NOWN; ++q) {
+            const int i = tid + q * kScThreads;
+            if (i < NRP) {
+                double pro = s_part[0][i];
+#pragma unroll
+                for (int v = 1; v < kScWarps; ++v) pro += s_part[v][i];
+                const bool sick = (ro[q] < density_cutoff) || (pro < density_cutoff);
+                const double ratio = sick ? 0.0 : ro[q] / pro;
+                const double e = oldpro[q] - pro;
+                s_rw[i] = wo[q] * ratio;
+                s_chg[i] = (it > 0) ? wo[q] * e * e : 0.0;
+                oldpro[q] = pro;
+            }
+        }
+        __syncthreads();
+        // 3. coefficient update of this warp's shells + the (redundant) change
+        double rw[NPL], chg = 0.0;
+#pragma unroll
+        for (int j = 0; j < NPL; ++j) {
+            rw[j] = s_rw[lane + 32 * j];
+            chg += s_chg[lane + 32 * j];
+        }
+        double sums[KPW];
+#pragma unroll
+        for (int kk = 0; kk < KPW; ++kk) {
+            double sk = 0.0;
+#pragma unroll
+            for (int j = 0; j < NPL; ++j) sk = fma(g[kk][j], rw[j], sk);
+            sums[kk] = sk;
+        }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+#pragma unroll
+            for (int kk = 0; kk < KPW; ++kk) sums[kk] += __shfl_xor_sync(0xffffffffu, sums[kk], off);
+            chg += __shfl_xor_sync(0xffffffffu, chg, off);
+        }
+#pragma unroll
+        for (int kk = 0; kk < KPW; ++kk) c[kk] *= sums[kk];
+        if (single_update) {
+            ++it;
+            break;
+        }
+        const double change = (it == 0) ? 1e100 : sqrt(chg);
+        if (change < threshold) {
+            flags &= ~HP_SOLVE_NOT_CONVERGED;
+            ++it;
+            break;
+        }
+    }
+
+    // this atom's term of compute_change (core/iterstock.py:36-44) and the population check
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < NPL; ++j) {
+        double pn = 0.0, po = 0.0;
+#pragma unroll
+        for (int kk = 0; kk < KPW; ++kk) {
+            pn = fma(g[kk][j], c[kk], pn);
+            po = fma(g[kk][j], c0[kk], po);
+        }
+        s_part[warp][lane + 32 * j] = pn - po;
+    }
+    if (lane == 0) {
+#pragma unroll
+        for (int kk = 0; kk < KPW; ++kk) {
+            const int k = warp + kk * kScWarps;
+            s_c[k] = c[kk];
+            if (k < K) propars[p0 + k] = c[kk];
+        }
+    }
+    __syncthreads();
+    double dev = 0.0;
+#pragma unroll
+    for (int q = 0; q < NOWN; ++q) {
+        const int i = tid + q * kScThreads;
+        if (i < NRP) {
+            double d = s_part[0][i];
+#pragma unroll
+            for (int v = 1; v < kScWarps; ++v) d += s_part[v][i];
+            dev += wo[q] * d * d;
+        }
+    }
+    dev = block_sum(dev, s_red);
+    if (tid == 0) {
+        double csum = 0.0;
+        bool finite = true;
+        for (int k = 0; k < K; ++k) {
+            csum += s_c[k];
+            finite = finite && isfinite(s_c[k]);
+        }
+        // check_pars_population, utils.py:434: only reached on convergence in the reference
+        if (!single_update && !(flags & HP_SOLVE_NOT_CONVERGED) && fabs(csum - pop) > population_cutoff)
+            flags |= HP_SOLVE_POP_MISMATCH;
+        if (!finite) flags |= HP_SOLVE_NONFINITE;
+        charges[a] = pseudo[a] - pop;  // gisa.py:315-318
+        msd[a] = dev;
+        niter_out[a] = it;
+        flags_out[a] = flags;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // Row a13: multipole moments of w_a*rho about R_a on atom a's own atomic grid (core/base.py:329-402
 // with qc-grid Grid.moments): Cartesian monomials in HORTON order, real regular solid harmonics
 // (Racah normalisation, order C_l0 C_l1 S_l1 C_l2 S_l2 ...), radial moments r^n.  One block per
@@ -798,6 +990,25 @@ extern "C" int hp_lisa_sc_radial_solve(int32_t natom, int32_t atom_base, const i
     HP_REQUIRE(rad_offsets && rad_w4 && sph_avg && par_offsets && propars && bs_offsets && bs_funcs &&
                    pseudo_numbers && charges && msd && niter && flags, "null input");
     HP_REQUIRE(nrad_max > 0 && nshell_max > 0, "bad shared-memory sizes");
+#define HP_SC_BLOCK(KPW, NPL)                                                                            \
+    lisa_sc_block_kernel<KPW, NPL><<<natom, kScThreads, 0, as_stream(stream)>>>(                         \
+        natom, atom_base, rad_offsets, rad_w4, sph_avg, par_offsets, propars, bs_offsets, bs_funcs,     \
+        pseudo_numbers, inner_threshold, density_cutoff, population_cutoff, max_inner, single_update,   \
+        charges, msd, niter, flags)
+    // block-per-atom kernel for the usual shapes (K <= 24 shells, <= 256 radial points)
+    // (HP_B200_SC_GENERIC=1 forces the one-warp-per-atom kernel: A/B runs and shape-fallback tests)
+    static const bool force_generic = [] { const char* e = getenv("HP_B200_SC_GENERIC"); return e && e[0] == '1'; }();
+    if (!force_generic && nshell_max <= 6 * kScWarps && nrad_max <= 256) {
+        const bool small_k = nshell_max <= 4 * kScWarps;
+        if (nrad_max <= 160) {
+            if (small_k) HP_SC_BLOCK(4, 5); else HP_SC_BLOCK(6, 5);
+        } else {
+            if (small_k) HP_SC_BLOCK(4, 8); else HP_SC_BLOCK(6, 8);
+        }
+        HP_LAUNCH_CHECK("lisa_sc_block_kernel");
+        return HP_OK;
+    }
+#undef HP_SC_BLOCK
     const size_t smem = sizeof(double) * (2 * size_t(nrad_max) + 2 * size_t(nshell_max));
     HP_REQUIRE(smem <= 200 * 1024, "radial grid / basis too large for shared memory");
     if (smem > 48 * 1024) {

@@ -142,11 +142,12 @@ HP_API int hp_shell_screen(int32_t natom, int32_t nshell, const int32_t* atom_sh
 /* Chunks: the local points of atom a (atom_point_offsets[a..a+1] - point_base) are cut into pieces of
  * hp_local_chunk_points() points; chunk_offsets[i] (natom_local + 1 entries, device) = number of chunks
  * of the local atoms before atom atom_lo + i, nchunk = chunk_offsets[natom_local].  Blocks take chunks
- * from a global work counter (not re-entrant across streams of one device) in the order given by
+ * from the launch's own work counter (slot [nchunk] of chunk_scratch) in the order given by
  * chunk_order (a permutation of 0..nchunk-1, may be NULL = ascending; the host puts the expensive
  * chunks, the outer radial shells, first so that the launch does not end on them); chunk_scratch (nchunk
- * doubles) receives the per-chunk entropy terms, which are folded into entropy_partials in a fixed
- * order.  pair_partials must hold 2 x hp_num_partials() uint64 ([0] = pairs, [hp_num_partials()] =
+ * + 1 doubles, required; one buffer per concurrently running launch) receives the per-chunk entropy
+ * terms, which are folded into entropy_partials in a fixed order, and its last slot is the work
+ * counter, zeroed on `stream` by the call.  pair_partials must hold 2 x hp_num_partials() uint64 ([0] = pairs, [hp_num_partials()] =
  * shell evaluations of the launch; the rest is zeroed).  Tiles must respect hp_local_tile_limits(). */
 HP_API void hp_local_tile_limits(int32_t* max_atoms_host, int32_t* max_shells_host);
 HP_API int32_t hp_local_chunk_points(void);

@@ -590,9 +590,148 @@ def case_molecules():
     print("wrote", GOLD / "ref_molecules.npz", f"{(GOLD / 'ref_molecules.npz').stat().st_size / 1024:.0f} KiB")
 
 
+def _pack_records(numbers, level=None):
+    """ProAtomDB records for `numbers` from the reference's cached isolated-atom files
+    (tests/common.py:64-111) + the packed raw arrays the GPU-side test rebuilds them from."""
+    from horton_part.core.proatomdb import ProAtomRecord
+
+    records, raw = [], {}
+    for z in numbers:
+        pat = f"atom_Z{z:02d}_N*_pow.npz" if level is None else f"atom_{level}_Z{z:02d}_N*_pow.npz"
+        for path in sorted(REF_CACHED.glob(pat)):
+            with np.load(path) as f:
+                number, charge, energy = int(f["number"]), int(f["charge"]), float(f["energy"])
+                rmin, rmax, npoint = f["rgrid"]
+                rgrid = qcgrid.PowerRTransform(rmin, rmax, int(npoint) - 1).transform_1d_grid(qcgrid.UniformInteger(int(npoint)))
+                records.append(ProAtomRecord(number, charge, energy, rgrid, f["dens"], f["deriv"]))
+                raw[f"Z{number}_q{charge}"] = np.concatenate([[number, charge, energy, rmin, rmax, npoint], f["dens"], f["deriv"]])
+    return records, raw
+
+
+def _full_out(part, grid, natom_samples=3):
+    out = {"charges": part["charges"], "promoldens_sample": part["promoldens"][::997].copy()}
+    for key in ("niter", "propars", "history_changes", "history_entropies"):
+        if key in part.cache:
+            out[key] = np.asarray(part[key])
+    if "history_charges" in part.cache:
+        out["history_charges_last"] = np.asarray(part["history_charges"])[-1]
+    for a in range(natom_samples):
+        w = part[f"at_weights_{a}"]
+        if w.shape == grid.weights.shape:
+            w = w[grid.indices[a] : grid.indices[a + 1]]
+        out[f"at_weights_{a}_sample"] = w[::53].copy()
+    return out
+
+
+def case_config2(natom=20, nrad=150, nang=194, seed=0):
+    """BASELINE.json config 2 at FULL size: 20-atom organic-like chain, 150 x 194 grid per atom
+    (582,000 points), exact Slater promolecule; ISA, Hirshfeld, Hirshfeld-I (database = the reference's
+    cached H/C/N/O records) and MBIS, all through the unmodified reference."""
+    import contextlib
+    import io
+
+    from horton_part.core.proatomdb import ProAtomDB
+
+    coords, numbers = synthetic.organic_like(natom, seed)
+    t0 = time.time()
+    grid = synthetic_grid(coords, numbers, nrad, nang)
+    print(f"  grid {grid.size} points, {time.time() - t0:.0f} s", flush=True)
+    rho = synthetic.slater_promolecule_host(grid.points, coords, numbers)
+    pseudo = numbers.astype(float)
+    records, raw = _pack_records((1, 6, 7, 8))
+    results = {}
+    for tag, scheme, kw in (("mbis", "mbis", {}), ("h", "h", dict(proatomdb=ProAtomDB(records))), ("isa", "is", {})):
+        t0 = time.time()
+        with contextlib.redirect_stdout(io.StringIO()):
+            part = wpart_schemes(scheme)(coords, numbers, pseudo, grid, rho, **kw)
+            part.do_charges()
+        results[tag] = _full_out(part, grid)
+        results[tag]["seconds"] = np.float64(time.time() - t0)
+        print(f"  config2 {tag}: niter={results[tag].get('niter')} q={np.round(part['charges'][:4], 6)} "
+              f"{time.time() - t0:.0f} s", flush=True)
+    # Hirshfeld-I needs the anion of every element that ends up negative; the reference's cached
+    # database has no N(-1) record (atom_Z07_N08 is absent: KeyError (7, -1) in core/proatomdb.py:282),
+    # so the HI run uses the same chain with N replaced by O (C6O4H10-like) and its own promolecule.
+    numbers_hi = np.where(numbers == 7, 8, numbers)
+    rho_hi = synthetic.slater_promolecule_host(grid.points, coords, numbers_hi)
+    grid_hi = synthetic_grid(coords, numbers_hi, nrad, nang)
+    t0 = time.time()
+    with contextlib.redirect_stdout(io.StringIO()):
+        part = wpart_schemes("hi")(coords, numbers_hi, numbers_hi.astype(float), grid_hi, rho_hi, proatomdb=ProAtomDB(records))
+        part.do_charges()
+    results["hi"] = _full_out(part, grid_hi)
+    results["hi"]["seconds"] = np.float64(time.time() - t0)
+    results["hi"]["numbers"] = numbers_hi
+    print(f"  config2 hi: niter={results['hi'].get('niter')} q={np.round(part['charges'][:4], 6)} {time.time() - t0:.0f} s", flush=True)
+    save("config2_organic20.npz", results, coordinates=coords, numbers=numbers, pseudo_numbers=pseudo,
+         dens_sample=rho[::997].copy(), aim_weights_sample=grid.aim_weights[::997].copy(),
+         nelec=np.float64(grid.integrate(rho)),
+         grid_spec=np.array(f"BeckeRTransform(1e-4,1.5) o GaussChebyshev({nrad}) x Lebedev{nang}, BeckeWeights(); "
+                            f"synthetic.organic_like({natom}, {seed})"),
+         **{f"record/{k}": v for k, v in raw.items()})  # fmt: skip
+
+
+def case_config3(natom=24, nrad=150, nang=194, seed=0, maxiter=500):
+    """BASELINE.json config 3 reduced in atoms only (24-atom water cluster on the REAL 150 x 194 grid,
+    698,400 points, Gaussian promolecule): aLISA `sc` with the gauss and the slater basis, run to
+    convergence (the 100-atom runs need hundreds of iterations of minutes each on the CPU)."""
+    from horton_part.core.basis import ExpBasisFuncHelper
+
+    coords, numbers = synthetic.water_cluster(natom, seed)
+    grid = synthetic_grid(coords, numbers, nrad, nang)
+    helper = ExpBasisFuncHelper.from_function_type("gauss")
+    rho = synthetic.expbasis_promolecule_host(grid.points, coords, numbers, helper, scale={8: 8.6, 1: 0.7})
+    pseudo = numbers.astype(float)
+    results = {}
+    for tag, kw in (("lisa_sc_gauss", dict(solver="sc", maxiter=maxiter)),
+                    ("lisa_sc_slater", dict(solver="sc", basis_func="slater", maxiter=maxiter))):
+        t0 = time.time()
+        results[tag] = run_reference_light("lisa", coords, numbers, pseudo, grid, rho, **kw)
+        results[tag]["seconds"] = np.float64(time.time() - t0)
+        print(f"  config3 {tag}: niter={results[tag].get('niter')} q={results[tag]['charges'][:3]} {time.time() - t0:.0f} s",
+              flush=True)
+    save(f"config3_water{natom}.npz", results, coordinates=coords, numbers=numbers,
+         dens_sample=rho[::997].copy(), aim_weights_sample=grid.aim_weights[::997].copy(),
+         grid_spec=np.array(f"BeckeRTransform(1e-4,1.5) o GaussChebyshev({nrad}) x Lebedev{nang}, BeckeWeights(); "
+                            f"synthetic.water_cluster({natom}, {seed}); maxiter={maxiter}"))  # fmt: skip
+
+
+#: electrons per element of the config-4 promolecule (not Z: the start, c = initials scaled to Z, is then off the solution)
+CONFIG4_SCALE = {1: 0.75, 6: 6.2, 7: 7.3, 8: 8.4}
+
+
+def case_config4(natom=12, nrad=150, nang=194, seed=0):
+    """BASELINE.json config 4 reduced in atoms only (12-atom peptide-like chain, REAL grid, Gaussian
+    promolecule of the gauss table's initials): gLISA `newton` (exact Hessian) and `sc`."""
+    from horton_part.core.basis import ExpBasisFuncHelper
+
+    coords, numbers = synthetic.peptide_like(natom, seed)
+    grid = synthetic_grid(coords, numbers, nrad, nang)
+    helper = ExpBasisFuncHelper.from_function_type("gauss")
+    rho = synthetic.expbasis_promolecule_host(grid.points, coords, numbers, helper, scale=CONFIG4_SCALE)
+    pseudo = numbers.astype(float)
+    results = {}
+    for tag, kw in (("glisa_newton", dict(solver="newton")), ("glisa_sc", dict(solver="sc", maxiter=60))):
+        t0 = time.time()
+        try:
+            results[tag] = run_reference_light("glisa", coords, numbers, pseudo, grid, rho, **kw)
+        except Exception as exc:
+            results[tag] = {"raised": np.array(f"{type(exc).__name__}: {exc}")}
+            print(f"  config4 {tag}: reference raised {type(exc).__name__}: {exc}", flush=True)
+            continue
+        results[tag]["seconds"] = np.float64(time.time() - t0)
+        print(f"  config4 {tag}: niter={results[tag].get('niter')} q={results[tag]['charges'][:3]} {time.time() - t0:.0f} s",
+              flush=True)
+    save(f"config4_peptide{natom}.npz", results, coordinates=coords, numbers=numbers,
+         dens_sample=rho[::997].copy(), aim_weights_sample=grid.aim_weights[::997].copy(),
+         grid_spec=np.array(f"BeckeRTransform(1e-4,1.5) o GaussChebyshev({nrad}) x Lebedev{nang}, BeckeWeights(); "
+                            f"synthetic.peptide_like({natom}, {seed})"))  # fmt: skip
+
+
 CASES = {"h2o": case_h2o, "water6": case_water_cluster, "water6g": case_water_gauss, "hirshfeld": case_hirshfeld,
          "solvers": case_water6_solvers, "convex": case_water6_convex, "convex_radial": case_convex_radial, "numeric": case_numeric, "proatomdb": case_proatomdb, "algo": case_algo, "postproc": case_postproc,
-         "molecules": case_molecules}
+         "molecules": case_molecules,
+         "config2": case_config2, "config3": case_config3, "config4": case_config4}
 
 if __name__ == "__main__":
     for name in sys.argv[1:] or CASES:
