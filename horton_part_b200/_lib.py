@@ -64,9 +64,12 @@ EXPORTS = {
         [_i32, _i32, _p, _p, _p, _p, _p, _p, _p, _p, _f64, _f64, _f64, _i32, _i32, _i32, _i32, _p, _p, _p, _p, _p],
     ),
     "hp_spline_build": (_int, [_i32, _p, _p, _p, _i32, _p, _p, _p]),
+    "hp_spline_lut_size": (_i32, [_i32, _p]),
+    "hp_spline_lut_fill": (_int, [_i32, _p, _p, _p]),
+    "hp_spline_tile_limits": (None, [_p, _p]),
     "hp_promol_weights_spline": (
         _int,
-        [_i64, _p, _p, _p, _i64, _i32, _p, _p, _p, _p, _p, _f64, _p, _p, _f64, _p, _p, _p, _p],
+        [_i64, _p, _p, _p, _i64, _i32, _p, _p, _p, _p, _p, _p, _p, _i32, _p, _f64, _p, _p, _f64, _p, _p, _p, _p],
     ),
     "hp_isa_update": (_int, [_i32, _i32, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
     "hp_spline_integral_blocks": (_i32, [_i64]),
@@ -104,13 +107,19 @@ EXPORTS = {
     "hp_host_is_pinned": (_int, [_p]),
     "hp_host_to_device": (_int, [_p, _p, _sz, _p, _sz, _i32, _p]),
     "hp_dfma_probe": (_int, [_i32, _p, _p, _p, _p]),
+    "hp_loop_begin": (_int, [_p, _p]),
+    "hp_loop_stamp": (_int, [_p, _p, _i32, _i32, _p, _p]),
+    "hp_loop_commit": (_int, [_p, _i32, _p, _p, _f64, _i32, _p, _p, _p, _p]),
+    "hp_loop_end": (_int, [_p, _p]),
+    "hp_loop_launch": (_int, [_p, _p]),
+    "hp_loop_destroy": (_int, [_p, _p]),
 }
 
 
 # int-returning functions whose result is a value, not a status code
 _NOT_STATUS = {"hp_abi_version", "hp_num_partials", "hp_local_index_scratch_bytes", "hp_last_error", "hp_tile_limits", "hp_molgrid_num_blocks", "hp_hessian_scratch_bytes",
                "hp_molgrid_update_tile_limits", "hp_host_is_pinned", "hp_local_tile_limits", "hp_local_chunk_points",
-               "hp_spline_integral_blocks"}
+               "hp_spline_integral_blocks", "hp_spline_lut_size", "hp_spline_tile_limits"}
 
 
 class HpError(RuntimeError):

@@ -78,7 +78,8 @@ class AbstractISAWPart(AbstractStockholderWPart):
 
     def __init__(self, coordinates, numbers, pseudo_numbers, grid, moldens, spindens=None, lmax=3,
                  logger=None, threshold=1e-6, maxiter=500, inner_threshold=1e-8, grid_type=1,
-                 **kwargs):  # fmt: skip
+                 device_loop=True, **kwargs):  # fmt: skip
+        self._device_loop = device_loop
         self._threshold = threshold
         self._inner_threshold = inner_threshold if inner_threshold < threshold else threshold
         self._maxiter = maxiter
@@ -264,6 +265,82 @@ class AbstractISAWPart(AbstractStockholderWPart):
         self.cache.load("charges", alloc=n, tags="o")[0][:] = host[1 + n : 1 + 2 * n]
         return float(host[nv]), float(host[nv + 1])
 
+    # -- device-resident loop -------------------------------------------------------------------
+    #: True for schemes whose iteration is nothing but kernel launches on the slab's stream (no host
+    #: solver, no torch allocation, no collective): MBIS, NLIS/GMBIS, ISA, aLISA with a device solver
+    device_loop_capable = False
+
+    def _use_device_loop(self):
+        """Run iterations 2..n as ONE CUDA-graph launch (csrc/hp_loop.cu: the body of a conditional WHILE
+        node, convergence test on the device)?  Default: whenever the scheme allows it -- the host then
+        pays one launch and one synchronisation for the whole loop instead of one D2H + sync per
+        iteration, which is what bounds H2O-sized systems.  ``device_loop=False`` (constructor) or
+        HP_B200_DEVICE_LOOP=0 keeps the host-driven loop; the results are identical."""
+        import os
+
+        env = os.environ.get("HP_B200_DEVICE_LOOP")
+        want = self._device_loop if env is None else env != "0"
+        return bool(want and self.device_loop_capable and self._comm is None and not self.on_molgrid)
+
+    def _run_device_loop(self, done, propars):
+        """Iterations done+1 .. niter on the device.  Returns (counter, change, entropy) of the last
+        iteration and appends to the history lists exactly what the host loop would have appended."""
+        import torch
+
+        from .device import stream_ptr
+
+        st, slab = self._state, self.slab
+        dev = slab.device
+        nv, n = st.vec.numel(), self.natom
+        maxiter = int(self._maxiter)
+        hist = torch.zeros((maxiter, nv + 2), dtype=torch.float64, device=dev)
+        counter = torch.full((1,), done, dtype=torch.int32, device=dev)
+        stamps = torch.zeros(2 * (maxiter + 1), dtype=torch.int64, device=dev)
+        # stream capture is not allowed on the legacy default stream: the loop runs on a side stream
+        main = torch.cuda.current_stream(dev)
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
+            stream = stream_ptr(dev)
+            handle = np.zeros(1, dtype=np.uint64)
+            _lib.call("hp_loop_stamp", None, counter, -1, 1, stamps, stream)  # "end of the previous iteration"
+            _lib.call("hp_loop_begin", stream, handle)
+            loop = int(handle[0])
+            try:
+                # the body: one iteration, exactly the launches of _run_iteration
+                self._launch_promol_weights(want_entropy=True)
+                _lib.call("hp_loop_stamp", loop, counter, 0, 0, stamps, stream)
+                self._launch_radial_update()
+                _lib.call("hp_finish_iteration", slab.npartial, slab.entropy_partials, n, st.msd, st.out2, stream)
+                _lib.call("hp_loop_commit", loop, nv, st.vec, st.out2, float(self._threshold), maxiter, hist,
+                          counter, stamps, stream)  # fmt: skip
+                _lib.call("hp_loop_end", loop, stream)
+                t0 = time.time()
+                _lib.call("hp_loop_launch", loop, stream)
+                side.synchronize()
+                self.time_usage["device_loop"] = time.time() - t0
+            finally:
+                _lib.call("hp_loop_destroy", loop, stream)
+        main.wait_stream(side)
+        niter = int(counter.item())
+        rows = hist[done:niter].cpu().numpy()
+        ns = stamps.cpu().numpy().reshape(-1, 2)
+        charges = self.cache.load("charges", alloc=n, tags="o")[0]
+        change = entropy = None
+        for k, row in enumerate(rows):
+            c = done + k  # zero-based index of this iteration
+            propars[:] = row[1 + 2 * n : nv]
+            charges[:] = row[1 + n : 1 + 2 * n]
+            change, entropy = float(row[nv]), float(row[nv + 1])
+            self.history_propars.append(propars.copy())
+            self.history_charges.append(charges.copy())
+            self.history_entropies.append(entropy)
+            self.history_changes.append(change)
+            self.history_time_update_at_weights.append((ns[c, 0] - ns[c - 1, 1]) * 1e-9)
+            self.history_time_update_propars.append((ns[c, 1] - ns[c, 0]) * 1e-9)
+            self.logger.info("%9i   %10.5e   %10.5e" % (c + 1, change, entropy))
+        return niter, change, entropy
+
     # -- the loop -------------------------------------------------------------------------------
     def _finalize_propars(self):
         charges = self._cache.load("charges")
@@ -299,6 +376,15 @@ class AbstractISAWPart(AbstractStockholderWPart):
             self.history_changes.append(change)
             self.logger.info("%9i   %10.5e   %10.5e" % (counter, change, entropy))
             if change < self._threshold or counter >= self._maxiter:
+                break
+            if counter == 1 and self._use_device_loop():
+                # every lazily allocated buffer exists after the first iteration: the rest of the loop
+                # runs on the device (same kernels, same order, same stopping rule)
+                for ev in self._state.events:
+                    self.history_time_update_at_weights.append(ev[0].elapsed_time(ev[1]) * 1e-3)
+                    self.history_time_update_propars.append(ev[1].elapsed_time(ev[2]) * 1e-3)
+                self._state.events = []
+                counter, change, entropy = self._run_device_loop(counter, propars)
                 break
         self.logger.info("")
         # device-timed split of the iterations (CUDA events; the reference uses time.time())

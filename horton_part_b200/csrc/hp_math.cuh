@@ -80,12 +80,19 @@ struct ExpConsts {
 };
 
 // Unguarded exp(x), -700 < x <= 0, constants from registers (same arithmetic as exp_neg_poly).
+// TWO_STEP = false drops the second Cody-Waite constant: r = x - k fl(ln2) in one FMA (the product is
+// exact inside the FMA), leaving the systematic error k (ln2 - fl(ln2)) = k * 2.3e-17 in the reduced
+// argument, i.e. a RELATIVE error of the result of at most 0.1 ulp per unit of k (1.4e-15 at
+// x = -40, 2.4e-14 at the underflow edge) on top of the polynomial's 0.67 ulp -- 15 FP64 operations
+// instead of 16, and the argument x = fl(alpha r) still rounds exactly like the reference's
+// np.exp(-S * r) (mbis.py:286), which the base-2 variant below does not.
+template <bool TWO_STEP = true>
 __device__ __forceinline__ double exp_neg_poly_regs(double x, const ExpConsts& c) {
     const double t = fma(x, c.log2e, 6755399441055744.0);
     const int k = __double2loint(t);
     const double kd = t - 6755399441055744.0;
     double r = fma(kd, c.ln2hi, x);
-    r = fma(kd, c.ln2lo, r);
+    if (TWO_STEP) r = fma(kd, c.ln2lo, r);
     double g = fma(c.g[9], r, c.g[8]);
 #pragma unroll
     for (int i = 7; i >= 0; --i) g = fma(g, r, c.g[i]);

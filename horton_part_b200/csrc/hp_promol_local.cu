@@ -47,9 +47,12 @@ namespace hp {
 #define HP_LOC_THREADS 128
 #endif
 #ifndef HP_LOC_BLOCKS
-#define HP_LOC_BLOCKS 2
+#define HP_LOC_BLOCKS 3
 #endif
-constexpr int kLocThreads = HP_LOC_THREADS;      // 128 threads x 2 blocks/SM: 255 registers per thread
+// 128 threads x 3 blocks/SM (<= 170 registers per thread): 3 warps x 8 points = 24 independent FP64
+// dependency chains per scheduler; with 2 blocks (16 chains) the FP64 pipe waits on its own latency
+// (B200, config 5: 112.4 -> 103.2 ms per iteration, profiles/r2_hot_kernel_variants.txt)
+constexpr int kLocThreads = HP_LOC_THREADS;
 constexpr int kLocBlocksPerSM = HP_LOC_BLOCKS;
 #ifndef HP_LOC_PTS
 #define HP_LOC_PTS 8
@@ -87,6 +90,9 @@ __device__ __forceinline__ void lds_z_pack(unsigned addr, double& z, int& s0, in
 #ifndef HP_LOC_EXP2
 #define HP_LOC_EXP2 0  // 1: base-2 exponential in the candidate loop (hp_math.cuh), for A/B runs
 #endif
+#ifndef HP_LOC_EXP_TWO_STEP
+#define HP_LOC_EXP_TWO_STEP 0  // 1: two-constant Cody-Waite reduction (16 FP64 operations per shell instead of 15)
+#endif
 
 #if HP_LOC_EXP2
 using LocExpConsts = Exp2Consts;
@@ -104,14 +110,17 @@ __device__ __forceinline__ double loc_neg_exponent(double alpha, const LocExpCon
 // exp(x) for x <= 0 with the constants in registers; GUARD adds the underflow flush of exp_neg_poly.
 template <bool GUARD>
 __device__ __forceinline__ double exp_regs(double x, const LocExpConsts& c) {
-    const double e = exp_neg_poly_regs(x, c);
+    const double e = exp_neg_poly_regs<HP_LOC_EXP_TWO_STEP != 0>(x, c);
     if (!GUARD) return e;
     return exp_arg_tiny(x) ? 0.0 : e;
 }
 #endif
 
+// the general-order functor (pow per shell) needs more registers: 2 blocks per SM there
+constexpr int loc_blocks_per_sm(int functor) { return functor == HP_FUNCTOR_GENERAL ? 2 : kLocBlocksPerSM; }
+
 template <int F, bool LOCAL>
-__global__ void __launch_bounds__(kLocThreads, kLocBlocksPerSM)
+__global__ void __launch_bounds__(kLocThreads, loc_blocks_per_sm(F))
 promol_weights_local_kernel(int64_t npts, const double* __restrict__ px, const double* __restrict__ py,
                             const double* __restrict__ pz, int64_t point_base, int natom,
                             const double* __restrict__ atom_xyz, const int64_t* __restrict__ atom_pt_off,
@@ -610,7 +619,7 @@ extern "C" int hp_promol_weights_local(int functor, int64_t npts, const double* 
     unsigned long long* counter = reinterpret_cast<unsigned long long*>(chunk_scratch + nchunk);
     rc = check_cuda(cudaMemsetAsync(counter, 0, sizeof(unsigned long long), st), "memset");
     if (rc) return rc;
-    int64_t grid = int64_t(sm_count()) * kLocBlocksPerSM;
+    int64_t grid = int64_t(sm_count()) * loc_blocks_per_sm(functor);
     if (grid > nchunk) grid = nchunk;
     const bool local = !isinf(radius);
     double* chunk_entropy = entropy_partials ? chunk_scratch : nullptr;

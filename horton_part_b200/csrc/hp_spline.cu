@@ -7,6 +7,8 @@
 //                            extrapolating with the end pieces exactly like PPoly
 //   hp_isa_update            ISA's parameter update: propars = clipped spherical average, charge,
 //                            change term (isa.py:102-122, core/iterstock.py:32-45)
+#include <cstring>
+
 #include "hp_common.cuh"
 #include "hp_math.cuh"
 
@@ -109,58 +111,150 @@ __device__ __forceinline__ double spline_eval(const double* __restrict__ x, cons
     return fma(ci[0], z, res);
 }
 
+// ---------------------------------------------------------------------------------------------
+// Fused promolecule / owner-weight / entropy pass for piecewise-cubic pro-atoms.
+//
+// Interval index without a binary search: the top bits of the double r (sign, exponent and the first
+// kLutMantBits mantissa bits) are a piecewise-linear log2 r, monotone in r, so
+//     bin = clamp((hi32(r) >> kLutShift) - key0, 0, nbins - 1),   i = lut[bin]
+// is the interval that contains the lower edge of r's bin; a forward scan `while x[i+1] <= r` (0-1
+// steps for the radial transforms of qc-grid at 32 bins per octave, bounded by the knot count for
+// any grid) then lands on searchsorted_right(x, r) - 1 clamped to [0, n-2], i.e. exactly PPoly's
+// interval incl. extrapolation with the end pieces.  The table is built on the host once per distinct
+// knot array (hp_spline_lut_size / hp_spline_lut_fill); atoms with the same radial grid share it.
+//
+// Atoms are streamed through shared memory in tiles (knots + PPoly coefficients, <= kSplTileKnots
+// knots per tile); a thread owns kSplPts points of a chunk of consecutive points and keeps their
+// running promolecule sums in registers, summing in atom order like the reference.
+// ---------------------------------------------------------------------------------------------
 constexpr int kSplThreads = 256;
-constexpr int kSplPts = 2;
+constexpr int kSplTileKnots = 1536;  // 1536 knots + 4 x 1536 coefficients = 61,440 B of dynamic shared memory: 3 blocks per SM
+constexpr int kSplTileAtoms = 64;
+constexpr int kLutMantBits = 5;
+constexpr int kLutShift = 20 - kLutMantBits;
 
-__global__ void __launch_bounds__(kSplThreads)
+struct SplAtom {  // 48 bytes
+    double x, y, z;
+    int ko, n;       // first knot in the tile's knot array, number of knots
+    int key0, nbins;
+    long long lut;   // offset of the atom's table in the LUT pool
+};
+
+template <int PTS>
+__global__ void __launch_bounds__(kSplThreads, 3)
 promol_weights_spline_kernel(int64_t npts, const double* __restrict__ px, const double* __restrict__ py,
                              const double* __restrict__ pz, int64_t point_base, int natom,
                              const double* __restrict__ atom_xyz, const int64_t* __restrict__ atom_pt_off,
                              const int* __restrict__ knot_off, const double* __restrict__ knots,
-                             const double* __restrict__ coef, double proatom_offset,
+                             const double* __restrict__ coef, const int* __restrict__ lut_meta,
+                             const unsigned short* __restrict__ lut, int ntile,
+                             const int* __restrict__ tile_off, double proatom_offset,
                              const double* __restrict__ rho, const double* __restrict__ molw,
                              double density_cutoff, double* __restrict__ promol_out,
                              double* __restrict__ w_out, double* __restrict__ entropy_partials,
                              int npartial) {
+    extern __shared__ __align__(16) double s_dyn[];  // coefficients (4 per segment) | knots
+    double* s_coef = s_dyn;
+    double* s_knots = s_dyn + 4 * kSplTileKnots;
+    __shared__ SplAtom s_atoms[kSplTileAtoms];
     __shared__ double s_red[32];
-    const int64_t span = int64_t(kSplThreads) * kSplPts;
+    __shared__ int s_own[2];
+    const int64_t span = int64_t(kSplThreads) * PTS;
     const int64_t nchunk = (npts + span - 1) / span;
     double entropy_acc = 0.0;
     for (int64_t chunk = blockIdx.x; chunk < nchunk; chunk += gridDim.x) {
-        double x[kSplPts], y[kSplPts], z[kSplPts], pro[kSplPts], own[kSplPts];
-        int owner[kSplPts];
-#pragma unroll
-        for (int j = 0; j < kSplPts; ++j) {
-            const int64_t p = chunk * span + int64_t(j) * kSplThreads + threadIdx.x;
-            const int64_t q = p < npts ? p : npts - 1;
-            x[j] = px[q]; y[j] = py[q]; z[j] = pz[q];
-            pro[j] = 0.0; own[j] = 0.0;
-            const int64_t g = point_base + q;
+        // owner atoms of the chunk's first and last point (block-uniform); a per-point search is only
+        // needed when the chunk straddles atom blocks
+        if (threadIdx.x < 2) {
+            const int64_t last = (chunk + 1) * span - 1;
+            const int64_t g = point_base + (threadIdx.x == 0 ? chunk * span : (last < npts ? last : npts - 1));
             int lo = 0, hi = natom;
             while (hi - lo > 1) {
                 const int mid = (lo + hi) >> 1;
                 if (atom_pt_off[mid] <= g) lo = mid; else hi = mid;
             }
+            s_own[threadIdx.x] = lo;
+        }
+        __syncthreads();
+        const int own_lo = s_own[0], own_hi = s_own[1];
+        double x[PTS], y[PTS], z[PTS], pro[PTS], own[PTS];
+        int owner[PTS];
+#pragma unroll
+        for (int j = 0; j < PTS; ++j) {
+            const int64_t p = chunk * span + int64_t(j) * kSplThreads + threadIdx.x;
+            const int64_t q = p < npts ? p : npts - 1;
+            x[j] = px[q]; y[j] = py[q]; z[j] = pz[q];
+            pro[j] = 0.0; own[j] = 0.0;
+            int lo = own_lo;
+            if (own_hi != own_lo) {
+                const int64_t g = point_base + q;
+                int hi = own_hi + 1;
+                while (hi - lo > 1) {
+                    const int mid = (lo + hi) >> 1;
+                    if (atom_pt_off[mid] <= g) lo = mid; else hi = mid;
+                }
+            }
             owner[j] = lo;
         }
-        for (int a = 0; a < natom; ++a) {
-            const double ax = atom_xyz[3 * a], ay = atom_xyz[3 * a + 1], az = atom_xyz[3 * a + 2];
-            const int o = knot_off[a], n = knot_off[a + 1] - o;
-            const double* xk = knots + o;
-            const double* ck = coef + 4 * (o - a);
+        for (int t = 0; t < ntile; ++t) {
+            const int a0 = tile_off[t], a1 = tile_off[t + 1];
+            const int k0 = knot_off[a0], k1 = knot_off[a1];
+            __syncthreads();  // previous tile consumed
+            // knots of atoms a0..a1-1 are contiguous, and so are their coefficient blocks
+            for (int i = threadIdx.x; i < k1 - k0; i += kSplThreads) s_knots[i] = knots[k0 + i];
+            {
+                const double2* src = reinterpret_cast<const double2*>(coef + 4 * int64_t(k0 - a0));
+                double2* dst = reinterpret_cast<double2*>(s_coef);
+                const int n2 = 2 * ((k1 - k0) - (a1 - a0));
+                for (int i = threadIdx.x; i < n2; i += kSplThreads) dst[i] = src[i];
+            }
+            if (threadIdx.x < a1 - a0) {
+                const int a = a0 + threadIdx.x;
+                SplAtom rec;
+                rec.x = atom_xyz[3 * a]; rec.y = atom_xyz[3 * a + 1]; rec.z = atom_xyz[3 * a + 2];
+                rec.ko = knot_off[a] - k0;
+                rec.n = knot_off[a + 1] - knot_off[a];
+                rec.key0 = lut_meta[3 * a];
+                rec.nbins = lut_meta[3 * a + 1];
+                rec.lut = lut_meta[3 * a + 2];
+                s_atoms[threadIdx.x] = rec;
+            }
+            __syncthreads();
+            for (int ia = 0; ia < a1 - a0; ++ia) {
+                const SplAtom at = s_atoms[ia];
+                const int a = a0 + ia;
+                const double* xk = s_knots + at.ko;
+                const double* ck = s_coef + 4 * (at.ko - ia);
+                const unsigned short* tab = lut + at.lut;
+                const int last = at.n - 2;
 #pragma unroll
-            for (int j = 0; j < kSplPts; ++j) {
-                const double dx = x[j] - ax, dy = y[j] - ay, dz = z[j] - az;
-                const double r = sqrt_nocall(fma(dz, dz, fma(dy, dy, dx * dx)));
-                // eval_proatom (core/stockholder.py:343-349): spline(r) + 1e-100 ...
-                const double f = spline_eval(xk, ck, n, r) + proatom_offset;
-                // ... update_pro (:169-170): promoldens += work; promoldens += 1e-100
-                pro[j] = (pro[j] + f) + 1e-100;
-                if (a == owner[j]) own[j] = f;
+                for (int j = 0; j < PTS; ++j) {
+                    const double dx = x[j] - at.x, dy = y[j] - at.y, dz = z[j] - at.z;
+                    const double r = sqrt_nocall(fma(dz, dz, fma(dy, dy, dx * dx)));
+                    int bin = (__double2hiint(r) >> kLutShift) - at.key0;
+                    bin = max(0, min(bin, at.nbins - 1));
+                    int i = tab[bin];
+                    while (i < last && xk[i + 1] <= r) ++i;
+                    const double d = r - xk[i];
+                    const double2 c01 = *reinterpret_cast<const double2*>(ck + 4 * i);
+                    const double2 c23 = *reinterpret_cast<const double2*>(ck + 4 * i + 2);
+                    // PPoly's evaluation order: c3 + c2 d + c1 d^2 + c0 d^3
+                    double zz = d;
+                    double res = fma(c23.x, zz, c23.y);
+                    zz *= d;
+                    res = fma(c01.y, zz, res);
+                    zz *= d;
+                    res = fma(c01.x, zz, res);
+                    // eval_proatom (core/stockholder.py:343-349): spline(r) + 1e-100 ...
+                    const double f = res + proatom_offset;
+                    // ... update_pro (:169-170): promoldens += work; promoldens += 1e-100
+                    pro[j] = (pro[j] + f) + 1e-100;
+                    own[j] = (a == owner[j]) ? f : own[j];
+                }
             }
         }
 #pragma unroll
-        for (int j = 0; j < kSplPts; ++j) {
+        for (int j = 0; j < PTS; ++j) {
             const int64_t p = chunk * span + int64_t(j) * kSplThreads + threadIdx.x;
             if (p >= npts) continue;
             if (promol_out) promol_out[p] = pro[j];
@@ -264,16 +358,70 @@ extern "C" int hp_spline_build(int32_t natom, const int32_t* knot_offsets, const
     return HP_OK;
 }
 
+// ---- interval look-up tables (host) -------------------------------------------------------------
+namespace {
+inline int lut_key(double r) {
+    long long bits;
+    memcpy(&bits, &r, sizeof(bits));
+    return int(bits >> (32 + hp::kLutShift));
+}
+// first key of the table and its number of bins for a knot array (capped: the scan covers the rest)
+inline void lut_range(const double* x, int n, int* key0, int* nbins) {
+    const int hi = lut_key(x[n - 1] > 0.0 ? x[n - 1] : 0.0);
+    int lo = lut_key(x[0] > 0.0 ? x[0] : 0.0);
+    const int cap = 4096;
+    if (hi - lo + 1 > cap) lo = hi - cap + 1;
+    *key0 = lo;
+    *nbins = hi - lo + 1;
+}
+}  // namespace
+
+extern "C" int32_t hp_spline_lut_size(int32_t nknot, const double* knots_host) {
+    if (nknot < 2 || !knots_host) return 0;
+    int key0, nbins;
+    lut_range(knots_host, nknot, &key0, &nbins);
+    return nbins;
+}
+
+extern "C" int hp_spline_lut_fill(int32_t nknot, const double* knots_host, int32_t* key0_out,
+                                  uint16_t* lut_host) {
+    HP_REQUIRE(nknot >= 2 && nknot <= 65535 && knots_host && key0_out && lut_host, "bad arguments");
+    int key0, nbins;
+    lut_range(knots_host, nknot, &key0, &nbins);
+    *key0_out = key0;
+    int i = 0;
+    for (int b = 0; b < nbins; ++b) {
+        // lower edge of bin b: the double whose top bits are key0 + b and whose other bits are 0
+        const long long bits = (long long)(key0 + b) << (32 + hp::kLutShift);
+        double edge;
+        memcpy(&edge, &bits, sizeof(edge));
+        while (i < nknot - 2 && knots_host[i + 1] <= edge) ++i;  // searchsorted_right(x, edge) - 1, clamped
+        lut_host[b] = uint16_t(i);
+    }
+    // everything below the first bin is clamped into it: start the scan at the first interval there
+    // (matters only when the number of bins was capped, i.e. key0 raised above the first knot's key)
+    lut_host[0] = 0;
+    return HP_OK;
+}
+
+extern "C" void hp_spline_tile_limits(int32_t* max_atoms_host, int32_t* max_knots_host) {
+    *max_atoms_host = kSplTileAtoms;
+    *max_knots_host = kSplTileKnots;
+}
+
 extern "C" int hp_promol_weights_spline(int64_t npts, const double* px, const double* py,
                                         const double* pz, int64_t point_base, int32_t natom,
                                         const double* atom_xyz, const int64_t* atom_point_offsets,
                                         const int32_t* knot_offsets, const double* knots,
-                                        const double* coef, double proatom_offset, const double* rho,
+                                        const double* coef, const int32_t* lut_meta, const uint16_t* lut,
+                                        int32_t ntile, const int32_t* tile_atom_offsets,
+                                        double proatom_offset, const double* rho,
                                         const double* molw, double density_cutoff, double* promol,
                                         double* at_weights, double* entropy_partials, void* stream) {
-    HP_REQUIRE(npts >= 0 && natom > 0, "bad sizes");
+    HP_REQUIRE(npts >= 0 && natom > 0 && ntile > 0, "bad sizes");
     HP_REQUIRE(px && py && pz && atom_xyz && atom_point_offsets && knot_offsets && knots && coef,
                "null input");
+    HP_REQUIRE(lut_meta && lut && tile_atom_offsets, "null look-up table / tiling");
     HP_REQUIRE(!entropy_partials || (rho && molw), "entropy needs rho and molw");
     const int npartial = hp_num_partials();
     if (npts == 0) {
@@ -282,17 +430,32 @@ extern "C" int hp_promol_weights_spline(int64_t npts, const double* px, const do
                                               as_stream(stream)), "memset partials");
         return HP_OK;
     }
-    int per_sm = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, promol_weights_spline_kernel, kSplThreads, 0);
-    if (per_sm < 1) per_sm = 1;
-    const int64_t span = int64_t(kSplThreads) * kSplPts;
+    const size_t smem = sizeof(double) * 5 * kSplTileKnots;
+    // small grids: fewer points per thread so that the chunks cover the SMs
+    const bool small = npts < int64_t(sm_count()) * 3 * kSplThreads * 4;
+    static bool configured = false;
+    if (!configured) {
+        int rc = check_cuda(cudaFuncSetAttribute(promol_weights_spline_kernel<4>,
+                                                 cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)), "cudaFuncSetAttribute");
+        if (rc) return rc;
+        rc = check_cuda(cudaFuncSetAttribute(promol_weights_spline_kernel<1>,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)), "cudaFuncSetAttribute");
+        if (rc) return rc;
+        configured = true;
+    }
+    const int pts = small ? 1 : 4;
+    const int64_t span = int64_t(kSplThreads) * pts;
     int64_t grid = (npts + span - 1) / span;
-    int64_t cap = int64_t(sm_count()) * per_sm;
+    int64_t cap = int64_t(sm_count()) * 3;
     if (cap > npartial) cap = npartial;
     if (grid > cap) grid = cap;
-    promol_weights_spline_kernel<<<int(grid), kSplThreads, 0, as_stream(stream)>>>(
-        npts, px, py, pz, point_base, natom, atom_xyz, atom_point_offsets, knot_offsets, knots, coef,
-        proatom_offset, rho, molw, density_cutoff, promol, at_weights, entropy_partials, npartial);
+#define HP_SPL_ARGS                                                                                        \
+    npts, px, py, pz, point_base, natom, atom_xyz, atom_point_offsets, knot_offsets, knots, coef, lut_meta, \
+        lut, ntile, tile_atom_offsets, proatom_offset, rho, molw, density_cutoff, promol, at_weights,      \
+        entropy_partials, npartial
+    if (small) promol_weights_spline_kernel<1><<<int(grid), kSplThreads, smem, as_stream(stream)>>>(HP_SPL_ARGS);
+    else promol_weights_spline_kernel<4><<<int(grid), kSplThreads, smem, as_stream(stream)>>>(HP_SPL_ARGS);
+#undef HP_SPL_ARGS
     HP_LAUNCH_CHECK("promol_weights_spline_kernel");
     return HP_OK;
 }

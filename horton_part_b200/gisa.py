@@ -316,6 +316,12 @@ class GaussianISAWPart(AbstractISAWPart):
         self.cache.load("charges", alloc=self.natom, tags="o")[0][:] = charges
         return float(out2[0]), float(out2[1])
 
+    @property
+    def device_loop_capable(self):
+        """Only the device solvers keep the whole iteration on the GPU (host plug-ins need the spherical
+        averages on the host every iteration; tabulated bases mix their splines on the host)."""
+        return (not callable(self._solver)) and self._solver in self.device_solvers and not self._numeric
+
     def _launch_radial_update(self):
         self.slab.shell_project()
         if not callable(self._solver) and self._solver in self.device_solvers:

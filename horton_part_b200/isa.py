@@ -43,6 +43,44 @@ class SplineTable:
         #: added to every spline value: base eval_proatom does ``spline(r) + 1e-100``
         #: (core/stockholder.py:349); 0 for pro-atoms that are plain sums of tabulated shells
         self.proatom_offset = proatom_offset
+        self._build_lookup(rgrids, sizes)
+
+    def _build_lookup(self, rgrids, sizes):
+        """Interval look-up tables (one per distinct knot array, shared by the atoms that use it) and
+        the shared-memory tiling of the atom list for ``hp_promol_weights_spline``."""
+        from .core.device import to_device
+
+        dev = self.slab.device
+        tables, pool, meta, pos = {}, [], np.zeros((len(rgrids), 3), dtype=np.int32), 0
+        for a, g in enumerate(rgrids):
+            x = np.ascontiguousarray(g.points, dtype=np.float64)
+            if len(x) < 2:
+                raise ValueError("a spline pro-atom needs at least two knots")
+            key = x.tobytes()
+            if key not in tables:
+                nb = int(_lib.call("hp_spline_lut_size", len(x), x))
+                lut, key0 = np.zeros(nb, dtype=np.uint16), np.zeros(1, dtype=np.int32)
+                _lib.call("hp_spline_lut_fill", len(x), x, key0, lut)
+                tables[key] = (int(key0[0]), nb, pos)
+                pool.append(lut)
+                pos += nb
+            meta[a] = tables[key]
+        self.lut_meta = to_device(meta.ravel(), dev, np.int32)
+        self.lut = to_device(np.concatenate(pool), dev, np.uint16)
+        max_atoms, max_knots = np.zeros(1, np.int32), np.zeros(1, np.int32)
+        _lib.call("hp_spline_tile_limits", max_atoms, max_knots)
+        if max(sizes) > int(max_knots[0]):
+            raise ValueError(f"radial grids with more than {int(max_knots[0])} points are not supported by the spline pass")
+        tiles, a, natom = [0], 0, len(sizes)
+        while a < natom:
+            b, nk = a, 0
+            while b < natom and b - a < int(max_atoms[0]) and nk + sizes[b] <= int(max_knots[0]):
+                nk += sizes[b]
+                b += 1
+            tiles.append(b)
+            a = b
+        self.ntile = len(tiles) - 1
+        self.tiles = to_device(np.asarray(tiles, dtype=np.int32), dev)
 
     def build(self, values, clip_negative=True):
         from .core.device import stream_ptr
@@ -59,7 +97,8 @@ class SplineTable:
             proatom_offset = self.proatom_offset
         _lib.call(
             "hp_promol_weights_spline", s.npts, s.px, s.py, s.pz, s.point_base, s.natom, s.atom_xyz,
-            s.atom_point_offsets, self.offsets, self.knots, self.coef, float(proatom_offset), s.rho,
+            s.atom_point_offsets, self.offsets, self.knots, self.coef, self.lut_meta, self.lut, self.ntile,
+            self.tiles, float(proatom_offset), s.rho,
             s.molw, float(density_cutoff), s.promol if want_promol else None,
             s.at_w if want_weights else None, s.entropy_partials if want_entropy else None,
             stream_ptr(s.device),
@@ -70,6 +109,7 @@ class ISAWPart(AbstractISAWPart):
     """Iterative Stockholder Partitioning with Becke-Lebedev grids"""
 
     name = "is"
+    device_loop_capable = True
 
     def _init_log_scheme(self):
         logger.info("Initialized: %s" % self.__class__.__name__)

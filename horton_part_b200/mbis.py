@@ -64,6 +64,7 @@ class MBISWPart(AbstractISAWPart):
 
     name = "mbis"
     max_inner = 2000  # mbis.py:123
+    device_loop_capable = True
 
     def _init_log_scheme(self):
         logger.info("Initialized: %s" % self.__class__.__name__)

@@ -46,6 +46,7 @@ class NLISWPart(AbstractISAWPart):
 
     name = "nlis"
     max_inner = 2000  # nlis.py:141
+    device_loop_capable = True
     _scheme_label = "Non-Linear approximation of Iterative Stockholder (NLIS)"
 
     def __init__(self, coordinates, numbers, pseudo_numbers, grid, moldens, spindens=None, lmax=3,

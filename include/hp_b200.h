@@ -248,11 +248,26 @@ HP_API int hp_lisa_sc_radial_solve(int32_t natom, int32_t atom_base, const int32
 HP_API int hp_spline_build(int32_t natom, const int32_t* knot_offsets, const double* knots,
                            const double* values, int32_t clip_negative, double* coef, double* work,
                            void* stream);
+/* Interval index of the fused spline pass (the reference's eval_spline is scipy PPoly's binary
+ * search, core/stockholder.py:271-302): the top bits of the double r (sign, exponent, 5 mantissa bits)
+ * are a piecewise-linear, monotone log2 r; lut[(hi32(r) >> 15) - key0] is the interval holding the
+ * lower edge of r's bin and a short forward scan finishes on searchsorted_right(x, r) - 1 clamped to
+ * [0, n-2] -- PPoly's interval, end pieces extrapolating.  HOST helpers, one table per distinct knot
+ * array: hp_spline_lut_size = number of bins, hp_spline_lut_fill writes them (uint16) and key0.
+ * Per atom lut_meta = (key0, nbins, offset of its table in the device pool `lut`), 3 int32 each.
+ * Atoms are streamed through shared memory in tiles of consecutive atoms (tile_atom_offsets, ntile + 1
+ * entries) that respect hp_spline_tile_limits (atoms and knots per tile). */
+HP_API int32_t hp_spline_lut_size(int32_t nknot, const double* knots_host);
+HP_API int hp_spline_lut_fill(int32_t nknot, const double* knots_host, int32_t* key0_out,
+                              uint16_t* lut_host);
+HP_API void hp_spline_tile_limits(int32_t* max_atoms_host, int32_t* max_knots_host);
 HP_API int hp_promol_weights_spline(int64_t npts, const double* px, const double* py,
                                     const double* pz, int64_t point_base, int32_t natom,
                                     const double* atom_xyz, const int64_t* atom_point_offsets,
                                     const int32_t* knot_offsets, const double* knots,
-                                    const double* coef, double proatom_offset, const double* rho,
+                                    const double* coef, const int32_t* lut_meta, const uint16_t* lut,
+                                    int32_t ntile, const int32_t* tile_atom_offsets,
+                                    double proatom_offset, const double* rho,
                                     const double* molw, double density_cutoff, double* promol,
                                     double* at_weights, double* entropy_partials, void* stream);
 HP_API int hp_isa_update(int32_t natom, int32_t atom_base, const int32_t* rad_offsets,
@@ -409,6 +424,31 @@ HP_API int hp_host_to_device(void* dst_dev, const void* src_host, size_t bytes, 
  * DFMA chains (8 independent per thread) on a full grid; returns elapsed ms in *ms_host and the
  * flop count in *flops_host.  Synchronises the stream. */
 HP_API int hp_dfma_probe(int32_t iters, double* sink, float* ms_host, double* flops_host, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Device-resident outer loop (row a11): `while True: ...; if change < threshold or counter >= maxiter:
+ * break` of do_partitioning (core/iterstock.py:171-188) as ONE CUDA-graph launch.
+ *   hp_loop_begin   creates a graph with a conditional WHILE node and starts capturing `stream` (not the
+ *                   legacy default stream) into the node's body; *loop_out receives an opaque handle.
+ *   ...             the caller issues the launches of one iteration on `stream` (any hp_* entry point
+ *                   that only enqueues work; no synchronisation, no allocation)
+ *   hp_loop_stamp   (optional, also usable outside a capture) stamps[2 * (*counter + row_shift) + slot] =
+ *                   %globaltimer in ns, for the per-iteration timings the reference records
+ *                   (core/iterstock.py:135-145)
+ *   hp_loop_commit  last launch of the body: history[c] = [state_vec (nvec) | out2[0] = change | out2[1] =
+ *                   entropy] with c = *counter, stamps[2 c + 1] = now, *counter = c + 1, and the loop
+ *                   continues iff not (change < threshold) and c + 1 < maxiter.  history holds maxiter rows.
+ *   hp_loop_end     ends the capture and instantiates the graph; hp_loop_launch runs the whole loop;
+ *   hp_loop_destroy releases it (and abandons an unfinished capture). */
+HP_API int hp_loop_begin(void* stream, void** loop_out);
+HP_API int hp_loop_stamp(void* loop, const int32_t* counter, int32_t row_shift, int32_t slot,
+                         uint64_t* stamps, void* stream);
+HP_API int hp_loop_commit(void* loop, int32_t nvec, const double* state_vec, const double* out2,
+                          double threshold, int32_t maxiter, double* history, int32_t* counter,
+                          uint64_t* stamps, void* stream);
+HP_API int hp_loop_end(void* loop, void* stream);
+HP_API int hp_loop_launch(void* loop, void* stream);
+HP_API int hp_loop_destroy(void* loop, void* stream);
 
 #ifdef __cplusplus
 }

@@ -649,26 +649,47 @@ def case_config2(natom=20, nrad=150, nang=194, seed=0):
         results[tag]["seconds"] = np.float64(time.time() - t0)
         print(f"  config2 {tag}: niter={results[tag].get('niter')} q={np.round(part['charges'][:4], 6)} "
               f"{time.time() - t0:.0f} s", flush=True)
-    # Hirshfeld-I needs the anion of every element that ends up negative; the reference's cached
-    # database has no N(-1) record (atom_Z07_N08 is absent: KeyError (7, -1) in core/proatomdb.py:282),
-    # so the HI run uses the same chain with N replaced by O (C6O4H10-like) and its own promolecule.
-    numbers_hi = np.where(numbers == 7, 8, numbers)
-    rho_hi = synthetic.slater_promolecule_host(grid.points, coords, numbers_hi)
-    grid_hi = synthetic_grid(coords, numbers_hi, nrad, nang)
-    t0 = time.time()
-    with contextlib.redirect_stdout(io.StringIO()):
-        part = wpart_schemes("hi")(coords, numbers_hi, numbers_hi.astype(float), grid_hi, rho_hi, proatomdb=ProAtomDB(records))
-        part.do_charges()
-    results["hi"] = _full_out(part, grid_hi)
-    results["hi"]["seconds"] = np.float64(time.time() - t0)
-    results["hi"]["numbers"] = numbers_hi
-    print(f"  config2 hi: niter={results['hi'].get('niter')} q={np.round(part['charges'][:4], 6)} {time.time() - t0:.0f} s", flush=True)
+    # Hirshfeld-I: case_config2_hi (its own file; it needs a database-compatible element set and density)
     save("config2_organic20.npz", results, coordinates=coords, numbers=numbers, pseudo_numbers=pseudo,
          dens_sample=rho[::997].copy(), aim_weights_sample=grid.aim_weights[::997].copy(),
          nelec=np.float64(grid.integrate(rho)),
          grid_spec=np.array(f"BeckeRTransform(1e-4,1.5) o GaussChebyshev({nrad}) x Lebedev{nang}, BeckeWeights(); "
                             f"synthetic.organic_like({natom}, {seed})"),
          **{f"record/{k}": v for k, v in raw.items()})  # fmt: skip
+
+
+#: shells of the Hirshfeld-I variant of config 2: milder populations than synthetic.SLATER_SHELLS, because
+#: Hirshfeld-I amplifies charges and the reference's cached database stops at O(-1) / C(-1) / H(-1)
+#: (a charge beyond that raises KeyError in core/proatomdb.py:282)
+CONFIG2_HI_SHELLS = {1: ((0.95, 2.0),), 6: ((1.70, 11.3), (4.25, 1.9)), 8: ((1.65, 15.0), (6.45, 2.4))}
+
+
+def case_config2_hi(natom=20, nrad=150, nang=194, seed=0):
+    """Hirshfeld-I at config-2 size: the same 20-atom chain with N replaced by O (the reference's cached
+    database has no N anion: atom_Z07_N08 is absent), promolecule of CONFIG2_HI_SHELLS, 582,000 points."""
+    import contextlib
+    import io
+
+    from horton_part.core.proatomdb import ProAtomDB
+
+    coords, numbers = synthetic.organic_like(natom, seed)
+    numbers = np.where(numbers == 7, 8, numbers)
+    grid = synthetic_grid(coords, numbers, nrad, nang)
+    rho = synthetic.slater_promolecule_host(grid.points, coords, numbers, shells=CONFIG2_HI_SHELLS)
+    records, raw = _pack_records((1, 6, 8))
+    t0 = time.time()
+    with contextlib.redirect_stdout(io.StringIO()):
+        part = wpart_schemes("hi")(coords, numbers, numbers.astype(float), grid, rho, proatomdb=ProAtomDB(records))
+        part.do_charges()
+    res = _full_out(part, grid)
+    res["seconds"] = np.float64(time.time() - t0)
+    print(f"  config2 hi: niter={res.get('niter')} q={np.round(part['charges'][:6], 6)} {time.time() - t0:.0f} s", flush=True)
+    shells = {f"shells/Z{z}": np.asarray(v, float) for z, v in CONFIG2_HI_SHELLS.items()}
+    save("config2_hi.npz", {"hi": res}, coordinates=coords, numbers=numbers,
+         dens_sample=rho[::997].copy(), aim_weights_sample=grid.aim_weights[::997].copy(),
+         grid_spec=np.array(f"BeckeRTransform(1e-4,1.5) o GaussChebyshev({nrad}) x Lebedev{nang}, BeckeWeights(); "
+                            f"synthetic.organic_like({natom}, {seed}) with N -> O"),
+         **shells, **{f"record/{k}": v for k, v in raw.items()})  # fmt: skip
 
 
 def case_config3(natom=24, nrad=150, nang=194, seed=0, maxiter=500):
@@ -731,7 +752,7 @@ def case_config4(natom=12, nrad=150, nang=194, seed=0):
 CASES = {"h2o": case_h2o, "water6": case_water_cluster, "water6g": case_water_gauss, "hirshfeld": case_hirshfeld,
          "solvers": case_water6_solvers, "convex": case_water6_convex, "convex_radial": case_convex_radial, "numeric": case_numeric, "proatomdb": case_proatomdb, "algo": case_algo, "postproc": case_postproc,
          "molecules": case_molecules,
-         "config2": case_config2, "config3": case_config3, "config4": case_config4}
+         "config2": case_config2, "config2_hi": case_config2_hi, "config3": case_config3, "config4": case_config4}
 
 if __name__ == "__main__":
     for name in sys.argv[1:] or CASES:

@@ -38,10 +38,15 @@ def test_atom_screening_is_exact(make_water, monkeypatch):
     # first, then added): the chunk kernel feeds every shell straight into the running sum with one
     # FMA, an equally valid but different rounding sequence of ~natom*K additions (random walk of
     # half-ulp steps: a few hundred ulp at worst over 768,000 points).
+    # The chunk kernel's exponential reduces its argument with ONE constant (r = x - k fl(ln2), hp_math.cuh):
+    # a systematic relative error of k * 2.3e-17 = 0.1-0.2 ulp per unit of k = -x / ln2.  Where the
+    # promolecule is above 1e-30 (k <= 100) that is below the rounding-sequence noise; in the far field
+    # (values down to 1e-98 here, k up to ~1000) it reaches a few hundred ulp, i.e. 1e-13 relative.
     for other, max_ulp, same, wtol in ((off, 64, 0.9, 1e-15), (plain, 512, 0.0, 1e-13)):
         a, b = on["promoldens"], other["promoldens"]
         ulp = np.spacing(np.abs(b))
-        assert (np.abs(a - b) <= max_ulp * ulp).all(), float((np.abs(a - b) / ulp).max())
+        tol = np.where(b >= 1e-30, max_ulp, max(max_ulp, 2048)) if other is plain else max_ulp
+        assert (np.abs(a - b) <= tol * ulp).all(), float((np.abs(a - b) / ulp).max())
         assert (a == b).mean() >= same
         np.testing.assert_allclose(on["charges"], other["charges"], rtol=0, atol=5e-14)
         np.testing.assert_allclose(on["propars"], other["propars"], rtol=1e-13)

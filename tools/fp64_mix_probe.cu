@@ -10,8 +10,8 @@ using namespace hp;
 
 // STAGE 1: Horner only (11 DFMA)   2: + range reduction & exponent splice (16)   3: + sqrt_fast (21)
 //       4: + distance (27)         5: + A*e and the two accumulating adds (30) = the kernel's fast path
-template <int STAGE, int NP>
-__global__ void __launch_bounds__(256) mix(int iters, const double* in, double* sink) {
+template <int STAGE, int NP, int MINB = 1>
+__global__ void __launch_bounds__(128 * (MINB > 1 ? 1 : 2), MINB) mix(int iters, const double* in, double* sink) {
     double x[NP], y[NP], z[NP], pro[NP];
     for (int j = 0; j < NP; ++j) {
         x[j] = in[j] + threadIdx.x * 1e-3;
@@ -67,7 +67,7 @@ __global__ void __launch_bounds__(256) mix(int iters, const double* in, double* 
     if (s == 123.456) sink[0] = s;
 }
 
-template <int STAGE, int NP>
+template <int STAGE, int NP, int MINB = 1>
 void run(int threads, int bps, const double* in, double* sink) {
     // FP64 instructions per point and iteration (counted from the source; +1 accumulate)
     const int fp64_per_point[9] = {0, 13, 18, 23, 28, 31, 23, 18, 30};
@@ -77,17 +77,22 @@ void run(int threads, int bps, const double* in, double* sink) {
     cudaEvent_t e0, e1;
     cudaEventCreate(&e0);
     cudaEventCreate(&e1);
-    mix<STAGE, NP><<<sms * bps, threads>>>(iters / 10, in, sink);
+    int occ = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, mix<STAGE, NP, MINB>, threads, 0);
+    cudaFuncAttributes fa;
+    cudaFuncGetAttributes(&fa, mix<STAGE, NP, MINB>);
+    if (occ < bps) printf("(occupancy %d blocks/SM < %d requested, %d regs) ", occ, bps, fa.numRegs);
+    mix<STAGE, NP, MINB><<<sms * bps, threads>>>(iters / 10, in, sink);
     cudaEventRecord(e0);
-    mix<STAGE, NP><<<sms * bps, threads>>>(iters, in, sink);
+    mix<STAGE, NP, MINB><<<sms * bps, threads>>>(iters, in, sink);
     cudaEventRecord(e1);
     cudaEventSynchronize(e1);
     float ms;
     cudaEventElapsedTime(&ms, e0, e1);
     const double warp_instr = double(fp64_per_point[STAGE]) * NP * iters * (threads / 32) * bps;  // per SM
     const double cycles = ms * 1e-3 * 1.965e9;
-    printf("stage %d, %d points/thread, %2d warps/SM: %.3f FP64 instr/cycle/SM = %.1f %% of 2.0\n", STAGE, NP,
-           threads * bps / 32, warp_instr / cycles, 50.0 * warp_instr / cycles);
+    printf("stage %d, %d points/thread, %2d warps/SM (%d chains/SMSP, %d regs): %.3f FP64 instr/cycle/SM = %.1f %% of 2.0\n", STAGE, NP,
+           threads * bps / 32, NP * threads * bps / 128, fa.numRegs, warp_instr / cycles, 50.0 * warp_instr / cycles);
 }
 
 int main() {
@@ -104,5 +109,8 @@ int main() {
     run<6, 4>(128, 4, in, sink); run<7, 4>(128, 4, in, sink); run<4, 4>(128, 4, in, sink); run<5, 4>(128, 4, in, sink);
     run<5, 4>(128, 3, in, sink); run<5, 8>(256, 1, in, sink);
     run<8, 8>(128, 2, in, sink); run<8, 4>(128, 4, in, sink); run<5, 8>(128, 1, in, sink); run<5, 8>(64, 2, in, sink);
+    // more independent chains in flight per scheduler (the FP64 dependent-issue latency is ~36 cycles)
+    run<5, 8, 3>(128, 3, in, sink); run<5, 6, 4>(128, 4, in, sink); run<5, 5, 4>(128, 4, in, sink); run<5, 4, 6>(128, 6, in, sink);
+    run<8, 8, 3>(128, 3, in, sink); run<8, 6, 4>(128, 4, in, sink); run<5, 3, 8>(128, 8, in, sink); run<1, 8, 4>(128, 4, in, sink);
     return 0;
 }
