@@ -235,6 +235,8 @@ def main():
     ap.add_argument("--cpu-reps", type=int, default=48, help="passes over the CPU sample (48: about 15 s of CPU work)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-unscreened", action="store_true", help="skip the extra run with atom screening off")
+    ap.add_argument("--no-extras", action="store_true",
+                    help="skip the config 1-4 blocks (tools/cases.py: small-system wall time, spline / aLISA / Hessian rooflines)")
     ap.add_argument("--pinned-inputs", action="store_true",
                     help="keep the host input arrays of the end-to-end arm in page-locked memory")
     ap.add_argument("--local-radius", type=float, default=16.0,
@@ -488,10 +490,19 @@ def main():
         "hbm_gbs_achieved": hbm_bytes / (kernel_ms_mean * 1e-3) / 1e9, "hbm_gbs_peak": hbm_peak,
         "hbm_bytes_algorithmic": hbm_bytes,
         "hbm_peak_source": "MEASURED_PEAKS.json" if peaks else "fallback 6650",
-        "traffic": 0.966 * hbm_bytes,
-        "traffic_source": "dram__bytes_read+write of the ncu --set full capture (profiles/r1_final_promol_weights_ncu_full.txt: "
-                          "945 MB vs 978 MB algorithmic at 600 atoms) scaled to this launch",
     }  # fmt: skip
+    # dram__bytes_read + write per launch from the committed `ncu --set full` capture of THIS kernel on THIS
+    # workload (profiles/r2_promol_weights_ncu_config5.json, written by tools/ncu_traffic.py); null if the
+    # capture does not match the launch (other natom / sharded run)
+    roofline["traffic"], roofline["traffic_source"] = None, None
+    try:
+        cap = json.load(open(os.path.join(ROOT, "profiles", "r2_promol_weights_ncu_config5.json")))
+        if int(cap.get("natom", -1)) == natom and world == 1:
+            roofline["traffic"] = float(cap["dram_bytes_read"]) + float(cap["dram_bytes_write"])
+            roofline["traffic_source"] = cap.get("source")
+            roofline["traffic_over_algorithmic"] = roofline["traffic"] / hbm_bytes
+    except Exception:
+        pass
     if shells_local is not None:
         dense_equiv = kernel_evals_per_s * F / 1e12
         roofline.update({
@@ -540,6 +551,21 @@ def main():
         "charges_sum": float(charges_resident.sum()), "charges_abs_sum": float(np.abs(charges_resident).sum()),
         "cutoff_mode": cutoff, "unscreened": unscreened,
     }  # fmt: skip
+    # ---- the other BASELINE.json configurations: timings + rooflines of their dominant kernels --------
+    if rank == 0 and world == 1 and not args.no_extras:
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        import cases
+
+        extras = {}
+        for name, fn in (("config1", lambda: cases.config1(dev)), ("config2", lambda: cases.config2(dev, peak=fp64_peak_tflops)),
+                         ("config3", lambda: cases.config3(dev, peak=fp64_peak_tflops)),
+                         ("config4", lambda: cases.config4(dev, peak=fp64_peak_tflops))):  # fmt: skip
+            try:
+                extras[name] = fn()
+            except Exception as exc:  # an extra must never cost the headline line
+                extras[name] = {"error": f"{type(exc).__name__}: {exc}"}
+            torch.cuda.empty_cache()
+        line["configs_1_to_4"] = extras
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(coords, numbers, grid, os.cpu_count() or 1, points_per_core=args.cpu_points, reps=args.cpu_reps)
     if rank == 0:

@@ -236,6 +236,7 @@ class GridSlab:
                 rad_r2w.append(r**2 * w)  # qc-grid integrate_angular_coordinates
             cat = lambda xs: np.concatenate(xs) if xs else np.zeros(0)  # noqa: E731
             self.rad_offsets_host = np.asarray(rad_off, dtype=np.int32)
+            self.nrad_max = int(np.max(np.diff(self.rad_offsets_host), initial=1))
             self.rad_r_host, self.rad_w_host, self.rad_w4_host = cat(rad_r), cat(rad_w), cat(rad_w4)
             self.nshell = len(shell_off) - 1
             self.shell_point_offsets = up(np.asarray(shell_off, dtype=np.int64), np.int64)

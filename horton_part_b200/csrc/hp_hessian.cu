@@ -12,7 +12,10 @@
 //   3. hessian_finish_kernel  H = sum_s C_s in a fixed order, mirrored to the lower triangle.
 // Every element of every partial matrix is owned by exactly one block, so the result is
 // bit-reproducible.  Bound: FP64 pipe, M(M+1) Npts flop (unit U2); B200 has no
-// tcgen05 FP64 kind and its DMMA rate equals the vector rate, so plain DFMA is used.
+// tcgen05 FP64 kind; the tile product runs on the FP64 tensor cores (mma.sync m8n8k4 = DMMA, see
+// syrk_panel_dmma_kernel), the DFMA micro-kernel is kept behind HP_B200_HESSIAN_DFMA=1 for A/B runs.
+#include <cstdlib>
+
 #include "hp_common.cuh"
 #include "hp_math.cuh"
 
@@ -150,6 +153,102 @@ syrk_panel_kernel(const double* __restrict__ Gu, int Mpad, int pc_sub, const int
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// FP64 tensor-core version of the tile product (mma.sync.m8n8k4.f64 = DMMA.8x8x4): one DMMA does the
+// work of eight warp-wide DFMAs with a single issue slot, which is what the DFMA micro-kernel above
+// runs out of (FP64 instructions occupy the issue port for two cycles: ncu showed 68.8 % pipe
+// utilisation with the math-pipe throttle as top stall, i.e. contraction-bound -- SURVEY.md 8d's
+// condition for trying the tensor path; tools/dmma_probe.cu is the measurement behind the choice).
+//   block tile 128 x 128, 8 warps as 2 (rows) x 4 (columns), warp tile 64 x 32 = 8 x 4 DMMA tiles;
+//   per 4-point k-step a warp loads 8 + 4 operand doubles per lane from shared memory for 32 DMMAs;
+//   the slab stride is padded to 132 doubles (= 4 mod 16): the fragment pattern
+//   (k = lane % 4, column = lane / 4) is then bank-conflict-free.
+// Fragment layout (PTX ISA, mma.m8n8k4 .f64): A row-major a0 = A[lane/4][lane%4], B column-major
+// b0 = B[lane%4][lane/4], C c0,c1 = C[lane/4][2 (lane%4) + 0,1].  Here A[m][k] = Gu[p0+k][row0+m] and
+// B[k][n] = Gu[p0+k][col0+n]: both operands are read from the same point-major slab.
+// ---------------------------------------------------------------------------------------------
+constexpr int kDK = 16;            // points per shared-memory slab
+constexpr int kDStride = kHT + 4;  // padded row length of a slab row (doubles)
+constexpr int kDStages = 3;
+
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
+__global__ void __launch_bounds__(256)
+syrk_panel_dmma_kernel(const double* __restrict__ Gu, int Mpad, int pc_sub, const int2* __restrict__ tiles,
+                       double* __restrict__ Cpart) {
+    extern __shared__ __align__(16) double smem_syrk[];  // [stage][A|B][kDK][kDStride]
+    auto As = [&](int st, int kk) { return smem_syrk + ((st * 2 + 0) * kDK + kk) * kDStride; };
+    auto Bs = [&](int st, int kk) { return smem_syrk + ((st * 2 + 1) * kDK + kk) * kDStride; };
+    const int2 tile = tiles[blockIdx.x];
+    const int s = blockIdx.y;
+    const double* panel = Gu + int64_t(s) * pc_sub * Mpad;
+    double* C = Cpart + int64_t(s) * Mpad * Mpad;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int gid = lane >> 2, tig = lane & 3;
+    const int wrow = (warp >> 2) * 64, wcol = (warp & 3) * 32;
+    double acc[8][4][2];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+    auto issue = [&](int st, int k0) {
+#pragma unroll
+        for (int j = 0; j < (kDK * kHT) / (2 * 256); ++j) {
+            const int idx = (threadIdx.x + j * 256) * 2;  // double index within the (unpadded) slab
+            const int kk = idx / kHT, mm = idx % kHT;
+            const double* src = panel + int64_t(k0 + kk) * Mpad;
+            cp_async16(As(st, kk) + mm, src + tile.x * kHT + mm);
+            cp_async16(Bs(st, kk) + mm, src + tile.y * kHT + mm);
+        }
+        cp_async_commit();
+    };
+
+    const int nslab = pc_sub / kDK;
+    for (int pre = 0; pre < kDStages - 1; ++pre) {
+        if (pre < nslab) issue(pre, pre * kDK);
+        else cp_async_commit();
+    }
+    for (int sl = 0; sl < nslab; ++sl) {
+        const int st = sl % kDStages;
+        cp_async_wait<kDStages - 2>();
+        __syncthreads();  // slab `sl` has landed for every thread; slab sl-1 is consumed by everyone
+        if (sl + kDStages - 1 < nslab) issue((sl + kDStages - 1) % kDStages, (sl + kDStages - 1) * kDK);
+        else cp_async_commit();
+#pragma unroll
+        for (int k4 = 0; k4 < kDK; k4 += 4) {
+            const double* ar = As(st, k4 + tig) + wrow + gid;
+            const double* br = Bs(st, k4 + tig) + wcol + gid;
+            double a[8], b[4];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) a[i] = ar[8 * i];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) b[j] = br[8 * j];
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+        }
+    }
+    cp_async_wait<0>();
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int row = tile.x * kHT + wrow + 8 * i + gid;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int col = tile.y * kHT + wcol + 8 * j + 2 * tig;
+            double2* dst = reinterpret_cast<double2*>(&C[int64_t(row) * Mpad + col]);
+            double2 v = *dst;
+            v.x += acc[i][j][0];
+            v.y += acc[i][j][1];
+            *dst = v;
+        }
+    }
+}
+
 __global__ void __launch_bounds__(256)
 hessian_finish_kernel(int M, int Mpad, int nsplit, const double* __restrict__ Cpart,
                       double* __restrict__ H) {
@@ -160,6 +259,18 @@ hessian_finish_kernel(int M, int Mpad, int nsplit, const double* __restrict__ Cp
     double s = 0.0;
     for (int k = 0; k < nsplit; ++k) s += Cpart[int64_t(k) * Mpad * Mpad + int64_t(r) * Mpad + c];
     H[idx] = s;
+}
+
+// tiles[k] = (i, j), i <= j, row-major over the upper triangle of the nt x nt tile grid
+__global__ void tile_list_kernel(int nt, int2* __restrict__ tiles) {
+    for (int k = threadIdx.x; k < nt * (nt + 1) / 2; k += blockDim.x) {
+        int i = 0, rem = k;
+        while (rem >= nt - i) {
+            rem -= nt - i;
+            ++i;
+        }
+        tiles[k] = make_int2(i, i + rem);
+    }
 }
 
 static int hessian_mpad(int M) { return ((M + kHT - 1) / kHT) * kHT; }
@@ -181,9 +292,11 @@ static int hessian_split(int ntile) {
     return best;
 }
 
-// points per chunk: bounded panel size (<= 512 MB) and a multiple of nsplit * kHK
+// points per chunk: the panel (pc x Mpad doubles) is written by one kernel and read ~2 Mpad/128 times by the
+// next: keep it inside the 126 MB L2 (<= 64 MB) so that those reads never go to HBM; a multiple of
+// nsplit * kHK
 static int hessian_chunk_points(int Mpad, int nsplit) {
-    int64_t pc = (int64_t(512) << 20) / (int64_t(Mpad) * 8);
+    int64_t pc = (int64_t(64) << 20) / (int64_t(Mpad) * 8);
     if (pc > 65536) pc = 65536;
     const int q = nsplit * kHK;
     pc = (pc / q) * q;
@@ -222,22 +335,26 @@ extern "C" int hp_hessian(int functor, int64_t npts, const double* px, const dou
     double* panel = static_cast<double*>(scratch);
     double* parts = panel + size_t(pc) * Mpad;
     int2* tiles = reinterpret_cast<int2*>(parts + size_t(nsplit) * Mpad * Mpad);
-    const size_t syrk_smem = sizeof(double) * 2 * 2 * kHK * kHT;
+    // tensor-core (DMMA) tile product by default; HP_B200_HESSIAN_DFMA=1 selects the vector-FMA kernel
+    static const bool use_dfma = [] { const char* e = getenv("HP_B200_HESSIAN_DFMA"); return e && e[0] == '1'; }();
+    const size_t syrk_smem = use_dfma ? sizeof(double) * 2 * 2 * kHK * kHT
+                                      : sizeof(double) * kDStages * 2 * kDK * kDStride;
     {
-        int rc0 = check_cuda(cudaFuncSetAttribute(syrk_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                  int(syrk_smem)), "cudaFuncSetAttribute");
-        if (rc0) return rc0;
+        static bool configured = false;  // attributes are per function, set once per process
+        if (!configured) {
+            int rc0 = check_cuda(cudaFuncSetAttribute(syrk_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                      int(sizeof(double) * 2 * 2 * kHK * kHT)), "cudaFuncSetAttribute");
+            if (rc0) return rc0;
+            rc0 = check_cuda(cudaFuncSetAttribute(syrk_panel_dmma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                  int(sizeof(double) * kDStages * 2 * kDK * kDStride)), "cudaFuncSetAttribute");
+            if (rc0) return rc0;
+            configured = true;
+        }
     }
-    // tile list (upper triangle), built on the host
-    int2* host_tiles = new int2[ntile];
-    int k = 0;
-    for (int i = 0; i < nt; ++i)
-        for (int j = i; j < nt; ++j) host_tiles[k++] = make_int2(i, j);
-    int rc = check_cuda(cudaMemcpyAsync(tiles, host_tiles, sizeof(int2) * ntile, cudaMemcpyHostToDevice, st),
-                        "tile list copy");
-    if (rc == HP_OK) rc = check_cuda(cudaStreamSynchronize(st), "tile list sync");
-    delete[] host_tiles;
-    if (rc) return rc;
+    // tile list (upper triangle), written on the device: no host allocation, copy or synchronisation
+    tile_list_kernel<<<1, 256, 0, st>>>(nt, tiles);
+    HP_LAUNCH_CHECK("tile_list_kernel");
+    int rc = HP_OK;
     rc = check_cuda(cudaMemsetAsync(parts, 0, sizeof(double) * nsplit * size_t(Mpad) * Mpad, st), "memset");
     if (rc) return rc;
     for (int64_t p0 = 0; p0 < npts; p0 += pc) {
@@ -262,7 +379,8 @@ extern "C" int hp_hessian(int functor, int64_t npts, const double* px, const dou
                 return HP_ERR_ARG;
         }
         HP_LAUNCH_CHECK("basis_chunk_kernel");
-        syrk_panel_kernel<<<dim3(ntile, nsplit), 256, syrk_smem, st>>>(panel, Mpad, pc_sub, tiles, parts);
+        if (use_dfma) syrk_panel_kernel<<<dim3(ntile, nsplit), 256, syrk_smem, st>>>(panel, Mpad, pc_sub, tiles, parts);
+        else syrk_panel_dmma_kernel<<<dim3(ntile, nsplit), 256, syrk_smem, st>>>(panel, Mpad, pc_sub, tiles, parts);
         HP_LAUNCH_CHECK("syrk_panel_kernel");
     }
     const int64_t total = int64_t(M) * M;

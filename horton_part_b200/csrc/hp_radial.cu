@@ -272,6 +272,219 @@ mbis_radial_kernel(int natom, int atom_base, const int* __restrict__ rad_off, co
 }
 
 // ---------------------------------------------------------------------------------------------
+// MBIS / NLIS radial fixed point, one BLOCK of 128 threads per atom (<= 256 radial points): the same
+// arithmetic per point as the one-warp kernels above/below, but a thread owns at most two radial points
+// instead of five to eight, and the 2K+1 sums of an inner iteration are reduced by warp butterflies +
+// one barrier.  The inner loop is a chain of ~30-100 strictly sequential steps per outer iteration, each
+// bounded by the latency of exp + two divisions; with one warp per atom that chain was 65 % of the GPU
+// time of a small system (round-1 smoke profile).  NLIS = true: shells (N, S, n), nlis.py:99-194.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ double pow_order(double r, double n);
+
+constexpr int kRadThreads = 128;
+constexpr int kRadWarps = kRadThreads / 32;
+constexpr int kRadOwn = 2;  // radial points per thread
+
+template <bool NLIS>
+__global__ void __launch_bounds__(kRadThreads)
+shell_fixed_point_block_kernel(int natom, int atom_base, const int* __restrict__ rad_off,
+                               const double* __restrict__ rad_r, const double* __restrict__ rad_w4,
+                               const double* __restrict__ sph, const int* __restrict__ par_off,
+                               double* __restrict__ propars, const int* __restrict__ shell_off,
+                               const double* __restrict__ inv_gamma, const double* __restrict__ pseudo,
+                               double threshold, double density_cutoff, int max_inner,
+                               double* __restrict__ charges, double* __restrict__ msd,
+                               int* __restrict__ niter_out, uint32_t* __restrict__ flags_out) {
+    constexpr int NV = 2 * kMaxMbisShells + 1;  // (m0, m1) per shell | change term (also used for pop / dev)
+    __shared__ double s_part[2][kRadWarps][NV];
+    if (int(blockIdx.x) >= natom) return;
+    const int a = atom_base + blockIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int r0 = rad_off[blockIdx.x], nrad = rad_off[blockIdx.x + 1] - r0;
+    constexpr int PW = NLIS ? 3 : 2;
+    const int p0 = par_off[a], K = (par_off[a + 1] - p0) / PW;
+    const double* ig = NLIS ? inv_gamma + shell_off[a] : nullptr;
+
+    double N[kMaxMbisShells], S[kMaxMbisShells], n[kMaxMbisShells], G[kMaxMbisShells], N0[kMaxMbisShells],
+        S0[kMaxMbisShells];
+#pragma unroll
+    for (int k = 0; k < kMaxMbisShells; ++k) {
+        N[k] = S[k] = 0.0;
+        n[k] = G[k] = 1.0;
+        if (k < K) {
+            N[k] = propars[p0 + PW * k];
+            S[k] = propars[p0 + PW * k + 1];
+            if (NLIS) {
+                n[k] = propars[p0 + 3 * k + 2];
+                G[k] = ig[k];
+            }
+        }
+        N0[k] = N[k];
+        S0[k] = S[k];
+    }
+    double ri[kRadOwn], wi[kRadOwn], rhoi[kRadOwn], oldpro[kRadOwn];
+    bool live[kRadOwn];
+#pragma unroll
+    for (int q = 0; q < kRadOwn; ++q) {
+        const int i = tid + q * kRadThreads;
+        live[q] = i < nrad;
+        ri[q] = live[q] ? rad_r[r0 + i] : 1.0;
+        wi[q] = live[q] ? rad_w4[r0 + i] : 0.0;
+        rhoi[q] = live[q] ? sph[r0 + i] : 0.0;
+        oldpro[q] = 0.0;
+    }
+    // all-reduce of per-thread values: butterflies, one barrier, fixed summation order.  Slots 0..2K-1 hold
+    // (m0, m1) per shell, slot CHG the change term; every loop is unrolled so that `v` stays in registers.
+    constexpr int CHG = 2 * kMaxMbisShells;
+    int parity = 0;
+    auto block_allsum = [&](double (&v)[NV], int nshell2) {
+#pragma unroll
+        for (int j = 0; j < NV; ++j) {
+            if (j < nshell2 || j == CHG) {
+#pragma unroll
+                for (int off = 16; off > 0; off >>= 1) v[j] += __shfl_xor_sync(0xffffffffu, v[j], off);
+                if (lane == 0) s_part[parity][warp][j] = v[j];
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < NV; ++j) {
+            if (j < nshell2 || j == CHG) {
+                double t = s_part[parity][0][j];
+#pragma unroll
+                for (int wq = 1; wq < kRadWarps; ++wq) t += s_part[parity][wq][j];
+                v[j] = t;
+            }
+        }
+        parity ^= 1;  // the next reduction writes the other buffer: no second barrier needed
+    };
+
+    // MBIS: one shell's pro-atom term N S^3 exp(-S r) / (8 pi) (mbis.py:128).  NLIS: the normalised shell
+    // function WITHOUT its population, n S^(3/n) exp(-S r^n) / (4 pi Gamma(3/n)) (nlis.py:147).
+    auto shell_term = [&](int k, double Nk, double Sk, double r, double& rn) -> double {
+        if (!NLIS) {
+            rn = r;
+            return Nk * (Sk * Sk * Sk) * exp(-Sk * r) / kEightPi;
+        }
+        rn = pow_order(r, n[k]);
+        return n[k] * pow(Sk, 3.0 / n[k]) * exp(-Sk * rn) * G[k] / kFourPi;
+    };
+
+    double red[NV];
+#pragma unroll
+    for (int j = 0; j < NV; ++j) red[j] = 0.0;
+#pragma unroll
+    for (int q = 0; q < kRadOwn; ++q) red[CHG] += wi[q] * rhoi[q];  // mbis.py:122, :201
+    block_allsum(red, 0);
+    const double pop = red[CHG];
+
+    uint32_t flags = HP_SOLVE_NOT_CONVERGED;
+    int it = 0;
+    for (; it < max_inner; ++it) {
+#pragma unroll
+        for (int j = 0; j < NV; ++j) red[j] = 0.0;
+#pragma unroll
+        for (int q = 0; q < kRadOwn; ++q) {
+            double term[kMaxMbisShells], rn[kMaxMbisShells];
+            double pro = 0.0;
+#pragma unroll
+            for (int k = 0; k < kMaxMbisShells; ++k) {
+                term[k] = 0.0;
+                rn[k] = 0.0;
+                if (k < K) {
+                    term[k] = shell_term(k, N[k], S[k], ri[q], rn[k]);
+                    pro += NLIS ? term[k] * N[k] : term[k];  // nlis.py:150
+                }
+            }
+            const bool sick = (rhoi[q] < density_cutoff) || (pro < density_cutoff);
+            const double ratio = sick ? 0.0 : rhoi[q] / pro;
+#pragma unroll
+            for (int k = 0; k < kMaxMbisShells; ++k) {
+                if (k < K) {
+                    const double tr = term[k] * ratio;
+                    red[2 * k] += NLIS ? wi[q] * (tr * N[k]) : wi[q] * tr;  // nlis.py:166 / mbis.py:143
+                    red[2 * k + 1] += wi[q] * tr * rn[k];                   // nlis.py:167 / mbis.py:144
+                }
+            }
+            if (it > 0) {
+                const double e = oldpro[q] - pro;
+                red[CHG] += wi[q] * e * e;  // mbis.py:151-152
+            }
+            oldpro[q] = pro;
+        }
+        block_allsum(red, 2 * K);
+#pragma unroll
+        for (int k = 0; k < kMaxMbisShells; ++k) {
+            if (k < K) {
+                const double a0 = red[2 * k], a1 = red[2 * k + 1];
+                if (!NLIS) {
+                    N[k] = a0;                 // mbis.py:145
+                    S[k] = 3.0 * a0 / a1;      // mbis.py:146
+                } else {
+                    N[k] = a0;
+                    // nlis.py:170-176: np.isclose(m1, 0) -> |m1| <= 1e-8
+                    S[k] = (fabs(a1) <= 1e-8) ? 1e-5 : 3.0 / (a1 * n[k]);
+                }
+            }
+        }
+        const double change = (it == 0) ? 1e100 : sqrt(red[CHG]);
+        if (change < threshold) {
+            flags &= ~HP_SOLVE_NOT_CONVERGED;
+            ++it;
+            break;
+        }
+    }
+
+    double nsum = 0.0;
+    bool finite = true;
+#pragma unroll
+    for (int k = 0; k < kMaxMbisShells; ++k) {
+        if (k < K) {
+            nsum += N[k];
+            finite = finite && isfinite(N[k]) && isfinite(S[k]);
+        }
+    }
+    if (!(fabs(pop - nsum) <= 1e-4 + 1e-5 * fabs(nsum))) flags |= HP_SOLVE_POP_MISMATCH;  // mbis.py:157
+    if (!finite) flags |= HP_SOLVE_NONFINITE;
+
+    // this atom's contribution to compute_change (core/iterstock.py:36-44)
+    red[CHG] = 0.0;
+#pragma unroll
+    for (int q = 0; q < kRadOwn; ++q) {
+        double ynew = 0.0, yold = 0.0, rn;
+#pragma unroll
+        for (int k = 0; k < kMaxMbisShells; ++k) {
+            if (k < K) {
+                if (!NLIS) {
+                    ynew += shell_term(k, N[k], S[k], ri[q], rn);
+                    yold += shell_term(k, N0[k], S0[k], ri[q], rn);
+                } else {  // nlis.py:296-299
+                    rn = pow_order(ri[q], n[k]);
+                    ynew += N[k] * n[k] * pow(S[k], 3.0 / n[k]) * exp(-S[k] * rn) * G[k] / kFourPi;
+                    yold += N0[k] * n[k] * pow(S0[k], 3.0 / n[k]) * exp(-S0[k] * rn) * G[k] / kFourPi;
+                }
+            }
+        }
+        const double d = ynew - yold;
+        red[CHG] += wi[q] * d * d;
+    }
+    block_allsum(red, 0);
+    if (tid == 0) {
+#pragma unroll
+        for (int k = 0; k < kMaxMbisShells; ++k) {
+            if (k < K) {
+                propars[p0 + PW * k] = N[k];
+                propars[p0 + PW * k + 1] = S[k];
+            }
+        }
+        charges[a] = pseudo[a] - pop;  // mbis.py:203
+        msd[a] = red[CHG];
+        niter_out[a] = it;
+        flags_out[a] = flags;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // NLIS / GMBIS radial fixed point (nlis.py:99-194), one warp per atom.  Shells are (N, S, n) with
 // n fixed; inv_gamma[k] = 1/Gamma(3/n_k) comes from the host.
 // ---------------------------------------------------------------------------------------------
@@ -931,14 +1144,24 @@ extern "C" int hp_mbis_radial_solve(int32_t natom, int32_t atom_base, const int3
                                     const double* rad_w4, const double* sph_avg,
                                     const int32_t* par_offsets, double* propars,
                                     const double* pseudo_numbers, double inner_threshold,
-                                    double density_cutoff, int32_t max_inner, double* charges,
-                                    double* msd, int32_t* niter, uint32_t* flags, void* stream) {
+                                    double density_cutoff, int32_t max_inner, int32_t nrad_max,
+                                    double* charges, double* msd, int32_t* niter, uint32_t* flags,
+                                    void* stream) {
     HP_REQUIRE(natom >= 0, "bad sizes");
     if (natom == 0) return HP_OK;
     HP_REQUIRE(rad_offsets && rad_r && rad_w4 && sph_avg && par_offsets && propars &&
                    pseudo_numbers && charges && msd && niter && flags, "null input");
+    HP_REQUIRE(nrad_max > 0 && nrad_max <= 4096, "nrad_max must be in 1..4096");
     // shared memory: one double per radial point of the largest atom; the caller guarantees
     // nrad <= 4096 (checked on the Python side where the offsets live on the host)
+    static const bool force_warp = [] { const char* e = getenv("HP_B200_RADIAL_WARP"); return e && e[0] == '1'; }();
+    if (!force_warp && nrad_max <= kRadThreads * kRadOwn) {
+        shell_fixed_point_block_kernel<false><<<natom, kRadThreads, 0, as_stream(stream)>>>(
+            natom, atom_base, rad_offsets, rad_r, rad_w4, sph_avg, par_offsets, propars, nullptr, nullptr,
+            pseudo_numbers, inner_threshold, density_cutoff, max_inner, charges, msd, niter, flags);
+        HP_LAUNCH_CHECK("shell_fixed_point_block_kernel<mbis>");
+        return HP_OK;
+    }
     const size_t smem = sizeof(double) * 4096;
     mbis_radial_kernel<<<natom, 32, smem, as_stream(stream)>>>(
         natom, atom_base, rad_offsets, rad_r, rad_w4, sph_avg, par_offsets, propars, pseudo_numbers,
@@ -961,13 +1184,23 @@ extern "C" int hp_nlis_radial_solve(int32_t natom, int32_t atom_base, const int3
                                     const int32_t* par_offsets, double* propars,
                                     const int32_t* shell_offsets, const double* inv_gamma,
                                     const double* pseudo_numbers, double inner_threshold,
-                                    double density_cutoff, int32_t max_inner, double* charges,
-                                    double* msd, int32_t* niter, uint32_t* flags, void* stream) {
+                                    double density_cutoff, int32_t max_inner, int32_t nrad_max,
+                                    double* charges, double* msd, int32_t* niter, uint32_t* flags,
+                                    void* stream) {
     HP_REQUIRE(natom >= 0, "bad sizes");
     if (natom == 0) return HP_OK;
     HP_REQUIRE(rad_offsets && rad_r && rad_w4 && sph_avg && par_offsets && propars &&
                    shell_offsets && inv_gamma && pseudo_numbers && charges && msd && niter && flags,
                "null input");
+    HP_REQUIRE(nrad_max > 0 && nrad_max <= 4096, "nrad_max must be in 1..4096");
+    static const bool force_warp = [] { const char* e = getenv("HP_B200_RADIAL_WARP"); return e && e[0] == '1'; }();
+    if (!force_warp && nrad_max <= kRadThreads * kRadOwn) {
+        shell_fixed_point_block_kernel<true><<<natom, kRadThreads, 0, as_stream(stream)>>>(
+            natom, atom_base, rad_offsets, rad_r, rad_w4, sph_avg, par_offsets, propars, shell_offsets, inv_gamma,
+            pseudo_numbers, inner_threshold, density_cutoff, max_inner, charges, msd, niter, flags);
+        HP_LAUNCH_CHECK("shell_fixed_point_block_kernel<nlis>");
+        return HP_OK;
+    }
     nlis_radial_kernel<<<natom, 32, sizeof(double) * 4096, as_stream(stream)>>>(
         natom, atom_base, rad_offsets, rad_r, rad_w4, sph_avg, par_offsets, propars, shell_offsets,
         inv_gamma, pseudo_numbers, inner_threshold, density_cutoff, max_inner, charges, msd, niter,

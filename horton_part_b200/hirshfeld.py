@@ -127,7 +127,7 @@ class HirshfeldWPart(DatabaseSplineMixin, AbstractStockholderWPart):
                  lmax=3, logger=None, grid_type=1, **kwargs):  # fmt: skip
         check_proatomdb(numbers, pseudo_numbers, proatomdb)
         self._proatomdb = proatomdb
-        device_kw = {k: kwargs[k] for k in ("device", "comm", "local_radius") if k in kwargs}
+        device_kw = {k: kwargs[k] for k in ("device", "comm", "local_radius", "device_loop") if k in kwargs}
         AbstractStockholderWPart.__init__(self, coordinates, numbers, pseudo_numbers, grid, moldens, spindens,
                                           lmax, logger, grid_type=grid_type, **device_kw)  # fmt: skip
 

@@ -29,7 +29,7 @@ class HirshfeldIWPart(DatabaseSplineMixin, AbstractISAWPart):
                  lmax=3, logger=None, threshold=1e-6, maxiter=500, grid_type=1, **kwargs):  # fmt: skip
         check_proatomdb(numbers, pseudo_numbers, proatomdb)
         self._proatomdb = proatomdb
-        device_kw = {k: kwargs[k] for k in ("device", "comm", "local_radius") if k in kwargs}
+        device_kw = {k: kwargs[k] for k in ("device", "comm", "local_radius", "device_loop") if k in kwargs}
         AbstractISAWPart.__init__(self, coordinates, numbers, pseudo_numbers, grid, moldens, spindens, lmax,
                                   logger, threshold, maxiter, grid_type=grid_type, **device_kw)  # fmt: skip
 

@@ -54,7 +54,7 @@ class NLISWPart(AbstractISAWPart):
                  nshell_dict=None, grid_type=1, **kwargs):  # fmt: skip
         self._exp_n_dict = exp_n_dict
         self._nshell_dict = nshell_dict or {}
-        device_kw = {k: kwargs[k] for k in ("device", "comm", "local_radius") if k in kwargs}
+        device_kw = {k: kwargs[k] for k in ("device", "comm", "local_radius", "device_loop") if k in kwargs}
         super().__init__(coordinates, numbers, pseudo_numbers, grid, moldens, spindens, lmax=lmax,
                          logger=logger, threshold=threshold, maxiter=maxiter,
                          inner_threshold=inner_threshold, grid_type=grid_type, **device_kw)  # fmt: skip
@@ -156,7 +156,7 @@ class NLISWPart(AbstractISAWPart):
         _lib.call(
             "hp_nlis_radial_solve", sh.nlocal, sh.atom_lo, slab.rad_offsets, slab.rad_r, slab.rad_w4,
             slab.sph_avg, self._par_offsets, st.propars, self._table.offsets, self._inv_gamma, self._pseudo,
-            float(self._inner_threshold), float(self.density_cutoff), int(self.max_inner), st.charges,
+            float(self._inner_threshold), float(self.density_cutoff), int(self.max_inner), slab.nrad_max, st.charges,
             st.msd, st.niter, st.flags, stream_ptr(slab.device),
         )  # fmt: skip
 

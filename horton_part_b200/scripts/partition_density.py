@@ -71,7 +71,23 @@ class _StoredAtomGrid(_Stored):
         super().__init__(points, weights)
         self.rgrid, self.center = rgrid, np.asarray(center, dtype=float)
         self.indices = np.asarray(indices, dtype=np.int64)
-        self.degrees = list(np.diff(self.indices))  # shell sizes (Lebedev point counts)
+        # Lebedev degree of every radial shell from its point count (qc-grid AtomGrid.degrees / l_max,
+        # read by do_density_decomposition, core/base.py:646-657)
+        from ..gridlite import _DEGREE_OF_SIZE
+
+        sizes = np.diff(self.indices)
+        unknown = sorted(set(int(n) for n in sizes) - set(_DEGREE_OF_SIZE))
+        if unknown:
+            raise ValueError(f"shell sizes {unknown} are not Lebedev-Laikov grid sizes")
+        self.degrees = [_DEGREE_OF_SIZE[int(n)] for n in sizes]
+
+    @property
+    def l_max(self):
+        return max(self.degrees)
+
+    @property
+    def n_shells(self):
+        return len(self.degrees)
 
 
 class _StoredMolGrid(_Stored):
@@ -182,8 +198,44 @@ def single_launch(settings, fn_in, fn_out, fn_log, logger):
         "history_charges": cache["history_charges"], "history_propars": cache["history_propars"],
         "history_entropies": cache["history_entropies"], "history_changes": cache["history_changes"],
     }  # fmt: skip
+    if settings["part_job_type"] == "do_density_decomposition":
+        # scripts/partition_density.py:290-322 of the reference: radial projections and the final basis
+        # table (order, exponent, population) of every atom
+        propars = np.asarray(cache["history_propars"])[-1, :]
+        for a in range(part.natom):
+            for key in (f"radial_points_{a}", f"spherical_average_{a}", f"radial_weights_{a}"):
+                out[key] = cache[key]
+            mine = propars[part._ranges[a] : part._ranges[a + 1]]
+            if kind in ("gisa", "lisa", "glisa"):
+                helper, z = part.bs_helper, int(part.numbers[a])
+                info = np.asarray([helper.orders[z], helper.exponents[z], helper.initials[z]], dtype=float).T
+                info[:, -1] = mine
+            elif kind == "mbis":
+                mine = mine.reshape((-1, 2))
+                info = np.ones((mine.shape[0], 3))
+                info[:, 1], info[:, 2] = mine[:, 1], mine[:, 0]
+            elif kind in ("gmbis", "nlis"):
+                mine = mine.reshape((-1, 3))
+                info = np.stack([mine[:, 2], mine[:, 1], mine[:, 0]], axis=1)
+            elif kind == "is":
+                info = mine
+            else:
+                raise NotImplementedError
+            out[f"bs_info_{a}"] = info
     for key in settings.get("save") or []:
-        if key in cache:
+        # nested attributes of the partitioning object in dot notation first, cache keys second
+        # (scripts/partition_density.py:324-340)
+        if isinstance(key, list):
+            key, value = tuple(key), None
+        else:
+            value = part
+            for attr in key.split("."):
+                value = getattr(value, attr, None)
+                if value is None:
+                    break
+        if isinstance(value, np.ndarray):
+            out[f"save/part.{key}"] = value
+        if value is None and key in cache:
             out[f"save/part.cache/{key}"] = cache[key]
     os.makedirs(os.path.dirname(os.path.abspath(fn_out)), exist_ok=True)
     np.savez_compressed(fn_out, **out)
