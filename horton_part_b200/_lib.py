@@ -107,6 +107,12 @@ EXPORTS = {
     "hp_host_is_pinned": (_int, [_p]),
     "hp_host_to_device": (_int, [_p, _p, _sz, _p, _sz, _i32, _p]),
     "hp_dfma_probe": (_int, [_i32, _p, _p, _p, _p]),
+    "hp_comm_nccl_version": (_i32, []),
+    "hp_comm_unique_id": (_int, [_p]),
+    "hp_comm_init": (_int, [_i32, _i32, _p, _p]),
+    "hp_comm_allreduce": (_int, [_p, _p, _i64, _i32, _p]),
+    "hp_comm_allgather": (_int, [_p, _p, _p, _i64, _p]),
+    "hp_comm_destroy": (_int, [_p]),
     "hp_loop_begin": (_int, [_p, _p]),
     "hp_loop_stamp": (_int, [_p, _p, _i32, _i32, _p, _p]),
     "hp_loop_commit": (_int, [_p, _i32, _p, _p, _f64, _i32, _p, _p, _p, _p]),
@@ -119,7 +125,7 @@ EXPORTS = {
 # int-returning functions whose result is a value, not a status code
 _NOT_STATUS = {"hp_abi_version", "hp_num_partials", "hp_local_index_scratch_bytes", "hp_last_error", "hp_tile_limits", "hp_molgrid_num_blocks", "hp_hessian_scratch_bytes",
                "hp_molgrid_update_tile_limits", "hp_host_is_pinned", "hp_local_tile_limits", "hp_local_chunk_points",
-               "hp_spline_integral_blocks", "hp_spline_lut_size", "hp_spline_tile_limits"}
+               "hp_spline_integral_blocks", "hp_spline_lut_size", "hp_spline_tile_limits", "hp_comm_nccl_version"}
 
 
 class HpError(RuntimeError):

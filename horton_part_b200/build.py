@@ -56,7 +56,7 @@ def build(force: bool = False, verbose: bool = False) -> pathlib.Path:
     cmd = [_nvcc(), *NVCC_FLAGS, "-I", str(ROOT / "include"), "-I", str(CSRC)]
     if verbose:
         cmd += ["-Xptxas", "-v"]
-    cmd += [str(s) for s in srcs] + ["-o", str(LIB)]
+    cmd += [str(s) for s in srcs] + ["-o", str(LIB), "-ldl"]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
         sys.stderr.write(res.stdout + res.stderr)

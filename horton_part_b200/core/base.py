@@ -9,7 +9,8 @@ cache are downloads of device results.  Additional keyword arguments of this imp
     local_radius   cut-off radius (bohr) of the local-grid mode: atom a contributes only to points
                with |r - R_a| <= local_radius (the reference's removed `radius_cutoff` design,
                core/stockholder.py:45-112; None/inf = dense = the reference's live behaviour)
-    comm       a ``torch.distributed`` process group: the grid is sharded by atom blocks over its
+    comm       a ``torch.distributed`` process group or a ``core.comm.HpComm`` (NCCL through the C ABI,
+               ``hp_comm_*``): the grid is sharded by atom blocks over its
                ranks and per-iteration results are exchanged with NCCL
 """
 
@@ -339,10 +340,10 @@ class WPart(Part):
 
             shard = None
             if self._comm is not None:
-                import torch.distributed as dist
+                from .comm import comm_rank, comm_world
 
-                shard = Shard(self.natom, self._grid.indices, dist.get_rank(self._comm),
-                              dist.get_world_size(self._comm), work=self._estimate_atom_work())  # fmt: skip
+                shard = Shard(self.natom, self._grid.indices, comm_rank(self._comm),
+                              comm_world(self._comm), work=self._estimate_atom_work())  # fmt: skip
             self._slab = GridSlab(self._grid, self._moldens, self.coordinates, self._device, shard,
                                   need_atgrids=self.local)  # fmt: skip
         return self._slab
@@ -363,9 +364,9 @@ class WPart(Part):
         _lib.call("hp_atom_moments", sh.nlocal, sh.atom_lo, lmax, seg, slab.px, slab.py, slab.pz, slab.atw,
                   slab.at_w, slab.rho, slab.atom_xyz, out, stream_ptr(slab.device))  # fmt: skip
         if self._comm is not None:
-            import torch.distributed as dist
+            from .comm import all_reduce
 
-            dist.all_reduce(out, group=self._comm)
+            all_reduce(self._comm, out)
         return out.cpu().numpy()
 
     def _atom_integrals(self, density):
@@ -384,7 +385,7 @@ class WPart(Part):
         _lib.call("hp_segment_integrate", sh.nlocal, seg.contiguous(), slab.atw, slab.at_w, dens,
                   out[sh.atom_lo : sh.atom_hi], stream_ptr(slab.device))  # fmt: skip
         if self._comm is not None:
-            import torch.distributed as dist
+            from .comm import all_reduce
 
-            dist.all_reduce(out, group=self._comm)
+            all_reduce(self._comm, out)
         return out.cpu().numpy()

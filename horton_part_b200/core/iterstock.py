@@ -68,9 +68,9 @@ class IterationState:
         self.propars[par_lo:par_hi] = self.propars_prev[par_lo:par_hi]
 
     def gather(self, comm):
-        import torch.distributed as dist
+        from .comm import all_reduce
 
-        dist.all_reduce(self.vec, op=dist.ReduceOp.SUM, group=comm)
+        all_reduce(comm, self.vec)
 
 
 class AbstractISAWPart(AbstractStockholderWPart):
@@ -156,10 +156,10 @@ class AbstractISAWPart(AbstractStockholderWPart):
         )  # fmt: skip
         out = mg["out"]
         if self._comm is not None:
-            import torch.distributed as dist
+            from .comm import all_reduce
 
             out = out.clone()
-            dist.all_reduce(out, group=self._comm)
+            all_reduce(self._comm, out)
         M = t.nshell
         return out[0 : 2 * M : 2], out[1 : 2 * M : 2], out[2 * M :: 2], out[2 * M + 1 :: 2]
 
@@ -210,9 +210,9 @@ class AbstractISAWPart(AbstractStockholderWPart):
         st.msd.copy_(msd)
         _lib.call("hp_sum_partials", slab.npartial, slab.entropy_partials, st.entropy, stream_ptr(dev))
         if self._comm is not None:
-            import torch.distributed as dist
+            from .comm import all_reduce
 
-            dist.all_reduce(st.entropy, group=self._comm)
+            all_reduce(self._comm, st.entropy)
         _lib.call("hp_finish_iteration", 1, st.entropy, self.natom, st.msd, st.out2, stream_ptr(dev))
         ev[2].record()
         nv = st.vec.numel()

@@ -161,9 +161,9 @@ class GlobalLinearISAWPart(AbstractStockholderWPart):
 
     def _all_reduce(self, tensor):
         if self._comm is not None:
-            import torch.distributed as dist
+            from .core.comm import all_reduce
 
-            dist.all_reduce(tensor, group=self._comm)
+            all_reduce(self._comm, tensor)
 
     def _promol_and_entropy(self):
         """rho0 = sum_m c_m g_m on the local slab (no 1e-100 offsets: calc_promol_dens) and the
@@ -365,9 +365,9 @@ class GlobalLinearISAWPart(AbstractStockholderWPart):
                   stream_ptr(s.device))  # fmt: skip
         bad = (flags != 0).any(dim=1).to(torch.int32)
         if self._comm is not None:
-            import torch.distributed as dist
+            from .core.comm import all_reduce
 
-            dist.all_reduce(bad, op=dist.ReduceOp.MAX, group=self._comm)
+            all_reduce(self._comm, bad, "max")
         return ~bad.bool().cpu().numpy()
 
     def is_promol_valid(self, propars, check_mono):
@@ -527,9 +527,9 @@ class GlobalLinearISAWPart(AbstractStockholderWPart):
             warnings.warn("WARNING: Not all pro-atom parameters are positive!")
         pmin = self.slab.promol.min().reshape(1) if self.slab.npts else torch.zeros(1, device=self.slab.device)
         if self._comm is not None:
-            import torch.distributed as dist
+            from .core.comm import all_reduce
 
-            dist.all_reduce(pmin, op=dist.ReduceOp.MIN, group=self._comm)
+            all_reduce(self._comm, pmin, "min")
         if float(pmin.item()) < -1e-12:
             raise RuntimeError("Negative pro-atom density found!")
         if abs(np.sum(propars) - self.mol_pop) > 1e-4:

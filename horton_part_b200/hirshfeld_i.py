@@ -122,9 +122,9 @@ class HirshfeldIWPart(DatabaseSplineMixin, AbstractISAWPart):
         _lib.call("hp_sum_partials", slab.npartial, slab.entropy_partials, self._scal, stream_ptr(dev))
         pack = torch.cat([self._pops, self._scal])
         if self._comm is not None:
-            import torch.distributed as dist
+            from .core.comm import all_reduce
 
-            dist.all_reduce(pack, group=self._comm)
+            all_reduce(self._comm, pack)
         ev[2].record()
         host = pack.cpu().numpy()
         if self._state is None:

@@ -452,6 +452,24 @@ HP_API int hp_loop_end(void* loop, void* stream);
 HP_API int hp_loop_launch(void* loop, void* stream);
 HP_API int hp_loop_destroy(void* loop, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * (section 8e) multi-GPU plumbing: NCCL behind the C ABI, for consumers that shard the grid by atom blocks
+ * without torch.distributed.  The reference has no communication layer; the exchange it would need is the
+ * per-iteration propars / charges / change terms / entropy of core/iterstock.py:132-149, 171-188 -- one sum
+ * all-reduce of the zero-filled state vector per iteration.  libnccl.so.2 is bound at run time (dlopen).
+ *   hp_comm_unique_id   rank 0: 128-byte NCCL id into id128_host; ship it to the other ranks on the host
+ *   hp_comm_init        every rank (its CUDA device current): *comm_out = communicator handle
+ *   hp_comm_allreduce   in place over `count` doubles on `stream`; op_max = 0: sum, 1: max
+ *   hp_comm_allgather   recv[r * count_per_rank ...] = send of rank r
+ *   hp_comm_destroy     releases the communicator;  hp_comm_nccl_version: NCCL_VERSION_CODE or 0 */
+HP_API int32_t hp_comm_nccl_version(void);
+HP_API int hp_comm_unique_id(void* id128_host);
+HP_API int hp_comm_init(int32_t world, int32_t rank, const void* id128_host, void** comm_out);
+HP_API int hp_comm_allreduce(void* comm, double* buf, int64_t count, int32_t op_max, void* stream);
+HP_API int hp_comm_allgather(void* comm, const double* send, double* recv, int64_t count_per_rank,
+                             void* stream);
+HP_API int hp_comm_destroy(void* comm);
+
 #ifdef __cplusplus
 }
 #endif

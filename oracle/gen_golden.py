@@ -658,15 +658,29 @@ def case_config2(natom=20, nrad=150, nang=194, seed=0):
          **{f"record/{k}": v for k, v in raw.items()})  # fmt: skip
 
 
-#: shells of the Hirshfeld-I variant of config 2: milder populations than synthetic.SLATER_SHELLS, because
-#: Hirshfeld-I amplifies charges and the reference's cached database stops at O(-1) / C(-1) / H(-1)
-#: (a charge beyond that raises KeyError in core/proatomdb.py:282)
-CONFIG2_HI_SHELLS = {1: ((0.95, 2.0),), 6: ((1.70, 11.3), (4.25, 1.9)), 8: ((1.65, 15.0), (6.45, 2.4))}
+#: target charges of the Hirshfeld-I variant of config 2 (per element)
+CONFIG2_HI_CHARGES = {1: 0.12, 6: 0.08, 8: -0.42}
+
+
+def database_promolecule(db, points, coords, numbers, charges):
+    """sum_a rho_db(Z_a, q_a)(|r - R_a|) with linearly interpolated charge states (hirshfeld_i.py:116-134):
+    a density for which Hirshfeld-I has the exact fixed point q_a.  `db` is a ProAtomDB (reference or
+    product: same get_spline API)."""
+    rho = np.zeros(len(points))
+    for R, z, q in zip(coords, numbers, charges):
+        ic = int(np.floor(q))
+        x = float(q - ic)
+        spline = db.get_spline(int(z), {ic: 1 - x, ic + 1: x} if x != 0.0 else {ic: 1.0})
+        rho += spline(np.linalg.norm(points - R, axis=1))
+    return rho
 
 
 def case_config2_hi(natom=20, nrad=150, nang=194, seed=0):
     """Hirshfeld-I at config-2 size: the same 20-atom chain with N replaced by O (the reference's cached
-    database has no N anion: atom_Z07_N08 is absent), promolecule of CONFIG2_HI_SHELLS, 582,000 points."""
+    database has no N anion: atom_Z07_N08 is absent), 582,000 points.  The density is the promolecule of
+    the DATABASE pro-atoms at the charges CONFIG2_HI_CHARGES: the Slater promolecule of the other cases
+    is too diffuse for the compact HF/STO-3G database atoms and drives oxygen beyond charge -1, where the
+    reference's database ends (KeyError (8, -2) in core/proatomdb.py:282)."""
     import contextlib
     import io
 
@@ -675,21 +689,22 @@ def case_config2_hi(natom=20, nrad=150, nang=194, seed=0):
     coords, numbers = synthetic.organic_like(natom, seed)
     numbers = np.where(numbers == 7, 8, numbers)
     grid = synthetic_grid(coords, numbers, nrad, nang)
-    rho = synthetic.slater_promolecule_host(grid.points, coords, numbers, shells=CONFIG2_HI_SHELLS)
     records, raw = _pack_records((1, 6, 8))
+    db = ProAtomDB(records)
+    q_gen = np.array([CONFIG2_HI_CHARGES[int(z)] for z in numbers])
+    rho = database_promolecule(db, grid.points, coords, numbers, q_gen)
     t0 = time.time()
     with contextlib.redirect_stdout(io.StringIO()):
-        part = wpart_schemes("hi")(coords, numbers, numbers.astype(float), grid, rho, proatomdb=ProAtomDB(records))
+        part = wpart_schemes("hi")(coords, numbers, numbers.astype(float), grid, rho, proatomdb=db)
         part.do_charges()
     res = _full_out(part, grid)
     res["seconds"] = np.float64(time.time() - t0)
     print(f"  config2 hi: niter={res.get('niter')} q={np.round(part['charges'][:6], 6)} {time.time() - t0:.0f} s", flush=True)
-    shells = {f"shells/Z{z}": np.asarray(v, float) for z, v in CONFIG2_HI_SHELLS.items()}
-    save("config2_hi.npz", {"hi": res}, coordinates=coords, numbers=numbers,
+    save("config2_hi.npz", {"hi": res}, coordinates=coords, numbers=numbers, generating_charges=q_gen,
          dens_sample=rho[::997].copy(), aim_weights_sample=grid.aim_weights[::997].copy(),
          grid_spec=np.array(f"BeckeRTransform(1e-4,1.5) o GaussChebyshev({nrad}) x Lebedev{nang}, BeckeWeights(); "
-                            f"synthetic.organic_like({natom}, {seed}) with N -> O"),
-         **shells, **{f"record/{k}": v for k, v in raw.items()})  # fmt: skip
+                            f"synthetic.organic_like({natom}, {seed}) with N -> O; density = database promolecule"),
+         **{f"record/{k}": v for k, v in raw.items()})  # fmt: skip
 
 
 def case_config3(natom=24, nrad=150, nang=194, seed=0, maxiter=500):

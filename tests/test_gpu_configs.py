@@ -2,7 +2,7 @@
 the UNMODIFIED reference on the real 150 x 194 grid (oracle/gen_golden.py: case_config2/3/4).
 
   config 2  20-atom organic-like chain, 582,000 points: MBIS, Hirshfeld, ISA at full size; Hirshfeld-I on
-            the same chain with N -> O and milder populations (the reference's database ends at charge -1)
+            the same chain with N -> O on a database promolecule (the reference's database ends at charge -1)
   config 3  aLISA `sc`, gauss and slater basis: 24-atom water cluster, 698,400 points, to convergence
   config 4  gLISA `newton` (exact Hessian) and `sc`: 12-atom peptide-like chain, 349,200 points
 
@@ -114,20 +114,27 @@ def test_config2_isa_full_size(config2):
 
 
 def test_config2_hirshfeld_i_full_size():
-    """Hirshfeld-I at config-2 size (oracle/gen_golden.py case_config2_hi: the chain with N -> O and milder
-    shell populations, because the reference's cached database ends at charge -1)."""
+    """Hirshfeld-I at config-2 size (oracle/gen_golden.py case_config2_hi: the chain with N -> O, density =
+    promolecule of the database pro-atoms at fixed charges, because the reference's cached database ends at
+    charge -1 and the diffuse Slater promolecule drives oxygen beyond it)."""
     from conftest import GOLDEN
-    from horton_part_b200 import HirshfeldIWPart, synthetic
+    from horton_part_b200 import HirshfeldIWPart
 
     if not (GOLDEN / "config2_hi.npz").exists():
         pytest.skip("tests/golden/config2_hi.npz not generated yet (oracle/gen_golden.py config2_hi)")
     z = np.load(GOLDEN / "config2_hi.npz")
     ref = _gold(z, "hi")
     coords, numbers = z["coordinates"], z["numbers"]
-    shells = {int(k.split("Z")[1]): tuple(map(tuple, z[k])) for k in z.files if k.startswith("shells/")}
     grid = _grid(coords, numbers)
-    rho = synthetic.slater_promolecule_host(grid.points, coords, numbers, shells=shells)
-    np.testing.assert_allclose(rho[::997], z["dens_sample"], rtol=1e-13)
+    # the density: promolecule of the database pro-atoms at the generating charges (gen_golden.database_promolecule)
+    db = _records(z)
+    rho = np.zeros(grid.size)
+    for R, zn, q in zip(coords, numbers, z["generating_charges"]):
+        ic = int(np.floor(q))
+        x = float(q - ic)
+        spline = db.get_spline(int(zn), {ic: 1 - x, ic + 1: x} if x != 0.0 else {ic: 1.0})
+        rho += spline(np.linalg.norm(grid.points - R, axis=1))
+    np.testing.assert_allclose(rho[::997], z["dens_sample"], rtol=1e-12, atol=1e-300)
     part = HirshfeldIWPart(coords, numbers, numbers.astype(float), grid, rho, _records(z))
     part.do_charges()
     assert part["niter"] == int(ref["niter"])

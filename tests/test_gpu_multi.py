@@ -72,6 +72,73 @@ def test_sharded_equals_single_gpu(make_water):
         assert np.array_equal(out[0][name][1], out[1][name][1])  # ranks agree bit for bit
 
 
+def _worker_hpcomm(rank, world, idfile, payload, out):
+    """Same run with the communicator of the C ABI (hp_comm_*): no torch.distributed anywhere; the NCCL id
+    travels through a file, as a launcher without any Python messaging layer would do it."""
+    import sys
+    import time
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, root)
+    import logging
+
+    import torch
+
+    logging.disable(logging.INFO)
+    torch.cuda.set_device(rank)
+    from horton_part_b200 import MBISWPart
+    from horton_part_b200.core.comm import HpComm
+
+    if rank == 0:
+        with open(idfile + ".tmp", "wb") as fh:
+            fh.write(HpComm.unique_id())
+        os.replace(idfile + ".tmp", idfile)
+    else:
+        for _ in range(600):
+            if os.path.exists(idfile):
+                break
+            time.sleep(0.05)
+    uid = open(idfile, "rb").read()
+    comm = HpComm(world, rank, uid, device=torch.device("cuda", rank))
+    coords, numbers, pseudo, grid, rho = payload
+    part = MBISWPart(coords, numbers, pseudo, grid, rho, device=torch.device("cuda", rank), comm=comm)
+    part.do_charges()
+    part.do_moments()
+    out[rank] = (int(part["niter"]), part["charges"].copy(), part["propars"].copy(), part["cartesian_multipoles"].copy())
+    comm.close()
+
+
+def test_sharded_through_the_c_abi_communicator(make_water, tmp_path):
+    import torch
+    import torch.multiprocessing as mp
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    from horton_part_b200 import MBISWPart
+
+    case = make_water(9, nrad=30, nang=38, seed=2)
+    payload = (case["coords"], case["numbers"], case["pseudo"], case["grid"], case["rho"])
+    out = mp.Manager().dict()
+    mp.spawn(_worker_hpcomm, args=(2, str(tmp_path / "nccl_id"), payload, out), nprocs=2, join=True)
+    single = MBISWPart(*payload)
+    single.do_charges()
+    single.do_moments()
+    for rank in (0, 1):
+        niter, charges, propars, moments = out[rank]
+        assert niter == single["niter"]
+        np.testing.assert_allclose(charges, single["charges"], rtol=0, atol=1e-12)
+        np.testing.assert_allclose(propars, single["propars"], rtol=1e-11, atol=1e-14)
+        np.testing.assert_allclose(moments, single["cartesian_multipoles"], rtol=1e-10, atol=1e-12)
+    assert np.array_equal(out[0][1], out[1][1])
+
+
+def test_c_abi_communicator_symbols_load():
+    """hp_comm_* bind NCCL at run time; on any GPU box the library must be found."""
+    from horton_part_b200 import _lib
+
+    assert int(_lib.call("hp_comm_nccl_version")) >= 20000
+
+
 def test_work_estimate_matches_the_kernel_counters(make_water):
     """estimate_dense_work (geometry only) against the pairs the screened dense pass really evaluates:
     same total to ~15 %, and per-rank loads of a work-balanced split within a few per cent."""

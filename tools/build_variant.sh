@@ -5,5 +5,5 @@ set -e
 name=$1; shift
 cd "$(dirname "$0")/.."
 nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -Xcompiler -fvisibility=hidden \
-    --shared -cudart shared -I include -I horton_part_b200/csrc "$@" horton_part_b200/csrc/*.cu -o horton_part_b200/libhp_${name}.so
+    --shared -cudart shared -I include -I horton_part_b200/csrc "$@" horton_part_b200/csrc/*.cu -o horton_part_b200/libhp_${name}.so -ldl
 echo horton_part_b200/libhp_${name}.so
