@@ -107,6 +107,7 @@ EXPORTS = {
     "hp_host_is_pinned": (_int, [_p]),
     "hp_host_to_device": (_int, [_p, _p, _sz, _p, _sz, _i32, _p]),
     "hp_dfma_probe": (_int, [_i32, _p, _p, _p, _p]),
+    "hp_aim_on_points": (_int, [_int, _i64, _p, _p, _p, _i32, _p, _p, _p, _p, _p, _i32, _p, _p, _f64, _p, _p, _p, _p]),
     "hp_comm_nccl_version": (_i32, []),
     "hp_comm_unique_id": (_int, [_p]),
     "hp_comm_init": (_int, [_i32, _i32, _p, _p]),

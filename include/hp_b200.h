@@ -470,6 +470,18 @@ HP_API int hp_comm_allgather(void* comm, const double* send, double* recv, int64
                              void* stream);
 HP_API int hp_comm_destroy(void* comm);
 
+/* ------------------------------------------------------------------------------------------
+ * (section 8f-3) AIM quantities on the points of a uniform grid, the arrays behind `part-cube`
+ * (scripts/generate_cube.py:140-157, 213-227): rho0 (natom x npts, atom-major) = the pro-atoms from the shell
+ * table, promol = sum_a rho0_a + promol_offset (1e-100), aim_rho = rho0 / promol * density.  Same functors,
+ * shell table and atom tiling (hp_tile_limits) as hp_promol_weights.  rho0 / promol / aim_rho may be NULL
+ * when not wanted (aim_rho needs rho0). */
+HP_API int hp_aim_on_points(int functor, int64_t npts, const double* px, const double* py, const double* pz,
+                            int32_t natom, const double* atom_xyz, const int32_t* atom_shell_offsets,
+                            const double* shell_A, const double* shell_alpha, const double* shell_order,
+                            int32_t ntile, const int32_t* tile_atom_offsets, const double* density,
+                            double promol_offset, double* rho0, double* promol, double* aim_rho, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,6 +1,7 @@
 """AIM cube export (horton_part_b200/scripts/generate_cube.py): file format as the reference
 writes it (scripts/generate_cube.py:100-137), round trip, and the AIM arrays on a uniform grid for
-a promolecular density, where the weight functions reproduce the generating atoms.  CPU only."""
+a promolecular density, where the weight functions reproduce the generating atoms.  CPU only: the
+arrays come from the oracle's NumPy restatement here, tests/test_gpu_postproc.py checks the device kernel."""
 
 import numpy as np
 import pytest
@@ -65,7 +66,10 @@ def test_aim_arrays_of_a_promolecular_density(tmp_path):
     grid = gc.UniformGrid.from_molecule(numbers, coords, spacing=0.35, extension=6.0)
     pts = grid.points
     density = synthetic.expbasis_promolecule_host(pts, coords, numbers, helper, scale={8: 8.6, 1: 0.7})
-    out = gc.write_aim_cubes(str(tmp_path / "w"), numbers, numbers.astype(float), coords, grid, density, propars)
+    import cube_oracle  # the NumPy restatement of the reference's lines (oracle/); the product evaluates on the GPU
+
+    arrays = cube_oracle.aim_on_points(helper, numbers, coords, pts, density, propars)
+    out = gc.write_aim_cubes(str(tmp_path / "w"), numbers, numbers.astype(float), coords, grid, density, arrays=arrays)
     rho0, promol, aim = out["rho0"], out["promol"], out["aim_rho"]
     assert rho0.shape == aim.shape == (3, grid.size)
     # the density IS the promolecule of these coefficients: the AIM densities are the pro-atoms

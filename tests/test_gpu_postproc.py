@@ -110,3 +110,44 @@ def test_do_all_lists_output_keys(h2o):
     for expected in ("charges", "populations", "cartesian_multipoles", "pure_multipoles", "radial_moments",
                      "niter", "history_charges", ("density_decomposition", 0), ("spline_prodensity", 2)):  # fmt: skip
         assert expected in keys, expected
+
+
+@pytest.mark.parametrize("basis", ["gauss", "slater"])
+def test_aim_cube_arrays_on_the_device(tmp_path, basis):
+    """hp_aim_on_points against the NumPy restatement of the reference's part-cube lines (oracle/cube_oracle.py,
+    scripts/generate_cube.py:140-157, 213-227), then the `part-cube` program end to end."""
+    import cube_oracle
+    import yaml
+
+    from horton_part_b200 import synthetic
+    from horton_part_b200.core.basis import ExpBasisFuncHelper
+    from horton_part_b200.scripts import generate_cube as gc
+
+    coords, numbers = synthetic.water_cluster(6, 0)
+    helper = ExpBasisFuncHelper.from_function_type(basis)
+    rng = np.random.default_rng(7)
+    propars = np.concatenate([np.asarray(helper.get_initial(int(z)), float) * rng.uniform(0.5, 1.5, helper.get_nshell(int(z)))
+                              for z in numbers])  # fmt: skip
+    grid = gc.UniformGrid.from_molecule(numbers, coords, spacing=0.45, extension=5.0)
+    pts = grid.points
+    density = synthetic.expbasis_promolecule_host(pts, coords, numbers, ExpBasisFuncHelper.from_function_type("gauss"),
+                                                  scale={8: 8.6, 1: 0.7})  # fmt: skip
+    rho0, promol, aim = gc.aim_on_points(numbers, coords, pts, density, propars, basis, chunk=50000)  # several chunks
+    r0, p0, a0 = cube_oracle.aim_on_points(helper, numbers, coords, pts, density, propars)
+    np.testing.assert_allclose(rho0, r0, rtol=1e-12, atol=1e-300)
+    np.testing.assert_allclose(promol, p0, rtol=1e-12, atol=1e-300)
+    np.testing.assert_allclose(aim, a0, rtol=1e-12, atol=1e-300)
+    # the program: uniform-grid NPZ + part-dens output -> NPZ with the AIM arrays + cube files
+    fn_in, fn_part, fn_out = tmp_path / "grid.npz", tmp_path / "part.npz", tmp_path / "out" / "cube.npz"
+    np.savez(fn_in, atnums=numbers, atcorenums=numbers.astype(float), atcoords=coords, origin=grid.origin,
+             axes=grid.axes, shape=np.array(grid.shape), density=density)
+    np.savez(fn_part, history_propars=np.stack([propars * 0.9, propars]))
+    cfg = tmp_path / "cube.yaml"
+    cfg.write_text(yaml.safe_dump({"part-cube": {"inputs": [str(fn_in)], "partdens": [str(fn_part)],
+                                                 "outputs": [str(fn_out)], "basis_func": basis}}))
+    assert gc.main([str(cfg)]) == 0
+    out = np.load(fn_out)
+    np.testing.assert_allclose(out["aim_rho"], a0, rtol=1e-12, atol=1e-300)
+    back = gc.read_cube(tmp_path / "out" / "cube_rho0_3.cube")
+    np.testing.assert_allclose(back["data"], r0[3], rtol=1e-5, atol=1e-30)
+    assert (tmp_path / "out" / "cube_rho_mol.cube").exists() and (tmp_path / "out" / "cube_rho0_mol.cube").exists()
