@@ -354,7 +354,8 @@ class WPart(Part):
         from .device import stream_ptr
 
         if not self.local:
-            raise NotImplementedError("moments need atomic grids (grid_type 1 or 2)")
+            raise NotImplementedError("do_moments needs atomic grids (grid_type 1 or 2); with grid_type 3 the "
+                                      "reference integrates the multipoles on the molecular grid, which is not built")
         slab = self.slab
         sh = slab.shard
         lmax = int(self.lmax)
@@ -380,10 +381,25 @@ class WPart(Part):
         else:
             dens = to_device(np.asarray(density)[slab.point_base : slab.point_base + slab.npts], slab.device)
         sh = slab.shard
-        seg = slab.atom_point_offsets[sh.atom_lo : sh.atom_hi + 1] - slab.point_base
         out = torch.zeros(self.natom, dtype=torch.float64, device=slab.device)
-        _lib.call("hp_segment_integrate", sh.nlocal, seg.contiguous(), slab.atw, slab.at_w, dens,
-                  out[sh.atom_lo : sh.atom_hi], stream_ptr(slab.device))  # fmt: skip
+        if slab.atw is None:
+            # grid_type 3: no atomic grids -- the reference integrates w_a * density over the WHOLE molecular
+            # grid (core/base.py:287-298 with full-grid weights).  Exponential pro-atoms: regenerate the weight
+            # functions inside hp_atom_weight_integrals (no natom x Npts arrays).
+            t = getattr(self, "_table", None)
+            if t is None or not hasattr(t, "functor"):
+                raise NotImplementedError(
+                    f"{self.name}: populations on the molecular grid only (grid_type 3) are built for "
+                    "exponential pro-atoms (MBIS, NLIS/GMBIS, GISA, aLISA, gLISA) and for Hirshfeld")
+            nblk = int(_lib.call("hp_molgrid_num_blocks", slab.npts))
+            partial = torch.zeros(nblk * max(t.nshell, self.natom), dtype=torch.float64, device=slab.device)
+            _lib.call("hp_atom_weight_integrals", t.functor, slab.npts, slab.px, slab.py, slab.pz, slab.natom,
+                      slab.atom_xyz, t.offsets, t.A, t.alpha, t.order, t.ntile, t.tiles, dens, slab.molw, slab.promol,
+                      partial, out, stream_ptr(slab.device))  # fmt: skip
+        else:
+            seg = slab.atom_point_offsets[sh.atom_lo : sh.atom_hi + 1] - slab.point_base
+            _lib.call("hp_segment_integrate", sh.nlocal, seg.contiguous(), slab.atw, slab.at_w, dens,
+                      out[sh.atom_lo : sh.atom_hi], stream_ptr(slab.device))  # fmt: skip
         if self._comm is not None:
             from .comm import all_reduce
 

@@ -252,6 +252,9 @@ class GridSlab:
         self.at_w = torch.empty(self.npts, dtype=torch.float64, device=dev)
         self.npartial = int(_lib.call("hp_num_partials"))
         self.entropy_partials = torch.zeros(self.npartial, dtype=torch.float64, device=dev)
+        from .hostmem import drain
+
+        drain(dev)  # asynchronous uploads from page-locked caller arrays have landed; sources released
 
     # ------------------------------------------------------------------------------------------
     def shell_project(self):

@@ -24,6 +24,7 @@ __all__ = ["pinned_empty", "is_pinned", "upload", "download", "pool_stats"]
 
 _STAGING_BYTES = 128 << 20
 _staging = None
+_pending = []  # (device, tensor, array) of asynchronous uploads from page-locked sources not yet drained
 _pool = []  # page-locked uint8 tensors handed out by download()
 _stats = {"pinned_allocs": 0, "pinned_reuses": 0, "staged_uploads": 0, "direct_uploads": 0}
 
@@ -68,14 +69,31 @@ def upload(array, device, dtype=None):
     out = torch.empty(src.shape, dtype=src.dtype, device=device)
     stream = torch.cuda.current_stream(device).cuda_stream
     if is_pinned(a):
+        # asynchronous copy straight from the caller's page-locked array: the source stays referenced in
+        # _pending until drain() has synchronised the stream (GridSlab.__init__ does that once for all of
+        # its uploads), so neither the garbage collector nor torch's host allocator can recycle it while
+        # the DMA engine still reads it.  The caller must not modify the array before drain() returns.
         _stats["direct_uploads"] += 1
         _lib.call("hp_host_to_device", out, int(a.ctypes.data), nbytes, None, 0, 1, stream)
-        out._hp_source = src  # keep the page-locked source alive until the async copy is consumed
+        _pending.append((torch.device(device), src, a))
         return out
     stage = _staging_buffer()
     _stats["staged_uploads"] += 1
     _lib.call("hp_host_to_device", out, int(a.ctypes.data), nbytes, stage, stage.numel(), _threads(), stream)
     return out
+
+
+def drain(device=None):
+    """Wait for the asynchronous uploads issued by :func:`upload` (on ``device``'s current stream) and
+    release the references that kept their page-locked sources alive."""
+    import torch
+
+    if not _pending:
+        return
+    devices = {d for d, _, _ in _pending} if device is None else {torch.device(device)}
+    for d in devices:
+        torch.cuda.current_stream(d).synchronize()
+    _pending[:] = [p for p in _pending if p[0] not in devices]
 
 
 def _take(nbytes):

@@ -60,10 +60,13 @@ extern "C" int hp_host_to_device(void* dst_dev, const void* src_host, size_t byt
         if (rc) return rc;
         return check_cuda(cudaStreamSynchronize(st), "cudaStreamSynchronize");
     }
-    cudaEvent_t ev[2];
+    cudaEvent_t ev[2] = {nullptr, nullptr};
     for (auto& e : ev) {
         int rc = check_cuda(cudaEventCreateWithFlags(&e, cudaEventDisableTiming), "cudaEventCreate");
-        if (rc) return rc;
+        if (rc) {
+            if (ev[0]) cudaEventDestroy(ev[0]);  // the second creation failed: do not leak the first
+            return rc;
+        }
     }
     bool used[2] = {false, false};
     int rc = HP_OK, i = 0;

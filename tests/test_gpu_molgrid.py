@@ -148,3 +148,21 @@ def test_host_plugins_on_the_molecular_grid(request, tag, scheme, case_name, kw,
     # (the promolecule of the PENULTIMATE parameters is cached; with DIIS those carry the solver's
     # restart noise: 1e-5 relative at single points, measured)
     np.testing.assert_allclose(part["promoldens"][::97], ref["promoldens_sample"], rtol=1e-8 if rtol <= 1e-8 else 1e-4)
+
+
+def test_spin_charges_without_atomic_grids(water6):
+    """grid_type 3 has no atomic grids: populations of a second density are integrated over the whole
+    molecular grid with the weight functions regenerated in hp_atom_weight_integrals (the reference does
+    grid.integrate(at_weights, spindens), core/base.py:287-298, 313-327)."""
+    from horton_part_b200 import MBISWPart
+
+    spin = 0.125 * water6["rho"]
+    part = MBISWPart(water6["coords"], water6["numbers"], water6["pseudo"], water6["grid"], water6["rho"],
+                     spindens=spin, grid_type=3)
+    part.do_spin_charges()
+    pops = water6["pseudo"] - part["charges"]
+    # the weights are those of the last iteration (penultimate parameters), the charges come from the same
+    # weights: spin populations = 0.125 x populations up to the quadrature of the two code paths
+    np.testing.assert_allclose(part["spin_charges"], 0.125 * pops, rtol=1e-9, atol=1e-12)
+    with pytest.raises(NotImplementedError, match="do_moments"):
+        part.do_moments()
