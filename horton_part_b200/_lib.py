@@ -63,7 +63,8 @@ EXPORTS = {
         _int,
         [_i32, _i32, _p, _p, _p, _p, _p, _p, _p, _p, _f64, _f64, _f64, _i32, _i32, _i32, _i32, _p, _p, _p, _p, _p],
     ),
-    "hp_spline_build": (_int, [_i32, _p, _p, _p, _i32, _p, _p, _p]),
+    "hp_spline_build": (_int, [_i32, _p, _p, _p, _i32, _p, _p, _p, _p, _i32, _p]),
+    "hp_spline_system_inverse": (_int, [_i32, _p, _p]),
     "hp_spline_lut_size": (_i32, [_i32, _p]),
     "hp_spline_lut_fill": (_int, [_i32, _p, _p, _p]),
     "hp_spline_tile_limits": (None, [_p, _p]),

@@ -7,7 +7,10 @@
 //                            extrapolating with the end pieces exactly like PPoly
 //   hp_isa_update            ISA's parameter update: propars = clipped spherical average, charge,
 //                            change term (isa.py:102-122, core/iterstock.py:32-45)
+#include <cmath>
 #include <cstring>
+#include <utility>
+#include <vector>
 
 #include "hp_common.cuh"
 #include "hp_math.cuh"
@@ -90,6 +93,78 @@ __global__ void spline_build_kernel(int natom, const int* __restrict__ knot_off,
         c[4 * i + 1] = (slope - s[i]) / dxi - t;
         c[4 * i + 2] = s[i];
         c[4 * i + 3] = Y(i);
+    }
+}
+
+// Parallel version for the iteration loop: the not-a-knot system matrix depends on the KNOTS only, which
+// never change during a partitioning -- only the right-hand side (the tabulated values) does.  The host
+// inverts the matrix once per distinct knot array (hp_spline_system_inverse, stored transposed so that the
+// matrix-vector product below reads it coalesced); one block per atom then builds the right-hand side, the
+// knot derivatives s = A^-1 b and the PPoly coefficients with all threads.  The serial Thomas solve above
+// (one thread per atom, ~300 dependent FP64 operations through global scratch) was 62 % of an ISA
+// iteration at config 2 (profiles/r2_launches_*.txt).  inv_offsets[a] < 0 selects the serial path for
+// that atom (fewer than 4 knots).
+constexpr int kSbThreads = 256;
+
+__global__ void __launch_bounds__(kSbThreads)
+spline_build_inv_kernel(int natom, const int* __restrict__ knot_off, const double* __restrict__ knots,
+                        const double* __restrict__ values, int clip_negative,
+                        const long long* __restrict__ inv_off, const double* __restrict__ invT,
+                        double* __restrict__ coef) {
+    extern __shared__ double s_sb[];  // y[n] | rhs[n] | s[n]
+    const int a = blockIdx.x;
+    if (a >= natom) return;
+    const int o = knot_off[a], n = knot_off[a + 1] - o;
+    const double* x = knots + o;
+    double* y = s_sb;
+    double* rhs = s_sb + n;
+    double* sd = s_sb + 2 * n;
+    double* c = coef + 4 * (long long)(o - a);
+    for (int i = threadIdx.x; i < n; i += kSbThreads) {
+        const double v = values[o + i];
+        y[i] = (clip_negative && v < 0.0) ? 0.0 : v;  // fix_proatom_rho, core/stockholder.py:218-219
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < n; i += kSbThreads) {
+        double b;
+        if (i == 0) {
+            const double dx0 = x[1] - x[0], dx1 = x[2] - x[1], d = x[2] - x[0];
+            const double sl0 = (y[1] - y[0]) / dx0, sl1 = (y[2] - y[1]) / dx1;
+            b = ((dx0 + 2 * d) * dx1 * sl0 + dx0 * dx0 * sl1) / d;
+        } else if (i == n - 1) {
+            const double dxl = x[n - 1] - x[n - 2], dxl2 = x[n - 2] - x[n - 3], d = x[n - 1] - x[n - 3];
+            const double sll = (y[n - 1] - y[n - 2]) / dxl, sll2 = (y[n - 2] - y[n - 3]) / dxl2;
+            b = (dxl * dxl * sll2 + (2 * d + dxl) * dxl2 * sll) / d;
+        } else {
+            const double dxm = x[i] - x[i - 1], dxi = x[i + 1] - x[i];
+            const double slm = (y[i] - y[i - 1]) / dxm, sli = (y[i + 1] - y[i]) / dxi;
+            b = 3 * (dxi * slm + dxm * sli);
+        }
+        rhs[i] = b;
+    }
+    __syncthreads();
+    const double* AT = invT + inv_off[a];  // AT[j * n + i] = (A^-1)[i][j]
+    for (int i = threadIdx.x; i < n; i += kSbThreads) {
+        double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;  // four partial sums: short dependency chains
+        int j = 0;
+        for (; j + 3 < n; j += 4) {
+            s0 = fma(AT[(long long)j * n + i], rhs[j], s0);
+            s1 = fma(AT[(long long)(j + 1) * n + i], rhs[j + 1], s1);
+            s2 = fma(AT[(long long)(j + 2) * n + i], rhs[j + 2], s2);
+            s3 = fma(AT[(long long)(j + 3) * n + i], rhs[j + 3], s3);
+        }
+        for (; j < n; ++j) s0 = fma(AT[(long long)j * n + i], rhs[j], s0);
+        sd[i] = (s0 + s1) + (s2 + s3);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < n - 1; i += kSbThreads) {
+        const double dxi = x[i + 1] - x[i];
+        const double slope = (y[i + 1] - y[i]) / dxi;
+        const double t = (sd[i] + sd[i + 1] - 2 * slope) / dxi;
+        c[4 * i + 0] = t / dxi;
+        c[4 * i + 1] = (slope - sd[i]) / dxi - t;
+        c[4 * i + 2] = sd[i];
+        c[4 * i + 3] = y[i];
     }
 }
 
@@ -227,15 +302,42 @@ promol_weights_spline_kernel(int64_t npts, const double* __restrict__ px, const 
                 const double* ck = s_coef + 4 * (at.ko - ia);
                 const unsigned short* tab = lut + at.lut;
                 const int last = at.n - 2;
+                // the PTS points of a thread go through every stage together (distance -> table look-up ->
+                // scan -> knot / coefficient loads -> Horner), so that their dependent shared-memory and L1
+                // latencies overlap instead of adding up
+                double r[PTS];
+                int idx[PTS];
 #pragma unroll
                 for (int j = 0; j < PTS; ++j) {
                     const double dx = x[j] - at.x, dy = y[j] - at.y, dz = z[j] - at.z;
-                    const double r = sqrt_nocall(fma(dz, dz, fma(dy, dy, dx * dx)));
-                    int bin = (__double2hiint(r) >> kLutShift) - at.key0;
+                    r[j] = sqrt_nocall(fma(dz, dz, fma(dy, dy, dx * dx)));
+                    int bin = (__double2hiint(r[j]) >> kLutShift) - at.key0;
                     bin = max(0, min(bin, at.nbins - 1));
-                    int i = tab[bin];
-                    while (i < last && xk[i + 1] <= r) ++i;
-                    const double d = r - xk[i];
+                    idx[j] = tab[bin];
+                }
+                // forward scan: two branch-free steps cover the radial transforms of qc-grid at 32 bins per
+                // octave (at most one knot per bin); the loop behind them is for arbitrary knot sets
+                bool more = false;
+#pragma unroll
+                for (int j = 0; j < PTS; ++j) {
+                    int i = idx[j];
+                    i += (i < last && xk[i + 1] <= r[j]) ? 1 : 0;
+                    i += (i < last && xk[i + 1] <= r[j]) ? 1 : 0;
+                    more = more || (i < last && xk[i + 1] <= r[j]);
+                    idx[j] = i;
+                }
+                if (__builtin_expect(more, 0)) {
+#pragma unroll
+                    for (int j = 0; j < PTS; ++j) {
+                        int i = idx[j];
+                        while (i < last && xk[i + 1] <= r[j]) ++i;
+                        idx[j] = i;
+                    }
+                }
+#pragma unroll
+                for (int j = 0; j < PTS; ++j) {
+                    const int i = idx[j];
+                    const double d = r[j] - xk[i];
                     const double2 c01 = *reinterpret_cast<const double2*>(ck + 4 * i);
                     const double2 c23 = *reinterpret_cast<const double2*>(ck + 4 * i + 2);
                     // PPoly's evaluation order: c3 + c2 d + c1 d^2 + c0 d^3
@@ -348,10 +450,68 @@ isa_update_kernel(int natom, int atom_base, const int* __restrict__ rad_off,
 
 using namespace hp;
 
+// Host helper: transposed inverse of the not-a-knot system of a knot array (n >= 4), n x n doubles:
+// out[j * n + i] = (A^-1)[i][j], A as assembled by SciPy's CubicSpline(bc_type="not-a-knot") and by
+// spline_build_kernel.  Gauss-Jordan with partial pivoting in long double, rounded to double at the end.
+extern "C" int hp_spline_system_inverse(int32_t n, const double* knots_host, double* invT_host) {
+    HP_REQUIRE(n >= 4 && knots_host && invT_host, "needs at least 4 knots");
+    const double* x = knots_host;
+    std::vector<long double> A(size_t(n) * n, 0.0L), B(size_t(n) * n, 0.0L);
+    auto at = [&](std::vector<long double>& M, int r, int c) -> long double& { return M[size_t(r) * n + c]; };
+    at(A, 0, 0) = (long double)x[2] - x[1];
+    at(A, 0, 1) = (long double)x[2] - x[0];
+    for (int i = 1; i < n - 1; ++i) {
+        const long double dxm = (long double)x[i] - x[i - 1], dxi = (long double)x[i + 1] - x[i];
+        at(A, i, i - 1) = dxi;
+        at(A, i, i) = 2 * (dxm + dxi);
+        at(A, i, i + 1) = dxm;
+    }
+    at(A, n - 1, n - 2) = (long double)x[n - 1] - x[n - 3];
+    at(A, n - 1, n - 1) = (long double)x[n - 2] - x[n - 3];
+    for (int i = 0; i < n; ++i) at(B, i, i) = 1.0L;
+    for (int col = 0; col < n; ++col) {
+        int piv = col;
+        for (int r = col + 1; r < n; ++r)
+            if (fabsl(at(A, r, col)) > fabsl(at(A, piv, col))) piv = r;
+        HP_REQUIRE(at(A, piv, col) != 0.0L, "singular spline system (repeated knots?)");
+        if (piv != col)
+            for (int k = 0; k < n; ++k) {
+                std::swap(at(A, piv, k), at(A, col, k));
+                std::swap(at(B, piv, k), at(B, col, k));
+            }
+        const long double inv = 1.0L / at(A, col, col);
+        for (int k = 0; k < n; ++k) {
+            at(A, col, k) *= inv;
+            at(B, col, k) *= inv;
+        }
+        for (int r = 0; r < n; ++r) {
+            if (r == col) continue;
+            const long double f = at(A, r, col);
+            if (f == 0.0L) continue;
+            for (int k = 0; k < n; ++k) {
+                at(A, r, k) -= f * at(A, col, k);
+                at(B, r, k) -= f * at(B, col, k);
+            }
+        }
+    }
+    for (int i = 0; i < n; ++i)
+        for (int j = 0; j < n; ++j) invT_host[size_t(j) * n + i] = double(at(B, i, j));
+    return HP_OK;
+}
+
 extern "C" int hp_spline_build(int32_t natom, const int32_t* knot_offsets, const double* knots,
                                const double* values, int32_t clip_negative, double* coef,
-                               double* work, void* stream) {
+                               double* work, const int64_t* inv_offsets, const double* invT,
+                               int32_t nknot_max, void* stream) {
     HP_REQUIRE(natom > 0 && knot_offsets && knots && values && coef && work, "bad arguments");
+    if (inv_offsets && invT && nknot_max >= 4 && nknot_max <= 2048) {
+        // every atom of the launch has >= 4 knots (the caller passes inv_offsets only then)
+        spline_build_inv_kernel<<<natom, kSbThreads, sizeof(double) * 3 * size_t(nknot_max), as_stream(stream)>>>(
+            natom, knot_offsets, knots, values, clip_negative, reinterpret_cast<const long long*>(inv_offsets), invT,
+            coef);
+        HP_LAUNCH_CHECK("spline_build_inv_kernel");
+        return HP_OK;
+    }
     spline_build_kernel<<<(natom + 63) / 64, 64, 0, as_stream(stream)>>>(natom, knot_offsets, knots,
                                                                          values, clip_negative, coef, work);
     HP_LAUNCH_CHECK("spline_build_kernel");

@@ -65,6 +65,24 @@ class SplineTable:
                 pool.append(lut)
                 pos += nb
             meta[a] = tables[key]
+        # transposed inverses of the not-a-knot systems (one per distinct knot array with >= 4 knots): the
+        # per-iteration spline construction is then a parallel matrix-vector product (hp_spline_build)
+        self.inv_offsets = self.invT = None
+        self.nknot_max = int(max(sizes))
+        if min(sizes) >= 4 and self.nknot_max <= 2048:
+            inv_pool, inv_pos, inv_of, where = [], 0, {}, np.zeros(len(rgrids), dtype=np.int64)
+            for a, g in enumerate(rgrids):
+                x = np.ascontiguousarray(g.points, dtype=np.float64)
+                key = x.tobytes()
+                if key not in inv_of:
+                    mat = np.zeros(len(x) * len(x))
+                    _lib.call("hp_spline_system_inverse", len(x), x, mat)
+                    inv_of[key] = inv_pos
+                    inv_pool.append(mat)
+                    inv_pos += mat.size
+                where[a] = inv_of[key]
+            self.inv_offsets = to_device(where, dev, np.int64)
+            self.invT = to_device(np.concatenate(inv_pool), dev)
         self.lut_meta = to_device(meta.ravel(), dev, np.int32)
         self.lut = to_device(np.concatenate(pool), dev, np.uint16)
         max_atoms, max_knots = np.zeros(1, np.int32), np.zeros(1, np.int32)
@@ -86,7 +104,8 @@ class SplineTable:
         from .core.device import stream_ptr
 
         _lib.call("hp_spline_build", len(self.offsets_host) - 1, self.offsets, self.knots, values,
-                  int(clip_negative), self.coef, self.work, stream_ptr(self.slab.device))  # fmt: skip
+                  int(clip_negative), self.coef, self.work, self.inv_offsets, self.invT, self.nknot_max,
+                  stream_ptr(self.slab.device))  # fmt: skip
 
     def promol_weights(self, density_cutoff, want_promol=True, want_weights=True, want_entropy=True,
                        proatom_offset=None):  # fmt: skip

@@ -249,7 +249,14 @@ HP_API int hp_lisa_sc_radial_solve(int32_t natom, int32_t atom_base, const int32
  * rad_w are the plain radial weights (rgrid.weights). */
 HP_API int hp_spline_build(int32_t natom, const int32_t* knot_offsets, const double* knots,
                            const double* values, int32_t clip_negative, double* coef, double* work,
-                           void* stream);
+                           const int64_t* inv_offsets, const double* invT, int32_t nknot_max, void* stream);
+/* The not-a-knot system matrix depends on the knots only, which never change during a partitioning.
+ * hp_spline_system_inverse (HOST, n >= 4): invT_host[j * n + i] = (A^-1)[i][j], n x n doubles, computed in
+ * long double.  With inv_offsets (per atom: offset of its matrix in the device pool invT; atoms with equal
+ * knots share one) and nknot_max (largest knot count, <= 2048) hp_spline_build runs one block per atom:
+ * right-hand side, s = A^-1 b and the coefficients in parallel.  NULL inv_offsets / invT: the serial Thomas
+ * solve per atom (any knot count >= 2; `work` = 2 doubles per knot). */
+HP_API int hp_spline_system_inverse(int32_t n, const double* knots_host, double* invT_host);
 /* Interval index of the fused spline pass (the reference's eval_spline is scipy PPoly's binary
  * search, core/stockholder.py:271-302): the top bits of the double r (sign, exponent, 5 mantissa bits)
  * are a piecewise-linear, monotone log2 r; lut[(hi32(r) >> 15) - key0] is the interval holding the

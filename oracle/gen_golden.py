@@ -670,8 +670,13 @@ def database_promolecule(db, points, coords, numbers, charges):
     for R, z, q in zip(coords, numbers, charges):
         ic = int(np.floor(q))
         x = float(q - ic)
-        spline = db.get_spline(int(z), {ic: 1 - x, ic + 1: x} if x != 0.0 else {ic: 1.0})
-        rho += spline(np.linalg.norm(points - R, axis=1))
+        # hirshfeld_i.py:125-132: a one-electron atom (or an integer charge) uses the scaled lower state only
+        one = (int(z) - ic) == 1 or x == 0.0
+        spline = db.get_spline(int(z), {ic: 1 - x} if one else {ic: 1 - x, ic + 1: x})
+        r = np.linalg.norm(points - R, axis=1)
+        # inside the record's radial grid only: beyond it the extrapolating cubic is meaningless (the
+        # outermost points of the Becke-transformed grid sit at 1e4 bohr and more)
+        rho += np.where(r <= db.get_rgrid(int(z)).points[-1], np.clip(spline(np.minimum(r, 1e3)), 0.0, None), 0.0)
     return rho
 
 

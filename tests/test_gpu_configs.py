@@ -132,8 +132,10 @@ def test_config2_hirshfeld_i_full_size():
     for R, zn, q in zip(coords, numbers, z["generating_charges"]):
         ic = int(np.floor(q))
         x = float(q - ic)
-        spline = db.get_spline(int(zn), {ic: 1 - x, ic + 1: x} if x != 0.0 else {ic: 1.0})
-        rho += spline(np.linalg.norm(grid.points - R, axis=1))
+        one = (int(zn) - ic) == 1 or x == 0.0  # hirshfeld_i.py:125-132
+        spline = db.get_spline(int(zn), {ic: 1 - x} if one else {ic: 1 - x, ic + 1: x})
+        r = np.linalg.norm(grid.points - R, axis=1)
+        rho += np.where(r <= db.get_rgrid(int(zn)).points[-1], np.clip(spline(np.minimum(r, 1e3)), 0.0, None), 0.0)
     np.testing.assert_allclose(rho[::997], z["dens_sample"], rtol=1e-12, atol=1e-300)
     part = HirshfeldIWPart(coords, numbers, numbers.astype(float), grid, rho, _records(z))
     part.do_charges()

@@ -12,9 +12,23 @@ def _gold(gold, tag):
     return {k.split("/", 1)[1]: gold[k] for k in gold.files if k.startswith(tag + "/")}
 
 
+def _check_spline_coefficients(coef, off, xs, ys, tol=1e-12):
+    from scipy.interpolate import CubicSpline
+
+    for a, (x, y) in enumerate(zip(xs, ys)):
+        spl = CubicSpline(x, np.where(y < 0, 0.0, y), True)
+        got = coef[4 * (off[a] - a) : 4 * (off[a + 1] - a - 1)].reshape(-1, 4)
+        # same piecewise cubic: compare values (incl. extrapolation) on a dense sample
+        t = np.linspace(x[0] - 0.5, x[-1] + 2.0, 4001)
+        seg = np.clip(np.searchsorted(x, t, side="right") - 1, 0, len(x) - 2)
+        dd = t - x[seg]
+        mine = ((got[seg, 0] * dd + got[seg, 1]) * dd + got[seg, 2]) * dd + got[seg, 3]
+        ref = spl(t)
+        assert np.abs(mine - ref).max() <= tol * max(1.0, np.abs(ref).max()), a
+
+
 def test_spline_build_matches_scipy():
     import torch
-    from scipy.interpolate import CubicSpline
 
     from horton_part_b200 import _lib
 
@@ -29,19 +43,42 @@ def test_spline_build_matches_scipy():
     d = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)  # noqa: E731
     coef = torch.zeros(4 * (len(knots) - len(sizes)), dtype=torch.float64, device=dev)
     work = torch.zeros(2 * len(knots), dtype=torch.float64, device=dev)
-    _lib.call("hp_spline_build", len(sizes), d(off), d(knots), d(vals), 1, coef, work,
+    # serial Thomas solve (any knot count)
+    _lib.call("hp_spline_build", len(sizes), d(off), d(knots), d(vals), 1, coef, work, None, None, 0,
               torch.cuda.current_stream(dev).cuda_stream)
-    coef = coef.cpu().numpy()
-    for a, (x, y) in enumerate(zip(xs, ys)):
-        spl = CubicSpline(x, np.where(y < 0, 0.0, y), True)
-        got = coef[4 * (off[a] - a) : 4 * (off[a + 1] - a - 1)].reshape(-1, 4)
-        # same piecewise cubic: compare values (incl. extrapolation) on a dense sample
-        t = np.linspace(x[0] - 0.5, x[-1] + 2.0, 4001)
-        seg = np.clip(np.searchsorted(x, t, side="right") - 1, 0, len(x) - 2)
-        dd = t - x[seg]
-        mine = ((got[seg, 0] * dd + got[seg, 1]) * dd + got[seg, 2]) * dd + got[seg, 3]
-        ref = spl(t)
-        assert np.abs(mine - ref).max() <= 1e-12 * max(1.0, np.abs(ref).max()), a
+    _check_spline_coefficients(coef.cpu().numpy(), off, xs, ys)
+
+
+def test_spline_build_parallel_matches_scipy():
+    """One block per atom with the precomputed inverse of the not-a-knot system (hp_spline_system_inverse):
+    the version the ISA iteration uses; radial grids of the reference's tests and adversarial knot sets."""
+    import torch
+
+    from horton_part_b200 import _lib, gridlite
+
+    dev = torch.device("cuda:0")
+    rng = np.random.default_rng(4)
+    xs = [gridlite.BeckeRTransform(1e-4, 1.5).transform_1d_grid(gridlite.GaussChebyshev(150)).points,
+          gridlite.ExpRTransform(5e-4, 2e1, 119).transform_1d_grid(gridlite.UniformInteger(120)).points,
+          np.sort(rng.uniform(0.01, 20.0, 4)), np.sort(rng.uniform(0.01, 20.0, 37)) * np.linspace(1, 3, 37)]
+    ys = [np.exp(-1.3 * x) * (1 + 0.1 * rng.normal(size=x.size)) for x in xs]
+    ys[3][5] = -0.2
+    sizes = [len(x) for x in xs]
+    off = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int32)
+    knots, vals = np.concatenate(xs), np.concatenate(ys)
+    pool, where, pos = [], [], 0
+    for x in xs:
+        mat = np.zeros(len(x) ** 2)
+        _lib.call("hp_spline_system_inverse", len(x), np.ascontiguousarray(x), mat)
+        where.append(pos)
+        pool.append(mat)
+        pos += mat.size
+    d = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)  # noqa: E731
+    coef = torch.zeros(4 * (len(knots) - len(sizes)), dtype=torch.float64, device=dev)
+    work = torch.zeros(2 * len(knots), dtype=torch.float64, device=dev)
+    _lib.call("hp_spline_build", len(sizes), d(off), d(knots), d(vals), 1, coef, work, d(np.array(where, dtype=np.int64)),
+              d(np.concatenate(pool)), max(sizes), torch.cuda.current_stream(dev).cuda_stream)
+    _check_spline_coefficients(coef.cpu().numpy(), off, xs, ys, tol=1e-11)
 
 
 def _isa(case, **kw):
