@@ -53,11 +53,11 @@ EXPORTS = {
     "hp_shell_harmonics": (_int, [_i32, _i32, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
     "hp_mbis_radial_solve": (
         _int,
-        [_i32, _i32, _p, _p, _p, _p, _p, _p, _p, _f64, _f64, _i32, _i32, _p, _p, _p, _p, _p],
+        [_i32, _i32, _p, _p, _p, _p, _p, _p, _p, _f64, _f64, _i32, _i32, _i32, _p, _p, _p, _p, _p],
     ),
     "hp_nlis_radial_solve": (
         _int,
-        [_i32, _i32, _p, _p, _p, _p, _p, _p, _p, _p, _p, _f64, _f64, _i32, _i32, _p, _p, _p, _p, _p],
+        [_i32, _i32, _p, _p, _p, _p, _p, _p, _p, _p, _p, _f64, _f64, _i32, _i32, _i32, _p, _p, _p, _p, _p],
     ),
     "hp_lisa_sc_radial_solve": (
         _int,

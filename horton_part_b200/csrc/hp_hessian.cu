@@ -172,8 +172,10 @@ constexpr int kDStride = kHT + 4;  // padded row length of a slab row (doubles)
 constexpr int kDStages = 3;
 
 __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
-    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
-                 : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+    // not volatile: a pure function of its operands, so the compiler may hoist the operand loads of the
+    // next k-step above the DMMAs of this one
+    asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+        : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
 }
 
 __global__ void __launch_bounds__(256)
@@ -218,19 +220,31 @@ syrk_panel_dmma_kernel(const double* __restrict__ Gu, int Mpad, int pc_sub, cons
         __syncthreads();  // slab `sl` has landed for every thread; slab sl-1 is consumed by everyone
         if (sl + kDStages - 1 < nslab) issue((sl + kDStages - 1) % kDStages, (sl + kDStages - 1) * kDK);
         else cp_async_commit();
+        // operand fragments of k-step k4 + 4 are loaded while the 32 DMMAs of k-step k4 issue
+        double a[2][8], b[2][4];
+        {
+            const double* ar = As(st, tig) + wrow + gid;
+            const double* br = Bs(st, tig) + wcol + gid;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) a[0][i] = ar[8 * i];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) b[0][j] = br[8 * j];
+        }
 #pragma unroll
         for (int k4 = 0; k4 < kDK; k4 += 4) {
-            const double* ar = As(st, k4 + tig) + wrow + gid;
-            const double* br = Bs(st, k4 + tig) + wcol + gid;
-            double a[8], b[4];
+            const int cur = (k4 >> 2) & 1, nxt = cur ^ 1;
+            if (k4 + 4 < kDK) {
+                const double* ar = As(st, k4 + 4 + tig) + wrow + gid;
+                const double* br = Bs(st, k4 + 4 + tig) + wcol + gid;
 #pragma unroll
-            for (int i = 0; i < 8; ++i) a[i] = ar[8 * i];
+                for (int i = 0; i < 8; ++i) a[nxt][i] = ar[8 * i];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) b[j] = br[8 * j];
+                for (int j = 0; j < 4; ++j) b[nxt][j] = br[8 * j];
+            }
 #pragma unroll
             for (int i = 0; i < 8; ++i)
 #pragma unroll
-                for (int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+                for (int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[cur][i], b[cur][j]);
         }
     }
     cp_async_wait<0>();
@@ -292,11 +306,14 @@ static int hessian_split(int ntile) {
     return best;
 }
 
-// points per chunk: the panel (pc x Mpad doubles) is written by one kernel and read ~2 Mpad/128 times by the
-// next: keep it inside the 126 MB L2 (<= 64 MB) so that those reads never go to HBM; a multiple of
-// nsplit * kHK
+// points per chunk: bounded panel size (<= 512 MB) and a multiple of nsplit * kHK.  Large chunks on purpose:
+// every (tile, split) block ends with a read-modify-write of its 128 x 128 slice of the partial matrices
+// (nsplit x Mpad^2 doubles = 359 MB at M = 1,536: HBM traffic per chunk, not overlapped with the tile
+// product), so the fewer chunks the better -- measured 878 ms per Hessian with 64 MB chunks (1,690 chunks)
+// against the large ones.  The panel itself does not need to fit the L2: the blocks of one split run
+// together (blockIdx.x = tile is the fast index) and share its 3-30 MB sub-panel through the L2.
 static int hessian_chunk_points(int Mpad, int nsplit) {
-    int64_t pc = (int64_t(64) << 20) / (int64_t(Mpad) * 8);
+    int64_t pc = (int64_t(512) << 20) / (int64_t(Mpad) * 8);
     if (pc > 65536) pc = 65536;
     const int q = nsplit * kHK;
     pc = (pc / q) * q;

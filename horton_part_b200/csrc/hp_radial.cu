@@ -2,6 +2,7 @@
 #include <cstdlib>
 
 #include "hp_common.cuh"
+#include "hp_math.cuh"
 
 namespace hp {
 
@@ -280,12 +281,13 @@ mbis_radial_kernel(int natom, int atom_base, const int* __restrict__ rad_off, co
 // time of a small system (round-1 smoke profile).  NLIS = true: shells (N, S, n), nlis.py:99-194.
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ double pow_order(double r, double n);
+__device__ __forceinline__ double rcp_newton(double x);
 
 constexpr int kRadThreads = 128;
 constexpr int kRadWarps = kRadThreads / 32;
 constexpr int kRadOwn = 2;  // radial points per thread
 
-template <bool NLIS>
+template <bool NLIS, int KMAX>
 __global__ void __launch_bounds__(kRadThreads)
 shell_fixed_point_block_kernel(int natom, int atom_base, const int* __restrict__ rad_off,
                                const double* __restrict__ rad_r, const double* __restrict__ rad_w4,
@@ -295,7 +297,7 @@ shell_fixed_point_block_kernel(int natom, int atom_base, const int* __restrict__
                                double threshold, double density_cutoff, int max_inner,
                                double* __restrict__ charges, double* __restrict__ msd,
                                int* __restrict__ niter_out, uint32_t* __restrict__ flags_out) {
-    constexpr int NV = 2 * kMaxMbisShells + 1;  // (m0, m1) per shell | change term (also used for pop / dev)
+    constexpr int NV = 2 * KMAX + 1;  // (m0, m1) per shell | change term (also used for pop / dev)
     __shared__ double s_part[2][kRadWarps][NV];
     if (int(blockIdx.x) >= natom) return;
     const int a = atom_base + blockIdx.x;
@@ -305,10 +307,10 @@ shell_fixed_point_block_kernel(int natom, int atom_base, const int* __restrict__
     const int p0 = par_off[a], K = (par_off[a + 1] - p0) / PW;
     const double* ig = NLIS ? inv_gamma + shell_off[a] : nullptr;
 
-    double N[kMaxMbisShells], S[kMaxMbisShells], n[kMaxMbisShells], G[kMaxMbisShells], N0[kMaxMbisShells],
-        S0[kMaxMbisShells];
+    double N[KMAX], S[KMAX], n[KMAX], G[KMAX], N0[KMAX],
+        S0[KMAX];
 #pragma unroll
-    for (int k = 0; k < kMaxMbisShells; ++k) {
+    for (int k = 0; k < KMAX; ++k) {
         N[k] = S[k] = 0.0;
         n[k] = G[k] = 1.0;
         if (k < K) {
@@ -335,7 +337,7 @@ shell_fixed_point_block_kernel(int natom, int atom_base, const int* __restrict__
     }
     // all-reduce of per-thread values: butterflies, one barrier, fixed summation order.  Slots 0..2K-1 hold
     // (m0, m1) per shell, slot CHG the change term; every loop is unrolled so that `v` stays in registers.
-    constexpr int CHG = 2 * kMaxMbisShells;
+    constexpr int CHG = 2 * KMAX;
     int parity = 0;
     auto block_allsum = [&](double (&v)[NV], int nshell2) {
 #pragma unroll
@@ -364,7 +366,9 @@ shell_fixed_point_block_kernel(int natom, int atom_base, const int* __restrict__
     auto shell_term = [&](int k, double Nk, double Sk, double r, double& rn) -> double {
         if (!NLIS) {
             rn = r;
-            return Nk * (Sk * Sk * Sk) * exp(-Sk * r) / kEightPi;
+            // exp_neg_poly: the 16-operation inline exponential of the grid kernels (<= 0.67 ulp) instead of
+            // the library call -- this term sits on the sequential chain of the fixed point
+            return Nk * (Sk * Sk * Sk) * exp_neg_poly(-Sk * r) / kEightPi;
         }
         rn = pow_order(r, n[k]);
         return n[k] * pow(Sk, 3.0 / n[k]) * exp(-Sk * rn) * G[k] / kFourPi;
@@ -385,10 +389,10 @@ shell_fixed_point_block_kernel(int natom, int atom_base, const int* __restrict__
         for (int j = 0; j < NV; ++j) red[j] = 0.0;
 #pragma unroll
         for (int q = 0; q < kRadOwn; ++q) {
-            double term[kMaxMbisShells], rn[kMaxMbisShells];
+            double term[KMAX], rn[KMAX];
             double pro = 0.0;
 #pragma unroll
-            for (int k = 0; k < kMaxMbisShells; ++k) {
+            for (int k = 0; k < KMAX; ++k) {
                 term[k] = 0.0;
                 rn[k] = 0.0;
                 if (k < K) {
@@ -397,9 +401,9 @@ shell_fixed_point_block_kernel(int natom, int atom_base, const int* __restrict__
                 }
             }
             const bool sick = (rhoi[q] < density_cutoff) || (pro < density_cutoff);
-            const double ratio = sick ? 0.0 : rhoi[q] / pro;
+            const double ratio = sick ? 0.0 : rhoi[q] * rcp_newton(pro);
 #pragma unroll
-            for (int k = 0; k < kMaxMbisShells; ++k) {
+            for (int k = 0; k < KMAX; ++k) {
                 if (k < K) {
                     const double tr = term[k] * ratio;
                     red[2 * k] += NLIS ? wi[q] * (tr * N[k]) : wi[q] * tr;  // nlis.py:166 / mbis.py:143
@@ -414,7 +418,7 @@ shell_fixed_point_block_kernel(int natom, int atom_base, const int* __restrict__
         }
         block_allsum(red, 2 * K);
 #pragma unroll
-        for (int k = 0; k < kMaxMbisShells; ++k) {
+        for (int k = 0; k < KMAX; ++k) {
             if (k < K) {
                 const double a0 = red[2 * k], a1 = red[2 * k + 1];
                 if (!NLIS) {
@@ -438,7 +442,7 @@ shell_fixed_point_block_kernel(int natom, int atom_base, const int* __restrict__
     double nsum = 0.0;
     bool finite = true;
 #pragma unroll
-    for (int k = 0; k < kMaxMbisShells; ++k) {
+    for (int k = 0; k < KMAX; ++k) {
         if (k < K) {
             nsum += N[k];
             finite = finite && isfinite(N[k]) && isfinite(S[k]);
@@ -453,7 +457,7 @@ shell_fixed_point_block_kernel(int natom, int atom_base, const int* __restrict__
     for (int q = 0; q < kRadOwn; ++q) {
         double ynew = 0.0, yold = 0.0, rn;
 #pragma unroll
-        for (int k = 0; k < kMaxMbisShells; ++k) {
+        for (int k = 0; k < KMAX; ++k) {
             if (k < K) {
                 if (!NLIS) {
                     ynew += shell_term(k, N[k], S[k], ri[q], rn);
@@ -471,7 +475,7 @@ shell_fixed_point_block_kernel(int natom, int atom_base, const int* __restrict__
     block_allsum(red, 0);
     if (tid == 0) {
 #pragma unroll
-        for (int k = 0; k < kMaxMbisShells; ++k) {
+        for (int k = 0; k < KMAX; ++k) {
             if (k < K) {
                 propars[p0 + PW * k] = N[k];
                 propars[p0 + PW * k + 1] = S[k];
@@ -756,6 +760,20 @@ lisa_sc_radial_kernel(int natom, int atom_base, const int* __restrict__ rad_off,
 constexpr int kScWarps = 4;
 constexpr int kScThreads = kScWarps * 32;
 
+// 1 / x for a normal, positive x: MUFU.RCP64H seed and two Newton steps (relative error of the result below
+// 2^-52 before the caller's multiplication: rho * (1 / pro) differs from the correctly rounded quotient by at
+// most one unit in the last place).  Six dependent operations instead of the ~ten of a full division: the
+// inner fixed point is a chain of ~1e4 sequential steps and this quotient sits on it.  x below 1e-15 never
+// gets here (masked by density_cutoff).
+__device__ __forceinline__ double rcp_newton(double x) {
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    double e = fma(-x, y, 1.0);
+    y = fma(y, e, y);
+    e = fma(-x, y, 1.0);
+    return fma(y, e, y);
+}
+
 template <int KPW, int NPL>
 __global__ void __launch_bounds__(kScThreads)
 lisa_sc_block_kernel(int natom, int atom_base, const int* __restrict__ rad_off,
@@ -815,10 +833,13 @@ lisa_sc_block_kernel(int natom, int atom_base, const int* __restrict__ rad_off,
         // 1. partial pro-atom sums of this warp's shells
 #pragma unroll
         for (int j = 0; j < NPL; ++j) {
-            double p = 0.0;
+            double pa = 0.0, pb = 0.0;  // two chains: the step latency is what counts here
 #pragma unroll
-            for (int kk = 0; kk < KPW; ++kk) p = fma(g[kk][j], c[kk], p);
-            s_part[warp][lane + 32 * j] = p;
+            for (int kk = 0; kk < KPW; kk += 2) {
+                pa = fma(g[kk][j], c[kk], pa);
+                if (kk + 1 < KPW) pb = fma(g[kk + 1][j], c[kk + 1], pb);
+            }
+            s_part[warp][lane + 32 * j] = pa + pb;
         }
         __syncthreads();
         // 2. point owners: pro-atom, masked ratio, change term
@@ -826,11 +847,10 @@ lisa_sc_block_kernel(int natom, int atom_base, const int* __restrict__ rad_off,
         for (int q = 0; q < NOWN; ++q) {
             const int i = tid + q * kScThreads;
             if (i < NRP) {
-                double pro = s_part[0][i];
-#pragma unroll
-                for (int v = 1; v < kScWarps; ++v) pro += s_part[v][i];
+                static_assert(kScWarps == 4, "pairwise sum below is written for four warps");
+                const double pro = (s_part[0][i] + s_part[1][i]) + (s_part[2][i] + s_part[3][i]);
                 const bool sick = (ro[q] < density_cutoff) || (pro < density_cutoff);
-                const double ratio = sick ? 0.0 : ro[q] / pro;
+                const double ratio = sick ? 0.0 : ro[q] * rcp_newton(pro);
                 const double e = oldpro[q] - pro;
                 s_rw[i] = wo[q] * ratio;
                 s_chg[i] = (it > 0) ? wo[q] * e * e : 0.0;
@@ -848,10 +868,13 @@ lisa_sc_block_kernel(int natom, int atom_base, const int* __restrict__ rad_off,
         double sums[KPW];
 #pragma unroll
         for (int kk = 0; kk < KPW; ++kk) {
-            double sk = 0.0;
+            double sa = 0.0, sb = 0.0;
 #pragma unroll
-            for (int j = 0; j < NPL; ++j) sk = fma(g[kk][j], rw[j], sk);
-            sums[kk] = sk;
+            for (int j = 0; j < NPL; j += 2) {
+                sa = fma(g[kk][j], rw[j], sa);
+                if (j + 1 < NPL) sb = fma(g[kk][j + 1], rw[j + 1], sb);
+            }
+            sums[kk] = sa + sb;
         }
 #pragma unroll
         for (int off = 16; off > 0; off >>= 1) {
@@ -899,9 +922,7 @@ lisa_sc_block_kernel(int natom, int atom_base, const int* __restrict__ rad_off,
     for (int q = 0; q < NOWN; ++q) {
         const int i = tid + q * kScThreads;
         if (i < NRP) {
-            double d = s_part[0][i];
-#pragma unroll
-            for (int v = 1; v < kScWarps; ++v) d += s_part[v][i];
+            const double d = (s_part[0][i] + s_part[1][i]) + (s_part[2][i] + s_part[3][i]);
             dev += wo[q] * d * d;
         }
     }
@@ -1145,20 +1166,27 @@ extern "C" int hp_mbis_radial_solve(int32_t natom, int32_t atom_base, const int3
                                     const int32_t* par_offsets, double* propars,
                                     const double* pseudo_numbers, double inner_threshold,
                                     double density_cutoff, int32_t max_inner, int32_t nrad_max,
-                                    double* charges, double* msd, int32_t* niter, uint32_t* flags,
-                                    void* stream) {
+                                    int32_t nshell_max, double* charges, double* msd, int32_t* niter,
+                                    uint32_t* flags, void* stream) {
     HP_REQUIRE(natom >= 0, "bad sizes");
     if (natom == 0) return HP_OK;
     HP_REQUIRE(rad_offsets && rad_r && rad_w4 && sph_avg && par_offsets && propars &&
                    pseudo_numbers && charges && msd && niter && flags, "null input");
     HP_REQUIRE(nrad_max > 0 && nrad_max <= 4096, "nrad_max must be in 1..4096");
+    HP_REQUIRE(nshell_max > 0 && nshell_max <= kMaxMbisShells, "nshell_max must be in 1..7");
     // shared memory: one double per radial point of the largest atom; the caller guarantees
     // nrad <= 4096 (checked on the Python side where the offsets live on the host)
     static const bool force_warp = [] { const char* e = getenv("HP_B200_RADIAL_WARP"); return e && e[0] == '1'; }();
     if (!force_warp && nrad_max <= kRadThreads * kRadOwn) {
-        shell_fixed_point_block_kernel<false><<<natom, kRadThreads, 0, as_stream(stream)>>>(
-            natom, atom_base, rad_offsets, rad_r, rad_w4, sph_avg, par_offsets, propars, nullptr, nullptr,
-            pseudo_numbers, inner_threshold, density_cutoff, max_inner, charges, msd, niter, flags);
+        // shells per atom: <= 3 up to argon (mbis.py:36-46); the small instantiation halves the code size
+        if (nshell_max <= 3)
+            shell_fixed_point_block_kernel<false, 3><<<natom, kRadThreads, 0, as_stream(stream)>>>(
+                natom, atom_base, rad_offsets, rad_r, rad_w4, sph_avg, par_offsets, propars, nullptr, nullptr,
+                pseudo_numbers, inner_threshold, density_cutoff, max_inner, charges, msd, niter, flags);
+        else
+            shell_fixed_point_block_kernel<false, kMaxMbisShells><<<natom, kRadThreads, 0, as_stream(stream)>>>(
+                natom, atom_base, rad_offsets, rad_r, rad_w4, sph_avg, par_offsets, propars, nullptr, nullptr,
+                pseudo_numbers, inner_threshold, density_cutoff, max_inner, charges, msd, niter, flags);
         HP_LAUNCH_CHECK("shell_fixed_point_block_kernel<mbis>");
         return HP_OK;
     }
@@ -1185,19 +1213,25 @@ extern "C" int hp_nlis_radial_solve(int32_t natom, int32_t atom_base, const int3
                                     const int32_t* shell_offsets, const double* inv_gamma,
                                     const double* pseudo_numbers, double inner_threshold,
                                     double density_cutoff, int32_t max_inner, int32_t nrad_max,
-                                    double* charges, double* msd, int32_t* niter, uint32_t* flags,
-                                    void* stream) {
+                                    int32_t nshell_max, double* charges, double* msd, int32_t* niter,
+                                    uint32_t* flags, void* stream) {
     HP_REQUIRE(natom >= 0, "bad sizes");
     if (natom == 0) return HP_OK;
     HP_REQUIRE(rad_offsets && rad_r && rad_w4 && sph_avg && par_offsets && propars &&
                    shell_offsets && inv_gamma && pseudo_numbers && charges && msd && niter && flags,
                "null input");
     HP_REQUIRE(nrad_max > 0 && nrad_max <= 4096, "nrad_max must be in 1..4096");
+    HP_REQUIRE(nshell_max > 0 && nshell_max <= kMaxMbisShells, "nshell_max must be in 1..7");
     static const bool force_warp = [] { const char* e = getenv("HP_B200_RADIAL_WARP"); return e && e[0] == '1'; }();
     if (!force_warp && nrad_max <= kRadThreads * kRadOwn) {
-        shell_fixed_point_block_kernel<true><<<natom, kRadThreads, 0, as_stream(stream)>>>(
-            natom, atom_base, rad_offsets, rad_r, rad_w4, sph_avg, par_offsets, propars, shell_offsets, inv_gamma,
-            pseudo_numbers, inner_threshold, density_cutoff, max_inner, charges, msd, niter, flags);
+        if (nshell_max <= 3)
+            shell_fixed_point_block_kernel<true, 3><<<natom, kRadThreads, 0, as_stream(stream)>>>(
+                natom, atom_base, rad_offsets, rad_r, rad_w4, sph_avg, par_offsets, propars, shell_offsets, inv_gamma,
+                pseudo_numbers, inner_threshold, density_cutoff, max_inner, charges, msd, niter, flags);
+        else
+            shell_fixed_point_block_kernel<true, kMaxMbisShells><<<natom, kRadThreads, 0, as_stream(stream)>>>(
+                natom, atom_base, rad_offsets, rad_r, rad_w4, sph_avg, par_offsets, propars, shell_offsets, inv_gamma,
+                pseudo_numbers, inner_threshold, density_cutoff, max_inner, charges, msd, niter, flags);
         HP_LAUNCH_CHECK("shell_fixed_point_block_kernel<nlis>");
         return HP_OK;
     }

@@ -145,15 +145,19 @@ spline_build_inv_kernel(int natom, const int* __restrict__ knot_off, const doubl
     __syncthreads();
     const double* AT = invT + inv_off[a];  // AT[j * n + i] = (A^-1)[i][j]
     for (int i = threadIdx.x; i < n; i += kSbThreads) {
-        double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;  // four partial sums: short dependency chains
+        // eight partial sums, sixteen independent loads per trip: the product is bound by the latency of the
+        // (L2-resident) matrix reads, not by arithmetic
+        double acc[8] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
         int j = 0;
-        for (; j + 3 < n; j += 4) {
-            s0 = fma(AT[(long long)j * n + i], rhs[j], s0);
-            s1 = fma(AT[(long long)(j + 1) * n + i], rhs[j + 1], s1);
-            s2 = fma(AT[(long long)(j + 2) * n + i], rhs[j + 2], s2);
-            s3 = fma(AT[(long long)(j + 3) * n + i], rhs[j + 3], s3);
+        for (; j + 15 < n; j += 16) {
+            double m[16];
+#pragma unroll
+            for (int u = 0; u < 16; ++u) m[u] = AT[(long long)(j + u) * n + i];
+#pragma unroll
+            for (int u = 0; u < 16; ++u) acc[u & 7] = fma(m[u], rhs[j + u], acc[u & 7]);
         }
-        for (; j < n; ++j) s0 = fma(AT[(long long)j * n + i], rhs[j], s0);
+        for (; j < n; ++j) acc[j & 7] = fma(AT[(long long)j * n + i], rhs[j], acc[j & 7]);
+        const double s0 = acc[0] + acc[4], s1 = acc[1] + acc[5], s2 = acc[2] + acc[6], s3 = acc[3] + acc[7];
         sd[i] = (s0 + s1) + (s2 + s3);
     }
     __syncthreads();
@@ -591,30 +595,34 @@ extern "C" int hp_promol_weights_spline(int64_t npts, const double* px, const do
         return HP_OK;
     }
     const size_t smem = sizeof(double) * 5 * kSplTileKnots;
-    // small grids: fewer points per thread so that the chunks cover the SMs
-    const bool small = npts < int64_t(sm_count()) * 3 * kSplThreads * 4;
     static bool configured = false;
     if (!configured) {
         int rc = check_cuda(cudaFuncSetAttribute(promol_weights_spline_kernel<4>,
                                                  cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)), "cudaFuncSetAttribute");
-        if (rc) return rc;
-        rc = check_cuda(cudaFuncSetAttribute(promol_weights_spline_kernel<1>,
-                                             cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)), "cudaFuncSetAttribute");
+        if (rc == HP_OK)
+            rc = check_cuda(cudaFuncSetAttribute(promol_weights_spline_kernel<2>,
+                                                 cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)), "cudaFuncSetAttribute");
+        if (rc == HP_OK)
+            rc = check_cuda(cudaFuncSetAttribute(promol_weights_spline_kernel<1>,
+                                                 cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)), "cudaFuncSetAttribute");
         if (rc) return rc;
         configured = true;
     }
-    const int pts = small ? 1 : 4;
-    const int64_t span = int64_t(kSplThreads) * pts;
-    int64_t grid = (npts + span - 1) / span;
+    // points per thread: 4 when that still gives >= 4 chunks per resident block, else 2 or 1 so that small
+    // grids (config 2: 582,000 points = 569 chunks of 1,024 on 444 resident blocks) fill whole waves
     int64_t cap = int64_t(sm_count()) * 3;
     if (cap > npartial) cap = npartial;
+    auto chunks = [&](int pts) { return (npts + int64_t(kSplThreads) * pts - 1) / (int64_t(kSplThreads) * pts); };
+    const int pts = chunks(4) >= 4 * cap ? 4 : (chunks(2) >= 2 * cap ? 2 : 1);
+    int64_t grid = chunks(pts);
     if (grid > cap) grid = cap;
 #define HP_SPL_ARGS                                                                                        \
     npts, px, py, pz, point_base, natom, atom_xyz, atom_point_offsets, knot_offsets, knots, coef, lut_meta, \
         lut, ntile, tile_atom_offsets, proatom_offset, rho, molw, density_cutoff, promol, at_weights,      \
         entropy_partials, npartial
-    if (small) promol_weights_spline_kernel<1><<<int(grid), kSplThreads, smem, as_stream(stream)>>>(HP_SPL_ARGS);
-    else promol_weights_spline_kernel<4><<<int(grid), kSplThreads, smem, as_stream(stream)>>>(HP_SPL_ARGS);
+    if (pts == 4) promol_weights_spline_kernel<4><<<int(grid), kSplThreads, smem, as_stream(stream)>>>(HP_SPL_ARGS);
+    else if (pts == 2) promol_weights_spline_kernel<2><<<int(grid), kSplThreads, smem, as_stream(stream)>>>(HP_SPL_ARGS);
+    else promol_weights_spline_kernel<1><<<int(grid), kSplThreads, smem, as_stream(stream)>>>(HP_SPL_ARGS);
 #undef HP_SPL_ARGS
     HP_LAUNCH_CHECK("promol_weights_spline_kernel");
     return HP_OK;

@@ -157,7 +157,7 @@ class MBISWPart(AbstractISAWPart):
         _lib.call(
             "hp_mbis_radial_solve", sh.nlocal, sh.atom_lo, slab.rad_offsets, slab.rad_r, slab.rad_w4,
             slab.sph_avg, self._par_offsets, st.propars, self._pseudo, float(self._inner_threshold),
-            float(self.density_cutoff), int(self.max_inner), slab.nrad_max, st.charges, st.msd, st.niter, st.flags,
+            float(self.density_cutoff), int(self.max_inner), slab.nrad_max, int(max(self._nshells)), st.charges, st.msd, st.niter, st.flags,
             stream_ptr(slab.device),
         )  # fmt: skip
 

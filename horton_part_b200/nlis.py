@@ -156,7 +156,7 @@ class NLISWPart(AbstractISAWPart):
         _lib.call(
             "hp_nlis_radial_solve", sh.nlocal, sh.atom_lo, slab.rad_offsets, slab.rad_r, slab.rad_w4,
             slab.sph_avg, self._par_offsets, st.propars, self._table.offsets, self._inv_gamma, self._pseudo,
-            float(self._inner_threshold), float(self.density_cutoff), int(self.max_inner), slab.nrad_max, st.charges,
+            float(self._inner_threshold), float(self.density_cutoff), int(self.max_inner), slab.nrad_max, int(max(self._nshells)), st.charges,
             st.msd, st.niter, st.flags, stream_ptr(slab.device),
         )  # fmt: skip
 

@@ -189,7 +189,8 @@ HP_API int hp_shell_harmonics(int32_t nshell, int32_t lmax, const int64_t* shell
 /* ------------------------------------------------------------------------------------------
  * (rows a9 + a10 change) per-atom radial solves, one thread block per atom (one warp for radial grids
  * beyond 256 points / basis sets beyond 24 shells), all atoms in one launch.  nrad_max = largest number
- * of radial points of the atoms of the launch (chooses the kernel shape).
+ * of radial points of the atoms of the launch, nshell_max = largest number of shells of one atom (both choose
+ * the kernel shape).
  * Radial data are concatenated over atoms: atom a owns entries rad_offsets[a]..rad_offsets[a+1]
  * of rad_r (rgrid.points), rad_w4 (4 pi r^2 w_rad) and sph_avg.
  *
@@ -207,8 +208,8 @@ HP_API int hp_shell_harmonics(int32_t nshell, int32_t lmax, const int64_t* shell
 HP_API int hp_mbis_radial_solve(int32_t natom, int32_t atom_base, const int32_t* rad_offsets, const double* rad_r,
                          const double* rad_w4, const double* sph_avg, const int32_t* par_offsets,
                          double* propars, const double* pseudo_numbers, double inner_threshold,
-                         double density_cutoff, int32_t max_inner, int32_t nrad_max, double* charges,
-                         double* msd, int32_t* niter, uint32_t* flags, void* stream);
+                         double density_cutoff, int32_t max_inner, int32_t nrad_max, int32_t nshell_max,
+                         double* charges, double* msd, int32_t* niter, uint32_t* flags, void* stream);
 
 /* hp_nlis_radial_solve -- opt_nlis_propars (nlis.py:99-194): shells (N, S, n) with n fixed,
  * propars [N,S,n]*K per atom; shell_offsets (natom+1, global) index inv_gamma = 1/Gamma(3/n). */
@@ -217,8 +218,8 @@ HP_API int hp_nlis_radial_solve(int32_t natom, int32_t atom_base, const int32_t*
                                 const int32_t* par_offsets, double* propars,
                                 const int32_t* shell_offsets, const double* inv_gamma,
                                 const double* pseudo_numbers, double inner_threshold,
-                                double density_cutoff, int32_t max_inner, int32_t nrad_max, double* charges,
-                                double* msd, int32_t* niter, uint32_t* flags, void* stream);
+                                double density_cutoff, int32_t max_inner, int32_t nrad_max, int32_t nshell_max,
+                                double* charges, double* msd, int32_t* niter, uint32_t* flags, void* stream);
 
 /* hp_lisa_sc_radial_solve -- aLISA `solver_sc` (alisa.py:193-291) / `solver_sc_1_iter` (:294-353)
  * with compute_quantities (utils.py:198-252): c_k <- sum_i w_i c_k g_k(r_i) rho_i / pro_i.

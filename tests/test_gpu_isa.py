@@ -94,7 +94,7 @@ def _compare(part, ref, rtol=1e-8):
     np.testing.assert_allclose(part["charges"], ref["charges"], rtol=rtol, atol=1e-9)
     np.testing.assert_allclose(part["history_changes"], ref["history_changes"], rtol=1e-5)
     np.testing.assert_allclose(part["history_entropies"], ref["history_entropies"], rtol=rtol, atol=1e-11)
-    np.testing.assert_allclose(part["propars"], ref["propars"], rtol=1e-7, atol=1e-12)
+    np.testing.assert_allclose(part["propars"], ref["propars"], rtol=1e-9, atol=1e-12)  # measured 6e-14 (values > 1e-6)
 
 
 def test_isa_h2o_against_reference_run(h2o):
