@@ -70,7 +70,7 @@ EXPORTS = {
     "hp_spline_tile_limits": (None, [_p, _p]),
     "hp_promol_weights_spline": (
         _int,
-        [_i64, _p, _p, _p, _i64, _i32, _p, _p, _p, _p, _p, _p, _p, _i32, _p, _f64, _p, _p, _f64, _p, _p, _p, _p],
+        [_i64, _p, _p, _p, _i64, _i32, _p, _p, _p, _p, _p, _p, _p, _i32, _p, _f64, _f64, _p, _p, _f64, _p, _p, _p, _p],
     ),
     "hp_isa_update": (_int, [_i32, _i32, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
     "hp_spline_integral_blocks": (_i32, [_i64]),
@@ -108,6 +108,14 @@ EXPORTS = {
     "hp_host_is_pinned": (_int, [_p]),
     "hp_host_to_device": (_int, [_p, _p, _sz, _p, _sz, _i32, _p]),
     "hp_dfma_probe": (_int, [_i32, _p, _p, _p, _p]),
+    "hp_shell_moments_table": (
+        _int,
+        [_i64, _p, _p, _p, _i32, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _f64, _i32, _i32, _i32, _p, _p, _p],
+    ),
+    "hp_hessian_table": (
+        _int,
+        [_i64, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _f64, _i32, _p, _sz, _p, _p],
+    ),
     "hp_aim_on_points": (_int, [_int, _i64, _p, _p, _p, _i32, _p, _p, _p, _p, _p, _i32, _p, _p, _f64, _p, _p, _p, _p]),
     "hp_comm_nccl_version": (_i32, []),
     "hp_comm_unique_id": (_int, [_p]),

@@ -18,6 +18,7 @@
 
 #include "hp_common.cuh"
 #include "hp_math.cuh"
+#include "hp_table.cuh"
 
 namespace hp {
 
@@ -63,6 +64,38 @@ basis_chunk_kernel(int64_t p0, int pc, int M, int Mpad, const double* __restrict
                 e = exp(-shell_alpha[m] * rn);
             }
             v = su * shell_norm[m] * e;
+        }
+        row[m] = v;
+    }
+}
+
+// The same panel for tabulated basis functions (basis_type="numeric"): Gu[p][m] = sqrt(u_p) S_m(r_pm).
+__global__ void __launch_bounds__(256)
+table_basis_chunk_kernel(int64_t p0, int pc, int M, int Mpad, const double* __restrict__ px,
+                         const double* __restrict__ py, const double* __restrict__ pz,
+                         const double* __restrict__ rho, const double* __restrict__ molw,
+                         const double* __restrict__ promol, double cutoff, const int* __restrict__ shell_atom,
+                         const double* __restrict__ atom_xyz, TableArgs tab, int64_t npts,
+                         double* __restrict__ Gu) {
+    const int lp = blockIdx.x;
+    if (lp >= pc) return;
+    const int64_t p = p0 + lp;
+    double su = 0.0, x = 0.0, y = 0.0, z = 0.0;
+    if (p < npts) {
+        const double r0 = promol[p], rh = rho[p];
+        const bool sick = (rh < cutoff) || (r0 < cutoff);
+        su = sick ? 0.0 : sqrt(molw[p] * rh / r0 / r0);
+        x = px[p]; y = py[p]; z = pz[p];
+    }
+    double* row = Gu + int64_t(lp) * Mpad;
+    for (int m = threadIdx.x; m < Mpad; m += blockDim.x) {
+        double v = 0.0;
+        if (m < M && su != 0.0) {
+            const int a = shell_atom[m];
+            const double dx = x - atom_xyz[3 * a], dy = y - atom_xyz[3 * a + 1], dz = z - atom_xyz[3 * a + 2];
+            double d;
+            const int i = table_interval(tab, a, sqrt_nocall(fma(dz, dz, fma(dy, dy, dx * dx))), d);
+            v = su * table_cubic(tab.shell_coef + tab.shell_coef_off[m] + 4 * i, d);
         }
         row[m] = v;
     }
@@ -167,7 +200,7 @@ syrk_panel_kernel(const double* __restrict__ Gu, int Mpad, int pc_sub, const int
 // b0 = B[lane%4][lane/4], C c0,c1 = C[lane/4][2 (lane%4) + 0,1].  Here A[m][k] = Gu[p0+k][row0+m] and
 // B[k][n] = Gu[p0+k][col0+n]: both operands are read from the same point-major slab.
 // ---------------------------------------------------------------------------------------------
-constexpr int kDK = 16;            // points per shared-memory slab
+constexpr int kDK = 32;            // points per shared-memory slab (3 stages x 2 x 32 x 132 doubles = 203 KB)
 constexpr int kDStride = kHT + 4;  // padded row length of a slab row (doubles)
 constexpr int kDStages = 3;
 
@@ -315,7 +348,7 @@ static int hessian_split(int ntile) {
 static int hessian_chunk_points(int Mpad, int nsplit) {
     int64_t pc = (int64_t(512) << 20) / (int64_t(Mpad) * 8);
     if (pc > 65536) pc = 65536;
-    const int q = nsplit * kHK;
+    const int q = nsplit * (kDK > kHK ? kDK : kHK);  // whole slabs of either tile-product kernel
     pc = (pc / q) * q;
     return int(pc < q ? q : pc);
 }
@@ -331,26 +364,49 @@ extern "C" size_t hp_hessian_scratch_bytes(int32_t M) {
     const size_t panel = size_t(hessian_chunk_points(Mpad, nsplit)) * Mpad * sizeof(double);
     const size_t parts = size_t(nsplit) * Mpad * Mpad * sizeof(double);
     const size_t tiles = size_t(nt) * (nt + 1) / 2 * sizeof(int2);
-    return panel + parts + ((tiles + 255) / 256) * 256;
+    return 2 * panel + parts + ((tiles + 255) / 256) * 256;  // two panels: producer / consumer overlap
 }
 
-extern "C" int hp_hessian(int functor, int64_t npts, const double* px, const double* py,
-                          const double* pz, const double* atom_xyz, const int32_t* shell_atom,
-                          const double* shell_norm, const double* shell_alpha,
-                          const double* shell_order, const double* rho, const double* molw,
-                          const double* promol, double density_cutoff, int32_t M, void* scratch,
-                          size_t scratch_bytes, double* H, void* stream) {
-    HP_REQUIRE(npts > 0 && M > 0, "bad sizes");
-    HP_REQUIRE(px && py && pz && atom_xyz && shell_atom && shell_norm && shell_alpha && rho && molw &&
-                   promol && scratch && H, "null input");
-    HP_REQUIRE(functor != HP_FUNCTOR_GENERAL || shell_order, "general functor needs shell_order");
+namespace {
+
+// side stream + events of the panel pipeline, one set per device, created on first use
+struct HessianPipe {
+    cudaStream_t side = nullptr;
+    cudaEvent_t ready[2] = {nullptr, nullptr}, consumed[2] = {nullptr, nullptr}, start = nullptr;
+};
+
+int hessian_pipe(HessianPipe** out) {
+    static HessianPipe pipes[64];
+    int dev = 0;
+    int rc = check_cuda(cudaGetDevice(&dev), "cudaGetDevice");
+    if (rc) return rc;
+    HP_REQUIRE(dev >= 0 && dev < 64, "device index out of range");
+    HessianPipe& p = pipes[dev];
+    if (!p.side) {
+        rc = check_cuda(cudaStreamCreateWithFlags(&p.side, cudaStreamNonBlocking), "cudaStreamCreate");
+        for (int i = 0; i < 2 && rc == HP_OK; ++i) {
+            rc = check_cuda(cudaEventCreateWithFlags(&p.ready[i], cudaEventDisableTiming), "cudaEventCreate");
+            if (rc == HP_OK) rc = check_cuda(cudaEventCreateWithFlags(&p.consumed[i], cudaEventDisableTiming), "cudaEventCreate");
+        }
+        if (rc == HP_OK) rc = check_cuda(cudaEventCreateWithFlags(&p.start, cudaEventDisableTiming), "cudaEventCreate");
+        if (rc) return rc;
+    }
+    *out = &p;
+    return HP_OK;
+}
+
+// H = sum over chunks of panel^T panel.  `produce(p0, pc, Mpad, panel, stream)` launches the kernel that fills
+// one chunk of the panel.  Panels are double-buffered: chunk c + 1 is generated on a side stream while the
+// tile product of chunk c runs (the generator is 6 % of the work and the tile product leaves a third of
+// every SM's registers and most issue slots free).
+template <class Produce>
+int hessian_run(int64_t npts, int32_t M, void* scratch, size_t scratch_bytes, double* H, cudaStream_t st, Produce produce) {
     HP_REQUIRE(scratch_bytes >= hp_hessian_scratch_bytes(M), "scratch too small");
-    cudaStream_t st = as_stream(stream);
     const int Mpad = hessian_mpad(M), nt = Mpad / kHT, ntile = nt * (nt + 1) / 2;
     const int nsplit = hessian_split(ntile);
     const int pc = hessian_chunk_points(Mpad, nsplit), pc_sub = pc / nsplit;
-    double* panel = static_cast<double*>(scratch);
-    double* parts = panel + size_t(pc) * Mpad;
+    double* panel[2] = {static_cast<double*>(scratch), static_cast<double*>(scratch) + size_t(pc) * Mpad};
+    double* parts = panel[1] + size_t(pc) * Mpad;
     int2* tiles = reinterpret_cast<int2*>(parts + size_t(nsplit) * Mpad * Mpad);
     // tensor-core (DMMA) tile product by default; HP_B200_HESSIAN_DFMA=1 selects the vector-FMA kernel
     static const bool use_dfma = [] { const char* e = getenv("HP_B200_HESSIAN_DFMA"); return e && e[0] == '1'; }();
@@ -368,40 +424,80 @@ extern "C" int hp_hessian(int functor, int64_t npts, const double* px, const dou
             configured = true;
         }
     }
+    HessianPipe* pipe = nullptr;
+    int rc = hessian_pipe(&pipe);
+    if (rc) return rc;
     // tile list (upper triangle), written on the device: no host allocation, copy or synchronisation
     tile_list_kernel<<<1, 256, 0, st>>>(nt, tiles);
     HP_LAUNCH_CHECK("tile_list_kernel");
-    int rc = HP_OK;
     rc = check_cuda(cudaMemsetAsync(parts, 0, sizeof(double) * nsplit * size_t(Mpad) * Mpad, st), "memset");
     if (rc) return rc;
-    for (int64_t p0 = 0; p0 < npts; p0 += pc) {
-        switch (functor) {
-            case HP_FUNCTOR_SLATER:
-                basis_chunk_kernel<HP_FUNCTOR_SLATER><<<pc, 256, 0, st>>>(
-                    p0, pc, M, Mpad, px, py, pz, rho, molw, promol, density_cutoff, shell_atom, atom_xyz,
-                    shell_norm, shell_alpha, shell_order, npts, panel);
-                break;
-            case HP_FUNCTOR_GAUSS:
-                basis_chunk_kernel<HP_FUNCTOR_GAUSS><<<pc, 256, 0, st>>>(
-                    p0, pc, M, Mpad, px, py, pz, rho, molw, promol, density_cutoff, shell_atom, atom_xyz,
-                    shell_norm, shell_alpha, shell_order, npts, panel);
-                break;
-            case HP_FUNCTOR_GENERAL:
-                basis_chunk_kernel<HP_FUNCTOR_GENERAL><<<pc, 256, 0, st>>>(
-                    p0, pc, M, Mpad, px, py, pz, rho, molw, promol, density_cutoff, shell_atom, atom_xyz,
-                    shell_norm, shell_alpha, shell_order, npts, panel);
-                break;
-            default:
-                set_error("hp_hessian: unsupported functor %d", functor);
-                return HP_ERR_ARG;
-        }
-        HP_LAUNCH_CHECK("basis_chunk_kernel");
-        if (use_dfma) syrk_panel_kernel<<<dim3(ntile, nsplit), 256, syrk_smem, st>>>(panel, Mpad, pc_sub, tiles, parts);
-        else syrk_panel_dmma_kernel<<<dim3(ntile, nsplit), 256, syrk_smem, st>>>(panel, Mpad, pc_sub, tiles, parts);
+    // the side stream starts after everything already queued on `st` (promolecule, weights)
+    rc = check_cuda(cudaEventRecord(pipe->start, st), "cudaEventRecord");
+    if (rc == HP_OK) rc = check_cuda(cudaStreamWaitEvent(pipe->side, pipe->start, 0), "cudaStreamWaitEvent");
+    int64_t chunk = 0;
+    for (int64_t p0 = 0; p0 < npts && rc == HP_OK; p0 += pc, ++chunk) {
+        const int b = int(chunk & 1);
+        if (chunk >= 2) rc = check_cuda(cudaStreamWaitEvent(pipe->side, pipe->consumed[b], 0), "cudaStreamWaitEvent");
+        if (rc == HP_OK) rc = produce(p0, pc, Mpad, panel[b], pipe->side);
+        if (rc == HP_OK) rc = check_cuda(cudaEventRecord(pipe->ready[b], pipe->side), "cudaEventRecord");
+        if (rc == HP_OK) rc = check_cuda(cudaStreamWaitEvent(st, pipe->ready[b], 0), "cudaStreamWaitEvent");
+        if (rc) break;
+        if (use_dfma) syrk_panel_kernel<<<dim3(ntile, nsplit), 256, syrk_smem, st>>>(panel[b], Mpad, pc_sub, tiles, parts);
+        else syrk_panel_dmma_kernel<<<dim3(ntile, nsplit), 256, syrk_smem, st>>>(panel[b], Mpad, pc_sub, tiles, parts);
         HP_LAUNCH_CHECK("syrk_panel_kernel");
+        rc = check_cuda(cudaEventRecord(pipe->consumed[b], st), "cudaEventRecord");
     }
+    if (rc) return rc;
     const int64_t total = int64_t(M) * M;
     hessian_finish_kernel<<<int((total + 255) / 256), 256, 0, st>>>(M, Mpad, nsplit, parts, H);
     HP_LAUNCH_CHECK("hessian_finish_kernel");
     return HP_OK;
+}
+
+}  // namespace
+
+extern "C" int hp_hessian(int functor, int64_t npts, const double* px, const double* py,
+                          const double* pz, const double* atom_xyz, const int32_t* shell_atom,
+                          const double* shell_norm, const double* shell_alpha,
+                          const double* shell_order, const double* rho, const double* molw,
+                          const double* promol, double density_cutoff, int32_t M, void* scratch,
+                          size_t scratch_bytes, double* H, void* stream) {
+    HP_REQUIRE(npts > 0 && M > 0, "bad sizes");
+    HP_REQUIRE(px && py && pz && atom_xyz && shell_atom && shell_norm && shell_alpha && rho && molw &&
+                   promol && scratch && H, "null input");
+    HP_REQUIRE(functor != HP_FUNCTOR_GENERAL || shell_order, "general functor needs shell_order");
+    HP_REQUIRE(functor == HP_FUNCTOR_SLATER || functor == HP_FUNCTOR_GAUSS || functor == HP_FUNCTOR_GENERAL,
+               "unsupported functor");
+    auto produce = [&](int64_t p0, int pc, int Mpad, double* panel, cudaStream_t s) -> int {
+#define HP_BASIS(F)                                                                                         \
+    basis_chunk_kernel<F><<<pc, 256, 0, s>>>(p0, pc, M, Mpad, px, py, pz, rho, molw, promol, density_cutoff, \
+                                             shell_atom, atom_xyz, shell_norm, shell_alpha, shell_order, npts, panel)
+        if (functor == HP_FUNCTOR_SLATER) HP_BASIS(HP_FUNCTOR_SLATER);
+        else if (functor == HP_FUNCTOR_GAUSS) HP_BASIS(HP_FUNCTOR_GAUSS);
+        else HP_BASIS(HP_FUNCTOR_GENERAL);
+#undef HP_BASIS
+        HP_LAUNCH_CHECK("basis_chunk_kernel");
+        return HP_OK;
+    };
+    return hessian_run(npts, M, scratch, scratch_bytes, H, as_stream(stream), produce);
+}
+
+extern "C" int hp_hessian_table(int64_t npts, const double* px, const double* py, const double* pz,
+                                const double* atom_xyz, const int32_t* shell_atom, const int32_t* knot_offsets,
+                                const double* knots, const int32_t* lut_meta, const uint16_t* lut,
+                                const int64_t* shell_coef_offsets, const double* shell_coef, const double* rho,
+                                const double* molw, const double* promol, double density_cutoff, int32_t M,
+                                void* scratch, size_t scratch_bytes, double* H, void* stream) {
+    HP_REQUIRE(npts > 0 && M > 0, "bad sizes");
+    HP_REQUIRE(px && py && pz && atom_xyz && shell_atom && knot_offsets && knots && lut_meta && lut &&
+                   shell_coef_offsets && shell_coef && rho && molw && promol && scratch && H, "null input");
+    TableArgs tab{knot_offsets, knots, lut_meta, lut, reinterpret_cast<const long long*>(shell_coef_offsets), shell_coef};
+    auto produce = [&](int64_t p0, int pc, int Mpad, double* panel, cudaStream_t s) -> int {
+        table_basis_chunk_kernel<<<pc, 256, 0, s>>>(p0, pc, M, Mpad, px, py, pz, rho, molw, promol, density_cutoff,
+                                                    shell_atom, atom_xyz, tab, npts, panel);
+        HP_LAUNCH_CHECK("table_basis_chunk_kernel");
+        return HP_OK;
+    };
+    return hessian_run(npts, M, scratch, scratch_bytes, H, as_stream(stream), produce);
 }

@@ -227,7 +227,7 @@ promol_weights_spline_kernel(int64_t npts, const double* __restrict__ px, const 
                              const int* __restrict__ knot_off, const double* __restrict__ knots,
                              const double* __restrict__ coef, const int* __restrict__ lut_meta,
                              const unsigned short* __restrict__ lut, int ntile,
-                             const int* __restrict__ tile_off, double proatom_offset,
+                             const int* __restrict__ tile_off, double proatom_offset, double promol_offset,
                              const double* __restrict__ rho, const double* __restrict__ molw,
                              double density_cutoff, double* __restrict__ promol_out,
                              double* __restrict__ w_out, double* __restrict__ entropy_partials,
@@ -354,7 +354,7 @@ promol_weights_spline_kernel(int64_t npts, const double* __restrict__ px, const 
                     // eval_proatom (core/stockholder.py:343-349): spline(r) + 1e-100 ...
                     const double f = res + proatom_offset;
                     // ... update_pro (:169-170): promoldens += work; promoldens += 1e-100
-                    pro[j] = (pro[j] + f) + 1e-100;
+                    pro[j] = (pro[j] + f) + promol_offset;
                     own[j] = (a == owner[j]) ? f : own[j];
                 }
             }
@@ -579,7 +579,7 @@ extern "C" int hp_promol_weights_spline(int64_t npts, const double* px, const do
                                         const int32_t* knot_offsets, const double* knots,
                                         const double* coef, const int32_t* lut_meta, const uint16_t* lut,
                                         int32_t ntile, const int32_t* tile_atom_offsets,
-                                        double proatom_offset, const double* rho,
+                                        double proatom_offset, double promol_offset, const double* rho,
                                         const double* molw, double density_cutoff, double* promol,
                                         double* at_weights, double* entropy_partials, void* stream) {
     HP_REQUIRE(npts >= 0 && natom > 0 && ntile > 0, "bad sizes");
@@ -618,7 +618,8 @@ extern "C" int hp_promol_weights_spline(int64_t npts, const double* px, const do
     if (grid > cap) grid = cap;
 #define HP_SPL_ARGS                                                                                        \
     npts, px, py, pz, point_base, natom, atom_xyz, atom_point_offsets, knot_offsets, knots, coef, lut_meta, \
-        lut, ntile, tile_atom_offsets, proatom_offset, rho, molw, density_cutoff, promol, at_weights,      \
+        lut, ntile, tile_atom_offsets, proatom_offset, promol_offset, rho, molw, density_cutoff, promol,    \
+        at_weights,                                                                                      \
         entropy_partials, npartial
     if (pts == 4) promol_weights_spline_kernel<4><<<int(grid), kSplThreads, smem, as_stream(stream)>>>(HP_SPL_ARGS);
     else if (pts == 2) promol_weights_spline_kernel<2><<<int(grid), kSplThreads, smem, as_stream(stream)>>>(HP_SPL_ARGS);

@@ -121,22 +121,26 @@ class GlobalLinearISAWPart(AbstractStockholderWPart):
 
         from .core.device import ShellTable, to_device
 
-        if not isinstance(self.bs_helper, ExpBasisFuncHelper):
-            raise NotImplementedError('gLISA with basis_type="numeric" is not built: the moment and Hessian '
-                                      "kernels regenerate exponential basis functions (aLISA has it)")  # fmt: skip
+        self._numeric = not isinstance(self.bs_helper, ExpBasisFuncHelper)
+        if self._numeric and self.on_molgrid:
+            # as in the reference: the numeric helper has no exponents for the molecular-grid bookkeeping
+            raise NotImplementedError('gLISA with basis_type="numeric" needs grid_type=1')
         propars = gisa.init_propars(self)
         if not self.on_molgrid:
             gisa.evaluate_basis_functions(self)  # radial grids only: used by compute_change
         slab = self.slab
         dev = slab.device
-        orders = np.concatenate([np.asarray(self.bs_helper.get_order(z), float) for z in self.numbers])
-        alphas = np.concatenate([np.asarray(self.bs_helper.get_exponent(z), float) for z in self.numbers])
-        functor = 2 if np.all(orders == 2.0) else (1 if np.all(orders == 1.0) else 3)
-        self._table = ShellTable(slab, functor, self._nshells)
-        self._table.alpha.copy_(to_device(alphas, dev))
-        if functor == 3:
-            self._table.order.copy_(to_device(orders, dev))
-        self._norms = to_device(shell_norm(orders, alphas), dev)
+        if self._numeric:
+            self._init_numeric_tables(slab, dev)
+        else:
+            orders = np.concatenate([np.asarray(self.bs_helper.get_order(z), float) for z in self.numbers])
+            alphas = np.concatenate([np.asarray(self.bs_helper.get_exponent(z), float) for z in self.numbers])
+            functor = 2 if np.all(orders == 2.0) else (1 if np.all(orders == 1.0) else 3)
+            self._table = ShellTable(slab, functor, self._nshells)
+            self._table.alpha.copy_(to_device(alphas, dev))
+            if functor == 3:
+                self._table.order.copy_(to_device(orders, dev))
+            self._norms = to_device(shell_norm(orders, alphas), dev)
         self._c = to_device(propars, dev)
         self._par_offsets = to_device(np.asarray(self._ranges, dtype=np.int32), dev)
         sh = slab.shard
@@ -153,9 +157,46 @@ class GlobalLinearISAWPart(AbstractStockholderWPart):
         self._scal = torch.zeros(2, dtype=torch.float64, device=dev)
         return propars
 
+    def _init_numeric_tables(self, slab, dev):
+        """basis_type="numeric" (core/basis.py:330-387): every shell is a tabulated spline on its element's
+        knots.  The promolecule sum_m c_m S_m is ONE piecewise cubic per atom (coefficients mixed per
+        evaluation, as aLISA does) for ``hp_promol_weights_spline``; the shell integrals and the Hessian read
+        the per-shell coefficient blocks (``hp_shell_moments_table``, ``hp_hessian_table``)."""
+        from .core.device import to_device
+        from .isa import SplineTable
+
+        class _Knots:  # the SplineTable only needs .points / .size
+            def __init__(self, x):
+                self.points, self.size = x, x.size
+
+        helper = self.bs_helper
+        self._table = SplineTable(slab, [_Knots(helper.get_knots(int(z))) for z in self.numbers], proatom_offset=0.0)
+        self._ppoly = {int(z): helper.ppoly_coefficients(int(z)) for z in np.unique(self.numbers)}  # (K, nseg, 4)
+        pool, start, pos = [], {}, 0
+        for z, block in self._ppoly.items():
+            start[z] = pos
+            pool.append(block.ravel())
+            pos += block.size
+        offs = []
+        for z, k in zip(self.numbers, self._nshells):
+            seg = self._ppoly[int(z)].shape[1] * 4
+            offs.extend(start[int(z)] + j * seg for j in range(k))
+        self._shell_coef = to_device(np.concatenate(pool), dev)
+        self._shell_coef_off = to_device(np.asarray(offs, dtype=np.int64), dev, np.int64)
+        self._shell_offsets = to_device(np.asarray(self._ranges, dtype=np.int32), dev, np.int32)
+        self._norms = None
+
     def _refresh_table(self):
         from .core.device import stream_ptr
 
+        if self._numeric:
+            import torch
+
+            c = self._c.cpu().numpy()
+            mixed = [np.einsum("k,ksc->sc", c[self._ranges[a] : self._ranges[a + 1]], self._ppoly[int(z)])
+                     for a, z in enumerate(self.numbers)]  # fmt: skip
+            self._table.coef.copy_(torch.from_numpy(np.concatenate([m.ravel() for m in mixed])))
+            return
         t = self._table
         _lib.call("hp_table_scaled", t.nshell, self._c, self._norms, t.A, stream_ptr(self.slab.device))
 
@@ -171,7 +212,10 @@ class GlobalLinearISAWPart(AbstractStockholderWPart):
         from .core.device import stream_ptr
 
         self._refresh_table()
-        self._table.promol_weights(self.density_cutoff, True, False, True, promol_offset=0.0)
+        if self._numeric:
+            self._table.promol_weights(self.density_cutoff, True, False, True, proatom_offset=0.0, promol_offset=0.0)
+        else:
+            self._table.promol_weights(self.density_cutoff, True, False, True, promol_offset=0.0)
         slab = self.slab
         _lib.call("hp_sum_partials", slab.npartial, slab.entropy_partials, self._scal[1:], stream_ptr(slab.device))
 
@@ -180,6 +224,15 @@ class GlobalLinearISAWPart(AbstractStockholderWPart):
         from .core.device import stream_ptr
 
         t, s = self._table, self.slab
+        if self._numeric:
+            M = len(self._c)
+            _lib.call(
+                "hp_shell_moments_table", s.npts, s.px, s.py, s.pz, s.natom, s.atom_xyz, self._shell_offsets,
+                t.offsets, t.knots, t.lut_meta, t.lut, self._shell_coef_off, self._shell_coef, s.rho, s.molw,
+                s.promol, float(self.density_cutoff), int(power), M, int(max(self._nshells)), self._partial,
+                self._moments, stream_ptr(s.device),
+            )  # fmt: skip
+            return self._moments
         _lib.call(
             "hp_shell_moments", t.functor, s.npts, s.px, s.py, s.pz, s.natom, s.atom_xyz, t.offsets,
             self._norms, t.alpha, t.order, t.ntile, t.tiles, s.rho, s.molw, s.promol,
@@ -284,13 +337,21 @@ class GlobalLinearISAWPart(AbstractStockholderWPart):
         from .core.device import stream_ptr, to_device
 
         t, s = self._table, self.slab
-        M = t.nshell
+        M = len(self._c)
         if getattr(self, "_hess", None) is None:
             nbytes = int(_lib.call("hp_hessian_scratch_bytes", M))
             self._hess_scratch = torch.empty(nbytes, dtype=torch.uint8, device=s.device)
             self._hess = torch.zeros((M, M), dtype=torch.float64, device=s.device)
             shell_atom = np.repeat(np.arange(self.natom, dtype=np.int32), self._nshells)
             self._shell_atom = to_device(shell_atom, s.device)
+        if self._numeric:
+            _lib.call(
+                "hp_hessian_table", s.npts, s.px, s.py, s.pz, s.atom_xyz, self._shell_atom, t.offsets, t.knots,
+                t.lut_meta, t.lut, self._shell_coef_off, self._shell_coef, s.rho, s.molw, s.promol,
+                float(self.density_cutoff), M, self._hess_scratch, self._hess_scratch.numel(), self._hess,
+                stream_ptr(s.device),
+            )  # fmt: skip
+            return self._hess
         _lib.call(
             "hp_hessian", t.functor, s.npts, s.px, s.py, s.pz, s.atom_xyz, self._shell_atom, self._norms,
             t.alpha, t.order, s.rho, s.molw, s.promol, float(self.density_cutoff), M, self._hess_scratch,
@@ -663,14 +724,23 @@ class GlobalLinearISAWPart(AbstractStockholderWPart):
         # 1e-100 offsets, N_a = int clip(rho0_a/rho0, 0, 1) rho, without natom x Npts weight arrays
         t0 = time.time()
         self._refresh_table()
-        self._table.promol_weights(self.density_cutoff, True, True, False)
         t, s = self._table, self.slab
         pops = torch.zeros(self.natom, dtype=torch.float64, device=s.device)
-        _lib.call(
-            "hp_atom_weight_integrals", t.functor, s.npts, s.px, s.py, s.pz, s.natom, s.atom_xyz, t.offsets,
-            t.A, t.alpha, t.order, t.ntile, t.tiles, s.rho, s.molw, s.promol, self._partial, pops,
-            stream_ptr(s.device),
-        )  # fmt: skip
+        if self._numeric:
+            # eval_proatom of the reference adds no offset to a tabulated pro-atom (glisa.py:226-246);
+            # update_pro adds 1e-100 per atom to the promolecule
+            t.promol_weights(self.density_cutoff, True, True, False, proatom_offset=0.0)
+            nblk = int(_lib.call("hp_spline_integral_blocks", s.npts))
+            partial = torch.zeros(self.natom * nblk, dtype=torch.float64, device=s.device)
+            _lib.call("hp_atom_weight_integrals_spline", s.npts, s.px, s.py, s.pz, self.natom, s.atom_xyz, t.offsets,
+                      t.knots, t.coef, 0.0, s.rho, s.molw, s.promol, partial, pops, stream_ptr(s.device))  # fmt: skip
+        else:
+            t.promol_weights(self.density_cutoff, True, True, False)
+            _lib.call(
+                "hp_atom_weight_integrals", t.functor, s.npts, s.px, s.py, s.pz, s.natom, s.atom_xyz, t.offsets,
+                t.A, t.alpha, t.order, t.ntile, t.tiles, s.rho, s.molw, s.promol, self._partial, pops,
+                stream_ptr(s.device),
+            )  # fmt: skip
         self._all_reduce(pops)
         charges = self.cache.load("charges", alloc=self.natom, tags="o")[0]
         charges[:] = self.pseudo_numbers - pops.cpu().numpy()

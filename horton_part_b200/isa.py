@@ -108,7 +108,7 @@ class SplineTable:
                   stream_ptr(self.slab.device))  # fmt: skip
 
     def promol_weights(self, density_cutoff, want_promol=True, want_weights=True, want_entropy=True,
-                       proatom_offset=None):  # fmt: skip
+                       proatom_offset=None, promol_offset=1e-100):  # fmt: skip
         from .core.device import stream_ptr
 
         s = self.slab
@@ -117,7 +117,7 @@ class SplineTable:
         _lib.call(
             "hp_promol_weights_spline", s.npts, s.px, s.py, s.pz, s.point_base, s.natom, s.atom_xyz,
             s.atom_point_offsets, self.offsets, self.knots, self.coef, self.lut_meta, self.lut, self.ntile,
-            self.tiles, float(proatom_offset), s.rho,
+            self.tiles, float(proatom_offset), float(promol_offset), s.rho,
             s.molw, float(density_cutoff), s.promol if want_promol else None,
             s.at_w if want_weights else None, s.entropy_partials if want_entropy else None,
             stream_ptr(s.device),

@@ -108,13 +108,13 @@ class MBISWPart(AbstractISAWPart):
     def _init_propars(self):
         from .core.device import ShellTable, to_device
 
-        self._nshells = [int(get_nshell(z)) for z in self.numbers]
+        per_element = {int(z): get_initial_mbis_propars(int(z)) for z in np.unique(self.numbers)}  # once per element
+        self._nshells = [len(per_element[int(z)]) // 2 for z in self.numbers]
         self._ranges = [0]
         for k in self._nshells:
             self._ranges.append(self._ranges[-1] + 2 * k)
         propars = self.cache.load("propars", alloc=self._ranges[-1], tags="o")[0]
-        for a in range(self.natom):
-            propars[self._ranges[a] : self._ranges[a + 1]] = get_initial_mbis_propars(self.numbers[a])
+        propars[:] = np.concatenate([per_element[int(z)] for z in self.numbers])
         slab = self.slab
         self._table = ShellTable(slab, 1, self._nshells)  # HP_FUNCTOR_SLATER
         st = self._alloc_state(len(propars))

@@ -245,7 +245,9 @@ HP_API int hp_lisa_sc_radial_solve(int32_t natom, int32_t atom_base, const int32
  * coef[4*(knot_offsets[a]-a)].  clip_negative != 0 applies fix_proatom_rho (:218-219).  `work`
  * needs 2 doubles per knot.
  * hp_promol_weights_spline: like hp_promol_weights with rho0_a(p) = S_a(|r_p-R_a|) + proatom_offset
- * (eval_spline / eval_proatom, core/stockholder.py:271-350; proatom_offset = 1e-100).
+ * (eval_spline / eval_proatom, core/stockholder.py:271-350; proatom_offset = 1e-100) and promol_offset
+ * added per atom (update_pro's `promoldens += 1e-100`, core/stockholder.py:170; 0 for gLISA's
+ * calc_promol_dens, glisa.py:346-348).
  * hp_isa_update: propars_a = max(sph_avg_a, 1e-100), charge, change term (isa.py:102-122);
  * rad_w are the plain radial weights (rgrid.weights). */
 HP_API int hp_spline_build(int32_t natom, const int32_t* knot_offsets, const double* knots,
@@ -277,7 +279,7 @@ HP_API int hp_promol_weights_spline(int64_t npts, const double* px, const double
                                     const int32_t* knot_offsets, const double* knots,
                                     const double* coef, const int32_t* lut_meta, const uint16_t* lut,
                                     int32_t ntile, const int32_t* tile_atom_offsets,
-                                    double proatom_offset, const double* rho,
+                                    double proatom_offset, double promol_offset, const double* rho,
                                     const double* molw, double density_cutoff, double* promol,
                                     double* at_weights, double* entropy_partials, void* stream);
 HP_API int hp_isa_update(int32_t natom, int32_t atom_base, const int32_t* rad_offsets,
@@ -489,6 +491,28 @@ HP_API int hp_aim_on_points(int functor, int64_t npts, const double* px, const d
                             const double* shell_A, const double* shell_alpha, const double* shell_order,
                             int32_t ntile, const int32_t* tile_atom_offsets, const double* density,
                             double promol_offset, double* rho0, double* promol, double* aim_rho, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * (row a12 with basis_type="numeric", core/basis.py:330-387) gLISA on TABULATED basis functions: shell m is a
+ * piecewise cubic on its atom's knots (knot_offsets / knots as in hp_spline_build, interval tables lut_meta / lut
+ * as in hp_promol_weights_spline), 4 x (n_a - 1) PPoly coefficients (highest power first) at
+ * shell_coef + shell_coef_offsets[m]; atoms of one element share blocks.
+ *   hp_shell_moments_table  out[m] = sum_p t(p) S_m(r_pm), t as in hp_shell_moments (function_g, gradient);
+ *                           partial = hp_molgrid_num_blocks(npts) x nshell doubles of scratch
+ *   hp_hessian_table        H_mn = sum_p u(p) S_m S_n, u as in hp_hessian; same scratch and tile product */
+HP_API int hp_shell_moments_table(int64_t npts, const double* px, const double* py, const double* pz,
+                                  int32_t natom, const double* atom_xyz, const int32_t* atom_shell_offsets,
+                                  const int32_t* knot_offsets, const double* knots, const int32_t* lut_meta,
+                                  const uint16_t* lut, const int64_t* shell_coef_offsets,
+                                  const double* shell_coef, const double* rho, const double* molw,
+                                  const double* promol, double density_cutoff, int32_t power, int32_t nshell,
+                                  int32_t nshell_max_per_atom, double* partial, double* out, void* stream);
+HP_API int hp_hessian_table(int64_t npts, const double* px, const double* py, const double* pz,
+                            const double* atom_xyz, const int32_t* shell_atom, const int32_t* knot_offsets,
+                            const double* knots, const int32_t* lut_meta, const uint16_t* lut,
+                            const int64_t* shell_coef_offsets, const double* shell_coef, const double* rho,
+                            const double* molw, const double* promol, double density_cutoff, int32_t M,
+                            void* scratch, size_t scratch_bytes, double* H, void* stream);
 
 #ifdef __cplusplus
 }

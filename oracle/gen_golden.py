@@ -444,6 +444,27 @@ def case_numeric(natom=6, nrad=40, nang=50, seed=0):
     save("water6_numeric.npz", results, coordinates=coords, numbers=numbers, **extra)
 
 
+def case_numeric_glisa(natom=6, nrad=40, nang=50, seed=0):
+    """gLISA with basis_type="numeric" (core/basis.py:330-387 + glisa.py:226-246) on the 6-atom Slater
+    promolecule: fixed point, DIIS, exact Newton and the default convex programme."""
+    coords, numbers = synthetic.water_cluster(natom, seed)
+    grid = synthetic_grid(coords, numbers, nrad, nang)
+    rho = synthetic.slater_promolecule_host(grid.points, coords, numbers)
+    pseudo = numbers.astype(float)
+    results = {}
+    for tag, kw in {"glisa_sc": dict(solver="sc"), "glisa_diis": dict(solver="diis"), "glisa_newton": dict(solver="newton"),
+                    "glisa_m_newton": dict(solver="m-newton"), "glisa_cvxopt": dict(),
+                    "glisa_sc_slater": dict(solver="sc", basis_func="slater")}.items():  # fmt: skip
+        t0 = time.time()
+        try:
+            results[tag] = run_reference_light("glisa", coords, numbers, pseudo, grid, rho, basis_type="numeric", **kw)
+            print(f"  {tag}: niter={results[tag].get('niter')} q={results[tag]['charges'][:3]} {time.time()-t0:.1f}s")
+        except Exception as exc:
+            results[tag] = {"raised": np.array(f"{type(exc).__name__}: {exc}")}
+            print(f"  {tag}: reference raised {type(exc).__name__}: {exc}")
+    save("water6_numeric_glisa.npz", results, coordinates=coords, numbers=numbers)
+
+
 def case_proatomdb():
     """ProAtomDB.compact / normalize / compute_radii of the reference (core/proatomdb.py:154-190,
     390-447) on its cached HF/STO-3G records (the ones packed into h2o_hirshfeld.npz)."""
@@ -770,7 +791,7 @@ def case_config4(natom=12, nrad=150, nang=194, seed=0):
 
 
 CASES = {"h2o": case_h2o, "water6": case_water_cluster, "water6g": case_water_gauss, "hirshfeld": case_hirshfeld,
-         "solvers": case_water6_solvers, "convex": case_water6_convex, "convex_radial": case_convex_radial, "numeric": case_numeric, "proatomdb": case_proatomdb, "algo": case_algo, "postproc": case_postproc,
+         "solvers": case_water6_solvers, "convex": case_water6_convex, "convex_radial": case_convex_radial, "numeric": case_numeric, "numeric_glisa": case_numeric_glisa, "proatomdb": case_proatomdb, "algo": case_algo, "postproc": case_postproc,
          "molecules": case_molecules,
          "config2": case_config2, "config2_hi": case_config2_hi, "config3": case_config3, "config4": case_config4}
 

@@ -135,6 +135,27 @@ def test_alisa_numeric_basis_against_reference_run(water6, tag, kw):
         np.testing.assert_allclose(part["propars"], ref["propars"], rtol=1e-6, atol=1e-8)
 
 
-def test_glisa_numeric_basis_is_refused(water6):
-    with pytest.raises(NotImplementedError, match="numeric"):
-        _run("GlobalLinearISAWPart", water6, basis_type="numeric", solver="sc")
+@pytest.mark.parametrize("tag,kw", [
+    ("glisa_sc", dict(solver="sc")),
+    ("glisa_diis", dict(solver="diis")),
+    ("glisa_newton", dict(solver="newton")),
+    ("glisa_m_newton", dict(solver="m-newton")),
+])  # fmt: skip
+def test_glisa_numeric_basis_against_reference_run(water6, tag, kw):
+    """gLISA with basis_type="numeric" (core/basis.py:330-387, glisa.py:226-246): promolecule through the
+    mixed per-atom spline, shell integrals and Hessian from the tabulated shells (hp_shell_moments_table,
+    hp_hessian_table), charges from hp_atom_weight_integrals_spline.  Goldens: reference runs."""
+    from conftest import GOLDEN
+
+    ref = _gold(np.load(GOLDEN / "water6_numeric_glisa.npz"), tag)
+    part = _run("GlobalLinearISAWPart", water6, basis_type="numeric", **kw)
+    assert part["niter"] == int(ref["niter"])
+    np.testing.assert_allclose(part["charges"], ref["charges"], rtol=1e-8, atol=1e-9)
+    np.testing.assert_allclose(part["propars"], ref["propars"], rtol=1e-7, atol=1e-10)
+    np.testing.assert_allclose(part["history_entropies"], ref["history_entropies"], rtol=1e-8, atol=1e-11)
+    np.testing.assert_allclose(part["promoldens"][::97], ref["promoldens_sample"], rtol=1e-8, atol=1e-16)
+
+
+def test_glisa_numeric_basis_needs_atomic_grids(water6):
+    with pytest.raises(NotImplementedError, match="grid_type=1"):
+        _run("GlobalLinearISAWPart", water6, basis_type="numeric", solver="sc", grid_type=2)
