@@ -192,8 +192,10 @@ syrk_panel_kernel(const double* __restrict__ Gu, int Mpad, int pc_sub, const int
 // runs out of (FP64 instructions occupy the issue port for two cycles: ncu showed 68.8 % pipe
 // utilisation with the math-pipe throttle as top stall, i.e. contraction-bound -- SURVEY.md 8d's
 // condition for trying the tensor path; tools/dmma_probe.cu is the measurement behind the choice).
-//   block tile 128 x 128, 8 warps as 2 (rows) x 4 (columns), warp tile 64 x 32 = 8 x 4 DMMA tiles;
-//   per 4-point k-step a warp loads 8 + 4 operand doubles per lane from shared memory for 32 DMMAs;
+//   block tile 128 x 128, 16 warps as 2 (rows) x 8 (columns), warp tile 64 x 16 = 8 x 2 DMMA tiles; measured on
+//   config 4 (M = 1,500, 8.73 M points): 2 x 8 warps 731.7 ms, 2 x 4 744.1 ms, 4 x 4 752.7 ms per Hessian --
+//   the layout hardly matters, the tensor pipe is 85 % active either way (profiles/r2_hessian_ncu.txt);
+//   per 4-point k-step a warp loads 8 + 2 operand doubles per lane from shared memory for 16 DMMAs;
 //   the slab stride is padded to 132 doubles (= 4 mod 16): the fragment pattern
 //   (k = lane % 4, column = lane / 4) is then bank-conflict-free.
 // Fragment layout (PTX ISA, mma.m8n8k4 .f64): A row-major a0 = A[lane/4][lane%4], B column-major
@@ -203,6 +205,13 @@ syrk_panel_kernel(const double* __restrict__ Gu, int Mpad, int pc_sub, const int
 constexpr int kDK = 32;            // points per shared-memory slab (3 stages x 2 x 32 x 132 doubles = 203 KB)
 constexpr int kDStride = kHT + 4;  // padded row length of a slab row (doubles)
 constexpr int kDStages = 3;
+#ifndef HP_HESS_WM
+#define HP_HESS_WM 2
+#endif
+#ifndef HP_HESS_WN
+#define HP_HESS_WN 8
+#endif
+constexpr int kDWM = HP_HESS_WM, kDWN = HP_HESS_WN;  // warps along rows / columns of the 128 x 128 block tile
 
 __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
     // not volatile: a pure function of its operands, so the compiler may hoist the operand loads of the
@@ -211,9 +220,12 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
         : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
 }
 
-__global__ void __launch_bounds__(256)
+template <int WM, int WN>
+__global__ void __launch_bounds__(WM * WN * 32)
 syrk_panel_dmma_kernel(const double* __restrict__ Gu, int Mpad, int pc_sub, const int2* __restrict__ tiles,
                        double* __restrict__ Cpart) {
+    constexpr int kThreads = WM * WN * 32;
+    constexpr int TM = kHT / WM / 8, TN = kHT / WN / 8;  // 8 x 8 DMMA tiles per warp along rows / columns
     extern __shared__ __align__(16) double smem_syrk[];  // [stage][A|B][kDK][kDStride]
     auto As = [&](int st, int kk) { return smem_syrk + ((st * 2 + 0) * kDK + kk) * kDStride; };
     auto Bs = [&](int st, int kk) { return smem_syrk + ((st * 2 + 1) * kDK + kk) * kDStride; };
@@ -223,17 +235,17 @@ syrk_panel_dmma_kernel(const double* __restrict__ Gu, int Mpad, int pc_sub, cons
     double* C = Cpart + int64_t(s) * Mpad * Mpad;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int gid = lane >> 2, tig = lane & 3;
-    const int wrow = (warp >> 2) * 64, wcol = (warp & 3) * 32;
-    double acc[8][4][2];
+    const int wrow = (warp / WN) * (8 * TM), wcol = (warp % WN) * (8 * TN);
+    double acc[TM][TN][2];
 #pragma unroll
-    for (int i = 0; i < 8; ++i)
+    for (int i = 0; i < TM; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+        for (int j = 0; j < TN; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
 
     auto issue = [&](int st, int k0) {
 #pragma unroll
-        for (int j = 0; j < (kDK * kHT) / (2 * 256); ++j) {
-            const int idx = (threadIdx.x + j * 256) * 2;  // double index within the (unpadded) slab
+        for (int j = 0; j < (kDK * kHT) / (2 * kThreads); ++j) {
+            const int idx = (threadIdx.x + j * kThreads) * 2;  // double index within the (unpadded) slab
             const int kk = idx / kHT, mm = idx % kHT;
             const double* src = panel + int64_t(k0 + kk) * Mpad;
             cp_async16(As(st, kk) + mm, src + tile.x * kHT + mm);
@@ -253,15 +265,15 @@ syrk_panel_dmma_kernel(const double* __restrict__ Gu, int Mpad, int pc_sub, cons
         __syncthreads();  // slab `sl` has landed for every thread; slab sl-1 is consumed by everyone
         if (sl + kDStages - 1 < nslab) issue((sl + kDStages - 1) % kDStages, (sl + kDStages - 1) * kDK);
         else cp_async_commit();
-        // operand fragments of k-step k4 + 4 are loaded while the 32 DMMAs of k-step k4 issue
-        double a[2][8], b[2][4];
+        // operand fragments of k-step k4 + 4 are loaded while the DMMAs of k-step k4 issue
+        double a[2][TM], b[2][TN];
         {
             const double* ar = As(st, tig) + wrow + gid;
             const double* br = Bs(st, tig) + wcol + gid;
 #pragma unroll
-            for (int i = 0; i < 8; ++i) a[0][i] = ar[8 * i];
+            for (int i = 0; i < TM; ++i) a[0][i] = ar[8 * i];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) b[0][j] = br[8 * j];
+            for (int j = 0; j < TN; ++j) b[0][j] = br[8 * j];
         }
 #pragma unroll
         for (int k4 = 0; k4 < kDK; k4 += 4) {
@@ -270,22 +282,22 @@ syrk_panel_dmma_kernel(const double* __restrict__ Gu, int Mpad, int pc_sub, cons
                 const double* ar = As(st, k4 + 4 + tig) + wrow + gid;
                 const double* br = Bs(st, k4 + 4 + tig) + wcol + gid;
 #pragma unroll
-                for (int i = 0; i < 8; ++i) a[nxt][i] = ar[8 * i];
+                for (int i = 0; i < TM; ++i) a[nxt][i] = ar[8 * i];
 #pragma unroll
-                for (int j = 0; j < 4; ++j) b[nxt][j] = br[8 * j];
+                for (int j = 0; j < TN; ++j) b[nxt][j] = br[8 * j];
             }
 #pragma unroll
-            for (int i = 0; i < 8; ++i)
+            for (int i = 0; i < TM; ++i)
 #pragma unroll
-                for (int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[cur][i], b[cur][j]);
+                for (int j = 0; j < TN; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[cur][i], b[cur][j]);
         }
     }
     cp_async_wait<0>();
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
+    for (int i = 0; i < TM; ++i) {
         const int row = tile.x * kHT + wrow + 8 * i + gid;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
+        for (int j = 0; j < TN; ++j) {
             const int col = tile.y * kHT + wcol + 8 * j + 2 * tig;
             double2* dst = reinterpret_cast<double2*>(&C[int64_t(row) * Mpad + col]);
             double2 v = *dst;
@@ -418,7 +430,7 @@ int hessian_run(int64_t npts, int32_t M, void* scratch, size_t scratch_bytes, do
             int rc0 = check_cuda(cudaFuncSetAttribute(syrk_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                       int(sizeof(double) * 2 * 2 * kHK * kHT)), "cudaFuncSetAttribute");
             if (rc0) return rc0;
-            rc0 = check_cuda(cudaFuncSetAttribute(syrk_panel_dmma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+            rc0 = check_cuda(cudaFuncSetAttribute(syrk_panel_dmma_kernel<kDWM, kDWN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                   int(sizeof(double) * kDStages * 2 * kDK * kDStride)), "cudaFuncSetAttribute");
             if (rc0) return rc0;
             configured = true;
@@ -444,7 +456,7 @@ int hessian_run(int64_t npts, int32_t M, void* scratch, size_t scratch_bytes, do
         if (rc == HP_OK) rc = check_cuda(cudaStreamWaitEvent(st, pipe->ready[b], 0), "cudaStreamWaitEvent");
         if (rc) break;
         if (use_dfma) syrk_panel_kernel<<<dim3(ntile, nsplit), 256, syrk_smem, st>>>(panel[b], Mpad, pc_sub, tiles, parts);
-        else syrk_panel_dmma_kernel<<<dim3(ntile, nsplit), 256, syrk_smem, st>>>(panel[b], Mpad, pc_sub, tiles, parts);
+        else syrk_panel_dmma_kernel<kDWM, kDWN><<<dim3(ntile, nsplit), kDWM * kDWN * 32, syrk_smem, st>>>(panel[b], Mpad, pc_sub, tiles, parts);
         HP_LAUNCH_CHECK("syrk_panel_kernel");
         rc = check_cuda(cudaEventRecord(pipe->consumed[b], st), "cudaEventRecord");
     }
