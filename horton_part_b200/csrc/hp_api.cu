@@ -18,6 +18,14 @@ int check_cuda(cudaError_t err, const char* what) {
     return HP_ERR_CUDA;
 }
 
+bool first_use_on_device(bool (&flags)[64]) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return true;  // configure every time
+    if (flags[dev]) return false;
+    flags[dev] = true;
+    return true;
+}
+
 int sm_count() {
     static thread_local int cached_dev = -1, cached = 0;
     int dev = 0;

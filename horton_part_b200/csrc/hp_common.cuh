@@ -40,6 +40,10 @@ inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s
 
 int sm_count();
 
+// Function attributes (dynamic shared-memory limits) are per device: `flags` is a per-kernel-family array
+// indexed by the current device; returns true the first time it is called for that device.
+bool first_use_on_device(bool (&flags)[64]);
+
 // Butterfly sum: every lane ends with the same value, summation order fixed by lane id.
 __device__ __forceinline__ double warp_allsum(double v) {
 #pragma unroll

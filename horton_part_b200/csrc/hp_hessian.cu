@@ -425,15 +425,14 @@ int hessian_run(int64_t npts, int32_t M, void* scratch, size_t scratch_bytes, do
     const size_t syrk_smem = use_dfma ? sizeof(double) * 2 * 2 * kHK * kHT
                                       : sizeof(double) * kDStages * 2 * kDK * kDStride;
     {
-        static bool configured = false;  // attributes are per function, set once per process
-        if (!configured) {
+        static bool configured[64] = {};  // attributes are per function and device
+        if (first_use_on_device(configured)) {
             int rc0 = check_cuda(cudaFuncSetAttribute(syrk_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                       int(sizeof(double) * 2 * 2 * kHK * kHT)), "cudaFuncSetAttribute");
             if (rc0) return rc0;
             rc0 = check_cuda(cudaFuncSetAttribute(syrk_panel_dmma_kernel<kDWM, kDWN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                   int(sizeof(double) * kDStages * 2 * kDK * kDStride)), "cudaFuncSetAttribute");
             if (rc0) return rc0;
-            configured = true;
         }
     }
     HessianPipe* pipe = nullptr;

@@ -595,8 +595,8 @@ extern "C" int hp_promol_weights_spline(int64_t npts, const double* px, const do
         return HP_OK;
     }
     const size_t smem = sizeof(double) * 5 * kSplTileKnots;
-    static bool configured = false;
-    if (!configured) {
+    static bool configured[64] = {};  // per device
+    if (first_use_on_device(configured)) {
         int rc = check_cuda(cudaFuncSetAttribute(promol_weights_spline_kernel<4>,
                                                  cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)), "cudaFuncSetAttribute");
         if (rc == HP_OK)
@@ -606,7 +606,6 @@ extern "C" int hp_promol_weights_spline(int64_t npts, const double* px, const do
             rc = check_cuda(cudaFuncSetAttribute(promol_weights_spline_kernel<1>,
                                                  cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)), "cudaFuncSetAttribute");
         if (rc) return rc;
-        configured = true;
     }
     // points per thread: 4 when that still gives >= 4 chunks per resident block, else 2 or 1 so that small
     // grids (config 2: 582,000 points = 569 chunks of 1,024 on 444 resident blocks) fill whole waves

@@ -88,3 +88,12 @@ def test_two_partitionings_interleaved_on_one_device(h2o, water6):
     ref = MBISWPart(h2o["coords"], h2o["numbers"], h2o["pseudo"], h2o["grid"], h2o["rho"], maxiter=3, device_loop=False)
     ref.do_partitioning()
     assert np.array_equal(a.cache.load("charges"), ref["charges"])
+
+
+def test_cutoff_mode_in_the_device_loop(water6):
+    """local_radius (the reference's removed local-grid design) uses the same chunk kernel: the graph loop
+    reproduces the host loop there too."""
+    from horton_part_b200 import MBISWPart
+
+    dev, host = _pair(MBISWPart, water6, local_radius=9.0, maxiter=25)
+    _same(dev, host)
