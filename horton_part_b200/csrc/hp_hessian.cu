@@ -202,9 +202,15 @@ syrk_panel_kernel(const double* __restrict__ Gu, int Mpad, int pc_sub, const int
 // b0 = B[lane%4][lane/4], C c0,c1 = C[lane/4][2 (lane%4) + 0,1].  Here A[m][k] = Gu[p0+k][row0+m] and
 // B[k][n] = Gu[p0+k][col0+n]: both operands are read from the same point-major slab.
 // ---------------------------------------------------------------------------------------------
-constexpr int kDK = 32;            // points per shared-memory slab (3 stages x 2 x 32 x 132 doubles = 203 KB)
+#ifndef HP_HESS_DK
+#define HP_HESS_DK 32
+#endif
+#ifndef HP_HESS_STAGES
+#define HP_HESS_STAGES 3
+#endif
+constexpr int kDK = HP_HESS_DK;    // points per shared-memory slab (3 stages x 2 x 32 x 132 doubles = 203 KB)
 constexpr int kDStride = kHT + 4;  // padded row length of a slab row (doubles)
-constexpr int kDStages = 3;
+constexpr int kDStages = HP_HESS_STAGES;
 #ifndef HP_HESS_WM
 #define HP_HESS_WM 2
 #endif
