@@ -453,6 +453,10 @@ def main():
         "includes": "MBISWPart(...).do_partitioning() from host arrays: slab upload, K iterations with per-step "
         "state D2H, download of promolecule / at_weights / spherical averages into page-locked result arrays; "
         "second call in the process (the first one also allocates the page-locked buffers)",
+        "value_note": "value = executed pairs / s (the kernel skips pairs that cannot change the FP64 promolecule); value_job = "
+                      "dense natom x Npts pairs / s for the same call -- the reference arm evaluates every pair, so "
+                      "value_job / reference value is the time-to-identical-result speed-up, value / reference value "
+                      "understates it by the screened fraction",
         "charges_O_H_H_after_K_iterations": [float(v) for v in e2e_charges[:3]],
         "hostmem": hostmem.pool_stats(),
     }  # fmt: skip
