@@ -109,11 +109,61 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
 
+// ---------------------------------------------------------------------------------------------
+// Block screening of the panel.  A chunk of points sees only the basis functions of the atoms around it:
+// for most (sub-panel, 128-column block) pairs every entry of Gu is negligible.  panel_block_max_kernel
+// records max |Gu| per (sub-panel s, column block cb) and the chunk's overall maximum; a tile product is
+// skipped when either of its column blocks stays below 2^-kHessScreenBits of that maximum: its contribution
+// to any H_mn is then below 2^-kHessScreenBits of the largest term of the chunk, far below the rounding of
+// the FP64 sums it would be added to (same argument as the atom screening of the promolecule kernel).
+// flags layout: [nsplit * nt] block maxima | [1] chunk maximum | [1] executed-tile counter (all uint64;
+// non-negative doubles order like their bit patterns).  HP_B200_HESSIAN_SCREEN=0 disables the skip.
+// ---------------------------------------------------------------------------------------------
+constexpr int kHessScreenBits = 64;
+
+__global__ void __launch_bounds__(256)
+panel_block_max_kernel(const double* __restrict__ Gu, int Mpad, int pc_sub, int nt,
+                       unsigned long long* __restrict__ flags) {
+    __shared__ double s_red[32];
+    const int s = blockIdx.x, cb = blockIdx.y;
+    const double* base = Gu + int64_t(s) * pc_sub * Mpad + cb * kHT;
+    double m = 0.0;
+    for (int i = threadIdx.x; i < pc_sub * (kHT / 2); i += blockDim.x) {
+        const int row = i / (kHT / 2), c2 = i % (kHT / 2);
+        const double2 v = *reinterpret_cast<const double2*>(base + int64_t(row) * Mpad + 2 * c2);
+        m = fmax(m, fmax(fabs(v.x), fabs(v.y)));
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, off));
+    if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = m;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < int(blockDim.x >> 5); ++w) m = fmax(m, s_red[w]);
+        if (!(m == m)) m = __longlong_as_double(0x7ff0000000000000ll);  // NaN in the panel: never skip
+        const unsigned long long bits = static_cast<unsigned long long>(__double_as_longlong(m));
+        flags[s * nt + cb] = bits;
+        atomicMax(&flags[gridDim.x * nt], bits);
+    }
+}
+
+// true when the tile (tx, ty) of sub-panel s cannot contribute; counts the executed tiles otherwise
+__device__ __forceinline__ bool hessian_tile_skipped(const unsigned long long* __restrict__ flags, int nsplit, int nt,
+                                                     int s, int2 tile) {
+    if (!flags) return false;
+    const unsigned long long gmax = flags[nsplit * nt];
+    const unsigned long long drop = static_cast<unsigned long long>(kHessScreenBits) << 52;
+    const unsigned long long thr = gmax > drop ? gmax - drop : 0ull;  // gmax * 2^-bits (0: keep everything)
+    const bool skip = flags[s * nt + tile.x] < thr || flags[s * nt + tile.y] < thr;
+    if (!skip && threadIdx.x == 0) atomicAdd(const_cast<unsigned long long*>(&flags[nsplit * nt + 1]), 1ull);
+    return skip;
+}
+
 // C_s(tile) += Gu_s(:, tile.x)^T Gu_s(:, tile.y): 128x128 tile, 8x8 micro-tiles, the panel streamed
 // through a two-stage cp.async pipeline of kHK-point slabs.
 __global__ void __launch_bounds__(256)
 syrk_panel_kernel(const double* __restrict__ Gu, int Mpad, int pc_sub, const int2* __restrict__ tiles,
-                  double* __restrict__ Cpart) {
+                  double* __restrict__ Cpart, const unsigned long long* __restrict__ flags, int nt) {
+    if (hessian_tile_skipped(flags, gridDim.y, nt, blockIdx.y, tiles[blockIdx.x])) return;
     extern __shared__ __align__(16) double smem_syrk[];  // [2 stages][A|B][kHK][kHT]
     auto As = [&](int st, int kk) { return smem_syrk + ((st * 2 + 0) * kHK + kk) * kHT; };
     auto Bs = [&](int st, int kk) { return smem_syrk + ((st * 2 + 1) * kHK + kk) * kHT; };
@@ -229,7 +279,8 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
 template <int WM, int WN>
 __global__ void __launch_bounds__(WM * WN * 32)
 syrk_panel_dmma_kernel(const double* __restrict__ Gu, int Mpad, int pc_sub, const int2* __restrict__ tiles,
-                       double* __restrict__ Cpart) {
+                       double* __restrict__ Cpart, const unsigned long long* __restrict__ flags, int nt) {
+    if (hessian_tile_skipped(flags, gridDim.y, nt, blockIdx.y, tiles[blockIdx.x])) return;
     constexpr int kThreads = WM * WN * 32;
     constexpr int TM = kHT / WM / 8, TN = kHT / WN / 8;  // 8 x 8 DMMA tiles per warp along rows / columns
     extern __shared__ __align__(16) double smem_syrk[];  // [stage][A|B][kDK][kDStride]
@@ -382,7 +433,8 @@ extern "C" size_t hp_hessian_scratch_bytes(int32_t M) {
     const size_t panel = size_t(hessian_chunk_points(Mpad, nsplit)) * Mpad * sizeof(double);
     const size_t parts = size_t(nsplit) * Mpad * Mpad * sizeof(double);
     const size_t tiles = size_t(nt) * (nt + 1) / 2 * sizeof(int2);
-    return 2 * panel + parts + ((tiles + 255) / 256) * 256;  // two panels: producer / consumer overlap
+    const size_t flags = 2 * (size_t(nsplit) * nt + 2) * sizeof(unsigned long long);  // per panel buffer
+    return 2 * panel + parts + ((tiles + 255) / 256) * 256 + ((flags + 255) / 256) * 256;  // two panels: producer / consumer overlap
 }
 
 namespace {
@@ -426,6 +478,12 @@ int hessian_run(int64_t npts, int32_t M, void* scratch, size_t scratch_bytes, do
     double* panel[2] = {static_cast<double*>(scratch), static_cast<double*>(scratch) + size_t(pc) * Mpad};
     double* parts = panel[1] + size_t(pc) * Mpad;
     int2* tiles = reinterpret_cast<int2*>(parts + size_t(nsplit) * Mpad * Mpad);
+    const size_t tile_bytes = ((size_t(ntile) * sizeof(int2) + 255) / 256) * 256;
+    const size_t nflag = size_t(nsplit) * nt + 2;
+    unsigned long long* flag_base = reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(tiles) + tile_bytes);
+    const char* screen_env = getenv("HP_B200_HESSIAN_SCREEN");  // read per call: tests compare both settings
+    const bool screen = !(screen_env && screen_env[0] == '0');
+    unsigned long long* flags[2] = {screen ? flag_base : nullptr, screen ? flag_base + nflag : nullptr};
     // tensor-core (DMMA) tile product by default; HP_B200_HESSIAN_DFMA=1 selects the vector-FMA kernel
     static const bool use_dfma = [] { const char* e = getenv("HP_B200_HESSIAN_DFMA"); return e && e[0] == '1'; }();
     const size_t syrk_smem = use_dfma ? sizeof(double) * 2 * 2 * kHK * kHT
@@ -448,6 +506,7 @@ int hessian_run(int64_t npts, int32_t M, void* scratch, size_t scratch_bytes, do
     tile_list_kernel<<<1, 256, 0, st>>>(nt, tiles);
     HP_LAUNCH_CHECK("tile_list_kernel");
     rc = check_cuda(cudaMemsetAsync(parts, 0, sizeof(double) * nsplit * size_t(Mpad) * Mpad, st), "memset");
+    if (rc == HP_OK) rc = check_cuda(cudaMemsetAsync(flag_base, 0, sizeof(unsigned long long) * 2 * nflag, st), "memset");
     if (rc) return rc;
     // the side stream starts after everything already queued on `st` (promolecule, weights)
     rc = check_cuda(cudaEventRecord(pipe->start, st), "cudaEventRecord");
@@ -457,11 +516,19 @@ int hessian_run(int64_t npts, int32_t M, void* scratch, size_t scratch_bytes, do
         const int b = int(chunk & 1);
         if (chunk >= 2) rc = check_cuda(cudaStreamWaitEvent(pipe->side, pipe->consumed[b], 0), "cudaStreamWaitEvent");
         if (rc == HP_OK) rc = produce(p0, pc, Mpad, panel[b], pipe->side);
+        if (rc == HP_OK && screen) {
+            // executed-tile counter (last slot) accumulates over the chunks of one buffer: zero the maxima only
+            rc = check_cuda(cudaMemsetAsync(flags[b], 0, sizeof(unsigned long long) * (nflag - 1), pipe->side), "memset");
+            if (rc == HP_OK) {
+                panel_block_max_kernel<<<dim3(nsplit, nt), 256, 0, pipe->side>>>(panel[b], Mpad, pc_sub, nt, flags[b]);
+                HP_LAUNCH_CHECK("panel_block_max_kernel");
+            }
+        }
         if (rc == HP_OK) rc = check_cuda(cudaEventRecord(pipe->ready[b], pipe->side), "cudaEventRecord");
         if (rc == HP_OK) rc = check_cuda(cudaStreamWaitEvent(st, pipe->ready[b], 0), "cudaStreamWaitEvent");
         if (rc) break;
-        if (use_dfma) syrk_panel_kernel<<<dim3(ntile, nsplit), 256, syrk_smem, st>>>(panel[b], Mpad, pc_sub, tiles, parts);
-        else syrk_panel_dmma_kernel<kDWM, kDWN><<<dim3(ntile, nsplit), kDWM * kDWN * 32, syrk_smem, st>>>(panel[b], Mpad, pc_sub, tiles, parts);
+        if (use_dfma) syrk_panel_kernel<<<dim3(ntile, nsplit), 256, syrk_smem, st>>>(panel[b], Mpad, pc_sub, tiles, parts, flags[b], nt);
+        else syrk_panel_dmma_kernel<kDWM, kDWN><<<dim3(ntile, nsplit), kDWM * kDWN * 32, syrk_smem, st>>>(panel[b], Mpad, pc_sub, tiles, parts, flags[b], nt);
         HP_LAUNCH_CHECK("syrk_panel_kernel");
         rc = check_cuda(cudaEventRecord(pipe->consumed[b], st), "cudaEventRecord");
     }
@@ -517,4 +584,30 @@ extern "C" int hp_hessian_table(int64_t npts, const double* px, const double* py
         return HP_OK;
     };
     return hessian_run(npts, M, scratch, scratch_bytes, H, as_stream(stream), produce);
+}
+
+// Tile products executed by the last hp_hessian / hp_hessian_table call that used `scratch` (sum over chunks
+// and sub-panels; a tile = 128 x 128 x pc_sub multiply-adds, pc_sub = *points_per_tile_out) and the number the
+// unscreened product would have run.  Synchronises `stream`.  All zero when screening is disabled.
+extern "C" int hp_hessian_tiles_executed(int32_t M, int64_t npts, const void* scratch, int64_t* executed_out,
+                                         int64_t* total_out, int32_t* points_per_tile_out, void* stream) {
+    HP_REQUIRE(M > 0 && npts > 0 && scratch && executed_out && total_out && points_per_tile_out, "bad arguments");
+    const int Mpad = hessian_mpad(M), nt = Mpad / kHT, ntile = nt * (nt + 1) / 2;
+    const int nsplit = hessian_split(ntile);
+    const int pc = hessian_chunk_points(Mpad, nsplit);
+    const size_t nflag = size_t(nsplit) * nt + 2;
+    const char* base = static_cast<const char*>(scratch) + 2 * size_t(pc) * Mpad * sizeof(double) +
+                       size_t(nsplit) * Mpad * Mpad * sizeof(double) + ((size_t(ntile) * sizeof(int2) + 255) / 256) * 256;
+    const unsigned long long* f = reinterpret_cast<const unsigned long long*>(base);
+    unsigned long long host[2] = {0, 0};
+    cudaStream_t st = as_stream(stream);
+    int rc = check_cuda(cudaMemcpyAsync(&host[0], f + nflag - 1, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st), "copy");
+    if (rc == HP_OK) rc = check_cuda(cudaMemcpyAsync(&host[1], f + 2 * nflag - 1, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st), "copy");
+    if (rc == HP_OK) rc = check_cuda(cudaStreamSynchronize(st), "cudaStreamSynchronize");
+    if (rc) return rc;
+    const int64_t nchunk = (npts + pc - 1) / pc;
+    *executed_out = int64_t(host[0] + host[1]);
+    *total_out = nchunk * int64_t(ntile) * nsplit;
+    *points_per_tile_out = pc / nsplit;
+    return HP_OK;
 }

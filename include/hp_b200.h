@@ -492,6 +492,14 @@ HP_API int hp_aim_on_points(int functor, int64_t npts, const double* px, const d
                             int32_t ntile, const int32_t* tile_atom_offsets, const double* density,
                             double promol_offset, double* rho0, double* promol, double* aim_rho, void* stream);
 
+/* Block screening of the Hessian panel (on by default, HP_B200_HESSIAN_SCREEN=0 disables): a 128 x 128 tile
+ * product of a sub-panel is skipped when either of its 128-column blocks stays below 2^-64 of the chunk's
+ * largest |Gu| -- a chunk of points sees only the basis functions of the atoms around it.
+ * hp_hessian_tiles_executed reports how many tile products the last call on `scratch` ran, how many the
+ * unscreened product has, and the points per tile (flop executed = tiles x 2 x 128 x 128 x points). */
+HP_API int hp_hessian_tiles_executed(int32_t M, int64_t npts, const void* scratch, int64_t* executed_out,
+                                     int64_t* total_out, int32_t* points_per_tile_out, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * (row a12 with basis_type="numeric", core/basis.py:330-387) gLISA on TABULATED basis functions: shell m is a
  * piecewise cubic on its atom's knots (knot_offsets / knots as in hp_spline_build, interval tables lut_meta / lut

@@ -92,3 +92,36 @@ def test_glisa_newton_against_reference_run(water6g):
 def test_glisa_sc_gauss_promolecule(water6g):
     part = _glisa(water6g, solver="sc")
     _compare(part, _gold(water6g["gold"], "glisa_sc"))
+
+
+def test_hessian_block_screening_matches_dense_product(monkeypatch):
+    """The panel's block screening (tile products of vanishing column blocks skipped) changes no entry of H
+    beyond the rounding of the dense product, and it does skip tiles on an extended chain."""
+    import torch
+
+    from horton_part_b200 import GlobalLinearISAWPart, gridlite, synthetic
+    from horton_part_b200.core.basis import ExpBasisFuncHelper
+
+    coords, numbers = synthetic.peptide_like(80, seed=1)
+    rgrid = gridlite.BeckeRTransform(1e-4, 1.5).transform_1d_grid(gridlite.GaussChebyshev(40))
+    grid = gridlite.MolGrid.from_size(numbers, coords, 50, rgrid, np.ones(len(numbers) * 40 * 50), store=True)
+    helper = ExpBasisFuncHelper.from_function_type("gauss")
+    rho, w = synthetic.expbasis_promolecule_device(grid, coords, numbers, helper, device="cuda:0",
+                                                   scale={1: 0.75, 6: 6.2, 7: 7.3, 8: 8.4})  # fmt: skip
+    grid.aim_weights[:] = w
+    grid.weights[:] = grid.atweights * w
+    part = GlobalLinearISAWPart(coords, numbers, numbers.astype(float), grid, rho, solver="newton")
+    part._init_propars()
+    part._promol_and_entropy()
+    H = part.hessian().clone()
+    executed, total, ppt = part.hessian_tiles()
+    assert 0 < executed < total and ppt > 0
+    monkeypatch.setenv("HP_B200_HESSIAN_SCREEN", "0")
+    H0 = part.hessian().clone()
+    assert part.hessian_tiles()[0] == 0  # nothing counted when the screening is off
+    scale = float(H0.abs().max())
+    assert float((H - H0).abs().max()) <= 4e-16 * scale
+    assert torch.equal(H, H.T)
+    # entries between far-apart atoms, which the screening may drop entirely, are below rounding of the diagonal
+    dropped = (H == 0) & (H0 != 0)
+    assert float(H0[dropped].abs().max()) <= 1e-17 * scale if bool(dropped.any()) else True

@@ -227,6 +227,13 @@ def config4(dev, natom=300, peak=None, with_sc=False):
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1)
     flop = float(M) * (M + 1) * grid.size
+    executed, total, ppt = part.hessian_tiles()
+    flop_exec = executed * 2.0 * 128 * 128 * ppt
+    out["hessian_screening"] = {
+        "tiles_executed": executed, "tiles_total": total, "points_per_tile": ppt, "frac_executed": executed / max(total, 1),
+        "executed_tflops": flop_exec / (ms * 1e-3) / 1e12, "executed_frac_of_peak": flop_exec / (ms * 1e-3) / 1e12 / peak,
+        "note": "128 x 128 tile products whose column blocks are below 2^-64 of the chunk's largest |Gu| are skipped; "
+                "executed flop counts full tiles (padding and both halves of diagonal tiles included)"}  # fmt: skip
     out["roofline_hessian"] = {
         "kernel": "basis_chunk_kernel + syrk_panel_dmma_kernel (mma.sync m8n8k4 f64) + hessian_finish_kernel",
         "bound": "fp64 (tensor)", "ms": ms, "flop_algorithmic": flop, "achieved": flop / (ms * 1e-3) / 1e12,
