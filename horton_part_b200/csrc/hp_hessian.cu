@@ -26,6 +26,30 @@ constexpr int kHT = 128;   // tile edge
 constexpr int kHK = 16;        // points per shared-memory slab
 constexpr int kHMaxSplit = 24; // upper bound on sub-panels per chunk (partial matrices)
 
+// Block screening, producer side: running maximum of |Gu| per (sub-panel, 128-column block) of the chunk, kept
+// as the high word of the double (exponent + 20 mantissa bits: enough for a threshold test, and non-negative
+// doubles order like their bit patterns).  Thread t of the 256 handles the columns t + 256 j, so the warp's
+// j-th value lies in column block 2 j + (warp >= 4): one REDUX per value, lane j keeps the j-th result, and
+// after the row the lanes publish their maxima with a guarded atomicMax (a plain L2 read first: almost
+// every row is below the maximum already recorded).
+struct PanelMax {
+    unsigned keep = 0u;
+    __device__ __forceinline__ void add(int j, double v) {
+        const unsigned h = __reduce_max_sync(0xffffffffu, static_cast<unsigned>(__double2hiint(fabs(v))));
+        if ((threadIdx.x & 31) == (j & 31)) keep = max(keep, h);
+    }
+    __device__ __forceinline__ void publish(unsigned long long* __restrict__ flags, int s, int nt, int nj) {
+        const int j = threadIdx.x & 31;
+        for (int jj = j; jj < nj; jj += 32) {  // nj <= 32 for Mpad <= 8192; beyond that the lanes hold merged maxima
+            const int cb = 2 * jj + int(threadIdx.x >> 7);
+            if (cb >= nt) continue;
+            const unsigned long long bits = static_cast<unsigned long long>(keep) << 32;
+            unsigned long long* f = flags + s * nt + cb;
+            if (__ldcg(f) < bits) atomicMax(f, bits);
+        }
+    }
+};
+
 template <int F>
 __global__ void __launch_bounds__(256)
 basis_chunk_kernel(int64_t p0, int pc, int M, int Mpad, const double* __restrict__ px,
@@ -34,7 +58,8 @@ basis_chunk_kernel(int64_t p0, int pc, int M, int Mpad, const double* __restrict
                    const double* __restrict__ promol, double cutoff,
                    const int* __restrict__ shell_atom, const double* __restrict__ atom_xyz,
                    const double* __restrict__ shell_norm, const double* __restrict__ shell_alpha,
-                   const double* __restrict__ shell_order, int64_t npts, double* __restrict__ Gu) {
+                   const double* __restrict__ shell_order, int64_t npts, double* __restrict__ Gu,
+                   unsigned long long* __restrict__ flags, int pc_sub) {
     // one block per point, threads over shells (coalesced stores along m)
     const int lp = blockIdx.x;
     if (lp >= pc) return;
@@ -47,7 +72,9 @@ basis_chunk_kernel(int64_t p0, int pc, int M, int Mpad, const double* __restrict
         x = px[p]; y = py[p]; z = pz[p];
     }
     double* row = Gu + int64_t(lp) * Mpad;
-    for (int m = threadIdx.x; m < Mpad; m += blockDim.x) {
+    PanelMax pmax;
+    int j = 0;
+    for (int m = threadIdx.x; m < Mpad; m += blockDim.x, ++j) {
         double v = 0.0;
         if (m < M && su != 0.0) {
             const int a = shell_atom[m];
@@ -66,7 +93,9 @@ basis_chunk_kernel(int64_t p0, int pc, int M, int Mpad, const double* __restrict
             v = su * shell_norm[m] * e;
         }
         row[m] = v;
+        if (flags) pmax.add(j, v);
     }
+    if (flags) pmax.publish(flags, lp / pc_sub, Mpad / kHT, j);
 }
 
 // The same panel for tabulated basis functions (basis_type="numeric"): Gu[p][m] = sqrt(u_p) S_m(r_pm).
@@ -76,7 +105,7 @@ table_basis_chunk_kernel(int64_t p0, int pc, int M, int Mpad, const double* __re
                          const double* __restrict__ rho, const double* __restrict__ molw,
                          const double* __restrict__ promol, double cutoff, const int* __restrict__ shell_atom,
                          const double* __restrict__ atom_xyz, TableArgs tab, int64_t npts,
-                         double* __restrict__ Gu) {
+                         double* __restrict__ Gu, unsigned long long* __restrict__ flags, int pc_sub) {
     const int lp = blockIdx.x;
     if (lp >= pc) return;
     const int64_t p = p0 + lp;
@@ -88,7 +117,9 @@ table_basis_chunk_kernel(int64_t p0, int pc, int M, int Mpad, const double* __re
         x = px[p]; y = py[p]; z = pz[p];
     }
     double* row = Gu + int64_t(lp) * Mpad;
-    for (int m = threadIdx.x; m < Mpad; m += blockDim.x) {
+    PanelMax pmax;
+    int j = 0;
+    for (int m = threadIdx.x; m < Mpad; m += blockDim.x, ++j) {
         double v = 0.0;
         if (m < M && su != 0.0) {
             const int a = shell_atom[m];
@@ -98,7 +129,9 @@ table_basis_chunk_kernel(int64_t p0, int pc, int M, int Mpad, const double* __re
             v = su * table_cubic(tab.shell_coef + tab.shell_coef_off[m] + 4 * i, d);
         }
         row[m] = v;
+        if (flags) pmax.add(j, v);
     }
+    if (flags) pmax.publish(flags, lp / pc_sub, Mpad / kHT, j);
 }
 
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
@@ -111,8 +144,9 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 
 // ---------------------------------------------------------------------------------------------
 // Block screening of the panel.  A chunk of points sees only the basis functions of the atoms around it:
-// for most (sub-panel, 128-column block) pairs every entry of Gu is negligible.  panel_block_max_kernel
-// records max |Gu| per (sub-panel s, column block cb) and the chunk's overall maximum; a tile product is
+// for most (sub-panel, 128-column block) pairs every entry of Gu is negligible.  The producer kernels record
+// max |Gu| per (sub-panel s, column block cb) while they write the panel (PanelMax above, no second pass over
+// the 0.5 GB panel), panel_chunk_max_kernel the chunk's overall maximum; a tile product is
 // skipped when either of its column blocks stays below 2^-kHessScreenBits of that maximum: its contribution
 // to any H_mn is then below 2^-kHessScreenBits of the largest term of the chunk, far below the rounding of
 // the FP64 sums it would be added to (same argument as the atom screening of the promolecule kernel).
@@ -122,27 +156,17 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 constexpr int kHessScreenBits = 64;
 
 __global__ void __launch_bounds__(256)
-panel_block_max_kernel(const double* __restrict__ Gu, int Mpad, int pc_sub, int nt,
-                       unsigned long long* __restrict__ flags) {
-    __shared__ double s_red[32];
-    const int s = blockIdx.x, cb = blockIdx.y;
-    const double* base = Gu + int64_t(s) * pc_sub * Mpad + cb * kHT;
-    double m = 0.0;
-    for (int i = threadIdx.x; i < pc_sub * (kHT / 2); i += blockDim.x) {
-        const int row = i / (kHT / 2), c2 = i % (kHT / 2);
-        const double2 v = *reinterpret_cast<const double2*>(base + int64_t(row) * Mpad + 2 * c2);
-        m = fmax(m, fmax(fabs(v.x), fabs(v.y)));
-    }
+panel_chunk_max_kernel(int nblock, unsigned long long* __restrict__ flags) {
+    __shared__ unsigned long long s_red[8];
+    unsigned long long m = 0ull;
+    for (int i = threadIdx.x; i < nblock; i += blockDim.x) m = max(m, flags[i]);
 #pragma unroll
-    for (int off = 16; off > 0; off >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, off));
+    for (int off = 16; off > 0; off >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, off));
     if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = m;
     __syncthreads();
     if (threadIdx.x == 0) {
-        for (int w = 1; w < int(blockDim.x >> 5); ++w) m = fmax(m, s_red[w]);
-        if (!(m == m)) m = __longlong_as_double(0x7ff0000000000000ll);  // NaN in the panel: never skip
-        const unsigned long long bits = static_cast<unsigned long long>(__double_as_longlong(m));
-        flags[s * nt + cb] = bits;
-        atomicMax(&flags[gridDim.x * nt], bits);
+        for (int w = 1; w < 8; ++w) m = max(m, s_red[w]);
+        flags[nblock] = m;
     }
 }
 
@@ -515,14 +539,13 @@ int hessian_run(int64_t npts, int32_t M, void* scratch, size_t scratch_bytes, do
     for (int64_t p0 = 0; p0 < npts && rc == HP_OK; p0 += pc, ++chunk) {
         const int b = int(chunk & 1);
         if (chunk >= 2) rc = check_cuda(cudaStreamWaitEvent(pipe->side, pipe->consumed[b], 0), "cudaStreamWaitEvent");
-        if (rc == HP_OK) rc = produce(p0, pc, Mpad, panel[b], pipe->side);
-        if (rc == HP_OK && screen) {
-            // executed-tile counter (last slot) accumulates over the chunks of one buffer: zero the maxima only
+        // executed-tile counter (last slot) accumulates over the chunks of one buffer: zero the maxima only
+        if (rc == HP_OK && screen)
             rc = check_cuda(cudaMemsetAsync(flags[b], 0, sizeof(unsigned long long) * (nflag - 1), pipe->side), "memset");
-            if (rc == HP_OK) {
-                panel_block_max_kernel<<<dim3(nsplit, nt), 256, 0, pipe->side>>>(panel[b], Mpad, pc_sub, nt, flags[b]);
-                HP_LAUNCH_CHECK("panel_block_max_kernel");
-            }
+        if (rc == HP_OK) rc = produce(p0, pc, Mpad, panel[b], flags[b], pc_sub, pipe->side);
+        if (rc == HP_OK && screen) {
+            panel_chunk_max_kernel<<<1, 256, 0, pipe->side>>>(nsplit * nt, flags[b]);
+            HP_LAUNCH_CHECK("panel_chunk_max_kernel");
         }
         if (rc == HP_OK) rc = check_cuda(cudaEventRecord(pipe->ready[b], pipe->side), "cudaEventRecord");
         if (rc == HP_OK) rc = check_cuda(cudaStreamWaitEvent(st, pipe->ready[b], 0), "cudaStreamWaitEvent");
@@ -553,10 +576,12 @@ extern "C" int hp_hessian(int functor, int64_t npts, const double* px, const dou
     HP_REQUIRE(functor != HP_FUNCTOR_GENERAL || shell_order, "general functor needs shell_order");
     HP_REQUIRE(functor == HP_FUNCTOR_SLATER || functor == HP_FUNCTOR_GAUSS || functor == HP_FUNCTOR_GENERAL,
                "unsupported functor");
-    auto produce = [&](int64_t p0, int pc, int Mpad, double* panel, cudaStream_t s) -> int {
+    auto produce = [&](int64_t p0, int pc, int Mpad, double* panel, unsigned long long* flags, int pc_sub,
+                       cudaStream_t s) -> int {
 #define HP_BASIS(F)                                                                                         \
     basis_chunk_kernel<F><<<pc, 256, 0, s>>>(p0, pc, M, Mpad, px, py, pz, rho, molw, promol, density_cutoff, \
-                                             shell_atom, atom_xyz, shell_norm, shell_alpha, shell_order, npts, panel)
+                                             shell_atom, atom_xyz, shell_norm, shell_alpha, shell_order, npts, panel, \
+                                             flags, pc_sub)
         if (functor == HP_FUNCTOR_SLATER) HP_BASIS(HP_FUNCTOR_SLATER);
         else if (functor == HP_FUNCTOR_GAUSS) HP_BASIS(HP_FUNCTOR_GAUSS);
         else HP_BASIS(HP_FUNCTOR_GENERAL);
@@ -577,9 +602,10 @@ extern "C" int hp_hessian_table(int64_t npts, const double* px, const double* py
     HP_REQUIRE(px && py && pz && atom_xyz && shell_atom && knot_offsets && knots && lut_meta && lut &&
                    shell_coef_offsets && shell_coef && rho && molw && promol && scratch && H, "null input");
     TableArgs tab{knot_offsets, knots, lut_meta, lut, reinterpret_cast<const long long*>(shell_coef_offsets), shell_coef};
-    auto produce = [&](int64_t p0, int pc, int Mpad, double* panel, cudaStream_t s) -> int {
+    auto produce = [&](int64_t p0, int pc, int Mpad, double* panel, unsigned long long* flags, int pc_sub,
+                       cudaStream_t s) -> int {
         table_basis_chunk_kernel<<<pc, 256, 0, s>>>(p0, pc, M, Mpad, px, py, pz, rho, molw, promol, density_cutoff,
-                                                    shell_atom, atom_xyz, tab, npts, panel);
+                                                    shell_atom, atom_xyz, tab, npts, panel, flags, pc_sub);
         HP_LAUNCH_CHECK("table_basis_chunk_kernel");
         return HP_OK;
     };
