@@ -65,7 +65,12 @@ def warm_up(dev):
     grid = gridlite.MolGrid.from_size(numbers, coords, 26, rgrid, gridlite.BeckeWeights(), store=True)
     rho = synthetic.slater_promolecule_host(grid.points, coords, numbers)
     MBISWPart(coords, numbers, numbers.astype(float), grid, rho, device=dev, maxiter=3).do_partitioning()
-    _torch().cuda.synchronize()
+    torch = _torch()
+    # cuSOLVER / cuBLAS handles of the gLISA Newton step (Cholesky + refinement on the device)
+    a = torch.eye(8, dtype=torch.float64, device=dev) * 2.0
+    chol, _ = torch.linalg.cholesky_ex(a)
+    (a @ torch.cholesky_solve(a[:, :1], chol)).sum().item()
+    torch.cuda.synchronize()
     _WARM.add(str(dev))
 
 
