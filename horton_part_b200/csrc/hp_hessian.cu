@@ -22,14 +22,21 @@
 
 namespace hp {
 
+#ifndef HP_HESS_SUB
+#define HP_HESS_SUB 1280  // points per sub-panel (measured at M = 1,500: 5120 -> 191 ms, 2560 -> 168 ms, 1280 -> 161 ms)
+#endif
+#ifndef HP_HESS_PANEL_MB
+#define HP_HESS_PANEL_MB 1024  // bytes of one panel buffer (two of them)
+#endif
 constexpr int kHT = 128;   // tile edge
+constexpr int kHQ = 64;    // screening granularity along the columns (a quadrant of a tile)
 constexpr int kHK = 16;        // points per shared-memory slab
-constexpr int kHMaxSplit = 24; // upper bound on sub-panels per chunk (partial matrices)
+constexpr int kHMaxSplit = 64; // upper bound on sub-panels per chunk (partial matrices)
 
-// Block screening, producer side: running maximum of |Gu| per (sub-panel, 128-column block) of the chunk, kept
+// Block screening, producer side: running maximum of |Gu| per (sub-panel, 64-column block) of the chunk, kept
 // as the high word of the double (exponent + 20 mantissa bits: enough for a threshold test, and non-negative
 // doubles order like their bit patterns).  Thread t of the 256 handles the columns t + 256 j, so the warp's
-// j-th value lies in column block 2 j + (warp >= 4): one REDUX per value, lane j keeps the j-th result, and
+// j-th value lies in column block 4 j + warp / 2: one REDUX per value, lane j keeps the j-th result, and
 // after the row the lanes publish their maxima with a guarded atomicMax (a plain L2 read first: almost
 // every row is below the maximum already recorded).
 struct PanelMax {
@@ -38,17 +45,42 @@ struct PanelMax {
         const unsigned h = __reduce_max_sync(0xffffffffu, static_cast<unsigned>(__double2hiint(fabs(v))));
         if ((threadIdx.x & 31) == (j & 31)) keep = max(keep, h);
     }
-    __device__ __forceinline__ void publish(unsigned long long* __restrict__ flags, int s, int nt, int nj) {
+    __device__ __forceinline__ void publish(unsigned long long* __restrict__ flags, int s, int nq, int nj) {
         const int j = threadIdx.x & 31;
         for (int jj = j; jj < nj; jj += 32) {  // nj <= 32 for Mpad <= 8192; beyond that the lanes hold merged maxima
-            const int cb = 2 * jj + int(threadIdx.x >> 7);
-            if (cb >= nt) continue;
+            const int cb = 4 * jj + int(threadIdx.x >> 6);
+            if (cb >= nq) continue;
             const unsigned long long bits = static_cast<unsigned long long>(keep) << 32;
-            unsigned long long* f = flags + s * nt + cb;
+            unsigned long long* f = flags + s * nq + cb;
             if (__ldcg(f) < bits) atomicMax(f, bits);
         }
     }
 };
+
+// Rows (points) per producer block: the shell parameters of a thread's columns are loaded once for all of
+// them, and the block publishes its maxima once (one guarded atomic per 64-column block and kHRows rows).
+constexpr int kHRows = 8;
+static_assert(HP_HESS_SUB % kHRows == 0, "the rows of one producer block lie in one sub-panel");
+
+// sqrt(u_p) and the coordinates of the block's rows -> shared memory (threads 0 .. kHRows-1)
+__device__ __forceinline__ void panel_rows_setup(double (*s_pt)[4], int64_t p_first, int64_t npts,
+                                                 const double* __restrict__ px, const double* __restrict__ py,
+                                                 const double* __restrict__ pz, const double* __restrict__ rho,
+                                                 const double* __restrict__ molw, const double* __restrict__ promol,
+                                                 double cutoff) {
+    if (threadIdx.x < kHRows) {
+        const int64_t p = p_first + threadIdx.x;
+        double su = 0.0, x = 0.0, y = 0.0, z = 0.0;
+        if (p < npts) {
+            const double r0 = promol[p], rh = rho[p];
+            const bool sick = (rh < cutoff) || (r0 < cutoff);
+            su = sick ? 0.0 : sqrt(molw[p] * rh / r0 / r0);
+            x = px[p]; y = py[p]; z = pz[p];
+        }
+        s_pt[threadIdx.x][0] = su; s_pt[threadIdx.x][1] = x; s_pt[threadIdx.x][2] = y; s_pt[threadIdx.x][3] = z;
+    }
+    __syncthreads();
+}
 
 template <int F>
 __global__ void __launch_bounds__(256)
@@ -60,42 +92,47 @@ basis_chunk_kernel(int64_t p0, int pc, int M, int Mpad, const double* __restrict
                    const double* __restrict__ shell_norm, const double* __restrict__ shell_alpha,
                    const double* __restrict__ shell_order, int64_t npts, double* __restrict__ Gu,
                    unsigned long long* __restrict__ flags, int pc_sub) {
-    // one block per point, threads over shells (coalesced stores along m)
-    const int lp = blockIdx.x;
-    if (lp >= pc) return;
-    const int64_t p = p0 + lp;
-    double su = 0.0, x = 0.0, y = 0.0, z = 0.0;
-    if (p < npts) {
-        const double r0 = promol[p], rh = rho[p];
-        const bool sick = (rh < cutoff) || (r0 < cutoff);
-        su = sick ? 0.0 : sqrt(molw[p] * rh / r0 / r0);
-        x = px[p]; y = py[p]; z = pz[p];
-    }
-    double* row = Gu + int64_t(lp) * Mpad;
+    // one block per kHRows points, threads over shells (coalesced stores along m)
+    __shared__ double s_pt[kHRows][4];
+    const int lp0 = blockIdx.x * kHRows;
+    if (lp0 >= pc) return;
+    panel_rows_setup(s_pt, p0 + lp0, npts, px, py, pz, rho, molw, promol, cutoff);
+    double* rows = Gu + int64_t(lp0) * Mpad;
     PanelMax pmax;
     int j = 0;
     for (int m = threadIdx.x; m < Mpad; m += blockDim.x, ++j) {
-        double v = 0.0;
-        if (m < M && su != 0.0) {
-            const int a = shell_atom[m];
-            const double dx = x - atom_xyz[3 * a], dy = y - atom_xyz[3 * a + 1], dz = z - atom_xyz[3 * a + 2];
-            const double d2 = fma(dz, dz, fma(dy, dy, dx * dx));
-            double e;
-            if (F == HP_FUNCTOR_GAUSS) {
-                e = exp_neg_poly(-shell_alpha[m] * d2);
-            } else if (F == HP_FUNCTOR_SLATER) {
-                e = exp_neg_poly(-shell_alpha[m] * sqrt_nocall(d2));
-            } else {
-                const double r = sqrt(d2), n = shell_order[m];
-                const double rn = (n == 1.0) ? r : ((n == 2.0) ? r * r : pow(r, n));
-                e = exp(-shell_alpha[m] * rn);
+        const bool valid = m < M;
+        const int a = valid ? shell_atom[m] : 0;
+        const double ax = atom_xyz[3 * a], ay = atom_xyz[3 * a + 1], az = atom_xyz[3 * a + 2];
+        const double alpha = valid ? shell_alpha[m] : 0.0, norm = valid ? shell_norm[m] : 0.0;
+        const double order = (valid && F == HP_FUNCTOR_GENERAL) ? shell_order[m] : 1.0;
+        double vmax = 0.0;
+#pragma unroll
+        for (int r = 0; r < kHRows; ++r) {
+            const double su = s_pt[r][0];
+            double v = 0.0;
+            if (valid && su != 0.0) {
+                const double dx = s_pt[r][1] - ax, dy = s_pt[r][2] - ay, dz = s_pt[r][3] - az;
+                const double d2 = fma(dz, dz, fma(dy, dy, dx * dx));
+                double e;
+                if (F == HP_FUNCTOR_GAUSS) {
+                    e = exp_neg_poly(-alpha * d2);
+                } else if (F == HP_FUNCTOR_SLATER) {
+                    e = exp_neg_poly(-alpha * sqrt_nocall(d2));
+                } else {
+                    const double rr = sqrt(d2);
+                    const double rn = (order == 1.0) ? rr : ((order == 2.0) ? rr * rr : pow(rr, order));
+                    e = exp(-alpha * rn);
+                }
+                v = su * norm * e;
             }
-            v = su * shell_norm[m] * e;
+            rows[int64_t(r) * Mpad + m] = v;
+            vmax = fmax(vmax, fabs(v));  // fmax drops a NaN operand: pass NaNs on explicitly
+            if (v != v) vmax = __longlong_as_double(0x7ff0000000000000ll);
         }
-        row[m] = v;
-        if (flags) pmax.add(j, v);
+        if (flags) pmax.add(j, vmax);
     }
-    if (flags) pmax.publish(flags, lp / pc_sub, Mpad / kHT, j);
+    if (flags) pmax.publish(flags, lp0 / pc_sub, Mpad / kHQ, j);
 }
 
 // The same panel for tabulated basis functions (basis_type="numeric"): Gu[p][m] = sqrt(u_p) S_m(r_pm).
@@ -106,32 +143,36 @@ table_basis_chunk_kernel(int64_t p0, int pc, int M, int Mpad, const double* __re
                          const double* __restrict__ promol, double cutoff, const int* __restrict__ shell_atom,
                          const double* __restrict__ atom_xyz, TableArgs tab, int64_t npts,
                          double* __restrict__ Gu, unsigned long long* __restrict__ flags, int pc_sub) {
-    const int lp = blockIdx.x;
-    if (lp >= pc) return;
-    const int64_t p = p0 + lp;
-    double su = 0.0, x = 0.0, y = 0.0, z = 0.0;
-    if (p < npts) {
-        const double r0 = promol[p], rh = rho[p];
-        const bool sick = (rh < cutoff) || (r0 < cutoff);
-        su = sick ? 0.0 : sqrt(molw[p] * rh / r0 / r0);
-        x = px[p]; y = py[p]; z = pz[p];
-    }
-    double* row = Gu + int64_t(lp) * Mpad;
+    __shared__ double s_pt[kHRows][4];
+    const int lp0 = blockIdx.x * kHRows;
+    if (lp0 >= pc) return;
+    panel_rows_setup(s_pt, p0 + lp0, npts, px, py, pz, rho, molw, promol, cutoff);
+    double* rows = Gu + int64_t(lp0) * Mpad;
     PanelMax pmax;
     int j = 0;
     for (int m = threadIdx.x; m < Mpad; m += blockDim.x, ++j) {
-        double v = 0.0;
-        if (m < M && su != 0.0) {
-            const int a = shell_atom[m];
-            const double dx = x - atom_xyz[3 * a], dy = y - atom_xyz[3 * a + 1], dz = z - atom_xyz[3 * a + 2];
-            double d;
-            const int i = table_interval(tab, a, sqrt_nocall(fma(dz, dz, fma(dy, dy, dx * dx))), d);
-            v = su * table_cubic(tab.shell_coef + tab.shell_coef_off[m] + 4 * i, d);
+        const bool valid = m < M;
+        const int a = valid ? shell_atom[m] : 0;
+        const double ax = atom_xyz[3 * a], ay = atom_xyz[3 * a + 1], az = atom_xyz[3 * a + 2];
+        const double* coef = tab.shell_coef + (valid ? tab.shell_coef_off[m] : 0);
+        double vmax = 0.0;
+#pragma unroll 2
+        for (int r = 0; r < kHRows; ++r) {
+            const double su = s_pt[r][0];
+            double v = 0.0;
+            if (valid && su != 0.0) {
+                const double dx = s_pt[r][1] - ax, dy = s_pt[r][2] - ay, dz = s_pt[r][3] - az;
+                double d;
+                const int i = table_interval(tab, a, sqrt_nocall(fma(dz, dz, fma(dy, dy, dx * dx))), d);
+                v = su * table_cubic(coef + 4 * i, d);
+            }
+            rows[int64_t(r) * Mpad + m] = v;
+            vmax = fmax(vmax, fabs(v));
+            if (v != v) vmax = __longlong_as_double(0x7ff0000000000000ll);
         }
-        row[m] = v;
-        if (flags) pmax.add(j, v);
+        if (flags) pmax.add(j, vmax);
     }
-    if (flags) pmax.publish(flags, lp / pc_sub, Mpad / kHT, j);
+    if (flags) pmax.publish(flags, lp0 / pc_sub, Mpad / kHQ, j);
 }
 
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
@@ -144,14 +185,19 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 
 // ---------------------------------------------------------------------------------------------
 // Block screening of the panel.  A chunk of points sees only the basis functions of the atoms around it:
-// for most (sub-panel, 128-column block) pairs every entry of Gu is negligible.  The producer kernels record
-// max |Gu| per (sub-panel s, column block cb) while they write the panel (PanelMax above, no second pass over
-// the 0.5 GB panel), panel_chunk_max_kernel the chunk's overall maximum; a tile product is
+// for most (sub-panel, 64-column block) pairs every entry of Gu is negligible.  The producer kernels record
+// max |Gu| per (sub-panel s, column block q) while they write the panel (PanelMax above, no second pass over
+// the panel), panel_chunk_max_kernel the chunk's overall maximum.  A 64 x 64 quadrant of a tile product is
 // skipped when either of its column blocks stays below 2^-kHessScreenBits of that maximum: its contribution
 // to any H_mn is then below 2^-kHessScreenBits of the largest term of the chunk, far below the rounding of
-// the FP64 sums it would be added to (same argument as the atom screening of the promolecule kernel).
-// flags layout: [nsplit * nt] block maxima | [1] chunk maximum | [1] executed-tile counter (all uint64;
-// non-negative doubles order like their bit patterns).  HP_B200_HESSIAN_SCREEN=0 disables the skip.
+// the FP64 sums it would be added to (same argument as the atom screening of the promolecule kernel).  A
+// block whose four quadrants are all skipped returns at once; in the DMMA kernel the warps of a skipped
+// quadrant only take part in the operand pipeline (each warp scheduler holds one warp of every quadrant, so
+// the tile's time follows the number of live quadrants), and the lower-left quadrant of a diagonal tile --
+// never read by hessian_finish_kernel -- is always skipped.
+// flags layout: [nsplit * nq] block maxima (nq = Mpad / 64) | [1] chunk maximum | [1] executed-quadrant
+// counter (all uint64; non-negative doubles order like their bit patterns).  HP_B200_HESSIAN_SCREEN=0
+// disables the skip.
 // ---------------------------------------------------------------------------------------------
 constexpr int kHessScreenBits = 64;
 
@@ -170,24 +216,30 @@ panel_chunk_max_kernel(int nblock, unsigned long long* __restrict__ flags) {
     }
 }
 
-// true when the tile (tx, ty) of sub-panel s cannot contribute; counts the executed tiles otherwise
-__device__ __forceinline__ bool hessian_tile_skipped(const unsigned long long* __restrict__ flags, int nsplit, int nt,
-                                                     int s, int2 tile) {
-    if (!flags) return false;
-    const unsigned long long gmax = flags[nsplit * nt];
+// Bit q = 2 i + j of the result: quadrant (row half i, column half j) of tile (tx, ty) of sub-panel s has
+// to be computed.  Thread 0 adds the number of live quadrants to the counter.
+__device__ __forceinline__ unsigned hessian_live_quadrants(const unsigned long long* __restrict__ flags, int nsplit,
+                                                           int nq, int s, int2 tile) {
+    unsigned live = (tile.x == tile.y) ? 0xbu : 0xfu;  // diagonal tile: rows 64.. x columns ..63 are never read
+    if (!flags) return live;
+    const unsigned long long gmax = flags[nsplit * nq];
     const unsigned long long drop = static_cast<unsigned long long>(kHessScreenBits) << 52;
     const unsigned long long thr = gmax > drop ? gmax - drop : 0ull;  // gmax * 2^-bits (0: keep everything)
-    const bool skip = flags[s * nt + tile.x] < thr || flags[s * nt + tile.y] < thr;
-    if (!skip && threadIdx.x == 0) atomicAdd(const_cast<unsigned long long*>(&flags[nsplit * nt + 1]), 1ull);
-    return skip;
+    const unsigned long long* f = flags + s * nq;
+    const bool r0 = f[2 * tile.x] >= thr, r1 = f[2 * tile.x + 1] >= thr;
+    const bool c0 = f[2 * tile.y] >= thr, c1 = f[2 * tile.y + 1] >= thr;
+    live &= (r0 && c0 ? 1u : 0u) | (r0 && c1 ? 2u : 0u) | (r1 && c0 ? 4u : 0u) | (r1 && c1 ? 8u : 0u);
+    if (live && threadIdx.x == 0)
+        atomicAdd(const_cast<unsigned long long*>(&flags[nsplit * nq + 1]), static_cast<unsigned long long>(__popc(live)));
+    return live;
 }
 
 // C_s(tile) += Gu_s(:, tile.x)^T Gu_s(:, tile.y): 128x128 tile, 8x8 micro-tiles, the panel streamed
 // through a two-stage cp.async pipeline of kHK-point slabs.
 __global__ void __launch_bounds__(256)
 syrk_panel_kernel(const double* __restrict__ Gu, int Mpad, int pc_sub, const int2* __restrict__ tiles,
-                  double* __restrict__ Cpart, const unsigned long long* __restrict__ flags, int nt) {
-    if (hessian_tile_skipped(flags, gridDim.y, nt, blockIdx.y, tiles[blockIdx.x])) return;
+                  double* __restrict__ Cpart, const unsigned long long* __restrict__ flags, int nq) {
+    if (!hessian_live_quadrants(flags, gridDim.y, nq, blockIdx.y, tiles[blockIdx.x])) return;
     extern __shared__ __align__(16) double smem_syrk[];  // [2 stages][A|B][kHK][kHT]
     auto As = [&](int st, int kk) { return smem_syrk + ((st * 2 + 0) * kHK + kk) * kHT; };
     auto Bs = [&](int st, int kk) { return smem_syrk + ((st * 2 + 1) * kHK + kk) * kHT; };
@@ -303,8 +355,9 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
 template <int WM, int WN>
 __global__ void __launch_bounds__(WM * WN * 32)
 syrk_panel_dmma_kernel(const double* __restrict__ Gu, int Mpad, int pc_sub, const int2* __restrict__ tiles,
-                       double* __restrict__ Cpart, const unsigned long long* __restrict__ flags, int nt) {
-    if (hessian_tile_skipped(flags, gridDim.y, nt, blockIdx.y, tiles[blockIdx.x])) return;
+                       double* __restrict__ Cpart, const unsigned long long* __restrict__ flags, int nq) {
+    const unsigned live = hessian_live_quadrants(flags, gridDim.y, nq, blockIdx.y, tiles[blockIdx.x]);
+    if (!live) return;
     constexpr int kThreads = WM * WN * 32;
     constexpr int TM = kHT / WM / 8, TN = kHT / WN / 8;  // 8 x 8 DMMA tiles per warp along rows / columns
     extern __shared__ __align__(16) double smem_syrk[];  // [stage][A|B][kDK][kDStride]
@@ -317,6 +370,8 @@ syrk_panel_dmma_kernel(const double* __restrict__ Gu, int Mpad, int pc_sub, cons
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int gid = lane >> 2, tig = lane & 3;
     const int wrow = (warp / WN) * (8 * TM), wcol = (warp % WN) * (8 * TN);
+    static_assert(kHQ % (8 * TM) == 0 && kHQ % (8 * TN) == 0, "a warp's sub-tile must lie inside one quadrant");
+    const bool mine = (live >> (2 * (wrow / kHQ) + wcol / kHQ)) & 1u;  // warp-uniform
     double acc[TM][TN][2];
 #pragma unroll
     for (int i = 0; i < TM; ++i)
@@ -346,6 +401,7 @@ syrk_panel_dmma_kernel(const double* __restrict__ Gu, int Mpad, int pc_sub, cons
         __syncthreads();  // slab `sl` has landed for every thread; slab sl-1 is consumed by everyone
         if (sl + kDStages - 1 < nslab) issue((sl + kDStages - 1) % kDStages, (sl + kDStages - 1) * kDK);
         else cp_async_commit();
+        if (!mine) continue;  // this warp's quadrant is screened out: it only feeds the operand pipeline
         // operand fragments of k-step k4 + 4 are loaded while the DMMAs of k-step k4 issue
         double a[2][TM], b[2][TN];
         {
@@ -374,6 +430,7 @@ syrk_panel_dmma_kernel(const double* __restrict__ Gu, int Mpad, int pc_sub, cons
         }
     }
     cp_async_wait<0>();
+    if (!mine) return;
 #pragma unroll
     for (int i = 0; i < TM; ++i) {
         const int row = tile.x * kHT + wrow + 8 * i + gid;
@@ -413,53 +470,57 @@ __global__ void tile_list_kernel(int nt, int2* __restrict__ tiles) {
     }
 }
 
-static int hessian_mpad(int M) { return ((M + kHT - 1) / kHT) * kHT; }
+// Layout of one chunk of the panel and of the scratch buffer.  A chunk is `nsplit` sub-panels of kHSub points
+// each; every (tile, sub-panel) pair is one thread block of the tile product and owns its own 128 x 128 slice
+// of the partial matrices (no atomics: H is a fixed-order sum of the nsplit partial matrices).  Many short
+// sub-panels on purpose: the screening decides per (sub-panel, column block), so short sub-panels (one atom's
+// radial shells: 1,280 points are a twentieth of an atomic grid) skip more, and a launch of ntile x nsplit
+// blocks of which a fifth is live still fills several waves of SMs.  The panel does not need to fit the L2:
+// the blocks of one sub-panel run together (blockIdx.x = tile is the fast index) and share its 3-30 MB.
+// Every block ends with a read-modify-write of its slice of the partial matrices, so the chunk is as large
+// as the panel budget allows (measured in round 2: 878 ms per Hessian with 64 MB chunks against 738 ms).
+constexpr int kHSub = HP_HESS_SUB;                      // points per sub-panel
+constexpr int64_t kHPanelBytes = int64_t(HP_HESS_PANEL_MB) << 20;  // per panel buffer (two of them)
+static_assert(kHSub % kDK == 0 && kHSub % kHK == 0, "whole slabs of either tile-product kernel");
 
-// Number of sub-panels: the (tiles x splits) grid should fill whole waves of SMs (1 block per SM).
-static int hessian_split(int ntile) {
-    const int sms = sm_count();
-    int best = 2;
-    double best_eff = 0.0;
-    for (int s = 2; s <= kHMaxSplit; ++s) {
-        const int blocks = ntile * s;
-        const int waves = (blocks + sms - 1) / sms;
-        const double eff = double(blocks) / (double(waves) * sms);
-        if (eff > best_eff + 1e-9) {
-            best_eff = eff;
-            best = s;
-        }
+struct HessianLayout {
+    int Mpad, nt, nq, ntile, nsplit, pc_sub, pc;
+    size_t panel_doubles, parts_doubles, tile_bytes, nflag;
+    size_t bytes() const {
+        return 2 * panel_doubles * sizeof(double) + parts_doubles * sizeof(double) + tile_bytes +
+               ((2 * nflag * sizeof(unsigned long long) + 255) / 256) * 256;
     }
-    return best;
-}
+};
 
-// points per chunk: bounded panel size (<= 512 MB) and a multiple of nsplit * kHK.  Large chunks on purpose:
-// every (tile, split) block ends with a read-modify-write of its 128 x 128 slice of the partial matrices
-// (nsplit x Mpad^2 doubles = 359 MB at M = 1,536: HBM traffic per chunk, not overlapped with the tile
-// product), so the fewer chunks the better -- measured 878 ms per Hessian with 64 MB chunks (1,690 chunks)
-// against the large ones.  The panel itself does not need to fit the L2: the blocks of one split run
-// together (blockIdx.x = tile is the fast index) and share its 3-30 MB sub-panel through the L2.
-static int hessian_chunk_points(int Mpad, int nsplit) {
-    int64_t pc = (int64_t(512) << 20) / (int64_t(Mpad) * 8);
-    if (pc > 65536) pc = 65536;
-    const int q = nsplit * (kDK > kHK ? kDK : kHK);  // whole slabs of either tile-product kernel
-    pc = (pc / q) * q;
-    return int(pc < q ? q : pc);
+// npts < 0: the largest layout for M (what hp_hessian_scratch_bytes reserves); otherwise no more sub-panels
+// than the points need (the offsets inside the scratch buffer then depend on npts, consistently everywhere).
+static HessianLayout hessian_layout(int M, int64_t npts) {
+    HessianLayout L;
+    L.Mpad = ((M + kHT - 1) / kHT) * kHT;
+    L.nt = L.Mpad / kHT;
+    L.nq = L.Mpad / kHQ;
+    L.ntile = L.nt * (L.nt + 1) / 2;
+    L.pc_sub = kHSub;
+    int64_t ns = kHPanelBytes / (int64_t(kHSub) * L.Mpad * 8);
+    ns = ns < 2 ? 2 : (ns > kHMaxSplit ? kHMaxSplit : ns);
+    if (npts >= 0) {
+        const int64_t need = (npts + kHSub - 1) / kHSub;
+        if (need < ns) ns = need < 1 ? 1 : need;
+    }
+    L.nsplit = int(ns);
+    L.pc = L.nsplit * L.pc_sub;
+    L.panel_doubles = size_t(L.pc) * L.Mpad;
+    L.parts_doubles = size_t(L.nsplit) * L.Mpad * L.Mpad;
+    L.tile_bytes = ((size_t(L.ntile) * sizeof(int2) + 255) / 256) * 256;
+    L.nflag = size_t(L.nsplit) * L.nq + 2;
+    return L;
 }
 
 }  // namespace hp
 
 using namespace hp;
 
-extern "C" size_t hp_hessian_scratch_bytes(int32_t M) {
-    const int Mpad = hessian_mpad(M);
-    const int nt = Mpad / kHT;
-    const int nsplit = hessian_split(nt * (nt + 1) / 2);
-    const size_t panel = size_t(hessian_chunk_points(Mpad, nsplit)) * Mpad * sizeof(double);
-    const size_t parts = size_t(nsplit) * Mpad * Mpad * sizeof(double);
-    const size_t tiles = size_t(nt) * (nt + 1) / 2 * sizeof(int2);
-    const size_t flags = 2 * (size_t(nsplit) * nt + 2) * sizeof(unsigned long long);  // per panel buffer
-    return 2 * panel + parts + ((tiles + 255) / 256) * 256 + ((flags + 255) / 256) * 256;  // two panels: producer / consumer overlap
-}
+extern "C" size_t hp_hessian_scratch_bytes(int32_t M) { return hessian_layout(M, -1).bytes(); }
 
 namespace {
 
@@ -496,15 +557,13 @@ int hessian_pipe(HessianPipe** out) {
 template <class Produce>
 int hessian_run(int64_t npts, int32_t M, void* scratch, size_t scratch_bytes, double* H, cudaStream_t st, Produce produce) {
     HP_REQUIRE(scratch_bytes >= hp_hessian_scratch_bytes(M), "scratch too small");
-    const int Mpad = hessian_mpad(M), nt = Mpad / kHT, ntile = nt * (nt + 1) / 2;
-    const int nsplit = hessian_split(ntile);
-    const int pc = hessian_chunk_points(Mpad, nsplit), pc_sub = pc / nsplit;
-    double* panel[2] = {static_cast<double*>(scratch), static_cast<double*>(scratch) + size_t(pc) * Mpad};
-    double* parts = panel[1] + size_t(pc) * Mpad;
-    int2* tiles = reinterpret_cast<int2*>(parts + size_t(nsplit) * Mpad * Mpad);
-    const size_t tile_bytes = ((size_t(ntile) * sizeof(int2) + 255) / 256) * 256;
-    const size_t nflag = size_t(nsplit) * nt + 2;
-    unsigned long long* flag_base = reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(tiles) + tile_bytes);
+    const HessianLayout L = hessian_layout(M, npts);
+    const int Mpad = L.Mpad, nt = L.nt, nq = L.nq, ntile = L.ntile, nsplit = L.nsplit, pc = L.pc, pc_sub = L.pc_sub;
+    double* panel[2] = {static_cast<double*>(scratch), static_cast<double*>(scratch) + L.panel_doubles};
+    double* parts = panel[1] + L.panel_doubles;
+    int2* tiles = reinterpret_cast<int2*>(parts + L.parts_doubles);
+    const size_t nflag = L.nflag;
+    unsigned long long* flag_base = reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(tiles) + L.tile_bytes);
     const char* screen_env = getenv("HP_B200_HESSIAN_SCREEN");  // read per call: tests compare both settings
     const bool screen = !(screen_env && screen_env[0] == '0');
     unsigned long long* flags[2] = {screen ? flag_base : nullptr, screen ? flag_base + nflag : nullptr};
@@ -544,14 +603,14 @@ int hessian_run(int64_t npts, int32_t M, void* scratch, size_t scratch_bytes, do
             rc = check_cuda(cudaMemsetAsync(flags[b], 0, sizeof(unsigned long long) * (nflag - 1), pipe->side), "memset");
         if (rc == HP_OK) rc = produce(p0, pc, Mpad, panel[b], flags[b], pc_sub, pipe->side);
         if (rc == HP_OK && screen) {
-            panel_chunk_max_kernel<<<1, 256, 0, pipe->side>>>(nsplit * nt, flags[b]);
+            panel_chunk_max_kernel<<<1, 256, 0, pipe->side>>>(nsplit * nq, flags[b]);
             HP_LAUNCH_CHECK("panel_chunk_max_kernel");
         }
         if (rc == HP_OK) rc = check_cuda(cudaEventRecord(pipe->ready[b], pipe->side), "cudaEventRecord");
         if (rc == HP_OK) rc = check_cuda(cudaStreamWaitEvent(st, pipe->ready[b], 0), "cudaStreamWaitEvent");
         if (rc) break;
-        if (use_dfma) syrk_panel_kernel<<<dim3(ntile, nsplit), 256, syrk_smem, st>>>(panel[b], Mpad, pc_sub, tiles, parts, flags[b], nt);
-        else syrk_panel_dmma_kernel<kDWM, kDWN><<<dim3(ntile, nsplit), kDWM * kDWN * 32, syrk_smem, st>>>(panel[b], Mpad, pc_sub, tiles, parts, flags[b], nt);
+        if (use_dfma) syrk_panel_kernel<<<dim3(ntile, nsplit), 256, syrk_smem, st>>>(panel[b], Mpad, pc_sub, tiles, parts, flags[b], nq);
+        else syrk_panel_dmma_kernel<kDWM, kDWN><<<dim3(ntile, nsplit), kDWM * kDWN * 32, syrk_smem, st>>>(panel[b], Mpad, pc_sub, tiles, parts, flags[b], nq);
         HP_LAUNCH_CHECK("syrk_panel_kernel");
         rc = check_cuda(cudaEventRecord(pipe->consumed[b], st), "cudaEventRecord");
     }
@@ -579,7 +638,7 @@ extern "C" int hp_hessian(int functor, int64_t npts, const double* px, const dou
     auto produce = [&](int64_t p0, int pc, int Mpad, double* panel, unsigned long long* flags, int pc_sub,
                        cudaStream_t s) -> int {
 #define HP_BASIS(F)                                                                                         \
-    basis_chunk_kernel<F><<<pc, 256, 0, s>>>(p0, pc, M, Mpad, px, py, pz, rho, molw, promol, density_cutoff, \
+    basis_chunk_kernel<F><<<pc / kHRows, 256, 0, s>>>(p0, pc, M, Mpad, px, py, pz, rho, molw, promol, density_cutoff, \
                                              shell_atom, atom_xyz, shell_norm, shell_alpha, shell_order, npts, panel, \
                                              flags, pc_sub)
         if (functor == HP_FUNCTOR_SLATER) HP_BASIS(HP_FUNCTOR_SLATER);
@@ -604,7 +663,7 @@ extern "C" int hp_hessian_table(int64_t npts, const double* px, const double* py
     TableArgs tab{knot_offsets, knots, lut_meta, lut, reinterpret_cast<const long long*>(shell_coef_offsets), shell_coef};
     auto produce = [&](int64_t p0, int pc, int Mpad, double* panel, unsigned long long* flags, int pc_sub,
                        cudaStream_t s) -> int {
-        table_basis_chunk_kernel<<<pc, 256, 0, s>>>(p0, pc, M, Mpad, px, py, pz, rho, molw, promol, density_cutoff,
+        table_basis_chunk_kernel<<<pc / kHRows, 256, 0, s>>>(p0, pc, M, Mpad, px, py, pz, rho, molw, promol, density_cutoff,
                                                     shell_atom, atom_xyz, tab, npts, panel, flags, pc_sub);
         HP_LAUNCH_CHECK("table_basis_chunk_kernel");
         return HP_OK;
@@ -612,28 +671,25 @@ extern "C" int hp_hessian_table(int64_t npts, const double* px, const double* py
     return hessian_run(npts, M, scratch, scratch_bytes, H, as_stream(stream), produce);
 }
 
-// Tile products executed by the last hp_hessian / hp_hessian_table call that used `scratch` (sum over chunks
-// and sub-panels; a tile = 128 x 128 x pc_sub multiply-adds, pc_sub = *points_per_tile_out) and the number the
-// unscreened product would have run.  Synchronises `stream`.  All zero when screening is disabled.
+// 64 x 64 quadrant products executed by the last hp_hessian / hp_hessian_table call that used `scratch` (sum
+// over chunks and sub-panels; one quadrant = 64 x 64 x *points_per_tile_out multiply-adds) and the number the
+// unscreened product needs (four per tile, three for the tiles on the diagonal).  Synchronises `stream`.
+// executed = 0 when screening is disabled.
 extern "C" int hp_hessian_tiles_executed(int32_t M, int64_t npts, const void* scratch, int64_t* executed_out,
                                          int64_t* total_out, int32_t* points_per_tile_out, void* stream) {
     HP_REQUIRE(M > 0 && npts > 0 && scratch && executed_out && total_out && points_per_tile_out, "bad arguments");
-    const int Mpad = hessian_mpad(M), nt = Mpad / kHT, ntile = nt * (nt + 1) / 2;
-    const int nsplit = hessian_split(ntile);
-    const int pc = hessian_chunk_points(Mpad, nsplit);
-    const size_t nflag = size_t(nsplit) * nt + 2;
-    const char* base = static_cast<const char*>(scratch) + 2 * size_t(pc) * Mpad * sizeof(double) +
-                       size_t(nsplit) * Mpad * Mpad * sizeof(double) + ((size_t(ntile) * sizeof(int2) + 255) / 256) * 256;
+    const HessianLayout L = hessian_layout(M, npts);
+    const char* base = static_cast<const char*>(scratch) + (2 * L.panel_doubles + L.parts_doubles) * sizeof(double) + L.tile_bytes;
     const unsigned long long* f = reinterpret_cast<const unsigned long long*>(base);
     unsigned long long host[2] = {0, 0};
     cudaStream_t st = as_stream(stream);
-    int rc = check_cuda(cudaMemcpyAsync(&host[0], f + nflag - 1, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st), "copy");
-    if (rc == HP_OK) rc = check_cuda(cudaMemcpyAsync(&host[1], f + 2 * nflag - 1, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st), "copy");
+    int rc = check_cuda(cudaMemcpyAsync(&host[0], f + L.nflag - 1, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st), "copy");
+    if (rc == HP_OK) rc = check_cuda(cudaMemcpyAsync(&host[1], f + 2 * L.nflag - 1, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st), "copy");
     if (rc == HP_OK) rc = check_cuda(cudaStreamSynchronize(st), "cudaStreamSynchronize");
     if (rc) return rc;
-    const int64_t nchunk = (npts + pc - 1) / pc;
+    const int64_t nchunk = (npts + L.pc - 1) / L.pc;
     *executed_out = int64_t(host[0] + host[1]);
-    *total_out = nchunk * int64_t(ntile) * nsplit;
-    *points_per_tile_out = pc / nsplit;
+    *total_out = nchunk * L.nsplit * (int64_t(4) * L.ntile - L.nt);
+    *points_per_tile_out = L.pc_sub;
     return HP_OK;
 }

@@ -362,9 +362,9 @@ class GlobalLinearISAWPart(AbstractStockholderWPart):
         return self._hess
 
     def hessian_tiles(self):
-        """(executed, total, points per tile) of the 128 x 128 tile products of the last :meth:`hessian`
-        call: the panel's block screening skips the tiles whose basis functions vanish on a chunk of
-        points.  flop executed = executed * 2 * 128 * 128 * points per tile."""
+        """(executed, total, points per sub-panel) of the 64 x 64 quadrant products of the last
+        :meth:`hessian` call: the panel's block screening skips the quadrants whose basis functions vanish
+        on a sub-panel of points.  flop executed = executed * 2 * 64 * 64 * points per sub-panel."""
         from .core.device import stream_ptr
 
         out = np.zeros(2, dtype=np.int64)

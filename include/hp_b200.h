@@ -492,11 +492,12 @@ HP_API int hp_aim_on_points(int functor, int64_t npts, const double* px, const d
                             int32_t ntile, const int32_t* tile_atom_offsets, const double* density,
                             double promol_offset, double* rho0, double* promol, double* aim_rho, void* stream);
 
-/* Block screening of the Hessian panel (on by default, HP_B200_HESSIAN_SCREEN=0 disables): a 128 x 128 tile
- * product of a sub-panel is skipped when either of its 128-column blocks stays below 2^-64 of the chunk's
- * largest |Gu| -- a chunk of points sees only the basis functions of the atoms around it.
- * hp_hessian_tiles_executed reports how many tile products the last call on `scratch` ran, how many the
- * unscreened product has, and the points per tile (flop executed = tiles x 2 x 128 x 128 x points). */
+/* Block screening of the Hessian panel (on by default, HP_B200_HESSIAN_SCREEN=0 disables): a 64 x 64
+ * quadrant of a 128 x 128 tile product of a sub-panel (1,280 points) is skipped when either of its 64-column
+ * blocks stays below 2^-64 of the chunk's largest |Gu| -- a chunk of points sees only the basis functions of
+ * the atoms around it.  hp_hessian_tiles_executed reports how many quadrant products the last call on
+ * `scratch` ran, how many the unscreened product needs, and the points per sub-panel
+ * (flop executed = quadrants x 2 x 64 x 64 x points). */
 HP_API int hp_hessian_tiles_executed(int32_t M, int64_t npts, const void* scratch, int64_t* executed_out,
                                      int64_t* total_out, int32_t* points_per_tile_out, void* stream);
 
