@@ -25,6 +25,12 @@ namespace hp {
 #ifndef HP_HESS_SUB
 #define HP_HESS_SUB 1280  // points per sub-panel (measured at M = 1,500: 5120 -> 191 ms, 2560 -> 168 ms, 1280 -> 161 ms)
 #endif
+#ifndef HP_HESS_ROWS
+#define HP_HESS_ROWS 32  // points per producer block
+#endif
+#ifndef HP_HESS_PBLOCKS
+#define HP_HESS_PBLOCKS 3  // producer blocks per SM the register budget is set for
+#endif
 #ifndef HP_HESS_PANEL_MB
 #define HP_HESS_PANEL_MB 1024  // bytes of one panel buffer (two of them)
 #endif
@@ -59,7 +65,9 @@ struct PanelMax {
 
 // Rows (points) per producer block: the shell parameters of a thread's columns are loaded once for all of
 // them, and the block publishes its maxima once (one guarded atomic per 64-column block and kHRows rows).
-constexpr int kHRows = 8;
+constexpr int kHRows = HP_HESS_ROWS;
+constexpr int kHRowUnroll = 8;  // rows in flight per thread (independent exponential chains)
+static_assert(kHRows % kHRowUnroll == 0 && kHRows <= 256, "row groups");
 static_assert(HP_HESS_SUB % kHRows == 0, "the rows of one producer block lie in one sub-panel");
 
 // sqrt(u_p) and the coordinates of the block's rows -> shared memory (threads 0 .. kHRows-1)
@@ -83,7 +91,7 @@ __device__ __forceinline__ void panel_rows_setup(double (*s_pt)[4], int64_t p_fi
 }
 
 template <int F>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, HP_HESS_PBLOCKS)
 basis_chunk_kernel(int64_t p0, int pc, int M, int Mpad, const double* __restrict__ px,
                    const double* __restrict__ py, const double* __restrict__ pz,
                    const double* __restrict__ rho, const double* __restrict__ molw,
@@ -107,8 +115,10 @@ basis_chunk_kernel(int64_t p0, int pc, int M, int Mpad, const double* __restrict
         const double alpha = valid ? shell_alpha[m] : 0.0, norm = valid ? shell_norm[m] : 0.0;
         const double order = (valid && F == HP_FUNCTOR_GENERAL) ? shell_order[m] : 1.0;
         double vmax = 0.0;
+        for (int r0 = 0; r0 < kHRows; r0 += kHRowUnroll)
 #pragma unroll
-        for (int r = 0; r < kHRows; ++r) {
+        for (int rr = 0; rr < kHRowUnroll; ++rr) {
+            const int r = r0 + rr;
             const double su = s_pt[r][0];
             double v = 0.0;
             if (valid && su != 0.0) {
@@ -120,8 +130,8 @@ basis_chunk_kernel(int64_t p0, int pc, int M, int Mpad, const double* __restrict
                 } else if (F == HP_FUNCTOR_SLATER) {
                     e = exp_neg_poly(-alpha * sqrt_nocall(d2));
                 } else {
-                    const double rr = sqrt(d2);
-                    const double rn = (order == 1.0) ? rr : ((order == 2.0) ? rr * rr : pow(rr, order));
+                    const double dist = sqrt(d2);
+                    const double rn = (order == 1.0) ? dist : ((order == 2.0) ? dist * dist : pow(dist, order));
                     e = exp(-alpha * rn);
                 }
                 v = su * norm * e;
