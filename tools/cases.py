@@ -157,7 +157,48 @@ def config2(dev, peak=None):
         "note": "dense (no screening: spline tails are not monotone); 1.2e7 pairs per launch is ~80 us of work on 148 SMs"}  # fmt: skip
     mbis = MBISWPart(coords, numbers, pseudo, grid, rho, device=dev)
     out["mbis"] = timed_partitioning(mbis)
+    hi = config2_hirshfeld_i(dev)
+    if hi is not None:
+        out["hirshfeld_i"] = hi
     return out
+
+
+def config2_hirshfeld_i(dev):
+    """Hirshfeld-I at config-2 size on the inputs of tests/golden/config2_hi.npz (20 atoms, 582,000 points, pro-atom
+    database records of the reference's tests/cached/atom_*_pow.npz packed in the fixture; density = promolecule of
+    the database pro-atoms at fixed charges).  None when the fixture is not there."""
+    from horton_part_b200 import HirshfeldIWPart, gridlite
+    from horton_part_b200.core.proatomdb import ProAtomDB, ProAtomRecord
+
+    path = os.path.join(ROOT, "tests", "golden", "config2_hi.npz")
+    if not os.path.exists(path):
+        return None
+    z = np.load(path)
+    records = []
+    for key in z.files:
+        if key.startswith("record/"):
+            v = z[key]
+            npoint = int(v[5])
+            rgrid = gridlite.PowerRTransform(v[3], v[4], npoint - 1).transform_1d_grid(gridlite.UniformInteger(npoint))
+            records.append(ProAtomRecord(int(v[0]), int(v[1]), float(v[2]), rgrid, v[6 : 6 + npoint].copy(), v[6 + npoint :].copy()))
+    db = ProAtomDB(records)
+    coords, numbers = z["coordinates"], z["numbers"]
+    rgrid = gridlite.BeckeRTransform(1e-4, 1.5).transform_1d_grid(gridlite.GaussChebyshev(NRAD))
+    grid = gridlite.MolGrid.from_size(numbers, coords, NANG, rgrid, gridlite.DeviceBeckeWeights(), store=True)
+    rho = np.zeros(grid.size)
+    for R, zn, q in zip(coords, numbers, z["generating_charges"]):  # as in tests/test_gpu_configs.py
+        ic = int(np.floor(q))
+        x = float(q - ic)
+        one = (int(zn) - ic) == 1 or x == 0.0
+        spline = db.get_spline(int(zn), {ic: 1 - x} if one else {ic: 1 - x, ic + 1: x})
+        r = np.linalg.norm(grid.points - R, axis=1)
+        rho += np.where(r <= db.get_rgrid(int(zn)).points[-1], np.clip(spline(np.minimum(r, 1e3)), 0.0, None), 0.0)
+    part = HirshfeldIWPart(coords, numbers, numbers.astype(float), grid, rho, db, device=dev)
+    res = timed_partitioning(part)
+    res["niter_reference"] = int(z["hi/niter"])
+    res["reference_cpu_seconds"] = float(z["hi/seconds"])  # the unmodified reference on this repo's build container
+    res["max_abs_charge_diff_vs_reference_run"] = float(np.abs(part["charges"] - z["hi/charges"]).max())
+    return res
 
 
 def config3(dev, natom=100, peak=None, slater_maxiter=50):
