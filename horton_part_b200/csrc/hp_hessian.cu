@@ -456,6 +456,147 @@ syrk_panel_dmma_kernel(const double* __restrict__ Gu, int Mpad, int pc_sub, cons
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// The same tile product with the operand slabs moved by the bulk-copy engine (cp.async.bulk = UBLKCP, one
+// 1 KB row of a slab per copy, padded destination rows) and an mbarrier ring instead of cp.async groups +
+// __syncthreads: a 17th warp is the producer (waits for a stage to be released by all 16 consumer warps,
+// arms the stage's `full` barrier with the slab's byte count, issues the 2 x kDK row copies), the consumer
+// warps wait for `full`, run their DMMAs and release the stage -- no block-wide barrier in the loop, every
+// warp runs at its own pace.  Default; HP_B200_HESSIAN_PIPE=cpasync selects the kernel above.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return static_cast<unsigned>(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(unsigned long long* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "LAB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra DONE;\n"
+        "bra LAB_WAIT;\n"
+        "DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// 16-byte aligned global -> shared bulk copy; completion is counted in bytes on `bar`
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, unsigned bytes, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(smem_dst)), "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+template <int WM, int WN>
+__global__ void __launch_bounds__(WM * WN * 32 + 32)
+syrk_panel_bulk_kernel(const double* __restrict__ Gu, int Mpad, int pc_sub, const int2* __restrict__ tiles,
+                       double* __restrict__ Cpart, const unsigned long long* __restrict__ flags, int nq) {
+    const unsigned live = hessian_live_quadrants(flags, gridDim.y, nq, blockIdx.y, tiles[blockIdx.x]);
+    if (!live) return;
+    constexpr int kConsumers = WM * WN;
+    constexpr int TM = kHT / WM / 8, TN = kHT / WN / 8;
+    constexpr unsigned kRowBytes = kHT * sizeof(double);
+    extern __shared__ __align__(16) double smem_syrk[];  // [stage][A|B][kDK][kDStride] | full[stages] | empty[stages]
+    auto As = [&](int st, int kk) { return smem_syrk + ((st * 2 + 0) * kDK + kk) * kDStride; };
+    auto Bs = [&](int st, int kk) { return smem_syrk + ((st * 2 + 1) * kDK + kk) * kDStride; };
+    unsigned long long* full = reinterpret_cast<unsigned long long*>(smem_syrk + kDStages * 2 * kDK * kDStride);
+    unsigned long long* empty = full + kDStages;
+    const int2 tile = tiles[blockIdx.x];
+    const int s = blockIdx.y;
+    const double* panel = Gu + int64_t(s) * pc_sub * Mpad;
+    double* C = Cpart + int64_t(s) * Mpad * Mpad;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int st = 0; st < kDStages; ++st) {
+            mbar_init(&full[st], 1);            // the producer's arrive.expect_tx; the bytes complete the phase
+            mbar_init(&empty[st], kConsumers);  // one arrival per consumer warp
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    __syncthreads();
+    const int nslab = pc_sub / kDK;
+
+    if (warp == kConsumers) {  // ---- producer warp
+        for (int sl = 0; sl < nslab; ++sl) {
+            const int st = sl % kDStages, round = sl / kDStages;
+            if (round > 0) mbar_wait(&empty[st], (round - 1) & 1);
+            if (lane == 0) mbar_arrive_expect_tx(&full[st], 2u * kDK * kRowBytes);
+            __syncwarp();
+            for (int kk = lane; kk < kDK; kk += 32) {
+                const double* src = panel + int64_t(sl * kDK + kk) * Mpad;
+                bulk_g2s(As(st, kk), src + tile.x * kHT, kRowBytes, &full[st]);
+                bulk_g2s(Bs(st, kk), src + tile.y * kHT, kRowBytes, &full[st]);
+            }
+        }
+        return;
+    }
+
+    // ---- consumer warps
+    const int gid = lane >> 2, tig = lane & 3;
+    const int wrow = (warp / WN) * (8 * TM), wcol = (warp % WN) * (8 * TN);
+    static_assert(kHQ % (8 * TM) == 0 && kHQ % (8 * TN) == 0, "a warp's sub-tile must lie inside one quadrant");
+    const bool mine = (live >> (2 * (wrow / kHQ) + wcol / kHQ)) & 1u;  // warp-uniform
+    double acc[TM][TN][2];
+#pragma unroll
+    for (int i = 0; i < TM; ++i)
+#pragma unroll
+        for (int j = 0; j < TN; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+    for (int sl = 0; sl < nslab; ++sl) {
+        const int st = sl % kDStages, round = sl / kDStages;
+        mbar_wait(&full[st], round & 1);
+        if (mine) {
+            double a[2][TM], b[2][TN];
+            {
+                const double* ar = As(st, tig) + wrow + gid;
+                const double* br = Bs(st, tig) + wcol + gid;
+#pragma unroll
+                for (int i = 0; i < TM; ++i) a[0][i] = ar[8 * i];
+#pragma unroll
+                for (int j = 0; j < TN; ++j) b[0][j] = br[8 * j];
+            }
+#pragma unroll
+            for (int k4 = 0; k4 < kDK; k4 += 4) {
+                const int cur = (k4 >> 2) & 1, nxt = cur ^ 1;
+                if (k4 + 4 < kDK) {
+                    const double* ar = As(st, k4 + 4 + tig) + wrow + gid;
+                    const double* br = Bs(st, k4 + 4 + tig) + wcol + gid;
+#pragma unroll
+                    for (int i = 0; i < TM; ++i) a[nxt][i] = ar[8 * i];
+#pragma unroll
+                    for (int j = 0; j < TN; ++j) b[nxt][j] = br[8 * j];
+                }
+#pragma unroll
+                for (int i = 0; i < TM; ++i)
+#pragma unroll
+                    for (int j = 0; j < TN; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[cur][i], b[cur][j]);
+            }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[st]);  // this warp has read everything it needs from the stage
+    }
+    if (!mine) return;
+#pragma unroll
+    for (int i = 0; i < TM; ++i) {
+        const int row = tile.x * kHT + wrow + 8 * i + gid;
+#pragma unroll
+        for (int j = 0; j < TN; ++j) {
+            const int col = tile.y * kHT + wcol + 8 * j + 2 * tig;
+            double2* dst = reinterpret_cast<double2*>(&C[int64_t(row) * Mpad + col]);
+            double2 v = *dst;
+            v.x += acc[i][j][0];
+            v.y += acc[i][j][1];
+            *dst = v;
+        }
+    }
+}
+
 __global__ void __launch_bounds__(256)
 hessian_finish_kernel(int M, int Mpad, int nsplit, const double* __restrict__ Cpart,
                       double* __restrict__ H) {
@@ -579,8 +720,11 @@ int hessian_run(int64_t npts, int32_t M, void* scratch, size_t scratch_bytes, do
     unsigned long long* flags[2] = {screen ? flag_base : nullptr, screen ? flag_base + nflag : nullptr};
     // tensor-core (DMMA) tile product by default; HP_B200_HESSIAN_DFMA=1 selects the vector-FMA kernel
     static const bool use_dfma = [] { const char* e = getenv("HP_B200_HESSIAN_DFMA"); return e && e[0] == '1'; }();
+    // operand pipeline of the DMMA kernel: bulk copies + mbarriers (default) or cp.async groups + __syncthreads
+    static const bool use_cpasync = [] { const char* e = getenv("HP_B200_HESSIAN_PIPE"); return e && e[0] == 'c'; }();
+    constexpr size_t kBulkSmem = sizeof(double) * kDStages * 2 * kDK * kDStride + 2 * kDStages * sizeof(unsigned long long);
     const size_t syrk_smem = use_dfma ? sizeof(double) * 2 * 2 * kHK * kHT
-                                      : sizeof(double) * kDStages * 2 * kDK * kDStride;
+                                      : (use_cpasync ? sizeof(double) * kDStages * 2 * kDK * kDStride : kBulkSmem);
     {
         static bool configured[64] = {};  // attributes are per function and device
         if (first_use_on_device(configured)) {
@@ -589,6 +733,9 @@ int hessian_run(int64_t npts, int32_t M, void* scratch, size_t scratch_bytes, do
             if (rc0) return rc0;
             rc0 = check_cuda(cudaFuncSetAttribute(syrk_panel_dmma_kernel<kDWM, kDWN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                   int(sizeof(double) * kDStages * 2 * kDK * kDStride)), "cudaFuncSetAttribute");
+            if (rc0) return rc0;
+            rc0 = check_cuda(cudaFuncSetAttribute(syrk_panel_bulk_kernel<kDWM, kDWN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                  int(kBulkSmem)), "cudaFuncSetAttribute");
             if (rc0) return rc0;
         }
     }
@@ -620,7 +767,8 @@ int hessian_run(int64_t npts, int32_t M, void* scratch, size_t scratch_bytes, do
         if (rc == HP_OK) rc = check_cuda(cudaStreamWaitEvent(st, pipe->ready[b], 0), "cudaStreamWaitEvent");
         if (rc) break;
         if (use_dfma) syrk_panel_kernel<<<dim3(ntile, nsplit), 256, syrk_smem, st>>>(panel[b], Mpad, pc_sub, tiles, parts, flags[b], nq);
-        else syrk_panel_dmma_kernel<kDWM, kDWN><<<dim3(ntile, nsplit), kDWM * kDWN * 32, syrk_smem, st>>>(panel[b], Mpad, pc_sub, tiles, parts, flags[b], nq);
+        else if (use_cpasync) syrk_panel_dmma_kernel<kDWM, kDWN><<<dim3(ntile, nsplit), kDWM * kDWN * 32, syrk_smem, st>>>(panel[b], Mpad, pc_sub, tiles, parts, flags[b], nq);
+        else syrk_panel_bulk_kernel<kDWM, kDWN><<<dim3(ntile, nsplit), kDWM * kDWN * 32 + 32, syrk_smem, st>>>(panel[b], Mpad, pc_sub, tiles, parts, flags[b], nq);
         HP_LAUNCH_CHECK("syrk_panel_kernel");
         rc = check_cuda(cudaEventRecord(pipe->consumed[b], st), "cudaEventRecord");
     }

@@ -287,7 +287,7 @@ def config4(dev, natom=300, peak=None, with_sc=False):
     flop_regen = float(grid.size) * (8.0 * natom + 36.0 * M)
     flop_credit = flop * (frac_exec if executed else 1.0) + flop_regen  # screening off: every tile ran
     out["roofline_hessian"] = {
-        "kernel": "basis_chunk_kernel + syrk_panel_dmma_kernel (mma.sync m8n8k4 f64) + hessian_finish_kernel",
+        "kernel": "basis_chunk_kernel + syrk_panel_bulk_kernel (mma.sync m8n8k4 f64, cp.async.bulk + mbarrier operand ring) + hessian_finish_kernel",
         "bound": "fp64 (tensor)", "ms": ms, "flop_algorithmic_dense": flop + flop_regen, "flop_regeneration": flop_regen,
         "flop_credited": flop_credit,
         "achieved": flop_credit / (ms * 1e-3) / 1e12, "peak": peak, "unit": "TFLOP/s",
