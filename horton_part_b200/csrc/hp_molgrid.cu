@@ -11,6 +11,8 @@
 // (M, Npts) `pro_shells` / `rho*pro_shells` arrays (glisa.py:335-344; 2 x 105 GB at config 4) are
 // never materialised.  Partial sums are kept per thread block and combined in a fixed order, so
 // results are bit-reproducible run to run.
+#include <cstdlib>
+
 #include "hp_common.cuh"
 #include "hp_math.cuh"
 
@@ -40,6 +42,72 @@ __device__ __forceinline__ double mg_shell(double alpha, double n, double r) {
     return exp_neg_poly(-alpha * r);
 }
 
+// Screening of the moments pass (MODE 0).  For one chunk of points with bounding sphere (c, R) every point
+// is at least dmin = max(|c - R_a| - R, 0) away from atom a, so shell k of that atom adds at most
+// |A_k| exp(-alpha_k dmin^n) sum_p |t(p)| to out[k] over the whole chunk.  Below 2^-kMgScreenBits the
+// (chunk, shell) pair is skipped by the whole block: the integrals I_k = int rho g_k / rho0 are O(1) (they are
+// 1 at the gLISA fixed point) and a grid has < 2^20 chunks, so everything skipped together stays below
+// 2^-60 -- under the rounding of the sums themselves.  HP_B200_MOMENTS_SCREEN=0 evaluates every pair.
+constexpr double kMgScreenBits = 80.0;
+
+template <int kP>
+__device__ __forceinline__ void mg_chunk_bounds(const double (&x)[kP], const double (&y)[kP], const double (&z)[kP],
+                                                const double (&t)[kP], int64_t first, int64_t npts,
+                                                double (*s_box)[kMgWarps], double& cx, double& cy, double& cz,
+                                                double& crad, double& log_tsum) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const double big = 1e300;
+    double lo[3] = {big, big, big}, hi[3] = {-big, -big, -big}, ts = 0.0;
+#pragma unroll
+    for (int j = 0; j < kP; ++j) {
+        if (first + int64_t(j) * kMgThreads + threadIdx.x < npts) {
+            lo[0] = fmin(lo[0], x[j]); hi[0] = fmax(hi[0], x[j]);
+            lo[1] = fmin(lo[1], y[j]); hi[1] = fmax(hi[1], y[j]);
+            lo[2] = fmin(lo[2], z[j]); hi[2] = fmax(hi[2], z[j]);
+        }
+        ts += fabs(t[j]);
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            lo[a] = fmin(lo[a], __shfl_xor_sync(0xffffffffu, lo[a], off));
+            hi[a] = fmax(hi[a], __shfl_xor_sync(0xffffffffu, hi[a], off));
+        }
+        ts += __shfl_xor_sync(0xffffffffu, ts, off);
+    }
+    __syncthreads();
+    if (lane == 0) {
+#pragma unroll
+        for (int a = 0; a < 3; ++a) { s_box[a][warp] = lo[a]; s_box[3 + a][warp] = hi[a]; }
+        s_box[6][warp] = ts;
+    }
+    __syncthreads();
+    ts = 0.0;
+    for (int w = 0; w < kMgWarps; ++w) {
+#pragma unroll
+        for (int a = 0; a < 3; ++a) { lo[a] = fmin(lo[a], s_box[a][w]); hi[a] = fmax(hi[a], s_box[3 + a][w]); }
+        ts += s_box[6][w];
+    }
+    cx = 0.5 * (lo[0] + hi[0]); cy = 0.5 * (lo[1] + hi[1]); cz = 0.5 * (lo[2] + hi[2]);
+    // radius: farthest point of the chunk from the box centre (tighter than the half diagonal)
+    double r2 = 0.0;
+#pragma unroll
+    for (int j = 0; j < kP; ++j) {
+        if (first + int64_t(j) * kMgThreads + threadIdx.x < npts) {
+            const double dx = x[j] - cx, dy = y[j] - cy, dz = z[j] - cz;
+            r2 = fmax(r2, fma(dz, dz, fma(dy, dy, dx * dx)));
+        }
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) r2 = fmax(r2, __shfl_xor_sync(0xffffffffu, r2, off));
+    if (lane == 0) s_box[7][warp] = r2;
+    __syncthreads();
+    for (int w = 0; w < kMgWarps; ++w) r2 = fmax(r2, s_box[7][w]);
+    crad = sqrt(r2) * (1.0 + 1e-12);
+    log_tsum = log(ts);  // -inf for an all-masked chunk: every shell is dead
+}
+
 // MODE 0: per-shell moments with weight t;  MODE 1: per-atom clipped-weight integrals.
 template <int F, int MODE, int kP>
 __global__ void __launch_bounds__(kMgThreads, 2)
@@ -49,8 +117,13 @@ molgrid_reduce_kernel(int64_t npts, const double* __restrict__ px, const double*
                       const double* __restrict__ shell_alpha, const double* __restrict__ shell_order,
                       int ntile, const int* __restrict__ tile_off, const double* __restrict__ rho,
                       const double* __restrict__ molw, const double* __restrict__ promol,
-                      double density_cutoff, int power, int nout, double* __restrict__ partial) {
+                      double density_cutoff, int power, int nout, int screen, double* __restrict__ partial) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    // MODE 0 screening (see mg_chunk_bounds): per chunk, shells that cannot contribute are skipped block-wide
+    __shared__ double s_box[8][kMgWarps];
+    __shared__ double s_dmin[kMgTileAtoms];
+    __shared__ unsigned char s_live[kMgTileShells];
+    __shared__ unsigned char s_alive[kMgTileAtoms];
     MgAtom* s_atoms = reinterpret_cast<MgAtom*>(smem_raw);
     double2* s_AB = reinterpret_cast<double2*>(s_atoms + kMgTileAtoms);
     double* s_N = reinterpret_cast<double*>(s_AB + kMgTileShells);
@@ -82,6 +155,10 @@ molgrid_reduce_kernel(int64_t npts, const double* __restrict__ px, const double*
                 inv[j] = r0;
             }
         }
+        // bounding sphere of the chunk's points and sum |t| over them (MODE 0 with screening)
+        double cx = 0.0, cy = 0.0, cz = 0.0, crad = 0.0, log_tsum = 0.0;
+        const bool screened = (MODE == 0) && screen;
+        if (screened) mg_chunk_bounds<kP>(x, y, z, t, chunk * span, npts, s_box, cx, cy, cz, crad, log_tsum);
         for (int tl = 0; tl < ntile; ++tl) {
             const int a0 = tile_off[tl], a1 = tile_off[tl + 1];
             const int sh0 = atom_sh_off[a0], sh1 = atom_sh_off[a1];
@@ -92,13 +169,38 @@ molgrid_reduce_kernel(int64_t npts, const double* __restrict__ px, const double*
                 rec.s0 = atom_sh_off[a0 + i] - sh0;
                 rec.ns = atom_sh_off[a0 + i + 1] - atom_sh_off[a0 + i];
                 s_atoms[i] = rec;
+                if (screened) {
+                    const double dx = cx - rec.x, dy = cy - rec.y, dz = cz - rec.z;
+                    s_dmin[i] = fmax(sqrt(fma(dz, dz, fma(dy, dy, dx * dx))) - crad, 0.0);
+                }
             }
             for (int i = threadIdx.x; i < sh1 - sh0; i += kMgThreads) {
                 s_AB[i] = make_double2(shell_A[sh0 + i], shell_alpha[sh0 + i]);
                 if (F == HP_FUNCTOR_GENERAL) s_N[i] = shell_order[sh0 + i];
             }
             __syncthreads();
+            if (screened) {
+                // shell k of atom i is dead for this chunk when |A_k| exp(-alpha_k dmin^n) sum|t| < 2^-kMgScreenBits
+                for (int i = threadIdx.x; i < a1 - a0; i += kMgThreads) {
+                    const MgAtom rec = s_atoms[i];
+                    const double d = s_dmin[i];
+                    unsigned char any = 0;
+                    for (int k = 0; k < rec.ns; ++k) {
+                        const double2 ab = s_AB[rec.s0 + k];
+                        const double n = (F == HP_FUNCTOR_GENERAL) ? s_N[rec.s0 + k] : 1.0;
+                        const double dn = (F == HP_FUNCTOR_GAUSS) ? d * d
+                                          : ((F == HP_FUNCTOR_SLATER || n == 1.0) ? d : ((n == 2.0) ? d * d : pow(d, n)));
+                        // log(|A| sum|t|) - alpha d^n >= -bits ln 2  (a NaN anywhere keeps the shell)
+                        const bool dead = log(fabs(ab.x)) + log_tsum - ab.y * dn < -kMgScreenBits * 0.6931471805599453;
+                        s_live[rec.s0 + k] = dead ? 0 : 1;
+                        any |= dead ? 0 : 1;
+                    }
+                    s_alive[i] = any;
+                }
+                __syncthreads();
+            }
             for (int i = 0; i < a1 - a0; ++i) {
+                if (screened && !s_alive[i]) continue;
                 const MgAtom rec = s_atoms[i];
                 double r[kP], f[kP];
 #pragma unroll
@@ -108,6 +210,7 @@ molgrid_reduce_kernel(int64_t npts, const double* __restrict__ px, const double*
                     f[j] = 0.0;
                 }
                 for (int k = 0; k < rec.ns; ++k) {
+                    if (screened && !s_live[rec.s0 + k]) continue;
                     const double2 ab = s_AB[rec.s0 + k];
                     const double n = (F == HP_FUNCTOR_GENERAL) ? s_N[rec.s0 + k] : 1.0;
                     if (MODE == 0) {
@@ -133,6 +236,7 @@ molgrid_reduce_kernel(int64_t npts, const double* __restrict__ px, const double*
             const int ncol = (MODE == 0) ? (sh1 - sh0) : (a1 - a0);
             const int col0 = (MODE == 0) ? sh0 : a0;
             for (int c = threadIdx.x; c < ncol; c += kMgThreads) {
+                if (screened && !s_live[c]) continue;  // nothing was accumulated for a dead shell
                 double tot = 0.0;
 #pragma unroll
                 for (int w = 0; w < kMgWarps; ++w) tot += s_acc[w * kMgTileShells + c];
@@ -375,9 +479,11 @@ static int launch_molgrid(int64_t npts, const double* px, const double* py, cons
     int rc = check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)),
                         "cudaFuncSetAttribute");
     if (rc) return rc;
+    const char* env = getenv("HP_B200_MOMENTS_SCREEN");  // read per call: tests compare both settings
+    const int screen = !(env && env[0] == '0');
     kern<<<nblocks, kMgThreads, smem, st>>>(npts, px, py, pz, natom, atom_xyz, atom_sh_off, shell_A,
                                             shell_alpha, shell_order, ntile, tile_off, rho, molw, promol,
-                                            cutoff, power, nout, partial);
+                                            cutoff, power, nout, screen, partial);
     return check_cuda(cudaGetLastError(), "molgrid_reduce_kernel");
 }
 

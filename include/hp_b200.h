@@ -311,7 +311,8 @@ HP_API int hp_atom_weight_integrals_spline(int64_t npts, const double* px, const
  *   hp_shell_moments: out[m] = sum_p t(p) * shell_A[m] * exp(-alpha_m r^n_m),
  *       t = molw*rho/promol^power, 0 where rho < cutoff or promol < cutoff.  With shell_A = the
  *       normalisation of g_m: power 1 gives function_g's integrals (glisa.py:866-873) and minus
- *       the gradient (glisa.py:454-458).
+ *       the gradient (glisa.py:454-458).  (chunk of 1,024 points, shell) pairs whose bound
+ *       |shell_A| exp(-alpha dmin^n) sum|t| is below 2^-80 are skipped (HP_B200_MOMENTS_SCREEN=0 disables).
  *   hp_atom_weight_integrals: out[a] = sum_p molw*rho*clip(rho0_a/promol, 0, 1) with
  *       rho0_a = sum_{m in a} shell_A[m] exp(...)  (update_at_weights(force_on_molgrid) +
  *       grid.integrate(at_weights*rho), glisa.py:269-278), without storing natom x Npts weights.
@@ -373,8 +374,9 @@ HP_API int hp_molgrid_update_pass(int functor, int64_t npts, const double* px, c
 /* hp_hessian: H[m][n] = sum_p molw*rho*g_m*g_n/promol^2 (masked like hp_shell_moments), the dense
  * M x M gLISA Hessian of _working_matrix(nderiv=2) (glisa.py:459-470), row-major, both triangles
  * filled.  shell_atom[m] = atom of shell m; g_m = shell_norm[m]*exp(-alpha_m r^n).  `scratch` needs
- * hp_hessian_scratch_bytes(M) bytes.  The function enqueues one basis-panel kernel and one SYRK
- * kernel per chunk of <= 65,536 grid points and synchronises the stream once at the start. */
+ * hp_hessian_scratch_bytes(M) bytes.  The function enqueues one basis-panel kernel (on an internal side
+ * stream, double-buffered) and one tile-product kernel per chunk of up to 64 x 1,280 grid points; it does not
+ * synchronise the stream. */
 HP_API size_t hp_hessian_scratch_bytes(int32_t M);
 HP_API int hp_hessian(int functor, int64_t npts, const double* px, const double* py, const double* pz,
                       const double* atom_xyz, const int32_t* shell_atom, const double* shell_norm,

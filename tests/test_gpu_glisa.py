@@ -125,3 +125,30 @@ def test_hessian_block_screening_matches_dense_product(monkeypatch):
     # entries between far-apart atoms, which the screening may drop entirely, are below rounding of the diagonal
     dropped = (H == 0) & (H0 != 0)
     assert float(H0[dropped].abs().max()) <= 1e-17 * scale if bool(dropped.any()) else True
+
+
+def test_moment_screening_matches_unscreened_pass(monkeypatch):
+    """function_g's integrals with the chunk-geometry screening of the moments pass equal the unscreened ones
+    to rounding (skipped terms are below 2^-80 per chunk and shell)."""
+    from horton_part_b200 import GlobalLinearISAWPart, gridlite, synthetic
+    from horton_part_b200.core.basis import ExpBasisFuncHelper
+
+    coords, numbers = synthetic.peptide_like(80, seed=1)
+    rgrid = gridlite.BeckeRTransform(1e-4, 1.5).transform_1d_grid(gridlite.GaussChebyshev(40))
+    grid = gridlite.MolGrid.from_size(numbers, coords, 50, rgrid, np.ones(len(numbers) * 40 * 50), store=True)
+    for basis in ("gauss", "slater"):
+        helper = ExpBasisFuncHelper.from_function_type(basis)
+        rho, w = synthetic.expbasis_promolecule_device(grid, coords, numbers, helper, device="cuda:0",
+                                                       scale={1: 0.75, 6: 6.2, 7: 7.3, 8: 8.4})  # fmt: skip
+        grid.aim_weights[:] = w
+        grid.weights[:] = grid.atweights * w
+        part = GlobalLinearISAWPart(coords, numbers, numbers.astype(float), grid, rho, solver="sc", basis_func=basis)
+        part._init_propars()
+        part._promol_and_entropy()
+        monkeypatch.delenv("HP_B200_MOMENTS_SCREEN", raising=False)
+        screened = part._shell_integrals(1).cpu().numpy().copy()
+        monkeypatch.setenv("HP_B200_MOMENTS_SCREEN", "0")
+        dense = part._shell_integrals(1).cpu().numpy().copy()
+        monkeypatch.delenv("HP_B200_MOMENTS_SCREEN", raising=False)
+        assert np.all(np.isfinite(dense)) and np.abs(dense).min() > 1e-3
+        np.testing.assert_allclose(screened, dense, rtol=1e-13, atol=0.0)
