@@ -116,6 +116,7 @@ EXPORTS = {
         _int,
         [_i64, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _f64, _i32, _p, _sz, _p, _p],
     ),
+    "hp_fold_chunk_entropy": (_int, [_i64, _p, _p, _p]),
     "hp_hessian_tiles_executed": (_int, [_i32, _i64, _p, _p, _p, _p, _p]),
     "hp_aim_on_points": (_int, [_int, _i64, _p, _p, _p, _i32, _p, _p, _p, _p, _p, _i32, _p, _p, _f64, _p, _p, _p, _p]),
     "hp_comm_nccl_version": (_i32, []),

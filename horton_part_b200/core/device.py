@@ -188,25 +188,56 @@ class GridSlab:
             raise ValueError("grid.points must have shape (Npts, 3)")
         self.bytes_h2d = 0
 
-        from .hostmem import upload
+        from .hostmem import upload, upload_into
 
         def up(a, dtype=np.float64):
             t = upload(a, dev, dtype)  # pipelined through page-locked staging when `a` is pageable
             self.bytes_h2d += t.numel() * t.element_size()
             return t
 
-        aos = up(pts[lo:hi])
-        self.px = torch.empty(self.npts, dtype=torch.float64, device=dev)
-        self.py = torch.empty_like(self.px)
-        self.pz = torch.empty_like(self.px)
-        _lib.call("hp_split_points", aos, self.npts, self.px, self.py, self.pz, stream_ptr(dev))
-        self.points_aos = aos if keep_aos else None
-        self.molw = up(np.asarray(grid.weights)[lo:hi])
-        self.rho = up(np.asarray(moldens)[lo:hi])
+        # Large slabs go up in two parts: the points of the first local atoms now, the rest when the first
+        # pass over the grid has been launched on them (ShellTable.promol_weights), so that most of the upload
+        # runs under the first iteration's kernel.  Anything else that touches the point arrays first
+        # completes the upload on the spot (the properties below).
+        self._pending_upload = None
+        self._split_atoms = self._choose_split(grid, moldens, need_atgrids)
+        cut = self.npts if not self._split_atoms else int(
+            self.atom_point_offsets_host[self.shard.atom_lo + self._split_atoms] - lo)
+        later = []
+
+        def up_big(host, local=False):
+            """Device tensor for host[lo:hi] (host itself when ``local``); rows [0, cut) are uploaded now,
+            the rest is queued for complete_upload()."""
+            host = np.asarray(host)
+            part = host if local else host[lo:hi]
+            if part.dtype != np.float64 or not part.flags.c_contiguous:
+                part = np.ascontiguousarray(part, dtype=np.float64)
+            if cut == self.npts and part.nbytes < (8 << 20):
+                out = torch.from_numpy(part).to(dev)
+                self.bytes_h2d += out.numel() * out.element_size()
+                return out
+            out = torch.empty(part.shape, dtype=torch.float64, device=dev)
+            self.bytes_h2d += out.numel() * out.element_size()
+            if cut:
+                upload_into(out[:cut], part[:cut])
+            if cut < self.npts:
+                later.append((out[cut:], part[cut:]))
+            return out
+
+        aos = up_big(pts)
+        self._px = torch.empty(self.npts, dtype=torch.float64, device=dev)
+        self._py = torch.empty_like(self._px)
+        self._pz = torch.empty_like(self._px)
+        if cut:
+            _lib.call("hp_split_points", aos, cut, self._px, self._py, self._pz, stream_ptr(dev))
+        self._aos = aos if (keep_aos or cut < self.npts) else None
+        self._keep_aos = keep_aos
+        self._molw = up_big(grid.weights)
+        self._rho = up_big(moldens)
         self.atom_xyz = up(coordinates)
         self.atom_point_offsets = up(self.atom_point_offsets_host, np.int64)
 
-        self.atw = None
+        self._atw = None
         if need_atgrids:
             atgrids = grid.atgrids
             if atgrids is None:
@@ -217,10 +248,10 @@ class GridSlab:
             a_lo, a_hi = self.shard.atom_lo, self.shard.atom_hi
             whole = getattr(grid, "atweights", None)
             if whole is not None and len(whole) == self.npts_global:
-                atw = np.asarray(whole)[lo:hi]
+                self._atw = up_big(whole)
             else:
                 atw = np.concatenate([atgrids[a].weights for a in range(a_lo, a_hi)]) if a_hi > a_lo else np.zeros(0)
-            self.atw = up(atw)
+                self._atw = up_big(atw, local=True)
             shell_off, rad_off = [0], [0]
             rad_r, rad_w, rad_w4, rad_r2w = [], [], [], []
             for a in range(a_lo, a_hi):
@@ -254,7 +285,80 @@ class GridSlab:
         self.entropy_partials = torch.zeros(self.npartial, dtype=torch.float64, device=dev)
         from .hostmem import drain
 
-        drain(dev)  # asynchronous uploads from page-locked caller arrays have landed; sources released
+        if later:
+            self._pending_upload = later
+            # the copy stream starts after the allocations and the first part's copies queued so far -- and
+            # NOT after the kernels launched later on the first part (complete_upload does not wait again)
+            self._copy_stream = torch.cuda.Stream(device=dev)
+            self._copy_stream.wait_stream(torch.cuda.current_stream(dev))
+        else:
+            drain(dev)  # asynchronous uploads from page-locked caller arrays have landed; sources released
+
+    # -- two-part upload ------------------------------------------------------------------------------
+    #: slabs below this many bytes of point data go up in one piece
+    split_upload_min_bytes = 512 << 20
+
+    def _choose_split(self, grid, moldens, need_atgrids):
+        """Number of local atoms whose points are uploaded before the first pass starts (0 = no split).
+        With upload time u and pass time c the best cut is the fraction u / (u + c) of the work; the pass
+        costs about twice the upload from page-locked arrays and about as much as the upload from pageable
+        ones, so a third / a half of the points go first."""
+        from .hostmem import is_pinned
+
+        sh = self.shard
+        if (not need_atgrids or sh.nlocal < 8 or os.environ.get("HP_B200_SPLIT_UPLOAD", "1") == "0"
+                or 48 * self.npts < self.split_upload_min_bytes):  # fmt: skip
+            return 0
+        pts = np.asarray(grid.points)
+        frac = 1.0 / 3.0 if (pts.dtype == np.float64 and is_pinned(pts)) else 0.5
+        off = self.atom_point_offsets_host[sh.atom_lo : sh.atom_hi + 1] - self.point_base
+        m = int(np.searchsorted(off, frac * self.npts))
+        return min(max(m, 1), sh.nlocal - 1)
+
+    def complete_upload(self):
+        """Upload the second part of a split slab (copy stream; the current stream waits for it)."""
+        import torch
+
+        later = self._pending_upload
+        if later is None:
+            return
+        self._pending_upload = None
+        from .hostmem import upload_into
+
+        dev = self.device
+        cur = torch.cuda.current_stream(dev)
+        cs = self._copy_stream
+        for out, host in later:
+            upload_into(out, host, stream=cs.cuda_stream)
+        cut = self.npts - later[0][0].shape[0]
+        _lib.call("hp_split_points", self._aos[cut:], self.npts - cut, self._px[cut:], self._py[cut:], self._pz[cut:],
+                  cs.cuda_stream)  # fmt: skip
+        cur.wait_stream(cs)
+        for out, _ in later:
+            out.record_stream(cs)
+        if not self._keep_aos:
+            self._aos.record_stream(cs)
+            self._aos = None
+
+    def finish_upload(self):
+        """complete_upload + release of the page-locked sources (synchronises the current stream)."""
+        from .hostmem import drain
+
+        self.complete_upload()
+        drain(self.device)
+
+    def _whole(self, name):
+        if self._pending_upload is not None:
+            self.finish_upload()  # a consumer that does not know about the split: no overlap, same result
+        return getattr(self, name)
+
+    px = property(lambda self: self._whole("_px"))
+    py = property(lambda self: self._whole("_py"))
+    pz = property(lambda self: self._whole("_pz"))
+    molw = property(lambda self: self._whole("_molw"))
+    rho = property(lambda self: self._whole("_rho"))
+    atw = property(lambda self: self._whole("_atw"))
+    points_aos = property(lambda self: self._whole("_aos") if self._keep_aos else None)
 
     # ------------------------------------------------------------------------------------------
     def shell_project(self):
@@ -358,8 +462,20 @@ class ShellTable:
                 counts = np.diff(coff)
                 sub = np.arange(self._loc_nchunk) - np.repeat(coff[:-1], counts)
                 from_end = np.repeat(counts, counts) - 1 - sub
-                self._loc_chunk_order = to_device(np.argsort(from_end, kind="stable"), s.device, np.int64)
+                order = np.argsort(from_end, kind="stable")
+                self._loc_chunk_order = to_device(order, s.device, np.int64)
                 self._loc_scratch = torch.zeros(self._loc_nchunk + 1, dtype=torch.float64, device=s.device)
+                self._loc_split = None
+                if s._pending_upload is not None:
+                    # first pass of a slab that is still uploading: the atoms whose points are there / the rest
+                    m = s._split_atoms
+                    n_a = int(coff[m])
+                    self._loc_split = (
+                        m, n_a, to_device(order[order < n_a], s.device, np.int64),
+                        to_device(order[order >= n_a] - n_a, s.device, np.int64),
+                        to_device(coff[m:] - n_a, s.device, np.int64),
+                        torch.zeros_like(self.pair_partials),
+                    )
             atom_eps = 0.0
             if bits:
                 if self.skip is None:
@@ -369,16 +485,39 @@ class ShellTable:
                 if self.atom_screen and os.environ.get("HP_B200_ATOM_SCREEN", "1") != "0":
                     atom_eps = 2.0 ** -(float(os.environ.get("HP_B200_ATOM_BITS", 55)) + int(np.ceil(np.log2(max(s.natom, 2)))))
             radius = float("inf") if self.local_radius is None else float(self.local_radius)
-            _lib.call(
-                "hp_promol_weights_local", self.functor, s.npts, s.px, s.py, s.pz, s.point_base, s.natom,
-                s.atom_xyz, s.atom_point_offsets, self.offsets, self.A, self.alpha, self.order,
-                self._loc_ntile, self._loc_tiles, s.rho, s.molw, float(density_cutoff), float(promol_offset),
-                radius, self.skip if bits else None, atom_eps, s.shard.atom_lo, s.shard.nlocal,
-                self._loc_chunk_off, self._loc_chunk_order, self._loc_nchunk, self._loc_scratch,
-                s.promol if want_promol else None,
-                s.at_w if want_weights else None, s.entropy_partials if want_entropy else None,
-                self.pair_partials, stream_ptr(s.device),
-            )  # fmt: skip
+
+            def launch(atom_lo, nlocal, chunk_off, chunk_order, nchunk, scratch, pairs):
+                _lib.call(
+                    "hp_promol_weights_local", self.functor, s.npts, s._px, s._py, s._pz, s.point_base, s.natom,
+                    s.atom_xyz, s.atom_point_offsets, self.offsets, self.A, self.alpha, self.order,
+                    self._loc_ntile, self._loc_tiles, s._rho, s._molw, float(density_cutoff), float(promol_offset),
+                    radius, self.skip if bits else None, atom_eps, atom_lo, nlocal,
+                    chunk_off, chunk_order, nchunk, scratch,
+                    s.promol if want_promol else None,
+                    s.at_w if want_weights else None, s.entropy_partials if want_entropy else None,
+                    pairs, stream_ptr(s.device),
+                )  # fmt: skip
+
+            if s._pending_upload is not None and getattr(self, "_loc_split", None) is not None:
+                # the slab's second part is not on the device yet: pass over the atoms that are, start the
+                # rest of the upload on the copy stream under that kernel, then pass over the other atoms.
+                # Same chunks, same per-chunk entropy slots, one fold over all of them: results are
+                # bit-identical to the single launch.
+                m, n_a, order_a, order_b, coff_b, pairs_a = self._loc_split
+                sh = s.shard
+                launch(sh.atom_lo, m, self._loc_chunk_off, order_a, n_a, self._loc_scratch, pairs_a)
+                s.complete_upload()
+                launch(sh.atom_lo + m, sh.nlocal - m, coff_b, order_b, self._loc_nchunk - n_a,
+                       self._loc_scratch[n_a:], self.pair_partials)
+                self.pair_partials += pairs_a
+                if want_entropy:
+                    _lib.call("hp_fold_chunk_entropy", self._loc_nchunk, self._loc_scratch, s.entropy_partials,
+                              stream_ptr(s.device))  # fmt: skip
+                s.finish_upload()
+                return
+            s.px  # completes a pending upload (no-op otherwise)
+            launch(s.shard.atom_lo, s.shard.nlocal, self._loc_chunk_off, self._loc_chunk_order, self._loc_nchunk,
+                   self._loc_scratch, self.pair_partials)
             return
         _lib.call(
             "hp_promol_weights", self.functor, s.npts, s.px, s.py, s.pz, s.point_base, s.natom,

@@ -20,7 +20,7 @@ import numpy as np
 
 from .. import _lib
 
-__all__ = ["pinned_empty", "is_pinned", "upload", "download", "pool_stats"]
+__all__ = ["pinned_empty", "is_pinned", "upload", "upload_into", "download", "pool_stats"]
 
 _STAGING_BYTES = 128 << 20
 _staging = None
@@ -57,30 +57,46 @@ def _staging_buffer():
     return _staging
 
 
+def upload_into(out, array, stream=None):
+    """Copy the C-contiguous NumPy ``array`` into the device tensor ``out`` (same number of bytes) on the CUDA
+    stream ``stream`` (raw handle; default: the device's current stream).  Page-locked sources go out as one
+    asynchronous copy and stay referenced until :func:`drain`; pageable ones are pipelined through the pooled
+    page-locked staging buffer (the call returns when the source has been read)."""
+    import torch
+
+    a = np.ascontiguousarray(array)
+    nbytes = a.nbytes
+    if nbytes != out.numel() * out.element_size() or not out.is_contiguous():
+        raise ValueError("upload_into: destination must be a contiguous tensor of the source's size")
+    if nbytes == 0:
+        return out
+    device = out.device
+    if stream is None:
+        stream = torch.cuda.current_stream(device).cuda_stream
+    if is_pinned(a):
+        # asynchronous copy straight from the caller's page-locked array: the source stays referenced in
+        # _pending until drain() has synchronised the stream the consumers run on (GridSlab does that once for
+        # all of its uploads), so neither the garbage collector nor torch's host allocator can recycle it while
+        # the DMA engine still reads it.  The caller must not modify the array before drain() returns.
+        _stats["direct_uploads"] += 1
+        _lib.call("hp_host_to_device", out, int(a.ctypes.data), nbytes, None, 0, 1, stream)
+        _pending.append((torch.device(device), out, a))
+        return out
+    stage = _staging_buffer()
+    _stats["staged_uploads"] += 1
+    _lib.call("hp_host_to_device", out, int(a.ctypes.data), nbytes, stage, stage.numel(), _threads(), stream)
+    return out
+
+
 def upload(array, device, dtype=None):
     """Device tensor holding a copy of ``array`` (C-contiguous, optionally converted to ``dtype``)."""
     import torch
 
     a = np.ascontiguousarray(array, dtype=dtype)
     src = torch.from_numpy(a)
-    nbytes = a.nbytes
-    if nbytes < (8 << 20):
+    if a.nbytes < (8 << 20):
         return src.to(device)
-    out = torch.empty(src.shape, dtype=src.dtype, device=device)
-    stream = torch.cuda.current_stream(device).cuda_stream
-    if is_pinned(a):
-        # asynchronous copy straight from the caller's page-locked array: the source stays referenced in
-        # _pending until drain() has synchronised the stream (GridSlab.__init__ does that once for all of
-        # its uploads), so neither the garbage collector nor torch's host allocator can recycle it while
-        # the DMA engine still reads it.  The caller must not modify the array before drain() returns.
-        _stats["direct_uploads"] += 1
-        _lib.call("hp_host_to_device", out, int(a.ctypes.data), nbytes, None, 0, 1, stream)
-        _pending.append((torch.device(device), src, a))
-        return out
-    stage = _staging_buffer()
-    _stats["staged_uploads"] += 1
-    _lib.call("hp_host_to_device", out, int(a.ctypes.data), nbytes, stage, stage.numel(), _threads(), stream)
-    return out
+    return upload_into(torch.empty(src.shape, dtype=src.dtype, device=device), a)
 
 
 def drain(device=None):

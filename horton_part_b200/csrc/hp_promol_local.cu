@@ -647,3 +647,14 @@ extern "C" int hp_promol_weights_local(int functor, int64_t npts, const double* 
     }
     return HP_OK;
 }
+
+// Fold of the per-chunk entropy slots into the kMaxPartials partial sums, as hp_promol_weights_local does
+// at its end: for a pass that was launched in several parts over disjoint chunk ranges (first iteration of
+// a slab whose upload is still running), one fold over all slots gives the single launch's result bit for bit.
+extern "C" int hp_fold_chunk_entropy(int64_t nchunk, const double* chunk_scratch, double* entropy_partials,
+                                     void* stream) {
+    HP_REQUIRE(nchunk >= 0 && entropy_partials && (nchunk == 0 || chunk_scratch), "bad arguments");
+    fold_chunk_entropy_kernel<<<kMaxPartials / 256, 256, 0, as_stream(stream)>>>(nchunk, chunk_scratch, entropy_partials);
+    HP_LAUNCH_CHECK("fold_chunk_entropy_kernel");
+    return HP_OK;
+}

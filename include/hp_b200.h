@@ -164,6 +164,12 @@ HP_API int hp_promol_weights_local(int functor, int64_t npts, const double* px, 
                                    int64_t nchunk, double* chunk_scratch, double* promol,
                                    double* at_weights, double* entropy_partials,
                                    uint64_t* pair_partials, void* stream);
+/* One fold of `nchunk` per-chunk entropy slots (chunk_scratch, as filled by hp_promol_weights_local) into the
+ * entropy partial sums: used when one pass is launched in parts over disjoint ranges of local atoms (first
+ * iteration of a slab whose second half is still uploading, core/device.py) -- the result equals the single
+ * launch's bit for bit.  `_update_entropy`, core/iterstock.py:125-130. */
+HP_API int hp_fold_chunk_entropy(int64_t nchunk, const double* chunk_scratch, double* entropy_partials,
+                                 void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * (row a8) spherical average of w_a*rho over each radial shell of each atom's own atomic grid.

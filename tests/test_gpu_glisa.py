@@ -78,7 +78,11 @@ def test_hessian_against_oracle(water6g):
     assert float(part._scal[1].item()) == pytest.approx(f, rel=1e-10)
 
 
-def test_glisa_newton_against_reference_run(water6g):
+@pytest.mark.parametrize("host_solve", [False, True])
+def test_glisa_newton_against_reference_run(water6g, host_solve, monkeypatch):
+    """Newton step by Cholesky + refinement on the device (default) and by the reference's host LAPACK route."""
+    if host_solve:
+        monkeypatch.setenv("HP_B200_HOST_SOLVE", "1")
     part = _glisa(water6g, solver="newton")
     ref = _gold(water6g["gold"], "glisa_newton")
     assert part["niter"] == int(ref["niter"]) == 5

@@ -85,3 +85,65 @@ def test_results_survive_a_second_job(make_water):
     second.do_partitioning()
     assert np.array_equal(promol, keep_p) and np.array_equal(w0, keep_w)
     assert not np.array_equal(second["promoldens"], promol)
+
+
+@pytest.mark.parametrize("pinned", [False, True])
+def test_split_upload_gives_bit_identical_results(pinned, monkeypatch):
+    """A slab uploaded in two parts (second part under the first pass's kernel) gives the same bits as the
+    one-piece upload: charges, parameters, entropies, pair counters -- from pageable and page-locked arrays."""
+    from horton_part_b200 import MBISWPart, gridlite, synthetic
+    from horton_part_b200.core import hostmem
+    from horton_part_b200.core.device import GridSlab
+
+    coords, numbers = synthetic.water_cluster(30, seed=3)
+    rgrid = gridlite.BeckeRTransform(1e-4, 1.5).transform_1d_grid(gridlite.GaussChebyshev(40))
+    grid = gridlite.MolGrid.from_size(numbers, coords, 50, rgrid, np.ones(len(numbers) * 40 * 50), store=True)
+    rho, w, _, _ = synthetic.slater_promolecule_device(grid, coords, numbers, device="cuda:0")
+    grid.aim_weights[:] = w
+    grid.weights[:] = grid.atweights * w
+    if pinned:
+        for name in ("points", "weights"):
+            pin = hostmem.pinned_empty(getattr(grid, name).shape)
+            pin[...] = getattr(grid, name)
+            setattr(grid, name, pin)
+        pin = hostmem.pinned_empty(rho.shape)
+        pin[...] = rho
+        rho = pin
+    monkeypatch.setattr(GridSlab, "split_upload_min_bytes", 1 << 20)
+
+    def run(split):
+        monkeypatch.setenv("HP_B200_SPLIT_UPLOAD", "1" if split else "0")
+        part = MBISWPart(coords, numbers, numbers.astype(float), grid, rho, maxiter=6)
+        part.do_partitioning()
+        assert bool(part.slab._split_atoms) == split and part.slab._pending_upload is None
+        return part
+
+    one, two = run(False), run(True)
+    assert one["niter"] == two["niter"] == 6
+    for key in ("charges", "propars", "history_entropies", "history_changes", "promoldens"):
+        assert np.array_equal(np.asarray(one[key]), np.asarray(two[key])), key
+    for a in range(len(numbers)):
+        assert np.array_equal(one[f"at_weights_{a}"], two[f"at_weights_{a}"])
+
+
+def test_split_upload_is_completed_by_unaware_consumers(monkeypatch):
+    """Reading a point array of a half-uploaded slab completes the upload first."""
+    import torch
+
+    from horton_part_b200 import gridlite, synthetic
+    from horton_part_b200.core.device import GridSlab
+
+    coords, numbers = synthetic.water_cluster(30, seed=3)
+    rgrid = gridlite.BeckeRTransform(1e-4, 1.5).transform_1d_grid(gridlite.GaussChebyshev(40))
+    grid = gridlite.MolGrid.from_size(numbers, coords, 50, rgrid, np.ones(len(numbers) * 40 * 50), store=True)
+    rho = np.random.default_rng(1).random(grid.size)
+    monkeypatch.setattr(GridSlab, "split_upload_min_bytes", 1 << 20)
+    slab = GridSlab(grid, rho, coords, device="cuda:0")
+    assert slab._pending_upload is not None and slab._split_atoms > 0
+    assert np.array_equal(slab.rho.cpu().numpy(), rho)
+    assert slab._pending_upload is None
+    torch.cuda.synchronize()
+    assert np.array_equal(slab.px.cpu().numpy(), grid.points[:, 0])
+    assert np.array_equal(slab.pz.cpu().numpy(), grid.points[:, 2])
+    assert np.array_equal(slab.molw.cpu().numpy(), grid.weights)
+    assert np.array_equal(slab.atw.cpu().numpy(), np.concatenate([g.weights for g in grid.atgrids]))
