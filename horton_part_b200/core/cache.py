@@ -63,13 +63,35 @@ def _tagset(tags):
     return set() if tags is None else set(tags)
 
 
+class Deferred:
+    """A cache value that is assembled on first access: ``Deferred(thunk)`` stored with :meth:`Cache.dump`
+    is replaced by ``thunk()`` the first time the key is loaded or iterated over.  Used for results whose
+    data is already on the host but whose reference-shaped array costs time to build (a sharded rank's
+    whole-grid ``promoldens``: 0.5 GB of pages for a slice that is already there)."""
+
+    __slots__ = ("thunk",)
+
+    def __init__(self, thunk):
+        self.thunk = thunk
+
+
 class _Entry:
-    __slots__ = ("value", "valid", "tags")
+    __slots__ = ("_value", "valid", "tags")
 
     def __init__(self, value, tags):
-        self.value = value
+        self._value = value
         self.valid = True
         self.tags = _tagset(tags)
+
+    @property
+    def value(self):
+        if isinstance(self._value, Deferred):
+            self._value = self._value.thunk()
+        return self._value
+
+    @value.setter
+    def value(self, v):
+        self._value = v
 
     def matches(self, shape):
         v = self.value
@@ -78,6 +100,8 @@ class _Entry:
     def invalidate(self):
         """Returns True when the payload could be wiped in place (memory kept for reuse)."""
         self.valid = False
+        if isinstance(self._value, Deferred):
+            return False  # never assembled: nothing to keep
         v = self.value
         if isinstance(v, np.ndarray):
             v[...] = 0.0

@@ -89,9 +89,21 @@ class AbstractStockholderWPart(WPart):
         promol_h = download(slab.promol)
         if slab.npts == self.grid.size:
             self.cache.dump("promoldens", promol_h)
-        else:  # sharded: only this rank's slice is known
-            promol = self.cache.load("promoldens", alloc=self.grid.size)[0]
-            promol[lo : lo + slab.npts] = promol_h
+        else:
+            # sharded: only this rank's slice is known.  The slice is on the host now; the whole-grid array
+            # (zeros elsewhere) is assembled when somebody asks for it -- touching 8 bytes x Npts of fresh
+            # pages per call costs more than the rank's share of an iteration.
+            from .cache import Deferred
+
+            npts, n = self.grid.size, slab.npts
+            self.cache.dump("promoldens_local", promol_h)
+
+            def assemble():
+                whole = np.zeros(npts)
+                whole[lo : lo + n] = promol_h
+                return whole
+
+            self.cache.dump("promoldens", Deferred(assemble))
         at_w = download(slab.at_w)
         off = slab.atom_point_offsets_host
         for a in range(slab.shard.atom_lo, slab.shard.atom_hi):

@@ -168,3 +168,26 @@ def test_tags_in_load_and_clear():
     for tags in ("w", "aw"):
         with pytest.raises(ValueError):
             c.load("tmp", alloc=5, tags=tags)
+
+
+def test_deferred_values_are_assembled_on_first_access():
+    from horton_part_b200.core.cache import Cache, Deferred
+
+    calls = []
+
+    def build():
+        calls.append(1)
+        return np.arange(4.0)
+
+    c = Cache()
+    c.dump("whole", Deferred(build), tags="o")
+    assert "whole" in c and not calls  # membership does not assemble
+    assert np.array_equal(c.load("whole"), np.arange(4.0)) and len(calls) == 1
+    assert c.load("whole") is c.load("whole") and len(calls) == 1  # assembled once, then an ordinary value
+    c.dump("never", Deferred(build))
+    c.clear()
+    assert len(calls) == 1  # clearing an unassembled value does not build it
+    with __import__("pytest").raises(KeyError):
+        c.load("never")
+    c.dump("again", Deferred(build))
+    assert dict(c.iteritems())["again"].shape == (4,) and len(calls) == 2
