@@ -721,7 +721,8 @@ int hessian_run(int64_t npts, int32_t M, void* scratch, size_t scratch_bytes, do
     // tensor-core (DMMA) tile product by default; HP_B200_HESSIAN_DFMA=1 selects the vector-FMA kernel
     static const bool use_dfma = [] { const char* e = getenv("HP_B200_HESSIAN_DFMA"); return e && e[0] == '1'; }();
     // operand pipeline of the DMMA kernel: bulk copies + mbarriers (default) or cp.async groups + __syncthreads
-    static const bool use_cpasync = [] { const char* e = getenv("HP_B200_HESSIAN_PIPE"); return e && e[0] == 'c'; }();
+    const char* pipe_env = getenv("HP_B200_HESSIAN_PIPE");  // read per call: a test compares the two bit for bit
+    const bool use_cpasync = pipe_env && pipe_env[0] == 'c';
     constexpr size_t kBulkSmem = sizeof(double) * kDStages * 2 * kDK * kDStride + 2 * kDStages * sizeof(unsigned long long);
     const size_t syrk_smem = use_dfma ? sizeof(double) * 2 * 2 * kHK * kHT
                                       : (use_cpasync ? sizeof(double) * kDStages * 2 * kDK * kDStride : kBulkSmem);

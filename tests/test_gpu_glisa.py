@@ -156,3 +156,32 @@ def test_moment_screening_matches_unscreened_pass(monkeypatch):
         monkeypatch.delenv("HP_B200_MOMENTS_SCREEN", raising=False)
         assert np.all(np.isfinite(dense)) and np.abs(dense).min() > 1e-3
         np.testing.assert_allclose(screened, dense, rtol=1e-13, atol=0.0)
+
+
+def test_hessian_operand_pipelines_agree_bit_for_bit(monkeypatch):
+    """The bulk-copy + mbarrier operand ring and the cp.async + __syncthreads pipeline feed the same DMMAs in
+    the same order: H must be identical to the last bit, call after call (a missed dependency between the
+    asynchronous copies and the fragment loads would show up here as run-to-run differences)."""
+    import torch
+
+    from horton_part_b200 import GlobalLinearISAWPart, gridlite, synthetic
+    from horton_part_b200.core.basis import ExpBasisFuncHelper
+
+    coords, numbers = synthetic.peptide_like(80, seed=1)
+    rgrid = gridlite.BeckeRTransform(1e-4, 1.5).transform_1d_grid(gridlite.GaussChebyshev(40))
+    grid = gridlite.MolGrid.from_size(numbers, coords, 50, rgrid, np.ones(len(numbers) * 40 * 50), store=True)
+    helper = ExpBasisFuncHelper.from_function_type("gauss")
+    rho, w = synthetic.expbasis_promolecule_device(grid, coords, numbers, helper, device="cuda:0",
+                                                   scale={1: 0.75, 6: 6.2, 7: 7.3, 8: 8.4})  # fmt: skip
+    grid.aim_weights[:] = w
+    grid.weights[:] = grid.atweights * w
+    part = GlobalLinearISAWPart(coords, numbers, numbers.astype(float), grid, rho, solver="newton")
+    part._init_propars()
+    part._promol_and_entropy()
+    for screen in ("1", "0"):
+        monkeypatch.setenv("HP_B200_HESSIAN_SCREEN", screen)
+        monkeypatch.setenv("HP_B200_HESSIAN_PIPE", "cpasync")
+        ref = part.hessian().clone()
+        monkeypatch.setenv("HP_B200_HESSIAN_PIPE", "bulk")
+        for _ in range(4):
+            assert torch.equal(part.hessian(), ref)
