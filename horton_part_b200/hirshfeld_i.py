@@ -80,9 +80,68 @@ class HirshfeldIWPart(DatabaseSplineMixin, AbstractISAWPart):
         self._seg = None
         return charges
 
+    # -- vectorised mixing of the database states (all atoms of an element at once) --------------------
+    def _element_tables(self):
+        """Per element: the charges of its database states (a contiguous range), their PPoly coefficient rows,
+        their radial densities, the quadrature weights 4 pi r^2 w of the element's radial grid, the atoms of
+        that element and where their coefficient blocks sit in the device table."""
+        tabs = getattr(self, "_hi_tables", None)
+        if tabs is not None:
+            return tabs
+        nseg4 = np.array([4 * (self.proatomdb.get_rgrid(int(z)).size - 1) for z in self.numbers], dtype=np.int64)
+        block = np.concatenate([[0], np.cumsum(nseg4)])
+        tabs = {}
+        for z in np.unique(self.numbers):
+            z = int(z)
+            charges = sorted(self.proatomdb.get_charges(z))
+            if charges != list(range(charges[0], charges[-1] + 1)):
+                tabs = None  # gaps in the database: keep the per-atom route
+                break
+            rgrid = self.proatomdb.get_rgrid(z)
+            atoms = np.flatnonzero(self.numbers == z)
+            tabs[z] = dict(
+                first=charges[0], nstate=len(charges), atoms=atoms,
+                coef=np.stack([self._state_coefficients(z, q).ravel() for q in charges]),
+                rho=np.stack([self.proatomdb.get_rho(z, q) for q in charges]),
+                w4=rgrid.weights * (4 * np.pi * rgrid.points**2),
+                where=block[atoms][:, None] + np.arange(nseg4[atoms[0]])[None, :],
+            )
+        self._hi_tables = tabs if tabs is not None else False
+        self._hi_flat = np.zeros(block[-1])
+        return self._hi_tables
+
+    def _mix(self, tab, charges, rows):
+        """(1 - x) * rows[floor(q)] + x * rows[floor(q) + 1] for the atoms of one element, with the
+        reference's rules (hirshfeld_i.py:125-132): one state only for one-electron pro-atoms and for integer
+        charges.  None when a state is missing (the per-atom route then raises the reference's error)."""
+        q = charges[tab["atoms"]]
+        ic = np.floor(q).astype(np.int64)
+        x = q - ic
+        pseudo_pop = self.pseudo_numbers[tab["atoms"]] - ic
+        single = (pseudo_pop == 1) | (x == 0.0)
+        lo = ic - tab["first"]
+        hi = np.where(single, lo, lo + 1)
+        if (pseudo_pop < 1).any() or lo.min() < 0 or hi.max() >= tab["nstate"]:
+            return None
+        out = 0.0 + (1 - x)[:, None] * rows[lo]
+        two = ~single
+        if two.any():
+            out[two] = out[two] + x[two, None] * rows[hi[two]]
+        return out
+
     def _refresh_table(self):
         """Mixed pro-atom coefficients for the current charges (hirshfeld_i.py:136-158)."""
+        import torch
+
         charges = self.cache.load("charges")
+        tabs = self._element_tables()
+        if tabs:
+            mixed = {z: self._mix(tab, charges, tab["coef"]) for z, tab in tabs.items()}
+            if all(m is not None for m in mixed.values()):
+                for z, tab in tabs.items():
+                    self._hi_flat[tab["where"]] = mixed[z]
+                self._table.coef.copy_(torch.from_numpy(self._hi_flat))
+                return
         per_atom = []
         for a in range(self.natom):
             icharge, x = self.get_interpolation_info(a, charges)
@@ -94,6 +153,26 @@ class HirshfeldIWPart(DatabaseSplineMixin, AbstractISAWPart):
                 raise ValueError("Requesting a pro-atom with a negative (pseudo) population")
             per_atom.append(coef)
         self._upload_coefficients(per_atom)
+
+    def compute_change(self, propars1, propars2):
+        """core/iterstock.py:32-45 for the charges as parameters: all atoms of an element at once (the database
+        states are mixed as rows of one table); per-atom route of the base class when a state is missing."""
+        tabs = self._element_tables()
+        if tabs:
+            c1, c2 = np.asarray(propars1, dtype=float), np.asarray(propars2, dtype=float)
+            terms = np.zeros(self.natom)
+            for tab in tabs.values():
+                r1, r2 = self._mix(tab, c1, tab["rho"]), self._mix(tab, c2, tab["rho"])
+                if r1 is None or r2 is None:
+                    break
+                delta = r1 - r2
+                terms[tab["atoms"]] = np.einsum("i,ai,ai->a", tab["w4"], delta, delta)
+            else:
+                msd = 0.0
+                for t in terms:  # atom order, as the reference accumulates
+                    msd += t
+                return np.sqrt(msd)
+        return AbstractISAWPart.compute_change(self, propars1, propars2)
 
     def _launch_promol_weights(self, want_entropy=True):
         self._refresh_table()
