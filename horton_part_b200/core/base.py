@@ -78,7 +78,12 @@ class Part(JustOnceClass):
 
     @property
     def nelec(self):
-        return self.grid.integrate(self._moldens)
+        """grid.integrate(moldens) (core/base.py:139): a pass over the whole grid on the host, so the value is
+        kept (the density array is an input that is never modified)."""
+        value = getattr(self, "_nelec_value", None)
+        if value is None:
+            value = self._nelec_value = self.grid.integrate(self._moldens)
+        return value
 
     @property
     def grid(self):

@@ -55,11 +55,23 @@ def evaluate_basis_functions(part, force_on_molgrid=False):
     """Unit-population basis functions -> cache ``bs_funcs_{a}`` (gisa.py:91-106): on each atom's
     radial grid, or -- only for host plug-in solvers with grid_type 2/3, the device solvers
     regenerate them in-kernel -- on the whole molecular grid."""
+    molgrid = part.on_molgrid or force_on_molgrid
+    shared = {}  # radial grids: atoms of one element on the same radial grid object share the table
     for a in range(part.natom):
-        r = part.radial_distances[a] if (part.on_molgrid or force_on_molgrid) else part.get_rgrid(a).points
         k = part._ranges[a + 1] - part._ranges[a]
+        if molgrid:
+            r = part.radial_distances[a]
+            table = None
+        else:
+            rgrid = part.get_rgrid(a)
+            r = rgrid.points
+            table = shared.get((int(part.numbers[a]), id(rgrid)))
+        if table is None:
+            table = np.array([part.bs_helper.compute_proshell_dens(part.numbers[a], i, 1.0, r) for i in range(k)])
+            if not molgrid:
+                shared[(int(part.numbers[a]), id(rgrid))] = table
         bs = part.cache.load(f"bs_funcs_{a}", alloc=(k, r.size))[0]
-        bs[:, :] = np.array([part.bs_helper.compute_proshell_dens(part.numbers[a], i, 1.0, r) for i in range(k)])
+        bs[:, :] = table
 
 
 def expbasis_atom_work(coordinates, numbers, pseudo_numbers, grid, bs_helper, device=None):

@@ -73,7 +73,7 @@ class GlobalLinearISAWPart(AbstractStockholderWPart):
 
     @property
     def mol_pop(self):
-        return self.grid.integrate(self._moldens)
+        return self.nelec  # grid.integrate(moldens), glisa.py:186-188
 
     @property
     def propars(self):
