@@ -298,6 +298,23 @@ def config4(dev, natom=300, peak=None, with_sc=False):
                         "Npts (8 natom + 36 M), which is never skipped; dense_equivalent_tflops = the "
                         "unscreened count over the same time (exceeds the peak because work is skipped); peak = "
                         "measured DFMA rate (B200's FP64 tensor rate is nominally the same)"}  # fmt: skip
+    # the same Hessian with the screening off: the tile product's own rate on the full M (M + 1) Npts
+    os.environ["HP_B200_HESSIAN_SCREEN"] = "0"
+    try:
+        part.hessian()
+        torch.cuda.synchronize()
+        e0.record()
+        part.hessian()
+        e1.record()
+        torch.cuda.synchronize()
+    finally:
+        os.environ.pop("HP_B200_HESSIAN_SCREEN", None)
+    ms_dense = e0.elapsed_time(e1)
+    out["roofline_hessian_unscreened"] = {
+        "ms": ms_dense, "flop_algorithmic": flop + flop_regen, "achieved": (flop + flop_regen) / (ms_dense * 1e-3) / 1e12,
+        "peak": peak, "unit": "TFLOP/s", "frac": (flop + flop_regen) / (ms_dense * 1e-3) / 1e12 / peak,
+        "note": "HP_B200_HESSIAN_SCREEN=0: every tile product runs (the lower-left quadrant of the diagonal tiles, never "
+                "read, is still skipped)"}  # fmt: skip
     e0.record()
     part._shell_integrals(1)
     e1.record()
