@@ -75,12 +75,19 @@ def warm_up(dev):
 
 
 def timed_partitioning(part):
+    import gc
+
     torch = _torch()
-    torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    part.do_partitioning()
-    torch.cuda.synchronize()
-    dt = time.perf_counter() - t0
+    gc.collect()  # garbage of the previous case (host arrays of 10^6-10^7 points) is not this job's time
+    gc.disable()
+    try:
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        part.do_partitioning()
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+    finally:
+        gc.enable()
     niter = int(part["niter"])
     return {"niter": niter, "seconds": dt, "ms_per_iteration": 1e3 * dt / niter,
             "gpu_ms_weights_per_iteration": 1e3 * float(np.mean(part.history_time_update_at_weights)),
