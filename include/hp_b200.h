@@ -382,7 +382,9 @@ HP_API int hp_molgrid_update_pass(int functor, int64_t npts, const double* px, c
  * filled.  shell_atom[m] = atom of shell m; g_m = shell_norm[m]*exp(-alpha_m r^n).  `scratch` needs
  * hp_hessian_scratch_bytes(M) bytes.  The function enqueues one basis-panel kernel (on an internal side
  * stream, double-buffered) and one tile-product kernel per chunk of up to 64 x 1,280 grid points; it does not
- * synchronise the stream. */
+ * synchronise the stream.  The side stream and its events exist once per device: like the reference's classes
+ * (single-threaded, not re-entrant) two Hessians must not be enqueued concurrently on one device from two
+ * host threads; consecutive calls on any streams are fine. */
 HP_API size_t hp_hessian_scratch_bytes(int32_t M);
 HP_API int hp_hessian(int functor, int64_t npts, const double* px, const double* py, const double* pz,
                       const double* atom_xyz, const int32_t* shell_atom, const double* shell_norm,
