@@ -139,6 +139,16 @@ class Cache:
             raise TypeError("At least two arguments are required: key1 and value.")
         self._store[_flatten_key(args[:-1])] = _Entry(args[-1], tags)
 
+    def dump_many(self, items, tags=None):
+        """``dump(key, value, tags=tags)`` for every (key, value) of ``items`` (keys already flat): the per-atom
+        results of a large system are thousands of entries, and the per-call bookkeeping of ``dump`` adds up."""
+        tagset = _tagset(tags)  # shared by the entries: tag sets are only compared and intersected
+        store = self._store
+        for key, value in items:
+            entry = _Entry.__new__(_Entry)
+            entry._value, entry.valid, entry.tags = value, True, tagset
+            store[key] = entry
+
     def load(self, *key, **kwargs):
         key = _flatten_key(key)
         alloc = kwargs.pop("alloc", None)

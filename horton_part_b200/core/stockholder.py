@@ -106,8 +106,8 @@ class AbstractStockholderWPart(WPart):
             self.cache.dump("promoldens", Deferred(assemble))
         at_w = download(slab.at_w)
         off = slab.atom_point_offsets_host
-        for a in range(slab.shard.atom_lo, slab.shard.atom_hi):
-            self.cache.dump(f"at_weights_{a}", at_w[off[a] - lo : off[a + 1] - lo])
+        self.cache.dump_many((f"at_weights_{a}", at_w[off[a] - lo : off[a + 1] - lo])
+                             for a in range(slab.shard.atom_lo, slab.shard.atom_hi))  # fmt: skip
 
     # -- host helpers of the reference API (spline objects for user code) --------------------------
     def fix_proatom_rho(self, index, rho, deriv):

@@ -186,7 +186,10 @@ class MBISWPart(AbstractISAWPart):
         slab = self.slab
         sph = slab.sph_avg.cpu().numpy()
         ro = slab.rad_offsets_host
-        for i, a in enumerate(range(slab.shard.atom_lo, slab.shard.atom_hi)):
-            self.cache.dump(f"radial_points_{a}", slab.rad_r_host[ro[i] : ro[i + 1]], tags="o")
-            self.cache.dump(f"spherical_average_{a}", sph[ro[i] : ro[i + 1]], tags="o")
-            self.cache.dump(f"radial_weights_{a}", slab.rad_w_host[ro[i] : ro[i + 1]], tags="o")
+        def entries():
+            for i, a in enumerate(range(slab.shard.atom_lo, slab.shard.atom_hi)):
+                yield f"radial_points_{a}", slab.rad_r_host[ro[i] : ro[i + 1]]
+                yield f"spherical_average_{a}", sph[ro[i] : ro[i + 1]]
+                yield f"radial_weights_{a}", slab.rad_w_host[ro[i] : ro[i + 1]]
+
+        self.cache.dump_many(entries(), tags="o")

@@ -191,3 +191,19 @@ def test_deferred_values_are_assembled_on_first_access():
         c.load("never")
     c.dump("again", Deferred(build))
     assert dict(c.iteritems())["again"].shape == (4,) and len(calls) == 2
+
+
+def test_dump_many_equals_repeated_dump():
+    from horton_part_b200.core.cache import Cache
+
+    a, b = Cache(), Cache()
+    items = [(f"k_{i}", np.full(3, float(i))) for i in range(5)]
+    for k, v in items:
+        a.dump(k, v, tags="o")
+    b.dump_many(iter(items), tags="o")
+    assert sorted(a.iterkeys(tags="o")) == sorted(b.iterkeys(tags="o")) == sorted(k for k, _ in items)
+    for k, v in items:
+        assert b.load(k) is v
+        assert b.load(k, alloc=3, tags="o")[1] is False
+    b.clear(tags="o")
+    assert "k_0" not in b
