@@ -252,25 +252,31 @@ class GridSlab:
             else:
                 atw = np.concatenate([atgrids[a].weights for a in range(a_lo, a_hi)]) if a_hi > a_lo else np.zeros(0)
                 self._atw = up_big(atw, local=True)
-            shell_off, rad_off = [0], [0]
+            shell_parts, rad_off = [np.zeros(1, dtype=np.int64)], [0]
             rad_r, rad_w, rad_w4, rad_r2w = [], [], [], []
+            per_rgrid = {}  # atoms usually share one radial grid object: its tables are formed once
             for a in range(a_lo, a_hi):
                 g = atgrids[a]
-                r, w = np.asarray(g.rgrid.points, float), np.asarray(g.rgrid.weights, float)
+                tabs = per_rgrid.get(id(g.rgrid))
+                if tabs is None:
+                    r, w = np.asarray(g.rgrid.points, float), np.asarray(g.rgrid.weights, float)
+                    # 4 pi r^2 w: mbis.py:182, gisa.py:298;  r^2 w: qc-grid integrate_angular_coordinates
+                    tabs = per_rgrid[id(g.rgrid)] = (r, w, 4 * np.pi * r**2 * w, r**2 * w)
+                r, w, w4, r2w = tabs
                 idx = np.asarray(g.indices, dtype=np.int64)
-                base = self.atom_point_offsets_host[a] - lo
-                shell_off.extend((base + idx[1:]).tolist())
+                shell_parts.append((self.atom_point_offsets_host[a] - lo) + idx[1:])
                 rad_off.append(rad_off[-1] + len(r))
                 rad_r.append(r)
                 rad_w.append(w)
-                rad_w4.append(4 * np.pi * r**2 * w)  # mbis.py:182, gisa.py:298
-                rad_r2w.append(r**2 * w)  # qc-grid integrate_angular_coordinates
+                rad_w4.append(w4)
+                rad_r2w.append(r2w)
             cat = lambda xs: np.concatenate(xs) if xs else np.zeros(0)  # noqa: E731
             self.rad_offsets_host = np.asarray(rad_off, dtype=np.int32)
             self.nrad_max = int(np.max(np.diff(self.rad_offsets_host), initial=1))
             self.rad_r_host, self.rad_w_host, self.rad_w4_host = cat(rad_r), cat(rad_w), cat(rad_w4)
+            shell_off = np.concatenate(shell_parts)
             self.nshell = len(shell_off) - 1
-            self.shell_point_offsets = up(np.asarray(shell_off, dtype=np.int64), np.int64)
+            self.shell_point_offsets = up(shell_off, np.int64)
             self.rad_offsets = up(self.rad_offsets_host, np.int32)
             self.rad_r = up(self.rad_r_host)
             self.rad_w4 = up(self.rad_w4_host)
