@@ -8,7 +8,8 @@ and 0.93 GB down per job, so how those bytes move decides the end-to-end rate:
                   pageable sources are pipelined through a pooled page-locked staging buffer by
                   ``hp_host_to_device`` (multi-threaded memcpy overlapped with the DMA).
 * ``download``    device -> a pooled page-locked buffer, returned as a NumPy array without a second
-                  copy.  The pool re-issues a buffer only when nothing refers to it any more.
+                  copy.  The pool re-issues a buffer only when nothing refers to it any more; idle
+                  buffers of other sizes are kept up to HP_B200_PINNED_POOL_BYTES (default 8 GiB).
 * ``pinned_empty``  for callers who want their input arrays page-locked from the start.
 """
 
@@ -123,7 +124,20 @@ def _take(nbytes):
         if nbytes <= buf.numel() <= 2 * nbytes + 4096:
             _stats["pinned_reuses"] += 1
             return entry
-    _pool[:] = [e for e in _pool if e[1] is not None and e[1]() is not None][-16:]  # drop idle misfits
+    # No idle buffer fits.  Idle buffers of other sizes stay (freeing and re-allocating page-locked memory costs
+    # ~0.1 s per GB: a process that alternates between job sizes would pay it on every call); the oldest idle
+    # ones go only when the pool would exceed its budget.
+    budget = int(os.environ.get("HP_B200_PINNED_POOL_BYTES", 8 << 30))
+    total = sum(e[0].numel() for e in _pool) + nbytes
+    if total > budget:
+        keep = []
+        for e in _pool:  # oldest first
+            idle = e[1] is None or e[1]() is None
+            if idle and total > budget:
+                total -= e[0].numel()
+            else:
+                keep.append(e)
+        _pool[:] = keep
     entry = [torch.empty(max(nbytes, 1), dtype=torch.uint8, pin_memory=True), None]
     _stats["pinned_allocs"] += 1
     _pool.append(entry)

@@ -147,3 +147,34 @@ def test_split_upload_is_completed_by_unaware_consumers(monkeypatch):
     assert np.array_equal(slab.pz.cpu().numpy(), grid.points[:, 2])
     assert np.array_equal(slab.molw.cpu().numpy(), grid.weights)
     assert np.array_equal(slab.atw.cpu().numpy(), np.concatenate([g.weights for g in grid.atgrids]))
+
+
+def test_pool_keeps_idle_buffers_of_other_sizes_within_its_budget(monkeypatch):
+    """Alternating result sizes re-use their own buffers (page-locked memory is expensive to free and to
+    allocate); idle buffers are dropped only when the pool would exceed HP_B200_PINNED_POOL_BYTES."""
+    import torch
+
+    from horton_part_b200.core import hostmem
+
+    dev = torch.device("cuda", 0)
+    small = torch.arange((16 << 20) // 8, dtype=torch.float64, device=dev)
+    large = torch.arange((40 << 20) // 8, dtype=torch.float64, device=dev)
+
+    def cycle():
+        for t in (small, large, small, large):
+            a = hostmem.download(t)
+            assert a[-1] == t.numel() - 1
+            del a
+            gc.collect()
+
+    cycle()  # both sizes are in the pool now
+    before = hostmem.pool_stats()
+    cycle()
+    after = hostmem.pool_stats()
+    assert after["pinned_allocs"] == before["pinned_allocs"] and after["pinned_reuses"] == before["pinned_reuses"] + 4
+    monkeypatch.setenv("HP_B200_PINNED_POOL_BYTES", "1")  # nothing idle may stay when a new buffer is needed
+    odd = torch.zeros((100 << 20) // 8 + 1, dtype=torch.float64, device=dev)  # fits neither of the two
+    a = hostmem.download(odd)
+    stats = hostmem.pool_stats()
+    assert stats["pool_buffers"] == 1 and stats["pinned_allocs"] == after["pinned_allocs"] + 1
+    del a
